@@ -1,0 +1,191 @@
+/* include/lgarb.h -- C ABI of the B200-native batched LGAR/CASAM engine (liblgarb.so).
+ *
+ * This is the drop-in boundary for the reference's Basic Model Interface, extended with a column
+ * batch: one engine advances `n_columns` independent soil columns per Update().  Every entry point
+ * names the reference interface it replaces (NOAA-OWP/LGAR-C, file:line).  The reference exports
+ * only three C symbols (bmi_model_create / bmi_model_destroy under -DNGEN,
+ * include/bmi_lgar.hxx:187-215, and giuh_convolution_integral); everything else is the C++ class
+ * `BmiLGAR : bmi::Bmi` (include/bmi_lgar.hxx:30-184), so each BMI virtual gets a C function here
+ * taking an opaque handle.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - return value: LGARB_SUCCESS (0 == BMI_SUCCESS) or LGARB_FAILURE (1 == BMI_FAILURE)
+ *     (bmi/bmi.hxx:14-15); lgarb_last_error() gives the message.  No exception crosses the ABI and a
+ *     numerical failure in one column never aborts the process: see lgarb_get_status().
+ *   - units and names of variables are exactly the reference's (src/bmi_lgar.cxx:1186-1210,
+ *     1319-1430): inputs in mm/h, per-step outputs in metres.
+ *   - batched layout: scalar variables are `double[n_columns]` (int32 for soil_num_wetting_fronts);
+ *     the two ragged per-front arrays are returned padded, `double[n_columns][LGARB_MAX_FRONTS]`
+ *     with NaN beyond soil_num_wetting_fronts[c]; soil_depth_layers is `double[n_columns][num_layers]`.
+ *   - "host" pointers are ordinary (optionally pinned) host memory; "_device" variants take CUDA
+ *     device pointers on the engine's device and never stage through the host.
+ *   - calls on one handle must be serialised by the caller (same as the reference, which is not
+ *     re-entrant per instance); distinct handles are independent.
+ *   - There is no CPU fallback: lgarb_initialize fails if no CUDA device is usable.
+ */
+#ifndef LGARB_H
+#define LGARB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGARB_SUCCESS 0
+#define LGARB_FAILURE 1
+#define LGARB_MAX_FRONTS 16 /* front capacity per column; overflow sets LGARB_STATUS_FRONT_OVERFLOW */
+#define LGARB_MAX_LAYERS 4
+#define LGARB_NUM_OUTPUT_SCALARS 12
+
+/* per-column status bits (lgarb_get_status).  The low 16 bits replace the reference's
+ * abort()/exit()/assert sites; a column with any of them set is frozen and reports NaN. */
+#define LGARB_STATUS_OK 0
+#define LGARB_STATUS_MBAL_TOL_EXCEEDED 1   /* src/bmi_lgar.cxx:785-788 abort() */
+#define LGARB_STATUS_NEGATIVE_RUNOFF 2     /* src/bmi_lgar.cxx:614-617 abort() */
+#define LGARB_STATUS_K_NEGATIVE 4          /* src/lgar.cxx:2805-2812 abort()   */
+#define LGARB_STATUS_THETA_ORDER 8         /* src/lgar.cxx:2850-2853 exit()    */
+#define LGARB_STATUS_FRONT_OVERFLOW 16     /* > LGARB_MAX_FRONTS wetting fronts */
+#define LGARB_STATUS_LIST_CORRUPT 32       /* the reference would dereference NULL */
+#define LGARB_STATUS_TOP_DEPTH 64          /* src/bmi_lgar.cxx:795 assert      */
+#define LGARB_STATUS_TO_BOTTOM_COUNT 128   /* src/bmi_lgar.cxx:830-834 abort() */
+#define LGARB_STATUS_OLD_MASS 256          /* src/lgar.cxx:1654 assert         */
+#define LGARB_STATUS_MERGE_DEPTH 512       /* src/lgar.cxx:1916 assert         */
+#define LGARB_STATUS_NAN 1024
+#define LGARB_STATUS_FAIL_MASK 0xFFFF
+#define LGARB_STATUS_WARN_NEGATIVE_FORCING 0x10000 /* src/bmi_lgar.cxx:325-337 warning */
+
+typedef struct lgarb_engine lgarb_engine;
+
+/* ---- life cycle ---------------------------------------------------------------------------- */
+
+/* replaces bmi_model_create(), include/bmi_lgar.hxx:197-200 */
+int lgarb_create(lgarb_engine** out);
+/* replaces bmi_model_destroy(), include/bmi_lgar.hxx:208-211 */
+int lgarb_destroy(lgarb_engine* e);
+
+/* replaces BmiLGAR::Initialize(config_file), src/bmi_lgar.cxx:72-113 -> lgar_initialize,
+ * src/lgar.cxx:81-194.  Reads the reference's own key=value[unit] config and soil-parameter file
+ * (parser quirks included).  All n_columns columns start identical.  device = CUDA ordinal. */
+int lgarb_initialize(lgarb_engine* e, const char* config_file, int64_t n_columns, int device);
+
+/* Batch extension of Initialize: per-column soil types and/or layer thicknesses.
+ *   layer_soil_type : int32[n_columns][num_layers] indices into the config's soil file (1-based,
+ *                     as `layer_soil_type=` in the config), or NULL to use the config's
+ *   layer_thickness_cm : double[n_columns][num_layers], or NULL to use the config's
+ * num_layers is the config's layer count.  Columns sharing (types, thicknesses) share one
+ * read-only parameter row on the device. */
+int lgarb_initialize_columns(lgarb_engine* e, const char* config_file, int64_t n_columns, int device,
+                             const int32_t* layer_soil_type, const double* layer_thickness_cm);
+
+/* replaces BmiLGAR::Finalize(), src/bmi_lgar.cxx:1080-1109.  Frees device memory.  The global mass
+ * balance the reference prints there (src/lgar.cxx:1162-1216) is available per column through
+ * lgarb_get_global_mass_balance() before this call. */
+int lgarb_finalize(lgarb_engine* e);
+
+const char* lgarb_last_error(const lgarb_engine* e);
+
+/* ---- time stepping -------------------------------------------------------------------------- */
+
+/* replaces BmiLGAR::Update(), src/bmi_lgar.cxx:133-895: one forcing interval for every column
+ * (all internal sub-steps included), using the forcing last set.  Synchronous at the ABI. */
+int lgarb_update(lgarb_engine* e);
+/* replaces BmiLGAR::UpdateUntil(t), src/bmi_lgar.cxx:898-903 (like the reference: t must be > 0 and
+ * is otherwise ignored -- exactly one Update; quirk Q10) */
+int lgarb_update_until(lgarb_engine* e, double t);
+
+/* Batch extension: advance n_steps forcing intervals from device-resident series laid out
+ * [step][series_stride] (mm/h), with no host round trip between steps.  sinks (nullable) is an
+ * array of LGARB_NUM_OUTPUT_SCALARS device pointers, each NULL or a [n_steps][sink_stride] buffer
+ * receiving that output variable for every step (order: lgarb_output_scalar_name());
+ * d_nfronts_sink (nullable) is an int32 [n_steps][sink_stride] buffer receiving
+ * soil_num_wetting_fronts after every step.
+ * Asynchronous on the engine's stream; lgarb_synchronize() or any get_value waits. */
+int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_precip_mm_per_h,
+                              const double* d_pet_mm_per_h, int64_t series_stride,
+                              double* const* d_sinks, int64_t sink_stride, int32_t* d_nfronts_sink);
+int lgarb_synchronize(lgarb_engine* e);
+
+/* ---- variable access (BMI getters/setters) -------------------------------------------------- */
+
+/* replaces BmiLGAR::SetValue(name, src), src/bmi_lgar.cxx:1455-1467.  src = host array with one
+ * item per column.  Settable: precipitation_rate, potential_evapotranspiration_rate (mm/h). */
+int lgarb_set_value(lgarb_engine* e, const char* name, const void* src);
+int lgarb_set_value_range(lgarb_engine* e, const char* name, int64_t col0, int64_t ncol, const void* src);
+int lgarb_set_value_device(lgarb_engine* e, const char* name, const void* d_src);
+/* replaces BmiLGAR::SetValueAtIndices, src/bmi_lgar.cxx:1470-1490 (inds = column indices) */
+int lgarb_set_value_at_indices(lgarb_engine* e, const char* name, const int* inds, int count, const void* src);
+
+/* replaces BmiLGAR::GetValue(name, dest), src/bmi_lgar.cxx:1307-1316.  dest = host buffer of
+ * lgarb_get_var_nbytes(name) bytes. */
+int lgarb_get_value(lgarb_engine* e, const char* name, void* dest);
+int lgarb_get_value_range(lgarb_engine* e, const char* name, int64_t col0, int64_t ncol, void* dest);
+int lgarb_get_value_device(lgarb_engine* e, const char* name, void* d_dest);
+/* replaces BmiLGAR::GetValuePtr, src/bmi_lgar.cxx:1319-1430: a DEVICE pointer to the engine's own
+ * array for a scalar variable (valid until the next update; per-front arrays have no flat pointer) */
+int lgarb_get_value_ptr(lgarb_engine* e, const char* name, void** d_ptr);
+/* replaces BmiLGAR::GetValueAtIndices, src/bmi_lgar.cxx:1432-1452 (inds = column indices) */
+int lgarb_get_value_at_indices(lgarb_engine* e, const char* name, void* dest, const int* inds, int count);
+
+/* ---- metadata (same answers as the reference, scaled by the batch where a size is involved) -- */
+int lgarb_get_component_name(const lgarb_engine* e, char* name, int cap);        /* :1493-1497 */
+int lgarb_get_input_item_count(const lgarb_engine* e, int* count);               /* :1500-1504 */
+int lgarb_get_output_item_count(const lgarb_engine* e, int* count);              /* :1507-1511 */
+const char* lgarb_get_input_var_name(const lgarb_engine* e, int i);              /* :1514-1523 */
+const char* lgarb_get_output_var_name(const lgarb_engine* e, int i);             /* :1526-1535 */
+int lgarb_get_var_grid(const lgarb_engine* e, const char* name, int* grid);      /* :1112-1154 */
+int lgarb_get_var_type(const lgarb_engine* e, const char* name, char* type, int cap);     /* :1157-1168 */
+int lgarb_get_var_itemsize(const lgarb_engine* e, const char* name, int* size);  /* :1171-1182 */
+int lgarb_get_var_units(const lgarb_engine* e, const char* name, char* units, int cap);   /* :1185-1210 */
+int lgarb_get_var_nbytes(const lgarb_engine* e, const char* name, int64_t* nbytes);       /* :1213-1222 */
+int lgarb_get_var_location(const lgarb_engine* e, const char* name, char* loc, int cap);  /* :1225-1249 */
+int lgarb_get_current_time(const lgarb_engine* e, double* t);                    /* :1550-1553 */
+int lgarb_get_start_time(const lgarb_engine* e, double* t);                      /* :1538-1541 */
+int lgarb_get_end_time(const lgarb_engine* e, double* t);                        /* :1544-1547 */
+int lgarb_get_time_step(const lgarb_engine* e, double* dt);                      /* :1562-1565 */
+int lgarb_get_time_units(const lgarb_engine* e, char* units, int cap);           /* :1556-1559 */
+int lgarb_get_grid_rank(const lgarb_engine* e, int grid, int* rank);             /* :1280-1287 */
+int lgarb_get_grid_size(const lgarb_engine* e, int grid, int64_t* size);         /* :1290-1303 */
+int lgarb_get_grid_type(const lgarb_engine* e, int grid, char* type, int cap);   /* :1567-1574 */
+
+/* ---- batch-only services ------------------------------------------------------------------- */
+int64_t lgarb_get_num_columns(const lgarb_engine* e);
+int lgarb_get_num_layers(const lgarb_engine* e);
+int lgarb_get_num_giuh_ordinates(const lgarb_engine* e);
+const char* lgarb_output_scalar_name(int k); /* k in [0, LGARB_NUM_OUTPUT_SCALARS) */
+
+/* per-column status word (see LGARB_STATUS_*) */
+int lgarb_get_status(lgarb_engine* e, int64_t col0, int64_t ncol, int32_t* dest);
+
+/* Raw wetting-front state, what the reference keeps in model_state.head (include/all.hxx:45-56,
+ * src/bmi_lgar.cxx:905): arrays [ncol][LGARB_MAX_FRONTS] in cm / cm h^-1, layer 1-based; any
+ * destination may be NULL.  nfronts = int32[ncol]. */
+int lgarb_get_fronts(lgarb_engine* e, int64_t col0, int64_t ncol, double* depth_cm, double* theta,
+                     double* psi_cm, double* K_cm_per_h, double* dzdt_cm_per_h, int32_t* layer_num,
+                     int32_t* to_bottom, int32_t* nfronts);
+
+/* the terms of lgar_global_mass_balance(), src/lgar.cxx:1162-1216, per column, cm:
+ * out[ncol][16] = volstart, volprecip, volin, volend, volon, volrunoff, volrunoff_giuh, volrech,
+ *                 volAET, volPET, volrunoff_CR, volCRend, volQ, volchange_calib(0), volQ_CR,
+ *                 global_error */
+int lgarb_get_global_mass_balance(lgarb_engine* e, int64_t col0, int64_t ncol, double* out);
+
+/* The parsed soil table row the engine uses for `soil` (1-based), for checking the parser quirk
+ *  against the reference: out[10] = theta_r, theta_e, alpha, n, m, lambda, psib,
+ * h_min, Ksat, theta_wp (include/all.hxx:66-79). */
+int lgarb_get_soil_row(const lgarb_engine* e, int soil, double* out10);
+
+/* Test hook: route every column through the active kernel (no cached-flux fast path), to check
+ * that the two kernels implement the same Update(). */
+int lgarb_set_force_all_active(lgarb_engine* e, int on);
+/* number of kernels launched by this engine so far, and columns routed to the active kernel in
+ * the last step */
+int64_t lgarb_get_launch_count(const lgarb_engine* e);
+int64_t lgarb_get_last_active_count(lgarb_engine* e);
+/* the CUDA stream the engine launches on (cudaStream_t), for callers that time with events */
+void* lgarb_get_stream(lgarb_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGARB_H */

@@ -1,0 +1,677 @@
+// lgar_c_b200/csrc/lgar_engine.cu -- host side of liblgarb.so: the reference's BMI verbs over a
+// column batch (C ABI declared in include/lgarb.h).
+//
+//   * config reader      mirrors InitFromConfigFile        (reference src/lgar.cxx:231-1016)
+//   * soil-table reader  mirrors lgar_read_vG_param_file   (reference src/lgar.cxx:2674-2758, quirk Q2)
+//   * initial fronts     mirrors InitializeWettingFronts   (reference src/lgar.cxx:1024-1064)
+//   * Update/GetValue/SetValue/metadata mirror BmiLGAR      (reference src/bmi_lgar.cxx)
+//
+// The engine owns all device memory (fixed-capacity SoA, lgar_types.h) and a CUDA stream.  There is
+// no CPU path: without a usable CUDA device initialisation fails.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/lgarb.h"
+#include "lgar_kernels.h"
+#include "lgar_types.h"
+
+#include "lgar_config.hpp"
+
+using namespace lgarhost;
+
+namespace {
+
+#define CUDA_TRY(expr)                                                                                     \
+  do {                                                                                                     \
+    cudaError_t _err = (expr);                                                                             \
+    if (_err != cudaSuccess) throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_err)); \
+  } while (0)
+
+const char* kOutNames[LGAR_NOUT] = {
+    "precipitation", "potential_evapotranspiration", "actual_evapotranspiration", "surface_runoff", "giuh_runoff",
+    "soil_storage", "total_discharge", "infiltration", "percolation", "conceptual_reservoir_to_stream_discharge",
+    "mass_balance", "conceptual_reservoir_storage"};
+// bmi_lgar.hxx:34-54
+const char* kInputNames[3] = {"precipitation_rate", "potential_evapotranspiration_rate", "soil_temperature_profile"};
+const char* kOutputNames[15] = {"soil_moisture_wetting_fronts", "soil_depth_layers", "soil_depth_wetting_fronts", "soil_num_wetting_fronts",
+                                "precipitation", "potential_evapotranspiration", "actual_evapotranspiration", "surface_runoff",
+                                "giuh_runoff", "soil_storage", "total_discharge", "infiltration", "percolation",
+                                "conceptual_reservoir_to_stream_discharge", "mass_balance"};
+
+int out_index(const std::string& name) {
+  for (int k = 0; k < LGAR_NOUT; k++)
+    if (name == kOutNames[k]) return k;
+  return -1;
+}
+
+}  // namespace
+
+struct lgarb_engine {
+  bool initialized = false;
+  int device = 0;
+  int64_t ncol = 0, stride = 0;
+  int num_layers = 0;
+  ParsedConfig pc;
+  LgarConfig cfg;
+  std::vector<SoilRow> soils;  // 1-based
+  std::vector<LgarColumnClass> classes;
+  LgarDeviceState d;
+  std::vector<void*> allocs;
+  double *d_precip = nullptr, *d_pet = nullptr, *d_stage = nullptr;
+  LgarColumnClass* d_classes = nullptr;
+  double* volstart = nullptr;  // [stride] initial storage (cm)
+  int32_t* d_stage_i = nullptr;
+  void* h_pinned = nullptr;
+  size_t h_pinned_bytes = 0;
+  cudaStream_t stream = nullptr;
+  int active_blocks = 0;
+  int force_all_active = 0;
+  int64_t steps = 0;
+  int64_t launches = 0;
+  double time_s = 0.0;
+  std::string last_error;
+
+  template <typename T>
+  T* dalloc(size_t n, bool zero = true) {
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, n * sizeof(T)));
+    allocs.push_back(p);
+    if (zero) CUDA_TRY(cudaMemsetAsync(p, 0, n * sizeof(T), stream));
+    return (T*)p;
+  }
+  void* pinned(size_t bytes) {
+    if (bytes > h_pinned_bytes) {
+      if (h_pinned) cudaFreeHost(h_pinned);
+      h_pinned = nullptr;
+      CUDA_TRY(cudaMallocHost(&h_pinned, bytes));
+      h_pinned_bytes = bytes;
+    }
+    return h_pinned;
+  }
+  void release() {
+    if (stream) cudaStreamSynchronize(stream);
+    for (void* p : allocs) cudaFree(p);
+    allocs.clear();
+    if (h_pinned) cudaFreeHost(h_pinned);
+    h_pinned = nullptr;
+    h_pinned_bytes = 0;
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+    initialized = false;
+  }
+};
+
+namespace {
+
+void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int device, const int32_t* types_in, const double* thick_in) {
+  if (e->initialized) e->release();
+  if (ncol <= 0) throw std::runtime_error("n_columns must be positive");
+  if (ncol > 0x7FFFFFF0LL) throw std::runtime_error("n_columns must fit in int32");
+  int ndev = 0;
+  cudaError_t derr = cudaGetDeviceCount(&ndev);
+  if (derr != cudaSuccess || ndev == 0)
+    throw std::runtime_error(std::string("no usable CUDA device (this engine has no CPU path): ") + cudaGetErrorString(derr));
+  if (device < 0 || device >= ndev) throw std::runtime_error("invalid CUDA device ordinal");
+  CUDA_TRY(cudaSetDevice(device));
+  e->device = device;
+  e->pc = parse_config(config_file);
+  const ParsedConfig& pc = e->pc;
+  const int L = (int)pc.layer_thickness.size();
+  if (L < 1 || L > LGAR_MAXL) throw std::runtime_error("number of soil layers must be 1.." + std::to_string(LGAR_MAXL));
+  if ((int)pc.layer_soil_type.size() != L) throw std::runtime_error("layer_soil_type and layer_thickness differ in length");
+  e->num_layers = L;
+  int nread = read_soil_file(pc.soil_params_file, pc.num_soil_types, pc.wilting_point_psi, pc.log_mode, e->soils, config_file);
+
+  e->cfg = make_engine_config(pc);
+  LgarConfig& g = e->cfg;
+
+  // column classes: one parameter row per distinct (soil types, thicknesses)
+  std::vector<int32_t> class_of((size_t)ncol);
+  e->classes.clear();
+  std::map<std::vector<double>, int> seen;
+  std::vector<int> types(L);
+  std::vector<double> thick(L);
+  for (int64_t c = 0; c < ncol; c++) {
+    std::vector<double> key(2 * L);
+    for (int k = 0; k < L; k++) {
+      types[k] = types_in ? types_in[c * L + k] : pc.layer_soil_type[k];
+      thick[k] = thick_in ? thick_in[c * L + k] : pc.layer_thickness[k];
+      key[k] = types[k];
+      key[L + k] = thick[k];
+    }
+    auto it = seen.find(key);
+    if (it == seen.end()) {
+      for (int k = 0; k < L; k++) {
+        if (types[k] > nread && types[k] <= pc.num_soil_types)  // lgar.cxx:814-820
+          throw std::runtime_error("Soil type is less than max_valid_soil_types but is greater than the number of lines in the soil data file.");
+        if (!(thick[k] > 0)) throw std::runtime_error("layer thickness must be positive");
+      }
+      int id = (int)e->classes.size();
+      e->classes.push_back(make_class(pc, e->soils, L, types.data(), thick.data()));
+      it = seen.emplace(key, id).first;
+    }
+    class_of[c] = it->second;
+    if (!types_in && !thick_in) {  // homogeneous batch: every column is class 0
+      for (int64_t c2 = 1; c2 < ncol; c2++) class_of[c2] = 0;
+      break;
+    }
+  }
+
+  // device memory
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  e->ncol = ncol;
+  e->stride = (ncol + 31) / 32 * 32;
+  const size_t st = (size_t)e->stride;
+  LgarDeviceState& d = e->d;
+  memset(&d, 0, sizeof(d));
+  d.ncol = ncol;
+  d.stride = e->stride;
+  d.depth = e->dalloc<double>(st * LGAR_W);
+  d.theta = e->dalloc<double>(st * LGAR_W);
+  d.psi = e->dalloc<double>(st * LGAR_W);
+  d.K = e->dalloc<double>(st * LGAR_W);
+  d.dzdt = e->dalloc<double>(st * LGAR_W);
+  d.fflags = e->dalloc<unsigned long long>(st);
+  d.nfront = e->dalloc<int32_t>(st);
+  d.scal = e->dalloc<double>(st * LGAR_NSCAL);
+  d.bits = e->dalloc<int32_t>(st);
+  d.status = e->dalloc<int32_t>(st);
+  d.class_id = e->dalloc<int32_t>(st);
+  d.giuhq = e->dalloc<double>(st * (size_t)std::max(1, g.num_giuh - 1));
+  d.cum = e->dalloc<double>(st * LGAR_NCUM);
+  d.out = e->dalloc<double>(st * LGAR_NOUT);
+  d.work = e->dalloc<int32_t>(st);
+  d.work_count = e->dalloc<int32_t>(2);
+  e->d_precip = e->dalloc<double>(st);
+  e->d_pet = e->dalloc<double>(st);
+  e->volstart = e->dalloc<double>(st);
+  e->d_stage = e->dalloc<double>(st * LGAR_W);
+  e->d_stage_i = e->dalloc<int32_t>(st);
+  e->d_classes = e->dalloc<LgarColumnClass>(e->classes.size(), false);
+  d.classes = e->d_classes;
+  d.precip = e->d_precip;
+  d.pet = e->d_pet;
+  CUDA_TRY(cudaMemcpyAsync(e->d_classes, e->classes.data(), e->classes.size() * sizeof(LgarColumnClass), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(d.class_id, class_of.data(), (size_t)ncol * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+
+  // initial state: InitializeWettingFronts (lgar.cxx:1024-1064) + lgar_initialize (lgar.cxx:172-193).
+  // Forcing defaults to -1 so that a missing SetValue is visible (lgar.cxx:172-175).
+  {
+    std::vector<double> h((size_t)ncol);
+    std::vector<double> buf((size_t)ncol * 5 * L);
+    auto plane = [&](int which, int k) { return buf.data() + ((size_t)which * L + k) * (size_t)ncol; };
+    std::vector<unsigned long long> fl((size_t)ncol);
+    std::vector<int32_t> nf((size_t)ncol);
+    std::vector<double> stor((size_t)ncol), tsh((size_t)ncol, pc.timestep_h);
+    for (int64_t c = 0; c < ncol; c++) {
+      const LgarColumnClass& cc = e->classes[class_of[c]];
+      unsigned long long f = 0;
+      if (!cc.invalid_soil_type) {
+        for (int k = 0; k < L; k++) {
+          plane(0, k)[c] = cc.cum[k + 1];
+          plane(1, k)[c] = cc.initial_theta[k + 1];
+          plane(2, k)[c] = pc.initial_psi;
+          plane(3, k)[c] = cc.initial_K[k + 1];
+          plane(4, k)[c] = 0.0;
+          f |= (unsigned long long)(((k + 1) & 7) | 8) << (4 * k);
+        }
+        nf[c] = L;
+        stor[c] = class_initial_storage(cc);
+      } else {
+        nf[c] = 0;
+        stor[c] = 0.0;
+      }
+      fl[c] = f;
+    }
+    double* dst[5] = {d.depth, d.theta, d.psi, d.K, d.dzdt};
+    for (int w = 0; w < 5; w++)
+      for (int k = 0; k < L; k++)
+        CUDA_TRY(cudaMemcpyAsync(dst[w] + (size_t)k * st, plane(w, k), (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.fflags, fl.data(), (size_t)ncol * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.nfront, nf.data(), (size_t)ncol * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.scal + (size_t)LGAR_S_STORAGE * st, stor.data(), (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->volstart, stor.data(), (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.scal + (size_t)LGAR_S_TIMESTEP_H * st, tsh.data(), (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    std::vector<int32_t> bits((size_t)ncol, 1 << 8);  // cache_count = 1 (all.hxx:165)
+    CUDA_TRY(cudaMemcpyAsync(d.bits, bits.data(), (size_t)ncol * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    std::vector<double> minus1((size_t)ncol, -1.0);
+    CUDA_TRY(cudaMemcpyAsync(e->d_precip, minus1.data(), (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->d_pet, minus1.data(), (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+  }
+
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  int per_sm = lgar_active_kernel_max_blocks_per_sm();
+  if (per_sm < 1) per_sm = 1;
+  e->active_blocks = prop.multiProcessorCount * per_sm;  // persistent: a whole number of waves of the SM count
+  e->steps = 0;
+  e->launches = 0;
+  e->time_s = 0.0;
+  e->initialized = true;
+}
+
+void launch_step(lgarb_engine* e, const double* d_precip, const double* d_pet, const LgarSinks& sinks) {
+  LgarDeviceState d = e->d;
+  d.precip = d_precip;
+  d.pet = d_pet;
+  CUDA_TRY(lgar_launch_step(e->cfg, d, sinks, e->active_blocks, e->force_all_active, e->stream));
+  e->launches += 2;
+  e->steps++;
+  e->time_s += e->cfg.forcing_resolution_h * 3600.0;  // bmi_lgar.cxx:359 summed over the sub-cycles
+}
+
+void require_init(const lgarb_engine* e) {
+  if (!e || !e->initialized) throw std::runtime_error("engine is not initialized");
+}
+
+void check_range(const lgarb_engine* e, int64_t col0, int64_t ncol) {
+  if (col0 < 0 || ncol < 0 || col0 + ncol > e->ncol) throw std::runtime_error("column range out of bounds");
+}
+
+// copy a strided device plane [rows][stride] -> host [ncol][rows]?  No: scalar variables are
+// [ncol] planes, returned as they are.
+void d2h(lgarb_engine* e, void* dst, const void* src, size_t bytes) {
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+}
+void h2d(lgarb_engine* e, void* dst, const void* src, size_t bytes) {
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+}
+
+int var_grid(const std::string& name) {  // bmi_lgar.cxx:1112-1154
+  if (name == "soil_storage_model" || name == "soil_num_wetting_fronts") return 0;
+  static const char* g1[] = {"precipitation_rate", "precipitation", "potential_evapotranspiration_rate", "potential_evapotranspiration",
+                             "actual_evapotranspiration", "surface_runoff", "giuh_runoff", "a", "b", "frac_to_CR", "spf_factor", "a_slow",
+                             "b_slow", "frac_slow", "soil_storage", "field_capacity", "ponded_depth_max", "total_discharge", "infiltration",
+                             "percolation", "conceptual_reservoir_to_stream_discharge", "mass_balance", "smcmax_1", "smcmin_1",
+                             "van_genuchten_m_1", "van_genuchten_alpha_1", "van_genuchten_n_1", "hydraulic_conductivity_1", "smcmax_2",
+                             "smcmin_2", "van_genuchten_m_2", "van_genuchten_alpha_2", "van_genuchten_n_2", "hydraulic_conductivity_2"};
+  for (const char* s : g1)
+    if (name == s) return 1;
+  if (name == "soil_depth_layers") return 2;
+  if (name == "soil_moisture_wetting_fronts" || name == "soil_depth_wetting_fronts") return 3;
+  if (name == "soil_temperature_profile") return 4;
+  return -1;
+}
+
+// where a gettable variable lives: returns the device pointer of a [ncol] plane, or null for the
+// gathered (per-front / per-layer) ones
+const void* scalar_plane(lgarb_engine* e, const std::string& name, size_t* itemsize) {
+  *itemsize = sizeof(double);
+  if (name == "precipitation_rate") return e->d_precip;
+  if (name == "potential_evapotranspiration_rate") return e->d_pet;
+  int k = out_index(name);
+  if (k >= 0) return e->d.out + (size_t)k * e->stride;
+  if (name == "soil_num_wetting_fronts") {
+    *itemsize = sizeof(int32_t);
+    return e->d.nfront;
+  }
+  return nullptr;
+}
+
+void get_value_range(lgarb_engine* e, const std::string& name, int64_t col0, int64_t ncol, void* dest, bool dest_is_device) {
+  require_init(e);
+  check_range(e, col0, ncol);
+  size_t isz;
+  const void* plane = scalar_plane(e, name, &isz);
+  cudaMemcpyKind kind = dest_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (plane) {
+    CUDA_TRY(cudaMemcpyAsync(dest, (const char*)plane + (size_t)col0 * isz, (size_t)ncol * isz, kind, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return;
+  }
+  if (name == "soil_moisture_wetting_fronts" || name == "soil_depth_wetting_fronts") {
+    bool depth = name == "soil_depth_wetting_fronts";
+    CUDA_TRY(lgar_launch_gather_fronts(e->d, depth ? 0 : 1, depth ? 0.01 : 1.0, e->d_stage, col0, ncol, e->stream));  // bmi_lgar.cxx:836-837
+    e->launches++;
+    CUDA_TRY(cudaMemcpyAsync(dest, e->d_stage, (size_t)ncol * LGAR_W * sizeof(double), kind, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return;
+  }
+  if (name == "soil_depth_layers") {
+    CUDA_TRY(lgar_launch_gather_layers(e->d, e->d_stage, col0, ncol, e->num_layers, e->stream));
+    e->launches++;
+    CUDA_TRY(cudaMemcpyAsync(dest, e->d_stage, (size_t)ncol * e->num_layers * sizeof(double), kind, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return;
+  }
+  throw std::runtime_error("variable " + name + " does not exist");  // bmi_lgar.cxx:1421-1425
+}
+
+void set_value_range(lgarb_engine* e, const std::string& name, int64_t col0, int64_t ncol, const void* src, bool src_is_device) {
+  require_init(e);
+  check_range(e, col0, ncol);
+  double* plane = nullptr;
+  if (name == "precipitation_rate") plane = e->d_precip;
+  else if (name == "potential_evapotranspiration_rate") plane = e->d_pet;
+  else if (name == "soil_temperature_profile") return;  // accepted and ignored: SFT coupling is out of scope (frozen_factor == 1)
+  else if (var_grid(name) >= 0) throw std::runtime_error("variable " + name + " is not settable in this engine");
+  else throw std::runtime_error("variable " + name + " does not exist");
+  CUDA_TRY(cudaMemcpyAsync(plane + col0, src, (size_t)ncol * sizeof(double), src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                           e->stream));
+  if (!src_is_device) CUDA_TRY(cudaStreamSynchronize(e->stream));  // the caller may reuse src immediately
+}
+
+void copy_str(char* dst, int cap, const std::string& s) {
+  if (!dst || cap <= 0) throw std::runtime_error("bad string buffer");
+  snprintf(dst, (size_t)cap, "%s", s.c_str());
+}
+
+}  // namespace
+
+#define LGARB_GUARD(e, ...)                                   \
+  try {                                                       \
+    __VA_ARGS__;                                              \
+    return LGARB_SUCCESS;                                     \
+  } catch (const std::exception& ex) {                        \
+    if (e) const_cast<lgarb_engine*>(e)->last_error = ex.what(); \
+    return LGARB_FAILURE;                                     \
+  } catch (...) {                                             \
+    if (e) const_cast<lgarb_engine*>(e)->last_error = "unknown error"; \
+    return LGARB_FAILURE;                                     \
+  }
+
+extern "C" {
+
+int lgarb_create(lgarb_engine** out) {
+  if (!out) return LGARB_FAILURE;
+  *out = new (std::nothrow) lgarb_engine();
+  return *out ? LGARB_SUCCESS : LGARB_FAILURE;
+}
+
+int lgarb_destroy(lgarb_engine* e) {
+  if (!e) return LGARB_FAILURE;
+  if (e->initialized) e->release();
+  delete e;
+  return LGARB_SUCCESS;
+}
+
+int lgarb_initialize(lgarb_engine* e, const char* config_file, int64_t n_columns, int device) {
+  if (!e || !config_file) return LGARB_FAILURE;
+  LGARB_GUARD(e, do_initialize(e, config_file, n_columns, device, nullptr, nullptr));
+}
+
+int lgarb_initialize_columns(lgarb_engine* e, const char* config_file, int64_t n_columns, int device, const int32_t* layer_soil_type,
+                             const double* layer_thickness_cm) {
+  if (!e || !config_file) return LGARB_FAILURE;
+  LGARB_GUARD(e, do_initialize(e, config_file, n_columns, device, layer_soil_type, layer_thickness_cm));
+}
+
+int lgarb_finalize(lgarb_engine* e) {
+  if (!e) return LGARB_FAILURE;
+  LGARB_GUARD(e, { require_init(e); e->release(); });
+}
+
+const char* lgarb_last_error(const lgarb_engine* e) { return e ? e->last_error.c_str() : "null engine"; }
+
+int lgarb_update(lgarb_engine* e) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    LgarSinks sinks;
+    memset(&sinks, 0, sizeof(sinks));
+    launch_step(e, e->d_precip, e->d_pet, sinks);
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+  });
+}
+
+int lgarb_update_until(lgarb_engine* e, double t) {
+  if (e && !(t > 0.0)) {  // bmi_lgar.cxx:901 assert (t > 0.0)
+    e->last_error = "UpdateUntil: t must be > 0";
+    return LGARB_FAILURE;
+  }
+  return lgarb_update(e);
+}
+
+int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_precip, const double* d_pet, int64_t series_stride,
+                              double* const* d_sinks, int64_t sink_stride, int32_t* d_nfronts_sink) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (n_steps < 0 || !d_precip || !d_pet || series_stride < e->ncol) throw std::runtime_error("bad forcing series");
+    if ((d_sinks || d_nfronts_sink) && sink_stride < e->ncol) throw std::runtime_error("bad sink stride");
+    for (int64_t t = 0; t < n_steps; t++) {
+      LgarSinks sinks;
+      for (int k = 0; k < LGAR_NOUT; k++) sinks.p[k] = (d_sinks && d_sinks[k]) ? d_sinks[k] + t * sink_stride : nullptr;
+      launch_step(e, d_precip + t * series_stride, d_pet + t * series_stride, sinks);
+      if (d_nfronts_sink)
+        CUDA_TRY(cudaMemcpyAsync(d_nfronts_sink + t * sink_stride, e->d.nfront, (size_t)e->ncol * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                                 e->stream));
+    }
+  });
+}
+
+int lgarb_synchronize(lgarb_engine* e) {
+  LGARB_GUARD(e, { require_init(e); CUDA_TRY(cudaStreamSynchronize(e->stream)); });
+}
+
+int lgarb_set_value(lgarb_engine* e, const char* name, const void* src) {
+  LGARB_GUARD(e, { require_init(e); set_value_range(e, name, 0, e->ncol, src, false); });
+}
+int lgarb_set_value_range(lgarb_engine* e, const char* name, int64_t col0, int64_t ncol, const void* src) {
+  LGARB_GUARD(e, set_value_range(e, name, col0, ncol, src, false));
+}
+int lgarb_set_value_device(lgarb_engine* e, const char* name, const void* d_src) {
+  LGARB_GUARD(e, { require_init(e); set_value_range(e, name, 0, e->ncol, d_src, true); });
+}
+int lgarb_set_value_at_indices(lgarb_engine* e, const char* name, const int* inds, int count, const void* src) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    for (int i = 0; i < count; i++) set_value_range(e, name, inds[i], 1, (const double*)src + i, false);
+  });
+}
+
+int lgarb_get_value(lgarb_engine* e, const char* name, void* dest) {
+  LGARB_GUARD(e, { require_init(e); get_value_range(e, name, 0, e->ncol, dest, false); });
+}
+int lgarb_get_value_range(lgarb_engine* e, const char* name, int64_t col0, int64_t ncol, void* dest) {
+  LGARB_GUARD(e, get_value_range(e, name, col0, ncol, dest, false));
+}
+int lgarb_get_value_device(lgarb_engine* e, const char* name, void* d_dest) {
+  LGARB_GUARD(e, { require_init(e); get_value_range(e, name, 0, e->ncol, d_dest, true); });
+}
+int lgarb_get_value_ptr(lgarb_engine* e, const char* name, void** d_ptr) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    size_t isz;
+    const void* p = scalar_plane(e, name, &isz);
+    if (!p) throw std::runtime_error(std::string("variable ") + name + " has no flat device array");
+    *d_ptr = const_cast<void*>(p);
+  });
+}
+int lgarb_get_value_at_indices(lgarb_engine* e, const char* name, void* dest, const int* inds, int count) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    size_t isz;
+    const void* plane = scalar_plane(e, name, &isz);
+    if (!plane) throw std::runtime_error(std::string("variable ") + name + " is not addressable by column index");
+    for (int i = 0; i < count; i++) {
+      check_range(e, inds[i], 1);
+      CUDA_TRY(cudaMemcpyAsync((char*)dest + (size_t)i * isz, (const char*)plane + (size_t)inds[i] * isz, isz, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+  });
+}
+
+int lgarb_get_component_name(const lgarb_engine* e, char* name, int cap) {
+  LGARB_GUARD(e, copy_str(name, cap, "LASAM (Lumped Arid/Semi-arid Model)"));
+}
+int lgarb_get_input_item_count(const lgarb_engine* e, int* count) { LGARB_GUARD(e, *count = 3); }
+int lgarb_get_output_item_count(const lgarb_engine* e, int* count) { LGARB_GUARD(e, *count = 15); }
+const char* lgarb_get_input_var_name(const lgarb_engine*, int i) { return (i >= 0 && i < 3) ? kInputNames[i] : nullptr; }
+const char* lgarb_get_output_var_name(const lgarb_engine*, int i) { return (i >= 0 && i < 15) ? kOutputNames[i] : nullptr; }
+int lgarb_get_var_grid(const lgarb_engine* e, const char* name, int* grid) { LGARB_GUARD(e, *grid = var_grid(name)); }
+int lgarb_get_var_type(const lgarb_engine* e, const char* name, char* type, int cap) {
+  LGARB_GUARD(e, {
+    int g = var_grid(name);
+    copy_str(type, cap, g == 0 ? "int" : (g >= 1 && g <= 4) ? "double" : "none");
+  });
+}
+int lgarb_get_var_itemsize(const lgarb_engine* e, const char* name, int* size) {
+  LGARB_GUARD(e, {
+    int g = var_grid(name);
+    *size = g == 0 ? (int)sizeof(int) : (g >= 1 && g <= 4) ? (int)sizeof(double) : 0;
+  });
+}
+int lgarb_get_var_units(const lgarb_engine* e, const char* name, char* units, int cap) {
+  LGARB_GUARD(e, {
+    std::string n = name, u = "none";
+    if (n == "precipitation_rate" || n == "potential_evapotranspiration_rate") u = "mm h^-1";
+    else if (n == "soil_moisture_wetting_fronts") u = "none";
+    else if (n == "soil_temperature_profile") u = "K";
+    else if (out_index(n) >= 0 && n != "conceptual_reservoir_storage") u = "m";
+    else if (n == "soil_depth_layers" || n == "soil_depth_wetting_fronts") u = "m";
+    copy_str(units, cap, u);
+  });
+}
+int lgarb_get_grid_size(const lgarb_engine* e, int grid, int64_t* size) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (grid == 0 || grid == 1) *size = e->ncol;
+    else if (grid == 2) *size = e->ncol * e->num_layers;
+    else if (grid == 3) *size = e->ncol * LGAR_W;  // padded; the reference's is the live front count
+    else if (grid == 4) *size = 1;                  // num_cells_temp without SFT (lgar.cxx:956-958)
+    else *size = -1;
+  });
+}
+int lgarb_get_var_nbytes(const lgarb_engine* e, const char* name, int64_t* nbytes) {
+  LGARB_GUARD(e, {
+    int isz = 0;
+    int64_t gs = 0;
+    int g = var_grid(name);
+    if (lgarb_get_var_itemsize(e, name, &isz) != LGARB_SUCCESS || lgarb_get_grid_size(e, g, &gs) != LGARB_SUCCESS)
+      throw std::runtime_error(e->last_error);
+    *nbytes = (int64_t)isz * gs;
+  });
+}
+int lgarb_get_var_location(const lgarb_engine* e, const char* name, char* loc, int cap) {
+  LGARB_GUARD(e, {
+    std::string n = name;
+    bool node = (var_grid(n) >= 0) && n != "field_capacity" && n != "ponded_depth_max" && n.rfind("smc", 0) != 0 &&
+                n.rfind("van_genuchten", 0) != 0 && n.rfind("hydraulic_conductivity", 0) != 0 && n != "soil_storage_model";
+    copy_str(loc, cap, node ? "node" : "none");
+  });
+}
+int lgarb_get_current_time(const lgarb_engine* e, double* t) { LGARB_GUARD(e, { require_init(e); *t = e->time_s; }); }
+int lgarb_get_start_time(const lgarb_engine* e, double* t) { LGARB_GUARD(e, *t = 0.0); }
+int lgarb_get_end_time(const lgarb_engine* e, double* t) { LGARB_GUARD(e, { require_init(e); *t = e->pc.endtime_s; }); }
+int lgarb_get_time_step(const lgarb_engine* e, double* dt) {
+  LGARB_GUARD(e, { require_init(e); *dt = e->cfg.forcing_resolution_h * 3600.; });
+}
+int lgarb_get_time_units(const lgarb_engine* e, char* units, int cap) { LGARB_GUARD(e, copy_str(units, cap, "s")); }
+int lgarb_get_grid_rank(const lgarb_engine* e, int grid, int* rank) { LGARB_GUARD(e, *rank = (grid >= 0 && grid <= 4) ? 1 : -1); }
+int lgarb_get_grid_type(const lgarb_engine* e, int grid, char* type, int cap) {
+  LGARB_GUARD(e, copy_str(type, cap, grid == 0 ? "uniform_rectilinear" : ""));
+}
+
+int64_t lgarb_get_num_columns(const lgarb_engine* e) { return (e && e->initialized) ? e->ncol : -1; }
+int lgarb_get_num_layers(const lgarb_engine* e) { return (e && e->initialized) ? e->num_layers : -1; }
+int lgarb_get_num_giuh_ordinates(const lgarb_engine* e) { return (e && e->initialized) ? e->cfg.num_giuh : -1; }
+const char* lgarb_output_scalar_name(int k) { return (k >= 0 && k < LGAR_NOUT) ? kOutNames[k] : nullptr; }
+
+int lgarb_get_status(lgarb_engine* e, int64_t col0, int64_t ncol, int32_t* dest) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    check_range(e, col0, ncol);
+    d2h(e, dest, e->d.status + col0, (size_t)ncol * sizeof(int32_t));
+  });
+}
+
+int lgarb_get_fronts(lgarb_engine* e, int64_t col0, int64_t ncol, double* depth_cm, double* theta, double* psi_cm, double* K, double* dzdt,
+                     int32_t* layer_num, int32_t* to_bottom, int32_t* nfronts) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    check_range(e, col0, ncol);
+    double* dsts[5] = {depth_cm, theta, psi_cm, K, dzdt};
+    for (int w = 0; w < 5; w++) {
+      if (!dsts[w]) continue;
+      CUDA_TRY(lgar_launch_gather_fronts(e->d, w, 1.0, e->d_stage, col0, ncol, e->stream));
+      e->launches++;
+      d2h(e, dsts[w], e->d_stage, (size_t)ncol * LGAR_W * sizeof(double));
+    }
+    std::vector<int32_t> nf((size_t)ncol);
+    d2h(e, nf.data(), e->d.nfront + col0, (size_t)ncol * sizeof(int32_t));
+    if (nfronts) memcpy(nfronts, nf.data(), (size_t)ncol * sizeof(int32_t));
+    if (layer_num || to_bottom) {
+      std::vector<unsigned long long> fl((size_t)ncol);
+      d2h(e, fl.data(), e->d.fflags + col0, (size_t)ncol * sizeof(unsigned long long));
+      for (int64_t c = 0; c < ncol; c++)
+        for (int i = 0; i < LGAR_W; i++) {
+          int nib = (i < nf[c]) ? (int)((fl[c] >> (4 * i)) & 0xF) : 0;
+          if (layer_num) layer_num[c * LGAR_W + i] = (i < nf[c]) ? (nib & 7) : 0;
+          if (to_bottom) to_bottom[c * LGAR_W + i] = (i < nf[c]) ? (nib >> 3) : 0;
+        }
+    }
+  });
+}
+
+int lgarb_get_global_mass_balance(lgarb_engine* e, int64_t col0, int64_t ncol, double* out) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    check_range(e, col0, ncol);
+    const size_t n = (size_t)ncol, st = (size_t)e->stride;
+    std::vector<double> cum(n * LGAR_NCUM), vs(n), volon(n), volend(n), crf(n), crs(n);
+    for (int k = 0; k < LGAR_NCUM; k++) d2h(e, cum.data() + k * n, e->d.cum + k * st + col0, n * sizeof(double));
+    d2h(e, vs.data(), e->volstart + col0, n * sizeof(double));
+    d2h(e, volon.data(), e->d.scal + LGAR_S_VOLON * st + col0, n * sizeof(double));
+    d2h(e, volend.data(), e->d.scal + LGAR_S_STORAGE * st + col0, n * sizeof(double));
+    d2h(e, crf.data(), e->d.scal + LGAR_S_CR_FAST * st + col0, n * sizeof(double));
+    d2h(e, crs.data(), e->d.scal + LGAR_S_CR_SLOW * st + col0, n * sizeof(double));
+    for (size_t c = 0; c < n; c++) {
+      double* o = out + c * 16;
+      double volCRend = crf[c] + crs[c];
+      o[0] = vs[c];
+      o[1] = cum[LGAR_CUM_PRECIP * n + c];
+      o[2] = cum[LGAR_CUM_IN * n + c];
+      o[3] = volend[c];
+      o[4] = volon[c];
+      o[5] = cum[LGAR_CUM_RUNOFF * n + c];
+      o[6] = cum[LGAR_CUM_GIUH * n + c];
+      o[7] = cum[LGAR_CUM_RECH * n + c];
+      o[8] = cum[LGAR_CUM_AET * n + c];
+      o[9] = cum[LGAR_CUM_PET * n + c];
+      o[10] = cum[LGAR_CUM_RUNOFF_CR * n + c];
+      o[11] = volCRend;
+      o[12] = cum[LGAR_CUM_Q * n + c];
+      o[13] = 0.0;
+      o[14] = cum[LGAR_CUM_Q_CR * n + c];
+      o[15] = o[0] + o[1] - o[5] - o[8] - o[4] - o[7] - o[3] + o[13] - o[10] - o[11];  // lgar.cxx:1185
+    }
+  });
+}
+
+int lgarb_get_soil_row(const lgarb_engine* e, int soil, double* o) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (soil < 1 || soil >= (int)e->soils.size()) throw std::runtime_error("soil index out of range");
+    const SoilRow& s = e->soils[soil];
+    o[0] = s.theta_r; o[1] = s.theta_e; o[2] = s.alpha; o[3] = s.n; o[4] = s.m; o[5] = s.lambda; o[6] = s.psib; o[7] = s.h_min;
+    o[8] = s.Ksat; o[9] = s.theta_wp;
+  });
+}
+
+int lgarb_set_force_all_active(lgarb_engine* e, int on) { LGARB_GUARD(e, e->force_all_active = on ? 1 : 0); }
+int64_t lgarb_get_launch_count(const lgarb_engine* e) { return e ? e->launches : -1; }
+int64_t lgarb_get_last_active_count(lgarb_engine* e) {
+  if (!e || !e->initialized) return -1;
+  int32_t c = -1;
+  try {
+    d2h(e, &c, e->d.work_count, sizeof(int32_t));
+  } catch (...) {
+    return -1;
+  }
+  return c;
+}
+void* lgarb_get_stream(lgarb_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// lgar_c_b200/csrc/lgar_kernels.cu -- the batched BmiLGAR::Update() step for sm_100a.
+//
+// One forcing step over all columns is two launches:
+//
+//   lgar_step_stream_kernel   every column, one thread each, fully coalesced SoA traffic.
+//                             Runs the adaptive-dt / flux-cache decision (reference
+//                             src/bmi_lgar.cxx:260-318).  Columns that replay cached fluxes (80-90 %
+//                             of column-steps on the shipped configs) and
+//                             invalid-soil columns are finished here without touching their fronts:
+//                             reservoir, GIUH, mass balance, outputs.  Columns that must compute
+//                             fluxes are compacted into a work list (warp-aggregated atomics).
+//   lgar_step_active_kernel   work-list entries only, one thread per active column, so warps are
+//                             dense in the FP64-heavy path instead of 15 % occupied.  Warps pull
+//                             32 entries at a time from a device-side cursor (heavy-tailed trip
+//                             counts: a static split would leave SMs idle).  Fronts live in
+//                             thread-private arrays for the duration of the step.
+//
+// HBM-bound in the stream kernel, FP64-pipe-bound in the active kernel; no tensor-core work exists
+// on this path (nothing is a contraction).
+#include <cuda_runtime.h>
+#include "lgar_step.cuh"
+
+
+__global__ void __launch_bounds__(256) lgar_step_stream_kernel(LgarConfig cfg, LgarDeviceState d, LgarSinks sinks, int force_all_active) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool needs_active = false;
+  if (col < d.ncol) needs_active = lg_stream_column(cfg, d, sinks, col, force_all_active);
+  // warp-aggregated append to the work list
+  const unsigned mask = __ballot_sync(0xFFFFFFFFu, needs_active);
+  if (mask) {
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(d.work_count, __popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (needs_active) d.work[base + __popc(mask & ((1u << lane) - 1))] = (int32_t)col;
+  }
+}
+
+__global__ void __launch_bounds__(LGAR_ACTIVE_THREADS) lgar_step_active_kernel(LgarConfig cfg, LgarDeviceState d, LgarSinks sinks) {
+  const int lane = threadIdx.x & 31;
+  const int count = d.work_count[0];
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(d.work_count + 1, 32);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= count) break;
+    const int idx = base + lane;
+    if (idx < count) lg_active_column(cfg, d, sinks, d.work[idx]);
+  }
+}
+
+// Gather per-front BMI arrays into a caller-facing [ncol][LGAR_W] layout (pad = NaN).
+__global__ void lgar_gather_fronts_kernel(LgarDeviceState d, int which, double scale, double* dst, int64_t col0, int64_t ncol) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncol * LGAR_W) return;
+  const int64_t c = i / LGAR_W;
+  const int slot = (int)(i % LGAR_W);
+  const int64_t col = col0 + c;
+  const double* src = which == 0 ? d.depth : which == 1 ? d.theta : which == 2 ? d.psi : which == 3 ? d.K : d.dzdt;
+  dst[i] = (slot < d.nfront[col]) ? src[(int64_t)slot * d.stride + col] * scale : LG_NAN;
+}
+
+__global__ void lgar_gather_layers_kernel(LgarDeviceState d, double* dst, int64_t col0, int64_t ncol, int L) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncol * L) return;
+  const int64_t c = i / L;
+  const int k = (int)(i % L);
+  const LgarColumnClass* cls = d.classes + d.class_id[col0 + c];
+  dst[i] = (k < cls->num_layers) ? cls->cum[k] : LG_NAN;  // quirk Q10: from index 0, in cm
+}
+
+// ---- launch wrappers ------------------------------------------------------------------------------
+cudaError_t lgar_launch_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int active_blocks,
+                             int force_all_active, cudaStream_t stream) {
+  cudaError_t err = cudaMemsetAsync(d.work_count, 0, 2 * sizeof(int32_t), stream);
+  if (err != cudaSuccess) return err;
+  const int threads = 256;
+  const int64_t blocks = (d.ncol + threads - 1) / threads;
+  lgar_step_stream_kernel<<<(unsigned)blocks, threads, 0, stream>>>(cfg, d, sinks, force_all_active);
+  lgar_step_active_kernel<<<active_blocks, LGAR_ACTIVE_THREADS, 0, stream>>>(cfg, d, sinks);
+  return cudaGetLastError();
+}
+
+cudaError_t lgar_launch_gather_fronts(const LgarDeviceState& d, int which, double scale, double* dst, int64_t col0, int64_t ncol,
+                                      cudaStream_t stream) {
+  const int64_t n = ncol * LGAR_W;
+  lgar_gather_fronts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d, which, scale, dst, col0, ncol);
+  return cudaGetLastError();
+}
+
+cudaError_t lgar_launch_gather_layers(const LgarDeviceState& d, double* dst, int64_t col0, int64_t ncol, int L, cudaStream_t stream) {
+  const int64_t n = ncol * L;
+  lgar_gather_layers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d, dst, col0, ncol, L);
+  return cudaGetLastError();
+}
+
+int lgar_active_kernel_max_blocks_per_sm() {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lgar_step_active_kernel, LGAR_ACTIVE_THREADS, 0);
+  return nb;
+}

@@ -1,0 +1,254 @@
+// lgar_c_b200/csrc/lgar_step.cuh -- per-column bodies of the two step kernels: HBM <-> thread state
+// marshalling (structure-of-arrays, column fastest), the decision which kernel finishes a column,
+// and the per-step epilogue (GIUH, outputs, cumulative volumes).  Kept apart from lgar_kernels.cu so
+// that tests/hostsim can run exactly this text on a CPU against the oracle (test infrastructure).
+#ifndef LGAR_STEP_CUH
+#define LGAR_STEP_CUH
+
+#include "lgar_kernels.h"
+#include "lgar_physics.cuh"
+
+#ifdef LGAR_HOSTSIM
+#define LG_NAN (std::nan(""))
+#else
+#include <math_constants.h>
+#define LG_NAN CUDART_NAN
+#endif
+
+LG_FN void load_scalars(const LgarDeviceState& d, int64_t col, LgScalars& s) {
+  const double* p = d.scal + col;
+  const int64_t st = d.stride;
+  s.volon = p[LGAR_S_VOLON * st];
+  s.precip_prev = p[LGAR_S_PRECIP_PREV * st];
+  s.cr_fast = p[LGAR_S_CR_FAST * st];
+  s.cr_slow = p[LGAR_S_CR_SLOW * st];
+  s.prev_aet = p[LGAR_S_PREV_AET * st];
+  s.prev_pet = p[LGAR_S_PREV_PET * st];
+  s.prev_rech = p[LGAR_S_PREV_RECH * st];
+  s.acc_pet = p[LGAR_S_ACC_PET * st];
+  s.acc_fd = p[LGAR_S_ACC_FD * st];
+  s.timestep_h = p[LGAR_S_TIMESTEP_H * st];
+  s.storage = p[LGAR_S_STORAGE * st];
+  s.fd_dzdt = p[LGAR_S_FD_DZDT * st];
+  const int b = d.bits[col];
+  s.cache_fluxes = b & 1;
+  s.runoff_prev = (b >> 1) & 1;
+  s.cache_count = (b >> 8) & 0xFF;
+  s.status = d.status[col];
+}
+
+LG_FN void store_scalars(const LgarDeviceState& d, int64_t col, const LgScalars& s, bool active) {
+  double* p = d.scal + col;
+  const int64_t st = d.stride;
+  p[LGAR_S_VOLON * st] = s.volon;
+  p[LGAR_S_PRECIP_PREV * st] = s.precip_prev;
+  p[LGAR_S_CR_FAST * st] = s.cr_fast;
+  p[LGAR_S_CR_SLOW * st] = s.cr_slow;
+  p[LGAR_S_PREV_AET * st] = s.prev_aet;
+  p[LGAR_S_PREV_PET * st] = s.prev_pet;
+  p[LGAR_S_ACC_PET * st] = s.acc_pet;
+  p[LGAR_S_ACC_FD * st] = s.acc_fd;
+  p[LGAR_S_TIMESTEP_H * st] = s.timestep_h;
+  if (active) {  // a step that replays cached fluxes leaves these three untouched
+    p[LGAR_S_PREV_RECH * st] = s.prev_rech;
+    p[LGAR_S_STORAGE * st] = s.storage;
+    p[LGAR_S_FD_DZDT * st] = s.fd_dzdt;
+  }
+  d.bits[col] = (s.cache_fluxes & 1) | ((s.runoff_prev & 1) << 1) | ((s.cache_count & 0xFF) << 8);
+  d.status[col] = s.status;
+}
+
+LG_FN void load_fronts(const LgarDeviceState& d, int64_t col, LgFronts& f) {
+  const int n = d.nfront[col];
+  const unsigned long long fl = d.fflags[col];
+  f.n = n;
+#pragma unroll 1
+  for (int i = 0; i < n; i++) {
+    const int64_t o = (int64_t)i * d.stride + col;
+    f.depth[i] = d.depth[o];
+    f.theta[i] = d.theta[o];
+    f.psi[i] = d.psi[o];
+    f.K[i] = d.K[o];
+    f.dzdt[i] = d.dzdt[o];
+    const int nib = (int)((fl >> (4 * i)) & 0xF);
+    f.layer[i] = (signed char)(nib & 7);
+    f.tb[i] = (signed char)(nib >> 3);
+  }
+}
+
+LG_FN void store_fronts(const LgarDeviceState& d, int64_t col, const LgFronts& f) {
+  unsigned long long fl = 0ull;
+#pragma unroll 1
+  for (int i = 0; i < f.n; i++) {
+    const int64_t o = (int64_t)i * d.stride + col;
+    d.depth[o] = f.depth[i];
+    d.theta[o] = f.theta[i];
+    d.psi[o] = f.psi[i];
+    d.K[o] = f.K[i];
+    d.dzdt[o] = f.dzdt[i];
+    fl |= (unsigned long long)((f.layer[i] & 7) | ((f.tb[i] ? 1 : 0) << 3)) << (4 * i);
+  }
+  d.fflags[col] = fl;
+  d.nfront[col] = f.n;
+}
+
+// GIUH convolution (giuh/giuh.c:12-39; input in cm, quirk Q12), outputs in metres
+// (bmi_lgar.cxx:808-893) and the cumulative volumes of the global balance (lgar.cxx:1162-1185).
+LG_FN void epilogue(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int64_t col,
+                                         const LgStepVols& v, int status) {
+  const int64_t st = d.stride;
+  if (status & LGAR_FAIL_MASK) {
+    const double nan = LG_NAN;
+#pragma unroll
+    for (int k = 0; k < LGAR_NOUT; k++) {
+      d.out[k * st + col] = nan;
+      if (sinks.p[k]) sinks.p[k][col] = nan;
+    }
+    return;
+  }
+  const int N = cfg.num_giuh;
+  const double r = v.volrunoff + v.volQ_CR;
+  // queue slot N-1 is always zero between steps, so only N-1 slots are stored
+  double carry = (N > 1) ? d.giuhq[col] : 0.0;
+  const double now = carry + cfg.giuh[0] * r;
+  for (int i = 1; i < N; i++) {
+    double qi = (i < N - 1) ? d.giuhq[(int64_t)i * st + col] : 0.0;
+    qi += cfg.giuh[i] * r;
+    d.giuhq[(int64_t)(i - 1) * st + col] = qi;  // shifted left; i-1 <= N-2
+  }
+  const double cm_to_m = 0.01;
+  double o[LGAR_NOUT];
+  o[LGAR_OUT_PRECIP] = v.precip * cm_to_m;
+  o[LGAR_OUT_PET] = v.PET * cm_to_m;
+  o[LGAR_OUT_AET] = v.AET * cm_to_m;
+  o[LGAR_OUT_RUNOFF] = v.volrunoff * cm_to_m;
+  o[LGAR_OUT_GIUH_RUNOFF] = now * cm_to_m;
+  o[LGAR_OUT_STORAGE] = v.volend * cm_to_m;
+  o[LGAR_OUT_Q] = now * cm_to_m;
+  o[LGAR_OUT_INFIL] = v.volin * cm_to_m;
+  o[LGAR_OUT_PERC] = v.volrech * cm_to_m;
+  o[LGAR_OUT_Q_CR] = v.volQ_CR * cm_to_m;
+  o[LGAR_OUT_MBAL] = v.local_mb * cm_to_m;
+  o[LGAR_OUT_CR_STORAGE] = v.volCRend * cm_to_m;
+#pragma unroll
+  for (int k = 0; k < LGAR_NOUT; k++) {
+    d.out[k * st + col] = o[k];
+    if (sinks.p[k]) sinks.p[k][col] = o[k];
+  }
+  double* cu = d.cum + col;
+  cu[LGAR_CUM_PRECIP * st] += v.precip;
+  cu[LGAR_CUM_IN * st] += v.volin;
+  cu[LGAR_CUM_AET * st] += v.AET;
+  cu[LGAR_CUM_RECH * st] += v.volrech;
+  cu[LGAR_CUM_RUNOFF * st] += v.volrunoff;
+  cu[LGAR_CUM_Q * st] += now;
+  cu[LGAR_CUM_Q_CR * st] += v.volQ_CR;
+  cu[LGAR_CUM_PET * st] += v.PET;
+  cu[LGAR_CUM_GIUH * st] += now;
+  cu[LGAR_CUM_RUNOFF_CR * st] += v.volQ_CR;
+}
+
+LG_FN void zero_vols(LgStepVols& v) {
+  v.precip = v.PET = v.AET = v.volin = v.volrech = v.volrunoff = v.volQ_CR = 0.0;
+  v.volend = v.volCRend = v.local_mb = 0.0;
+}
+
+// Clamp / PET_affects_precip, bmi_lgar.cxx:325-348.  NB the sub-step and cache decisions above it
+// in the reference see the raw forcing; only the sub-cycle loop sees the adjusted one.
+LG_FN void adjust_forcing(const LgarConfig& cfg, double& P, double& E, int& status) {
+  if (P < 0.0) {
+    P = 0.0;
+    status |= LGAR_WARN_NEG_FORCING;
+  }
+  if (E < 0.0) {
+    E = 0.0;
+    status |= LGAR_WARN_NEG_FORCING;
+  }
+  if (cfg.PET_affects_precip) {
+    if (P > E) {
+      P = P - E;
+      E = 0.0;
+    } else {
+      E = E - P;
+      P = 0.0;
+    }
+  }
+}
+
+// Invalid soil type: Q = precip (bmi_lgar.cxx:145-179)
+LG_FN void step_invalid(const LgarDeviceState& d, const LgarSinks& sinks, int64_t col, double P) {
+  const int64_t st = d.stride;
+  const double pm = P * 0.001;
+#pragma unroll
+  for (int k = 0; k < LGAR_NOUT; k++) {
+    double val = (k == LGAR_OUT_PRECIP || k == LGAR_OUT_RUNOFF || k == LGAR_OUT_Q) ? pm : 0.0;
+    d.out[k * st + col] = val;
+    if (sinks.p[k]) sinks.p[k][col] = val;
+  }
+  double* cu = d.cum + col;
+  cu[LGAR_CUM_PRECIP * st] += P * 0.1;
+  cu[LGAR_CUM_RUNOFF * st] += P * 0.1;
+  cu[LGAR_CUM_Q * st] += P * 0.1;
+}
+
+// Body of lgar_step_stream_kernel for one column.  Returns true when the column must compute fluxes
+// this step (and was therefore left untouched for the active kernel).
+LG_FN bool lg_stream_column(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int64_t col, int force_all_active) {
+  const LgarColumnClass* cls = d.classes + d.class_id[col];
+  double P = d.precip[col], E = d.pet[col];
+  if (cls->invalid_soil_type) {
+    step_invalid(d, sinks, col, P);
+    return false;
+  }
+  LgScalars s;
+  load_scalars(d, col, s);
+  if (s.status & LGAR_FAIL_MASK) {
+    LgStepVols v;
+    zero_vols(v);
+    epilogue(cfg, d, sinks, col, v, s.status);
+    return false;
+  }
+  const LgPrologue pro = lg_prologue(cfg, s, P);
+  if (!pro.cache_fluxes || force_all_active) return true;
+  if (cfg.adaptive_timestep) s.timestep_h = pro.subtimestep_h;
+  s.cache_fluxes = 1;
+  s.cache_count = pro.cache_count;
+  adjust_forcing(cfg, P, E, s.status);
+  LgStepVols v;
+  zero_vols(v);
+  lg_step_cached(cfg, s, pro, P, E, v);
+  if (!(fabs(v.local_mb) <= cfg.mbal_tol)) s.status |= (isnan(v.local_mb) ? LGAR_FAIL_NAN : LGAR_FAIL_MBAL);
+  store_scalars(d, col, s, false);
+  epilogue(cfg, d, sinks, col, v, s.status);
+  return false;
+}
+
+// Body of lgar_step_active_kernel for one work-list entry: the full Update() of one column.
+LG_FN void lg_active_column(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int64_t col) {
+  const LgarColumnClass* cls = d.classes + d.class_id[col];
+  double P = d.precip[col], E = d.pet[col];
+  LgScalars s;
+  load_scalars(d, col, s);
+  LgPrologue pro = lg_prologue(cfg, s, P);
+  if (cfg.adaptive_timestep) s.timestep_h = pro.subtimestep_h;
+  s.cache_count = pro.cache_count;
+  adjust_forcing(cfg, P, E, s.status);
+  LgStepVols v;
+  zero_vols(v);
+  if (pro.cache_fluxes) {  // only reachable with force_all_active (the two kernels tested against each other)
+    s.cache_fluxes = 1;
+    lg_step_cached(cfg, s, pro, P, E, v);
+    if (!(fabs(v.local_mb) <= cfg.mbal_tol)) s.status |= (isnan(v.local_mb) ? LGAR_FAIL_NAN : LGAR_FAIL_MBAL);
+    store_scalars(d, col, s, false);
+  } else {
+    LgFronts f;
+    load_fronts(d, col, f);
+    s.cache_fluxes = 0;
+    lg_step_active(cfg, *cls, s, f, pro, P, E, v);
+    store_scalars(d, col, s, true);
+    store_fronts(d, col, f);
+  }
+  epilogue(cfg, d, sinks, col, v, s.status);
+}
+
+#endif  // LGAR_STEP_CUH

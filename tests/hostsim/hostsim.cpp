@@ -1,0 +1,80 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the kernel text (lgar_c_b200/csrc/lgar_physics.cuh + lgar_step.cuh) with a host compiler
+// and drives it for ONE column, so the kernel's logic can be compared with the oracle on a machine
+// without a GPU.  It is never linked into, nor loaded by, liblgarb.so or the lgar_c_b200 package:
+// the product has no CPU path.  Arithmetic differs from the GPU only in libm's pow vs CUDA's pow.
+#define LGAR_HOSTSIM 1
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../lgar_c_b200/csrc/lgar_config.hpp"
+#include "../../lgar_c_b200/csrc/lgar_step.cuh"
+
+using namespace lgarhost;
+
+extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, const double* thick_in, int nsteps, const double* P,
+                                  const double* E, double* scalars, int* nfronts, int cap, double* fronts, int* flags,
+                                  int force_all_active, int* status_out, char* err, int errcap) {
+  try {
+    ParsedConfig pc = parse_config(cfg_path);
+    const int L = (int)pc.layer_thickness.size();
+    std::vector<SoilRow> soils;
+    read_soil_file(pc.soil_params_file, pc.num_soil_types, pc.wilting_point_psi, pc.log_mode, soils, cfg_path);
+    LgarConfig cfg = make_engine_config(pc);
+    std::vector<int> types(L);
+    std::vector<double> thick(L);
+    for (int k = 0; k < L; k++) {
+      types[k] = types_in ? types_in[k] : pc.layer_soil_type[k];
+      thick[k] = thick_in ? thick_in[k] : pc.layer_thickness[k];
+    }
+    LgarColumnClass cls = make_class(pc, soils, L, types.data(), thick.data());
+
+    const int64_t st = 1;
+    std::vector<double> depth(LGAR_W), theta(LGAR_W), psi(LGAR_W), K(LGAR_W), dzdt(LGAR_W), scal(LGAR_NSCAL), giuhq(LGAR_MAXG), cum(LGAR_NCUM),
+        out(LGAR_NOUT);
+    unsigned long long fflags = 0;
+    int32_t nf = 0, bits = 1 << 8, status = 0, class_id = 0, work[1], work_count[2];
+    double p1, e1;
+    LgarDeviceState d;
+    memset(&d, 0, sizeof(d));
+    d.ncol = 1; d.stride = st;
+    d.depth = depth.data(); d.theta = theta.data(); d.psi = psi.data(); d.K = K.data(); d.dzdt = dzdt.data();
+    d.fflags = &fflags; d.nfront = &nf; d.scal = scal.data(); d.bits = &bits; d.status = &status; d.class_id = &class_id;
+    d.giuhq = giuhq.data(); d.cum = cum.data(); d.out = out.data(); d.classes = &cls; d.precip = &p1; d.pet = &e1;
+    d.work = work; d.work_count = work_count;
+    if (!cls.invalid_soil_type) {
+      for (int k = 0; k < L; k++) {
+        depth[k] = cls.cum[k + 1]; theta[k] = cls.initial_theta[k + 1]; psi[k] = pc.initial_psi; K[k] = cls.initial_K[k + 1]; dzdt[k] = 0.0;
+        fflags |= (unsigned long long)(((k + 1) & 7) | 8) << (4 * k);
+      }
+      nf = L;
+      scal[LGAR_S_STORAGE] = class_initial_storage(cls);
+    }
+    scal[LGAR_S_TIMESTEP_H] = pc.timestep_h;
+    LgarSinks sinks;
+    memset(&sinks, 0, sizeof(sinks));
+    int t;
+    for (t = 0; t < nsteps; t++) {
+      p1 = P[t]; e1 = E[t];
+      if (lg_stream_column(cfg, d, sinks, 0, force_all_active)) lg_active_column(cfg, d, sinks, 0);
+      if (status & LGAR_FAIL_MASK) break;
+      if (scalars) for (int k = 0; k < LGAR_NOUT; k++) scalars[(size_t)t * LGAR_NOUT + k] = out[k];
+      if (nfronts) nfronts[t] = nf;
+      if (fronts) {
+        for (int i = 0; i < nf && i < cap; i++) {
+          double* q = fronts + ((size_t)t * cap + i) * 5;
+          q[0] = depth[i]; q[1] = theta[i]; q[2] = psi[i]; q[3] = K[i]; q[4] = dzdt[i];
+          int nib = (int)((fflags >> (4 * i)) & 0xF);
+          flags[(size_t)t * cap + i] = (nib & 7) | ((nib >> 3) << 8);
+        }
+      }
+    }
+    if (status_out) *status_out = status;
+    return t;
+  } catch (const std::exception& ex) {
+    if (err && errcap > 0) snprintf(err, (size_t)errcap, "%s", ex.what());
+    return -1;
+  }
+}

@@ -1,0 +1,222 @@
+"""Parity of the CUDA engine (through the C ABI) with the oracle / the reference's golden vectors.
+Bar (BASELINE.json north_star): every per-step result within 1e-9 relative, front counts exact.
+All tests here need a B200 (pytest -m gpu); they never read /root/reference."""
+import numpy as np
+import pytest
+
+from helpers import STANDARD, RANDOM, load_golden, config_for, assert_scalars_close, assert_fronts_close, RTOL
+
+pytestmark = pytest.mark.gpu
+
+
+def engine_run(cfg, P, E, ncol=3, soil_types=None, thickness=None, force_all_active=False, shifts=None, mult=None):
+    """Run the engine over a [T] forcing series (optionally per-column circularly shifted / scaled)
+    with the forcing resident on the device; returns per-step scalars [T][12][ncol], nfronts [T][ncol]
+    and the engine (for final-state queries)."""
+    import torch
+    import lgar_c_b200
+    b = lgar_c_b200.BmiLGARBatch()
+    b.initialize(cfg, ncol, 0, soil_types, thickness)
+    if force_all_active:
+        b.set_force_all_active(True)
+    T = len(P)
+    Pm = np.empty((T, ncol)); Em = np.empty((T, ncol))
+    for c in range(ncol):
+        sh = 0 if shifts is None else int(shifts[c])
+        m = 1.0 if mult is None else float(mult[c])
+        Pm[:, c] = np.roll(P, -sh)[:T] * m
+        Em[:, c] = np.roll(E, -sh)[:T]
+    dev = torch.device("cuda:0")
+    dP = torch.from_numpy(Pm).to(dev); dE = torch.from_numpy(Em).to(dev)
+    sinks = torch.full((12, T, ncol), float("nan"), dtype=torch.float64, device=dev)
+    nfs = torch.zeros((T, ncol), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    b.update_steps_device(T, dP.data_ptr(), dE.data_ptr(), ncol,
+                          {n: sinks[k].data_ptr() for k, n in enumerate(lgar_c_b200.OUTPUT_SCALARS)}, ncol, nfs.data_ptr())
+    b.synchronize()
+    return b, sinks.cpu().numpy().transpose(1, 0, 2), nfs.cpu().numpy(), (Pm, Em)
+
+
+def fronts_record(fr, c):
+    n = int(fr["nfronts"][c])
+    arr = np.stack([fr[k][c] for k in ("depth", "theta", "psi", "K", "dzdt")], axis=1)
+    flags = (fr["layer"][c] | (fr["to_bottom"][c] << 8)).astype(np.int32)
+    return arr, flags, n
+
+
+@pytest.mark.parametrize("name", STANDARD + RANDOM)
+def test_engine_matches_reference_golden(cuda_device, name, tmp_path):
+    g = load_golden(name)
+    cfg = config_for(name, tmp_path)
+    T = len(g["precip"])
+    b, scal, nf, _ = engine_run(cfg, g["precip"], g["pet"], ncol=3)
+    st = b.get_status()
+    assert (st & 0xFFFF == 0).all(), st
+    for c in range(3):
+        assert np.array_equal(nf[:, c], g["nfronts"]), f"{name}: front count differs at step {int(np.argmax(nf[:, c] != g['nfronts']))}"
+        assert_scalars_close(scal[:, :, c], g["scalars"], f"{name} col {c}")
+    fr = b.get_fronts()
+    for c in range(3):
+        arr, flags, n = fronts_record(fr, c)
+        assert n == g["nfronts"][-1]
+        assert_fronts_close(arr, flags, g["ck_fronts"][-1], g["ck_flags"][-1], n, f"{name} final fronts")
+    mb = b.get_global_mass_balance()
+    ref_cum = g["cumulative"]
+    # volprecip, volin, volrunoff, volAET, volrech, volQ: cumulative sums to 1e-9 relative
+    for mine, theirs in ((1, 1), (2, 2), (5, 5), (7, 7), (8, 8), (9, 9), (10, 10), (12, 12)):
+        assert abs(mb[0, mine] - ref_cum[theirs]) <= 1e-9 * abs(ref_cum[theirs]) + 1e-10, (mine, mb[0, mine], ref_cum[theirs])
+    assert abs(mb[0, 15] - ref_cum[15]) < 1e-8
+    b.finalize()
+
+
+def test_reference_unit_test_known_answers_on_gpu(cuda_device, tmp_path):
+    """reference tests/main_unit_test_bmi.cxx:424-568 through the BMI verbs of the C ABI"""
+    import lgar_c_b200
+    b = lgar_c_b200.BmiLGARBatch()
+    b.initialize(config_for("unittest", tmp_path), 2)
+    b.set_value("precipitation_rate", [1.896, 1.896])
+    b.set_value("potential_evapotranspiration_rate", [0.104, 0.104])
+    assert list(b.get_value("precipitation_rate")) == [1.896, 1.896]
+    b.update()
+    n = b.get_value("soil_num_wetting_fronts")
+    assert list(n) == [4, 4]
+    depth = b.get_value("soil_depth_wetting_fronts")
+    theta = b.get_value("soil_moisture_wetting_fronts")
+    depth_b = [4.55355239489608365, 44.00, 175.0, 200.0]
+    theta_b = [0.21371581122514613, 0.17270389607163267, 0.25211383152603861, 0.17959348005962811]
+    for c in range(2):
+        for i in range(4):
+            assert abs(depth[c, i] * 100 - depth_b[i]) < 1e-5 and abs(theta[c, i] - theta_b[i]) < 1e-5
+        assert np.isnan(depth[c, 4:]).all()
+    assert abs(b.get_value("infiltration")[0] * 1000 - 1.896) < 1e-5
+    assert abs(b.get_value("actual_evapotranspiration")[0] * 1000 - 0.02980092620558239) < 1e-5
+    assert abs(b.get_value("potential_evapotranspiration")[0] * 1000 - 0.104) < 1e-5
+    assert b.get_current_time() == 3600.0 and b.get_time_step() == 3600.0 and b.get_end_time() == 3600.0
+
+
+def test_two_kernel_split_equals_single_path(cuda_device, tmp_path):
+    """The streaming kernel (cached-flux steps) + active kernel must be indistinguishable from
+    routing every column through the active kernel."""
+    g = load_golden("Phillipsburg_with_reservoir")
+    cfg = config_for("Phillipsburg_with_reservoir", tmp_path)
+    T = 2500
+    b1, s1, n1, _ = engine_run(cfg, g["precip"][:T], g["pet"][:T], ncol=5)
+    b2, s2, n2, _ = engine_run(cfg, g["precip"][:T], g["pet"][:T], ncol=5, force_all_active=True)
+    assert np.array_equal(n1, n2) and np.array_equal(s1, s2)
+    f1, f2 = b1.get_fronts(), b2.get_fronts()
+    for k in ("depth", "theta", "psi", "K", "dzdt", "layer", "to_bottom", "nfronts"):
+        assert np.array_equal(f1[k], f2[k], equal_nan=True)
+
+
+def test_heterogeneous_batch_against_oracle(cuda_device, oracle, tmp_path):
+    """BASELINE config 3 in small: Bushland layering, per-column soil triples drawn from the PARSED
+    vG_params_stat_nom_ordered.dat (quirk Q2), per-column circular time shift of the forcing."""
+    from oracle.oracle_py import DATA, write_config, read_forcing
+    ncol, T = 192, 1200
+    rng = np.random.default_rng(12345)
+    types = rng.integers(1, 13, size=(ncol, 3)).astype(np.int32)
+    shifts = (np.arange(ncol) * 7919) % 8760
+    cfg = write_config(DATA / "configs" / "config_lasam_Bushland.txt", tmp_path / "c3.txt",
+                       soil_params_file=str(DATA / "vG_params_stat_nom_ordered.dat"), max_valid_soil_types="12", layer_soil_type="1,2,3")
+    P, E = read_forcing(DATA / "forcing" / "forcing_data_resampled_uniform_Bushland.csv")
+    P, E = P[:8760], E[:8760]
+    import torch
+    import lgar_c_b200
+    Pm = np.stack([np.roll(P, -int(s))[:T] for s in shifts], axis=1)
+    Em = np.stack([np.roll(E, -int(s))[:T] for s in shifts], axis=1)
+    b = lgar_c_b200.BmiLGARBatch()
+    b.initialize(cfg, ncol, 0, types)
+    dP = torch.from_numpy(np.ascontiguousarray(Pm)).cuda(); dE = torch.from_numpy(np.ascontiguousarray(Em)).cuda()
+    sinks = torch.zeros((12, T, ncol), dtype=torch.float64, device="cuda"); nfs = torch.zeros((T, ncol), dtype=torch.int32, device="cuda")
+    b.update_steps_device(T, dP.data_ptr(), dE.data_ptr(), ncol, {n: sinks[k].data_ptr() for k, n in enumerate(lgar_c_b200.OUTPUT_SCALARS)}, ncol, nfs.data_ptr())
+    b.synchronize()
+    scal = sinks.cpu().numpy().transpose(1, 0, 2); nf = nfs.cpu().numpy()
+    assert (b.get_status() & 0xFFFF == 0).all()
+    fr = b.get_fronts()
+    for c in range(ncol):
+        p = oracle.params_from_config(cfg, layer_soil_type=[int(x) for x in types[c]])
+        s = oracle.new_state(p)
+        r = oracle.run_series(p, s, Pm[:, c], Em[:, c], cap=16)
+        assert r["done"] == T
+        assert np.array_equal(nf[:, c], r["nfronts"]), f"col {c} soils {types[c]}: front count differs at step {int(np.argmax(nf[:, c] != r['nfronts']))}"
+        assert_scalars_close(scal[:, :, c], r["scalars"], f"col {c} soils {types[c]}")
+        arr, flags, n = fronts_record(fr, c)
+        assert_fronts_close(arr, flags, r["fronts"][-1], r["flags"][-1], n, f"col {c} final fronts")
+
+
+def test_replicated_columns_are_identical_100k(cuda_device, tmp_path):
+    """BASELINE config 2: a synthetic case replicated to 100 000 columns on one GPU -- every column
+    must equal column 0 bit for bit, and column 0 must match the reference's golden vector."""
+    g = load_golden("synth_1")
+    cfg = config_for("synth_1", tmp_path)
+    import torch
+    import lgar_c_b200
+    ncol, T = 100_000, len(g["precip"])
+    b = lgar_c_b200.BmiLGARBatch()
+    b.initialize(cfg, ncol)
+    dP = torch.from_numpy(np.repeat(g["precip"][:, None], ncol, axis=1).copy()).cuda()
+    dE = torch.from_numpy(np.repeat(g["pet"][:, None], ncol, axis=1).copy()).cuda()
+    b.update_steps_device(T, dP.data_ptr(), dE.data_ptr(), ncol)
+    b.synchronize()
+    for name in ("soil_storage", "infiltration", "surface_runoff", "mass_balance"):
+        v = b.get_value(name)
+        assert (v == v[0]).all(), name
+    assert (b.get_value("soil_num_wetting_fronts") == g["nfronts"][-1]).all()
+    assert abs(b.get_value("soil_storage")[0] - g["scalars"][-1, 5]) <= RTOL * g["scalars"][-1, 5]
+    mb = b.get_global_mass_balance(0, 1000)
+    assert np.abs(mb[:, 15]).max() < 1e-6     # global balance closes (reference: 1.9e-9 cm on this case)
+
+
+def test_bmi_variable_access_semantics(cuda_device, tmp_path):
+    import lgar_c_b200
+    b = lgar_c_b200.BmiLGARBatch()
+    ncol = 7
+    b.initialize(config_for("Phillipsburg", tmp_path), ncol)
+    assert b.get_grid_size(1) == ncol and b.get_grid_size(2) == ncol * 3 and b.get_var_nbytes("soil_storage") == 8 * ncol
+    # forcing defaults to -1 until set (reference src/lgar.cxx:172-175)
+    assert (b.get_value("precipitation_rate") == -1.0).all()
+    # soil_depth_layers: cumulative thickness from index 0, in cm (reference quirk Q10, src/bmi_lgar.cxx:1350)
+    assert np.array_equal(b.get_value("soil_depth_layers")[3], [0.0, 44.0, 175.0])
+    assert list(b.get_value("soil_num_wetting_fronts")) == [3] * ncol
+    b.set_value("precipitation_rate", np.zeros(ncol))
+    b.set_value("potential_evapotranspiration_rate", np.full(ncol, 0.1))
+    b.set_value_at_indices("precipitation_rate", [2, 5], [4.0, 12.0])
+    assert list(b.get_value_at_indices("precipitation_rate", [5, 2, 0])) == [12.0, 4.0, 0.0]
+    b.update_until(3600.0)
+    with pytest.raises(lgar_c_b200.LgarbError):
+        b.update_until(0.0)       # reference: assert (t > 0.0), src/bmi_lgar.cxx:901
+    infil = b.get_value("infiltration")
+    assert infil[0] == 0.0 and infil[2] > 0.0 and infil[5] > infil[2]
+    assert list(b.get_value_range("infiltration", 2, 2)) == [infil[2], infil[3]]
+    with pytest.raises(lgar_c_b200.LgarbError, match="does not exist"):
+        b.get_value("nonexistent_variable")      # reference: throw, src/bmi_lgar.cxx:1421-1425
+    import torch
+    ptr = b.get_value_ptr("infiltration")
+    assert ptr != 0
+    out = torch.zeros(ncol, dtype=torch.float64, device="cuda")
+    b.get_value_device("infiltration", out.data_ptr())
+    assert np.array_equal(out.cpu().numpy(), infil)
+    # negative forcing is clamped with a warning bit (reference src/bmi_lgar.cxx:325-337), never fatal
+    b.set_value("precipitation_rate", np.full(ncol, -2.0))
+    b.update()
+    st = b.get_status()
+    assert (st & lgar_c_b200.STATUS_FAIL_MASK == 0).all() and (st & 0x10000).all()
+    b.finalize()
+    with pytest.raises(lgar_c_b200.LgarbError):
+        b.update()
+
+
+def test_invalid_soil_columns_pass_precip_through(cuda_device, tmp_path):
+    """Columns whose soil type exceeds max_valid_soil_types return Q = precip (src/bmi_lgar.cxx:145-179)
+    while their neighbours run normally."""
+    import lgar_c_b200
+    b = lgar_c_b200.BmiLGARBatch()
+    types = np.array([[13, 14, 15], [13, 26, 15], [13, 14, 15]], dtype=np.int32)
+    b.initialize(config_for("Phillipsburg", tmp_path), 3, 0, types)
+    b.set_value("precipitation_rate", [3.0, 3.0, 3.0])
+    b.set_value("potential_evapotranspiration_rate", [0.2, 0.2, 0.2])
+    b.update()
+    q = b.get_value("total_discharge"); r = b.get_value("surface_runoff"); i = b.get_value("infiltration")
+    assert q[1] == r[1] == 3.0 * 0.001 and i[1] == 0.0
+    assert i[0] == i[2] and i[0] > 0.0
+    assert list(b.get_value("soil_num_wetting_fronts")) == [4, 0, 4]

@@ -1,0 +1,53 @@
+"""The kernel TEXT (lgar_c_b200/csrc/lgar_physics.cuh + lgar_step.cuh) compiled for the host by
+tests/hostsim and run against the oracle: a CPU-side check of the device code's logic (slot
+arithmetic, the two-kernel split, the epilogue).  Test infrastructure only -- the product library
+contains no host path.  Remaining differences are libm pow vs x*x / x*x*x (<= 1 ulp)."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import STANDARD, RANDOM, load_golden, config_for, assert_scalars_close, assert_fronts_close
+
+HS = Path(__file__).resolve().parent / "hostsim"
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+@pytest.fixture(scope="module")
+def hostsim():
+    so = HS / "libhostsim.so"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-o", str(so), str(HS / "hostsim.cpp")])
+    lib = C.CDLL(str(so))
+    lib.hostsim_run_series.argtypes = [C.c_char_p, _ip, _dp, C.c_int, _dp, _dp, _dp, _ip, C.c_int, _dp, _ip, C.c_int, _ip, C.c_char_p, C.c_int]
+    lib.hostsim_run_series.restype = C.c_int
+    return lib
+
+
+def run(lib, cfg, P, E, force, cap=16):
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    E = np.ascontiguousarray(E, dtype=np.float64)
+    n = len(P)
+    scal = np.zeros((n, 12)); nf = np.zeros(n, dtype=np.int32); fr = np.zeros((n, cap, 5)); fl = np.zeros((n, cap), dtype=np.int32)
+    st = C.c_int(0)
+    err = C.create_string_buffer(512)
+    done = lib.hostsim_run_series(str(cfg).encode(), None, None, n, P.ctypes.data_as(_dp), E.ctypes.data_as(_dp), scal.ctypes.data_as(_dp),
+                                  nf.ctypes.data_as(_ip), cap, fr.ctypes.data_as(_dp), fl.ctypes.data_as(_ip), force, C.byref(st), err, 512)
+    assert done >= 0, err.value.decode()
+    return done, scal, nf, fr, fl, st.value
+
+
+@pytest.mark.parametrize("force", [0, 1])
+@pytest.mark.parametrize("name", STANDARD + RANDOM)
+def test_kernel_text_matches_golden(hostsim, name, force, tmp_path):
+    g = load_golden(name)
+    n = min(len(g["precip"]), 3000)
+    done, scal, nf, fr, fl, status = run(hostsim, config_for(name, tmp_path), g["precip"][:n], g["pet"][:n], force)
+    assert done == n and status & 0xFFFF == 0
+    assert np.array_equal(nf, g["nfronts"][:n]), "front counts differ from the reference"
+    assert_scalars_close(scal, g["scalars"][:n], name, rtol=1e-12)
+    for i, t in enumerate(g["ck_steps"]):
+        if t < n:
+            assert_fronts_close(fr[t], fl[t], g["ck_fronts"][i], g["ck_flags"][i], int(nf[t]), f"{name}@{t}", rtol=1e-12)
