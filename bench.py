@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py -- column-timesteps/second of the batched LGAR/CASAM Update() path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # the B200 engine
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU implementation
+
+Workload (config.workload = "config5-shard"): BASELINE.json config 5 cut to one GPU's share --
+1 250 000 columns per GPU (10 M over 8), 3 layers, layering Phillipsburg / Bushland by global
+column parity, soils drawn per column and layer from the PARSED data/vG_params_stat_nom_ordered.dat
+(12 rows, reader quirk Q2 included), flags of config_lasam_Phillipsburg_with_reservoir.txt (CASAM:
+LGAR + nonlinear reservoir + GIUH, closed-form G, adaptive sub-step, flux caching), synthetic hourly
+forcing: wet hour with probability 0.03, intensity Exp(mean 2.5 mm/h) capped at 170, PET =
+0.21*max(0,1+cos(2pi(h-14)/24))*(1+0.5 sin(2pi d/365)) mm/h.
+
+A bench "step" is one simulated day: --hours-per-step (24) consecutive Update() calls over every
+column of the rank.  Before warm-up every column is spun up for --spinup-hours so that the timed
+region sees a developed wetting-front population rather than the 3-front initial state.
+
+value   = column-timesteps / s, device-timed (CUDA events on the engine's stream), forcing resident
+          in HBM, whole job (sum over ranks / max time over ranks)
+e2e     = the same through the BMI verbs with HOST buffers: per forcing hour SetValue(precip),
+          SetValue(PET) from pinned host memory, Update(), GetValue(total_discharge) to host
+roofline, cpu_baseline: see DESIGN.md section 7.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+DATA = ROOT / "data"
+
+PH_LAYERS = (44.0, 131.0, 25.0)   # data/configs/config_lasam_Phillipsburg.txt
+BU_LAYERS = (18.0, 76.0, 135.0)   # data/configs/config_lasam_Bushland.txt
+N_GIUH = 5
+
+
+# --------------------------------------------------------------------------------------------------
+# workload definition (shared by both arms)
+# --------------------------------------------------------------------------------------------------
+def splitmix64(x: np.ndarray) -> np.ndarray:
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    z = x
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    return z ^ (z >> np.uint64(31))
+
+
+def column_soils(col0: int, ncol: int, seed: int = 12345) -> np.ndarray:
+    """soil index in 1..12 for (global column c, layer k): counter-based so any shard can draw its own."""
+    c = np.arange(col0, col0 + ncol, dtype=np.uint64)
+    out = np.empty((ncol, 3), dtype=np.int32)
+    with np.errstate(over="ignore"):
+        for k in range(3):
+            h = splitmix64(c * np.uint64(3) + np.uint64(k) + np.uint64(seed) * np.uint64(0x100000001B3))
+            out[:, k] = (h % np.uint64(12)).astype(np.int32) + 1
+    return out
+
+
+def column_layers(col0: int, ncol: int) -> np.ndarray:
+    c = np.arange(col0, col0 + ncol)
+    out = np.empty((ncol, 3))
+    out[c % 2 == 0] = PH_LAYERS
+    out[c % 2 == 1] = BU_LAYERS
+    return out
+
+
+def write_workload_config(tmpdir: Path) -> Path:
+    """config_lasam_Phillipsburg_with_reservoir.txt with the stat_nom soil table, absolute paths."""
+    lines = []
+    for line in (DATA / "configs" / "config_lasam_Phillipsburg_with_reservoir.txt").read_text().splitlines():
+        if line.startswith("soil_params_file="):
+            line = f"soil_params_file={DATA / 'vG_params_stat_nom_ordered.dat'}"
+        elif line.startswith("max_valid_soil_types="):
+            line = "max_valid_soil_types=12"
+        elif line.startswith("layer_soil_type="):
+            line = "layer_soil_type=1,2,3"
+        elif line.startswith("forcing_file="):
+            continue
+        lines.append(line)
+    p = tmpdir / "bench_config5.txt"
+    p.write_text("\n".join(lines) + "\n")
+    return p
+
+
+def pet_series(hours: np.ndarray) -> np.ndarray:
+    h = hours % 24
+    d = (hours // 24) % 365
+    return 0.21 * np.maximum(0.0, 1.0 + np.cos(2 * np.pi * (h - 14) / 24.0)) * (1.0 + 0.5 * np.sin(2 * np.pi * d / 365.0))
+
+
+def host_forcing(ncol: int, hour0: int, nhours: int, seed: int):
+    """numpy version of the synthetic forcing (used by the CPU arm)."""
+    rng = np.random.default_rng([777, seed, hour0])
+    u1 = rng.random((nhours, ncol))
+    u2 = rng.random((nhours, ncol))
+    P = np.where(u1 < 0.03, np.minimum(-2.5 * np.log1p(-u2), 170.0), 0.0)
+    E = np.repeat(pet_series(np.arange(hour0, hour0 + nhours))[:, None], ncol, axis=1)
+    return np.ascontiguousarray(P), np.ascontiguousarray(E)
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation on the host cores
+# --------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One process = one core: owns `ncol` reference columns, advances them `spin + warm + timed` hours,
+    returns wall seconds of the timed part."""
+    kind, wid, ncol, col0, spin_h, blocks, cfg_dir = args
+    import ctypes as C
+    from oracle.oracle_py import Oracle, RefHarness
+    soils = column_soils(col0, ncol)
+    layers = column_layers(col0, ncol)
+    base = Path(cfg_dir) / "bench_config5.txt"  # written once by the parent
+    times = []
+    if kind == "reference":
+        ref = RefHarness()
+        hs = []
+        made = {}
+        for c in range(ncol):
+            key = (tuple(soils[c]), tuple(layers[c]))
+            if key not in made:
+                txt = base.read_text().replace("layer_soil_type=1,2,3", "layer_soil_type=" + ",".join(map(str, soils[c])))
+                txt = "\n".join(("layer_thickness=" + ",".join(map(str, layers[c])) + "[cm]") if l.startswith("layer_thickness=") else l
+                                for l in txt.splitlines()) + "\n"
+                p = Path(cfg_dir) / f"w{wid}_{len(made)}.txt"
+                p.write_text(txt)
+                made[key] = p
+            hs.append(ref.create(made[key]))
+        arr = (C.c_void_p * ncol)(*hs)
+        sumq = C.c_double(0.0)
+
+        ref.lib.lgref_time_columns_series.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        ref.lib.lgref_time_columns_series.restype = C.c_double
+
+        def advance(P, E):
+            return ref.lib.lgref_time_columns_series(arr, ncol, P.shape[0], P.ctypes.data_as(C.POINTER(C.c_double)),
+                                                     E.ctypes.data_as(C.POINTER(C.c_double)), C.byref(sumq))
+    else:
+        orc = Oracle()
+        ps, ss = [], []
+        for c in range(ncol):
+            p = orc.params_from_config(base, layer_soil_type=[int(x) for x in soils[c]], layer_thickness=[float(x) for x in layers[c]])
+            ps.append(p)
+            ss.append(orc.new_state(p))
+
+        def advance(P, E):
+            t0 = time.perf_counter()
+            for c in range(ncol):
+                orc.lib.lgo_run_series(C.byref(ps[c]), C.byref(ss[c]), P.shape[0], np.ascontiguousarray(P[:, c]).ctypes.data_as(C.POINTER(C.c_double)),
+                                       np.ascontiguousarray(E[:, c]).ctypes.data_as(C.POINTER(C.c_double)), None, None, 0, None, None)
+            return time.perf_counter() - t0
+    hour = 0
+    if spin_h:
+        P, E = host_forcing(ncol, hour, spin_h, wid)
+        advance(P, E)
+        hour += spin_h
+    for nh, timed in blocks:
+        P, E = host_forcing(ncol, hour, nh, wid)
+        dt = advance(P, E)
+        hour += nh
+        if timed:
+            times.append(dt)
+    return times
+
+
+def run_cpu(kind: str, cores: int, cols_per_core: int, spin_h: int, blocks):
+    """blocks: list of (hours, timed?).  Returns per-timed-block wall seconds = max over workers."""
+    import multiprocessing as mp
+    tmp = tempfile.mkdtemp(prefix="lgar_cpu_")
+    write_workload_config(Path(tmp))
+    ctx = mp.get_context("fork")
+    jobs = [(kind, w, cols_per_core, w * cols_per_core, spin_h, blocks, tmp) for w in range(cores)]
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    per_block = np.max(np.array(res), axis=0)
+    return per_block
+
+
+def cpu_kind() -> str:
+    return "reference" if (ROOT / "oracle" / "_ref" / "liblgar_ref.so").exists() else "port"
+
+
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for i, nm in enumerate(names):
+                if len(s) > 2 + i and s[2 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--columns", type=int, default=1_250_000, help="columns per GPU")
+    ap.add_argument("--hours-per-step", type=int, default=24)
+    ap.add_argument("--spinup-hours", type=int, default=720)
+    ap.add_argument("--e2e-hours", type=int, default=48)
+    ap.add_argument("--cpu-cols-per-core", type=int, default=256)
+    ap.add_argument("--cpu-hours", type=int, default=1440)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    H = args.hours_per_step
+    workload = {"workload": "config5-shard", "columns_per_gpu": args.columns, "layers": 3, "giuh_ordinates": N_GIUH,
+                "hours_per_step": H, "spinup_hours": args.spinup_hours, "flags": "Phillipsburg_with_reservoir (CASAM)",
+                "soils": "12 parsed rows of vG_params_stat_nom_ordered.dat, i.i.d. per column and layer",
+                "forcing": "synthetic hourly, P(wet)=0.03, Exp(2.5 mm/h) cap 170, diurnal/seasonal PET",
+                "l2": "inputs larger than L2: state + one day of forcing > 1 GB per rank, nothing is reused between hours"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        kind = cpu_kind()
+        cores = host_cores()
+        cpc = args.cpu_cols_per_core
+        blocks = [(H, False)] * args.warmup + [(H, True)] * args.steps
+        per_block = run_cpu(kind, cores, cpc, min(args.spinup_hours, 240), blocks)
+        total_s = float(per_block.sum())
+        colsteps = cores * cpc * H * args.steps
+        val = colsteps / total_s
+        line = {"impl": "reference", "metric": "column-timesteps/sec", "value": val, "unit": "column-timesteps/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
+                "cpu_baseline": {"value": val, "unit": "column-timesteps/s", "cores": cores, "kind": kind,
+                                 "sample": f"{cores} processes x {cpc} columns x {H} h per step, spin-up {min(args.spinup_hours, 240)} h; "
+                                           "SetValue x2 -> Update -> GetValue(total_discharge) per column-step, no file I/O"},
+                "e2e": {"value": val, "unit": "column-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import lgar_c_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    ncol = args.columns
+    col0 = rank * ncol
+    tmp = Path(tempfile.mkdtemp(prefix="lgar_bench_"))
+    cfg = write_workload_config(tmp)
+    b = lgar_c_b200.BmiLGARBatch()
+    b.initialize(cfg, ncol, local_rank, column_soils(col0, ncol), column_layers(col0, ncol))
+    ext = torch.cuda.ExternalStream(b.get_stream(), device=dev)
+
+    # forcing ring on the device: R day-blocks, each [H][ncol]
+    R = max(2, min(args.warmup + args.steps, 16))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(777 * 1000003 + rank)
+    dP = torch.empty((R * H, ncol), dtype=torch.float64, device=dev)
+    dE = torch.empty((R * H, ncol), dtype=torch.float64, device=dev)
+    pet = torch.from_numpy(pet_series(np.arange(R * H))).to(dev)
+    for blk in range(R):
+        u1 = torch.rand((H, ncol), generator=gen, device=dev, dtype=torch.float64)
+        u2 = torch.rand((H, ncol), generator=gen, device=dev, dtype=torch.float64)
+        sl = slice(blk * H, (blk + 1) * H)
+        dP[sl] = torch.where(u1 < 0.03, torch.clamp(-2.5 * torch.log1p(-u2), max=170.0), torch.zeros_like(u1))
+        dE[sl] = pet[sl, None].expand(H, ncol)
+        del u1, u2
+    torch.cuda.synchronize()
+
+    def run_block(blk):
+        o = (blk % R) * H
+        b.update_steps_device(H, dP[o].data_ptr(), dE[o].data_ptr(), ncol)
+
+    blk = 0
+    for _ in range(max(0, args.spinup_hours // H)):
+        run_block(blk)
+        blk += 1
+    for _ in range(args.warmup):
+        run_block(blk)
+        blk += 1
+    b.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    launches0 = b.get_launch_count()
+    b.set_profiling(True)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ext)
+    for _ in range(args.steps):
+        run_block(blk)
+        blk += 1
+    ev1.record(ext)
+    ev1.synchronize()
+    barrier()
+    sampler.stop_flag.set()
+    ms = ev0.elapsed_time(ev1)
+    prof = b.get_profile()
+    b.set_profiling(False)
+    launches = b.get_launch_count() - launches0
+    st = b.get_status()
+    n_failed = int(np.count_nonzero(st & lgar_c_b200.STATUS_FAIL_MASK))
+
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    colsteps_total = world * ncol * H * args.steps
+    value = colsteps_total / (ms_max * 1e-3)
+
+    # ---- end-to-end through the BMI verbs with host buffers -------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        nh = args.e2e_hours
+        hP = torch.empty((nh, ncol), dtype=torch.float64).pin_memory()
+        hE = torch.empty((nh, ncol), dtype=torch.float64).pin_memory()
+        o = (blk % R) * H
+        hP.copy_(dP[o:o + nh] if o + nh <= R * H else dP[:nh])
+        hE.copy_(dE[o:o + nh] if o + nh <= R * H else dE[:nh])
+        hQ = torch.empty(ncol, dtype=torch.float64).pin_memory()
+        hPn, hEn, hQn = hP.numpy(), hE.numpy(), hQ.numpy()
+        for t in range(3):  # warm-up of the path
+            b.set_value("precipitation_rate", hPn[t]); b.set_value("potential_evapotranspiration_rate", hEn[t]); b.update(); b.get_value("total_discharge", hQn)
+        barrier()
+        t0 = time.perf_counter()
+        acc = 0.0
+        for t in range(3, nh):
+            b.set_value("precipitation_rate", hPn[t])
+            b.set_value("potential_evapotranspiration_rate", hEn[t])
+            b.update()
+            b.get_value("total_discharge", hQn)
+            acc += float(hQn[0])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * ncol * (nh - 3) / float(t_e.item()), "unit": "column-timesteps/s",
+               "h2d_bytes_per_step": 2 * 8 * ncol * H, "d2h_bytes_per_step": 8 * ncol * H,
+               "note": "per forcing hour: SetValue(precipitation_rate), SetValue(potential_evapotranspiration_rate) from pinned host, "
+                       "Update(), GetValue(total_discharge) to host; bytes are per bench step (one day) per rank"}
+
+    # ---- end-of-run gather of per-column summaries over NCCL (outside every timed region) -------
+    summary = torch.from_numpy(b.get_global_mass_balance(0, min(ncol, 65536))[:, [3, 15]].copy()).to(dev)
+    if dist is not None:
+        gathered = [torch.empty_like(summary) for _ in range(world)] if rank == 0 else None
+        dist.gather(summary, gathered, dst=0)
+        if rank == 0:
+            summary = torch.cat(gathered)
+    max_global_balance = float(summary[:, 1].abs().max().item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    nsteps_h = max(1, prof["steps"])
+    mean_fronts = prof["front_sum"] / (nsteps_h * ncol)
+    active_frac = prof["active_colsteps"] / (nsteps_h * ncol)
+    L, NG = 3, N_GIUH
+    B_full = 16 + 12 * L + 2 * (44 * mean_fronts + 88 + 8 * (NG + 1)) + 104      # 88*n_wf + 428
+    B_nofront = B_full - 2 * 44 * mean_fronts
+    ms_s, ms_a = prof["ms_stream"], prof["ms_active"]
+    dominant = "lgar_step_active_kernel" if ms_a >= ms_s else "lgar_step_stream_kernel"
+    if dominant == "lgar_step_active_kernel":
+        units = prof["active_colsteps"] / nsteps_h
+        bytes_per_launch = units * B_full
+        dur_s = ms_a * 1e-3 / nsteps_h
+    else:
+        units = ncol
+        bytes_per_launch = units * B_nofront
+        dur_s = ms_s * 1e-3 / nsteps_h
+    achieved = bytes_per_launch / dur_s / 1e9
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_unit": B_full if dominant.endswith("active_kernel") else B_nofront,
+                "units_per_launch": units, "avg_launch_ms": dur_s * 1e3,
+                "kernel_time_share": {"lgar_step_stream_kernel": ms_s / (ms_s + ms_a), "lgar_step_active_kernel": ms_a / (ms_s + ms_a)},
+                "whole_step": {"bytes_per_colstep": B_full, "achieved": (ncol * nsteps_h * B_full) / (ms * 1e-3) / 1e9,
+                               "frac": (ncol * nsteps_h * B_full) / (ms * 1e-3) / 1e9 / hbm_peak},
+                "mean_fronts": mean_fronts, "active_fraction": active_frac}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        kind = cpu_kind()
+        cores = host_cores()
+        cpc = args.cpu_cols_per_core
+        per_block = run_cpu(kind, cores, cpc, 240, [(args.cpu_hours, True)])
+        cpu = {"value": cores * cpc * args.cpu_hours / float(per_block.sum()), "unit": "column-timesteps/s", "cores": cores, "kind": kind,
+               "sample": f"{cores} processes x {cpc} columns x {args.cpu_hours} h of the same workload after a 240 h spin-up; "
+                         "SetValue x2 -> Update -> GetValue(total_discharge) per column-step, no file I/O"}
+
+    line = {"metric": "column-timesteps/sec", "value": value, "unit": "column-timesteps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload, "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "failed_columns": n_failed, "max_abs_global_mass_balance_cm": max_global_balance,
+            "target": {"colsteps_per_s_per_gpu": 1.25e9, "frac_of_target": value / world / 1.25e9}}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -182,6 +182,14 @@ int lgarb_set_force_all_active(lgarb_engine* e, int on);
  * the last step */
 int64_t lgarb_get_launch_count(const lgarb_engine* e);
 int64_t lgarb_get_last_active_count(lgarb_engine* e);
+/* Per-kernel device timing with CUDA events recorded on the engine's own stream (the only place
+ * they can see its kernels).  lgarb_set_profiling(e, 1) starts a fresh accumulation;
+ * lgarb_get_profile waits for the stream and returns out[6] = { total ms in the stream kernel, total
+ * ms in the active kernel, steps timed, sum over steps of columns routed to the active kernel,
+ * sum over steps and columns of the wetting-front count after the step, 0 }.  While profiling, each
+ * step also copies two counters D2D; leave it off outside measurements. */
+int lgarb_set_profiling(lgarb_engine* e, int on);
+int lgarb_get_profile(lgarb_engine* e, double* out6);
 /* the CUDA stream the engine launches on (cudaStream_t), for callers that time with events */
 void* lgarb_get_stream(lgarb_engine* e);
 

@@ -106,6 +106,8 @@ def _load():
         "lgarb_get_launch_count": ([vp], i64),
         "lgarb_get_last_active_count": ([vp], i64),
         "lgarb_get_stream": ([vp], vp),
+        "lgarb_set_profiling": ([vp, C.c_int], C.c_int),
+        "lgarb_get_profile": ([vp, dp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -357,6 +359,15 @@ class BmiLGARBatch:
 
     def get_last_active_count(self):
         return self._L.lgarb_get_last_active_count(self._h)
+
+    def set_profiling(self, on):
+        self._ck(self._L.lgarb_set_profiling(self._h, int(bool(on))))
+
+    def get_profile(self):
+        """dict(ms_stream, ms_active, steps, active_colsteps, front_sum) accumulated since set_profiling(True)."""
+        out = np.zeros(6)
+        self._ck(self._L.lgarb_get_profile(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return dict(ms_stream=out[0], ms_active=out[1], steps=int(out[2]), active_colsteps=int(out[3]), front_sum=int(out[4]))
 
     def get_stream(self) -> int:
         return int(self._L.lgarb_get_stream(self._h) or 0)

@@ -78,6 +78,13 @@ struct lgarb_engine {
   int force_all_active = 0;
   int64_t steps = 0;
   int64_t launches = 0;
+  // profiling (lgarb_set_profiling): event triples per step, resolved lazily
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  double prof_ms_stream = 0, prof_ms_active = 0;
+  int64_t prof_steps = 0;
+  unsigned long long* d_prof_acc = nullptr;  // [2]: sum nfront, sum active count
   double time_s = 0.0;
   std::string last_error;
 
@@ -100,6 +107,10 @@ struct lgarb_engine {
   }
   void release() {
     if (stream) cudaStreamSynchronize(stream);
+    for (cudaEvent_t x : ev_pool) cudaEventDestroy(x);
+    ev_pool.clear();
+    ev_used = 0;
+    profiling = false;
     for (void* p : allocs) cudaFree(p);
     allocs.clear();
     if (h_pinned) cudaFreeHost(h_pinned);
@@ -195,6 +206,7 @@ void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int d
   e->d_precip = e->dalloc<double>(st);
   e->d_pet = e->dalloc<double>(st);
   e->volstart = e->dalloc<double>(st);
+  e->d_prof_acc = e->dalloc<unsigned long long>(2);
   e->d_stage = e->dalloc<double>(st * LGAR_W);
   e->d_stage_i = e->dalloc<int32_t>(st);
   e->d_classes = e->dalloc<LgarColumnClass>(e->classes.size(), false);
@@ -265,7 +277,36 @@ void launch_step(lgarb_engine* e, const double* d_precip, const double* d_pet, c
   LgarDeviceState d = e->d;
   d.precip = d_precip;
   d.pet = d_pet;
-  CUDA_TRY(lgar_launch_step(e->cfg, d, sinks, e->active_blocks, e->force_all_active, e->stream));
+  cudaEvent_t* ev = nullptr;
+  if (e->profiling) {
+    if (e->ev_used + 3 > e->ev_pool.size()) {
+      if (e->ev_pool.size() >= 3 * 4096) {  // bound the pool: fold finished triples into the totals
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        for (size_t i = 0; i + 2 < e->ev_used; i += 3) {
+          float a = 0, b = 0;
+          cudaEventElapsedTime(&a, e->ev_pool[i], e->ev_pool[i + 1]);
+          cudaEventElapsedTime(&b, e->ev_pool[i + 1], e->ev_pool[i + 2]);
+          e->prof_ms_stream += a;
+          e->prof_ms_active += b;
+        }
+        e->ev_used = 0;
+      } else {
+        for (int i = 0; i < 3; i++) {
+          cudaEvent_t x;
+          CUDA_TRY(cudaEventCreate(&x));
+          e->ev_pool.push_back(x);
+        }
+      }
+    }
+    ev = e->ev_pool.data() + e->ev_used;
+    e->ev_used += 3;
+    e->prof_steps++;
+  }
+  CUDA_TRY(lgar_launch_step(e->cfg, d, sinks, e->active_blocks, e->force_all_active, e->stream, ev));
+  if (e->profiling) {
+    CUDA_TRY(lgar_launch_sum_fronts(e->d, e->d_prof_acc, e->stream));
+    e->launches += 1;
+  }
   e->launches += 2;
   e->steps++;
   e->time_s += e->cfg.forcing_resolution_h * 3600.0;  // bmi_lgar.cxx:359 summed over the sub-cycles
@@ -672,6 +713,41 @@ int64_t lgarb_get_last_active_count(lgarb_engine* e) {
   }
   return c;
 }
+int lgarb_set_profiling(lgarb_engine* e, int on) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->profiling = on != 0;
+    e->ev_used = 0;
+    e->prof_ms_stream = e->prof_ms_active = 0;
+    e->prof_steps = 0;
+    CUDA_TRY(cudaMemsetAsync(e->d_prof_acc, 0, 2 * sizeof(unsigned long long), e->stream));
+  });
+}
+
+int lgarb_get_profile(lgarb_engine* e, double* out6) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i + 2 < e->ev_used; i += 3) {
+      float a = 0, b = 0;
+      CUDA_TRY(cudaEventElapsedTime(&a, e->ev_pool[i], e->ev_pool[i + 1]));
+      CUDA_TRY(cudaEventElapsedTime(&b, e->ev_pool[i + 1], e->ev_pool[i + 2]));
+      e->prof_ms_stream += a;
+      e->prof_ms_active += b;
+    }
+    e->ev_used = 0;
+    unsigned long long acc[2];
+    d2h(e, acc, e->d_prof_acc, sizeof(acc));
+    out6[0] = e->prof_ms_stream;
+    out6[1] = e->prof_ms_active;
+    out6[2] = (double)e->prof_steps;
+    out6[3] = (double)acc[1];
+    out6[4] = (double)acc[0];
+    out6[5] = 0.0;
+  });
+}
+
 void* lgarb_get_stream(lgarb_engine* e) { return e ? (void*)e->stream : nullptr; }
 
 }  // extern "C"

@@ -72,13 +72,29 @@ __global__ void lgar_gather_layers_kernel(LgarDeviceState d, double* dst, int64_
 
 // ---- launch wrappers ------------------------------------------------------------------------------
 cudaError_t lgar_launch_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int active_blocks,
-                             int force_all_active, cudaStream_t stream) {
+                             int force_all_active, cudaStream_t stream, cudaEvent_t* ev) {
   cudaError_t err = cudaMemsetAsync(d.work_count, 0, 2 * sizeof(int32_t), stream);
   if (err != cudaSuccess) return err;
   const int threads = 256;
   const int64_t blocks = (d.ncol + threads - 1) / threads;
+  if (ev) cudaEventRecord(ev[0], stream);
   lgar_step_stream_kernel<<<(unsigned)blocks, threads, 0, stream>>>(cfg, d, sinks, force_all_active);
+  if (ev) cudaEventRecord(ev[1], stream);
   lgar_step_active_kernel<<<active_blocks, LGAR_ACTIVE_THREADS, 0, stream>>>(cfg, d, sinks);
+  if (ev) cudaEventRecord(ev[2], stream);
+  return cudaGetLastError();
+}
+
+__global__ void lgar_sum_fronts_kernel(LgarDeviceState d, unsigned long long* acc) {
+  unsigned long long s = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.ncol; i += (int64_t)gridDim.x * blockDim.x) s += (unsigned)d.nfront[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(acc, s);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(acc + 1, (unsigned long long)d.work_count[0]);
+}
+
+cudaError_t lgar_launch_sum_fronts(const LgarDeviceState& d, unsigned long long* acc, cudaStream_t stream) {
+  lgar_sum_fronts_kernel<<<296, 256, 0, stream>>>(d, acc);
   return cudaGetLastError();
 }
 

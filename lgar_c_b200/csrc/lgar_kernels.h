@@ -17,8 +17,11 @@ struct LgarSinks {
 };
 
 #ifndef LGAR_HOSTSIM
+// ev (nullable): three events recorded before the stream kernel, between the kernels, after the active kernel
 cudaError_t lgar_launch_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int active_blocks,
-                             int force_all_active, cudaStream_t stream);
+                             int force_all_active, cudaStream_t stream, cudaEvent_t* ev);
+// sum of d.nfront over all columns, added into *acc (unsigned long long, device)
+cudaError_t lgar_launch_sum_fronts(const LgarDeviceState& d, unsigned long long* acc, cudaStream_t stream);
 cudaError_t lgar_launch_gather_fronts(const LgarDeviceState& d, int which, double scale, double* dst, int64_t col0, int64_t ncol,
                                       cudaStream_t stream);
 cudaError_t lgar_launch_gather_layers(const LgarDeviceState& d, double* dst, int64_t col0, int64_t ncol, int L, cudaStream_t stream);

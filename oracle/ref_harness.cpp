@@ -231,6 +231,25 @@ double lgref_time_columns(void** hs, int ncol, int nsteps, const double* precip,
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Same loop with a per-column forcing series laid out [nsteps][ncol] (mm/h).
+double lgref_time_columns_series(void** hs, int ncol, int nsteps, const double* precip, const double* pet, double* sum_q) {
+  auto t0 = std::chrono::steady_clock::now();
+  double acc = 0.0;
+  for (int t = 0; t < nsteps; t++) {
+    for (int i = 0; i < ncol; i++) {
+      RefCol* c = (RefCol*)hs[i];
+      if (c->dead) continue;
+      if (lgref_update(c, precip[(size_t)t * ncol + i], pet[(size_t)t * ncol + i]) != 0) continue;
+      double q;
+      c->model.GetValue("total_discharge", &q);
+      acc += q;
+    }
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  *sum_q = acc;
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
 void lgref_destroy(void* h) {
   RefCol* c = (RefCol*)h;
   if (!c) return;
