@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--cpu-hours", type=int, default=1440)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--hourly", action="store_true", help="one stream+active kernel pair per forcing hour instead of the window kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -300,6 +301,8 @@ def main():
     cfg = write_workload_config(tmp)
     b = lgar_c_b200.BmiLGARBatch()
     b.initialize(cfg, ncol, local_rank, column_soils(col0, ncol), column_layers(col0, ncol))
+    if args.hourly:
+        b.set_window_mode(False)
     ext = torch.cuda.ExternalStream(b.get_stream(), device=dev)
 
     # forcing ring on the device: R day-blocks, each [H][ncol]
@@ -422,24 +425,28 @@ def main():
     L, NG = 3, N_GIUH
     B_full = 16 + 12 * L + 2 * (44 * mean_fronts + 88 + 8 * (NG + 1)) + 104      # 88*n_wf + 428
     B_nofront = B_full - 2 * 44 * mean_fronts
-    ms_s, ms_a = prof["ms_stream"], prof["ms_active"]
-    dominant = "lgar_step_active_kernel" if ms_a >= ms_s else "lgar_step_stream_kernel"
-    if dominant == "lgar_step_active_kernel":
-        units = prof["active_colsteps"] / nsteps_h
-        bytes_per_launch = units * B_full
-        dur_s = ms_a * 1e-3 / nsteps_h
+    ms_s, ms_a, ms_w = prof["ms_stream"], prof["ms_active"], prof["ms_window"]
+    if ms_w > 0:  # window mode: one kernel per bench step (H forcing hours for every column)
+        dominant = "lgar_window_kernel"
+        units = ncol * H
+        B_unit = B_full
+        dur_s = ms_w * 1e-3 / args.steps
+        share = {"lgar_window_kernel": 1.0}
     else:
-        units = ncol
-        bytes_per_launch = units * B_nofront
-        dur_s = ms_s * 1e-3 / nsteps_h
+        dominant = "lgar_step_active_kernel" if ms_a >= ms_s else "lgar_step_stream_kernel"
+        if dominant == "lgar_step_active_kernel":
+            units, B_unit, dur_s = prof["active_colsteps"] / nsteps_h, B_full, ms_a * 1e-3 / nsteps_h
+        else:
+            units, B_unit, dur_s = ncol, B_nofront, ms_s * 1e-3 / nsteps_h
+        share = {"lgar_step_stream_kernel": ms_s / (ms_s + ms_a), "lgar_step_active_kernel": ms_a / (ms_s + ms_a)}
+    bytes_per_launch = units * B_unit
     achieved = bytes_per_launch / dur_s / 1e9
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_unit": B_full if dominant.endswith("active_kernel") else B_nofront,
-                "units_per_launch": units, "avg_launch_ms": dur_s * 1e3,
-                "kernel_time_share": {"lgar_step_stream_kernel": ms_s / (ms_s + ms_a), "lgar_step_active_kernel": ms_a / (ms_s + ms_a)},
-                "whole_step": {"bytes_per_colstep": B_full, "achieved": (ncol * nsteps_h * B_full) / (ms * 1e-3) / 1e9,
-                               "frac": (ncol * nsteps_h * B_full) / (ms * 1e-3) / 1e9 / hbm_peak},
-                "mean_fronts": mean_fronts, "active_fraction": active_frac}
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_unit": B_unit,
+                "units_per_launch": units, "avg_launch_ms": dur_s * 1e3, "kernel_time_share": share,
+                "mean_fronts": mean_fronts, "active_fraction": active_frac,
+                "note": "unit = one column-timestep; B = 88*mean_fronts + 428 bytes (SURVEY.md 8d). The kernel is FP64-latency/divergence "
+                        "bound, not HBM bound: see DESIGN.md section 7"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

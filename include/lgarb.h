@@ -178,6 +178,10 @@ int lgarb_get_soil_row(const lgarb_engine* e, int soil, double* out10);
 /* Test hook: route every column through the active kernel (no cached-flux fast path), to check
  * that the two kernels implement the same Update(). */
 int lgarb_set_force_all_active(lgarb_engine* e, int on);
+/* Scheduling of lgarb_update_steps_device: 1 (default) = one window-kernel launch for the whole run,
+ * every column advancing on its own time pointer; 0 = one stream+active kernel pair per forcing
+ * hour (what lgarb_update does).  Both produce identical results. */
+int lgarb_set_window_mode(lgarb_engine* e, int on);
 /* number of kernels launched by this engine so far, and columns routed to the active kernel in
  * the last step */
 int64_t lgarb_get_launch_count(const lgarb_engine* e);
@@ -186,7 +190,7 @@ int64_t lgarb_get_last_active_count(lgarb_engine* e);
  * they can see its kernels).  lgarb_set_profiling(e, 1) starts a fresh accumulation;
  * lgarb_get_profile waits for the stream and returns out[6] = { total ms in the stream kernel, total
  * ms in the active kernel, steps timed, sum over steps of columns routed to the active kernel,
- * sum over steps and columns of the wetting-front count after the step, 0 }.  While profiling, each
+ * sum over steps and columns of the wetting-front count after the step, total ms in window kernels }.  While profiling, each
  * step also copies two counters D2D; leave it off outside measurements. */
 int lgarb_set_profiling(lgarb_engine* e, int on);
 int lgarb_get_profile(lgarb_engine* e, double* out6);

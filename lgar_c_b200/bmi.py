@@ -103,6 +103,7 @@ def _load():
         "lgarb_get_global_mass_balance": ([vp, i64, i64, vp], C.c_int),
         "lgarb_get_soil_row": ([vp, C.c_int, dp], C.c_int),
         "lgarb_set_force_all_active": ([vp, C.c_int], C.c_int),
+        "lgarb_set_window_mode": ([vp, C.c_int], C.c_int),
         "lgarb_get_launch_count": ([vp], i64),
         "lgarb_get_last_active_count": ([vp], i64),
         "lgarb_get_stream": ([vp], vp),
@@ -354,6 +355,9 @@ class BmiLGARBatch:
     def set_force_all_active(self, on):
         self._ck(self._L.lgarb_set_force_all_active(self._h, int(bool(on))))
 
+    def set_window_mode(self, on):
+        self._ck(self._L.lgarb_set_window_mode(self._h, int(bool(on))))
+
     def get_launch_count(self):
         return self._L.lgarb_get_launch_count(self._h)
 
@@ -367,7 +371,8 @@ class BmiLGARBatch:
         """dict(ms_stream, ms_active, steps, active_colsteps, front_sum) accumulated since set_profiling(True)."""
         out = np.zeros(6)
         self._ck(self._L.lgarb_get_profile(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
-        return dict(ms_stream=out[0], ms_active=out[1], steps=int(out[2]), active_colsteps=int(out[3]), front_sum=int(out[4]))
+        return dict(ms_stream=out[0], ms_active=out[1], steps=int(out[2]), active_colsteps=int(out[3]), front_sum=int(out[4]),
+                    ms_window=out[5])
 
     def get_stream(self) -> int:
         return int(self._L.lgarb_get_stream(self._h) or 0)

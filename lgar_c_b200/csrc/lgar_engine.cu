@@ -75,6 +75,12 @@ struct lgarb_engine {
   size_t h_pinned_bytes = 0;
   cudaStream_t stream = nullptr;
   int active_blocks = 0;
+  int window_blocks = 0;
+  int use_window = 1;          // multi-step runs go through the window kernel (0: hour-by-hour kernel pairs)
+  int32_t* d_tile_counter = nullptr;
+  cudaEvent_t win_ev[2] = {nullptr, nullptr};
+  double prof_ms_window = 0;
+  int64_t prof_windows = 0;
   int force_all_active = 0;
   int64_t steps = 0;
   int64_t launches = 0;
@@ -108,6 +114,10 @@ struct lgarb_engine {
   void release() {
     if (stream) cudaStreamSynchronize(stream);
     for (cudaEvent_t x : ev_pool) cudaEventDestroy(x);
+    for (int i = 0; i < 2; i++) {
+      if (win_ev[i]) cudaEventDestroy(win_ev[i]);
+      win_ev[i] = nullptr;
+    }
     ev_pool.clear();
     ev_used = 0;
     profiling = false;
@@ -207,6 +217,7 @@ void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int d
   e->d_pet = e->dalloc<double>(st);
   e->volstart = e->dalloc<double>(st);
   e->d_prof_acc = e->dalloc<unsigned long long>(2);
+  e->d_tile_counter = e->dalloc<int32_t>(1);
   e->d_stage = e->dalloc<double>(st * LGAR_W);
   e->d_stage_i = e->dalloc<int32_t>(st);
   e->d_classes = e->dalloc<LgarColumnClass>(e->classes.size(), false);
@@ -267,6 +278,9 @@ void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int d
   int per_sm = lgar_active_kernel_max_blocks_per_sm();
   if (per_sm < 1) per_sm = 1;
   e->active_blocks = prop.multiProcessorCount * per_sm;  // persistent: a whole number of waves of the SM count
+  int wper_sm = lgar_window_kernel_max_blocks_per_sm();
+  if (wper_sm < 1) wper_sm = 1;
+  e->window_blocks = prop.multiProcessorCount * wper_sm;
   e->steps = 0;
   e->launches = 0;
   e->time_s = 0.0;
@@ -481,13 +495,52 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
     require_init(e);
     if (n_steps < 0 || !d_precip || !d_pet || series_stride < e->ncol) throw std::runtime_error("bad forcing series");
     if ((d_sinks || d_nfronts_sink) && sink_stride < e->ncol) throw std::runtime_error("bad sink stride");
-    for (int64_t t = 0; t < n_steps; t++) {
-      LgarSinks sinks;
-      for (int k = 0; k < LGAR_NOUT; k++) sinks.p[k] = (d_sinks && d_sinks[k]) ? d_sinks[k] + t * sink_stride : nullptr;
-      launch_step(e, d_precip + t * series_stride, d_pet + t * series_stride, sinks);
-      if (d_nfronts_sink)
-        CUDA_TRY(cudaMemcpyAsync(d_nfronts_sink + t * sink_stride, e->d.nfront, (size_t)e->ncol * sizeof(int32_t), cudaMemcpyDeviceToDevice,
-                                 e->stream));
+    if (!e->use_window) {
+      for (int64_t t = 0; t < n_steps; t++) {
+        LgarSinks sinks;
+        for (int k = 0; k < LGAR_NOUT; k++) sinks.p[k] = (d_sinks && d_sinks[k]) ? d_sinks[k] + t * sink_stride : nullptr;
+        launch_step(e, d_precip + t * series_stride, d_pet + t * series_stride, sinks);
+        if (d_nfronts_sink)
+          CUDA_TRY(cudaMemcpyAsync(d_nfronts_sink + t * sink_stride, e->d.nfront, (size_t)e->ncol * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                                   e->stream));
+      }
+    } else {
+      for (int64_t t0 = 0; t0 < n_steps; t0 += LGAR_MAX_WINDOW) {
+        const int K = (int)std::min<int64_t>(LGAR_MAX_WINDOW, n_steps - t0);
+        LgarWindow w;
+        memset(&w, 0, sizeof(w));
+        w.precip = d_precip + t0 * series_stride;
+        w.pet = d_pet + t0 * series_stride;
+        w.series_stride = series_stride;
+        for (int k = 0; k < LGAR_NOUT; k++) w.sinks.p[k] = (d_sinks && d_sinks[k]) ? d_sinks[k] + t0 * sink_stride : nullptr;
+        w.sink_stride = sink_stride;
+        w.nf_sink = d_nfronts_sink ? d_nfronts_sink + t0 * sink_stride : nullptr;
+        w.K = K;
+        w.force_all_active = e->force_all_active;
+        w.tile_counter = e->d_tile_counter;
+        w.prof = e->profiling ? e->d_prof_acc : nullptr;
+        if (e->profiling) {
+          if (!e->win_ev[0]) {
+            CUDA_TRY(cudaEventCreate(&e->win_ev[0]));
+            CUDA_TRY(cudaEventCreate(&e->win_ev[1]));
+          } else if (e->prof_windows > 0) {  // fold the previous window's time before reusing the events
+            CUDA_TRY(cudaEventSynchronize(e->win_ev[1]));
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, e->win_ev[0], e->win_ev[1]));
+            e->prof_ms_window += ms;
+          }
+          CUDA_TRY(cudaEventRecord(e->win_ev[0], e->stream));
+        }
+        CUDA_TRY(lgar_launch_window(e->cfg, e->d, w, e->window_blocks, e->stream));
+        if (e->profiling) {
+          CUDA_TRY(cudaEventRecord(e->win_ev[1], e->stream));
+          e->prof_windows++;
+          e->prof_steps += K;
+        }
+        e->launches += 1;
+        e->steps += K;
+        e->time_s += K * e->cfg.forcing_resolution_h * 3600.0;
+      }
     }
   });
 }
@@ -702,6 +755,7 @@ int lgarb_get_soil_row(const lgarb_engine* e, int soil, double* o) {
 }
 
 int lgarb_set_force_all_active(lgarb_engine* e, int on) { LGARB_GUARD(e, e->force_all_active = on ? 1 : 0); }
+int lgarb_set_window_mode(lgarb_engine* e, int on) { LGARB_GUARD(e, e->use_window = on ? 1 : 0); }
 int64_t lgarb_get_launch_count(const lgarb_engine* e) { return e ? e->launches : -1; }
 int64_t lgarb_get_last_active_count(lgarb_engine* e) {
   if (!e || !e->initialized) return -1;
@@ -720,6 +774,8 @@ int lgarb_set_profiling(lgarb_engine* e, int on) {
     e->profiling = on != 0;
     e->ev_used = 0;
     e->prof_ms_stream = e->prof_ms_active = 0;
+    e->prof_ms_window = 0;
+    e->prof_windows = 0;
     e->prof_steps = 0;
     CUDA_TRY(cudaMemsetAsync(e->d_prof_acc, 0, 2 * sizeof(unsigned long long), e->stream));
   });
@@ -744,7 +800,13 @@ int lgarb_get_profile(lgarb_engine* e, double* out6) {
     out6[2] = (double)e->prof_steps;
     out6[3] = (double)acc[1];
     out6[4] = (double)acc[0];
-    out6[5] = 0.0;
+    if (e->prof_windows > 0) {  // the last window's events have not been folded yet
+      float ms = 0;
+      CUDA_TRY(cudaEventElapsedTime(&ms, e->win_ev[0], e->win_ev[1]));
+      e->prof_ms_window += ms;
+      e->prof_windows = 0;
+    }
+    out6[5] = e->prof_ms_window;
   });
 }
 

@@ -50,6 +50,80 @@ __global__ void __launch_bounds__(LGAR_ACTIVE_THREADS) lgar_step_active_kernel(L
   }
 }
 
+// ---- window kernel ----------------------------------------------------------------------------------
+// K forcing hours per launch, no grid-wide or block-wide barrier anywhere.  A warp owns a tile of
+// LGAR_TILE consecutive columns at a time (tiles are handed out by an atomic counter, so SMs stay
+// busy until the last tile).  Every column of the tile carries its own time pointer:
+//   ADVANCE  each lane walks its columns through the hours that need no flux computation (scalars in
+//            registers across hours, fronts untouched) until the column needs an active step;
+//   COLLECT  the columns now waiting at an active step are compacted into a ready list (ballot);
+//   PROCESS  the ready list is worked off 32 columns at a time, one full Update() per lane.
+// After the first round every column of the tile sits at an active step of its own hour, so PROCESS
+// batches are full warps.  A straggler (the trip counts are heavy tailed: median 7, max > 20 000
+// theta evaluations per active step) delays only its own tile, never the other 147 SMs.
+__global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_window_kernel(LgarConfig cfg, LgarDeviceState d, LgarWindow w) {
+  __shared__ unsigned short s_t[LGAR_WINDOW_THREADS / 32][LGAR_TILE];
+  __shared__ unsigned short s_ready[LGAR_WINDOW_THREADS / 32][LGAR_TILE];
+  __shared__ unsigned char s_flag[LGAR_WINDOW_THREADS / 32][LGAR_TILE];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned short* tcur = s_t[wid];
+  unsigned short* ready = s_ready[wid];
+  unsigned char* flag = s_flag[wid];   // 0 idle, 1 ready, 2 done
+  const int64_t ntiles = (d.ncol + LGAR_TILE - 1) / LGAR_TILE;
+  unsigned long long front_sum = 0, active_sum = 0;
+  unsigned long long* fsp = w.prof ? &front_sum : nullptr;
+  for (;;) {
+    int tile = 0;
+    if (lane == 0) tile = atomicAdd(w.tile_counter, 1);
+    tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+    if (tile >= ntiles) break;
+    const int64_t c0 = (int64_t)tile * LGAR_TILE;
+    for (int j = lane; j < LGAR_TILE; j += 32) {
+      tcur[j] = 0;
+      flag[j] = (c0 + j < d.ncol) ? 0 : 2;
+    }
+    __syncwarp();
+    for (;;) {
+      for (int j = lane; j < LGAR_TILE; j += 32) {  // ADVANCE
+        if (flag[j] == 0) {
+          const int t = lg_advance_column(cfg, d, w, c0 + j, tcur[j], fsp);
+          tcur[j] = (unsigned short)t;
+          flag[j] = (t < w.K) ? 1 : 2;
+        }
+      }
+      __syncwarp();
+      int n = 0;
+      for (int base = 0; base < LGAR_TILE; base += 32) {  // COLLECT
+        const int j = base + lane;
+        const bool r = flag[j] == 1;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, r);
+        if (r) ready[n + __popc(m & ((1u << lane) - 1))] = (unsigned short)j;
+        n += __popc(m);
+      }
+      __syncwarp();
+      if (n == 0) break;
+      active_sum += (lane == 0) ? n : 0;
+      for (int b = 0; b < n; b += 32) {  // PROCESS
+        const int i = b + lane;
+        if (i < n) {
+          const int j = ready[i];
+          lg_active_column_at(cfg, d, w, c0 + j, tcur[j], fsp);
+          tcur[j] = (unsigned short)(tcur[j] + 1);
+          flag[j] = 0;
+        }
+        __syncwarp();
+      }
+    }
+  }
+  if (w.prof) {
+    for (int o = 16; o > 0; o >>= 1) front_sum += __shfl_down_sync(0xFFFFFFFFu, front_sum, o);
+    if (lane == 0) {
+      atomicAdd(w.prof, front_sum);
+      atomicAdd(w.prof + 1, active_sum);
+    }
+  }
+}
+
 // Gather per-front BMI arrays into a caller-facing [ncol][LGAR_W] layout (pad = NaN).
 __global__ void lgar_gather_fronts_kernel(LgarDeviceState d, int which, double scale, double* dst, int64_t col0, int64_t ncol) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,6 +183,19 @@ cudaError_t lgar_launch_gather_layers(const LgarDeviceState& d, double* dst, int
   const int64_t n = ncol * L;
   lgar_gather_layers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d, dst, col0, ncol, L);
   return cudaGetLastError();
+}
+
+cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream) {
+  cudaError_t err = cudaMemsetAsync(w.tile_counter, 0, sizeof(int32_t), stream);
+  if (err != cudaSuccess) return err;
+  lgar_window_kernel<<<blocks, LGAR_WINDOW_THREADS, 0, stream>>>(cfg, d, w);
+  return cudaGetLastError();
+}
+
+int lgar_window_kernel_max_blocks_per_sm() {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lgar_window_kernel, LGAR_WINDOW_THREADS, 0);
+  return nb;
 }
 
 int lgar_active_kernel_max_blocks_per_sm() {

@@ -16,7 +16,27 @@ struct LgarSinks {
   double* p[LGAR_NOUT];
 };
 
+// One launch of the window kernel: K consecutive forcing hours for every column.
+struct LgarWindow {
+  const double* precip;   // [K][series_stride] mm/h
+  const double* pet;
+  int64_t series_stride;
+  LgarSinks sinks;        // each non-null: [K][sink_stride]
+  int64_t sink_stride;
+  int32_t* nf_sink;       // nullable: [K][sink_stride] soil_num_wetting_fronts after each hour
+  int K;
+  int force_all_active;
+  int32_t* tile_counter;  // device, zeroed before launch
+  unsigned long long* prof;  // nullable: [0] += sum of front counts, [1] += active column-steps
+};
+#define LGAR_TILE 256            // columns owned by one warp at a time
+#define LGAR_WINDOW_THREADS 128
+#define LGAR_MAX_WINDOW 32768    // hours per launch (time pointers are 16 bit)
+
 #ifndef LGAR_HOSTSIM
+cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream);
+int lgar_window_kernel_max_blocks_per_sm();
+
 // ev (nullable): three events recorded before the stream kernel, between the kernels, after the active kernel
 cudaError_t lgar_launch_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int active_blocks,
                              int force_all_active, cudaStream_t stream, cudaEvent_t* ev);

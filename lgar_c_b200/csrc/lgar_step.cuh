@@ -95,13 +95,13 @@ LG_FN void store_fronts(const LgarDeviceState& d, int64_t col, const LgFronts& f
 // GIUH convolution (giuh/giuh.c:12-39; input in cm, quirk Q12), outputs in metres
 // (bmi_lgar.cxx:808-893) and the cumulative volumes of the global balance (lgar.cxx:1162-1185).
 LG_FN void epilogue(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int64_t col,
-                                         const LgStepVols& v, int status) {
+                    const LgStepVols& v, int status, bool write_out = true) {
   const int64_t st = d.stride;
   if (status & LGAR_FAIL_MASK) {
     const double nan = LG_NAN;
 #pragma unroll
     for (int k = 0; k < LGAR_NOUT; k++) {
-      d.out[k * st + col] = nan;
+      if (write_out) d.out[k * st + col] = nan;
       if (sinks.p[k]) sinks.p[k][col] = nan;
     }
     return;
@@ -132,7 +132,7 @@ LG_FN void epilogue(const LgarConfig& cfg, const LgarDeviceState& d, const LgarS
   o[LGAR_OUT_CR_STORAGE] = v.volCRend * cm_to_m;
 #pragma unroll
   for (int k = 0; k < LGAR_NOUT; k++) {
-    d.out[k * st + col] = o[k];
+    if (write_out) d.out[k * st + col] = o[k];
     if (sinks.p[k]) sinks.p[k][col] = o[k];
   }
   double* cu = d.cum + col;
@@ -176,13 +176,13 @@ LG_FN void adjust_forcing(const LgarConfig& cfg, double& P, double& E, int& stat
 }
 
 // Invalid soil type: Q = precip (bmi_lgar.cxx:145-179)
-LG_FN void step_invalid(const LgarDeviceState& d, const LgarSinks& sinks, int64_t col, double P) {
+LG_FN void step_invalid(const LgarDeviceState& d, const LgarSinks& sinks, int64_t col, double P, bool write_out = true) {
   const int64_t st = d.stride;
   const double pm = P * 0.001;
 #pragma unroll
   for (int k = 0; k < LGAR_NOUT; k++) {
     double val = (k == LGAR_OUT_PRECIP || k == LGAR_OUT_RUNOFF || k == LGAR_OUT_Q) ? pm : 0.0;
-    d.out[k * st + col] = val;
+    if (write_out) d.out[k * st + col] = val;
     if (sinks.p[k]) sinks.p[k][col] = val;
   }
   double* cu = d.cum + col;
@@ -224,7 +224,7 @@ LG_FN bool lg_stream_column(const LgarConfig& cfg, const LgarDeviceState& d, con
 }
 
 // Body of lgar_step_active_kernel for one work-list entry: the full Update() of one column.
-LG_FN void lg_active_column(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int64_t col) {
+LG_FN_NOINLINE void lg_active_column(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int64_t col, bool write_out = true) {
   const LgarColumnClass* cls = d.classes + d.class_id[col];
   double P = d.precip[col], E = d.pet[col];
   LgScalars s;
@@ -248,7 +248,75 @@ LG_FN void lg_active_column(const LgarConfig& cfg, const LgarDeviceState& d, con
     store_scalars(d, col, s, true);
     store_fronts(d, col, f);
   }
-  epilogue(cfg, d, sinks, col, v, s.status);
+  epilogue(cfg, d, sinks, col, v, s.status, write_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Window stepping: K forcing hours per launch with per-column time pointers (lgar_window_kernel).
+// ------------------------------------------------------------------------------------------------
+LG_FN LgarSinks lg_sinks_at(const LgarWindow& w, int t) {
+  LgarSinks s;
+#pragma unroll
+  for (int k = 0; k < LGAR_NOUT; k++) s.p[k] = w.sinks.p[k] ? w.sinks.p[k] + (int64_t)t * w.sink_stride : nullptr;
+  return s;
+}
+
+// Advance one column from hour t through every step that needs no flux computation (cached-flux
+// replay, invalid soil, failed column), scalars held in registers across hours.  Returns the hour at
+// which the column needs an active step, or w.K when it reached the end of the window.
+LG_FN_NOINLINE int lg_advance_column(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int64_t col, int t,
+                            unsigned long long* front_sum) {
+  const LgarColumnClass* cls = d.classes + d.class_id[col];
+  const int K = w.K;
+  if (cls->invalid_soil_type) {
+    for (; t < K; t++) {
+      const LgarSinks sk = lg_sinks_at(w, t);
+      step_invalid(d, sk, col, w.precip[(int64_t)t * w.series_stride + col], t == K - 1);
+      if (w.nf_sink) w.nf_sink[(int64_t)t * w.sink_stride + col] = 0;
+    }
+    return K;
+  }
+  LgScalars s;
+  load_scalars(d, col, s);
+  const int nf = (w.nf_sink || front_sum) ? d.nfront[col] : 0;
+  bool dirty = false;
+  for (; t < K; t++) {
+    double P = w.precip[(int64_t)t * w.series_stride + col], E = w.pet[(int64_t)t * w.series_stride + col];
+    LgStepVols v;
+    zero_vols(v);
+    if (!(s.status & LGAR_FAIL_MASK)) {
+      const LgPrologue pro = lg_prologue(cfg, s, P);
+      if (!pro.cache_fluxes || w.force_all_active) break;
+      if (cfg.adaptive_timestep) s.timestep_h = pro.subtimestep_h;
+      s.cache_fluxes = 1;
+      s.cache_count = pro.cache_count;
+      adjust_forcing(cfg, P, E, s.status);
+      lg_step_cached(cfg, s, pro, P, E, v);
+      if (!(fabs(v.local_mb) <= cfg.mbal_tol)) s.status |= (isnan(v.local_mb) ? LGAR_FAIL_NAN : LGAR_FAIL_MBAL);
+      dirty = true;
+    }
+    const LgarSinks sk = lg_sinks_at(w, t);
+    epilogue(cfg, d, sk, col, v, s.status, t == K - 1);
+    if (w.nf_sink) w.nf_sink[(int64_t)t * w.sink_stride + col] = nf;
+    if (front_sum) *front_sum += (unsigned)nf;
+  }
+  if (dirty) store_scalars(d, col, s, false);
+  return t;
+}
+
+// The full Update() of one column at hour t of the window.
+LG_FN void lg_active_column_at(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int64_t col, int t,
+                               unsigned long long* front_sum) {
+  LgarDeviceState dd = d;
+  dd.precip = w.precip + (int64_t)t * w.series_stride;
+  dd.pet = w.pet + (int64_t)t * w.series_stride;
+  const LgarSinks sk = lg_sinks_at(w, t);
+  lg_active_column(cfg, dd, sk, col, t == w.K - 1);
+  if (w.nf_sink || front_sum) {
+    const int nf = d.nfront[col];
+    if (w.nf_sink) w.nf_sink[(int64_t)t * w.sink_stride + col] = nf;
+    if (front_sum) *front_sum += (unsigned)nf;
+  }
 }
 
 #endif  // LGAR_STEP_CUH

@@ -56,6 +56,36 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
     LgarSinks sinks;
     memset(&sinks, 0, sizeof(sinks));
     int t;
+    if (force_all_active >= 2) {
+      // window-kernel emulation (one-column tile): advance through cached hours, then one active step
+      std::vector<double> sk((size_t)LGAR_NOUT * nsteps, 0.0);
+      std::vector<int32_t> nfs((size_t)nsteps, 0);
+      LgarWindow w;
+      memset(&w, 0, sizeof(w));
+      w.precip = P; w.pet = E; w.series_stride = 1; w.sink_stride = 1; w.K = nsteps; w.force_all_active = (force_all_active == 3);
+      for (int k = 0; k < LGAR_NOUT; k++) w.sinks.p[k] = sk.data() + (size_t)k * nsteps;
+      w.nf_sink = nfs.data();
+      int tt = 0;
+      while (tt < nsteps) {
+        tt = lg_advance_column(cfg, d, w, 0, tt, nullptr);
+        if (tt < nsteps) { lg_active_column_at(cfg, d, w, 0, tt, nullptr); tt++; }
+      }
+      for (t = 0; t < nsteps; t++) {
+        if (scalars) for (int k = 0; k < LGAR_NOUT; k++) scalars[(size_t)t * LGAR_NOUT + k] = sk[(size_t)k * nsteps + t];
+        if (nfronts) nfronts[t] = nfs[t];
+      }
+      if (fronts) {  // only the final front list is available in window mode: store it at the last step
+        t = nsteps - 1;
+        for (int i = 0; i < nf && i < cap; i++) {
+          double* q = fronts + ((size_t)t * cap + i) * 5;
+          q[0] = depth[i]; q[1] = theta[i]; q[2] = psi[i]; q[3] = K[i]; q[4] = dzdt[i];
+          int nib = (int)((fflags >> (4 * i)) & 0xF);
+          flags[(size_t)t * cap + i] = (nib & 7) | ((nib >> 3) << 8);
+        }
+      }
+      if (status_out) *status_out = status;
+      return nsteps;
+    }
     for (t = 0; t < nsteps; t++) {
       p1 = P[t]; e1 = E[t];
       if (lg_stream_column(cfg, d, sinks, 0, force_all_active)) lg_active_column(cfg, d, sinks, 0);

@@ -108,6 +108,38 @@ def test_two_kernel_split_equals_single_path(cuda_device, tmp_path):
         assert np.array_equal(f1[k], f2[k], equal_nan=True)
 
 
+def test_window_kernel_equals_hourly_kernels(cuda_device, tmp_path):
+    """lgarb_update_steps_device in window mode (one launch, per-column time pointers) vs one kernel pair
+    per hour: identical per-step outputs, front counts and final state."""
+    import torch
+    import lgar_c_b200
+    g = load_golden("Phillipsburg_with_reservoir")
+    cfg = config_for("Phillipsburg_with_reservoir", tmp_path)
+    ncol, T = 700, 1500                      # 700 columns: more than two warp tiles, last one ragged
+    shifts = (np.arange(ncol) * 7919) % 8760
+    Pm = np.ascontiguousarray(np.stack([np.roll(g["precip"], -int(s))[:T] for s in shifts], axis=1))
+    Em = np.ascontiguousarray(np.stack([np.roll(g["pet"], -int(s))[:T] for s in shifts], axis=1))
+    res = []
+    for window in (True, False):
+        b = lgar_c_b200.BmiLGARBatch()
+        b.initialize(cfg, ncol)
+        b.set_window_mode(window)
+        dP, dE = torch.from_numpy(Pm).cuda(), torch.from_numpy(Em).cuda()
+        sinks = torch.zeros((12, T, ncol), dtype=torch.float64, device="cuda")
+        nfs = torch.zeros((T, ncol), dtype=torch.int32, device="cuda")
+        # two consecutive windows, to cross a window boundary
+        for t0, n in ((0, 900), (900, T - 900)):
+            b.update_steps_device(n, dP[t0].data_ptr(), dE[t0].data_ptr(), ncol,
+                                  {nm: sinks[k, t0].data_ptr() for k, nm in enumerate(lgar_c_b200.OUTPUT_SCALARS)}, ncol, nfs[t0].data_ptr())
+        b.synchronize()
+        res.append((sinks.cpu().numpy(), nfs.cpu().numpy(), b.get_fronts(), b.get_global_mass_balance(), b.get_value("soil_storage"),
+                    b.get_current_time()))
+    (s1, n1, f1, m1, v1, t1), (s2, n2, f2, m2, v2, t2) = res
+    assert np.array_equal(n1, n2) and np.array_equal(s1, s2) and np.array_equal(m1, m2) and np.array_equal(v1, v2) and t1 == t2
+    for k in ("depth", "theta", "psi", "K", "dzdt", "layer", "to_bottom", "nfronts"):
+        assert np.array_equal(f1[k], f2[k], equal_nan=True)
+
+
 def test_heterogeneous_batch_against_oracle(cuda_device, oracle, tmp_path):
     """BASELINE config 3 in small: Bushland layering, per-column soil triples drawn from the PARSED
     vG_params_stat_nom_ordered.dat (quirk Q2), per-column circular time shift of the forcing."""

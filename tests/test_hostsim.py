@@ -39,6 +39,21 @@ def run(lib, cfg, P, E, force, cap=16):
     return done, scal, nf, fr, fl, st.value
 
 
+@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("name", STANDARD + RANDOM)
+def test_window_stepping_equals_hourly_stepping(hostsim, name, mode, tmp_path):
+    """The window kernel's per-column functions (advance through cached hours in registers, active step
+    at the column's own hour) must reproduce hour-by-hour stepping bit for bit."""
+    g = load_golden(name)
+    n = min(len(g["precip"]), 2000)
+    cfg = config_for(name, tmp_path)
+    d0, s0, nf0, fr0, fl0, st0 = run(hostsim, cfg, g["precip"][:n], g["pet"][:n], 0)
+    d1, s1, nf1, fr1, fl1, st1 = run(hostsim, cfg, g["precip"][:n], g["pet"][:n], mode)
+    assert d0 == d1 == n and st0 == st1
+    assert np.array_equal(nf0, nf1) and np.array_equal(s0, s1)
+    assert np.array_equal(fr0[n - 1], fr1[n - 1]) and np.array_equal(fl0[n - 1], fl1[n - 1])
+
+
 @pytest.mark.parametrize("force", [0, 1])
 @pytest.mark.parametrize("name", STANDARD + RANDOM)
 def test_kernel_text_matches_golden(hostsim, name, force, tmp_path):
