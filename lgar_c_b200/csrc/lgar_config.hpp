@@ -269,6 +269,7 @@ inline LgarColumnClass make_class(const ParsedConfig& pc, const std::vector<Soil
     l.theta_min = theta_from_h(1.E7, s);
     l.thick = c.cum[k] - c.cum[k - 1];
     l.h_min = s.h_min;
+    l.ln_alpha = log(s.alpha);
     c.min_storage += s.theta_r * (c.cum[k] - c.cum[k - 1]);
     c.max_storage += s.theta_e * (c.cum[k] - c.cum[k - 1]);
     c.largest_Ks = fmax(s.Ksat, c.largest_Ks);

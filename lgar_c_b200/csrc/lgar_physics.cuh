@@ -22,7 +22,7 @@
 #include <cmath>
 #define LG_FN static inline
 #define LG_FN_NOINLINE static
-using std::fabs; using std::fmax; using std::fmin; using std::isinf; using std::isnan; using std::pow; using std::sqrt;
+using std::exp; using std::fabs; using std::fmax; using std::fmin; using std::isinf; using std::isnan; using std::log; using std::sqrt;
 #else
 #define LG_FN __device__ __forceinline__
 #define LG_FN_NOINLINE __device__ __noinline__
@@ -79,22 +79,33 @@ struct LgCtx {
 // ------------------------------------------------------------------------------------------------
 LG_FN double lg_sq(double x) { return x * x; }
 
-// calc_theta_from_h, soil_funcs.cxx:147-150
-LG_FN double lg_theta_from_h(double h, const LgarLayer& s) {
-  return 1.0 / (pow(1.0 + pow(s.alpha * h, s.n), s.m)) * s.de + s.theta_r;
+// x^y for x >= 0 as exp(y*log(x)).  The reference calls libm pow(); CUDA's pow() costs ~370 thread
+// instructions per call on sm_100a (ncu, profiles/r1_window_pow.md) because it carries log(x) in
+// extended precision.  exp(y*log x) is ~4x cheaper and differs from pow by <= |y log x| * 2^-52
+// (<= 1e-14 relative on this path) -- five orders below the 1e-9 parity bar and the same kind of
+// last-bits noise as CUDA pow vs glibc pow.  Edge cases used on the path: 0^y = 0 (y > 0), 0^-y = inf,
+// 1^y = 1, inf^y = inf, negative base = NaN -- all follow from log/exp.
+LG_FN double lg_pow(double x, double y) { return exp(y * log(x)); }
+
+// calc_theta_from_h with log(h) supplied: the psi search evaluates every layer at the same psi
+LG_FN double lg_theta_from_lnh(double lnh, const LgarLayer& s) {
+  const double y = exp(s.n * (s.ln_alpha + lnh));       // (alpha*h)^n
+  return exp(-s.m * log(1.0 + y)) * s.de + s.theta_r;   // 1/(1+y)^m * (theta_e-theta_r) + theta_r
 }
+// calc_theta_from_h, soil_funcs.cxx:147-150
+LG_FN double lg_theta_from_h(double h, const LgarLayer& s) { return lg_theta_from_lnh(log(h), s); }
 // calc_Se_from_h, soil_funcs.cxx:155-159
 LG_FN double lg_Se_from_h(double h, const LgarLayer& s) {
   if (fabs(h) < 1.0E-10) return 1.0;
-  return 1.0 / (pow(1.0 + pow(s.alpha * h, s.n), s.m));
+  return exp(-s.m * log(1.0 + exp(s.n * (s.ln_alpha + log(h)))));
 }
 // calc_K_from_Se, soil_funcs.cxx:164-167 (pow(x,2.0) -> x*x)
 LG_FN double lg_K_from_Se(double Se, const LgarLayer& s) {
-  return s.Ksat * sqrt(Se) * lg_sq(1.0 - pow(1.0 - pow(Se, s.inv_m), s.m));
+  return s.Ksat * sqrt(Se) * lg_sq(1.0 - lg_pow(1.0 - lg_pow(Se, s.inv_m), s.m));
 }
 // calc_h_from_Se, soil_funcs.cxx:172-179
 LG_FN double lg_h_from_Se(double Se, const LgarLayer& s) {
-  double r = s.inv_alpha * pow(pow(Se, s.neg_inv_m) - 1.0, s.inv_n);
+  double r = s.inv_alpha * lg_pow(lg_pow(Se, s.neg_inv_m) - 1.0, s.inv_n);
   if (r > 1.E20) r = 1.E20;
   return r;
 }
@@ -128,8 +139,8 @@ LG_FN_NOINLINE double lg_Geff(const LgarConfig& cfg, double theta1, double theta
   } else {
     double Se_f = lg_Se_from_theta(theta1, s);
     double Se_i = lg_Se_from_theta(theta2, s);
-    double pf = pow(Se_f, s.p_exp);
-    double Geff = s.H_c * (pow(Se_i, s.p_exp) - pf) / (1 - pf);
+    double pf = lg_pow(Se_f, s.p_exp);
+    double Geff = s.H_c * (lg_pow(Se_i, s.p_exp) - pf) / (1 - pf);
     if (isinf(Geff)) Geff = s.H_c;
     if (isnan(Geff)) Geff = s.H_c;
     return Geff;
@@ -298,11 +309,12 @@ LG_FN_NOINLINE double lg_theta_mass_balance(LgCtx& c, int layer_num, double psi_
       psi_loc = 0.0;
       factor = factor * 0.5;
     }
-    theta = lg_theta_from_h(psi_loc, sp);
+    const double lnpsi = log(psi_loc);
+    theta = lg_theta_from_lnh(lnpsi, sp);
     double mass_layers = 0.0;
     mass_layers += dz[layer_num] * (theta - dth[layer_num]);
     for (int k = 1; k < layer_num; k++) {
-      double theta_layer = lg_theta_from_h(psi_loc, cls.lay[k]);
+      double theta_layer = lg_theta_from_lnh(lnpsi, cls.lay[k]);
       mass_layers += dz[k] * (theta_layer - dth[k]);
     }
     new_mass = mass_layers;
@@ -1048,7 +1060,7 @@ LG_FN double lg_calc_CR_Q(const LgarConfig& cfg, double dt, double in_cm_per_h, 
   double input_slow = in_cm_per_h * cfg.frac_slow;
   double input_fast = in_cm_per_h - input_slow;
   double Q_fast = 0.0;
-  if (!(*fast < 0.01)) Q_fast = dt * (cfg.a * pow(*fast, cfg.b));
+  if (!(*fast < 0.01)) Q_fast = dt * (cfg.a * lg_pow(*fast, cfg.b));
   double delta_fast = dt * input_fast - Q_fast;
   if (*fast + delta_fast > 0.0) {
     *fast += delta_fast;
@@ -1057,7 +1069,7 @@ LG_FN double lg_calc_CR_Q(const LgarConfig& cfg, double dt, double in_cm_per_h, 
     *fast = 0.0;
   }
   double Q_slow = 0.0;
-  if (!(*slow < 0.01)) Q_slow = dt * (cfg.a_slow * pow(*slow, cfg.b_slow));
+  if (!(*slow < 0.01)) Q_slow = dt * (cfg.a_slow * lg_pow(*slow, cfg.b_slow));
   double delta_slow = dt * input_slow - Q_slow;
   if (*slow + delta_slow > 0.0) {
     *slow += delta_slow;

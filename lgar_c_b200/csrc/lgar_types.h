@@ -72,6 +72,7 @@ struct LgarLayer {
   double theta_min;  // theta(PSI_UPPER_LIM = 1e7)             (lgar.cxx:3222)
   double thick;      // cum[k]-cum[k-1]
   double h_min;      // kept for completeness (unused on the path, soil_funcs.cxx:59-61)
+  double ln_alpha;   // log(alpha): (alpha*h)^n is evaluated as exp(n*(ln_alpha + log h)), log h shared by all layers
 };
 
 struct LgarColumnClass {

@@ -1,7 +1,7 @@
 """The kernel TEXT (lgar_c_b200/csrc/lgar_physics.cuh + lgar_step.cuh) compiled for the host by
 tests/hostsim and run against the oracle: a CPU-side check of the device code's logic (slot
 arithmetic, the two-kernel split, the epilogue).  Test infrastructure only -- the product library
-contains no host path.  Remaining differences are libm pow vs x*x / x*x*x (<= 1 ulp)."""
+contains no host path.  Remaining differences: x^y evaluated as exp(y log x) instead of libm pow (<= 1e-14 relative per call)."""
 import ctypes as C
 import subprocess
 from pathlib import Path
@@ -62,7 +62,7 @@ def test_kernel_text_matches_golden(hostsim, name, force, tmp_path):
     done, scal, nf, fr, fl, status = run(hostsim, config_for(name, tmp_path), g["precip"][:n], g["pet"][:n], force)
     assert done == n and status & 0xFFFF == 0
     assert np.array_equal(nf, g["nfronts"][:n]), "front counts differ from the reference"
-    assert_scalars_close(scal, g["scalars"][:n], name, rtol=1e-12)
+    assert_scalars_close(scal, g["scalars"][:n], name, rtol=1e-10)
     for i, t in enumerate(g["ck_steps"]):
         if t < n:
-            assert_fronts_close(fr[t], fl[t], g["ck_fronts"][i], g["ck_flags"][i], int(nf[t]), f"{name}@{t}", rtol=1e-12)
+            assert_fronts_close(fr[t], fl[t], g["ck_fronts"][i], g["ck_flags"][i], int(nf[t]), f"{name}@{t}", rtol=1e-10)
