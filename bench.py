@@ -249,7 +249,7 @@ def main():
     ap.add_argument("--cpu-hours", type=int, default=1440)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--hourly", action="store_true", help="one stream+active kernel pair per forcing hour instead of the window kernel")
+    ap.add_argument("--mode", type=int, default=2, help="2 lanes kernel, 1 warp-tile window kernel, 0 one kernel pair per forcing hour")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -301,8 +301,7 @@ def main():
     cfg = write_workload_config(tmp)
     b = lgar_c_b200.BmiLGARBatch()
     b.initialize(cfg, ncol, local_rank, column_soils(col0, ncol), column_layers(col0, ncol))
-    if args.hourly:
-        b.set_window_mode(False)
+    b.set_window_mode(args.mode)
     ext = torch.cuda.ExternalStream(b.get_stream(), device=dev)
 
     # forcing ring on the device: R day-blocks, each [H][ncol]
@@ -427,11 +426,11 @@ def main():
     B_nofront = B_full - 2 * 44 * mean_fronts
     ms_s, ms_a, ms_w = prof["ms_stream"], prof["ms_active"], prof["ms_window"]
     if ms_w > 0:  # window mode: one kernel per bench step (H forcing hours for every column)
-        dominant = "lgar_window_kernel"
+        dominant = "lgar_lanes_kernel" if args.mode == 2 else "lgar_window_kernel"
         units = ncol * H
         B_unit = B_full
         dur_s = ms_w * 1e-3 / args.steps
-        share = {"lgar_window_kernel": 1.0}
+        share = {dominant: 1.0}
     else:
         dominant = "lgar_step_active_kernel" if ms_a >= ms_s else "lgar_step_stream_kernel"
         if dominant == "lgar_step_active_kernel":

@@ -178,10 +178,11 @@ int lgarb_get_soil_row(const lgarb_engine* e, int soil, double* out10);
 /* Test hook: route every column through the active kernel (no cached-flux fast path), to check
  * that the two kernels implement the same Update(). */
 int lgarb_set_force_all_active(lgarb_engine* e, int on);
-/* Scheduling of lgarb_update_steps_device: 1 (default) = one window-kernel launch for the whole run,
- * every column advancing on its own time pointer; 0 = one stream+active kernel pair per forcing
- * hour (what lgarb_update does).  Both produce identical results. */
-int lgarb_set_window_mode(lgarb_engine* e, int on);
+/* Scheduling of lgarb_update_steps_device.  2 (default) = one launch for the whole run, every lane
+ * running its own stream of columns and hours as a staged program (converged psi-search iterations);
+ * 1 = one launch, warp-owned tiles of columns with per-column time pointers; 0 = one stream+active
+ * kernel pair per forcing hour (what lgarb_update does).  All three produce identical results. */
+int lgarb_set_window_mode(lgarb_engine* e, int mode);
 /* number of kernels launched by this engine so far, and columns routed to the active kernel in
  * the last step */
 int64_t lgarb_get_launch_count(const lgarb_engine* e);

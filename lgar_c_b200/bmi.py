@@ -355,8 +355,9 @@ class BmiLGARBatch:
     def set_force_all_active(self, on):
         self._ck(self._L.lgarb_set_force_all_active(self._h, int(bool(on))))
 
-    def set_window_mode(self, on):
-        self._ck(self._L.lgarb_set_window_mode(self._h, int(bool(on))))
+    def set_window_mode(self, mode):
+        """2 lanes kernel (default), 1 warp-tile window kernel, 0 hour-by-hour kernel pairs."""
+        self._ck(self._L.lgarb_set_window_mode(self._h, int(mode)))
 
     def get_launch_count(self):
         return self._L.lgarb_get_launch_count(self._h)

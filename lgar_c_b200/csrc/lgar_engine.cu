@@ -76,7 +76,8 @@ struct lgarb_engine {
   cudaStream_t stream = nullptr;
   int active_blocks = 0;
   int window_blocks = 0;
-  int use_window = 1;          // multi-step runs go through the window kernel (0: hour-by-hour kernel pairs)
+  int use_window = 2;          // multi-step runs: 2 = lanes kernel, 1 = warp-tile window kernel, 0 = hour-by-hour kernel pairs
+  int lanes_blocks = 0;
   int32_t* d_tile_counter = nullptr;
   cudaEvent_t win_ev[2] = {nullptr, nullptr};
   double prof_ms_window = 0;
@@ -281,6 +282,9 @@ void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int d
   int wper_sm = lgar_window_kernel_max_blocks_per_sm();
   if (wper_sm < 1) wper_sm = 1;
   e->window_blocks = prop.multiProcessorCount * wper_sm;
+  int lper_sm = lgar_lanes_kernel_max_blocks_per_sm();
+  if (lper_sm < 1) lper_sm = 1;
+  e->lanes_blocks = prop.multiProcessorCount * lper_sm;
   e->steps = 0;
   e->launches = 0;
   e->time_s = 0.0;
@@ -531,7 +535,7 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
           }
           CUDA_TRY(cudaEventRecord(e->win_ev[0], e->stream));
         }
-        CUDA_TRY(lgar_launch_window(e->cfg, e->d, w, e->window_blocks, e->stream));
+        CUDA_TRY(lgar_launch_window(e->cfg, e->d, w, e->use_window == 2 ? e->lanes_blocks : e->window_blocks, e->stream, e->use_window));
         if (e->profiling) {
           CUDA_TRY(cudaEventRecord(e->win_ev[1], e->stream));
           e->prof_windows++;
@@ -755,7 +759,7 @@ int lgarb_get_soil_row(const lgarb_engine* e, int soil, double* o) {
 }
 
 int lgarb_set_force_all_active(lgarb_engine* e, int on) { LGARB_GUARD(e, e->force_all_active = on ? 1 : 0); }
-int lgarb_set_window_mode(lgarb_engine* e, int on) { LGARB_GUARD(e, e->use_window = on ? 1 : 0); }
+int lgarb_set_window_mode(lgarb_engine* e, int mode) { LGARB_GUARD(e, e->use_window = (mode < 0 || mode > 2) ? 2 : mode); }
 int64_t lgarb_get_launch_count(const lgarb_engine* e) { return e ? e->launches : -1; }
 int64_t lgarb_get_last_active_count(lgarb_engine* e) {
   if (!e || !e->initialized) return -1;

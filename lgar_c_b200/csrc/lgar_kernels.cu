@@ -18,7 +18,7 @@
 // HBM-bound in the stream kernel, FP64-pipe-bound in the active kernel; no tensor-core work exists
 // on this path (nothing is a contraction).
 #include <cuda_runtime.h>
-#include "lgar_step.cuh"
+#include "lgar_lanes.cuh"
 
 
 __global__ void __launch_bounds__(256) lgar_step_stream_kernel(LgarConfig cfg, LgarDeviceState d, LgarSinks sinks, int force_all_active) {
@@ -124,6 +124,79 @@ __global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_window_kernel(LgarCo
   }
 }
 
+// ---- lanes kernel -----------------------------------------------------------------------------------
+// K forcing hours per launch; every LANE runs its own stream of columns (atomic counter) and hours and
+// is in one stage of the resumable program of lgar_lanes.cuh.  The warp picks one stage per turn:
+// the psi search whenever at least LGAR_SEARCH_MIN lanes are in it (they iterate converged, up to
+// LGAR_SEARCH_QUANTUM trips or until too few are left), otherwise the most populated of the other
+// stages.  No shared memory, no barrier of any scope.
+#define LGAR_SEARCH_MIN 12
+#define LGAR_SEARCH_QUANTUM 32
+__global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_lanes_kernel(LgarConfig cfg, LgarDeviceState d, LgarWindow w) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  LgLane L;
+  L.stage = LG_ST_FETCH;
+  L.col = -1;
+  L.t = w.K;
+  L.resume = false;
+  unsigned long long front_sum = 0, active_sum = 0;
+  unsigned long long* fsp = w.prof ? &front_sum : nullptr;
+  for (;;) {
+    const int st = L.stage;
+    const unsigned m_search = __ballot_sync(FULL, st == LG_ST_SEARCH);
+    const unsigned m_front = __ballot_sync(FULL, st == LG_ST_FRONT);
+    const unsigned m_tail = __ballot_sync(FULL, st == LG_ST_TAIL);
+    const unsigned m_head = __ballot_sync(FULL, st == LG_ST_HEAD);
+    const unsigned m_fetch = __ballot_sync(FULL, st == LG_ST_FETCH);
+    if (!(m_search | m_front | m_tail | m_head | m_fetch)) break;  // every lane is DONE
+    const int n_search = __popc(m_search), n_front = __popc(m_front), n_tail = __popc(m_tail), n_head = __popc(m_head),
+              n_fetch = __popc(m_fetch);
+    int chosen;
+    if (n_search >= LGAR_SEARCH_MIN || !(m_front | m_tail | m_head | m_fetch)) {
+      chosen = LG_ST_SEARCH;
+    } else {  // most populated of the other stages; ties go to the stage closest to the search
+      chosen = LG_ST_FRONT;
+      int best = n_front;
+      if (n_tail > best) { best = n_tail; chosen = LG_ST_TAIL; }
+      if (n_head > best) { best = n_head; chosen = LG_ST_HEAD; }
+      if (n_fetch > best) { best = n_fetch; chosen = LG_ST_FETCH; }
+    }
+    if (st == chosen) {
+      if (chosen == LG_ST_SEARCH) {
+        const int keep = (n_search >= LGAR_SEARCH_MIN) ? LGAR_SEARCH_MIN : 1;
+        for (int it = 0; it < LGAR_SEARCH_QUANTUM; it++) {
+          if (!L.q.done) lg_search_iter(L.q, *L.cls);
+          if (__popc(__ballot_sync(m_search, !L.q.done)) < keep) break;
+        }
+        if (L.q.done) {
+          L.resume = true;
+          L.stage = LG_ST_FRONT;
+        }
+      } else if (chosen == LG_ST_FRONT) {
+        lg_stage_front(L);
+      } else if (chosen == LG_ST_TAIL) {
+        lg_stage_tail(cfg, d, w, L, fsp);
+      } else if (chosen == LG_ST_HEAD) {
+        lg_stage_head(cfg, d, w, L, fsp);
+        active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
+      } else {
+        lg_stage_fetch(cfg, d, w, L, fsp);
+      }
+    }
+  }
+  if (w.prof) {
+    for (int o = 16; o > 0; o >>= 1) {
+      front_sum += __shfl_down_sync(FULL, front_sum, o);
+      active_sum += __shfl_down_sync(FULL, active_sum, o);
+    }
+    if (lane == 0) {
+      atomicAdd(w.prof, front_sum);
+      atomicAdd(w.prof + 1, active_sum);
+    }
+  }
+}
+
 // Gather per-front BMI arrays into a caller-facing [ncol][LGAR_W] layout (pad = NaN).
 __global__ void lgar_gather_fronts_kernel(LgarDeviceState d, int which, double scale, double* dst, int64_t col0, int64_t ncol) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,11 +258,20 @@ cudaError_t lgar_launch_gather_layers(const LgarDeviceState& d, double* dst, int
   return cudaGetLastError();
 }
 
-cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream) {
+cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream, int mode) {
   cudaError_t err = cudaMemsetAsync(w.tile_counter, 0, sizeof(int32_t), stream);
   if (err != cudaSuccess) return err;
-  lgar_window_kernel<<<blocks, LGAR_WINDOW_THREADS, 0, stream>>>(cfg, d, w);
+  if (mode == 2)
+    lgar_lanes_kernel<<<blocks, LGAR_WINDOW_THREADS, 0, stream>>>(cfg, d, w);
+  else
+    lgar_window_kernel<<<blocks, LGAR_WINDOW_THREADS, 0, stream>>>(cfg, d, w);
   return cudaGetLastError();
+}
+
+int lgar_lanes_kernel_max_blocks_per_sm() {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lgar_lanes_kernel, LGAR_WINDOW_THREADS, 0);
+  return nb;
 }
 
 int lgar_window_kernel_max_blocks_per_sm() {

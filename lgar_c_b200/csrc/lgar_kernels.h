@@ -26,7 +26,7 @@ struct LgarWindow {
   int32_t* nf_sink;       // nullable: [K][sink_stride] soil_num_wetting_fronts after each hour
   int K;
   int force_all_active;
-  int32_t* tile_counter;  // device, zeroed before launch
+  int32_t* tile_counter;  // device, zeroed before launch (tile counter / column counter)
   unsigned long long* prof;  // nullable: [0] += sum of front counts, [1] += active column-steps
 };
 #define LGAR_TILE 256            // columns owned by one warp at a time
@@ -34,8 +34,10 @@ struct LgarWindow {
 #define LGAR_MAX_WINDOW 32768    // hours per launch (time pointers are 16 bit)
 
 #ifndef LGAR_HOSTSIM
-cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream);
+// mode 1: warp-tile window kernel; mode 2: per-lane staged program (lgar_lanes.cuh)
+cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream, int mode);
 int lgar_window_kernel_max_blocks_per_sm();
+int lgar_lanes_kernel_max_blocks_per_sm();
 
 // ev (nullable): three events recorded before the stream kernel, between the kernels, after the active kernel
 cudaError_t lgar_launch_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int active_blocks,

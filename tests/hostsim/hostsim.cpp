@@ -10,7 +10,7 @@
 #include <vector>
 
 #include "../../lgar_c_b200/csrc/lgar_config.hpp"
-#include "../../lgar_c_b200/csrc/lgar_step.cuh"
+#include "../../lgar_c_b200/csrc/lgar_lanes.cuh"
 
 using namespace lgarhost;
 
@@ -65,10 +65,30 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
       w.precip = P; w.pet = E; w.series_stride = 1; w.sink_stride = 1; w.K = nsteps; w.force_all_active = (force_all_active == 3);
       for (int k = 0; k < LGAR_NOUT; k++) w.sinks.p[k] = sk.data() + (size_t)k * nsteps;
       w.nf_sink = nfs.data();
+      if (force_all_active >= 4) {
+        // lane-program emulation: one lane walks the stages of lgar_lanes.cuh
+        w.force_all_active = (force_all_active == 5);
+        int32_t counter = 0;
+        w.tile_counter = &counter;
+        static LgLane L;  // large: keep it off the stack
+        L.stage = LG_ST_FETCH; L.col = -1; L.t = nsteps;
+        while (L.stage != LG_ST_DONE) {
+          switch (L.stage) {
+            case LG_ST_FETCH: lg_stage_fetch(cfg, d, w, L, nullptr); break;
+            case LG_ST_HEAD: lg_stage_head(cfg, d, w, L, nullptr); break;
+            case LG_ST_FRONT: lg_stage_front(L); break;
+            case LG_ST_SEARCH:
+              while (!L.q.done) lg_search_iter(L.q, *L.cls);
+              L.resume = true; L.stage = LG_ST_FRONT; break;
+            case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, nullptr); break;
+          }
+        }
+      } else {
       int tt = 0;
       while (tt < nsteps) {
         tt = lg_advance_column(cfg, d, w, 0, tt, nullptr);
         if (tt < nsteps) { lg_active_column_at(cfg, d, w, 0, tt, nullptr); tt++; }
+      }
       }
       for (t = 0; t < nsteps; t++) {
         if (scalars) for (int k = 0; k < LGAR_NOUT; k++) scalars[(size_t)t * LGAR_NOUT + k] = sk[(size_t)k * nsteps + t];

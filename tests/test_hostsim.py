@@ -39,11 +39,12 @@ def run(lib, cfg, P, E, force, cap=16):
     return done, scal, nf, fr, fl, st.value
 
 
-@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("mode", [2, 3, 4, 5])
 @pytest.mark.parametrize("name", STANDARD + RANDOM)
 def test_window_stepping_equals_hourly_stepping(hostsim, name, mode, tmp_path):
-    """The window kernel's per-column functions (advance through cached hours in registers, active step
-    at the column's own hour) must reproduce hour-by-hour stepping bit for bit."""
+    """The window kernel's per-column functions (modes 2/3: advance through cached hours in registers,
+    active step at the column's own hour) and the staged lane program of lgar_lanes.cuh (modes 4/5:
+    FETCH/HEAD/FRONT/SEARCH/TAIL) must reproduce hour-by-hour stepping bit for bit."""
     g = load_golden(name)
     n = min(len(g["precip"]), 2000)
     cfg = config_for(name, tmp_path)
