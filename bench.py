@@ -249,7 +249,7 @@ def main():
     ap.add_argument("--cpu-hours", type=int, default=1440)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--mode", type=int, default=2, help="2 lanes kernel, 1 warp-tile window kernel, 0 one kernel pair per forcing hour")
+    ap.add_argument("--mode", type=int, default=2, help="3 wavefront kernels, 2 lanes kernel, 1 warp-tile window kernel, 0 one kernel pair per forcing hour")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -426,7 +426,7 @@ def main():
     B_nofront = B_full - 2 * 44 * mean_fronts
     ms_s, ms_a, ms_w = prof["ms_stream"], prof["ms_active"], prof["ms_window"]
     if ms_w > 0:  # window mode: one kernel per bench step (H forcing hours for every column)
-        dominant = "lgar_lanes_kernel" if args.mode == 2 else "lgar_window_kernel"
+        dominant = {3: "lgar_wave_kernel<*> (5 stage kernels)", 2: "lgar_lanes_kernel", 1: "lgar_window_kernel"}[args.mode]
         units = ncol * H
         B_unit = B_full
         dur_s = ms_w * 1e-3 / args.steps

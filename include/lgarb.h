@@ -181,8 +181,21 @@ int lgarb_set_force_all_active(lgarb_engine* e, int on);
 /* Scheduling of lgarb_update_steps_device.  2 (default) = one launch for the whole run, every lane
  * running its own stream of columns and hours as a staged program (converged psi-search iterations);
  * 1 = one launch, warp-owned tiles of columns with per-column time pointers; 0 = one stream+active
- * kernel pair per forcing hour (what lgarb_update does).  All three produce identical results. */
+ * kernel pair per forcing hour (what lgarb_update does); 3 = wavefront scheduler: the same staged
+ * program with one small kernel per stage.  All produce identical results. */
 int lgarb_set_window_mode(lgarb_engine* e, int mode);
+/* mode 3 (wavefront: one small kernel per stage, contexts parked in HBM, compacted queues) tuning:
+ * psi-search trips per SEARCH launch, FRONT/SEARCH pairs per round, rounds between host polls.  0 keeps a value. */
+int lgarb_set_wave_params(lgarb_engine* e, int search_quantum, int front_search_pairs, int poll_rounds);
+/* Debug/profiling aid for the lanes kernel: per column, the number of psi-search trips and the
+ * kilo-cycles spent in the other stages during the LAST multi-step launch. */
+int lgarb_set_work_trace(lgarb_engine* e, int on);
+int lgarb_get_work_trace(lgarb_engine* e, int64_t col0, int64_t ncol, uint32_t* search_trips, uint32_t* other_kcycles);
+/* warp-level totals of the last launch for the stages FETCH, HEAD, FRONT, SEARCH, TAIL:
+ * out[0..4] cycles, out[5..9] stage turns, out[10..14] lanes that took part */
+int lgarb_get_stage_profile(lgarb_engine* e, uint64_t* out15);
+/* lifetime (us) and start time (us, mod 2^32) of the first 8192 warps of the last launch: out[0..8191], out[8192..16383] */
+int lgarb_get_warp_times(lgarb_engine* e, uint32_t* out16384);
 /* number of kernels launched by this engine so far, and columns routed to the active kernel in
  * the last step */
 int64_t lgarb_get_launch_count(const lgarb_engine* e);

@@ -29,7 +29,9 @@ class LgarbError(RuntimeError):
 
 
 def library_path() -> Path:
-    return HERE / "liblgarb.so"
+    import os
+    alt = os.environ.get("LGARB_LIBRARY")  # experiments with differently compiled builds of the same sources
+    return Path(alt) if alt else HERE / "liblgarb.so"
 
 
 def build_library(force: bool = False) -> Path:
@@ -104,6 +106,11 @@ def _load():
         "lgarb_get_soil_row": ([vp, C.c_int, dp], C.c_int),
         "lgarb_set_force_all_active": ([vp, C.c_int], C.c_int),
         "lgarb_set_window_mode": ([vp, C.c_int], C.c_int),
+        "lgarb_set_wave_params": ([vp, C.c_int, C.c_int, C.c_int], C.c_int),
+        "lgarb_set_work_trace": ([vp, C.c_int], C.c_int),
+        "lgarb_get_work_trace": ([vp, i64, i64, vp, vp], C.c_int),
+        "lgarb_get_stage_profile": ([vp, vp], C.c_int),
+        "lgarb_get_warp_times": ([vp, vp], C.c_int),
         "lgarb_get_launch_count": ([vp], i64),
         "lgarb_get_last_active_count": ([vp], i64),
         "lgarb_get_stream": ([vp], vp),
@@ -358,6 +365,30 @@ class BmiLGARBatch:
     def set_window_mode(self, mode):
         """2 lanes kernel (default), 1 warp-tile window kernel, 0 hour-by-hour kernel pairs."""
         self._ck(self._L.lgarb_set_window_mode(self._h, int(mode)))
+
+    def set_wave_params(self, search_quantum=0, front_search_pairs=0, poll_rounds=0):
+        self._ck(self._L.lgarb_set_wave_params(self._h, int(search_quantum), int(front_search_pairs), int(poll_rounds)))
+
+    def set_work_trace(self, on):
+        self._ck(self._L.lgarb_set_work_trace(self._h, int(bool(on))))
+
+    def get_work_trace(self, col0=0, ncol=None):
+        ncol = self.n_columns - col0 if ncol is None else ncol
+        a = np.empty(ncol, dtype=np.uint32)
+        b = np.empty(ncol, dtype=np.uint32)
+        self._ck(self._L.lgarb_get_work_trace(self._h, int(col0), int(ncol), _ptr(a), _ptr(b)))
+        return a, b
+
+    def get_stage_profile(self):
+        a = np.zeros(15, dtype=np.uint64)
+        self._ck(self._L.lgarb_get_stage_profile(self._h, _ptr(a)))
+        names = ["FETCH", "HEAD", "FRONT", "SEARCH", "TAIL"]
+        return {n: dict(cycles=int(a[k]), turns=int(a[5 + k]), lanes=int(a[10 + k])) for k, n in enumerate(names)}
+
+    def get_warp_times(self):
+        a = np.zeros(16384, dtype=np.uint32)
+        self._ck(self._L.lgarb_get_warp_times(self._h, _ptr(a)))
+        return a[:8192], a[8192:]
 
     def get_launch_count(self):
         return self._L.lgarb_get_launch_count(self._h)

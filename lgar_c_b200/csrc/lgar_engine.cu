@@ -78,6 +78,13 @@ struct lgarb_engine {
   int window_blocks = 0;
   int use_window = 2;          // multi-step runs: 2 = lanes kernel, 1 = warp-tile window kernel, 0 = hour-by-hour kernel pairs
   int lanes_blocks = 0;
+  unsigned int* d_work_trace = nullptr;  // [2][stride], allocated by lgarb_set_work_trace
+  // wavefront scheduler (mode 3)
+  LgarWave wave;
+  bool wave_ready = false;
+  int wave_quantum = 32, wave_pairs = 3, wave_poll = 4, wave_corr_pairs = 2;
+  int64_t wave_max_slots = 2097152;
+  int64_t wave_rounds = 0;
   int32_t* d_tile_counter = nullptr;
   cudaEvent_t win_ev[2] = {nullptr, nullptr};
   double prof_ms_window = 0;
@@ -114,6 +121,8 @@ struct lgarb_engine {
   }
   void release() {
     if (stream) cudaStreamSynchronize(stream);
+    d_work_trace = nullptr;
+    wave_ready = false;
     for (cudaEvent_t x : ev_pool) cudaEventDestroy(x);
     for (int i = 0; i < 2; i++) {
       if (win_ev[i]) cudaEventDestroy(win_ev[i]);
@@ -493,6 +502,88 @@ int lgarb_update_until(lgarb_engine* e, double t) {
   return lgarb_update(e);
 }
 
+namespace {
+void ensure_wave(lgarb_engine* e) {
+  if (e->wave_ready) return;
+  LgarWave& wv = e->wave;
+  memset(&wv, 0, sizeof(wv));
+  wv.nslots = (int32_t)std::min<int64_t>(e->ncol, e->wave_max_slots);
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, (size_t)wv.nslots * lgar_lane_context_bytes()));
+  e->allocs.push_back(p);
+  wv.ctx = (LgLane*)p;
+  for (int s = 0; s < LGAR_NSTAGE; s++)
+    for (int b = 0; b < 2; b++) wv.queue[s][b] = e->dalloc<int32_t>((size_t)wv.nslots, false);
+  wv.qcount = e->dalloc<int32_t>(LGAR_NSTAGE * 2);
+  wv.done_columns = e->dalloc<int32_t>(1);
+  e->wave_ready = true;
+}
+
+// one window of K hours through the wavefront kernels
+void run_wave_window(lgarb_engine* e, LgarWindow w) {
+  ensure_wave(e);
+  const LgarWave& wv = e->wave;
+  w.tile_counter = e->d_tile_counter;
+  w.done_columns = wv.done_columns;
+  CUDA_TRY(cudaMemsetAsync(e->d_tile_counter, 0, sizeof(int32_t), e->stream));
+  CUDA_TRY(lgar_launch_wave_init(wv, e->stream));
+  e->launches += 1;
+  int par[LGAR_NSTAGE] = {0, 0, 0, 0, 0, 0};
+  auto launch = [&](int stage) {
+    const int consume = par[stage];
+    par[stage] ^= 1;
+    unsigned mask = 0;
+    for (int s = 0; s < LGAR_NSTAGE; s++) mask |= (unsigned)par[s] << s;
+    CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, e->wave_quantum, e->stream));
+    e->launches += 2;
+  };
+  int32_t* h_done = (int32_t*)e->pinned(64 * sizeof(int32_t));
+  const bool debug = getenv("LGARB_WAVE_DEBUG") != nullptr;
+  cudaEvent_t dbg[2];
+  if (debug) {
+    cudaEventCreate(&dbg[0]);
+    cudaEventCreate(&dbg[1]);
+  }
+  for (int64_t round = 0;; round++) {
+    if (debug) {
+      CUDA_TRY(cudaMemcpyAsync(h_done + 1, wv.qcount, 12 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(cudaMemcpyAsync(h_done, wv.done_columns, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(cudaStreamSynchronize(e->stream));
+      cudaEventRecord(dbg[0], e->stream);
+    }
+    launch(0);  // FETCH
+    launch(1);  // HEAD
+    for (int k = 0; k < e->wave_pairs; k++) {
+      launch(2);  // FRONT
+      launch(3);  // SEARCH
+    }
+    launch(2);  // FRONT
+    launch(4);  // TAIL
+    for (int k = 0; k < e->wave_corr_pairs; k++) {
+      launch(5);  // CORR
+      launch(4);  // TAIL
+    }
+    e->wave_rounds++;
+    if (debug) {
+      cudaEventRecord(dbg[1], e->stream);
+      cudaEventSynchronize(dbg[1]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, dbg[0], dbg[1]);
+      if (round < 40 || round % 20 == 0)
+        fprintf(stderr, "[wave] round %lld: %.3f ms  done=%d  queues(before) F=%d H=%d FR=%d S=%d T=%d C=%d\n", (long long)round, ms, h_done[0],
+                h_done[1] + h_done[2], h_done[3] + h_done[4], h_done[5] + h_done[6], h_done[7] + h_done[8], h_done[9] + h_done[10],
+                h_done[11] + h_done[12]);
+    }
+    if ((round % e->wave_poll) == e->wave_poll - 1) {
+      CUDA_TRY(cudaMemcpyAsync(h_done, wv.done_columns, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(cudaStreamSynchronize(e->stream));
+      if (*h_done >= e->ncol) break;
+      if (round > 100000000) throw std::runtime_error("wavefront scheduler did not terminate");
+    }
+  }
+}
+}  // namespace
+
 int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_precip, const double* d_pet, int64_t series_stride,
                               double* const* d_sinks, int64_t sink_stride, int32_t* d_nfronts_sink) {
   LGARB_GUARD(e, {
@@ -523,6 +614,9 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
         w.force_all_active = e->force_all_active;
         w.tile_counter = e->d_tile_counter;
         w.prof = e->profiling ? e->d_prof_acc : nullptr;
+        w.work_trace = e->d_work_trace;
+        if (e->d_work_trace) CUDA_TRY(cudaMemsetAsync(e->d_work_trace + 2 * e->stride, 0, (64 + 2 * 8192) * sizeof(unsigned int), e->stream));
+        w.trace_stride = e->stride;
         if (e->profiling) {
           if (!e->win_ev[0]) {
             CUDA_TRY(cudaEventCreate(&e->win_ev[0]));
@@ -535,7 +629,10 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
           }
           CUDA_TRY(cudaEventRecord(e->win_ev[0], e->stream));
         }
-        CUDA_TRY(lgar_launch_window(e->cfg, e->d, w, e->use_window == 2 ? e->lanes_blocks : e->window_blocks, e->stream, e->use_window));
+        if (e->use_window == 3)
+          run_wave_window(e, w);
+        else
+          CUDA_TRY(lgar_launch_window(e->cfg, e->d, w, e->use_window == 2 ? e->lanes_blocks : e->window_blocks, e->stream, e->use_window));
         if (e->profiling) {
           CUDA_TRY(cudaEventRecord(e->win_ev[1], e->stream));
           e->prof_windows++;
@@ -759,7 +856,45 @@ int lgarb_get_soil_row(const lgarb_engine* e, int soil, double* o) {
 }
 
 int lgarb_set_force_all_active(lgarb_engine* e, int on) { LGARB_GUARD(e, e->force_all_active = on ? 1 : 0); }
-int lgarb_set_window_mode(lgarb_engine* e, int mode) { LGARB_GUARD(e, e->use_window = (mode < 0 || mode > 2) ? 2 : mode); }
+int lgarb_set_work_trace(lgarb_engine* e, int on) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (on && !e->d_work_trace) e->d_work_trace = e->dalloc<unsigned int>(2 * (size_t)e->stride + 64 + 2 * 8192);
+    if (!on) e->d_work_trace = nullptr;  // the buffer stays in the allocation list until finalize
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+  });
+}
+int lgarb_get_work_trace(lgarb_engine* e, int64_t col0, int64_t ncol, uint32_t* search_trips, uint32_t* other_kcycles) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    check_range(e, col0, ncol);
+    if (!e->d_work_trace) throw std::runtime_error("work trace is off");
+    d2h(e, search_trips, e->d_work_trace + col0, (size_t)ncol * sizeof(uint32_t));
+    d2h(e, other_kcycles, e->d_work_trace + e->stride + col0, (size_t)ncol * sizeof(uint32_t));
+  });
+}
+int lgarb_get_stage_profile(lgarb_engine* e, uint64_t* out15) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (!e->d_work_trace) throw std::runtime_error("work trace is off");
+    d2h(e, out15, e->d_work_trace + 2 * e->stride, 15 * sizeof(uint64_t));
+  });
+}
+int lgarb_get_warp_times(lgarb_engine* e, uint32_t* out16384) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (!e->d_work_trace) throw std::runtime_error("work trace is off");
+    d2h(e, out16384, e->d_work_trace + 2 * e->stride + 64, 2 * 8192 * sizeof(uint32_t));
+  });
+}
+int lgarb_set_window_mode(lgarb_engine* e, int mode) { LGARB_GUARD(e, e->use_window = (mode < 0 || mode > 3) ? 3 : mode); }
+int lgarb_set_wave_params(lgarb_engine* e, int search_quantum, int front_search_pairs, int poll_rounds) {
+  LGARB_GUARD(e, {
+    if (search_quantum > 0) e->wave_quantum = search_quantum;
+    if (front_search_pairs > 0) e->wave_pairs = front_search_pairs;
+    if (poll_rounds > 0) e->wave_poll = poll_rounds;
+  });
+}
 int64_t lgarb_get_launch_count(const lgarb_engine* e) { return e ? e->launches : -1; }
 int64_t lgarb_get_last_active_count(lgarb_engine* e) {
   if (!e || !e->initialized) return -1;

@@ -140,8 +140,13 @@ __global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_lanes_kernel(LgarCon
   L.col = -1;
   L.t = w.K;
   L.resume = false;
+  L.tr_iters = 0;
+  L.tr_kcyc = 0;
   unsigned long long front_sum = 0, active_sum = 0;
   unsigned long long* fsp = w.prof ? &front_sum : nullptr;
+  unsigned long long sp_cyc[5] = {0, 0, 0, 0, 0}, sp_calls[5] = {0, 0, 0, 0, 0}, sp_lanes[5] = {0, 0, 0, 0, 0};
+  unsigned long long gt0 = 0;
+  if (w.work_trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
   for (;;) {
     const int st = L.stage;
     const unsigned m_search = __ballot_sync(FULL, st == LG_ST_SEARCH);
@@ -149,12 +154,15 @@ __global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_lanes_kernel(LgarCon
     const unsigned m_tail = __ballot_sync(FULL, st == LG_ST_TAIL);
     const unsigned m_head = __ballot_sync(FULL, st == LG_ST_HEAD);
     const unsigned m_fetch = __ballot_sync(FULL, st == LG_ST_FETCH);
-    if (!(m_search | m_front | m_tail | m_head | m_fetch)) break;  // every lane is DONE
+    const unsigned m_corr = __ballot_sync(FULL, st == LG_ST_CORR);
+    if (!(m_search | m_front | m_tail | m_head | m_fetch | m_corr)) break;  // every lane is DONE
     const int n_search = __popc(m_search), n_front = __popc(m_front), n_tail = __popc(m_tail), n_head = __popc(m_head),
-              n_fetch = __popc(m_fetch);
+              n_fetch = __popc(m_fetch), n_corr = __popc(m_corr);
     int chosen;
-    if (n_search >= LGAR_SEARCH_MIN || !(m_front | m_tail | m_head | m_fetch)) {
+    if (n_search >= LGAR_SEARCH_MIN || (m_search && !(m_front | m_tail | m_head | m_fetch | m_corr))) {
       chosen = LG_ST_SEARCH;
+    } else if (n_corr >= LGAR_SEARCH_MIN || (m_corr && !(m_front | m_tail | m_head | m_fetch))) {
+      chosen = LG_ST_CORR;
     } else {  // most populated of the other stages; ties go to the stage closest to the search
       chosen = LG_ST_FRONT;
       int best = n_front;
@@ -162,27 +170,65 @@ __global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_lanes_kernel(LgarCon
       if (n_head > best) { best = n_head; chosen = LG_ST_HEAD; }
       if (n_fetch > best) { best = n_fetch; chosen = LG_ST_FETCH; }
     }
+    const long long sp_t0 = w.work_trace ? clock64() : 0;
     if (st == chosen) {
       if (chosen == LG_ST_SEARCH) {
         const int keep = (n_search >= LGAR_SEARCH_MIN) ? LGAR_SEARCH_MIN : 1;
         for (int it = 0; it < LGAR_SEARCH_QUANTUM; it++) {
-          if (!L.q.done) lg_search_iter(L.q, *L.cls);
+          if (!L.q.done) {
+            lg_search_iter(L.q, *L.cls);
+            L.tr_iters++;
+          }
           if (__popc(__ballot_sync(m_search, !L.q.done)) < keep) break;
         }
         if (L.q.done) {
           L.resume = true;
           L.stage = LG_ST_FRONT;
         }
-      } else if (chosen == LG_ST_FRONT) {
-        lg_stage_front(L);
-      } else if (chosen == LG_ST_TAIL) {
-        lg_stage_tail(cfg, d, w, L, fsp);
-      } else if (chosen == LG_ST_HEAD) {
-        lg_stage_head(cfg, d, w, L, fsp);
-        active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
+      } else if (chosen == LG_ST_CORR) {
+        const int keep = (n_corr >= LGAR_SEARCH_MIN) ? LGAR_SEARCH_MIN : 1;
+        for (int it = 0; it < LGAR_SEARCH_QUANTUM; it++) {
+          if (!L.k.done) lg_corr_iter(L.k, L.f, *L.cls);
+          if (__popc(__ballot_sync(m_corr, !L.k.done)) < keep) break;
+        }
+        if (L.k.done) L.stage = LG_ST_TAIL;
       } else {
-        lg_stage_fetch(cfg, d, w, L, fsp);
+        const long long c0 = w.work_trace ? clock64() : 0;
+        if (chosen == LG_ST_FRONT) {
+          lg_stage_front(L);
+        } else if (chosen == LG_ST_TAIL) {
+          lg_stage_tail(cfg, d, w, L, fsp);
+        } else if (chosen == LG_ST_HEAD) {
+          lg_stage_head(cfg, d, w, L, fsp);
+          active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
+        } else {
+          lg_stage_fetch(cfg, d, w, L, fsp);
+        }
+        if (w.work_trace && chosen != LG_ST_FETCH) L.tr_kcyc += (unsigned int)((clock64() - c0) >> 10);
       }
+    }
+    if (w.work_trace) {
+      __syncwarp();
+      const int np = chosen == LG_ST_SEARCH ? n_search : chosen == LG_ST_FRONT ? n_front : chosen == LG_ST_TAIL ? n_tail : chosen == LG_ST_HEAD ? n_head : chosen == LG_ST_CORR ? n_corr : n_fetch;
+      const int slot_ = chosen == LG_ST_CORR ? LG_ST_TAIL : chosen;  // the profile has five slots: CORR is booked under TAIL
+      sp_cyc[slot_] += (unsigned long long)(clock64() - sp_t0);
+      sp_calls[slot_] += 1;
+      sp_lanes[slot_] += np;
+    }
+  }
+  if (w.work_trace && lane == 0) {
+    unsigned long long gt1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+    const int gw = (blockIdx.x * LGAR_WINDOW_THREADS + threadIdx.x) >> 5;
+    if (gw < 8192) {
+      w.work_trace[2 * w.trace_stride + 64 + gw] = (unsigned int)((gt1 - gt0) / 1000ull);          // warp lifetime, us
+      w.work_trace[2 * w.trace_stride + 64 + 8192 + gw] = (unsigned int)((gt0 / 1000ull) & 0xFFFFFFFFull);  // start, us (mod 2^32)
+    }
+    unsigned long long* sp = (unsigned long long*)(w.work_trace + 2 * w.trace_stride);
+    for (int k = 0; k < 5; k++) {
+      atomicAdd(sp + k, sp_cyc[k]);
+      atomicAdd(sp + 5 + k, sp_calls[k]);
+      atomicAdd(sp + 10 + k, sp_lanes[k]);
     }
   }
   if (w.prof) {
@@ -196,6 +242,161 @@ __global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_lanes_kernel(LgarCon
     }
   }
 }
+
+// ---- wavefront kernels (mode 3) -------------------------------------------------------------------------
+// The lanes kernel proved the staged program right but ran at 0.2 instructions/clock/scheduler: its
+// code (206-437 KB of SASS) does not fit the 32 KB L1.5 instruction cache and every warp sits somewhere
+// else in it (ncu: 26 of 34 stall cycles per instruction are instruction fetch).  Here every stage is
+// its own small kernel; the context of an in-flight column-step (LgLane) is parked in HBM between
+// stages and stages hand slots to each other through compacted queues, so every kernel runs full warps
+// over one short piece of code.  The host enqueues rounds of FETCH, HEAD, (FRONT, SEARCH) x n, TAIL
+// without looking at the queues and polls one counter now and then.  A queue pair per stage: a launch
+// of stage S consumes the buffer that has been appended to since S last ran, and everything produced
+// meanwhile (including S re-queuing itself) goes to the other one.
+namespace {
+
+__device__ __forceinline__ void wave_push(const LgarWave& wv, unsigned append_mask, int stage, bool pred, int slot) {
+  const unsigned m = __ballot_sync(__activemask(), pred);
+  if (!pred) return;
+  const int buf = (append_mask >> stage) & 1;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(wv.qcount + stage * 2 + buf, __popc(m));
+  base = __shfl_sync(m, base, leader);
+  wv.queue[stage][buf][base + __popc(m & ((1u << lane) - 1))] = slot;
+}
+
+// context copy between HBM and thread-private memory, 16 bytes at a time
+template <typename T>
+__device__ __forceinline__ void ctx_copy(T* dst, const T* src) {
+  static_assert(sizeof(T) % 16 == 0, "context must be a multiple of 16 bytes");
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll 4
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d4[i] = s4[i];
+}
+
+}  // namespace
+
+struct alignas(16) LgLaneSlot {
+  LgLane L;
+};
+
+template <int STAGE>
+__global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDeviceState d, LgarWindow w, LgarWave wv, int consume,
+                                                        unsigned append_mask, int quantum) {
+  const int n = wv.qcount[STAGE * 2 + consume];
+  LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31); i += gridDim.x * blockDim.x) {
+    const bool valid = i < n;
+    const int slot = valid ? wv.queue[STAGE][consume][i] : 0;
+    int next = -1;
+    if (STAGE == LG_ST_SEARCH) {
+      if (valid) {  // only the search record travels
+        LgLane& G = slots[slot].L;
+        LgSearch q = G.q;
+        const LgarColumnClass* cls = G.cls;
+        for (int it = 0; it < quantum && !q.done; it++) lg_search_iter(q, *cls);
+        G.q = q;
+        if (q.done) G.resume = true;
+        next = q.done ? LG_ST_FRONT : LG_ST_SEARCH;
+      }
+    } else if (STAGE == LG_ST_CORR) {
+      if (valid) {  // the correction record and the front list travel
+        LgLane& G = slots[slot].L;
+        LgCorr k = G.k;
+        LgFronts f = G.f;
+        const LgarColumnClass* cls = G.cls;
+        for (int it = 0; it < quantum && !k.done; it++) lg_corr_iter(k, f, *cls);
+        G.k = k;
+        G.f = f;
+        next = k.done ? LG_ST_TAIL : LG_ST_CORR;
+      }
+    } else if (STAGE == LG_ST_FETCH) {
+      if (valid) {  // a fetching slot owns nothing but (column, hour)
+        LgLane& G = slots[slot].L;
+        LgLane L;
+        L.col = G.col;
+        L.t = G.t;
+        L.tr_iters = 0;
+        L.tr_kcyc = 0;
+        lg_stage_fetch(cfg, d, w, L, nullptr);
+        G.col = L.col;
+        G.t = L.t;
+        next = L.stage;
+      }
+    } else if (valid) {
+      LgLaneSlot S;
+      LgLane& L = S.L;
+      if (STAGE == LG_ST_HEAD) {  // HEAD builds the context from the column state
+        L.col = slots[slot].L.col;
+        L.t = slots[slot].L.t;
+        L.tr_iters = 0;
+        L.tr_kcyc = 0;
+        lg_stage_head(cfg, d, w, L, nullptr);
+      } else {
+        ctx_copy(&S, &slots[slot]);
+        L.c.cfg = &cfg;
+        L.c.cls = L.cls;
+        L.c.f = &L.f;
+        if (STAGE == LG_ST_FRONT)
+          lg_stage_front(L);
+        else
+          lg_stage_tail(cfg, d, w, L, nullptr);
+      }
+      next = L.stage;
+      if (next == LG_ST_FETCH) {
+        slots[slot].L.col = L.col;
+        slots[slot].L.t = L.t;
+      } else {
+        ctx_copy(&slots[slot], &S);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < LGAR_NSTAGE; s++) wave_push(wv, append_mask, s, valid && next == s, slot);
+  }
+}
+
+__global__ void lgar_wave_init_kernel(LgarWave wv) {
+  LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wv.nslots; i += gridDim.x * blockDim.x) {
+    slots[i].L.stage = LG_ST_FETCH;
+    slots[i].L.col = -1;
+    slots[i].L.t = 0x7FFFFFFF;
+    slots[i].L.resume = false;
+    slots[i].L.tr_iters = 0;
+    slots[i].L.tr_kcyc = 0;
+    wv.queue[LG_ST_FETCH][0][i] = i;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < LGAR_NSTAGE * 2) wv.qcount[threadIdx.x] = (threadIdx.x == LG_ST_FETCH * 2) ? wv.nslots : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *wv.done_columns = 0;
+}
+
+// reset the consumed queue's count after its kernel ran
+__global__ void lgar_wave_reset_kernel(int32_t* count) { *count = 0; }
+
+cudaError_t lgar_launch_wave_init(const LgarWave& wv, cudaStream_t stream) {
+  lgar_wave_init_kernel<<<(wv.nslots + 255) / 256, 256, 0, stream>>>(wv);
+  return cudaGetLastError();
+}
+
+cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int stage, int consume,
+                                   unsigned append_mask, int quantum, cudaStream_t stream) {
+  const int blocks = (wv.nslots + 127) / 128;
+  switch (stage) {
+    case LG_ST_FETCH: lgar_wave_kernel<LG_ST_FETCH><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+    case LG_ST_HEAD: lgar_wave_kernel<LG_ST_HEAD><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+    case LG_ST_FRONT: lgar_wave_kernel<LG_ST_FRONT><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+    case LG_ST_SEARCH: lgar_wave_kernel<LG_ST_SEARCH><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+    case LG_ST_CORR: lgar_wave_kernel<LG_ST_CORR><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+    default: lgar_wave_kernel<LG_ST_TAIL><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+  }
+  lgar_wave_reset_kernel<<<1, 1, 0, stream>>>(wv.qcount + stage * 2 + consume);
+  return cudaGetLastError();
+}
+
+size_t lgar_lane_context_bytes() { return sizeof(LgLaneSlot); }
 
 // Gather per-front BMI arrays into a caller-facing [ncol][LGAR_W] layout (pad = NaN).
 __global__ void lgar_gather_fronts_kernel(LgarDeviceState d, int which, double scale, double* dst, int64_t col0, int64_t ncol) {

@@ -28,12 +28,32 @@ struct LgarWindow {
   int force_all_active;
   int32_t* tile_counter;  // device, zeroed before launch (tile counter / column counter)
   unsigned long long* prof;  // nullable: [0] += sum of front counts, [1] += active column-steps
+  int32_t* done_columns;  // nullable: += 1 whenever a column finishes its window (wavefront scheduler)
+  unsigned int* work_trace;  // nullable: [2][stride] per column: psi-search trips, kilo-cycles in the non-search stages (lanes kernel)
+  int64_t trace_stride;
 };
 #define LGAR_TILE 256            // columns owned by one warp at a time
 #define LGAR_WINDOW_THREADS 128
 #define LGAR_MAX_WINDOW 32768    // hours per launch (time pointers are 16 bit)
 
+// Wavefront scheduler state (mode 3): contexts of in-flight column-steps parked in HBM and one
+// compacted queue pair per stage (see lgar_kernels.cu).
+struct LgLane;
+#define LGAR_NSTAGE 6
+struct LgarWave {
+  LgLane* ctx;                 // [nslots]
+  int32_t* queue[LGAR_NSTAGE][2];  // slot ids
+  int32_t* qcount;             // [LGAR_NSTAGE][2]
+  int32_t nslots;
+  int32_t* done_columns;       // columns that finished their window
+};
+
 #ifndef LGAR_HOSTSIM
+// one launch of the kernel of `stage`, consuming queue[stage][consume]; append_mask bit s = buffer of stage s to append to
+cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int stage, int consume,
+                                   unsigned append_mask, int quantum, cudaStream_t stream);
+cudaError_t lgar_launch_wave_init(const LgarWave& wv, cudaStream_t stream);
+size_t lgar_lane_context_bytes();
 // mode 1: warp-tile window kernel; mode 2: per-lane staged program (lgar_lanes.cuh)
 cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream, int mode);
 int lgar_window_kernel_max_blocks_per_sm();

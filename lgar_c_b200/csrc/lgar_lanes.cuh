@@ -14,6 +14,7 @@
 //   FRONT   iterations of that loop (deepest front first) until one needs a psi search
 //   SEARCH  iterations of the psi search, all searching lanes converged
 //   TAIL    merge/cross corrections, dzdt, reservoir, mass balance; next sub-cycle or end of step
+//   CORR    iterations of the correction search of lgar_fix_dry_over_wet_wetting_fronts, converged
 //
 // The arithmetic and its order are those of lgar_physics.cuh (the two are checked against each
 // other bit for bit, tests/test_hostsim.py and tests/test_gpu_parity.py); only the control
@@ -23,13 +24,21 @@
 
 #include "lgar_step.cuh"
 
-enum { LG_ST_FETCH = 0, LG_ST_HEAD = 1, LG_ST_FRONT = 2, LG_ST_SEARCH = 3, LG_ST_TAIL = 4, LG_ST_DONE = 5 };
+enum { LG_ST_FETCH = 0, LG_ST_HEAD = 1, LG_ST_FRONT = 2, LG_ST_SEARCH = 3, LG_ST_TAIL = 4, LG_ST_CORR = 5, LG_ST_DONE = 6 };
 
 struct LgSearch {  // one psi search in flight
   double psi_loc, factor, psi_prev, delta_mass, delta_mass_prev, new_mass, prior_mass, precip_mass_to_add, theta;
   double dth[LGAR_MAXL + 1], dz[LGAR_MAXL + 1];
   int layer_num, iter, count_no_mass_change;
   bool switched, wanted_to_saturate, aug, aug_extreme, done;
+};
+
+// one correction search in flight (lgar_theta_mass_balance_correction, lgar.cxx:3262-3435): it works on the
+// live front list, so the CORR stage carries the fronts with it
+struct LgCorr {
+  double psi_loc, factor, psi_prev, delta_mass, delta_mass_prev, new_mass, prior_mass;
+  int cur, iter, count_no_mass_change;
+  bool switched, aug, aug_extreme, done;
 };
 
 struct LgLane {
@@ -55,6 +64,12 @@ struct LgLane {
   bool resume;
   double precip_mass_to_add, bottom_flux, actual_ET_demand;
   LgSearch q;
+  // resumable lgar_move_wetting_fronts epilogue: correction loop + lgar_fix_dry_over_wet_wetting_fronts
+  int me_phase, me_correction, fx_cur, fx_nx, fx_l;
+  bool fx_resume;
+  double fx_prior_mass, fx_mass_change;
+  LgCorr k;
+  unsigned int tr_iters, tr_kcyc;  // work trace of the current column (debug)
 };
 
 // ---- psi search split into init / iterate / finish (lgar.cxx:2952-3112) ---------------------------
@@ -159,6 +174,7 @@ LG_FN void lg_move_begin(LgLane& L, double volin_arg) {
   L.bottom_flux = 0.0;
   L.wf_fd_demand = L.wf_fd;
   L.resume = false;
+  L.me_phase = 0;
 }
 
 // the saturated-front depth adjustment executed when wf == 1 (lgar.cxx:1644-1754)
@@ -362,32 +378,204 @@ LG_FN_NOINLINE bool lg_move_fronts(LgLane& L) {
   return false;
 }
 
-// corrections + refresh after the front loop (lgar.cxx:1777-1863); returns the bottom boundary flux
-LG_FN_NOINLINE double lg_move_end(LgLane& L) {
+// ---- correction search split into init / iterate (lgar.cxx:3262-3435) ---------------------------------
+// returns true when the loop has to iterate
+LG_FN_NOINLINE bool lg_corr_init(LgLane& L, int front_num, double prior_mass) {
+  LgCtx& c = L.c;
+  LgFronts& f = L.f;
+  LgCorr& k = L.k;
+  int cur = front_num - 1;
+  k.done = true;
+  k.iter = 0;
+  if (cur < 0 || cur >= f.n) {
+    c.status |= LGAR_FAIL_LIST;
+    return false;
+  }
+  if (cur + 1 > 1) {
+    if (f.tb[cur - 1]) cur = cur - 1;
+  }
+  while (f.tb[cur]) {
+    if (cur + 1 == 1) break;
+    cur = cur - 1;
+    if (!f.tb[cur]) {
+      cur = cur + 1;
+      break;
+    }
+  }
+  k.cur = cur;
+  k.new_mass = lg_mass_bal(c);
+  const double psi_cm = f.psi[cur];
+  k.psi_loc = psi_cm;
+  k.prior_mass = prior_mass;
+  k.delta_mass = fabs(k.new_mass - prior_mass);
+  k.factor = fmax(1.0, psi_cm / 10.0);
+  if (psi_cm > 1.E4) k.factor = psi_cm;
+  k.switched = false;
+  k.psi_prev = psi_cm;
+  k.delta_mass_prev = k.delta_mass;
+  k.count_no_mass_change = 0;
+  k.aug = false;
+  k.aug_extreme = false;
+  k.done = !(k.delta_mass > LG_MBAL_TOL);
+  return !k.done;
+}
+
+// one trip of the loop on the live front list
+LG_FN void lg_corr_iter(LgCorr& k, LgFronts& f, const LgarColumnClass& cls) {
+  const int first_thresh = LG_MAX_ITER_MBAL / 100, second_thresh = LG_MAX_ITER_MBAL / 10;
+  const int cur = k.cur;
+  k.iter++;
+  if (k.iter > first_thresh && !k.aug) {
+    k.factor = k.factor * 100;
+    k.aug = true;
+  }
+  if (k.iter > second_thresh && !k.aug_extreme) {
+    k.factor = k.factor * 100;
+    k.aug_extreme = true;
+  }
+  if (k.new_mass > k.prior_mass) {
+    k.psi_loc += 0.1 * k.factor;
+    k.switched = false;
+  } else {
+    if (!k.switched) {
+      k.switched = true;
+      k.factor = k.factor * 0.1;
+    }
+    k.psi_prev = k.psi_loc;
+    k.psi_loc -= 0.1 * k.factor;
+    if (k.psi_loc < 0 && k.psi_prev != 0) k.psi_loc = k.psi_prev * 0.1;
+  }
+  if (k.psi_loc < 0.0) {
+    k.psi_loc = 0.0;
+    k.factor = k.factor * 0.5;
+  }
+  const double lnpsi = log(k.psi_loc);
+  f.psi[cur] = k.psi_loc;
+  f.theta[cur] = lg_theta_from_lnh(lnpsi, cls.lay[f.layer[cur]]);
+  int nx = cur + 1, before = cur;
+  if (nx < f.n) {
+    while (f.tb[nx]) {
+      f.psi[nx] = f.psi[before];
+      f.theta[nx] = lg_theta_from_lnh(lnpsi, cls.lay[f.layer[nx]]);
+      before = nx;
+      nx = nx + 1;
+      if (nx >= f.n) break;
+    }
+    if (nx < f.n) {
+      if (!f.tb[nx] && f.tb[before]) {
+        f.psi[nx] = f.psi[before];
+        f.theta[nx] = lg_theta_from_lnh(lnpsi, cls.lay[f.layer[nx]]);
+      }
+    }
+  }
+  {  // lgar_calc_mass_bal, lgar.cxx:2632-2668
+    const double* cum = cls.cum;
+    double sum = 0.0;
+    for (int i = 0; i < f.n; i++) {
+      double base = cum[f.layer[i] - 1];
+      if (i + 1 < f.n) {
+        if (f.layer[i + 1] == f.layer[i])
+          sum += (f.depth[i] - base) * (f.theta[i] - f.theta[i + 1]);
+        else
+          sum += (f.depth[i] - base) * f.theta[i];
+      } else {
+        sum += f.theta[i] * (f.depth[i] - base);
+      }
+    }
+    k.new_mass = sum;
+  }
+  k.delta_mass = fabs(k.new_mass - k.prior_mass);
+  bool brk = false;
+  if (fabs(k.psi_loc - k.psi_prev) < 1E-15 && k.factor < 1E-13) brk = true;
+  if (!brk) {
+    if (fabs(k.delta_mass - k.delta_mass_prev) < 1E-15)
+      k.count_no_mass_change++;
+    else
+      k.count_no_mass_change = 0;
+    if (k.count_no_mass_change == 5) brk = true;
+    else if (k.iter > LG_MAX_ITER_MBAL) brk = true;
+    else if (k.psi_loc <= 0 && k.psi_prev < 0) brk = true;
+    else if ((k.psi_loc > LG_PSI_UPPER_LIM) && (k.iter > first_thresh)) brk = true;
+  }
+  if (!brk) k.delta_mass_prev = k.delta_mass;
+  if (brk || !(k.delta_mass > LG_MBAL_TOL)) k.done = true;
+}
+
+// lgar_fix_dry_over_wet_wetting_fronts (lgar.cxx:2260-2307), resumable around its correction search.
+// Returns true when a correction search has to iterate.
+LG_FN_NOINLINE bool lg_fix_run(LgLane& L) {
+  LgCtx& c = L.c;
+  LgFronts& f = L.f;
+  while (L.fx_l <= f.n) {
+    if (L.fx_nx >= 0) {
+      bool fixed = L.fx_resume;
+      if (!L.fx_resume) {
+        if ((f.theta[L.fx_cur] <= f.theta[L.fx_nx]) && (f.layer[L.fx_cur] == f.layer[L.fx_nx])) {
+          L.fx_prior_mass = lg_mass_bal(c);
+          L.fx_cur = lg_front_delete(c, L.fx_cur);
+          fixed = true;
+          if (lg_corr_init(L, L.fx_cur + 1, L.fx_prior_mass)) {
+            L.fx_resume = true;
+            return true;
+          }
+        }
+      }
+      L.fx_resume = false;
+      if (fixed) {
+        double mass_after = lg_mass_bal(c);
+        L.fx_mass_change += (mass_after - L.fx_prior_mass);
+      }
+      L.fx_cur = L.fx_cur + 1;
+      if (L.fx_cur >= f.n)
+        L.fx_nx = -1;
+      else
+        L.fx_nx = (L.fx_cur + 1 < f.n) ? L.fx_cur + 1 : -1;
+    }
+    L.fx_l++;
+  }
+  return false;
+}
+
+// corrections + refresh after the front loop (lgar.cxx:1777-1863), resumable.  Returns true when a
+// correction search has to iterate; otherwise the bottom boundary flux is in L.bottom_flux.
+LG_FN_NOINLINE bool lg_move_end(LgLane& L) {
   LgCtx& c = L.c;
   LgFronts& f = L.f;
   const LgarColumnClass& cls = *L.cls;
-  double bottom_flux = L.bottom_flux;
-  int correction = lg_correction_type(c);
-  while (correction != 0) {
+  if (L.me_phase == 0) {
+    L.me_correction = lg_correction_type(c);
+    L.me_phase = 1;
+  }
+  while (L.me_correction != 0) {
     if (c.status & (LGAR_FAIL_LIST | LGAR_FAIL_OVERFLOW)) break;
-    if (correction == 1) lg_merge(c);
-    if (correction == 2) {
-      double mass_before = lg_mass_bal(c);
-      lg_cross_layer_boundary(c);
-      double mass_after = lg_mass_bal(c);
-      if (fabs(mass_before - mass_after) > 100. * LG_MBAL_TOL) L.AET = L.AET + (mass_before - mass_after);
+    if (L.me_phase == 1) {
+      const int correction = L.me_correction;
+      if (correction == 1) lg_merge(c);
+      if (correction == 2) {
+        double mass_before = lg_mass_bal(c);
+        lg_cross_layer_boundary(c);
+        double mass_after = lg_mass_bal(c);
+        if (fabs(mass_before - mass_after) > 100. * LG_MBAL_TOL) L.AET = L.AET + (mass_before - mass_after);
+      }
+      if (correction == 3) {
+        L.bottom_flux += lg_cross_domain_boundary(c);
+        if (isnan(L.bottom_flux)) L.bottom_flux = 0.0;
+      }
+      if (correction == 4) {
+        L.fx_mass_change = 0.0;
+        L.fx_cur = 0;
+        L.fx_nx = (f.n > 1) ? 1 : -1;
+        L.fx_l = 1;
+        L.fx_resume = false;
+        L.me_phase = 2;
+      }
     }
-    if (correction == 3) {
-      bottom_flux += lg_cross_domain_boundary(c);
-      if (isnan(bottom_flux)) bottom_flux = 0.0;
+    if (L.me_phase == 2) {
+      if (lg_fix_run(L)) return true;
+      L.AET = L.AET - L.fx_mass_change;
+      L.me_phase = 1;
     }
-    if (correction == 4) {
-      double mass_change = 0.0;
-      lg_fix_dry_over_wet(c, &mass_change);
-      L.AET = L.AET - mass_change;
-    }
-    correction = lg_correction_type(c);
+    L.me_correction = lg_correction_type(c);
   }
   for (int i = 0; i < f.n; i++) {
     const LgarLayer& sk = cls.lay[f.layer[i]];
@@ -398,7 +586,8 @@ LG_FN_NOINLINE double lg_move_end(LgLane& L) {
   if (f.n == 1) {
     if (f.depth[0] != cls.cum[1]) f.depth[0] = cls.cum[1];
   }
-  return bottom_flux;
+  L.me_phase = 3;  // done
+  return false;
 }
 
 // ---- lg_step_active as cycle_begin / cycle_end ------------------------------------------------------
@@ -514,20 +703,25 @@ LG_FN_NOINLINE void lg_cycle_begin(const LgarConfig& cfg, LgLane& L) {
     else {
       L.nwf = 0;
       L.wf = 0;  // skip the front loop (and the corrections) of a failed column
+      L.me_phase = 0;
     }
   }
 }
 
-// From the end of the front loop to the end of the sub-cycle (bmi_lgar.cxx:553-805).  Returns true
-// when the forcing step is complete, false when another sub-cycle has been started.
-LG_FN_NOINLINE bool lg_cycle_end(const LgarConfig& cfg, LgLane& L) {
+// From the end of the front loop to the end of the sub-cycle (bmi_lgar.cxx:553-805).  Returns 1 when the
+// forcing step is complete, 0 when another sub-cycle has been started, 2 when a correction search has
+// to iterate first (call again afterwards).
+LG_FN_NOINLINE int lg_cycle_end(const LgarConfig& cfg, LgLane& L) {
   LgCtx& c = L.c;
   LgFronts& f = L.f;
   LgScalars& s = L.s;
   const LgarColumnClass& cls = *L.cls;
   const double dt = L.pro.subtimestep_h;
   LgCycle& cy = L.cy;
-  if (L.nwf != 0 || L.create) L.temp_rch = lg_move_end(L);
+  if ((L.nwf != 0 || L.create) && L.me_phase != 3) {
+    if (lg_move_end(L)) return 2;
+    L.temp_rch = L.bottom_flux;
+  }
   if (L.create) {  // :565-576, then the bookkeeping branch :619-632
     double dry_depth = lg_calc_dry_depth(c, dt);
     lg_create_surficial_front(c, &L.ponded, &L.volin, dry_depth, f.theta[0]);
@@ -571,7 +765,7 @@ LG_FN_NOINLINE bool lg_cycle_end(const LgarConfig& cfg, LgLane& L) {
   if (!(c.status & LGAR_FAIL_MASK) && L.cycle < L.pro.subcycles) {
     L.cycle++;
     lg_cycle_begin(cfg, L);
-    return false;
+    return 0;
   }
   int tbc = 0;  // :824-834
   for (int i = 0; i < f.n; i++) tbc += f.tb[i] ? 1 : 0;
@@ -583,7 +777,7 @@ LG_FN_NOINLINE bool lg_cycle_end(const LgarConfig& cfg, LgLane& L) {
   s.storage = L.volend_sub;
   s.fd_dzdt = f.dzdt[lg_wf_free_drainage(f) - 1];
   s.status |= c.status;
-  return true;
+  return 1;
 }
 
 // ---- stages -----------------------------------------------------------------------------------------
@@ -637,8 +831,13 @@ LG_FN void lg_stage_front(LgLane& L) { L.stage = lg_move_fronts(L) ? LG_ST_SEARC
 
 // TAIL: ends in FRONT (next sub-cycle) or FETCH (step finished, state written back)
 LG_FN_NOINLINE void lg_stage_tail(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, LgLane& L, unsigned long long* front_sum) {
-  if (!lg_cycle_end(cfg, L)) {
+  const int r = lg_cycle_end(cfg, L);
+  if (r == 0) {
     L.stage = LG_ST_FRONT;
+    return;
+  }
+  if (r == 2) {
+    L.stage = LG_ST_CORR;
     return;
   }
   const int64_t col = L.col;
@@ -663,7 +862,17 @@ LG_FN_NOINLINE void lg_stage_fetch(const LgarConfig& cfg, const LgarDeviceState&
 #else
       const int64_t col = atomicAdd(w.tile_counter, 1);
 #endif
+#ifndef LGAR_HOSTSIM
+      if (w.done_columns && L.col >= 0) atomicAdd(w.done_columns, 1);
+#endif
+      if (w.work_trace && L.col >= 0) {
+        w.work_trace[L.col] = L.tr_iters;
+        w.work_trace[w.trace_stride + L.col] = L.tr_kcyc;
+      }
+      L.tr_iters = 0;
+      L.tr_kcyc = 0;
       if (col >= d.ncol) {
+        L.col = -1;
         L.stage = LG_ST_DONE;
         return;
       }

@@ -85,26 +85,37 @@ LG_FN double lg_sq(double x) { return x * x; }
 // (<= 1e-14 relative on this path) -- five orders below the 1e-9 parity bar and the same kind of
 // last-bits noise as CUDA pow vs glibc pow.  Edge cases used on the path: 0^y = 0 (y > 0), 0^-y = inf,
 // 1^y = 1, inf^y = inf, negative base = NaN -- all follow from log/exp.
-LG_FN double lg_pow(double x, double y) { return exp(y * log(x)); }
+//
+// Code size matters as much as instruction count here: with every exp/log inlined the lanes kernel
+// was 437 KB of SASS and warps, each at a different place of the column program, stalled 26 of 34
+// cycles per instruction on instruction fetch (ncu smsp__average_warps_issue_stalled_no_instruction,
+// profiles/r1_lanes_icache.md).  So exp and log exist ONCE as out-of-line functions and the soil
+// functions are out of line too; only the psi-search iteration keeps its own inlined copies.
+LG_FN_NOINLINE double lg_exp(double x) { return exp(x); }
+LG_FN_NOINLINE double lg_log(double x) { return log(x); }
+LG_FN double lg_pow(double x, double y) { return lg_exp(y * lg_log(x)); }
 
-// calc_theta_from_h with log(h) supplied: the psi search evaluates every layer at the same psi
+// calc_theta_from_h with log(h) supplied, fully inlined: the psi search evaluates every layer at the same psi
 LG_FN double lg_theta_from_lnh(double lnh, const LgarLayer& s) {
   const double y = exp(s.n * (s.ln_alpha + lnh));       // (alpha*h)^n
   return exp(-s.m * log(1.0 + y)) * s.de + s.theta_r;   // 1/(1+y)^m * (theta_e-theta_r) + theta_r
 }
 // calc_theta_from_h, soil_funcs.cxx:147-150
-LG_FN double lg_theta_from_h(double h, const LgarLayer& s) { return lg_theta_from_lnh(log(h), s); }
+LG_FN_NOINLINE double lg_theta_from_h(double h, const LgarLayer& s) {
+  const double y = lg_exp(s.n * (s.ln_alpha + lg_log(h)));
+  return lg_exp(-s.m * lg_log(1.0 + y)) * s.de + s.theta_r;
+}
 // calc_Se_from_h, soil_funcs.cxx:155-159
-LG_FN double lg_Se_from_h(double h, const LgarLayer& s) {
+LG_FN_NOINLINE double lg_Se_from_h(double h, const LgarLayer& s) {
   if (fabs(h) < 1.0E-10) return 1.0;
-  return exp(-s.m * log(1.0 + exp(s.n * (s.ln_alpha + log(h)))));
+  return lg_exp(-s.m * lg_log(1.0 + lg_exp(s.n * (s.ln_alpha + lg_log(h)))));
 }
 // calc_K_from_Se, soil_funcs.cxx:164-167 (pow(x,2.0) -> x*x)
-LG_FN double lg_K_from_Se(double Se, const LgarLayer& s) {
+LG_FN_NOINLINE double lg_K_from_Se(double Se, const LgarLayer& s) {
   return s.Ksat * sqrt(Se) * lg_sq(1.0 - lg_pow(1.0 - lg_pow(Se, s.inv_m), s.m));
 }
 // calc_h_from_Se, soil_funcs.cxx:172-179
-LG_FN double lg_h_from_Se(double Se, const LgarLayer& s) {
+LG_FN_NOINLINE double lg_h_from_Se(double Se, const LgarLayer& s) {
   double r = s.inv_alpha * lg_pow(lg_pow(Se, s.neg_inv_m) - 1.0, s.inv_n);
   if (r > 1.E20) r = 1.E20;
   return r;
@@ -208,7 +219,7 @@ LG_FN void lg_front_insert_first(LgCtx& c, double depth, double theta, int layer
 // ------------------------------------------------------------------------------------------------
 
 // lgar_calc_mass_bal, lgar.cxx:2632-2668
-LG_FN double lg_mass_bal(const LgCtx& c) {
+LG_FN_NOINLINE double lg_mass_bal(const LgCtx& c) {
   const LgFronts& f = *c.f;
   const double* cum = c.cls->cum;
   double sum = 0.0;
@@ -634,7 +645,7 @@ LG_FN_NOINLINE void lg_fix_dry_over_wet(LgCtx& c, double* mass_change) {
 }
 
 // lgarto_correction_type_surf, lgar.cxx:3116-3169
-LG_FN int lg_correction_type(const LgCtx& c) {
+LG_FN_NOINLINE int lg_correction_type(const LgCtx& c) {
   const LgFronts& f = *c.f;
   const double* cum = c.cls->cum;
   const int num_layers = c.cls->num_layers;
@@ -657,7 +668,7 @@ LG_FN int lg_correction_type(const LgCtx& c) {
 }
 
 // lgar_clean_redundant_fronts, lgar.cxx:3171-3195
-LG_FN void lg_clean_redundant(LgCtx& c) {
+LG_FN_NOINLINE void lg_clean_redundant(LgCtx& c) {
   LgFronts& f = *c.f;
   int cur = 0;
   for (int wf = 1; wf != f.n; wf++) {
@@ -932,7 +943,7 @@ LG_FN_NOINLINE double lg_insert_water(LgCtx& c, double timestep_h, double AET_de
 }
 
 // lgar_calc_dry_depth, lgar.cxx:2577-2626
-LG_FN double lg_calc_dry_depth(LgCtx& c, double timestep_h) {
+LG_FN_NOINLINE double lg_calc_dry_depth(LgCtx& c, double timestep_h) {
   const LgFronts& f = *c.f;
   const int layer_num = f.layer[0];
   const LgarLayer& sp = c.cls->lay[layer_num];
@@ -1056,7 +1067,7 @@ LG_FN double lg_calc_aet(const LgCtx& c, double PET_cm_per_h, double dt_h) {
 }
 
 // calc_CR_Q, src/conceptual_reservoir.cxx:7-45
-LG_FN double lg_calc_CR_Q(const LgarConfig& cfg, double dt, double in_cm_per_h, double* fast, double* slow) {
+LG_FN_NOINLINE double lg_calc_CR_Q(const LgarConfig& cfg, double dt, double in_cm_per_h, double* fast, double* slow) {
   double input_slow = in_cm_per_h * cfg.frac_slow;
   double input_fast = in_cm_per_h - input_slow;
   double Q_fast = 0.0;
@@ -1097,7 +1108,7 @@ struct LgPrologue {
 };
 
 // adaptive sub-step + flux-cache decision, bmi_lgar.cxx:260-318.  Pure: commits nothing.
-LG_FN LgPrologue lg_prologue(const LgarConfig& cfg, const LgScalars& s, double precip_mm_h) {
+LG_FN_NOINLINE LgPrologue lg_prologue(const LgarConfig& cfg, const LgScalars& s, double precip_mm_h) {
   LgPrologue p;
   double timestep_h = s.timestep_h;
   p.subtimestep_h = timestep_h;
@@ -1141,7 +1152,7 @@ struct LgCycle {
   bool top_near_sat;
 };
 
-LG_FN double lg_cycle_tail(const LgarConfig& cfg, LgScalars& s, LgCycle& cy, double dt, double volend, LgStepVols& v) {
+LG_FN_NOINLINE double lg_cycle_tail(const LgarConfig& cfg, LgScalars& s, LgCycle& cy, double dt, double volend, LgStepVols& v) {
   s.precip_prev = cy.precip_sub;
   double volCRstart = s.cr_fast + s.cr_slow;
   double volQ_CR = lg_calc_CR_Q(cfg, dt, cy.precip_for_CR + cy.ponded_flux_for_CR + cy.fd_for_CR / dt, &s.cr_fast, &s.cr_slow);
@@ -1189,7 +1200,7 @@ LG_FN void lg_cycle_head(const LgarConfig& cfg, const LgScalars& s, LgCycle& cy,
 }
 
 // A forcing step that replays cached fluxes (bmi_lgar.cxx:683-695): one sub-cycle, fronts untouched.
-LG_FN void lg_step_cached(const LgarConfig& cfg, LgScalars& s, const LgPrologue& pro, double precip_mm_h, double pet_mm_h, LgStepVols& v) {
+LG_FN_NOINLINE void lg_step_cached(const LgarConfig& cfg, LgScalars& s, const LgPrologue& pro, double precip_mm_h, double pet_mm_h, LgStepVols& v) {
   const double dt = pro.subtimestep_h;
   double volon_ts = s.volon, PET_rate, ponded;
   LgCycle cy;

@@ -15,7 +15,7 @@
 #define LG_NAN CUDART_NAN
 #endif
 
-LG_FN void load_scalars(const LgarDeviceState& d, int64_t col, LgScalars& s) {
+LG_FN_NOINLINE void load_scalars(const LgarDeviceState& d, int64_t col, LgScalars& s) {
   const double* p = d.scal + col;
   const int64_t st = d.stride;
   s.volon = p[LGAR_S_VOLON * st];
@@ -37,7 +37,7 @@ LG_FN void load_scalars(const LgarDeviceState& d, int64_t col, LgScalars& s) {
   s.status = d.status[col];
 }
 
-LG_FN void store_scalars(const LgarDeviceState& d, int64_t col, const LgScalars& s, bool active) {
+LG_FN_NOINLINE void store_scalars(const LgarDeviceState& d, int64_t col, const LgScalars& s, bool active) {
   double* p = d.scal + col;
   const int64_t st = d.stride;
   p[LGAR_S_VOLON * st] = s.volon;
@@ -58,7 +58,7 @@ LG_FN void store_scalars(const LgarDeviceState& d, int64_t col, const LgScalars&
   d.status[col] = s.status;
 }
 
-LG_FN void load_fronts(const LgarDeviceState& d, int64_t col, LgFronts& f) {
+LG_FN_NOINLINE void load_fronts(const LgarDeviceState& d, int64_t col, LgFronts& f) {
   const int n = d.nfront[col];
   const unsigned long long fl = d.fflags[col];
   f.n = n;
@@ -76,7 +76,7 @@ LG_FN void load_fronts(const LgarDeviceState& d, int64_t col, LgFronts& f) {
   }
 }
 
-LG_FN void store_fronts(const LgarDeviceState& d, int64_t col, const LgFronts& f) {
+LG_FN_NOINLINE void store_fronts(const LgarDeviceState& d, int64_t col, const LgFronts& f) {
   unsigned long long fl = 0ull;
 #pragma unroll 1
   for (int i = 0; i < f.n; i++) {
@@ -94,7 +94,7 @@ LG_FN void store_fronts(const LgarDeviceState& d, int64_t col, const LgFronts& f
 
 // GIUH convolution (giuh/giuh.c:12-39; input in cm, quirk Q12), outputs in metres
 // (bmi_lgar.cxx:808-893) and the cumulative volumes of the global balance (lgar.cxx:1162-1185).
-LG_FN void epilogue(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int64_t col,
+LG_FN_NOINLINE void epilogue(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int64_t col,
                     const LgStepVols& v, int status, bool write_out = true) {
   const int64_t st = d.stride;
   if (status & LGAR_FAIL_MASK) {

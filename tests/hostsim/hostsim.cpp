@@ -81,6 +81,9 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
               while (!L.q.done) lg_search_iter(L.q, *L.cls);
               L.resume = true; L.stage = LG_ST_FRONT; break;
             case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, nullptr); break;
+            case LG_ST_CORR:
+              while (!L.k.done) lg_corr_iter(L.k, L.f, *L.cls);
+              L.stage = LG_ST_TAIL; break;
           }
         }
       } else {
