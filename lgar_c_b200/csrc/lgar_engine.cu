@@ -529,39 +529,58 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
   CUDA_TRY(lgar_launch_wave_init(wv, e->stream));
   e->launches += 1;
   int par[LGAR_NSTAGE] = {0, 0, 0, 0, 0, 0};
+  int quantum = e->wave_quantum;
+  int in_flight = wv.nslots;
   auto launch = [&](int stage) {
     const int consume = par[stage];
     par[stage] ^= 1;
     unsigned mask = 0;
     for (int s = 0; s < LGAR_NSTAGE; s++) mask |= (unsigned)par[s] << s;
-    CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, e->wave_quantum, e->stream));
+    CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, quantum, in_flight, e->stream));
     e->launches += 2;
   };
-  int32_t* h_done = (int32_t*)e->pinned(64 * sizeof(int32_t));
+  int32_t* h_cnt = (int32_t*)e->pinned(64 * sizeof(int32_t));
   const bool debug = getenv("LGARB_WAVE_DEBUG") != nullptr;
   cudaEvent_t dbg[2];
   if (debug) {
     cudaEventCreate(&dbg[0]);
     cudaEventCreate(&dbg[1]);
   }
+  // Every round starts with the queue counts on the host (48 bytes): the number of slots in flight bounds
+  // every queue of the round (grid size), empty parts of the round are not launched, and the window is over
+  // when nothing is in flight.
+  int cnt[LGAR_NSTAGE] = {wv.nslots, 0, 0, 0, 0, 0};
   for (int64_t round = 0;; round++) {
-    if (debug) {
-      CUDA_TRY(cudaMemcpyAsync(h_done + 1, wv.qcount, 12 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-      CUDA_TRY(cudaMemcpyAsync(h_done, wv.done_columns, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (round > 0) {
+      CUDA_TRY(cudaMemcpyAsync(h_cnt, wv.qcount, 2 * LGAR_NSTAGE * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
       CUDA_TRY(cudaStreamSynchronize(e->stream));
-      cudaEventRecord(dbg[0], e->stream);
+      in_flight = 0;
+      for (int s = 0; s < LGAR_NSTAGE; s++) {
+        cnt[s] = h_cnt[2 * s] + h_cnt[2 * s + 1];
+        in_flight += cnt[s];
+      }
+      if (in_flight == 0) break;
+      if (round > 100000000) throw std::runtime_error("wavefront scheduler did not terminate");
     }
-    launch(0);  // FETCH
-    launch(1);  // HEAD
-    for (int k = 0; k < e->wave_pairs; k++) {
-      launch(2);  // FRONT
-      launch(3);  // SEARCH
+    // late rounds hold the few long searches (up to 1e5 trips): let them run longer per launch
+    if (round >= 12 && (round % 4) == 0 && quantum < 8192) quantum *= 2;
+    if (debug) cudaEventRecord(dbg[0], e->stream);
+    const bool new_steps = cnt[LG_ST_FETCH] + cnt[LG_ST_HEAD] > 0;
+    if (new_steps) {
+      launch(LG_ST_FETCH);
+      launch(LG_ST_HEAD);
     }
-    launch(2);  // FRONT
-    launch(4);  // TAIL
+    if (new_steps || cnt[LG_ST_FRONT] + cnt[LG_ST_SEARCH] > 0) {
+      for (int k = 0; k < e->wave_pairs; k++) {
+        launch(LG_ST_FRONT);
+        launch(LG_ST_SEARCH);
+      }
+      launch(LG_ST_FRONT);
+    }
+    launch(LG_ST_TAIL);
     for (int k = 0; k < e->wave_corr_pairs; k++) {
-      launch(5);  // CORR
-      launch(4);  // TAIL
+      launch(LG_ST_CORR);
+      launch(LG_ST_TAIL);
     }
     e->wave_rounds++;
     if (debug) {
@@ -570,16 +589,13 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       float ms = 0;
       cudaEventElapsedTime(&ms, dbg[0], dbg[1]);
       if (round < 40 || round % 20 == 0)
-        fprintf(stderr, "[wave] round %lld: %.3f ms  done=%d  queues(before) F=%d H=%d FR=%d S=%d T=%d C=%d\n", (long long)round, ms, h_done[0],
-                h_done[1] + h_done[2], h_done[3] + h_done[4], h_done[5] + h_done[6], h_done[7] + h_done[8], h_done[9] + h_done[10],
-                h_done[11] + h_done[12]);
+        fprintf(stderr, "[wave] round %lld: %.3f ms  in flight %d  queues(before) F=%d H=%d FR=%d S=%d T=%d C=%d\n", (long long)round, ms, in_flight,
+                cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], cnt[5]);
     }
-    if ((round % e->wave_poll) == e->wave_poll - 1) {
-      CUDA_TRY(cudaMemcpyAsync(h_done, wv.done_columns, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-      CUDA_TRY(cudaStreamSynchronize(e->stream));
-      if (*h_done >= e->ncol) break;
-      if (round > 100000000) throw std::runtime_error("wavefront scheduler did not terminate");
-    }
+  }
+  if (debug) {
+    cudaEventDestroy(dbg[0]);
+    cudaEventDestroy(dbg[1]);
   }
 }
 }  // namespace

@@ -18,6 +18,9 @@
 // HBM-bound in the stream kernel, FP64-pipe-bound in the active kernel; no tensor-core work exists
 // on this path (nothing is a contraction).
 #include <cuda_runtime.h>
+
+#include <algorithm>
+
 #include "lgar_lanes.cuh"
 
 
@@ -382,8 +385,9 @@ cudaError_t lgar_launch_wave_init(const LgarWave& wv, cudaStream_t stream) {
 }
 
 cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int stage, int consume,
-                                   unsigned append_mask, int quantum, cudaStream_t stream) {
-  const int blocks = (wv.nslots + 127) / 128;
+                                   unsigned append_mask, int quantum, int max_items, cudaStream_t stream) {
+  // grid-stride over the queue; max_items (slots in flight at the start of the round) bounds every queue
+  const int blocks = std::max(1, std::min((std::min(wv.nslots, max_items) + 127) / 128, 148 * 16));
   switch (stage) {
     case LG_ST_FETCH: lgar_wave_kernel<LG_ST_FETCH><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
     case LG_ST_HEAD: lgar_wave_kernel<LG_ST_HEAD><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;

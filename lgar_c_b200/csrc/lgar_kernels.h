@@ -40,6 +40,8 @@ struct LgarWindow {
 // compacted queue pair per stage (see lgar_kernels.cu).
 struct LgLane;
 #define LGAR_NSTAGE 6
+// stages of the resumable column program (lgar_lanes.cuh)
+enum { LG_ST_FETCH = 0, LG_ST_HEAD = 1, LG_ST_FRONT = 2, LG_ST_SEARCH = 3, LG_ST_TAIL = 4, LG_ST_CORR = 5, LG_ST_DONE = 6 };
 struct LgarWave {
   LgLane* ctx;                 // [nslots]
   int32_t* queue[LGAR_NSTAGE][2];  // slot ids
@@ -51,7 +53,7 @@ struct LgarWave {
 #ifndef LGAR_HOSTSIM
 // one launch of the kernel of `stage`, consuming queue[stage][consume]; append_mask bit s = buffer of stage s to append to
 cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int stage, int consume,
-                                   unsigned append_mask, int quantum, cudaStream_t stream);
+                                   unsigned append_mask, int quantum, int max_items, cudaStream_t stream);
 cudaError_t lgar_launch_wave_init(const LgarWave& wv, cudaStream_t stream);
 size_t lgar_lane_context_bytes();
 // mode 1: warp-tile window kernel; mode 2: per-lane staged program (lgar_lanes.cuh)

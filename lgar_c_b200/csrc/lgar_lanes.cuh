@@ -24,7 +24,6 @@
 
 #include "lgar_step.cuh"
 
-enum { LG_ST_FETCH = 0, LG_ST_HEAD = 1, LG_ST_FRONT = 2, LG_ST_SEARCH = 3, LG_ST_TAIL = 4, LG_ST_CORR = 5, LG_ST_DONE = 6 };
 
 struct LgSearch {  // one psi search in flight
   double psi_loc, factor, psi_prev, delta_mass, delta_mass_prev, new_mass, prior_mass, precip_mass_to_add, theta;
