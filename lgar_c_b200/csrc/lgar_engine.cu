@@ -531,11 +531,19 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
   int par[LGAR_NSTAGE] = {0, 0, 0, 0, 0, 0};
   int quantum = e->wave_quantum;
   int in_flight = wv.nslots;
+  const bool dbg_on = getenv("LGARB_WAVE_DEBUG") != nullptr;
+  std::vector<std::pair<cudaEvent_t, int>> dbg_evs;
   auto launch = [&](int stage) {
     const int consume = par[stage];
     par[stage] ^= 1;
     unsigned mask = 0;
     for (int s = 0; s < LGAR_NSTAGE; s++) mask |= (unsigned)par[s] << s;
+    if (dbg_on) {
+      dbg_evs.emplace_back();
+      cudaEventCreate(&dbg_evs.back().first);
+      cudaEventRecord(dbg_evs.back().first, e->stream);
+      dbg_evs.back().second = stage;
+    }
     CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, quantum, in_flight, e->stream));
     e->launches += 2;
   };
@@ -562,8 +570,8 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       if (in_flight == 0) break;
       if (round > 100000000) throw std::runtime_error("wavefront scheduler did not terminate");
     }
-    // late rounds hold the few long searches (up to 1e5 trips): let them run longer per launch
-    if (round >= 12 && (round % 4) == 0 && quantum < 8192) quantum *= 2;
+    // few slots in flight = the long searches (up to 1e5 trips) are what is left: let them run longer per launch
+    quantum = in_flight > 65536 ? e->wave_quantum : in_flight > 8192 ? 4 * e->wave_quantum : in_flight > 1024 ? 32 * e->wave_quantum : 256 * e->wave_quantum;
     if (debug) cudaEventRecord(dbg[0], e->stream);
     const bool new_steps = cnt[LG_ST_FETCH] + cnt[LG_ST_HEAD] > 0;
     if (new_steps) {
@@ -588,6 +596,17 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       cudaEventSynchronize(dbg[1]);
       float ms = 0;
       cudaEventElapsedTime(&ms, dbg[0], dbg[1]);
+      float st_ms[LGAR_NSTAGE] = {0, 0, 0, 0, 0, 0};
+      for (size_t i = 0; i < dbg_evs.size(); i++) {
+        float x = 0;
+        cudaEventElapsedTime(&x, dbg_evs[i].first, i + 1 < dbg_evs.size() ? dbg_evs[i + 1].first : dbg[1]);
+        st_ms[dbg_evs[i].second] += x;
+      }
+      for (auto& pe : dbg_evs) cudaEventDestroy(pe.first);
+      dbg_evs.clear();
+      if (round < 40 || round % 20 == 0)
+        fprintf(stderr, "[wave]   stage ms: FETCH %.2f HEAD %.2f FRONT %.2f SEARCH %.2f TAIL %.2f CORR %.2f\n", st_ms[0], st_ms[1], st_ms[2], st_ms[3],
+                st_ms[4], st_ms[5]);
       if (round < 40 || round % 20 == 0)
         fprintf(stderr, "[wave] round %lld: %.3f ms  in flight %d  queues(before) F=%d H=%d FR=%d S=%d T=%d C=%d\n", (long long)round, ms, in_flight,
                 cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], cnt[5]);

@@ -261,6 +261,78 @@ LG_FN LgarSinks lg_sinks_at(const LgarWindow& w, int t) {
   return s;
 }
 
+// GIUH queue and cumulative volumes of one column held in thread-private memory while the column is
+// walked through many hours (same arithmetic, same order as epilogue()).
+struct LgEpi {
+  double q[LGAR_MAXG];
+  double cum[LGAR_NCUM];
+};
+LG_FN void lg_epi_load(const LgarConfig& cfg, const LgarDeviceState& d, int64_t col, LgEpi& e) {
+  const int64_t st = d.stride;
+  for (int i = 0; i + 1 < cfg.num_giuh; i++) e.q[i] = d.giuhq[(int64_t)i * st + col];
+#pragma unroll
+  for (int k = 0; k < LGAR_NCUM; k++) e.cum[k] = d.cum[(int64_t)k * st + col];
+}
+LG_FN void lg_epi_store(const LgarConfig& cfg, const LgarDeviceState& d, int64_t col, const LgEpi& e) {
+  const int64_t st = d.stride;
+  for (int i = 0; i + 1 < cfg.num_giuh; i++) d.giuhq[(int64_t)i * st + col] = e.q[i];
+#pragma unroll
+  for (int k = 0; k < LGAR_NCUM; k++) d.cum[(int64_t)k * st + col] = e.cum[k];
+}
+LG_FN void lg_epi_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int64_t col, LgEpi& e, const LgStepVols& v,
+                       int status, bool write_out) {
+  const int64_t st = d.stride;
+  if (status & LGAR_FAIL_MASK) {
+    const double nan = LG_NAN;
+    for (int k = 0; k < LGAR_NOUT; k++) {
+      if (write_out) d.out[k * st + col] = nan;
+      if (sinks.p[k]) sinks.p[k][col] = nan;
+    }
+    return;
+  }
+  const int N = cfg.num_giuh;
+  const double r = v.volrunoff + v.volQ_CR;
+  const double carry = (N > 1) ? e.q[0] : 0.0;
+  const double now = carry + cfg.giuh[0] * r;
+  for (int i = 1; i < N; i++) {
+    double qi = (i < N - 1) ? e.q[i] : 0.0;
+    qi += cfg.giuh[i] * r;
+    e.q[i - 1] = qi;
+  }
+  e.cum[LGAR_CUM_PRECIP] += v.precip;
+  e.cum[LGAR_CUM_IN] += v.volin;
+  e.cum[LGAR_CUM_AET] += v.AET;
+  e.cum[LGAR_CUM_RECH] += v.volrech;
+  e.cum[LGAR_CUM_RUNOFF] += v.volrunoff;
+  e.cum[LGAR_CUM_Q] += now;
+  e.cum[LGAR_CUM_Q_CR] += v.volQ_CR;
+  e.cum[LGAR_CUM_PET] += v.PET;
+  e.cum[LGAR_CUM_GIUH] += now;
+  e.cum[LGAR_CUM_RUNOFF_CR] += v.volQ_CR;
+  bool any_sink = write_out;
+#pragma unroll
+  for (int k = 0; k < LGAR_NOUT; k++) any_sink = any_sink || (sinks.p[k] != nullptr);
+  if (!any_sink) return;
+  const double cm_to_m = 0.01;
+  double o[LGAR_NOUT];
+  o[LGAR_OUT_PRECIP] = v.precip * cm_to_m;
+  o[LGAR_OUT_PET] = v.PET * cm_to_m;
+  o[LGAR_OUT_AET] = v.AET * cm_to_m;
+  o[LGAR_OUT_RUNOFF] = v.volrunoff * cm_to_m;
+  o[LGAR_OUT_GIUH_RUNOFF] = now * cm_to_m;
+  o[LGAR_OUT_STORAGE] = v.volend * cm_to_m;
+  o[LGAR_OUT_Q] = now * cm_to_m;
+  o[LGAR_OUT_INFIL] = v.volin * cm_to_m;
+  o[LGAR_OUT_PERC] = v.volrech * cm_to_m;
+  o[LGAR_OUT_Q_CR] = v.volQ_CR * cm_to_m;
+  o[LGAR_OUT_MBAL] = v.local_mb * cm_to_m;
+  o[LGAR_OUT_CR_STORAGE] = v.volCRend * cm_to_m;
+  for (int k = 0; k < LGAR_NOUT; k++) {
+    if (write_out) d.out[k * st + col] = o[k];
+    if (sinks.p[k]) sinks.p[k][col] = o[k];
+  }
+}
+
 // Advance one column from hour t through every step that needs no flux computation (cached-flux
 // replay, invalid soil, failed column), scalars held in registers across hours.  Returns the hour at
 // which the column needs an active step, or w.K when it reached the end of the window.
@@ -279,7 +351,8 @@ LG_FN_NOINLINE int lg_advance_column(const LgarConfig& cfg, const LgarDeviceStat
   LgScalars s;
   load_scalars(d, col, s);
   const int nf = (w.nf_sink || front_sum) ? d.nfront[col] : 0;
-  bool dirty = false;
+  bool dirty = false, epi_loaded = false;
+  LgEpi ep;
   for (; t < K; t++) {
     double P = w.precip[(int64_t)t * w.series_stride + col], E = w.pet[(int64_t)t * w.series_stride + col];
     LgStepVols v;
@@ -295,11 +368,16 @@ LG_FN_NOINLINE int lg_advance_column(const LgarConfig& cfg, const LgarDeviceStat
       if (!(fabs(v.local_mb) <= cfg.mbal_tol)) s.status |= (isnan(v.local_mb) ? LGAR_FAIL_NAN : LGAR_FAIL_MBAL);
       dirty = true;
     }
+    if (!epi_loaded) {
+      lg_epi_load(cfg, d, col, ep);
+      epi_loaded = true;
+    }
     const LgarSinks sk = lg_sinks_at(w, t);
-    epilogue(cfg, d, sk, col, v, s.status, t == K - 1);
+    lg_epi_step(cfg, d, sk, col, ep, v, s.status, t == K - 1);
     if (w.nf_sink) w.nf_sink[(int64_t)t * w.sink_stride + col] = nf;
     if (front_sum) *front_sum += (unsigned)nf;
   }
+  if (epi_loaded) lg_epi_store(cfg, d, col, ep);
   if (dirty) store_scalars(d, col, s, false);
   return t;
 }
