@@ -104,6 +104,12 @@ int lgarb_update_until(lgarb_engine* e, double t);
 int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_precip_mm_per_h,
                               const double* d_pet_mm_per_h, int64_t series_stride,
                               double* const* d_sinks, int64_t sink_stride, int32_t* d_nfronts_sink);
+/* The same with HOST buffers (what a framework feeding forcing chunks would call): h_precip / h_pet
+ * are [n_steps][n_columns] (mm/h, ideally pinned); output_names lists n_outputs per-step scalar
+ * variables and h_outputs[i] receives [n_steps][n_columns] values of output_names[i].  Host<->device
+ * copies are part of the call; it returns when the outputs are in place. */
+int lgarb_update_steps_host(lgarb_engine* e, int64_t n_steps, const double* h_precip_mm_per_h, const double* h_pet_mm_per_h,
+                            int n_outputs, const char* const* output_names, double* const* h_outputs);
 int lgarb_synchronize(lgarb_engine* e);
 
 /* ---- variable access (BMI getters/setters) -------------------------------------------------- */

@@ -67,6 +67,7 @@ def _load():
         "lgarb_update": ([vp], C.c_int),
         "lgarb_update_until": ([vp, C.c_double], C.c_int),
         "lgarb_update_steps_device": ([vp, i64, vp, vp, i64, vp, i64, vp], C.c_int),
+        "lgarb_update_steps_host": ([vp, i64, vp, vp, C.c_int, vp, vp], C.c_int),
         "lgarb_synchronize": ([vp], C.c_int),
         "lgarb_set_value": ([vp, cp, vp], C.c_int),
         "lgarb_set_value_range": ([vp, cp, i64, i64, vp], C.c_int),
@@ -194,6 +195,20 @@ class BmiLGARBatch:
         self._ck(self._L.lgarb_update_steps_device(self._h, int(n_steps), C.c_void_p(int(d_precip)), C.c_void_p(int(d_pet)),
                                                     int(series_stride), arr, int(sink_stride),
                                                     C.c_void_p(int(nfronts_sink)) if nfronts_sink else None))
+
+    def update_steps_host(self, precip, pet, outputs=()):
+        """precip/pet: host arrays [n_steps][n_columns] (mm/h).  outputs: {name: host array [n_steps][n_columns]}
+        filled in place (or a list of names: arrays are allocated and returned)."""
+        P = np.ascontiguousarray(precip, dtype=np.float64)
+        E = np.ascontiguousarray(pet, dtype=np.float64)
+        n_steps = P.shape[0]
+        if not isinstance(outputs, dict):
+            outputs = {n: np.empty((n_steps, self.n_columns)) for n in outputs}
+        names = list(outputs)
+        cn = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        cp = (C.c_void_p * len(names))(*[outputs[n].ctypes.data for n in names])
+        self._ck(self._L.lgarb_update_steps_host(self._h, int(n_steps), _ptr(P), _ptr(E), len(names), cn, cp))
+        return outputs
 
     def synchronize(self):
         self._ck(self._L.lgarb_synchronize(self._h))

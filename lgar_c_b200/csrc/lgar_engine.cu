@@ -79,6 +79,8 @@ struct lgarb_engine {
   int use_window = 2;          // multi-step runs: 2 = lanes kernel, 1 = warp-tile window kernel, 0 = hour-by-hour kernel pairs
   int lanes_blocks = 0;
   unsigned int* d_work_trace = nullptr;  // [2][stride], allocated by lgarb_set_work_trace
+  double* d_host_series = nullptr;  // staging of lgarb_update_steps_host
+  size_t host_series_cap = 0;
   // wavefront scheduler (mode 3)
   LgarWave wave;
   bool wave_ready = false;
@@ -123,6 +125,9 @@ struct lgarb_engine {
     if (stream) cudaStreamSynchronize(stream);
     d_work_trace = nullptr;
     wave_ready = false;
+    if (d_host_series) cudaFree(d_host_series);
+    d_host_series = nullptr;
+    host_series_cap = 0;
     for (cudaEvent_t x : ev_pool) cudaEventDestroy(x);
     for (int i = 0; i < 2; i++) {
       if (win_ev[i]) cudaEventDestroy(win_ev[i]);
@@ -678,6 +683,43 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
         e->time_s += K * e->cfg.forcing_resolution_h * 3600.0;
       }
     }
+  });
+}
+
+// Host-buffer variant of the multi-step call: forcing in, chosen outputs out, copies included.
+int lgarb_update_steps_host(lgarb_engine* e, int64_t n_steps, const double* h_precip, const double* h_pet, int n_outputs,
+                            const char* const* output_names, double* const* h_outputs) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (n_steps <= 0 || !h_precip || !h_pet) throw std::runtime_error("bad forcing series");
+    if (n_outputs < 0 || n_outputs > LGAR_NOUT) throw std::runtime_error("bad output count");
+    const size_t n = (size_t)n_steps * (size_t)e->ncol;
+    const size_t need = n * (2 + (size_t)n_outputs);
+    if (need > e->host_series_cap) {  // device staging for forcing + requested output series, grown on demand
+      if (e->d_host_series) {
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_host_series);
+        e->d_host_series = nullptr;
+        e->host_series_cap = 0;
+      }
+      CUDA_TRY(cudaMalloc((void**)&e->d_host_series, need * sizeof(double)));
+      e->host_series_cap = need;
+    }
+    double* dP = e->d_host_series;
+    double* dE = dP + n;
+    CUDA_TRY(cudaMemcpyAsync(dP, h_precip, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(dE, h_pet, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    double* sinks[LGAR_NOUT];
+    for (int k = 0; k < LGAR_NOUT; k++) sinks[k] = nullptr;
+    for (int i = 0; i < n_outputs; i++) {
+      int k = out_index(output_names[i]);
+      if (k < 0) throw std::runtime_error(std::string("variable ") + output_names[i] + " is not a per-step scalar output");
+      sinks[k] = dE + n * (size_t)(1 + i);
+    }
+    if (lgarb_update_steps_device(e, n_steps, dP, dE, e->ncol, sinks, e->ncol, nullptr) != LGARB_SUCCESS) throw std::runtime_error(e->last_error);
+    for (int i = 0; i < n_outputs; i++)
+      CUDA_TRY(cudaMemcpyAsync(h_outputs[i], dE + n * (size_t)(1 + i), n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
   });
 }
 

@@ -291,6 +291,8 @@ __global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDevi
                                                         unsigned append_mask, int quantum) {
   const int n = wv.qcount[STAGE * 2 + consume];
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
+  unsigned long long front_sum = 0, active_sum = 0;
+  unsigned long long* fsp = w.prof ? &front_sum : nullptr;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31); i += gridDim.x * blockDim.x) {
     const bool valid = i < n;
     const int slot = valid ? wv.queue[STAGE][consume][i] : 0;
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDevi
         L.t = G.t;
         L.tr_iters = 0;
         L.tr_kcyc = 0;
-        lg_stage_fetch(cfg, d, w, L, nullptr);
+        lg_stage_fetch(cfg, d, w, L, fsp);
         G.col = L.col;
         G.t = L.t;
         next = L.stage;
@@ -337,7 +339,8 @@ __global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDevi
         L.t = slots[slot].L.t;
         L.tr_iters = 0;
         L.tr_kcyc = 0;
-        lg_stage_head(cfg, d, w, L, nullptr);
+        lg_stage_head(cfg, d, w, L, fsp);
+        active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
       } else {
         ctx_copy(&S, &slots[slot]);
         L.c.cfg = &cfg;
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDevi
         if (STAGE == LG_ST_FRONT)
           lg_stage_front(L);
         else
-          lg_stage_tail(cfg, d, w, L, nullptr);
+          lg_stage_tail(cfg, d, w, L, fsp);
       }
       next = L.stage;
       if (next == LG_ST_FETCH) {
@@ -358,6 +361,10 @@ __global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDevi
     }
 #pragma unroll
     for (int s = 0; s < LGAR_NSTAGE; s++) wave_push(wv, append_mask, s, valid && next == s, slot);
+  }
+  if (w.prof && (STAGE == LG_ST_FETCH || STAGE == LG_ST_HEAD || STAGE == LG_ST_TAIL)) {
+    if (front_sum) atomicAdd(w.prof, front_sum);
+    if (active_sum) atomicAdd(w.prof + 1, active_sum);
   }
 }
 

@@ -131,7 +131,7 @@ LG_FN void lg_search_iter(LgSearch& q, const LgarColumnClass& cls) {
     q.psi_loc = 0.0;
     q.factor = q.factor * 0.5;
   }
-  const double lnpsi = log(q.psi_loc);
+  const double lnpsi = lg_lnh(q.psi_loc);
   q.theta = lg_theta_from_lnh(lnpsi, cls.lay[layer_num]);
   double mass_layers = 0.0;
   mass_layers += q.dz[layer_num] * (q.theta - q.dth[layer_num]);
@@ -448,7 +448,7 @@ LG_FN void lg_corr_iter(LgCorr& k, LgFronts& f, const LgarColumnClass& cls) {
     k.psi_loc = 0.0;
     k.factor = k.factor * 0.5;
   }
-  const double lnpsi = log(k.psi_loc);
+  const double lnpsi = lg_lnh(k.psi_loc);
   f.psi[cur] = k.psi_loc;
   f.theta[cur] = lg_theta_from_lnh(lnpsi, cls.lay[f.layer[cur]]);
   int nx = cur + 1, before = cur;

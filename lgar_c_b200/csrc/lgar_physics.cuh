@@ -93,6 +93,21 @@ LG_FN double lg_sq(double x) { return x * x; }
 // functions are out of line too; only the psi-search iteration keeps its own inlined copies.
 LG_FN_NOINLINE double lg_exp(double x) { return exp(x); }
 LG_FN_NOINLINE double lg_log(double x) { return log(x); }
+#ifdef LGAR_ACCURATE_POW
+// parity-first build: the library pow (<= 1-2 ulp, ~4x the instructions), out of line so the code stays small
+LG_FN_NOINLINE double lg_pow(double x, double y) { return pow(x, y); }
+LG_FN double lg_theta_from_lnh(double lnh, const LgarLayer& s) {  // lnh carries h itself in this build
+  return 1.0 / (lg_pow(1.0 + lg_pow(s.alpha * lnh, s.n), s.m)) * s.de + s.theta_r;
+}
+LG_FN double lg_lnh(double h) { return h; }
+LG_FN_NOINLINE double lg_theta_from_h(double h, const LgarLayer& s) {
+  return 1.0 / (lg_pow(1.0 + lg_pow(s.alpha * h, s.n), s.m)) * s.de + s.theta_r;
+}
+LG_FN_NOINLINE double lg_Se_from_h(double h, const LgarLayer& s) {
+  if (fabs(h) < 1.0E-10) return 1.0;
+  return 1.0 / (lg_pow(1.0 + lg_pow(s.alpha * h, s.n), s.m));
+}
+#else
 LG_FN double lg_pow(double x, double y) { return lg_exp(y * lg_log(x)); }
 
 // calc_theta_from_h with log(h) supplied, fully inlined: the psi search evaluates every layer at the same psi
@@ -100,6 +115,7 @@ LG_FN double lg_theta_from_lnh(double lnh, const LgarLayer& s) {
   const double y = exp(s.n * (s.ln_alpha + lnh));       // (alpha*h)^n
   return exp(-s.m * log(1.0 + y)) * s.de + s.theta_r;   // 1/(1+y)^m * (theta_e-theta_r) + theta_r
 }
+LG_FN double lg_lnh(double h) { return log(h); }
 // calc_theta_from_h, soil_funcs.cxx:147-150
 LG_FN_NOINLINE double lg_theta_from_h(double h, const LgarLayer& s) {
   const double y = lg_exp(s.n * (s.ln_alpha + lg_log(h)));
@@ -110,6 +126,7 @@ LG_FN_NOINLINE double lg_Se_from_h(double h, const LgarLayer& s) {
   if (fabs(h) < 1.0E-10) return 1.0;
   return lg_exp(-s.m * lg_log(1.0 + lg_exp(s.n * (s.ln_alpha + lg_log(h)))));
 }
+#endif
 // calc_K_from_Se, soil_funcs.cxx:164-167 (pow(x,2.0) -> x*x)
 LG_FN_NOINLINE double lg_K_from_Se(double Se, const LgarLayer& s) {
   return s.Ksat * sqrt(Se) * lg_sq(1.0 - lg_pow(1.0 - lg_pow(Se, s.inv_m), s.m));
@@ -320,7 +337,7 @@ LG_FN_NOINLINE double lg_theta_mass_balance(LgCtx& c, int layer_num, double psi_
       psi_loc = 0.0;
       factor = factor * 0.5;
     }
-    const double lnpsi = log(psi_loc);
+    const double lnpsi = lg_lnh(psi_loc);
     theta = lg_theta_from_lnh(lnpsi, sp);
     double mass_layers = 0.0;
     mass_layers += dz[layer_num] * (theta - dth[layer_num]);

@@ -17,6 +17,14 @@ RANDOM = [f"rand_{i}" for i in range(12)]
 RTOL = 1e-9
 ATOL_M = 1e-14        # metres; floor for quantities that are exactly or nearly zero
 MBAL_ATOL_M = 1e-11   # the local mass-balance residual is ~1e-12 cm noise: compared absolutely
+# The reference's psi searches accept any psi whose mass error is <= MBAL_ITERATIVE_TOLERANCE = 1e-10 cm
+# (src/lgar.cxx:64,2990) and book what is left of it into AET (:3096-3108) or the bottom flux (:1746-1751).
+# Those two fluxes are therefore only DEFINED to 1e-10 cm = 1e-12 m by the reference's own algorithm: two
+# correct libm's (glibc pow vs CUDA exp/log, 1 ulp apart) can stop a search one trip apart.  Measured on
+# 1.8e6 column-steps of the bench workload: worst |dAET| = 1.1e-12 m, identical for a build that calls the
+# CUDA library pow() (tools/scale_parity_stats.py).  Floor for these two: 2 x the iterative tolerance.
+RESIDUAL_ATOL_M = 2e-12
+RESIDUAL_SCALARS = (2, 8)   # actual_evapotranspiration, percolation
 
 
 def load_golden(name):
@@ -45,7 +53,7 @@ def assert_scalars_close(got, want, what="", rtol=RTOL):
             err = np.abs(g - w)
             assert np.all(err <= MBAL_ATOL_M), f"{what}: mass_balance differs by {err.max():.3e} m at step {int(np.argmax(err))}"
             continue
-        tol = rtol * np.maximum(np.abs(g), np.abs(w)) + ATOL_M
+        tol = rtol * np.maximum(np.abs(g), np.abs(w)) + (RESIDUAL_ATOL_M if k in RESIDUAL_SCALARS else ATOL_M)
         err = np.abs(g - w)
         bad = err > tol
         assert not bad.any(), (f"{what}: scalar {k} differs at step {int(np.argmax(bad))}: got {g.flat[np.argmax(bad)]!r} "

@@ -141,6 +141,32 @@ def test_window_and_lanes_kernels_equal_hourly_kernels(cuda_device, tmp_path):
             assert np.array_equal(f1[k], f2[k], equal_nan=True)
 
 
+def test_host_buffer_multi_step_call(cuda_device, tmp_path):
+    """lgarb_update_steps_host (forcing in / output series out through host buffers) equals the device path."""
+    import torch
+    import lgar_c_b200
+    g = load_golden("Bushland")
+    cfg = config_for("Bushland", tmp_path)
+    ncol, T = 300, 700
+    shifts = (np.arange(ncol) * 7919) % 8760
+    Pm = np.ascontiguousarray(np.stack([np.roll(g["precip"], -int(s))[:T] for s in shifts], axis=1))
+    Em = np.ascontiguousarray(np.stack([np.roll(g["pet"], -int(s))[:T] for s in shifts], axis=1))
+    b = lgar_c_b200.BmiLGARBatch()
+    b.initialize(cfg, ncol)
+    out = b.update_steps_host(Pm, Em, ["total_discharge", "soil_storage", "actual_evapotranspiration"])
+    b2 = lgar_c_b200.BmiLGARBatch()
+    b2.initialize(cfg, ncol)
+    dP, dE = torch.from_numpy(Pm).cuda(), torch.from_numpy(Em).cuda()
+    sinks = torch.zeros((12, T, ncol), dtype=torch.float64, device="cuda")
+    b2.update_steps_device(T, dP.data_ptr(), dE.data_ptr(), ncol, {n: sinks[k].data_ptr() for k, n in enumerate(lgar_c_b200.OUTPUT_SCALARS)}, ncol)
+    b2.synchronize()
+    ref = sinks.cpu().numpy()
+    for name, k in (("total_discharge", 6), ("soil_storage", 5), ("actual_evapotranspiration", 2)):
+        assert np.array_equal(out[name], ref[k]), name
+    with pytest.raises(lgar_c_b200.LgarbError):
+        b.update_steps_host(Pm, Em, ["soil_moisture_wetting_fronts"])
+
+
 def test_heterogeneous_batch_against_oracle(cuda_device, oracle, tmp_path):
     """BASELINE config 3 in small: Bushland layering, per-column soil triples drawn from the PARSED
     vG_params_stat_nom_ordered.dat (quirk Q2), per-column circular time shift of the forcing."""
