@@ -100,7 +100,9 @@ int lgarb_update_until(lgarb_engine* e, double t);
  * receiving that output variable for every step (order: lgarb_output_scalar_name());
  * d_nfronts_sink (nullable) is an int32 [n_steps][sink_stride] buffer receiving
  * soil_num_wetting_fronts after every step.
- * Asynchronous on the engine's stream; lgarb_synchronize() or any get_value waits. */
+ * Asynchronous on the engine's own (non-blocking) stream; lgarb_synchronize() or any get_value waits.
+ * The caller must make sure that work it queued on its own streams for these buffers (fills, copies)
+ * has completed before the call, and must not touch them before lgarb_synchronize(). */
 int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_precip_mm_per_h,
                               const double* d_pet_mm_per_h, int64_t series_stride,
                               double* const* d_sinks, int64_t sink_stride, int32_t* d_nfronts_sink);
@@ -184,7 +186,7 @@ int lgarb_get_soil_row(const lgarb_engine* e, int soil, double* out10);
 /* Test hook: route every column through the active kernel (no cached-flux fast path), to check
  * that the two kernels implement the same Update(). */
 int lgarb_set_force_all_active(lgarb_engine* e, int on);
-/* Scheduling of lgarb_update_steps_device.  2 (default) = one launch for the whole run, every lane
+/* Scheduling of lgarb_update_steps_device.  3 (default) = wavefront scheduler, see below; 2 = one launch for the whole run, every lane
  * running its own stream of columns and hours as a staged program (converged psi-search iterations);
  * 1 = one launch, warp-owned tiles of columns with per-column time pointers; 0 = one stream+active
  * kernel pair per forcing hour (what lgarb_update does); 3 = wavefront scheduler: the same staged

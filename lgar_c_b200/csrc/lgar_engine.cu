@@ -76,7 +76,7 @@ struct lgarb_engine {
   cudaStream_t stream = nullptr;
   int active_blocks = 0;
   int window_blocks = 0;
-  int use_window = 2;          // multi-step runs: 2 = lanes kernel, 1 = warp-tile window kernel, 0 = hour-by-hour kernel pairs
+  int use_window = 3;          // multi-step runs: 3 = wavefront kernels, 2 = lanes kernel, 1 = warp-tile window kernel, 0 = hour-by-hour kernel pairs
   int lanes_blocks = 0;
   unsigned int* d_work_trace = nullptr;  // [2][stride], allocated by lgarb_set_work_trace
   double* d_host_series = nullptr;  // staging of lgarb_update_steps_host
@@ -531,7 +531,8 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
   w.tile_counter = e->d_tile_counter;
   w.done_columns = wv.done_columns;
   CUDA_TRY(cudaMemsetAsync(e->d_tile_counter, 0, sizeof(int32_t), e->stream));
-  CUDA_TRY(lgar_launch_wave_init(wv, e->stream));
+  w.slot_is_column = (wv.nslots == e->ncol) ? 1 : 0;
+  CUDA_TRY(lgar_launch_wave_init(wv, w.slot_is_column, e->stream));
   e->launches += 1;
   int par[LGAR_NSTAGE] = {0, 0, 0, 0, 0, 0};
   int quantum = e->wave_quantum;
@@ -581,14 +582,14 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
     const bool new_steps = cnt[LG_ST_FETCH] + cnt[LG_ST_HEAD] > 0;
     if (new_steps) {
       launch(LG_ST_FETCH);
-      launch(LG_ST_HEAD);
+      launch(LG_ST_HEAD);  // runs the first stretch of the front loop too
     }
     if (new_steps || cnt[LG_ST_FRONT] + cnt[LG_ST_SEARCH] > 0) {
+      if (cnt[LG_ST_FRONT] > 0) launch(LG_ST_FRONT);
       for (int k = 0; k < e->wave_pairs; k++) {
-        launch(LG_ST_FRONT);
         launch(LG_ST_SEARCH);
+        launch(LG_ST_FRONT);
       }
-      launch(LG_ST_FRONT);
     }
     launch(LG_ST_TAIL);
     for (int k = 0; k < e->wave_corr_pairs; k++) {

@@ -276,8 +276,8 @@ __device__ __forceinline__ void ctx_copy(T* dst, const T* src) {
   static_assert(sizeof(T) % 16 == 0, "context must be a multiple of 16 bytes");
   const uint4* s4 = reinterpret_cast<const uint4*>(src);
   uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll 4
-  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d4[i] = s4[i];
+#pragma unroll 16
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d4[i] = s4[i];  // 16 independent 16-byte loads in flight per thread
 }
 
 }  // namespace
@@ -341,6 +341,8 @@ __global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDevi
         L.tr_kcyc = 0;
         lg_stage_head(cfg, d, w, L, fsp);
         active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
+        // every new step goes straight into its front loop: saves one 2.7 KB context round trip per step
+        if (L.stage == LG_ST_FRONT) lg_stage_front(L);
       } else {
         ctx_copy(&S, &slots[slot]);
         L.c.cfg = &cfg;
@@ -368,12 +370,14 @@ __global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDevi
   }
 }
 
-__global__ void lgar_wave_init_kernel(LgarWave wv) {
+__global__ void lgar_wave_init_kernel(LgarWave wv, int slot_is_column) {
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wv.nslots; i += gridDim.x * blockDim.x) {
     slots[i].L.stage = LG_ST_FETCH;
-    slots[i].L.col = -1;
-    slots[i].L.t = 0x7FFFFFFF;
+    // slot == column keeps queue order close to column order, so the column-state traffic of FETCH, HEAD and
+    // TAIL stays (nearly) coalesced; with fewer slots than columns, slots draw columns from a counter instead
+    slots[i].L.col = slot_is_column ? i : -1;
+    slots[i].L.t = slot_is_column ? 0 : 0x7FFFFFFF;
     slots[i].L.resume = false;
     slots[i].L.tr_iters = 0;
     slots[i].L.tr_kcyc = 0;
@@ -386,8 +390,8 @@ __global__ void lgar_wave_init_kernel(LgarWave wv) {
 // reset the consumed queue's count after its kernel ran
 __global__ void lgar_wave_reset_kernel(int32_t* count) { *count = 0; }
 
-cudaError_t lgar_launch_wave_init(const LgarWave& wv, cudaStream_t stream) {
-  lgar_wave_init_kernel<<<(wv.nslots + 255) / 256, 256, 0, stream>>>(wv);
+cudaError_t lgar_launch_wave_init(const LgarWave& wv, int slot_is_column, cudaStream_t stream) {
+  lgar_wave_init_kernel<<<(wv.nslots + 255) / 256, 256, 0, stream>>>(wv, slot_is_column);
   return cudaGetLastError();
 }
 

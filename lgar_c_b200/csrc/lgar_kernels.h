@@ -28,6 +28,7 @@ struct LgarWindow {
   int force_all_active;
   int32_t* tile_counter;  // device, zeroed before launch (tile counter / column counter)
   unsigned long long* prof;  // nullable: [0] += sum of front counts, [1] += active column-steps
+  int slot_is_column;     // wavefront: slot i owns column i for the whole window (no column counter)
   int32_t* done_columns;  // nullable: += 1 whenever a column finishes its window (wavefront scheduler)
   unsigned int* work_trace;  // nullable: [2][stride] per column: psi-search trips, kilo-cycles in the non-search stages (lanes kernel)
   int64_t trace_stride;
@@ -54,7 +55,7 @@ struct LgarWave {
 // one launch of the kernel of `stage`, consuming queue[stage][consume]; append_mask bit s = buffer of stage s to append to
 cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int stage, int consume,
                                    unsigned append_mask, int quantum, int max_items, cudaStream_t stream);
-cudaError_t lgar_launch_wave_init(const LgarWave& wv, cudaStream_t stream);
+cudaError_t lgar_launch_wave_init(const LgarWave& wv, int slot_is_column, cudaStream_t stream);
 size_t lgar_lane_context_bytes();
 // mode 1: warp-tile window kernel; mode 2: per-lane staged program (lgar_lanes.cuh)
 cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream, int mode);

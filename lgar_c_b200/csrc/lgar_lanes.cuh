@@ -855,6 +855,10 @@ LG_FN_NOINLINE void lg_stage_tail(const LgarConfig& cfg, const LgarDeviceState& 
 // that need no flux computation.  Ends in HEAD (active step at hour L.t) or DONE (no columns left).
 LG_FN_NOINLINE void lg_stage_fetch(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, LgLane& L, unsigned long long* front_sum) {
   for (;;) {
+    if (w.slot_is_column && L.t >= w.K) {  // this slot's only column has finished the window
+      L.stage = LG_ST_DONE;
+      return;
+    }
     if (L.col < 0 || L.t >= w.K) {
 #ifdef LGAR_HOSTSIM
       const int64_t col = (*w.tile_counter)++;

@@ -129,6 +129,7 @@ def test_window_and_lanes_kernels_equal_hourly_kernels(cuda_device, tmp_path):
         nfs = torch.zeros((T, ncol), dtype=torch.int32, device="cuda")
         # two consecutive windows, to cross a window boundary
         for t0, n in ((0, 900), (900, T - 900)):
+            torch.cuda.synchronize()  # the engine runs on its own stream: inputs/sinks made by torch must be complete
             b.update_steps_device(n, dP[t0].data_ptr(), dE[t0].data_ptr(), ncol,
                                   {nm: sinks[k, t0].data_ptr() for k, nm in enumerate(lgar_c_b200.OUTPUT_SCALARS)}, ncol, nfs[t0].data_ptr())
         b.synchronize()
@@ -158,6 +159,7 @@ def test_host_buffer_multi_step_call(cuda_device, tmp_path):
     b2.initialize(cfg, ncol)
     dP, dE = torch.from_numpy(Pm).cuda(), torch.from_numpy(Em).cuda()
     sinks = torch.zeros((12, T, ncol), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()  # the engine runs on its own stream: inputs/sinks made by torch must be complete
     b2.update_steps_device(T, dP.data_ptr(), dE.data_ptr(), ncol, {n: sinks[k].data_ptr() for k, n in enumerate(lgar_c_b200.OUTPUT_SCALARS)}, ncol)
     b2.synchronize()
     ref = sinks.cpu().numpy()
@@ -187,6 +189,7 @@ def test_heterogeneous_batch_against_oracle(cuda_device, oracle, tmp_path):
     b.initialize(cfg, ncol, 0, types)
     dP = torch.from_numpy(np.ascontiguousarray(Pm)).cuda(); dE = torch.from_numpy(np.ascontiguousarray(Em)).cuda()
     sinks = torch.zeros((12, T, ncol), dtype=torch.float64, device="cuda"); nfs = torch.zeros((T, ncol), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()  # the engine runs on its own stream: inputs/sinks made by torch must be complete
     b.update_steps_device(T, dP.data_ptr(), dE.data_ptr(), ncol, {n: sinks[k].data_ptr() for k, n in enumerate(lgar_c_b200.OUTPUT_SCALARS)}, ncol, nfs.data_ptr())
     b.synchronize()
     scal = sinks.cpu().numpy().transpose(1, 0, 2); nf = nfs.cpu().numpy()
@@ -215,6 +218,7 @@ def test_replicated_columns_are_identical_100k(cuda_device, tmp_path):
     b.initialize(cfg, ncol)
     dP = torch.from_numpy(np.repeat(g["precip"][:, None], ncol, axis=1).copy()).cuda()
     dE = torch.from_numpy(np.repeat(g["pet"][:, None], ncol, axis=1).copy()).cuda()
+    torch.cuda.synchronize()  # the engine runs on its own stream: inputs/sinks made by torch must be complete
     b.update_steps_device(T, dP.data_ptr(), dE.data_ptr(), ncol)
     b.synchronize()
     for name in ("soil_storage", "infiltration", "surface_runoff", "mass_balance"):

@@ -30,6 +30,7 @@ def test_bench_workload_sample_against_oracle(cuda_device, oracle, tmp_path):
     sample = np.sort(np.random.default_rng(99).choice(ncol, nsample, replace=False))
     sinks = torch.zeros((12, T, ncol), dtype=torch.float64, device="cuda")
     nfs = torch.zeros((T, ncol), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()  # the engine runs on its own stream: inputs/sinks made by torch must be complete
     b.update_steps_device(T, dP.data_ptr(), dE.data_ptr(), ncol, {n: sinks[k].data_ptr() for k, n in enumerate(lgar_c_b200.OUTPUT_SCALARS)},
                           ncol, nfs.data_ptr())
     b.synchronize()
