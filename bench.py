@@ -380,7 +380,7 @@ def main():
     if not args.no_e2e:
         # the multi-step verb with HOST buffers: forcing of `nh` hours in from pinned host memory, one output
         # series (total_discharge, ngen's usual main_output_variable) back to pinned host memory, all inside
-        nh = args.e2e_hours
+        nh = min(args.e2e_hours, R * H)
         hP = torch.empty((nh, ncol), dtype=torch.float64).pin_memory()
         hE = torch.empty((nh, ncol), dtype=torch.float64).pin_memory()
         hP.copy_(dP[:nh])
