@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--cpu-hours", type=int, default=1440)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--finish-below", type=int, default=-1, help="wavefront: slots in flight below which the finishing kernel takes over (-1: engine default)")
     ap.add_argument("--mode", type=int, default=3, help="3 wavefront kernels, 2 lanes kernel, 1 warp-tile window kernel, 0 one kernel pair per forcing hour")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -302,6 +303,8 @@ def main():
     b = lgar_c_b200.BmiLGARBatch()
     b.initialize(cfg, ncol, local_rank, column_soils(col0, ncol), column_layers(col0, ncol))
     b.set_window_mode(args.mode)
+    if args.finish_below >= 0:
+        b.set_wave_params(0, 0, args.finish_below)
     ext = torch.cuda.ExternalStream(b.get_stream(), device=dev)
 
     # forcing ring on the device: R day-blocks, each [H][ncol]

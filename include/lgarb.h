@@ -193,8 +193,9 @@ int lgarb_set_force_all_active(lgarb_engine* e, int on);
  * program with one small kernel per stage.  All produce identical results. */
 int lgarb_set_window_mode(lgarb_engine* e, int mode);
 /* mode 3 (wavefront: one small kernel per stage, contexts parked in HBM, compacted queues) tuning:
- * psi-search trips per SEARCH launch, FRONT/SEARCH pairs per round, rounds between host polls.  0 keeps a value. */
-int lgarb_set_wave_params(lgarb_engine* e, int search_quantum, int front_search_pairs, int poll_rounds);
+ * psi-search trips per SEARCH launch (0 keeps), FRONT/SEARCH pairs per round (0 keeps), and the number of
+ * slots in flight below which the remaining columns are finished by one thread each (-1 keeps, 0 = never). */
+int lgarb_set_wave_params(lgarb_engine* e, int search_quantum, int front_search_pairs, int finish_below);
 /* Debug/profiling aid for the lanes kernel: per column, the number of psi-search trips and the
  * kilo-cycles spent in the other stages during the LAST multi-step launch. */
 int lgarb_set_work_trace(lgarb_engine* e, int on);

@@ -381,8 +381,8 @@ class BmiLGARBatch:
         """2 lanes kernel (default), 1 warp-tile window kernel, 0 hour-by-hour kernel pairs."""
         self._ck(self._L.lgarb_set_window_mode(self._h, int(mode)))
 
-    def set_wave_params(self, search_quantum=0, front_search_pairs=0, poll_rounds=0):
-        self._ck(self._L.lgarb_set_wave_params(self._h, int(search_quantum), int(front_search_pairs), int(poll_rounds)))
+    def set_wave_params(self, search_quantum=0, front_search_pairs=0, finish_below=-1):
+        self._ck(self._L.lgarb_set_wave_params(self._h, int(search_quantum), int(front_search_pairs), int(finish_below)))
 
     def set_work_trace(self, on):
         self._ck(self._L.lgarb_set_work_trace(self._h, int(bool(on))))

@@ -84,8 +84,9 @@ struct lgarb_engine {
   // wavefront scheduler (mode 3)
   LgarWave wave;
   bool wave_ready = false;
-  int wave_quantum = 32, wave_pairs = 3, wave_poll = 4, wave_corr_pairs = 2;
-  int64_t wave_max_slots = 2097152;
+  int wave_quantum = 32, wave_pairs = 3, wave_corr_pairs = 2;
+  int wave_finish_below = 16384;
+  int64_t wave_max_slots = 16777216;  // 2.8 KB of context per slot
   int64_t wave_rounds = 0;
   int32_t* d_tile_counter = nullptr;
   cudaEvent_t win_ev[2] = {nullptr, nullptr};
@@ -574,6 +575,12 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
         in_flight += cnt[s];
       }
       if (in_flight == 0) break;
+      if (in_flight <= e->wave_finish_below) {  // the stragglers: one thread per slot runs its column to the end of the window
+        CUDA_TRY(lgar_launch_wave_finish(e->cfg, e->d, w, wv, in_flight, e->stream));
+        e->launches += 2;
+        if (debug) fprintf(stderr, "[wave] round %lld: finishing kernel for %d slots in flight\n", (long long)round, in_flight);
+        break;
+      }
       if (round > 100000000) throw std::runtime_error("wavefront scheduler did not terminate");
     }
     // few slots in flight = the long searches (up to 1e5 trips) are what is left: let them run longer per launch
@@ -966,11 +973,11 @@ int lgarb_get_warp_times(lgarb_engine* e, uint32_t* out16384) {
   });
 }
 int lgarb_set_window_mode(lgarb_engine* e, int mode) { LGARB_GUARD(e, e->use_window = (mode < 0 || mode > 3) ? 3 : mode); }
-int lgarb_set_wave_params(lgarb_engine* e, int search_quantum, int front_search_pairs, int poll_rounds) {
+int lgarb_set_wave_params(lgarb_engine* e, int search_quantum, int front_search_pairs, int finish_below) {
   LGARB_GUARD(e, {
     if (search_quantum > 0) e->wave_quantum = search_quantum;
     if (front_search_pairs > 0) e->wave_pairs = front_search_pairs;
-    if (poll_rounds > 0) e->wave_poll = poll_rounds;
+    if (finish_below >= 0) e->wave_finish_below = finish_below;
   });
 }
 int64_t lgarb_get_launch_count(const lgarb_engine* e) { return e ? e->launches : -1; }

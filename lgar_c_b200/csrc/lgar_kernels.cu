@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstddef>
 
 #include "lgar_lanes.cuh"
 
@@ -270,14 +271,14 @@ __device__ __forceinline__ void wave_push(const LgarWave& wv, unsigned append_ma
   wv.queue[stage][buf][base + __popc(m & ((1u << lane) - 1))] = slot;
 }
 
-// context copy between HBM and thread-private memory, 16 bytes at a time
-template <typename T>
+// context copy between HBM and thread-private memory, 16 bytes at a time; NBYTES = leading part to move
+template <int NBYTES, typename T>
 __device__ __forceinline__ void ctx_copy(T* dst, const T* src) {
-  static_assert(sizeof(T) % 16 == 0, "context must be a multiple of 16 bytes");
+  static_assert(NBYTES % 16 == 0 && NBYTES <= (int)sizeof(T), "context part must be a multiple of 16 bytes");
   const uint4* s4 = reinterpret_cast<const uint4*>(src);
   uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll 16
-  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d4[i] = s4[i];  // 16 independent 16-byte loads in flight per thread
+  for (int i = 0; i < NBYTES / 16; i++) d4[i] = s4[i];  // 16 independent 16-byte loads in flight per thread
 }
 
 }  // namespace
@@ -285,6 +286,8 @@ __device__ __forceinline__ void ctx_copy(T* dst, const T* src) {
 struct alignas(16) LgLaneSlot {
   LgLane L;
 };
+constexpr int kTailBytes = (int)offsetof(LgLane, old);
+static_assert(offsetof(LgLane, old) % 16 == 0 && offsetof(LgLane, k) % 16 == 0 && sizeof(LgLaneSlot) % 16 == 0, "LgLane layout");
 
 template <int STAGE>
 __global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDeviceState d, LgarWindow w, LgarWave wv, int consume,
@@ -344,7 +347,12 @@ __global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDevi
         // every new step goes straight into its front loop: saves one 2.7 KB context round trip per step
         if (L.stage == LG_ST_FRONT) lg_stage_front(L);
       } else {
-        ctx_copy(&S, &slots[slot]);
+        // TAIL works on everything up to and including the correction record; FRONT needs state_previous
+        // and the search record as well
+        if (STAGE == LG_ST_TAIL)
+          ctx_copy<kTailBytes>(&S, &slots[slot]);
+        else
+          ctx_copy<(int)sizeof(LgLaneSlot)>(&S, &slots[slot]);
         L.c.cfg = &cfg;
         L.c.cls = L.cls;
         L.c.f = &L.f;
@@ -357,8 +365,12 @@ __global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDevi
       if (next == LG_ST_FETCH) {
         slots[slot].L.col = L.col;
         slots[slot].L.t = L.t;
+      } else if (STAGE == LG_ST_TAIL && next == LG_ST_CORR) {
+        ctx_copy<kTailBytes>(&slots[slot], &S);  // TAIL -> CORR -> TAIL: neither state_previous nor the psi search is live
+      } else if (next == LG_ST_TAIL) {
+        ctx_copy<kTailBytes>(&slots[slot], &S);  // the front loop is over
       } else {
-        ctx_copy(&slots[slot], &S);
+        ctx_copy<(int)sizeof(LgLaneSlot)>(&slots[slot], &S);
       }
     }
 #pragma unroll
@@ -368,6 +380,74 @@ __global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDevi
     if (front_sum) atomicAdd(w.prof, front_sum);
     if (active_sum) atomicAdd(w.prof + 1, active_sum);
   }
+}
+
+// Finishing kernel: when only a few slots are left in flight (the columns that are active in almost every
+// hour of the window), a round of ~13 launches costs ~2.5 ms whatever it processes.  Here every remaining
+// slot is taken by one thread which runs its column through all stages to the end of the window without
+// going back to HBM between stages: the critical path per active step drops from one round to the serial
+// execution time of the step.  Lane utilisation is poor by construction, which does not matter for the few
+// thousand slots this is used for.
+__global__ void __launch_bounds__(128) lgar_wave_finish_kernel(LgarConfig cfg, LgarDeviceState d, LgarWindow w, LgarWave wv) {
+  LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
+  int total = 0;
+  for (int q = 0; q < 2 * LGAR_NSTAGE; q++) total += wv.qcount[q];
+  unsigned long long front_sum = 0, active_sum = 0;
+  unsigned long long* fsp = w.prof ? &front_sum : nullptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int j = i, slot = -1;
+    for (int q = 0; q < 2 * LGAR_NSTAGE; q++) {  // item i of the concatenation of all queues
+      const int n = wv.qcount[q];
+      if (j < n) {
+        slot = wv.queue[q >> 1][q & 1][j];
+        break;
+      }
+      j -= n;
+    }
+    LgLaneSlot S;
+    ctx_copy<(int)sizeof(LgLaneSlot)>(&S, &slots[slot]);
+    LgLane& L = S.L;
+    L.c.cfg = &cfg;
+    L.c.cls = L.cls;
+    L.c.f = &L.f;
+    while (L.stage != LG_ST_DONE) {
+      switch (L.stage) {
+        case LG_ST_FETCH: lg_stage_fetch(cfg, d, w, L, fsp); break;
+        case LG_ST_HEAD:
+          lg_stage_head(cfg, d, w, L, fsp);
+          active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
+          break;
+        case LG_ST_FRONT: lg_stage_front(L); break;
+        case LG_ST_SEARCH:
+          while (!L.q.done) lg_search_iter(L.q, *L.cls);
+          L.resume = true;
+          L.stage = LG_ST_FRONT;
+          break;
+        case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, fsp); break;
+        case LG_ST_CORR:
+          while (!L.k.done) lg_corr_iter(L.k, L.f, *L.cls);
+          L.stage = LG_ST_TAIL;
+          break;
+        default: L.stage = LG_ST_DONE; break;
+      }
+    }
+  }
+  if (w.prof) {
+    if (front_sum) atomicAdd(w.prof, front_sum);
+    if (active_sum) atomicAdd(w.prof + 1, active_sum);
+  }
+}
+
+__global__ void lgar_wave_clear_kernel(LgarWave wv) {
+  if (threadIdx.x < 2 * LGAR_NSTAGE) wv.qcount[threadIdx.x] = 0;
+}
+
+cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
+                                    cudaStream_t stream) {
+  const int blocks = std::max(1, std::min((in_flight + 127) / 128, 148 * 16));
+  lgar_wave_finish_kernel<<<blocks, 128, 0, stream>>>(cfg, d, w, wv);
+  lgar_wave_clear_kernel<<<1, 32, 0, stream>>>(wv);
+  return cudaGetLastError();
 }
 
 __global__ void lgar_wave_init_kernel(LgarWave wv, int slot_is_column) {

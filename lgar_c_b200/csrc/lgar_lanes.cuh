@@ -40,15 +40,15 @@ struct LgCorr {
   bool switched, aug, aug_extreme, done;
 };
 
+// Field order matters: the wavefront kernels copy only the leading part a stage needs
+// (TAIL: up to `old`; FRONT: up to `k`), see lgar_wave_kernel.
 struct LgLane {
   int stage;
-  int64_t col;
   int t;
+  int64_t col;
   const LgarColumnClass* cls;
-  LgScalars s;
-  LgFronts f;
-  LgOld old;
   LgCtx c;
+  LgScalars s;
   // step context (locals of lg_step_active)
   LgPrologue pro;
   double P, E;
@@ -57,18 +57,18 @@ struct LgLane {
   int cycle, wf_fd;
   double PET_rate, ponded, volon_ts, volend_sub, AET, free_drainage, mass_corr_fd, temp_rch;
   double volin, runoff, volon_sub, last_AET, last_PET_sub, last_volrech;
-  bool create;
   // front-loop context (locals of lg_move_wetting_fronts)
   int wf, nwf, wf_fd_demand, search_case;
-  bool resume;
   double precip_mass_to_add, bottom_flux, actual_ET_demand;
-  LgSearch q;
   // resumable lgar_move_wetting_fronts epilogue: correction loop + lgar_fix_dry_over_wet_wetting_fronts
   int me_phase, me_correction, fx_cur, fx_nx, fx_l;
-  bool fx_resume;
   double fx_prior_mass, fx_mass_change;
-  LgCorr k;
+  bool create, resume, fx_resume;
   unsigned int tr_iters, tr_kcyc;  // work trace of the current column (debug)
+  LgFronts f;
+  alignas(16) LgCorr k;   // TAIL/CORR stop copying after this
+  alignas(16) LgOld old;  // FRONT only
+  alignas(16) LgSearch q; // FRONT/SEARCH only
 };
 
 // ---- psi search split into init / iterate / finish (lgar.cxx:2952-3112) ---------------------------
