@@ -395,18 +395,21 @@ __global__ void __launch_bounds__(128) lgar_wave_finish_kernel(LgarConfig cfg, L
   unsigned long long front_sum = 0, active_sum = 0;
   unsigned long long* fsp = w.prof ? &front_sum : nullptr;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int j = i, slot = -1;
+    int j = i, slot = -1, stage = LG_ST_DONE;
     for (int q = 0; q < 2 * LGAR_NSTAGE; q++) {  // item i of the concatenation of all queues
       const int n = wv.qcount[q];
       if (j < n) {
         slot = wv.queue[q >> 1][q & 1][j];
+        stage = q >> 1;
         break;
       }
       j -= n;
     }
+    if (slot < 0) continue;
     LgLaneSlot S;
     ctx_copy<(int)sizeof(LgLaneSlot)>(&S, &slots[slot]);
     LgLane& L = S.L;
+    L.stage = stage;  // the queue a slot sits in is authoritative: the partial-context stages do not rewrite L.stage
     L.c.cfg = &cfg;
     L.c.cls = L.cls;
     L.c.f = &L.f;

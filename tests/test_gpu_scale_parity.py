@@ -63,3 +63,42 @@ def test_bench_workload_sample_against_oracle(cuda_device, oracle, tmp_path):
             flags = (fr["layer"][c] | (fr["to_bottom"][c] << 8)).astype(np.int32)
             assert_fronts_close(arr, flags, r["fronts"][-1], r["flags"][-1], n, f"column {c} final fronts")
     print(f"checked {len(cols)} columns x {T} steps against the oracle; {len(failed)} of {ncol} columns frozen, {n_checked_fail} of them cross-checked")
+
+
+def test_scheduling_does_not_change_results(cuda_device, tmp_path):
+    """A column's trajectory must not depend on how the wavefront scheduler interleaves it with the
+    others: the bench workload on 200 000 columns x 2 windows, run with (a) the defaults, (b) no
+    finishing kernel and a tiny search quantum, (c) the finishing kernel taking over early, and
+    (d) the warp-tile window kernel (mode 1) -- every output, status word and front bit-identical."""
+    import torch
+    import bench
+    import lgar_c_b200
+    ncol, T = 200_000, 96
+    cfg = bench.write_workload_config(tmp_path)
+    soils, layers = bench.column_soils(0, ncol), bench.column_layers(0, ncol)
+    P, E = bench.host_forcing(ncol, 0, T, 777)
+    P[10:14] = np.maximum(P[10:14], 8.0)     # a storm on every column: the whole batch active at once
+    dP, dE = torch.from_numpy(P).cuda(), torch.from_numpy(E).cuda()
+    res = []
+    for mode, wave in ((3, None), (3, (4, 1, 0)), (3, (64, 4, 150_000)), (1, None)):
+        b = lgar_c_b200.BmiLGARBatch()
+        b.initialize(cfg, ncol, 0, soils, layers)
+        b.set_window_mode(mode)
+        if wave is not None:
+            b.set_wave_params(*wave)
+        q = torch.zeros((T, ncol), dtype=torch.float64, device="cuda")
+        nfs = torch.zeros((T, ncol), dtype=torch.int32, device="cuda")
+        for t0, n in ((0, 60), (60, T - 60)):
+            torch.cuda.synchronize()
+            b.update_steps_device(n, dP[t0].data_ptr(), dE[t0].data_ptr(), ncol, {"total_discharge": q[t0].data_ptr()}, ncol, nfs[t0].data_ptr())
+        b.synchronize()
+        res.append((q.cpu().numpy(), nfs.cpu().numpy(), b.get_status(), b.get_fronts(), b.get_global_mass_balance(),
+                    np.stack([b.get_value(n) for n in lgar_c_b200.OUTPUT_SCALARS])))
+        del b
+    q0, n0, st0, f0, m0, v0 = res[0]
+    for (q1, n1, st1, f1, m1, v1) in res[1:]:
+        assert np.array_equal(st0, st1), f"status differs on {np.nonzero(st0 != st1)[0][:10]}"
+        assert np.array_equal(n0, n1) and np.array_equal(q0, q1, equal_nan=True)
+        assert np.array_equal(m0, m1, equal_nan=True) and np.array_equal(v0, v1, equal_nan=True)
+        for k in ("depth", "theta", "psi", "K", "dzdt", "layer", "to_bottom", "nfronts"):
+            assert np.array_equal(f0[k], f1[k], equal_nan=True), k
