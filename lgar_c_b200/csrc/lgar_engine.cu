@@ -657,6 +657,8 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
         w.series_stride = series_stride;
         for (int k = 0; k < LGAR_NOUT; k++) w.sinks.p[k] = (d_sinks && d_sinks[k]) ? d_sinks[k] + t0 * sink_stride : nullptr;
         w.sink_stride = sink_stride;
+        w.has_sinks = 0;
+        for (int k = 0; k < LGAR_NOUT; k++) w.has_sinks |= (w.sinks.p[k] != nullptr);
         w.nf_sink = d_nfronts_sink ? d_nfronts_sink + t0 * sink_stride : nullptr;
         w.K = K;
         w.force_all_active = e->force_all_active;

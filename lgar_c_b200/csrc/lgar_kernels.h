@@ -23,6 +23,7 @@ struct LgarWindow {
   int64_t series_stride;
   LgarSinks sinks;        // each non-null: [K][sink_stride]
   int64_t sink_stride;
+  int has_sinks;          // any sinks.p[k] non-null (host-computed: lets the per-hour code skip the output block)
   int32_t* nf_sink;       // nullable: [K][sink_stride] soil_num_wetting_fronts after each hour
   int K;
   int force_all_active;

@@ -1084,7 +1084,7 @@ LG_FN double lg_calc_aet(const LgCtx& c, double PET_cm_per_h, double dt_h) {
 }
 
 // calc_CR_Q, src/conceptual_reservoir.cxx:7-45
-LG_FN_NOINLINE double lg_calc_CR_Q(const LgarConfig& cfg, double dt, double in_cm_per_h, double* fast, double* slow) {
+LG_FN double lg_calc_CR_Q_inl(const LgarConfig& cfg, double dt, double in_cm_per_h, double* fast, double* slow) {
   double input_slow = in_cm_per_h * cfg.frac_slow;
   double input_fast = in_cm_per_h - input_slow;
   double Q_fast = 0.0;
@@ -1107,6 +1107,7 @@ LG_FN_NOINLINE double lg_calc_CR_Q(const LgarConfig& cfg, double dt, double in_c
   }
   return Q_fast + Q_slow;
 }
+LG_FN_NOINLINE double lg_calc_CR_Q(const LgarConfig& cfg, double dt, double in_cm_per_h, double* fast, double* slow) { return lg_calc_CR_Q_inl(cfg, dt, in_cm_per_h, fast, slow); }
 
 // ------------------------------------------------------------------------------------------------
 // L3: BmiLGAR::Update(), reference src/bmi_lgar.cxx:133-895
@@ -1125,7 +1126,7 @@ struct LgPrologue {
 };
 
 // adaptive sub-step + flux-cache decision, bmi_lgar.cxx:260-318.  Pure: commits nothing.
-LG_FN_NOINLINE LgPrologue lg_prologue(const LgarConfig& cfg, const LgScalars& s, double precip_mm_h) {
+LG_FN LgPrologue lg_prologue_inl(const LgarConfig& cfg, const LgScalars& s, double precip_mm_h) {
   LgPrologue p;
   double timestep_h = s.timestep_h;
   p.subtimestep_h = timestep_h;
@@ -1160,6 +1161,7 @@ LG_FN_NOINLINE LgPrologue lg_prologue(const LgarConfig& cfg, const LgScalars& s,
   p.subcycles = (int)(cfg.forcing_resolution_h / timestep_h + 1.0e-08);
   return p;
 }
+LG_FN_NOINLINE LgPrologue lg_prologue(const LgarConfig& cfg, const LgScalars& s, double precip_mm_h) { return lg_prologue_inl(cfg, s, precip_mm_h); }
 
 // One sub-cycle's tail shared by the cached and the computed branch: reservoir, preferential-flow
 // flag, local mass balance (bmi_lgar.cxx:697-737).
@@ -1169,10 +1171,10 @@ struct LgCycle {
   bool top_near_sat;
 };
 
-LG_FN_NOINLINE double lg_cycle_tail(const LgarConfig& cfg, LgScalars& s, LgCycle& cy, double dt, double volend, LgStepVols& v) {
+LG_FN double lg_cycle_tail_inl(const LgarConfig& cfg, LgScalars& s, LgCycle& cy, double dt, double volend, LgStepVols& v) {
   s.precip_prev = cy.precip_sub;
   double volCRstart = s.cr_fast + s.cr_slow;
-  double volQ_CR = lg_calc_CR_Q(cfg, dt, cy.precip_for_CR + cy.ponded_flux_for_CR + cy.fd_for_CR / dt, &s.cr_fast, &s.cr_slow);
+  double volQ_CR = lg_calc_CR_Q_inl(cfg, dt, cy.precip_for_CR + cy.ponded_flux_for_CR + cy.fd_for_CR / dt, &s.cr_fast, &s.cr_slow);
   v.volQ_CR += volQ_CR;
   double volCRend = s.cr_fast + s.cr_slow;
   v.volCRend = volCRend;
@@ -1188,6 +1190,7 @@ LG_FN_NOINLINE double lg_cycle_tail(const LgarConfig& cfg, LgScalars& s, LgCycle
   v.local_mb = local_mb;
   return local_mb;
 }
+LG_FN_NOINLINE double lg_cycle_tail(const LgarConfig& cfg, LgScalars& s, LgCycle& cy, double dt, double volend, LgStepVols& v) { return lg_cycle_tail_inl(cfg, s, cy, dt, volend, v); }
 
 // start of a sub-cycle: preferential flow split and forcing amounts, bmi_lgar.cxx:362-416
 LG_FN void lg_cycle_head(const LgarConfig& cfg, const LgScalars& s, LgCycle& cy, double precip_mm_h, double pet_mm_h, double dt,
@@ -1217,7 +1220,7 @@ LG_FN void lg_cycle_head(const LgarConfig& cfg, const LgScalars& s, LgCycle& cy,
 }
 
 // A forcing step that replays cached fluxes (bmi_lgar.cxx:683-695): one sub-cycle, fronts untouched.
-LG_FN_NOINLINE void lg_step_cached(const LgarConfig& cfg, LgScalars& s, const LgPrologue& pro, double precip_mm_h, double pet_mm_h, LgStepVols& v) {
+LG_FN void lg_step_cached_inl(const LgarConfig& cfg, LgScalars& s, const LgPrologue& pro, double precip_mm_h, double pet_mm_h, LgStepVols& v) {
   const double dt = pro.subtimestep_h;
   double volon_ts = s.volon, PET_rate, ponded;
   LgCycle cy;
@@ -1231,11 +1234,12 @@ LG_FN_NOINLINE void lg_step_cached(const LgarConfig& cfg, LgScalars& s, const Lg
     cy.fd_for_CR += s.prev_rech;
   s.acc_fd += s.prev_rech;
   cy.volon_ts = volon_ts;
-  lg_cycle_tail(cfg, s, cy, dt, s.storage, v);
+  lg_cycle_tail_inl(cfg, s, cy, dt, s.storage, v);
   s.volon = cy.volon_sub;
   s.prev_aet = cy.AET;
   s.prev_pet = cy.PET_sub;
 }
+LG_FN_NOINLINE void lg_step_cached(const LgarConfig& cfg, LgScalars& s, const LgPrologue& pro, double precip_mm_h, double pet_mm_h, LgStepVols& v) { lg_step_cached_inl(cfg, s, pro, precip_mm_h, pet_mm_h, v); }
 
 // A forcing step that computes fluxes (bmi_lgar.cxx:356-805 with cache_fluxes == false).
 LG_FN_NOINLINE void lg_step_active(const LgarConfig& cfg, const LgarColumnClass& cls, LgScalars& s, LgFronts& f, const LgPrologue& pro,

@@ -261,43 +261,81 @@ LG_FN LgarSinks lg_sinks_at(const LgarWindow& w, int t) {
   return s;
 }
 
-// GIUH queue and cumulative volumes of one column held in thread-private memory while the column is
-// walked through many hours (same arithmetic, same order as epilogue()).
+// GIUH queue and cumulative volumes of one column held in registers while the column is walked through
+// many hours (same arithmetic, same order as epilogue()).  Up to LGAR_EPI_REGS ordinates live in
+// statically indexed registers; longer unit hydrographs use the thread-private array qm.  (The first
+// version indexed one array dynamically: 1 KB of local-memory traffic per column-hour, which made the
+// FETCH kernel L2-write bound -- profiles/r1_ncu_summary.md r1f.)
+#define LGAR_EPI_REGS 8
 struct LgEpi {
-  double q[LGAR_MAXG];
+  double qr[LGAR_EPI_REGS];
+  double qm[LGAR_MAXG];
   double cum[LGAR_NCUM];
 };
 LG_FN void lg_epi_load(const LgarConfig& cfg, const LgarDeviceState& d, int64_t col, LgEpi& e) {
   const int64_t st = d.stride;
-  for (int i = 0; i + 1 < cfg.num_giuh; i++) e.q[i] = d.giuhq[(int64_t)i * st + col];
+  const int N = cfg.num_giuh;
+  if (N <= LGAR_EPI_REGS) {
+#pragma unroll
+    for (int i = 0; i < LGAR_EPI_REGS - 1; i++) e.qr[i] = (i + 1 < N) ? d.giuhq[(int64_t)i * st + col] : 0.0;
+    e.qr[LGAR_EPI_REGS - 1] = 0.0;
+  } else {
+    for (int i = 0; i + 1 < N; i++) e.qm[i] = d.giuhq[(int64_t)i * st + col];
+  }
 #pragma unroll
   for (int k = 0; k < LGAR_NCUM; k++) e.cum[k] = d.cum[(int64_t)k * st + col];
 }
 LG_FN void lg_epi_store(const LgarConfig& cfg, const LgarDeviceState& d, int64_t col, const LgEpi& e) {
   const int64_t st = d.stride;
-  for (int i = 0; i + 1 < cfg.num_giuh; i++) d.giuhq[(int64_t)i * st + col] = e.q[i];
+  const int N = cfg.num_giuh;
+  if (N <= LGAR_EPI_REGS) {
+#pragma unroll
+    for (int i = 0; i < LGAR_EPI_REGS - 1; i++)
+      if (i + 1 < N) d.giuhq[(int64_t)i * st + col] = e.qr[i];
+  } else {
+    for (int i = 0; i + 1 < N; i++) d.giuhq[(int64_t)i * st + col] = e.qm[i];
+  }
 #pragma unroll
   for (int k = 0; k < LGAR_NCUM; k++) d.cum[(int64_t)k * st + col] = e.cum[k];
 }
-LG_FN void lg_epi_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int64_t col, LgEpi& e, const LgStepVols& v,
+// one step of the epilogue at hour t of window w (sinks addressed at [t][col])
+LG_FN void lg_epi_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int t, int64_t col, LgEpi& e, const LgStepVols& v,
                        int status, bool write_out) {
   const int64_t st = d.stride;
+  const int64_t so = (int64_t)t * w.sink_stride + col;
   if (status & LGAR_FAIL_MASK) {
     const double nan = LG_NAN;
-    for (int k = 0; k < LGAR_NOUT; k++) {
-      if (write_out) d.out[k * st + col] = nan;
-      if (sinks.p[k]) sinks.p[k][col] = nan;
+    if (write_out || w.has_sinks) {
+#pragma unroll
+      for (int k = 0; k < LGAR_NOUT; k++) {
+        if (write_out) d.out[k * st + col] = nan;
+        if (w.sinks.p[k]) w.sinks.p[k][so] = nan;
+      }
     }
     return;
   }
   const int N = cfg.num_giuh;
   const double r = v.volrunoff + v.volQ_CR;
-  const double carry = (N > 1) ? e.q[0] : 0.0;
-  const double now = carry + cfg.giuh[0] * r;
-  for (int i = 1; i < N; i++) {
-    double qi = (i < N - 1) ? e.q[i] : 0.0;
-    qi += cfg.giuh[i] * r;
-    e.q[i - 1] = qi;
+  double now;
+  if (N <= LGAR_EPI_REGS) {
+    const double carry = (N > 1) ? e.qr[0] : 0.0;
+    now = carry + cfg.giuh[0] * r;
+#pragma unroll
+    for (int i = 1; i < LGAR_EPI_REGS; i++) {
+      if (i < N) {
+        double qi = (i < N - 1) ? e.qr[i] : 0.0;
+        qi += cfg.giuh[i] * r;
+        e.qr[i - 1] = qi;
+      }
+    }
+  } else {
+    const double carry = e.qm[0];
+    now = carry + cfg.giuh[0] * r;
+    for (int i = 1; i < N; i++) {
+      double qi = (i < N - 1) ? e.qm[i] : 0.0;
+      qi += cfg.giuh[i] * r;
+      e.qm[i - 1] = qi;
+    }
   }
   e.cum[LGAR_CUM_PRECIP] += v.precip;
   e.cum[LGAR_CUM_IN] += v.volin;
@@ -309,10 +347,7 @@ LG_FN void lg_epi_step(const LgarConfig& cfg, const LgarDeviceState& d, const Lg
   e.cum[LGAR_CUM_PET] += v.PET;
   e.cum[LGAR_CUM_GIUH] += now;
   e.cum[LGAR_CUM_RUNOFF_CR] += v.volQ_CR;
-  bool any_sink = write_out;
-#pragma unroll
-  for (int k = 0; k < LGAR_NOUT; k++) any_sink = any_sink || (sinks.p[k] != nullptr);
-  if (!any_sink) return;
+  if (!(write_out || w.has_sinks)) return;
   const double cm_to_m = 0.01;
   double o[LGAR_NOUT];
   o[LGAR_OUT_PRECIP] = v.precip * cm_to_m;
@@ -327,9 +362,10 @@ LG_FN void lg_epi_step(const LgarConfig& cfg, const LgarDeviceState& d, const Lg
   o[LGAR_OUT_Q_CR] = v.volQ_CR * cm_to_m;
   o[LGAR_OUT_MBAL] = v.local_mb * cm_to_m;
   o[LGAR_OUT_CR_STORAGE] = v.volCRend * cm_to_m;
+#pragma unroll
   for (int k = 0; k < LGAR_NOUT; k++) {
     if (write_out) d.out[k * st + col] = o[k];
-    if (sinks.p[k]) sinks.p[k][col] = o[k];
+    if (w.sinks.p[k]) w.sinks.p[k][so] = o[k];
   }
 }
 
@@ -358,13 +394,13 @@ LG_FN_NOINLINE int lg_advance_column(const LgarConfig& cfg, const LgarDeviceStat
     LgStepVols v;
     zero_vols(v);
     if (!(s.status & LGAR_FAIL_MASK)) {
-      const LgPrologue pro = lg_prologue(cfg, s, P);
+      const LgPrologue pro = lg_prologue_inl(cfg, s, P);
       if (!pro.cache_fluxes || w.force_all_active) break;
       if (cfg.adaptive_timestep) s.timestep_h = pro.subtimestep_h;
       s.cache_fluxes = 1;
       s.cache_count = pro.cache_count;
       adjust_forcing(cfg, P, E, s.status);
-      lg_step_cached(cfg, s, pro, P, E, v);
+      lg_step_cached_inl(cfg, s, pro, P, E, v);
       if (!(fabs(v.local_mb) <= cfg.mbal_tol)) s.status |= (isnan(v.local_mb) ? LGAR_FAIL_NAN : LGAR_FAIL_MBAL);
       dirty = true;
     }
@@ -372,8 +408,7 @@ LG_FN_NOINLINE int lg_advance_column(const LgarConfig& cfg, const LgarDeviceStat
       lg_epi_load(cfg, d, col, ep);
       epi_loaded = true;
     }
-    const LgarSinks sk = lg_sinks_at(w, t);
-    lg_epi_step(cfg, d, sk, col, ep, v, s.status, t == K - 1);
+    lg_epi_step(cfg, d, w, t, col, ep, v, s.status, t == K - 1);
     if (w.nf_sink) w.nf_sink[(int64_t)t * w.sink_stride + col] = nf;
     if (front_sum) *front_sum += (unsigned)nf;
   }

@@ -64,6 +64,7 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
       memset(&w, 0, sizeof(w));
       w.precip = P; w.pet = E; w.series_stride = 1; w.sink_stride = 1; w.K = nsteps; w.force_all_active = (force_all_active == 3);
       for (int k = 0; k < LGAR_NOUT; k++) w.sinks.p[k] = sk.data() + (size_t)k * nsteps;
+      w.has_sinks = 1;
       w.nf_sink = nfs.data();
       if (force_all_active >= 4) {
         // lane-program emulation: one lane walks the stages of lgar_lanes.cuh
