@@ -25,7 +25,7 @@
 #include "lgar_lanes.cuh"
 
 
-__global__ void __launch_bounds__(256) lgar_step_stream_kernel(LgarConfig cfg, LgarDeviceState d, LgarSinks sinks, int force_all_active) {
+__global__ void __launch_bounds__(256) lgar_step_stream_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarSinks sinks, int force_all_active) {
   const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool needs_active = false;
   if (col < d.ncol) needs_active = lg_stream_column(cfg, d, sinks, col, force_all_active);
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) lgar_step_stream_kernel(LgarConfig cfg, L
   }
 }
 
-__global__ void __launch_bounds__(LGAR_ACTIVE_THREADS) lgar_step_active_kernel(LgarConfig cfg, LgarDeviceState d, LgarSinks sinks) {
+__global__ void __launch_bounds__(LGAR_ACTIVE_THREADS) lgar_step_active_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarSinks sinks) {
   const int lane = threadIdx.x & 31;
   const int count = d.work_count[0];
   for (;;) {
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(LGAR_ACTIVE_THREADS) lgar_step_active_kernel(L
 // After the first round every column of the tile sits at an active step of its own hour, so PROCESS
 // batches are full warps.  A straggler (the trip counts are heavy tailed: median 7, max > 20 000
 // theta evaluations per active step) delays only its own tile, never the other 147 SMs.
-__global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_window_kernel(LgarConfig cfg, LgarDeviceState d, LgarWindow w) {
+__global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_window_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w) {
   __shared__ unsigned short s_t[LGAR_WINDOW_THREADS / 32][LGAR_TILE];
   __shared__ unsigned short s_ready[LGAR_WINDOW_THREADS / 32][LGAR_TILE];
   __shared__ unsigned char s_flag[LGAR_WINDOW_THREADS / 32][LGAR_TILE];
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_window_kernel(LgarCo
 // stages.  No shared memory, no barrier of any scope.
 #define LGAR_SEARCH_MIN 12
 #define LGAR_SEARCH_QUANTUM 32
-__global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_lanes_kernel(LgarConfig cfg, LgarDeviceState d, LgarWindow w) {
+__global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_lanes_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w) {
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   LgLane L;
@@ -289,8 +289,33 @@ struct alignas(16) LgLaneSlot {
 constexpr int kTailBytes = (int)offsetof(LgLane, old);
 static_assert(offsetof(LgLane, old) % 16 == 0 && offsetof(LgLane, k) % 16 == 0 && sizeof(LgLaneSlot) % 16 == 0, "LgLane layout");
 
+// Resident blocks per SM the compiler must leave room for, per stage (0 = no constraint).  The stages are bound by
+// memory latency, so occupancy pays more than a few extra registers; values picked from the sweep in
+// profiles/r1_ncu_summary.md.
+#ifndef LGAR_MB_FETCH
+#define LGAR_MB_FETCH 0
+#endif
+#ifndef LGAR_MB_HEAD
+#define LGAR_MB_HEAD 0
+#endif
+#ifndef LGAR_MB_FRONT
+#define LGAR_MB_FRONT 0
+#endif
+#ifndef LGAR_MB_SEARCH
+#define LGAR_MB_SEARCH 0
+#endif
+#ifndef LGAR_MB_TAIL
+#define LGAR_MB_TAIL 0
+#endif
+#ifndef LGAR_MB_CORR
+#define LGAR_MB_CORR 0
+#endif
+constexpr int wave_min_blocks(int stage) {
+  return stage == LG_ST_FETCH ? LGAR_MB_FETCH : stage == LG_ST_HEAD ? LGAR_MB_HEAD : stage == LG_ST_FRONT ? LGAR_MB_FRONT
+       : stage == LG_ST_SEARCH ? LGAR_MB_SEARCH : stage == LG_ST_TAIL ? LGAR_MB_TAIL : LGAR_MB_CORR;
+}
 template <int STAGE>
-__global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDeviceState d, LgarWindow w, LgarWave wv, int consume,
+__global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int consume,
                                                         unsigned append_mask, int quantum) {
   const int n = wv.qcount[STAGE * 2 + consume];
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
@@ -314,11 +339,14 @@ __global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDevi
       if (valid) {  // the correction record and the front list travel
         LgLane& G = slots[slot].L;
         LgCorr k = G.k;
-        LgFronts f = G.f;
+        // bounded unrolling: a plain struct copy keeps all 680 bytes in flight in registers (231 registers/thread)
+        struct alignas(16) FrontsBuf { LgFronts f; } fb;
+        static_assert(offsetof(LgLane, f) % 16 == 0 && sizeof(FrontsBuf) % 16 == 0, "front list must be 16-byte copyable");
+        ctx_copy<(int)sizeof(FrontsBuf)>(&fb, reinterpret_cast<const FrontsBuf*>(&G.f));
         const LgarColumnClass* cls = G.cls;
-        for (int it = 0; it < quantum && !k.done; it++) lg_corr_iter(k, f, *cls);
+        for (int it = 0; it < quantum && !k.done; it++) lg_corr_iter(k, fb.f, *cls);
         G.k = k;
-        G.f = f;
+        ctx_copy<(int)sizeof(FrontsBuf)>(reinterpret_cast<FrontsBuf*>(&G.f), &fb);
         next = k.done ? LG_ST_TAIL : LG_ST_CORR;
       }
     } else if (STAGE == LG_ST_FETCH) {
@@ -388,7 +416,7 @@ __global__ void __launch_bounds__(128) lgar_wave_kernel(LgarConfig cfg, LgarDevi
 // going back to HBM between stages: the critical path per active step drops from one round to the serial
 // execution time of the step.  Lane utilisation is poor by construction, which does not matter for the few
 // thousand slots this is used for.
-__global__ void __launch_bounds__(128) lgar_wave_finish_kernel(LgarConfig cfg, LgarDeviceState d, LgarWindow w, LgarWave wv) {
+__global__ void __launch_bounds__(128) lgar_wave_finish_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv) {
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
   int total = 0;
   for (int q = 0; q < 2 * LGAR_NSTAGE; q++) total += wv.qcount[q];
