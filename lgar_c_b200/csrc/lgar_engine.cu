@@ -84,8 +84,10 @@ struct lgarb_engine {
   // wavefront scheduler (mode 3)
   LgarWave wave;
   bool wave_ready = false;
-  int wave_quantum = 32, wave_pairs = 3, wave_corr_pairs = 2;
+  int wave_quantum = 64, wave_pairs = 4, wave_corr_pairs = 1;
   int wave_finish_below = 16384;
+  int wave_escalate_below = 8192;
+  int wave_corr_quantum = 64;  // correction-search trips per launch (scaled with the psi-search quantum when that escalates)
   int64_t wave_max_slots = 16777216;  // 2.8 KB of context per slot
   int64_t wave_rounds = 0;
   int32_t* d_tile_counter = nullptr;
@@ -462,7 +464,19 @@ extern "C" {
 int lgarb_create(lgarb_engine** out) {
   if (!out) return LGARB_FAILURE;
   *out = new (std::nothrow) lgarb_engine();
-  return *out ? LGARB_SUCCESS : LGARB_FAILURE;
+  if (!*out) return LGARB_FAILURE;
+  // scheduler tuning knobs for experiments (defaults are the measured optimum, profiles/r1_ncu_summary.md)
+  auto knob = [](const char* name, int& v) {
+    const char* x = getenv(name);
+    if (x && *x) v = atoi(x);
+  };
+  knob("LGARB_WAVE_QUANTUM", (*out)->wave_quantum);
+  knob("LGARB_WAVE_PAIRS", (*out)->wave_pairs);
+  knob("LGARB_WAVE_CORR_PAIRS", (*out)->wave_corr_pairs);
+  knob("LGARB_WAVE_FINISH_BELOW", (*out)->wave_finish_below);
+  knob("LGARB_WAVE_ESCALATE_BELOW", (*out)->wave_escalate_below);
+  knob("LGARB_WAVE_CORR_QUANTUM", (*out)->wave_corr_quantum);
+  return LGARB_SUCCESS;
 }
 
 int lgarb_destroy(lgarb_engine* e) {
@@ -551,7 +565,8 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       cudaEventRecord(dbg_evs.back().first, e->stream);
       dbg_evs.back().second = stage;
     }
-    CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, quantum, in_flight, e->stream));
+    CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, stage == LG_ST_CORR ? std::max(1, quantum * e->wave_corr_quantum / e->wave_quantum) : quantum, in_flight,
+                                    e->stream));
     e->launches += 2;
   };
   int32_t* h_cnt = (int32_t*)e->pinned(64 * sizeof(int32_t));
@@ -584,7 +599,9 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       if (round > 100000000) throw std::runtime_error("wavefront scheduler did not terminate");
     }
     // few slots in flight = the long searches (up to 1e5 trips) are what is left: let them run longer per launch
-    quantum = in_flight > 65536 ? e->wave_quantum : in_flight > 8192 ? 4 * e->wave_quantum : in_flight > 1024 ? 32 * e->wave_quantum : 256 * e->wave_quantum;
+    // (while thousands of other slots are in flight a long search must not hold the round up: it keeps its place in
+    // the SEARCH/CORR queue and continues next round)
+    quantum = in_flight > e->wave_escalate_below ? e->wave_quantum : in_flight > 1024 ? 32 * e->wave_quantum : 256 * e->wave_quantum;
     if (debug) cudaEventRecord(dbg[0], e->stream);
     const bool new_steps = cnt[LG_ST_FETCH] + cnt[LG_ST_HEAD] > 0;
     if (new_steps) {
@@ -617,12 +634,8 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       }
       for (auto& pe : dbg_evs) cudaEventDestroy(pe.first);
       dbg_evs.clear();
-      if (round < 40 || round % 20 == 0)
-        fprintf(stderr, "[wave]   stage ms: FETCH %.2f HEAD %.2f FRONT %.2f SEARCH %.2f TAIL %.2f CORR %.2f\n", st_ms[0], st_ms[1], st_ms[2], st_ms[3],
-                st_ms[4], st_ms[5]);
-      if (round < 40 || round % 20 == 0)
-        fprintf(stderr, "[wave] round %lld: %.3f ms  in flight %d  queues(before) F=%d H=%d FR=%d S=%d T=%d C=%d\n", (long long)round, ms, in_flight,
-                cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], cnt[5]);
+      fprintf(stderr, "[wave] round %lld: %.3f ms  in flight %d  queues F=%d H=%d FR=%d S=%d T=%d C=%d  ms: FETCH %.2f HEAD %.2f FRONT %.2f SEARCH %.2f TAIL %.2f CORR %.2f\n",
+              (long long)round, ms, in_flight, cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], cnt[5], st_ms[0], st_ms[1], st_ms[2], st_ms[3], st_ms[4], st_ms[5]);
     }
   }
   if (debug) {
