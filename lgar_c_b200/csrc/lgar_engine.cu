@@ -9,6 +9,7 @@
 // The engine owns all device memory (fixed-capacity SoA, lgar_types.h) and a CUDA stream.  There is
 // no CPU path: without a usable CUDA device initialisation fails.
 #include <cuda_runtime.h>
+#include <cuda_profiler_api.h>
 
 #include <cmath>
 #include <cstdio>
@@ -86,6 +87,7 @@ struct lgarb_engine {
   bool wave_ready = false;
   int wave_quantum = 64, wave_pairs = 4, wave_corr_pairs = 1;
   int wave_finish_below = 16384;
+  int wave_windows = 0;  // windows run so far (profiling range selection)
   int wave_escalate_below = 8192;
   int wave_corr_quantum = 64;  // correction-search trips per launch (scaled with the psi-search quantum when that escalates)
   int64_t wave_max_slots = 16777216;  // 2.8 KB of context per slot
@@ -547,12 +549,16 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
   w.done_columns = wv.done_columns;
   CUDA_TRY(cudaMemsetAsync(e->d_tile_counter, 0, sizeof(int32_t), e->stream));
   w.slot_is_column = (wv.nslots == e->ncol) ? 1 : 0;
-  CUDA_TRY(lgar_launch_wave_init(wv, w.slot_is_column, e->stream));
+  CUDA_TRY(lgar_launch_wave_init(e->cfg, e->d, wv, w.slot_is_column, e->stream));
   e->launches += 1;
   int par[LGAR_NSTAGE] = {0, 0, 0, 0, 0, 0};
   int quantum = e->wave_quantum;
   int in_flight = wv.nslots;
   const bool dbg_on = getenv("LGARB_WAVE_DEBUG") != nullptr;
+  // `ncu --profile-from-start off`: LGARB_NCU_WINDOW=i LGARB_NCU_ROUND=r profiles exactly round r of the i-th window of this engine
+  const int ncu_round = (getenv("LGARB_NCU_WINDOW") && atoi(getenv("LGARB_NCU_WINDOW")) == e->wave_windows)
+                            ? (getenv("LGARB_NCU_ROUND") ? atoi(getenv("LGARB_NCU_ROUND")) : 0) : -1;
+  e->wave_windows++;
   std::vector<std::pair<cudaEvent_t, int>> dbg_evs;
   auto launch = [&](int stage) {
     const int consume = par[stage];
@@ -603,6 +609,10 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
     // the SEARCH/CORR queue and continues next round)
     quantum = in_flight > e->wave_escalate_below ? e->wave_quantum : in_flight > 1024 ? 32 * e->wave_quantum : 256 * e->wave_quantum;
     if (debug) cudaEventRecord(dbg[0], e->stream);
+    if (round == ncu_round) {
+      cudaStreamSynchronize(e->stream);
+      cudaProfilerStart();
+    }
     const bool new_steps = cnt[LG_ST_FETCH] + cnt[LG_ST_HEAD] > 0;
     if (new_steps) {
       launch(LG_ST_FETCH);
@@ -621,6 +631,10 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       launch(LG_ST_TAIL);
     }
     e->wave_rounds++;
+    if (round == ncu_round) {
+      cudaStreamSynchronize(e->stream);
+      cudaProfilerStop();
+    }
     if (debug) {
       cudaEventRecord(dbg[1], e->stream);
       cudaEventSynchronize(dbg[1]);

@@ -287,7 +287,9 @@ struct alignas(16) LgLaneSlot {
   LgLane L;
 };
 constexpr int kTailBytes = (int)offsetof(LgLane, old);
-static_assert(offsetof(LgLane, old) % 16 == 0 && offsetof(LgLane, k) % 16 == 0 && sizeof(LgLaneSlot) % 16 == 0, "LgLane layout");
+constexpr int kStateBytes = (int)offsetof(LgLane, pro);  // the column state at the head of the record
+static_assert(offsetof(LgLane, old) % 16 == 0 && offsetof(LgLane, k) % 16 == 0 && offsetof(LgLane, pro) % 16 == 0 && sizeof(LgLaneSlot) % 16 == 0,
+              "LgLane layout");
 
 // Resident blocks per SM the compiler must leave room for, per stage (0 = no constraint).  The stages are bound by
 // memory latency, so occupancy pays more than a few extra registers; values picked from the sweep in
@@ -350,29 +352,19 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         next = k.done ? LG_ST_TAIL : LG_ST_CORR;
       }
     } else if (STAGE == LG_ST_FETCH) {
-      if (valid) {  // a fetching slot owns nothing but (column, hour)
+      if (valid) {  // works on the record in place: scalars and epilogue state through registers, nothing else is touched
         LgLane& G = slots[slot].L;
-        LgLane L;
-        L.col = G.col;
-        L.t = G.t;
-        L.tr_iters = 0;
-        L.tr_kcyc = 0;
-        lg_stage_fetch(cfg, d, w, L, fsp);
-        G.col = L.col;
-        G.t = L.t;
-        next = L.stage;
+        lg_stage_fetch(cfg, d, w, G, fsp);
+        next = G.stage;
       }
     } else if (valid) {
       LgLaneSlot S;
       LgLane& L = S.L;
-      if (STAGE == LG_ST_HEAD) {  // HEAD builds the context from the column state
-        L.col = slots[slot].L.col;
-        L.t = slots[slot].L.t;
-        L.tr_iters = 0;
-        L.tr_kcyc = 0;
+      if (STAGE == LG_ST_HEAD) {  // HEAD starts the step context behind the resident column state
+        ctx_copy<kStateBytes>(&S, &slots[slot]);
         lg_stage_head(cfg, d, w, L, fsp);
         active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
-        // every new step goes straight into its front loop: saves one 2.7 KB context round trip per step
+        // every new step goes straight into its front loop: saves one context round trip per step
         if (L.stage == LG_ST_FRONT) lg_stage_front(L);
       } else {
         // TAIL works on everything up to and including the correction record; FRONT needs state_previous
@@ -391,8 +383,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
       }
       next = L.stage;
       if (next == LG_ST_FETCH) {
-        slots[slot].L.col = L.col;
-        slots[slot].L.t = L.t;
+        ctx_copy<kStateBytes>(&slots[slot], &S);  // the step is over: only the column state lives on
       } else if (STAGE == LG_ST_TAIL && next == LG_ST_CORR) {
         ctx_copy<kTailBytes>(&slots[slot], &S);  // TAIL -> CORR -> TAIL: neither state_previous nor the psi search is live
       } else if (next == LG_ST_TAIL) {
@@ -481,17 +472,20 @@ cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState
   return cudaGetLastError();
 }
 
-__global__ void lgar_wave_init_kernel(LgarWave wv, int slot_is_column) {
+__global__ void lgar_wave_init_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWave wv,
+                                      int slot_is_column) {
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wv.nslots; i += gridDim.x * blockDim.x) {
-    slots[i].L.stage = LG_ST_FETCH;
-    // slot == column keeps queue order close to column order, so the column-state traffic of FETCH, HEAD and
-    // TAIL stays (nearly) coalesced; with fewer slots than columns, slots draw columns from a counter instead
-    slots[i].L.col = slot_is_column ? i : -1;
-    slots[i].L.t = slot_is_column ? 0 : 0x7FFFFFFF;
-    slots[i].L.resume = false;
-    slots[i].L.tr_iters = 0;
-    slots[i].L.tr_kcyc = 0;
+    LgLane& L = slots[i].L;
+    L.stage = LG_ST_FETCH;
+    // slot == column: the slot imports its column's state here (coalesced reads of the SoA arrays) and keeps it
+    // for the whole window; with fewer slots than columns, slots draw columns from a counter in FETCH instead
+    L.col = slot_is_column ? i : -1;
+    L.t = 0;
+    L.resume = false;
+    L.tr_iters = 0;
+    L.tr_kcyc = 0;
+    if (slot_is_column) lg_lane_import(cfg, d, i, L);
     wv.queue[LG_ST_FETCH][0][i] = i;
   }
   if (blockIdx.x == 0 && threadIdx.x < LGAR_NSTAGE * 2) wv.qcount[threadIdx.x] = (threadIdx.x == LG_ST_FETCH * 2) ? wv.nslots : 0;
@@ -501,8 +495,8 @@ __global__ void lgar_wave_init_kernel(LgarWave wv, int slot_is_column) {
 // reset the consumed queue's count after its kernel ran
 __global__ void lgar_wave_reset_kernel(int32_t* count) { *count = 0; }
 
-cudaError_t lgar_launch_wave_init(const LgarWave& wv, int slot_is_column, cudaStream_t stream) {
-  lgar_wave_init_kernel<<<(wv.nslots + 255) / 256, 256, 0, stream>>>(wv, slot_is_column);
+cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWave& wv, int slot_is_column, cudaStream_t stream) {
+  lgar_wave_init_kernel<<<(wv.nslots + 255) / 256, 256, 0, stream>>>(cfg, d, wv, slot_is_column);
   return cudaGetLastError();
 }
 

@@ -58,7 +58,7 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
                                    unsigned append_mask, int quantum, int max_items, cudaStream_t stream);
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
                                     cudaStream_t stream);
-cudaError_t lgar_launch_wave_init(const LgarWave& wv, int slot_is_column, cudaStream_t stream);
+cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWave& wv, int slot_is_column, cudaStream_t stream);
 size_t lgar_lane_context_bytes();
 // mode 1: warp-tile window kernel; mode 2: per-lane staged program (lgar_lanes.cuh)
 cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream, int mode);

@@ -40,17 +40,23 @@ struct LgCorr {
   bool switched, aug, aug_extreme, done;
 };
 
-// Field order matters: the wavefront kernels copy only the leading part a stage needs
-// (TAIL: up to `old`; FRONT: up to `k`), see lgar_wave_kernel.
+// The lane record.  Its head is the column's STATE (scalars, GIUH queue, cumulative volumes, front list): it is
+// imported from the SoA arrays when the lane takes the column and exported when the column has finished its
+// window (lg_lane_import/export), so between those two points no stage touches the SoA state -- the wavefront
+// kernels move contiguous records, not 45 scattered 8-byte values per step.  Behind it the context of the step in
+// flight.  Field order matters: the wavefront kernels copy only the leading part a stage needs (state: up to
+// `pro`; TAIL: up to `old`), see lgar_wave_kernel.
 struct LgLane {
   int stage;
   int t;
   int64_t col;
   const LgarColumnClass* cls;
   LgCtx c;
-  LgScalars s;
-  // step context (locals of lg_step_active)
-  LgPrologue pro;
+  alignas(16) LgScalars s;
+  LgEpi ep;
+  alignas(16) LgFronts f;
+  // ---- step context (locals of lg_step_active) ----
+  alignas(16) LgPrologue pro;
   double P, E;
   LgStepVols v;
   LgCycle cy;
@@ -65,11 +71,23 @@ struct LgLane {
   double fx_prior_mass, fx_mass_change;
   bool create, resume, fx_resume;
   unsigned int tr_iters, tr_kcyc;  // work trace of the current column (debug)
-  alignas(16) LgFronts f;
   alignas(16) LgCorr k;   // TAIL/CORR stop copying after this
   alignas(16) LgOld old;  // FRONT only
   alignas(16) LgSearch q; // FRONT/SEARCH only
 };
+
+// column state: SoA arrays <-> lane record
+LG_FN_NOINLINE void lg_lane_import(const LgarConfig& cfg, const LgarDeviceState& d, int64_t col, LgLane& L) {
+  L.cls = d.classes + d.class_id[col];
+  load_scalars(d, col, L.s);
+  load_fronts(d, col, L.f);
+  lg_epi_load(cfg, d, col, L.ep);
+}
+LG_FN_NOINLINE void lg_lane_export(const LgarConfig& cfg, const LgarDeviceState& d, int64_t col, const LgLane& L) {
+  store_scalars(d, col, L.s, true);
+  store_fronts(d, col, L.f);
+  lg_epi_store(cfg, d, col, L.ep);
+}
 
 // ---- psi search split into init / iterate / finish (lgar.cxx:2952-3112) ---------------------------
 // returns true when the search has to iterate (otherwise q.theta is final)
@@ -785,9 +803,7 @@ LG_FN_NOINLINE int lg_cycle_end(const LgarConfig& cfg, LgLane& L) {
 LG_FN_NOINLINE void lg_stage_head(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, LgLane& L, unsigned long long* front_sum) {
   const int64_t col = L.col;
   const int t = L.t;
-  L.cls = d.classes + d.class_id[col];
   double P = w.precip[(int64_t)t * w.series_stride + col], E = w.pet[(int64_t)t * w.series_stride + col];
-  load_scalars(d, col, L.s);
   L.pro = lg_prologue(cfg, L.s, P);
   if (cfg.adaptive_timestep) L.s.timestep_h = L.pro.subtimestep_h;
   L.s.cache_count = L.pro.cache_count;
@@ -799,19 +815,13 @@ LG_FN_NOINLINE void lg_stage_head(const LgarConfig& cfg, const LgarDeviceState& 
     L.s.cache_fluxes = 1;
     lg_step_cached(cfg, L.s, L.pro, P, E, L.v);
     if (!(fabs(L.v.local_mb) <= cfg.mbal_tol)) L.s.status |= (isnan(L.v.local_mb) ? LGAR_FAIL_NAN : LGAR_FAIL_MBAL);
-    store_scalars(d, col, L.s, false);
-    const LgarSinks sk = lg_sinks_at(w, t);
-    epilogue(cfg, d, sk, col, L.v, L.s.status, t == w.K - 1);
-    if (w.nf_sink || front_sum) {
-      const int nf = d.nfront[col];
-      if (w.nf_sink) w.nf_sink[(int64_t)t * w.sink_stride + col] = nf;
-      if (front_sum) *front_sum += (unsigned)nf;
-    }
+    lg_epi_step(cfg, d, w, t, col, L.ep, L.v, L.s.status, t == w.K - 1);
+    if (w.nf_sink) w.nf_sink[(int64_t)t * w.sink_stride + col] = L.f.n;
+    if (front_sum) *front_sum += (unsigned)L.f.n;
     L.t = t + 1;
     L.stage = LG_ST_FETCH;
     return;
   }
-  load_fronts(d, col, L.f);
   L.s.cache_fluxes = 0;
   L.c.cfg = &cfg;
   L.c.cls = L.cls;
@@ -828,7 +838,7 @@ LG_FN_NOINLINE void lg_stage_head(const LgarConfig& cfg, const LgarDeviceState& 
 // FRONT: front-loop iterations; ends in SEARCH or TAIL
 LG_FN void lg_stage_front(LgLane& L) { L.stage = lg_move_fronts(L) ? LG_ST_SEARCH : LG_ST_TAIL; }
 
-// TAIL: ends in FRONT (next sub-cycle) or FETCH (step finished, state written back)
+// TAIL: ends in FRONT (next sub-cycle), CORR, or FETCH (step finished: GIUH, cumulative volumes, outputs)
 LG_FN_NOINLINE void lg_stage_tail(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, LgLane& L, unsigned long long* front_sum) {
   const int r = lg_cycle_end(cfg, L);
   if (r == 0) {
@@ -841,49 +851,56 @@ LG_FN_NOINLINE void lg_stage_tail(const LgarConfig& cfg, const LgarDeviceState& 
   }
   const int64_t col = L.col;
   const int t = L.t;
-  store_scalars(d, col, L.s, true);
-  store_fronts(d, col, L.f);
-  const LgarSinks sk = lg_sinks_at(w, t);
-  epilogue(cfg, d, sk, col, L.v, L.s.status, t == w.K - 1);
+  lg_epi_step(cfg, d, w, t, col, L.ep, L.v, L.s.status, t == w.K - 1);
   if (w.nf_sink) w.nf_sink[(int64_t)t * w.sink_stride + col] = L.f.n;
   if (front_sum) *front_sum += (unsigned)L.f.n;
   L.t = t + 1;
   L.stage = LG_ST_FETCH;
 }
 
-// FETCH: take the next column when the current one has finished its window, walk it through the hours
-// that need no flux computation.  Ends in HEAD (active step at hour L.t) or DONE (no columns left).
+// FETCH: walk the resident column through the hours that need no flux computation; when it has finished the
+// window write its state back and (unless the slot is bound to one column) take the next column.  Ends in
+// HEAD (active step at hour L.t) or DONE.  L may live in HBM: the hot loop works on register copies.
 LG_FN_NOINLINE void lg_stage_fetch(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, LgLane& L, unsigned long long* front_sum) {
   for (;;) {
-    if (w.slot_is_column && L.t >= w.K) {  // this slot's only column has finished the window
-      L.stage = LG_ST_DONE;
-      return;
+    if (L.col >= 0 && L.t >= w.K) {  // this column has finished the window
+      lg_lane_export(cfg, d, L.col, L);
+#ifndef LGAR_HOSTSIM
+      if (w.done_columns) atomicAdd(w.done_columns, 1);
+#endif
+      if (w.work_trace) {
+        w.work_trace[L.col] = L.tr_iters;
+        w.work_trace[w.trace_stride + L.col] = L.tr_kcyc;
+      }
+      L.col = -1;
     }
-    if (L.col < 0 || L.t >= w.K) {
+    if (L.col < 0) {
+      if (w.slot_is_column) {
+        L.stage = LG_ST_DONE;
+        return;
+      }
 #ifdef LGAR_HOSTSIM
       const int64_t col = (*w.tile_counter)++;
 #else
       const int64_t col = atomicAdd(w.tile_counter, 1);
 #endif
-#ifndef LGAR_HOSTSIM
-      if (w.done_columns && L.col >= 0) atomicAdd(w.done_columns, 1);
-#endif
-      if (w.work_trace && L.col >= 0) {
-        w.work_trace[L.col] = L.tr_iters;
-        w.work_trace[w.trace_stride + L.col] = L.tr_kcyc;
-      }
-      L.tr_iters = 0;
-      L.tr_kcyc = 0;
       if (col >= d.ncol) {
-        L.col = -1;
         L.stage = LG_ST_DONE;
         return;
       }
       L.col = col;
       L.t = 0;
+      L.tr_iters = 0;
+      L.tr_kcyc = 0;
+      lg_lane_import(cfg, d, col, L);
     }
-    L.t = lg_advance_column(cfg, d, w, L.col, L.t, front_sum);
-    if (L.t < w.K) {
+    LgScalars s = L.s;
+    LgEpi ep = L.ep;
+    const int t1 = lg_advance_resident(cfg, d, w, L.cls, L.col, L.t, L.f.n, s, ep, front_sum);
+    L.s = s;
+    L.ep = ep;
+    L.t = t1;
+    if (t1 < w.K) {
       L.stage = LG_ST_HEAD;
       return;
     }

@@ -267,21 +267,15 @@ LG_FN LgarSinks lg_sinks_at(const LgarWindow& w, int t) {
 // version indexed one array dynamically: 1 KB of local-memory traffic per column-hour, which made the
 // FETCH kernel L2-write bound -- profiles/r1_ncu_summary.md r1f.)
 #define LGAR_EPI_REGS 8
-struct LgEpi {
-  double qr[LGAR_EPI_REGS];
-  double qm[LGAR_MAXG];
+struct alignas(16) LgEpi {
+  double qr[LGAR_EPI_REGS];  // GIUH queue slots 0..N-2 when N <= LGAR_EPI_REGS (longer queues stay in d.giuhq)
   double cum[LGAR_NCUM];
 };
 LG_FN void lg_epi_load(const LgarConfig& cfg, const LgarDeviceState& d, int64_t col, LgEpi& e) {
   const int64_t st = d.stride;
   const int N = cfg.num_giuh;
-  if (N <= LGAR_EPI_REGS) {
 #pragma unroll
-    for (int i = 0; i < LGAR_EPI_REGS - 1; i++) e.qr[i] = (i + 1 < N) ? d.giuhq[(int64_t)i * st + col] : 0.0;
-    e.qr[LGAR_EPI_REGS - 1] = 0.0;
-  } else {
-    for (int i = 0; i + 1 < N; i++) e.qm[i] = d.giuhq[(int64_t)i * st + col];
-  }
+  for (int i = 0; i < LGAR_EPI_REGS; i++) e.qr[i] = (N <= LGAR_EPI_REGS && i + 1 < N) ? d.giuhq[(int64_t)i * st + col] : 0.0;
 #pragma unroll
   for (int k = 0; k < LGAR_NCUM; k++) e.cum[k] = d.cum[(int64_t)k * st + col];
 }
@@ -292,8 +286,6 @@ LG_FN void lg_epi_store(const LgarConfig& cfg, const LgarDeviceState& d, int64_t
 #pragma unroll
     for (int i = 0; i < LGAR_EPI_REGS - 1; i++)
       if (i + 1 < N) d.giuhq[(int64_t)i * st + col] = e.qr[i];
-  } else {
-    for (int i = 0; i + 1 < N; i++) d.giuhq[(int64_t)i * st + col] = e.qm[i];
   }
 #pragma unroll
   for (int k = 0; k < LGAR_NCUM; k++) d.cum[(int64_t)k * st + col] = e.cum[k];
@@ -328,13 +320,13 @@ LG_FN void lg_epi_step(const LgarConfig& cfg, const LgarDeviceState& d, const Lg
         e.qr[i - 1] = qi;
       }
     }
-  } else {
-    const double carry = e.qm[0];
+  } else {  // long unit hydrograph: the queue is read-modify-written in HBM, as in epilogue()
+    const double carry = d.giuhq[col];
     now = carry + cfg.giuh[0] * r;
     for (int i = 1; i < N; i++) {
-      double qi = (i < N - 1) ? e.qm[i] : 0.0;
+      double qi = (i < N - 1) ? d.giuhq[(int64_t)i * st + col] : 0.0;
       qi += cfg.giuh[i] * r;
-      e.qm[i - 1] = qi;
+      d.giuhq[(int64_t)(i - 1) * st + col] = qi;
     }
   }
   e.cum[LGAR_CUM_PRECIP] += v.precip;
@@ -414,6 +406,50 @@ LG_FN_NOINLINE int lg_advance_column(const LgarConfig& cfg, const LgarDeviceStat
   }
   if (epi_loaded) lg_epi_store(cfg, d, col, ep);
   if (dirty) store_scalars(d, col, s, false);
+  return t;
+}
+
+// The same walk for a column whose scalars, GIUH queue and cumulative volumes are resident in its lane
+// record (lgar_lanes.cuh): nothing is read from or written to the SoA state.
+LG_FN int lg_advance_resident(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarColumnClass* cls, int64_t col, int t,
+                              int nf, LgScalars& s, LgEpi& ep, unsigned long long* front_sum) {
+  const int K = w.K;
+  if (cls->invalid_soil_type) {  // Q = precip (bmi_lgar.cxx:145-179); cumulative volumes as step_invalid()
+    for (; t < K; t++) {
+      const double P = w.precip[(int64_t)t * w.series_stride + col];
+      const double pm = P * 0.001;
+      const int64_t so = (int64_t)t * w.sink_stride + col;
+#pragma unroll
+      for (int k = 0; k < LGAR_NOUT; k++) {
+        const double val = (k == LGAR_OUT_PRECIP || k == LGAR_OUT_RUNOFF || k == LGAR_OUT_Q) ? pm : 0.0;
+        if (t == K - 1) d.out[k * d.stride + col] = val;
+        if (w.sinks.p[k]) w.sinks.p[k][so] = val;
+      }
+      ep.cum[LGAR_CUM_PRECIP] += P * 0.1;
+      ep.cum[LGAR_CUM_RUNOFF] += P * 0.1;
+      ep.cum[LGAR_CUM_Q] += P * 0.1;
+      if (w.nf_sink) w.nf_sink[so] = 0;
+    }
+    return K;
+  }
+  for (; t < K; t++) {
+    double P = w.precip[(int64_t)t * w.series_stride + col], E = w.pet[(int64_t)t * w.series_stride + col];
+    LgStepVols v;
+    zero_vols(v);
+    if (!(s.status & LGAR_FAIL_MASK)) {
+      const LgPrologue pro = lg_prologue_inl(cfg, s, P);
+      if (!pro.cache_fluxes || w.force_all_active) break;
+      if (cfg.adaptive_timestep) s.timestep_h = pro.subtimestep_h;
+      s.cache_fluxes = 1;
+      s.cache_count = pro.cache_count;
+      adjust_forcing(cfg, P, E, s.status);
+      lg_step_cached_inl(cfg, s, pro, P, E, v);
+      if (!(fabs(v.local_mb) <= cfg.mbal_tol)) s.status |= (isnan(v.local_mb) ? LGAR_FAIL_NAN : LGAR_FAIL_MBAL);
+    }
+    lg_epi_step(cfg, d, w, t, col, ep, v, s.status, t == K - 1);
+    if (w.nf_sink) w.nf_sink[(int64_t)t * w.sink_stride + col] = nf;
+    if (front_sum) *front_sum += (unsigned)nf;
+  }
   return t;
 }
 
