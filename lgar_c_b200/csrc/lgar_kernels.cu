@@ -271,24 +271,43 @@ __device__ __forceinline__ void wave_push(const LgarWave& wv, unsigned append_ma
   wv.queue[stage][buf][base + __popc(m & ((1u << lane) - 1))] = slot;
 }
 
-// context copy between HBM and thread-private memory, 16 bytes at a time; NBYTES = leading part to move
+// Context copy between HBM and thread-private memory.  The HBM side moves 32 bytes per lane per instruction
+// (LDG/STG.E.256, new on sm_100): a lane's record is contiguous, so every access is one full 32-byte sector --
+// with 16-byte accesses each sector is requested twice (ncu: lts write sectors = 2x the bytes stored).
+// NBYTES = leading part of the record to move.
 template <int NBYTES, typename T>
-__device__ __forceinline__ void ctx_copy(T* dst, const T* src) {
-  static_assert(NBYTES % 16 == 0 && NBYTES <= (int)sizeof(T), "context part must be a multiple of 16 bytes");
-  const uint4* s4 = reinterpret_cast<const uint4*>(src);
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll 16
-  for (int i = 0; i < NBYTES / 16; i++) d4[i] = s4[i];  // 16 independent 16-byte loads in flight per thread
+__device__ __forceinline__ void ctx_load(T* local_dst, const T* global_src) {
+  static_assert(NBYTES % 32 == 0 && NBYTES <= (int)sizeof(T), "context part must be a multiple of 32 bytes");
+  const char* g = reinterpret_cast<const char*>(global_src);
+  ulonglong2* l = reinterpret_cast<ulonglong2*>(local_dst);
+#pragma unroll 8
+  for (int i = 0; i < NBYTES / 32; i++) {
+    unsigned long long a, b, c, e;
+    asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(e) : "l"(g + 32 * i));
+    l[2 * i] = make_ulonglong2(a, b);
+    l[2 * i + 1] = make_ulonglong2(c, e);
+  }
+}
+template <int NBYTES, typename T>
+__device__ __forceinline__ void ctx_store(T* global_dst, const T* local_src) {
+  static_assert(NBYTES % 32 == 0 && NBYTES <= (int)sizeof(T), "context part must be a multiple of 32 bytes");
+  char* g = reinterpret_cast<char*>(global_dst);
+  const ulonglong2* l = reinterpret_cast<const ulonglong2*>(local_src);
+#pragma unroll 8
+  for (int i = 0; i < NBYTES / 32; i++) {
+    const ulonglong2 x = l[2 * i], y = l[2 * i + 1];
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(g + 32 * i), "l"(x.x), "l"(x.y), "l"(y.x), "l"(y.y) : "memory");
+  }
 }
 
 }  // namespace
 
-struct alignas(16) LgLaneSlot {
+struct alignas(32) LgLaneSlot {
   LgLane L;
 };
 constexpr int kTailBytes = (int)offsetof(LgLane, old);
 constexpr int kStateBytes = (int)offsetof(LgLane, pro);  // the column state at the head of the record
-static_assert(offsetof(LgLane, old) % 16 == 0 && offsetof(LgLane, k) % 16 == 0 && offsetof(LgLane, pro) % 16 == 0 && sizeof(LgLaneSlot) % 16 == 0,
+static_assert(offsetof(LgLane, old) % 32 == 0 && offsetof(LgLane, pro) % 32 == 0 && offsetof(LgLane, f) % 32 == 0 && sizeof(LgLaneSlot) % 32 == 0,
               "LgLane layout");
 
 // Resident blocks per SM the compiler must leave room for, per stage (0 = no constraint).  The stages are bound by
@@ -342,13 +361,13 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         LgLane& G = slots[slot].L;
         LgCorr k = G.k;
         // bounded unrolling: a plain struct copy keeps all 680 bytes in flight in registers (231 registers/thread)
-        struct alignas(16) FrontsBuf { LgFronts f; } fb;
-        static_assert(offsetof(LgLane, f) % 16 == 0 && sizeof(FrontsBuf) % 16 == 0, "front list must be 16-byte copyable");
-        ctx_copy<(int)sizeof(FrontsBuf)>(&fb, reinterpret_cast<const FrontsBuf*>(&G.f));
+        struct alignas(32) FrontsBuf { LgFronts f; } fb;
+        static_assert(sizeof(FrontsBuf) <= offsetof(LgLane, pro) - offsetof(LgLane, f), "front list copy must stay inside the record");
+        ctx_load<(int)sizeof(FrontsBuf)>(&fb, reinterpret_cast<const FrontsBuf*>(&G.f));
         const LgarColumnClass* cls = G.cls;
         for (int it = 0; it < quantum && !k.done; it++) lg_corr_iter(k, fb.f, *cls);
         G.k = k;
-        ctx_copy<(int)sizeof(FrontsBuf)>(reinterpret_cast<FrontsBuf*>(&G.f), &fb);
+        ctx_store<(int)sizeof(FrontsBuf)>(reinterpret_cast<FrontsBuf*>(&G.f), &fb);
         next = k.done ? LG_ST_TAIL : LG_ST_CORR;
       }
     } else if (STAGE == LG_ST_FETCH) {
@@ -361,7 +380,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
       LgLaneSlot S;
       LgLane& L = S.L;
       if (STAGE == LG_ST_HEAD) {  // HEAD starts the step context behind the resident column state
-        ctx_copy<kStateBytes>(&S, &slots[slot]);
+        ctx_load<kStateBytes>(&S, &slots[slot]);
         lg_stage_head(cfg, d, w, L, fsp);
         active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
         // every new step goes straight into its front loop: saves one context round trip per step
@@ -370,9 +389,9 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         // TAIL works on everything up to and including the correction record; FRONT needs state_previous
         // and the search record as well
         if (STAGE == LG_ST_TAIL)
-          ctx_copy<kTailBytes>(&S, &slots[slot]);
+          ctx_load<kTailBytes>(&S, &slots[slot]);
         else
-          ctx_copy<(int)sizeof(LgLaneSlot)>(&S, &slots[slot]);
+          ctx_load<(int)sizeof(LgLaneSlot)>(&S, &slots[slot]);
         L.c.cfg = &cfg;
         L.c.cls = L.cls;
         L.c.f = &L.f;
@@ -383,13 +402,13 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
       }
       next = L.stage;
       if (next == LG_ST_FETCH) {
-        ctx_copy<kStateBytes>(&slots[slot], &S);  // the step is over: only the column state lives on
+        ctx_store<kStateBytes>(&slots[slot], &S);  // the step is over: only the column state lives on
       } else if (STAGE == LG_ST_TAIL && next == LG_ST_CORR) {
-        ctx_copy<kTailBytes>(&slots[slot], &S);  // TAIL -> CORR -> TAIL: neither state_previous nor the psi search is live
+        ctx_store<kTailBytes>(&slots[slot], &S);  // TAIL -> CORR -> TAIL: neither state_previous nor the psi search is live
       } else if (next == LG_ST_TAIL) {
-        ctx_copy<kTailBytes>(&slots[slot], &S);  // the front loop is over
+        ctx_store<kTailBytes>(&slots[slot], &S);  // the front loop is over
       } else {
-        ctx_copy<(int)sizeof(LgLaneSlot)>(&slots[slot], &S);
+        ctx_store<(int)sizeof(LgLaneSlot)>(&slots[slot], &S);
       }
     }
 #pragma unroll
@@ -426,7 +445,7 @@ __global__ void __launch_bounds__(128) lgar_wave_finish_kernel(const __grid_cons
     }
     if (slot < 0) continue;
     LgLaneSlot S;
-    ctx_copy<(int)sizeof(LgLaneSlot)>(&S, &slots[slot]);
+    ctx_load<(int)sizeof(LgLaneSlot)>(&S, &slots[slot]);
     LgLane& L = S.L;
     L.stage = stage;  // the queue a slot sits in is authoritative: the partial-context stages do not rewrite L.stage
     L.c.cfg = &cfg;

@@ -54,9 +54,9 @@ struct LgLane {
   LgCtx c;
   alignas(16) LgScalars s;
   LgEpi ep;
-  alignas(16) LgFronts f;
+  alignas(32) LgFronts f;
   // ---- step context (locals of lg_step_active) ----
-  alignas(16) LgPrologue pro;
+  alignas(32) LgPrologue pro;
   double P, E;
   LgStepVols v;
   LgCycle cy;
@@ -72,7 +72,7 @@ struct LgLane {
   bool create, resume, fx_resume;
   unsigned int tr_iters, tr_kcyc;  // work trace of the current column (debug)
   alignas(16) LgCorr k;   // TAIL/CORR stop copying after this
-  alignas(16) LgOld old;  // FRONT only
+  alignas(32) LgOld old;  // FRONT only
   alignas(16) LgSearch q; // FRONT/SEARCH only
 };
 
