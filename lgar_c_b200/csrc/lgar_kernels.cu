@@ -300,15 +300,94 @@ __device__ __forceinline__ void ctx_store(T* global_dst, const T* local_src) {
   }
 }
 
+// dynamic-length variants (nchunks 32-byte chunks)
+__device__ __forceinline__ void ctx_load_n(char* l, const char* g, int nchunks) {
+#pragma unroll 1
+  for (int i = 0; i < nchunks; i++) {
+    unsigned long long a, b, c, e;
+    asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(e) : "l"(g + 32 * i));
+    reinterpret_cast<ulonglong2*>(l)[2 * i] = make_ulonglong2(a, b);
+    reinterpret_cast<ulonglong2*>(l)[2 * i + 1] = make_ulonglong2(c, e);
+  }
+}
+__device__ __forceinline__ void ctx_store_n(char* g, const char* l, int nchunks) {
+#pragma unroll 1
+  for (int i = 0; i < nchunks; i++) {
+    const ulonglong2 x = reinterpret_cast<const ulonglong2*>(l)[2 * i], y = reinterpret_cast<const ulonglong2*>(l)[2 * i + 1];
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(g + 32 * i), "l"(x.x), "l"(x.y), "l"(y.x), "l"(y.y) : "memory");
+  }
+}
+
 }  // namespace
 
 struct alignas(32) LgLaneSlot {
   LgLane L;
 };
-constexpr int kTailBytes = (int)offsetof(LgLane, old);
-constexpr int kStateBytes = (int)offsetof(LgLane, pro);  // the column state at the head of the record
-static_assert(offsetof(LgLane, old) % 32 == 0 && offsetof(LgLane, pro) % 32 == 0 && offsetof(LgLane, f) % 32 == 0 && sizeof(LgLaneSlot) % 32 == 0,
-              "LgLane layout");
+
+// Parts of the lane record (lgar_lanes.cuh) a stage moves between HBM and its thread-private copy.  The front
+// arrays have capacity LGAR_W = 16 but a column carries 4-5 fronts on average: only the live prefix of each
+// array travels (counts kept in the record's first sector), which removes about a third of the context traffic.
+enum { LG_PART_STATE = 1, LG_PART_STEP = 2, LG_PART_OLD = 4, LG_PART_SEARCH = 8, LG_PART_ALL = 15 };
+constexpr int kOffF = (int)offsetof(LgLane, f), kOffPro = (int)offsetof(LgLane, pro), kOffOld = (int)offsetof(LgLane, old),
+              kOffQ = (int)offsetof(LgLane, q);
+constexpr int kFrontTail = (int)offsetof(LgFronts, layer);  // layer[], tb[], n behind the five double arrays
+static_assert(kOffF % 32 == 0 && kOffPro % 32 == 0 && kOffOld % 32 == 0 && kOffQ % 32 == 0 && sizeof(LgLaneSlot) % 32 == 0, "LgLane layout");
+static_assert(offsetof(LgFronts, depth) == 0 && offsetof(LgFronts, theta) == 128 && offsetof(LgFronts, psi) == 256 && offsetof(LgFronts, K) == 384 &&
+                  offsetof(LgFronts, dzdt) == 512 && kFrontTail == 640 && kOffPro - kOffF - kFrontTail == 64 && LGAR_W == 16,
+              "LgFronts layout");
+static_assert(offsetof(LgOld, theta) == 128 && offsetof(LgOld, psi) == 256 && offsetof(LgOld, n) == 384 && kOffQ - kOffOld == 416, "LgOld layout");
+static_assert(offsetof(LgLane, nold_stored) < 32, "front counts must sit in the first sector of the record");
+
+template <int PARTS>
+__device__ __forceinline__ void lane_load(LgLaneSlot* S, const LgLaneSlot* G) {
+  char* l = reinterpret_cast<char*>(S);
+  const char* g = reinterpret_cast<const char*>(G);
+  ctx_load<32>(S, G);  // first sector: stage, hour, column, class, front counts
+  const int cf = (S->L.nf_stored + 3) >> 2, co = (S->L.nold_stored + 3) >> 2;
+  if (PARTS & LG_PART_STATE) {
+    ctx_load<kOffF - 32>(reinterpret_cast<LgLaneSlot*>(l + 32), reinterpret_cast<const LgLaneSlot*>(g + 32));
+#pragma unroll
+    for (int a = 0; a < 5; a++) ctx_load_n(l + kOffF + 128 * a, g + kOffF + 128 * a, cf);
+    ctx_load<64>(reinterpret_cast<LgLaneSlot*>(l + kOffF + kFrontTail), reinterpret_cast<const LgLaneSlot*>(g + kOffF + kFrontTail));
+  }
+  if (PARTS & LG_PART_STEP) ctx_load<kOffOld - kOffPro>(reinterpret_cast<LgLaneSlot*>(l + kOffPro), reinterpret_cast<const LgLaneSlot*>(g + kOffPro));
+  if (PARTS & LG_PART_OLD) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) ctx_load_n(l + kOffOld + 128 * a, g + kOffOld + 128 * a, co);
+    ctx_load<32>(reinterpret_cast<LgLaneSlot*>(l + kOffOld + 384), reinterpret_cast<const LgLaneSlot*>(g + kOffOld + 384));
+  }
+  if (PARTS & LG_PART_SEARCH)
+    ctx_load<(int)sizeof(LgLaneSlot) - kOffQ>(reinterpret_cast<LgLaneSlot*>(l + kOffQ), reinterpret_cast<const LgLaneSlot*>(g + kOffQ));
+#ifdef LGAR_POISON  // validation build: whatever was not moved must never be read
+  if (PARTS & LG_PART_STATE)
+    for (int i = 4 * cf; i < LGAR_W; i++) S->L.f.depth[i] = S->L.f.theta[i] = S->L.f.psi[i] = S->L.f.K[i] = S->L.f.dzdt[i] = LG_NAN;
+  if (PARTS & LG_PART_OLD)
+    for (int i = 4 * co; i < LGAR_W; i++) S->L.old.depth[i] = S->L.old.theta[i] = S->L.old.psi[i] = LG_NAN;
+#endif
+}
+template <int PARTS>
+__device__ __forceinline__ void lane_store(LgLaneSlot* G, LgLaneSlot* S) {
+  const char* l = reinterpret_cast<const char*>(S);
+  char* g = reinterpret_cast<char*>(G);
+  if (PARTS & LG_PART_STATE) S->L.nf_stored = S->L.f.n;
+  if (PARTS & LG_PART_OLD) S->L.nold_stored = S->L.old.n;
+  const int cf = (S->L.nf_stored + 3) >> 2, co = (S->L.nold_stored + 3) >> 2;
+  ctx_store<32>(G, S);
+  if (PARTS & LG_PART_STATE) {
+    ctx_store<kOffF - 32>(reinterpret_cast<LgLaneSlot*>(g + 32), reinterpret_cast<const LgLaneSlot*>(l + 32));
+#pragma unroll
+    for (int a = 0; a < 5; a++) ctx_store_n(g + kOffF + 128 * a, l + kOffF + 128 * a, cf);
+    ctx_store<64>(reinterpret_cast<LgLaneSlot*>(g + kOffF + kFrontTail), reinterpret_cast<const LgLaneSlot*>(l + kOffF + kFrontTail));
+  }
+  if (PARTS & LG_PART_STEP) ctx_store<kOffOld - kOffPro>(reinterpret_cast<LgLaneSlot*>(g + kOffPro), reinterpret_cast<const LgLaneSlot*>(l + kOffPro));
+  if (PARTS & LG_PART_OLD) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) ctx_store_n(g + kOffOld + 128 * a, l + kOffOld + 128 * a, co);
+    ctx_store<32>(reinterpret_cast<LgLaneSlot*>(g + kOffOld + 384), reinterpret_cast<const LgLaneSlot*>(l + kOffOld + 384));
+  }
+  if (PARTS & LG_PART_SEARCH)
+    ctx_store<(int)sizeof(LgLaneSlot) - kOffQ>(reinterpret_cast<LgLaneSlot*>(g + kOffQ), reinterpret_cast<const LgLaneSlot*>(l + kOffQ));
+}
 
 // Resident blocks per SM the compiler must leave room for, per stage (0 = no constraint).  The stages are bound by
 // memory latency, so occupancy pays more than a few extra registers; values picked from the sweep in
@@ -360,14 +439,19 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
       if (valid) {  // the correction record and the front list travel
         LgLane& G = slots[slot].L;
         LgCorr k = G.k;
-        // bounded unrolling: a plain struct copy keeps all 680 bytes in flight in registers (231 registers/thread)
+        // the correction search reads depth/theta/layer/to_bottom of the live fronts and rewrites theta and psi
         struct alignas(32) FrontsBuf { LgFronts f; } fb;
-        static_assert(sizeof(FrontsBuf) <= offsetof(LgLane, pro) - offsetof(LgLane, f), "front list copy must stay inside the record");
-        ctx_load<(int)sizeof(FrontsBuf)>(&fb, reinterpret_cast<const FrontsBuf*>(&G.f));
+        char* l = reinterpret_cast<char*>(&fb);
+        char* g = reinterpret_cast<char*>(&G.f);
+        ctx_load<64>(reinterpret_cast<FrontsBuf*>(l + kFrontTail), reinterpret_cast<const FrontsBuf*>(g + kFrontTail));
+        const int cf = (fb.f.n + 3) >> 2;
+#pragma unroll
+        for (int a = 0; a < 3; a++) ctx_load_n(l + 128 * a, g + 128 * a, cf);
         const LgarColumnClass* cls = G.cls;
         for (int it = 0; it < quantum && !k.done; it++) lg_corr_iter(k, fb.f, *cls);
         G.k = k;
-        ctx_store<(int)sizeof(FrontsBuf)>(reinterpret_cast<FrontsBuf*>(&G.f), &fb);
+#pragma unroll
+        for (int a = 1; a < 3; a++) ctx_store_n(g + 128 * a, l + 128 * a, cf);
         next = k.done ? LG_ST_TAIL : LG_ST_CORR;
       }
     } else if (STAGE == LG_ST_FETCH) {
@@ -380,7 +464,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
       LgLaneSlot S;
       LgLane& L = S.L;
       if (STAGE == LG_ST_HEAD) {  // HEAD starts the step context behind the resident column state
-        ctx_load<kStateBytes>(&S, &slots[slot]);
+        lane_load<LG_PART_STATE>(&S, &slots[slot]);
         lg_stage_head(cfg, d, w, L, fsp);
         active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
         // every new step goes straight into its front loop: saves one context round trip per step
@@ -389,9 +473,9 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         // TAIL works on everything up to and including the correction record; FRONT needs state_previous
         // and the search record as well
         if (STAGE == LG_ST_TAIL)
-          ctx_load<kTailBytes>(&S, &slots[slot]);
+          lane_load<LG_PART_STATE | LG_PART_STEP>(&S, &slots[slot]);
         else
-          ctx_load<(int)sizeof(LgLaneSlot)>(&S, &slots[slot]);
+          lane_load<LG_PART_ALL>(&S, &slots[slot]);
         L.c.cfg = &cfg;
         L.c.cls = L.cls;
         L.c.f = &L.f;
@@ -402,13 +486,13 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
       }
       next = L.stage;
       if (next == LG_ST_FETCH) {
-        ctx_store<kStateBytes>(&slots[slot], &S);  // the step is over: only the column state lives on
+        lane_store<LG_PART_STATE>(&slots[slot], &S);  // the step is over: only the column state lives on
       } else if (STAGE == LG_ST_TAIL && next == LG_ST_CORR) {
-        ctx_store<kTailBytes>(&slots[slot], &S);  // TAIL -> CORR -> TAIL: neither state_previous nor the psi search is live
+        lane_store<LG_PART_STATE | LG_PART_STEP>(&slots[slot], &S);  // TAIL -> CORR -> TAIL: neither state_previous nor the psi search is live
       } else if (next == LG_ST_TAIL) {
-        ctx_store<kTailBytes>(&slots[slot], &S);  // the front loop is over
+        lane_store<LG_PART_STATE | LG_PART_STEP>(&slots[slot], &S);  // the front loop is over
       } else {
-        ctx_store<(int)sizeof(LgLaneSlot)>(&slots[slot], &S);
+        lane_store<LG_PART_ALL>(&slots[slot], &S);
       }
     }
 #pragma unroll
@@ -445,7 +529,7 @@ __global__ void __launch_bounds__(128) lgar_wave_finish_kernel(const __grid_cons
     }
     if (slot < 0) continue;
     LgLaneSlot S;
-    ctx_load<(int)sizeof(LgLaneSlot)>(&S, &slots[slot]);
+    lane_load<LG_PART_ALL>(&S, &slots[slot]);
     LgLane& L = S.L;
     L.stage = stage;  // the queue a slot sits in is authoritative: the partial-context stages do not rewrite L.stage
     L.c.cfg = &cfg;
@@ -501,6 +585,8 @@ __global__ void lgar_wave_init_kernel(const __grid_constant__ LgarConfig cfg, co
     // for the whole window; with fewer slots than columns, slots draw columns from a counter in FETCH instead
     L.col = slot_is_column ? i : -1;
     L.t = 0;
+    L.nf_stored = 0;
+    L.nold_stored = 0;
     L.resume = false;
     L.tr_iters = 0;
     L.tr_kcyc = 0;

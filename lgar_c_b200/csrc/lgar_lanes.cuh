@@ -51,6 +51,7 @@ struct LgLane {
   int t;
   int64_t col;
   const LgarColumnClass* cls;
+  int nf_stored, nold_stored;  // front counts the record was last stored with: only that prefix of the arrays is moved
   LgCtx c;
   alignas(16) LgScalars s;
   LgEpi ep;
@@ -73,7 +74,7 @@ struct LgLane {
   unsigned int tr_iters, tr_kcyc;  // work trace of the current column (debug)
   alignas(16) LgCorr k;   // TAIL/CORR stop copying after this
   alignas(32) LgOld old;  // FRONT only
-  alignas(16) LgSearch q; // FRONT/SEARCH only
+  alignas(32) LgSearch q; // FRONT/SEARCH only
 };
 
 // column state: SoA arrays <-> lane record
@@ -82,6 +83,8 @@ LG_FN_NOINLINE void lg_lane_import(const LgarConfig& cfg, const LgarDeviceState&
   load_scalars(d, col, L.s);
   load_fronts(d, col, L.f);
   lg_epi_load(cfg, d, col, L.ep);
+  L.nf_stored = L.f.n;
+  L.nold_stored = 0;
 }
 LG_FN_NOINLINE void lg_lane_export(const LgarConfig& cfg, const LgarDeviceState& d, int64_t col, const LgLane& L) {
   store_scalars(d, col, L.s, true);
