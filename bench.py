@@ -250,7 +250,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--finish-below", type=int, default=-1, help="wavefront: slots in flight below which the finishing kernel takes over (-1: engine default)")
-    ap.add_argument("--mode", type=int, default=3, help="3 wavefront kernels, 2 lanes kernel, 1 warp-tile window kernel, 0 one kernel pair per forcing hour")
+    ap.add_argument("--mode", type=int, default=3, help="4 step kernel + parked searches, 3 wavefront kernels, 2 lanes kernel, 1 warp-tile window kernel, 0 one kernel pair per forcing hour")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -352,7 +352,7 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(ext)
-    if args.mode == 3:
+    if args.mode >= 3:
         # one call for the whole timed region: columns run ahead of each other across day boundaries
         b.update_steps_device(H * args.steps, dP.data_ptr(), dE.data_ptr(), ncol)
         blk += args.steps
@@ -441,7 +441,7 @@ def main():
     B_nofront = B_full - 2 * 44 * mean_fronts
     ms_s, ms_a, ms_w = prof["ms_stream"], prof["ms_active"], prof["ms_window"]
     if ms_w > 0:  # window mode: one kernel per bench step (H forcing hours for every column)
-        dominant = {3: "lgar_wave_kernel<*> (5 stage kernels)", 2: "lgar_lanes_kernel", 1: "lgar_window_kernel"}[args.mode]
+        dominant = {4: "lgar_wave_run_kernel (+ FETCH/SEARCH/CORR stage kernels)", 3: "lgar_wave_kernel<*> (5 stage kernels)", 2: "lgar_lanes_kernel", 1: "lgar_window_kernel"}[args.mode]
         units = ncol * H
         B_unit = B_full
         dur_s = ms_w * 1e-3 / args.steps  # per bench step (one day of every column); mode 3 runs all steps in one call

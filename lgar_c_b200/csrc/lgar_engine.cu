@@ -87,11 +87,14 @@ struct lgarb_engine {
   bool wave_ready = false;
   int wave_quantum = 64, wave_pairs = 4, wave_corr_pairs = 1;
   int wave_finish_below = 16384;
+  int finish_lane_stride = 4;  // finishing kernel: one slot per this many lanes
   int wave_windows = 0;  // windows run so far (profiling range selection)
   int wave_escalate_below = 8192;
   int wave_corr_quantum = 64;  // correction-search trips per launch (scaled with the psi-search quantum when that escalates)
   int64_t wave_max_slots = 16777216;  // 2.8 KB of context per slot
   int64_t wave_rounds = 0;
+  // step kernel (mode 4)
+  int run_inline_quantum = 16, run_inline_corr_quantum = 16, run_search_quantum = 128, run_corr_quantum = 64, run_pairs = 1, run_keep = 8;
   int32_t* d_tile_counter = nullptr;
   cudaEvent_t win_ev[2] = {nullptr, nullptr};
   double prof_ms_window = 0;
@@ -476,8 +479,16 @@ int lgarb_create(lgarb_engine** out) {
   knob("LGARB_WAVE_PAIRS", (*out)->wave_pairs);
   knob("LGARB_WAVE_CORR_PAIRS", (*out)->wave_corr_pairs);
   knob("LGARB_WAVE_FINISH_BELOW", (*out)->wave_finish_below);
+  knob("LGARB_FINISH_LANE_STRIDE", (*out)->finish_lane_stride);
   knob("LGARB_WAVE_ESCALATE_BELOW", (*out)->wave_escalate_below);
   knob("LGARB_WAVE_CORR_QUANTUM", (*out)->wave_corr_quantum);
+  knob("LGARB_RUN_QUANTUM", (*out)->run_inline_quantum);
+  knob("LGARB_RUN_CORR_QUANTUM", (*out)->run_inline_corr_quantum);
+  knob("LGARB_RUN_SEARCH_QUANTUM", (*out)->run_search_quantum);
+  knob("LGARB_RUN_PAIRS", (*out)->run_pairs);
+  knob("LGARB_RUN_KEEP", (*out)->run_keep);
+  knob("LGARB_RUN_BIG_CORR_QUANTUM", (*out)->run_corr_quantum);
+  knob("LGARB_WINDOW_MODE", (*out)->use_window);
   return LGARB_SUCCESS;
 }
 
@@ -575,6 +586,37 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
                                     e->stream));
     e->launches += 2;
   };
+  auto launch_q = [&](int stage, int q) {  // SEARCH / CORR with an explicit quantum
+    const int consume = par[stage];
+    par[stage] ^= 1;
+    unsigned mask = 0;
+    for (int s = 0; s < LGAR_NSTAGE; s++) mask |= (unsigned)par[s] << s;
+    if (dbg_on) {
+      dbg_evs.emplace_back();
+      cudaEventCreate(&dbg_evs.back().first);
+      cudaEventRecord(dbg_evs.back().first, e->stream);
+      dbg_evs.back().second = stage;
+    }
+    CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, q, in_flight, e->stream));
+    e->launches += 2;
+  };
+  auto launch_run = [&](int q, int qc) {  // the step kernel consumes the HEAD, FRONT and TAIL queues
+    unsigned consume_mask = 0;
+    for (int s : {LG_ST_HEAD, LG_ST_FRONT, LG_ST_TAIL}) {
+      consume_mask |= (unsigned)par[s] << s;
+      par[s] ^= 1;
+    }
+    unsigned mask = 0;
+    for (int s = 0; s < LGAR_NSTAGE; s++) mask |= (unsigned)par[s] << s;
+    if (dbg_on) {
+      dbg_evs.emplace_back();
+      cudaEventCreate(&dbg_evs.back().first);
+      cudaEventRecord(dbg_evs.back().first, e->stream);
+      dbg_evs.back().second = LG_ST_HEAD;  // booked under HEAD in the debug line
+    }
+    CUDA_TRY(lgar_launch_wave_run(e->cfg, e->d, w, wv, consume_mask, mask, q, qc, e->run_keep, in_flight, e->stream));
+    e->launches += 2;
+  };
   int32_t* h_cnt = (int32_t*)e->pinned(64 * sizeof(int32_t));
   const bool debug = getenv("LGARB_WAVE_DEBUG") != nullptr;
   cudaEvent_t dbg[2];
@@ -597,9 +639,16 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       }
       if (in_flight == 0) break;
       if (in_flight <= e->wave_finish_below) {  // the stragglers: one thread per slot runs its column to the end of the window
-        CUDA_TRY(lgar_launch_wave_finish(e->cfg, e->d, w, wv, in_flight, e->stream));
+        if (debug) cudaEventRecord(dbg[0], e->stream);
+        CUDA_TRY(lgar_launch_wave_finish(e->cfg, e->d, w, wv, in_flight, e->finish_lane_stride, e->stream));
         e->launches += 2;
-        if (debug) fprintf(stderr, "[wave] round %lld: finishing kernel for %d slots in flight\n", (long long)round, in_flight);
+        if (debug) {
+          cudaEventRecord(dbg[1], e->stream);
+          cudaEventSynchronize(dbg[1]);
+          float ms = 0;
+          cudaEventElapsedTime(&ms, dbg[0], dbg[1]);
+          fprintf(stderr, "[wave] round %lld: finishing kernel for %d slots in flight: %.3f ms\n", (long long)round, in_flight, ms);
+        }
         break;
       }
       if (round > 100000000) throw std::runtime_error("wavefront scheduler did not terminate");
@@ -614,21 +663,34 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       cudaProfilerStart();
     }
     const bool new_steps = cnt[LG_ST_FETCH] + cnt[LG_ST_HEAD] > 0;
-    if (new_steps) {
+    if (e->use_window == 4) {
+      // step kernel: FETCH, RUN (whole steps, searches inline up to the quantum), then the parked long searches
+      // (compacted, `run_search_quantum` trips per launch) and the steps they hand back
+      const int qbig = std::max(1, (int)((int64_t)e->run_search_quantum * quantum / e->wave_quantum));
+      if (cnt[LG_ST_FETCH] > 0) launch(LG_ST_FETCH);
+      launch_run(e->run_inline_quantum, e->run_inline_corr_quantum);
+      for (int k = 0; k < e->run_pairs; k++) {
+        launch_q(LG_ST_SEARCH, qbig);
+        launch_q(LG_ST_CORR, std::max(1, (int)((int64_t)e->run_corr_quantum * quantum / e->wave_quantum)));
+        launch_run(e->run_inline_quantum, e->run_inline_corr_quantum);
+      }
+    } else if (new_steps) {
       launch(LG_ST_FETCH);
       launch(LG_ST_HEAD);  // runs the first stretch of the front loop too
     }
-    if (new_steps || cnt[LG_ST_FRONT] + cnt[LG_ST_SEARCH] > 0) {
+    if (e->use_window != 4 && (new_steps || cnt[LG_ST_FRONT] + cnt[LG_ST_SEARCH] > 0)) {
       if (cnt[LG_ST_FRONT] > 0) launch(LG_ST_FRONT);
       for (int k = 0; k < e->wave_pairs; k++) {
         launch(LG_ST_SEARCH);
         launch(LG_ST_FRONT);
       }
     }
-    launch(LG_ST_TAIL);
-    for (int k = 0; k < e->wave_corr_pairs; k++) {
-      launch(LG_ST_CORR);
+    if (e->use_window != 4) {
       launch(LG_ST_TAIL);
+      for (int k = 0; k < e->wave_corr_pairs; k++) {
+        launch(LG_ST_CORR);
+        launch(LG_ST_TAIL);
+      }
     }
     e->wave_rounds++;
     if (round == ncu_round) {
@@ -706,7 +768,7 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
           }
           CUDA_TRY(cudaEventRecord(e->win_ev[0], e->stream));
         }
-        if (e->use_window == 3)
+        if (e->use_window >= 3)
           run_wave_window(e, w);
         else
           CUDA_TRY(lgar_launch_window(e->cfg, e->d, w, e->use_window == 2 ? e->lanes_blocks : e->window_blocks, e->stream, e->use_window));
@@ -1001,7 +1063,7 @@ int lgarb_get_warp_times(lgarb_engine* e, uint32_t* out16384) {
     d2h(e, out16384, e->d_work_trace + 2 * e->stride + 64, 2 * 8192 * sizeof(uint32_t));
   });
 }
-int lgarb_set_window_mode(lgarb_engine* e, int mode) { LGARB_GUARD(e, e->use_window = (mode < 0 || mode > 3) ? 3 : mode); }
+int lgarb_set_window_mode(lgarb_engine* e, int mode) { LGARB_GUARD(e, e->use_window = (mode < 0 || mode > 4) ? 3 : mode); }
 int lgarb_set_wave_params(lgarb_engine* e, int search_quantum, int front_search_pairs, int finish_below) {
   LGARB_GUARD(e, {
     if (search_quantum > 0) e->wave_quantum = search_quantum;

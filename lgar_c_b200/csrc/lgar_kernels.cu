@@ -504,19 +504,195 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
   }
 }
 
+// ---- step kernel (mode 4) ----------------------------------------------------------------------------
+// The stage kernels above move a context of 1.2-1.7 KB between HBM and the SM at every stage boundary (about
+// 11 KB per active column-step, plus the same again through thread-private memory) and a step crosses ~13
+// kernel boundaries, so a round never takes less than ~1.6 ms however few slots are left (ncu, round 1 of a
+// bench window: HEAD/FRONT/TAIL are 70 % of the round at 5-20 % issue utilisation).  Here a thread keeps its
+// slot for as much of the step as the psi searches allow: it takes a slot from the HEAD queue (new step), the
+// FRONT queue (a parked search has finished) or the TAIL queue (a parked correction search has finished),
+// loads what that entry point needs and runs the staged program of lgar_lanes.cuh to the end of the step.
+// The warp executes ONE stage at a time for the lanes that are in it (vote below): everything that is not a
+// search first, so that lanes meet again in the search loop; the searches then iterate converged for at most
+// `quantum` trips.  A lane whose search is not finished by then -- the heavy tail: mean 41 trips, max > 10^4 --
+// parks its context in HBM and queues for the SEARCH / CORR kernels, which iterate compacted and converged
+// with a large quantum and hand the slot back through the FRONT / TAIL queue.  A step that never exceeds the
+// quantum (the common case) costs one state read and one state write.
+#ifndef LGAR_RUN_THREADS
+#define LGAR_RUN_THREADS 256
+#endif
+#ifndef LGAR_MB_RUN
+#define LGAR_MB_RUN 0
+#endif
+#ifndef LGAR_RUN_BLOCKSYNC
+#define LGAR_RUN_BLOCKSYNC 1
+#endif
+__global__ void __launch_bounds__(LGAR_RUN_THREADS, LGAR_MB_RUN) lgar_wave_run_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv,
+                                                                                      unsigned consume_mask, unsigned append_mask, int quantum, int corr_quantum, int keep) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int cH = (consume_mask >> LG_ST_HEAD) & 1, cF = (consume_mask >> LG_ST_FRONT) & 1, cT = (consume_mask >> LG_ST_TAIL) & 1;
+  const int nH = wv.qcount[LG_ST_HEAD * 2 + cH], nF = wv.qcount[LG_ST_FRONT * 2 + cF], nT = wv.qcount[LG_ST_TAIL * 2 + cT];
+  // every queue starts on a warp boundary: the lanes of a warp enter at the same point of the program
+  const int eH = (nH + 31) & ~31, eF = (nF + 31) & ~31, eT = (nT + 31) & ~31;
+  const int total = eH + eF + eT;
+  LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
+  unsigned long long front_sum = 0, active_sum = 0;
+  unsigned long long* fsp = w.prof ? &front_sum : nullptr;
+#if LGAR_RUN_BLOCKSYNC
+  // block-wide vote (one barrier per turn): every warp of the block runs the same stage at the same time, so the
+  // SM fetches one stage's code at a time (ncu on the warp-level vote: 57 % of the stall cycles were
+  // instruction fetch, 20 warps per SM each somewhere else in 300 KB of SASS)
+  __shared__ unsigned s_present[2][LGAR_RUN_THREADS / 32];
+  int vote_buf = 0;
+  const int btotal = (total + LGAR_RUN_THREADS - 1) / LGAR_RUN_THREADS * LGAR_RUN_THREADS;
+#else
+  const int btotal = total;
+#endif
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < btotal; i += gridDim.x * blockDim.x) {
+    int entry, j;
+    if (i < eH) {
+      entry = LG_ST_HEAD; j = i;
+    } else if (i < eH + eF) {
+      entry = LG_ST_FRONT; j = i - eH;
+    } else {
+      entry = LG_ST_TAIL; j = i - eH - eF;
+    }
+    const int nq = entry == LG_ST_HEAD ? nH : entry == LG_ST_FRONT ? nF : nT;
+    const bool valid = j < nq;
+    const int slot = valid ? wv.queue[entry][entry == LG_ST_HEAD ? cH : entry == LG_ST_FRONT ? cF : cT][j] : 0;
+    LgLaneSlot S;
+    LgLane& L = S.L;
+    int st = LG_ST_DONE;   // DONE = this lane has nothing (more) to run in this pass
+    if (valid) {
+      if (entry == LG_ST_HEAD)
+        lane_load<LG_PART_STATE>(&S, &slots[slot]);
+      else if (entry == LG_ST_FRONT)
+        lane_load<LG_PART_ALL>(&S, &slots[slot]);
+      else
+        lane_load<LG_PART_STATE | LG_PART_STEP>(&S, &slots[slot]);
+      L.c.cfg = &cfg;
+      L.c.cls = L.cls;
+      L.c.f = &L.f;
+      st = entry;
+    }
+    int next = -1;
+    for (;;) {
+      const unsigned m_head = __ballot_sync(FULL, st == LG_ST_HEAD);
+      const unsigned m_front = __ballot_sync(FULL, st == LG_ST_FRONT);
+      const unsigned m_search = __ballot_sync(FULL, st == LG_ST_SEARCH);
+      const unsigned m_tail = __ballot_sync(FULL, st == LG_ST_TAIL);
+      const unsigned m_corr = __ballot_sync(FULL, st == LG_ST_CORR);
+#if LGAR_RUN_BLOCKSYNC
+      if ((threadIdx.x & 31) == 0)
+        s_present[vote_buf][threadIdx.x >> 5] = (m_head ? 1u : 0u) | (m_front ? 2u : 0u) | (m_search ? 4u : 0u) | (m_tail ? 8u : 0u) | (m_corr ? 16u : 0u);
+      __syncthreads();
+      unsigned present = 0;
+#pragma unroll
+      for (int wi = 0; wi < LGAR_RUN_THREADS / 32; wi++) present |= s_present[vote_buf][wi];
+      vote_buf ^= 1;
+      if (!present) break;
+      const int chosen = (present & 1u) ? LG_ST_HEAD : (present & 2u) ? LG_ST_FRONT : (present & 4u) ? LG_ST_SEARCH : (present & 8u) ? LG_ST_TAIL : LG_ST_CORR;
+#else
+      if (!(m_head | m_front | m_search | m_tail | m_corr)) break;
+      const int chosen = m_head ? LG_ST_HEAD : m_front ? LG_ST_FRONT : m_search ? LG_ST_SEARCH : m_tail ? LG_ST_TAIL : LG_ST_CORR;
+#endif
+      if (chosen == LG_ST_HEAD) {
+        if (st == LG_ST_HEAD) {
+          lg_stage_head(cfg, d, w, L, fsp);
+          active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
+          st = L.stage;
+          if (st == LG_ST_FETCH) { next = LG_ST_FETCH; st = LG_ST_DONE; }
+        }
+      } else if (chosen == LG_ST_FRONT) {
+        if (st == LG_ST_FRONT) {
+          lg_stage_front(L);
+          st = L.stage;
+        }
+      } else if (chosen == LG_ST_SEARCH) {
+        if (st == LG_ST_SEARCH) {
+          for (int it = 0; it < quantum; it++) {
+            if (!L.q.done) lg_search_iter(L.q, *L.cls);
+            if (__popc(__ballot_sync(m_search, !L.q.done)) < keep) break;
+          }
+          if (L.q.done) {
+            L.resume = true;
+            st = LG_ST_FRONT;
+          } else {
+            next = LG_ST_SEARCH;   // park: the SEARCH kernel continues this search
+            st = LG_ST_DONE;
+          }
+        }
+      } else if (chosen == LG_ST_TAIL) {
+        if (st == LG_ST_TAIL) {
+          lg_stage_tail(cfg, d, w, L, fsp);
+          st = L.stage;
+          if (st == LG_ST_FETCH) { next = LG_ST_FETCH; st = LG_ST_DONE; }
+        }
+      } else {
+        if (st == LG_ST_CORR) {
+          for (int it = 0; it < corr_quantum; it++) {
+            if (!L.k.done) lg_corr_iter(L.k, L.f, *L.cls);
+            if (__popc(__ballot_sync(m_corr, !L.k.done)) < keep) break;
+          }
+          if (L.k.done) {
+            st = LG_ST_TAIL;
+          } else {
+            next = LG_ST_CORR;   // park: the CORR kernel continues
+            st = LG_ST_DONE;
+          }
+        }
+      }
+    }
+    if (valid) {
+      if (next == LG_ST_FETCH)
+        lane_store<LG_PART_STATE>(&slots[slot], &S);   // the step is over: only the column state lives on
+      else if (next == LG_ST_CORR)
+        lane_store<LG_PART_STATE | LG_PART_STEP>(&slots[slot], &S);
+      else
+        lane_store<LG_PART_ALL>(&slots[slot], &S);
+    }
+    wave_push(wv, append_mask, LG_ST_FETCH, valid && next == LG_ST_FETCH, slot);
+    wave_push(wv, append_mask, LG_ST_SEARCH, valid && next == LG_ST_SEARCH, slot);
+    wave_push(wv, append_mask, LG_ST_CORR, valid && next == LG_ST_CORR, slot);
+  }
+  if (w.prof) {
+    if (front_sum) atomicAdd(w.prof, front_sum);
+    if (active_sum) atomicAdd(w.prof + 1, active_sum);
+  }
+}
+
+__global__ void lgar_wave_reset3_kernel(int32_t* a, int32_t* b, int32_t* c) { *a = 0; *b = 0; *c = 0; }
+
+cudaError_t lgar_launch_wave_run(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, unsigned consume_mask,
+                                 unsigned append_mask, int quantum, int corr_quantum, int keep, int max_items, cudaStream_t stream) {
+  const int items = std::min(wv.nslots, max_items) + 96;  // three queues, each padded to a warp
+  const int blocks = std::max(1, std::min((items + LGAR_RUN_THREADS - 1) / LGAR_RUN_THREADS, 148 * 16));
+  lgar_wave_run_kernel<<<blocks, LGAR_RUN_THREADS, 0, stream>>>(cfg, d, w, wv, consume_mask, append_mask, quantum, corr_quantum, keep);
+  lgar_wave_reset3_kernel<<<1, 1, 0, stream>>>(wv.qcount + LG_ST_HEAD * 2 + ((consume_mask >> LG_ST_HEAD) & 1),
+                                               wv.qcount + LG_ST_FRONT * 2 + ((consume_mask >> LG_ST_FRONT) & 1),
+                                               wv.qcount + LG_ST_TAIL * 2 + ((consume_mask >> LG_ST_TAIL) & 1));
+  return cudaGetLastError();
+}
+
 // Finishing kernel: when only a few slots are left in flight (the columns that are active in almost every
 // hour of the window), a round of ~13 launches costs ~2.5 ms whatever it processes.  Here every remaining
 // slot is taken by one thread which runs its column through all stages to the end of the window without
 // going back to HBM between stages: the critical path per active step drops from one round to the serial
 // execution time of the step.  Lane utilisation is poor by construction, which does not matter for the few
 // thousand slots this is used for.
-__global__ void __launch_bounds__(128) lgar_wave_finish_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv) {
+__global__ void __launch_bounds__(128) lgar_wave_finish_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int lane_stride) {
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
   int total = 0;
   for (int q = 0; q < 2 * LGAR_NSTAGE; q++) total += wv.qcount[q];
   unsigned long long front_sum = 0, active_sum = 0;
   unsigned long long* fsp = w.prof ? &front_sum : nullptr;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+  // `lane_stride` > 1: only every lane_stride-th lane of a warp takes a slot.  The lanes of a warp sit in different
+  // stages of different columns and are executed one after the other, so the time of the kernel -- the serial
+  // chain of the column with the most active hours left -- shrinks with the number of slots per warp as long as
+  // the warps still fit the machine.
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gtid % lane_stride != 0) return;
+  for (int i = gtid / lane_stride; i < total; i += gridDim.x * blockDim.x / lane_stride) {
     int j = i, slot = -1, stage = LG_ST_DONE;
     for (int q = 0; q < 2 * LGAR_NSTAGE; q++) {  // item i of the concatenation of all queues
       const int n = wv.qcount[q];
@@ -568,9 +744,10 @@ __global__ void lgar_wave_clear_kernel(LgarWave wv) {
 }
 
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
-                                    cudaStream_t stream) {
-  const int blocks = std::max(1, std::min((in_flight + 127) / 128, 148 * 16));
-  lgar_wave_finish_kernel<<<blocks, 128, 0, stream>>>(cfg, d, w, wv);
+                                    int lane_stride, cudaStream_t stream) {
+  lane_stride = std::max(1, std::min(lane_stride, 32));
+  const int blocks = std::max(1, std::min((int)(((int64_t)in_flight * lane_stride + 127) / 128), 148 * 16));
+  lgar_wave_finish_kernel<<<blocks, 128, 0, stream>>>(cfg, d, w, wv, lane_stride);
   lgar_wave_clear_kernel<<<1, 32, 0, stream>>>(wv);
   return cudaGetLastError();
 }

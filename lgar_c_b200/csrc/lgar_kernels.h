@@ -56,8 +56,11 @@ struct LgarWave {
 // one launch of the kernel of `stage`, consuming queue[stage][consume]; append_mask bit s = buffer of stage s to append to
 cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int stage, int consume,
                                    unsigned append_mask, int quantum, int max_items, cudaStream_t stream);
+// mode 4: one launch of the step kernel, consuming queue[s][(consume_mask >> s) & 1] for s = HEAD, FRONT, TAIL
+cudaError_t lgar_launch_wave_run(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, unsigned consume_mask,
+                                 unsigned append_mask, int quantum, int corr_quantum, int keep, int max_items, cudaStream_t stream);
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
-                                    cudaStream_t stream);
+                                    int lane_stride, cudaStream_t stream);
 cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWave& wv, int slot_is_column, cudaStream_t stream);
 size_t lgar_lane_context_bytes();
 // mode 1: warp-tile window kernel; mode 2: per-lane staged program (lgar_lanes.cuh)

@@ -80,7 +80,7 @@ def test_scheduling_does_not_change_results(cuda_device, tmp_path):
     P[10:14] = np.maximum(P[10:14], 8.0)     # a storm on every column: the whole batch active at once
     dP, dE = torch.from_numpy(P).cuda(), torch.from_numpy(E).cuda()
     res = []
-    for mode, wave in ((3, None), (3, (4, 1, 0)), (3, (64, 4, 150_000)), (1, None)):
+    for mode, wave in ((3, None), (4, None), (4, (64, 4, 150_000)), (3, (4, 1, 0)), (3, (64, 4, 150_000)), (1, None)):
         b = lgar_c_b200.BmiLGARBatch()
         b.initialize(cfg, ncol, 0, soils, layers)
         b.set_window_mode(mode)
