@@ -562,6 +562,8 @@ LG_FN_NOINLINE bool lg_move_end(LgLane& L) {
   LgCtx& c = L.c;
   LgFronts& f = L.f;
   const LgarColumnClass& cls = *L.cls;
+  const unsigned lanes_here = LG_LANES_HERE();
+  bool need_search = false;
   if (L.me_phase == 0) {
     L.me_correction = lg_correction_type(c);
     L.me_phase = 1;
@@ -591,23 +593,29 @@ LG_FN_NOINLINE bool lg_move_end(LgLane& L) {
       }
     }
     if (L.me_phase == 2) {
-      if (lg_fix_run(L)) return true;
+      if (lg_fix_run(L)) {
+        need_search = true;  // leave through the common exit: see LG_RECONVERGE
+        break;
+      }
       L.AET = L.AET - L.fx_mass_change;
       L.me_phase = 1;
     }
     L.me_correction = lg_correction_type(c);
   }
-  for (int i = 0; i < f.n; i++) {
-    const LgarLayer& sk = cls.lay[f.layer[i]];
-    double Se = lg_Se_from_theta(f.theta[i], sk);
-    if (f.psi[i] > 1.0) f.psi[i] = lg_h_from_Se(Se, sk);
-    f.K[i] = lg_K_from_Se(Se, sk);
+  LG_RECONVERGE(lanes_here);  // the few lanes that had corrections to make rejoin the others for the refresh
+  if (!need_search) {
+    for (int i = 0; i < f.n; i++) {
+      const LgarLayer& sk = cls.lay[f.layer[i]];
+      double Se = lg_Se_from_theta(f.theta[i], sk);
+      if (f.psi[i] > 1.0) f.psi[i] = lg_h_from_Se(Se, sk);
+      f.K[i] = lg_K_from_Se(Se, sk);
+    }
+    if (f.n == 1) {
+      if (f.depth[0] != cls.cum[1]) f.depth[0] = cls.cum[1];
+    }
+    L.me_phase = 3;  // done
   }
-  if (f.n == 1) {
-    if (f.depth[0] != cls.cum[1]) f.depth[0] = cls.cum[1];
-  }
-  L.me_phase = 3;  // done
-  return false;
+  return need_search;
 }
 
 // ---- lg_step_active as cycle_begin / cycle_end ------------------------------------------------------

@@ -22,10 +22,18 @@
 #include <cmath>
 #define LG_FN static inline
 #define LG_FN_NOINLINE static
+#define LG_LANES_HERE() 0u
+#define LG_RECONVERGE(m) ((void)(m))
 using std::exp; using std::fabs; using std::fmax; using std::fmin; using std::isinf; using std::isnan; using std::log; using std::sqrt;
 #else
 #define LG_FN __device__ __forceinline__
 #define LG_FN_NOINLINE __device__ __noinline__
+// Lanes that entered a function together meet again at LG_RECONVERGE before the expensive common part.  Without it
+// a function with an early exit in a divergent loop runs its common tail once per group of lanes (ncu source
+// view of the TAIL kernel: the K/psi refresh of lg_move_end ran at 17 of 32 lanes before its own loop divergence).
+// Every lane of LG_LANES_HERE() must reach the LG_RECONVERGE: no return in between.
+#define LG_LANES_HERE() __activemask()
+#define LG_RECONVERGE(m) __syncwarp(m)
 #endif
 
 // reference src/lgar.cxx:63-70
@@ -240,16 +248,13 @@ LG_FN_NOINLINE double lg_mass_bal(const LgCtx& c) {
   const LgFronts& f = *c.f;
   const double* cum = c.cls->cum;
   double sum = 0.0;
+  // one expression for the three cases of the reference (x - 0.0 == x and a*b == b*a exactly): no branch in the loop
+  // body, so the lanes of a warp stay together
   for (int i = 0; i < f.n; i++) {
-    double base = cum[f.layer[i] - 1];
-    if (i + 1 < f.n) {
-      if (f.layer[i + 1] == f.layer[i])
-        sum += (f.depth[i] - base) * (f.theta[i] - f.theta[i + 1]);
-      else
-        sum += (f.depth[i] - base) * f.theta[i];
-    } else {
-      sum += f.theta[i] * (f.depth[i] - base);
-    }
+    const double base = cum[f.layer[i] - 1];
+    const bool same_layer_below = (i + 1 < f.n) && (f.layer[i + 1] == f.layer[i]);
+    const double theta_below = same_layer_below ? f.theta[i + 1] : 0.0;
+    sum += (f.depth[i] - base) * (f.theta[i] - theta_below);
   }
   return sum;
 }
@@ -1010,6 +1015,14 @@ LG_FN_NOINLINE void lg_dzdt_calc(LgCtx& c, double h_p, double subtimestep_h, boo
   const double* cum = cls.cum;
   int count_correct_for_crossing = 0;
   for (int i = 0; i < f.n; i++) {
+    // Only the fronts that are not to-bottom (about one in four) need the Green-Ampt evaluation below.  The cheap
+    // cases are skipped in this inner loop, so that the k-th trip of the outer loop is the k-th MOVING front of
+    // every lane, whatever its index: the lanes of a warp run the expensive part together (it ran at 6.5 of 32
+    // lanes when the trips were aligned by front index).  Same visits in the same order per column.
+    while (i + 1 < f.n && f.tb[i] && !(f.K[i] < 0)) {
+      f.dzdt[i] = 0.0;
+      i++;
+    }
     double dzdt = 0.0;
     const int layer_num = f.layer[i];
     const double K_cm_per_h = f.K[i];
