@@ -112,6 +112,17 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
  * copies are part of the call; it returns when the outputs are in place. */
 int lgarb_update_steps_host(lgarb_engine* e, int64_t n_steps, const double* h_precip_mm_per_h, const double* h_pet_mm_per_h,
                             int n_outputs, const char* const* output_names, double* const* h_outputs);
+/* Streamed variant (forcing / output streaming; replaces the per-step CSV reader and
+ * writer loop of src/bmi_main_lgar.cxx:116-157,183-262 for batched runs).  The series are cut into chunks of
+ * chunk_steps hours; the host-to-device copy of chunk k+1 and the device-to-host copy of the outputs of chunk k-1
+ * overlap the computation of chunk k (separate copy streams, two staging buffers each way; pinned host memory is
+ * needed for the overlap).  forcing_dtype / output_dtype: LGARB_F64 or LGARB_F32 element type of the HOST arrays
+ * (gridded forcing products are f32; the engine always computes in f64).  chunk_steps <= 0: one chunk. */
+#define LGARB_F64 0
+#define LGARB_F32 1
+int lgarb_update_steps_host_stream(lgarb_engine* e, int64_t n_steps, int64_t chunk_steps, int forcing_dtype, const void* h_precip_mm_per_h,
+                                   const void* h_pet_mm_per_h, int n_outputs, const char* const* output_names, int output_dtype,
+                                   void* const* h_outputs);
 int lgarb_synchronize(lgarb_engine* e);
 
 /* ---- variable access (BMI getters/setters) -------------------------------------------------- */

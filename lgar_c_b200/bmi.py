@@ -68,6 +68,7 @@ def _load():
         "lgarb_update_until": ([vp, C.c_double], C.c_int),
         "lgarb_update_steps_device": ([vp, i64, vp, vp, i64, vp, i64, vp], C.c_int),
         "lgarb_update_steps_host": ([vp, i64, vp, vp, C.c_int, vp, vp], C.c_int),
+        "lgarb_update_steps_host_stream": ([vp, i64, i64, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp], C.c_int),
         "lgarb_synchronize": ([vp], C.c_int),
         "lgarb_set_value": ([vp, cp, vp], C.c_int),
         "lgarb_set_value_range": ([vp, cp, i64, i64, vp], C.c_int),
@@ -208,6 +209,29 @@ class BmiLGARBatch:
         cn = (C.c_char_p * len(names))(*[n.encode() for n in names])
         cp = (C.c_void_p * len(names))(*[outputs[n].ctypes.data for n in names])
         self._ck(self._L.lgarb_update_steps_host(self._h, int(n_steps), _ptr(P), _ptr(E), len(names), cn, cp))
+        return outputs
+
+    def update_steps_host_stream(self, precip, pet, outputs=(), chunk_steps=0, output_dtype=np.float64):
+        """Streamed variant of update_steps_host (lgarb_update_steps_host_stream): the series are cut into chunks of
+        `chunk_steps` hours and the copies of neighbouring chunks overlap the computation.  precip/pet may be float64
+        or float32 host arrays [n_steps][n_columns] (both the same type); outputs as in update_steps_host, of dtype
+        `output_dtype` (float64 or float32)."""
+        P = np.ascontiguousarray(precip)
+        in32 = P.dtype == np.float32
+        P = np.ascontiguousarray(P, dtype=np.float32 if in32 else np.float64)
+        E = np.ascontiguousarray(pet, dtype=P.dtype)
+        n_steps = P.shape[0]
+        out32 = np.dtype(output_dtype) == np.float32
+        if not isinstance(outputs, dict):
+            outputs = {n: np.empty((n_steps, self.n_columns), dtype=np.float32 if out32 else np.float64) for n in outputs}
+        names = list(outputs)
+        for n in names:
+            if outputs[n].dtype != (np.float32 if out32 else np.float64) or not outputs[n].flags.c_contiguous:
+                raise LgarbError(f"output array {n}: wrong dtype or not contiguous")
+        cn = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        cp = (C.c_void_p * len(names))(*[outputs[n].ctypes.data for n in names])
+        self._ck(self._L.lgarb_update_steps_host_stream(self._h, int(n_steps), int(chunk_steps), 1 if in32 else 0, _ptr(P), _ptr(E),
+                                                        len(names), cn, 1 if out32 else 0, cp))
         return outputs
 
     def synchronize(self):

@@ -57,8 +57,12 @@ int out_index(const std::string& name) {
 
 }  // namespace
 
+struct StreamBufs;
+void free_stream_bufs(StreamBufs*);
+
 struct lgarb_engine {
   bool initialized = false;
+  StreamBufs* sbufs = nullptr;  // staging of lgarb_update_steps_host_stream, kept between calls
   int device = 0;
   int64_t ncol = 0, stride = 0;
   int num_layers = 0;
@@ -136,6 +140,8 @@ struct lgarb_engine {
     if (d_host_series) cudaFree(d_host_series);
     d_host_series = nullptr;
     host_series_cap = 0;
+    free_stream_bufs(sbufs);
+    sbufs = nullptr;
     for (cudaEvent_t x : ev_pool) cudaEventDestroy(x);
     for (int i = 0; i < 2; i++) {
       if (win_ev[i]) cudaEventDestroy(win_ev[i]);
@@ -821,6 +827,170 @@ int lgarb_update_steps_host(lgarb_engine* e, int64_t n_steps, const double* h_pr
     CUDA_TRY(cudaStreamSynchronize(e->stream));
   });
 }
+
+// ---- streamed multi-step run (forcing / output streaming) ----------------------
+namespace {
+__global__ void lgarb_f32_to_f64_kernel(const float* __restrict__ src, double* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (double)src[i];
+}
+__global__ void lgarb_f64_to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (float)src[i];
+}
+}  // namespace
+extern "C++" {
+struct StreamBufs {
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  void* raw_in[2] = {nullptr, nullptr};     // f32 forcing as delivered (only for f32 input)
+  double* forcing[2] = {nullptr, nullptr};  // [2][chunk][ncol] f64: precip plane, pet plane
+  double* out[2] = {nullptr, nullptr};      // [n_out][chunk][ncol] f64
+  float* out32[2] = {nullptr, nullptr};
+  size_t cap_forcing[2] = {0, 0}, cap_raw[2] = {0, 0}, cap_out[2] = {0, 0}, cap_out32[2] = {0, 0};  // bytes
+  void free_all() {
+    for (int b = 0; b < 2; b++) {
+      if (raw_in[b]) cudaFree(raw_in[b]);
+      if (forcing[b]) cudaFree(forcing[b]);
+      if (out[b]) cudaFree(out[b]);
+      if (out32[b]) cudaFree(out32[b]);
+      if (ev_h2d[b]) cudaEventDestroy(ev_h2d[b]);
+      if (ev_comp[b]) cudaEventDestroy(ev_comp[b]);
+      if (ev_d2h[b]) cudaEventDestroy(ev_d2h[b]);
+      raw_in[b] = nullptr; forcing[b] = nullptr; out[b] = nullptr; out32[b] = nullptr;
+      ev_h2d[b] = ev_comp[b] = ev_d2h[b] = nullptr;
+      cap_forcing[b] = cap_raw[b] = cap_out[b] = cap_out32[b] = 0;
+    }
+    if (s_h2d) cudaStreamDestroy(s_h2d);
+    if (s_d2h) cudaStreamDestroy(s_d2h);
+    s_h2d = s_d2h = nullptr;
+  }
+};
+void free_stream_bufs(StreamBufs* p) {
+  if (p) {
+    p->free_all();
+    delete p;
+  }
+}
+}  // extern "C++"
+namespace {
+}  // namespace
+
+// n_steps forcing hours from host memory in chunks of chunk_steps: the host-to-device copy of chunk k+1 and the
+// device-to-host copy of the outputs of chunk k-1 run on their own streams while chunk k computes (two staging
+// buffers each way).  Forcing and outputs may be f64 or f32 on the host side; the engine computes in f64.
+#define STREAM_TRY(x)                          \
+  do {                                         \
+    cudaError_t err__ = (x);                   \
+    if (err__ != cudaSuccess) fail(#x, err__); \
+  } while (0)
+int lgarb_update_steps_host_stream(lgarb_engine* e, int64_t n_steps, int64_t chunk_steps, int forcing_dtype, const void* h_precip,
+                                   const void* h_pet, int n_outputs, const char* const* output_names, int output_dtype, void* const* h_outputs) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (n_steps <= 0 || !h_precip || !h_pet) throw std::runtime_error("bad forcing series");
+    if (n_outputs < 0 || n_outputs > LGAR_NOUT) throw std::runtime_error("bad output count");
+    if ((forcing_dtype != LGARB_F64 && forcing_dtype != LGARB_F32) || (output_dtype != LGARB_F64 && output_dtype != LGARB_F32))
+      throw std::runtime_error("dtype must be LGARB_F64 or LGARB_F32");
+    if (chunk_steps <= 0 || chunk_steps > n_steps) chunk_steps = n_steps;
+    chunk_steps = std::min<int64_t>(chunk_steps, LGAR_MAX_WINDOW);
+    const size_t ncol = (size_t)e->ncol, cn = (size_t)chunk_steps * ncol;
+    const size_t in_item = forcing_dtype == LGARB_F32 ? 4 : 8, out_item = output_dtype == LGARB_F32 ? 4 : 8;
+    int out_k[LGAR_NOUT];
+    for (int i = 0; i < n_outputs; i++) {
+      out_k[i] = out_index(output_names[i]);
+      if (out_k[i] < 0) throw std::runtime_error(std::string("variable ") + output_names[i] + " is not a per-step scalar output");
+      if (!h_outputs || !h_outputs[i]) throw std::runtime_error("null output buffer");
+    }
+    if (!e->sbufs) e->sbufs = new StreamBufs();
+    StreamBufs& sb = *e->sbufs;  // streams, events and staging live on between calls (freed by finalize)
+    auto fail = [&](const char* what, cudaError_t err) {
+      cudaDeviceSynchronize();
+      sb.free_all();
+      throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(err));
+    };
+    if (!sb.s_h2d) {
+      STREAM_TRY(cudaStreamCreateWithFlags(&sb.s_h2d, cudaStreamNonBlocking));
+      STREAM_TRY(cudaStreamCreateWithFlags(&sb.s_d2h, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; b++) {
+        STREAM_TRY(cudaEventCreateWithFlags(&sb.ev_h2d[b], cudaEventDisableTiming));
+        STREAM_TRY(cudaEventCreateWithFlags(&sb.ev_comp[b], cudaEventDisableTiming));
+        STREAM_TRY(cudaEventCreateWithFlags(&sb.ev_d2h[b], cudaEventDisableTiming));
+      }
+    }
+    const int nbuf = chunk_steps < n_steps ? 2 : 1;
+    auto grow = [&](void** p, size_t& cap, size_t bytes) {
+      if (bytes <= cap) return;
+      if (*p) {
+        STREAM_TRY(cudaDeviceSynchronize());
+        cudaFree(*p);
+        *p = nullptr;
+        cap = 0;
+      }
+      STREAM_TRY(cudaMalloc(p, bytes));
+      cap = bytes;
+    };
+    for (int b = 0; b < nbuf; b++) {
+      grow((void**)&sb.forcing[b], sb.cap_forcing[b], 2 * cn * sizeof(double));
+      if (forcing_dtype == LGARB_F32) grow(&sb.raw_in[b], sb.cap_raw[b], 2 * cn * sizeof(float));
+      if (n_outputs) {
+        grow((void**)&sb.out[b], sb.cap_out[b], (size_t)n_outputs * cn * sizeof(double));
+        if (output_dtype == LGARB_F32) grow((void**)&sb.out32[b], sb.cap_out32[b], (size_t)n_outputs * cn * sizeof(float));
+      }
+    }
+    const int64_t nchunks = (n_steps + chunk_steps - 1) / chunk_steps;
+    auto chunk_len = [&](int64_t k) { return (size_t)std::min<int64_t>(chunk_steps, n_steps - k * chunk_steps); };
+    auto enqueue_h2d = [&](int64_t k) {
+      const int b = (int)(k % nbuf);
+      const size_t n = chunk_len(k) * ncol, off = (size_t)k * (size_t)chunk_steps * ncol;
+      // the buffer was last read by the compute of chunk k - nbuf
+      if (k >= nbuf) STREAM_TRY(cudaStreamWaitEvent(sb.s_h2d, sb.ev_comp[b], 0));
+      char* dst = forcing_dtype == LGARB_F32 ? (char*)sb.raw_in[b] : (char*)sb.forcing[b];
+      STREAM_TRY(cudaMemcpyAsync(dst, (const char*)h_precip + off * in_item, n * in_item, cudaMemcpyHostToDevice, sb.s_h2d));
+      STREAM_TRY(cudaMemcpyAsync(dst + cn * in_item, (const char*)h_pet + off * in_item, n * in_item, cudaMemcpyHostToDevice, sb.s_h2d));
+      STREAM_TRY(cudaEventRecord(sb.ev_h2d[b], sb.s_h2d));
+    };
+    enqueue_h2d(0);
+    for (int64_t k = 0; k < nchunks; k++) {
+      const int b = (int)(k % nbuf);
+      const size_t len = chunk_len(k), n = len * ncol;
+      if (k + 1 < nchunks && nbuf == 2) enqueue_h2d(k + 1);  // overlaps the compute of chunk k
+      STREAM_TRY(cudaStreamWaitEvent(e->stream, sb.ev_h2d[b], 0));
+      if (k >= nbuf && n_outputs) STREAM_TRY(cudaStreamWaitEvent(e->stream, sb.ev_d2h[b], 0));  // output buffer b drained
+      if (forcing_dtype == LGARB_F32) {
+        lgarb_f32_to_f64_kernel<<<1184, 256, 0, e->stream>>>((const float*)sb.raw_in[b], sb.forcing[b], n);
+        lgarb_f32_to_f64_kernel<<<1184, 256, 0, e->stream>>>((const float*)sb.raw_in[b] + cn, sb.forcing[b] + cn, n);
+        e->launches += 2;
+      }
+      double* sinks[LGAR_NOUT];
+      for (int q = 0; q < LGAR_NOUT; q++) sinks[q] = nullptr;
+      for (int i = 0; i < n_outputs; i++) sinks[out_k[i]] = sb.out[b] + (size_t)i * cn;
+      if (lgarb_update_steps_device(e, (int64_t)len, sb.forcing[b], sb.forcing[b] + cn, e->ncol, n_outputs ? sinks : nullptr, e->ncol, nullptr) != LGARB_SUCCESS) {
+        const std::string msg = e->last_error;
+        cudaDeviceSynchronize();
+        throw std::runtime_error(msg);
+      }
+      if (output_dtype == LGARB_F32)
+        for (int i = 0; i < n_outputs; i++) {
+          lgarb_f64_to_f32_kernel<<<1184, 256, 0, e->stream>>>(sb.out[b] + (size_t)i * cn, sb.out32[b] + (size_t)i * cn, n);
+          e->launches += 1;
+        }
+      STREAM_TRY(cudaEventRecord(sb.ev_comp[b], e->stream));
+      if (n_outputs) {
+        STREAM_TRY(cudaStreamWaitEvent(sb.s_d2h, sb.ev_comp[b], 0));
+        const size_t off = (size_t)k * (size_t)chunk_steps * ncol;
+        for (int i = 0; i < n_outputs; i++) {
+          const char* src = output_dtype == LGARB_F32 ? (const char*)(sb.out32[b] + (size_t)i * cn) : (const char*)(sb.out[b] + (size_t)i * cn);
+          STREAM_TRY(cudaMemcpyAsync((char*)h_outputs[i] + off * out_item, src, n * out_item, cudaMemcpyDeviceToHost, sb.s_d2h));
+        }
+        STREAM_TRY(cudaEventRecord(sb.ev_d2h[b], sb.s_d2h));
+      }
+    }
+    STREAM_TRY(cudaStreamSynchronize(e->stream));
+    STREAM_TRY(cudaStreamSynchronize(sb.s_d2h));
+    STREAM_TRY(cudaStreamSynchronize(sb.s_h2d));
+  });
+}
+
+#undef STREAM_TRY
 
 int lgarb_synchronize(lgarb_engine* e) {
   LGARB_GUARD(e, { require_init(e); CUDA_TRY(cudaStreamSynchronize(e->stream)); });

@@ -21,6 +21,8 @@
 
 #include <algorithm>
 #include <cstddef>
+#include <cstdio>
+#include <cstdlib>
 
 #include "lgar_lanes.cuh"
 
@@ -680,7 +682,10 @@ cudaError_t lgar_launch_wave_run(const LgarConfig& cfg, const LgarDeviceState& d
 // going back to HBM between stages: the critical path per active step drops from one round to the serial
 // execution time of the step.  Lane utilisation is poor by construction, which does not matter for the few
 // thousand slots this is used for.
-__global__ void __launch_bounds__(128) lgar_wave_finish_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int lane_stride) {
+#ifndef LGAR_MB_FINISH
+#define LGAR_MB_FINISH 0
+#endif
+__global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int lane_stride) {
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
   int total = 0;
   for (int q = 0; q < 2 * LGAR_NSTAGE; q++) total += wv.qcount[q];
@@ -786,13 +791,31 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
                                    unsigned append_mask, int quantum, int max_items, cudaStream_t stream) {
   // grid-stride over the queue; max_items (slots in flight at the start of the round) bounds every queue
   const int blocks = std::max(1, std::min((std::min(wv.nslots, max_items) + 127) / 128, 148 * 16));
+  // Unused dynamic shared memory caps the resident blocks per SM of a stage (experiments on how much thread-private
+  // context the L2 can hold: LGARB_WAVE_SMEM_<stage index>=bytes).
+  static int smem[LGAR_NSTAGE] = {-1, -1, -1, -1, -1, -1};
+  if (smem[0] < 0) {
+    for (int s = 0; s < LGAR_NSTAGE; s++) {
+      char name[32];
+      snprintf(name, sizeof(name), "LGARB_WAVE_SMEM_%d", s);
+      const char* v = getenv(name);
+      smem[s] = v ? atoi(v) : 0;
+    }
+    cudaFuncSetAttribute(lgar_wave_kernel<LG_ST_FETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lgar_wave_kernel<LG_ST_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lgar_wave_kernel<LG_ST_FRONT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lgar_wave_kernel<LG_ST_SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lgar_wave_kernel<LG_ST_CORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lgar_wave_kernel<LG_ST_TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  }
+  const size_t sm = (size_t)smem[stage];
   switch (stage) {
-    case LG_ST_FETCH: lgar_wave_kernel<LG_ST_FETCH><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
-    case LG_ST_HEAD: lgar_wave_kernel<LG_ST_HEAD><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
-    case LG_ST_FRONT: lgar_wave_kernel<LG_ST_FRONT><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
-    case LG_ST_SEARCH: lgar_wave_kernel<LG_ST_SEARCH><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
-    case LG_ST_CORR: lgar_wave_kernel<LG_ST_CORR><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
-    default: lgar_wave_kernel<LG_ST_TAIL><<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+    case LG_ST_FETCH: lgar_wave_kernel<LG_ST_FETCH><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+    case LG_ST_HEAD: lgar_wave_kernel<LG_ST_HEAD><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+    case LG_ST_FRONT: lgar_wave_kernel<LG_ST_FRONT><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+    case LG_ST_SEARCH: lgar_wave_kernel<LG_ST_SEARCH><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+    case LG_ST_CORR: lgar_wave_kernel<LG_ST_CORR><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+    default: lgar_wave_kernel<LG_ST_TAIL><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
   }
   lgar_wave_reset_kernel<<<1, 1, 0, stream>>>(wv.qcount + stage * 2 + consume);
   return cudaGetLastError();

@@ -169,6 +169,47 @@ def test_host_buffer_multi_step_call(cuda_device, tmp_path):
         b.update_steps_host(Pm, Em, ["soil_moisture_wetting_fronts"])
 
 
+def test_streamed_host_call_equals_single_call(cuda_device, tmp_path):
+    """lgarb_update_steps_host_stream (chunks, copies overlapped with compute): f64 in / f64 out is bit-identical to
+    lgarb_update_steps_host whatever the chunk length (ragged last chunk included); f32 forcing equals an f64 run fed
+    the same rounded values, and f32 outputs are the f64 outputs rounded once."""
+    import lgar_c_b200
+    g = load_golden("Phillipsburg_with_reservoir")
+    cfg = config_for("Phillipsburg_with_reservoir", tmp_path)
+    ncol, T = 257, 530
+    shifts = (np.arange(ncol) * 7919) % 8760
+    Pm = np.ascontiguousarray(np.stack([np.roll(g["precip"], -int(s))[:T] for s in shifts], axis=1))
+    Em = np.ascontiguousarray(np.stack([np.roll(g["pet"], -int(s))[:T] for s in shifts], axis=1))
+    names = ["total_discharge", "soil_storage", "infiltration"]
+
+    def run(P, E, chunk=None, out_dtype=np.float64):
+        b = lgar_c_b200.BmiLGARBatch()
+        b.initialize(cfg, ncol)
+        if chunk is None:
+            out = b.update_steps_host(P, E, names)
+        else:
+            out = b.update_steps_host_stream(P, E, names, chunk_steps=chunk, output_dtype=out_dtype)
+        fr = b.get_fronts()
+        b.finalize()
+        return out, fr
+
+    ref, fr_ref = run(Pm, Em)
+    for chunk in (0, 530, 200, 64):
+        out, fr = run(Pm, Em, chunk)
+        for n in names:
+            assert np.array_equal(out[n], ref[n]), (chunk, n)
+        for k in ("depth", "theta", "psi", "nfronts"):
+            assert np.array_equal(fr[k], fr_ref[k], equal_nan=True), (chunk, k)
+    P32, E32 = Pm.astype(np.float32), Em.astype(np.float32)
+    ref32, _ = run(P32.astype(np.float64), E32.astype(np.float64))
+    out32, _ = run(P32, E32, 150)
+    for n in names:
+        assert np.array_equal(out32[n], ref32[n]), n
+    outf, _ = run(Pm, Em, 150, np.float32)
+    for n in names:
+        assert outf[n].dtype == np.float32 and np.array_equal(outf[n], ref[n].astype(np.float32)), n
+
+
 def test_heterogeneous_batch_against_oracle(cuda_device, oracle, tmp_path):
     """BASELINE config 3 in small: Bushland layering, per-column soil triples drawn from the PARSED
     vG_params_stat_nom_ordered.dat (quirk Q2), per-column circular time shift of the forcing."""
