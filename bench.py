@@ -294,6 +294,7 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     ncol = args.columns
@@ -384,43 +385,36 @@ def main():
         # the multi-step verb with HOST buffers: forcing of `nh` hours in from pinned host memory, one output
         # series (total_discharge, ngen's usual main_output_variable) back to pinned host memory, all inside
         nh = min(args.e2e_hours, R * H)
-        hP = torch.empty((nh, ncol), dtype=torch.float64).pin_memory()
-        hE = torch.empty((nh, ncol), dtype=torch.float64).pin_memory()
-        hP.copy_(dP[:nh])
-        hE.copy_(dE[:nh])
-        hQ = torch.empty((nh, ncol), dtype=torch.float64).pin_memory()
-        outs = {"total_discharge": hQ.numpy()}
+        nh2 = min(2 * nh, R * H)          # the streamed call runs over more hours; one set of pinned buffers serves both
+        hP = torch.empty((nh2, ncol), dtype=torch.float64).pin_memory()
+        hE = torch.empty((nh2, ncol), dtype=torch.float64).pin_memory()
+        hP.copy_(dP[:nh2])
+        hE.copy_(dE[:nh2])
+        hQ = torch.empty((nh2, ncol), dtype=torch.float64).pin_memory()
         b.update_steps_host(hP.numpy()[:H], hE.numpy()[:H], {"total_discharge": hQ.numpy()[:H]})  # warm-up: allocates the staging
         barrier()
         t0 = time.perf_counter()
-        b.update_steps_host(hP.numpy(), hE.numpy(), outs)
+        b.update_steps_host(hP.numpy()[:nh], hE.numpy()[:nh], {"total_discharge": hQ.numpy()[:nh]})
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         single = world * ncol * nh / float(t_e.item())
-        # the streamed verb: 2*nh hours in two chunks, the forcing copy of the second chunk and the output copy of
+        # the streamed verb: nh2 hours in two chunks, the forcing copy of the second chunk and the output copy of
         # the first overlap the computation (lgarb_update_steps_host_stream)
-        nh2 = min(2 * nh, R * H)
-        hP2 = torch.empty((nh2, ncol), dtype=torch.float64).pin_memory()
-        hE2 = torch.empty((nh2, ncol), dtype=torch.float64).pin_memory()
-        hP2.copy_(dP[:nh2])
-        hE2.copy_(dE[:nh2])
-        hQ2 = torch.empty((nh2, ncol), dtype=torch.float64).pin_memory()
         ch2 = (nh2 + 1) // 2
         # warm-up: allocates the two staging buffers per direction (chunk-sized) and the copy streams
-        b.update_steps_host_stream(hP2.numpy()[:ch2 + 1], hE2.numpy()[:ch2 + 1], {"total_discharge": hQ2.numpy()[:ch2 + 1]}, chunk_steps=ch2)
+        b.update_steps_host_stream(hP.numpy()[:ch2 + 1], hE.numpy()[:ch2 + 1], {"total_discharge": hQ.numpy()[:ch2 + 1]}, chunk_steps=ch2)
         barrier()
         t0 = time.perf_counter()
-        b.update_steps_host_stream(hP2.numpy(), hE2.numpy(), {"total_discharge": hQ2.numpy()}, chunk_steps=(nh2 + 1) // 2)
+        b.update_steps_host_stream(hP.numpy(), hE.numpy(), {"total_discharge": hQ.numpy()}, chunk_steps=ch2)
         torch.cuda.synchronize()
         dt2 = time.perf_counter() - t0
         t_e2 = torch.tensor([dt2], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t_e2, op=dist.ReduceOp.MAX)
         streamed = world * ncol * nh2 / float(t_e2.item())
-        del hP2, hE2, hQ2
         e2e = {"value": max(single, streamed), "unit": "column-timesteps/s",
                "h2d_bytes_per_step": 2 * 8 * ncol * H, "d2h_bytes_per_step": 8 * ncol * H,
                "verb": "lgarb_update_steps_host_stream" if streamed >= single else "lgarb_update_steps_host",
@@ -482,12 +476,21 @@ def main():
         share = {"lgar_step_stream_kernel": ms_s / (ms_s + ms_a), "lgar_step_active_kernel": ms_a / (ms_s + ms_a)}
     bytes_per_launch = units * B_unit
     achieved = bytes_per_launch / dur_s / 1e9
+    # DRAM bytes per launch unit from the committed ncu capture of one whole timed window of this command in mode 3
+    # (profiles/r1_session2_ncu_summary.md section 1: dram__bytes_read.sum + dram__bytes_write.sum over the 2 706 launches
+    # of a 240 h window of 1.25 M columns = 945.8 GB = 3 153 B per column-timestep); null for any other configuration
+    traffic = 3152.8 * units if (args.mode == 3 and ms_w > 0 and H == 24) else None
+    share_ncu = ({"TAIL": 0.291, "SEARCH": 0.157, "HEAD": 0.151, "FRONT": 0.112, "FETCH": 0.098, "finish": 0.095, "CORR": 0.088}
+                 if (args.mode == 3 and ms_w > 0) else None)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_unit": B_unit,
+                "traffic": traffic, "traffic_source": "ncu, profiles/r1_session2_ncu_summary.md section 1" if traffic else None,
+                "stage_time_share_ncu": share_ncu, "peak_source": peak_src, "algorithmic_bytes_per_unit": B_unit,
                 "units_per_launch": units, "avg_launch_ms": dur_s * 1e3, "kernel_time_share": share,
                 "mean_fronts": mean_fronts, "active_fraction": active_frac,
-                "note": "unit = one column-timestep; B = 88*mean_fronts + 428 bytes (SURVEY.md 8d). The kernel is FP64-latency/divergence "
-                        "bound, not HBM bound: see DESIGN.md section 7"}
+                "note": "unit = one column-timestep; a launch = one bench step (one simulated day of every column; the stage kernels of a "
+                        "window are timed together with CUDA events on the engine stream); B = 88*mean_fronts + 428 bytes (SURVEY.md 8d). "
+                        "Measured DRAM traffic is 4x the algorithmic bytes (step contexts crossing HBM at every stage boundary); the path is "
+                        "latency/divergence bound, not HBM bound: DESIGN.md section 4.4"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

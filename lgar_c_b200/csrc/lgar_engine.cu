@@ -576,6 +576,21 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
   const int ncu_round = (getenv("LGARB_NCU_WINDOW") && atoi(getenv("LGARB_NCU_WINDOW")) == e->wave_windows)
                             ? (getenv("LGARB_NCU_ROUND") ? atoi(getenv("LGARB_NCU_ROUND")) : 0) : -1;
   e->wave_windows++;
+  const bool ncu_whole_window = ncu_round == -2;  // LGARB_NCU_ROUND=-2: every launch of the window
+  if (ncu_whole_window) {
+    cudaStreamSynchronize(e->stream);
+    cudaProfilerStart();
+  }
+  struct NcuStop {
+    bool on;
+    cudaStream_t s;
+    ~NcuStop() {
+      if (on) {
+        cudaStreamSynchronize(s);
+        cudaProfilerStop();
+      }
+    }
+  } ncu_stop{ncu_whole_window, e->stream};
   std::vector<std::pair<cudaEvent_t, int>> dbg_evs;
   auto launch = [&](int stage) {
     const int consume = par[stage];
