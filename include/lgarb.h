@@ -128,7 +128,15 @@ int lgarb_synchronize(lgarb_engine* e);
 /* ---- variable access (BMI getters/setters) -------------------------------------------------- */
 
 /* replaces BmiLGAR::SetValue(name, src), src/bmi_lgar.cxx:1455-1467.  src = host array with one
- * item per column.  Settable: precipitation_rate, potential_evapotranspiration_rate (mm/h). */
+ * item per column.  Settable: precipitation_rate, potential_evapotranspiration_rate (mm/h), and the calibratable
+ * parameters of src/bmi_lgar.cxx:1372-1421 -- per COLUMN: smcmax_k, smcmin_k, van_genuchten_n_k,
+ * van_genuchten_alpha_k, hydraulic_conductivity_k (k = 1, 2; the k = 3 names are accepted and ignored exactly
+ * like the reference, whose GetVarGrid does not list them, :1133-1141); same value for every column of the batch:
+ * field_capacity, ponded_depth_max, a, b, frac_to_CR, a_slow, b_slow, frac_slow, spf_factor.  They take effect at
+ * the first Update of a run configured with calib_params=true (update_calibratable_parameters, :916-1078): theta
+ * of every front is recomputed from its psi, the change of stored water is reported as volchange_calib by
+ * lgarb_get_global_mass_balance, and never afterwards (the reference clears its flag, :187-190).  Millions of
+ * columns with millions of parameter sets is the calibration use of the engine. */
 int lgarb_set_value(lgarb_engine* e, const char* name, const void* src);
 int lgarb_set_value_range(lgarb_engine* e, const char* name, int64_t col0, int64_t ncol, const void* src);
 int lgarb_set_value_device(lgarb_engine* e, const char* name, const void* d_src);
@@ -185,7 +193,7 @@ int lgarb_get_fronts(lgarb_engine* e, int64_t col0, int64_t ncol, double* depth_
 
 /* the terms of lgar_global_mass_balance(), src/lgar.cxx:1162-1216, per column, cm:
  * out[ncol][16] = volstart, volprecip, volin, volend, volon, volrunoff, volrunoff_giuh, volrech,
- *                 volAET, volPET, volrunoff_CR, volCRend, volQ, volchange_calib(0), volQ_CR,
+ *                 volAET, volPET, volrunoff_CR, volCRend, volQ, volchange_calib, volQ_CR,
  *                 global_error */
 int lgarb_get_global_mass_balance(lgarb_engine* e, int64_t col0, int64_t ncol, double* out);
 

@@ -239,24 +239,12 @@ inline LgarConfig make_engine_config(const ParsedConfig& pc) {
   return g;
 }
 
-inline LgarColumnClass make_class(const ParsedConfig& pc, const std::vector<SoilRow>& soils, int num_layers, const int* types, const double* thick) {
-  LgarColumnClass c;
-  memset(&c, 0, sizeof(c));
-  const int L = num_layers;
-  c.num_layers = L;
-  c.cum[0] = 0.0;
-  for (int k = 1; k <= L; k++) c.cum[k] = c.cum[k - 1] + thick[k - 1];  // lgar.cxx:339-342
-  c.invalid_soil_type = 0;
+// per-layer part of a class row: the vG parameters and every quantity the reference recomputes per call, from the
+// soil_properties_ rows of the layers (1-based); c.num_layers and c.cum are set by the caller
+inline void fill_class_layers(LgarColumnClass& c, const ParsedConfig& pc, const SoilRow* rows) {
+  const int L = c.num_layers;
   for (int k = 1; k <= L; k++) {
-    if (types[k - 1] > pc.num_soil_types) {  // lgar.cxx:824-836
-      c.invalid_soil_type = 1;
-      break;
-    }
-    if (types[k - 1] < 1) throw std::runtime_error("layer_soil_type must be >= 1");
-  }
-  if (c.invalid_soil_type) return c;
-  for (int k = 1; k <= L; k++) {
-    const SoilRow& s = soils[types[k - 1]];
+    const SoilRow& s = rows[k];
     LgarLayer& l = c.lay[k];
     l.theta_r = s.theta_r; l.theta_e = s.theta_e; l.alpha = s.alpha; l.n = s.n; l.m = s.m; l.Ksat = s.Ksat;
     l.de = s.theta_e - s.theta_r;
@@ -284,6 +272,38 @@ inline LgarColumnClass make_class(const ParsedConfig& pc, const std::vector<Soil
     double Se0 = (c.initial_theta[k] - s.theta_r) / (s.theta_e - s.theta_r);
     c.initial_K[k] = K_from_Se(Se0, s.Ksat, s.m);
   }
+}
+
+inline LgarColumnClass make_class(const ParsedConfig& pc, const std::vector<SoilRow>& soils, int num_layers, const int* types, const double* thick) {
+  LgarColumnClass c;
+  memset(&c, 0, sizeof(c));
+  const int L = num_layers;
+  c.num_layers = L;
+  c.cum[0] = 0.0;
+  for (int k = 1; k <= L; k++) c.cum[k] = c.cum[k - 1] + thick[k - 1];  // lgar.cxx:339-342
+  c.invalid_soil_type = 0;
+  for (int k = 1; k <= L; k++) {
+    if (types[k - 1] > pc.num_soil_types) {  // lgar.cxx:824-836
+      c.invalid_soil_type = 1;
+      break;
+    }
+    if (types[k - 1] < 1) throw std::runtime_error("layer_soil_type must be >= 1");
+  }
+  if (c.invalid_soil_type) return c;
+  std::vector<SoilRow> rows((size_t)L + 1);
+  for (int k = 1; k <= L; k++) rows[k] = soils[types[k - 1]];
+  fill_class_layers(c, pc, rows.data());
+  return c;
+}
+
+// the same for explicit per-layer rows (1-based): calibrated parameters, src/bmi_lgar.cxx:916-1078
+inline LgarColumnClass make_class_from_rows(const ParsedConfig& pc, const SoilRow* rows, int num_layers, const double* thick) {
+  LgarColumnClass c;
+  memset(&c, 0, sizeof(c));
+  c.num_layers = num_layers;
+  c.cum[0] = 0.0;
+  for (int k = 1; k <= num_layers; k++) c.cum[k] = c.cum[k - 1] + thick[k - 1];
+  fill_class_layers(c, pc, rows);
   return c;
 }
 

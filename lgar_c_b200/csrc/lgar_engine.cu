@@ -63,6 +63,14 @@ void free_stream_bufs(StreamBufs*);
 struct lgarb_engine {
   bool initialized = false;
   StreamBufs* sbufs = nullptr;  // staging of lgarb_update_steps_host_stream, kept between calls
+  // calibratable parameters (src/bmi_lgar.cxx:916-1078): set through SetValue before the first Update
+  std::vector<int32_t> class_of;          // [ncol] class row of every column
+  std::vector<int32_t> col_types;         // [ncol][L] soil types (empty: the configuration's for every column)
+  std::vector<double> col_thick;          // [ncol][L] layer thicknesses (empty: the configuration's)
+  bool calib_pending = false, calib_touched = false;
+  std::vector<double> calib_soil[15];     // [layer 1..3][smcmax, smcmin, vg_n, vg_alpha, Ksat] -> [ncol], allocated when first set
+  double calib_glob[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // field_capacity, ponded_depth_max, a, b, frac_to_CR, a_slow, b_slow, frac_slow, spf_factor
+  std::vector<double> volchange_calib;    // [ncol] cm, change of stored water by the parameter update
   int device = 0;
   int64_t ncol = 0, stride = 0;
   int num_layers = 0;
@@ -217,6 +225,20 @@ void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int d
     }
   }
 
+  e->class_of = class_of;
+  e->col_types.clear();
+  e->col_thick.clear();
+  if (types_in) e->col_types.assign(types_in, types_in + (size_t)ncol * L);
+  if (thick_in) e->col_thick.assign(thick_in, thick_in + (size_t)ncol * L);
+  e->calib_pending = pc.calib_params;  // lgar.cxx:742: applied once, at the first Update
+  e->calib_touched = false;
+  for (auto& v : e->calib_soil) v.clear();
+  e->volchange_calib.clear();
+  {  // lgar.cxx:105-113
+    const double g0[9] = {pc.field_capacity_psi, pc.ponded_depth_max, pc.a, pc.b, pc.frac_to_CR, pc.a_slow, pc.b_slow, pc.frac_slow, pc.spf_factor};
+    for (int i = 0; i < 9; i++) e->calib_glob[i] = g0[i];
+  }
+
   // device memory
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   e->ncol = ncol;
@@ -317,6 +339,173 @@ void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int d
   e->launches = 0;
   e->time_s = 0.0;
   e->initialized = true;
+}
+
+// ---- calibratable parameters ---------------------------------------------------
+// index into calib_soil for "smcmax_2" etc. (src/bmi_lgar.cxx:1372-1402), -1 if `name` is not one of them
+int calib_soil_index(const std::string& name) {
+  static const char* stem[5] = {"smcmax_", "smcmin_", "van_genuchten_n_", "van_genuchten_alpha_", "hydraulic_conductivity_"};
+  for (int f = 0; f < 5; f++) {
+    const size_t n = strlen(stem[f]);
+    if (name.size() == n + 1 && name.compare(0, n, stem[f]) == 0 && name[n] >= '1' && name[n] <= '3') return (name[n] - '1') * 5 + f;
+  }
+  return -1;
+}
+int calib_glob_index(const std::string& name) {  // src/bmi_lgar.cxx:1404-1421
+  static const char* nm[9] = {"field_capacity", "ponded_depth_max", "a", "b", "frac_to_CR", "a_slow", "b_slow", "frac_slow", "spf_factor"};
+  for (int i = 0; i < 9; i++)
+    if (name == nm[i]) return i;
+  return -1;
+}
+// value Initialize() gives a per-layer calibratable parameter of column c (lgar.cxx:131-153): the soil row of the layer
+double calib_soil_initial(const lgarb_engine* e, int idx, int64_t c) {
+  const int layer = idx / 5 + 1, f = idx % 5;
+  const LgarColumnClass& cc = e->classes[e->class_of[c]];
+  if (cc.invalid_soil_type || layer > cc.num_layers) return 0.0;
+  const LgarLayer& l = cc.lay[layer];
+  return f == 0 ? l.theta_e : f == 1 ? l.theta_r : f == 2 ? l.n : f == 3 ? l.alpha : l.Ksat;
+}
+
+// update_calibratable_parameters (src/bmi_lgar.cxx:916-1078), once, before the first forcing step of a run whose
+// configuration says calib_params=true: every column gets the parameter set that was written through SetValue,
+// theta of every front is recomputed from its psi, and the change of stored water is booked in volchange_calib.
+// Host side (libm, the reference's own expressions): the result is what the reference computes, bit for bit.
+void apply_calibration(lgarb_engine* e) {
+  if (!e->calib_pending) return;
+  e->calib_pending = false;
+  const ParsedConfig pc0 = e->pc;
+  if (!e->calib_touched && !pc0.log_mode) return;  // same parameters: theta(psi) reproduces the initial theta, nothing changes
+  ParsedConfig& pc = e->pc;
+  const int L = e->num_layers;
+  const int64_t ncol = e->ncol;
+  const size_t st = (size_t)e->stride;
+  // parameters that do not depend on the layer (:1031-1049)
+  pc.field_capacity_psi = e->calib_glob[0];
+  pc.ponded_depth_max = e->calib_glob[1];
+  pc.a = e->calib_glob[2];
+  pc.b = e->calib_glob[3];
+  pc.frac_to_CR = e->calib_glob[4];
+  pc.spf_factor = e->calib_glob[8];
+  if (pc0.frac_slow) {
+    pc.a_slow = e->calib_glob[5];
+    pc.b_slow = e->calib_glob[6];
+    pc.frac_slow = e->calib_glob[7];
+  }
+  if (pc.log_mode) {
+    pc.a = pow(10.0, e->calib_glob[2]);
+    if (pc0.frac_slow) pc.a_slow = pow(10.0, e->calib_glob[5]);
+  }
+  LgarConfig& g = e->cfg;
+  g.field_capacity_psi_cm = pc.field_capacity_psi;
+  g.ponded_depth_max_cm = pc.ponded_depth_max;
+  g.a = pc.a; g.b = pc.b; g.frac_to_CR = pc.frac_to_CR; g.spf_factor = pc.spf_factor;
+  g.a_slow = pc.a_slow; g.b_slow = pc.b_slow; g.frac_slow = pc.frac_slow;
+
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  std::vector<int32_t> nf((size_t)ncol);
+  std::vector<unsigned long long> fl((size_t)ncol);
+  CUDA_TRY(cudaMemcpy(nf.data(), e->d.nfront, (size_t)ncol * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(fl.data(), e->d.fflags, (size_t)ncol * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  int maxnf = 0;
+  for (int64_t c = 0; c < ncol; c++) maxnf = std::max(maxnf, (int)nf[c]);
+  std::vector<double> depth((size_t)maxnf * ncol), theta((size_t)maxnf * ncol), psi((size_t)maxnf * ncol);
+  for (int i = 0; i < maxnf; i++) {
+    CUDA_TRY(cudaMemcpy(depth.data() + (size_t)i * ncol, e->d.depth + (size_t)i * st, (size_t)ncol * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(theta.data() + (size_t)i * ncol, e->d.theta + (size_t)i * st, (size_t)ncol * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(psi.data() + (size_t)i * ncol, e->d.psi + (size_t)i * st, (size_t)ncol * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  auto mass = [&](int64_t c, const double* cum) {  // lgar_calc_mass_bal, lgar.cxx:2632-2668
+    double sum = 0.0;
+    const int n = nf[c];
+    for (int i = 0; i < n; i++) {
+      const int li = (int)((fl[c] >> (4 * i)) & 7);
+      const double base = cum[li - 1];
+      const double th = theta[(size_t)i * ncol + c], dp = depth[(size_t)i * ncol + c];
+      if (i + 1 < n) {
+        const int ln = (int)((fl[c] >> (4 * (i + 1))) & 7);
+        if (ln == li) sum += (dp - base) * (th - theta[(size_t)(i + 1) * ncol + c]);
+        else sum += (dp - base) * th;
+      } else {
+        sum += th * (dp - base);
+      }
+    }
+    return sum;
+  };
+  std::vector<LgarColumnClass> classes;
+  std::map<std::vector<double>, int> seen;
+  std::vector<int32_t> class_of((size_t)ncol);
+  std::vector<double> storage((size_t)ncol, 0.0);
+  e->volchange_calib.assign((size_t)ncol, 0.0);
+  std::vector<int> types(L);
+  std::vector<double> thick(L);
+  std::vector<SoilRow> rows((size_t)L + 1);
+  for (int64_t c = 0; c < ncol; c++) {
+    const LgarColumnClass& old = e->classes[e->class_of[c]];
+    for (int k = 0; k < L; k++) {
+      types[k] = e->col_types.empty() ? pc.layer_soil_type[k] : e->col_types[(size_t)c * L + k];
+      thick[k] = e->col_thick.empty() ? pc.layer_thickness[k] : e->col_thick[(size_t)c * L + k];
+    }
+    std::vector<double> key;
+    if (old.invalid_soil_type) {  // no fronts, precipitation passes through: the class stays what it is
+      key.assign(1, -1.0 - e->class_of[c]);
+    } else {
+      // the reference walks the fronts top down and overwrites soil_properties[soil type of the front's layer] with
+      // the parameters of that LAYER (:929-990): layers that share a soil type end up with the parameters of the
+      // deepest of them, but a front's theta is computed with what the row holds when the walk reaches it
+      for (int k = 1; k <= L; k++) rows[k] = e->soils[types[k - 1]];
+      const double before = mass(c, old.cum);
+      for (int i = 0; i < nf[c]; i++) {
+        const int layer = (int)((fl[c] >> (4 * i)) & 7);
+        if (layer <= 3) {
+          auto val = [&](int f) {
+            const int idx = (layer - 1) * 5 + f;
+            return e->calib_soil[idx].empty() ? calib_soil_initial(e, idx, c) : e->calib_soil[idx][(size_t)c];
+          };
+          SoilRow r = rows[layer];
+          r.theta_e = val(0);
+          r.theta_r = val(1);
+          r.n = val(2);
+          r.m = 1.0 - 1.0 / r.n;
+          r.alpha = val(3);
+          r.Ksat = val(4);
+          if (pc.log_mode) {
+            r.alpha = pow(10.0, val(3));
+            r.Ksat = pow(10.0, val(4));
+          }
+          for (int k = 1; k <= L; k++)
+            if (types[k - 1] == types[layer - 1]) rows[k] = r;  // one row per soil TYPE in the reference
+        }
+        theta[(size_t)i * ncol + c] = theta_from_h(psi[(size_t)i * ncol + c], rows[layer]);
+      }
+      const double after = mass(c, old.cum);
+      e->volchange_calib[(size_t)c] = after - before;
+      storage[(size_t)c] = after;
+      for (int k = 0; k < L; k++) key.push_back(thick[k]);
+      for (int k = 1; k <= L; k++) {
+        const SoilRow& r = rows[k];
+        const double f[10] = {r.theta_r, r.theta_e, r.alpha, r.n, r.m, r.lambda, r.psib, r.h_min, r.Ksat, r.theta_wp};
+        key.insert(key.end(), f, f + 10);
+      }
+    }
+    auto it = seen.find(key);
+    if (it == seen.end()) {
+      const int id = (int)classes.size();
+      classes.push_back(old.invalid_soil_type ? old : make_class_from_rows(pc, rows.data(), L, thick.data()));
+      it = seen.emplace(std::move(key), id).first;
+    }
+    class_of[(size_t)c] = it->second;
+  }
+  // new class table, new theta, storage cache
+  e->classes.swap(classes);
+  e->class_of.swap(class_of);
+  e->d_classes = e->dalloc<LgarColumnClass>(e->classes.size(), false);
+  e->d.classes = e->d_classes;
+  CUDA_TRY(cudaMemcpyAsync(e->d_classes, e->classes.data(), e->classes.size() * sizeof(LgarColumnClass), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->d.class_id, e->class_of.data(), (size_t)ncol * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  for (int i = 0; i < maxnf; i++)
+    CUDA_TRY(cudaMemcpyAsync(e->d.theta + (size_t)i * st, theta.data() + (size_t)i * ncol, (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->d.scal + (size_t)LGAR_S_STORAGE * st, storage.data(), (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
 }
 
 void launch_step(lgarb_engine* e, const double* d_precip, const double* d_pet, const LgarSinks& sinks) {
@@ -434,6 +623,17 @@ void get_value_range(lgarb_engine* e, const std::string& name, int64_t col0, int
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     return;
   }
+  {  // calibratable parameters (src/bmi_lgar.cxx:1372-1421): one value per column
+    const int si = calib_soil_index(name), gi = calib_glob_index(name);
+    if (si >= 0 || gi >= 0) {
+      std::vector<double> v((size_t)ncol);
+      for (int64_t c = 0; c < ncol; c++)
+        v[(size_t)c] = gi >= 0 ? e->calib_glob[gi] : e->calib_soil[si].empty() ? calib_soil_initial(e, si, col0 + c) : e->calib_soil[si][(size_t)(col0 + c)];
+      if (dest_is_device) CUDA_TRY(cudaMemcpy(dest, v.data(), (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice));
+      else memcpy(dest, v.data(), (size_t)ncol * sizeof(double));
+      return;
+    }
+  }
   throw std::runtime_error("variable " + name + " does not exist");  // bmi_lgar.cxx:1421-1425
 }
 
@@ -444,6 +644,36 @@ void set_value_range(lgarb_engine* e, const std::string& name, int64_t col0, int
   if (name == "precipitation_rate") plane = e->d_precip;
   else if (name == "potential_evapotranspiration_rate") plane = e->d_pet;
   else if (name == "soil_temperature_profile") return;  // accepted and ignored: SFT coupling is out of scope (frozen_factor == 1)
+  else if (calib_soil_index(name) >= 0 || calib_glob_index(name) >= 0) {
+    // SetValue on a calibratable parameter writes lgar_calib_params (src/bmi_lgar.cxx:1455-1467); the values take
+    // effect at the first Update of a run configured with calib_params=true (:187-190) and never afterwards
+    std::vector<double> v((size_t)ncol);
+    if (src_is_device) CUDA_TRY(cudaMemcpy(v.data(), src, (size_t)ncol * sizeof(double), cudaMemcpyDeviceToHost));
+    else memcpy(v.data(), src, (size_t)ncol * sizeof(double));
+    const int si = calib_soil_index(name), gi = calib_glob_index(name);
+    if (si >= 10) {
+      // Reference quirk: GetVarGrid lists the *_2 names twice and the *_3 names never (src/bmi_lgar.cxx:1133-1141), so
+      // GetVarNbytes("smcmax_3") is 0 and SetValue copies nothing (:1455-1467): the layer-3 parameters cannot be changed
+      // through SetValue.  Same here, so that the same calls give the same run.
+      return;
+    }
+    if (si >= 0) {
+      std::vector<double>& a = e->calib_soil[si];
+      if (a.empty()) {
+        a.resize((size_t)e->ncol);
+        for (int64_t c = 0; c < e->ncol; c++) a[(size_t)c] = calib_soil_initial(e, si, c);
+      }
+      for (int64_t c = 0; c < ncol; c++) a[(size_t)(col0 + c)] = v[(size_t)c];
+    } else {
+      // the reservoir / ponding / field-capacity parameters are kernel constants of the batch
+      for (int64_t c = 1; c < ncol; c++)
+        if (v[(size_t)c] != v[0]) throw std::runtime_error("variable " + name + " must have the same value for every column of a batch");
+      if (ncol != e->ncol && v[0] != e->calib_glob[gi]) throw std::runtime_error("variable " + name + " can only be set for the whole batch");
+      e->calib_glob[gi] = v[0];
+    }
+    e->calib_touched = true;
+    return;
+  }
   else if (var_grid(name) >= 0) throw std::runtime_error("variable " + name + " is not settable in this engine");
   else throw std::runtime_error("variable " + name + " does not exist");
   CUDA_TRY(cudaMemcpyAsync(plane + col0, src, (size_t)ncol * sizeof(double), src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
@@ -526,6 +756,7 @@ const char* lgarb_last_error(const lgarb_engine* e) { return e ? e->last_error.c
 int lgarb_update(lgarb_engine* e) {
   LGARB_GUARD(e, {
     require_init(e);
+    apply_calibration(e);
     LgarSinks sinks;
     memset(&sinks, 0, sizeof(sinks));
     launch_step(e, e->d_precip, e->d_pet, sinks);
@@ -746,6 +977,7 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
                               double* const* d_sinks, int64_t sink_stride, int32_t* d_nfronts_sink) {
   LGARB_GUARD(e, {
     require_init(e);
+    apply_calibration(e);
     if (n_steps < 0 || !d_precip || !d_pet || series_stride < e->ncol) throw std::runtime_error("bad forcing series");
     if ((d_sinks || d_nfronts_sink) && sink_stride < e->ncol) throw std::runtime_error("bad sink stride");
     if (!e->use_window) {
@@ -1199,7 +1431,7 @@ int lgarb_get_global_mass_balance(lgarb_engine* e, int64_t col0, int64_t ncol, d
       o[10] = cum[LGAR_CUM_RUNOFF_CR * n + c];
       o[11] = volCRend;
       o[12] = cum[LGAR_CUM_Q * n + c];
-      o[13] = 0.0;
+      o[13] = e->volchange_calib.empty() ? 0.0 : e->volchange_calib[(size_t)col0 + c];
       o[14] = cum[LGAR_CUM_Q_CR * n + c];
       o[15] = o[0] + o[1] - o[5] - o[8] - o[4] - o[7] - o[3] + o[13] - o[10] - o[11];  // lgar.cxx:1185
     }

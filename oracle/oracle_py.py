@@ -378,6 +378,22 @@ class RefHarness:
         L.lgref_time_columns.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, _dp, _dp, C.c_int, _ip, _dp, _dp]
         L.lgref_time_columns.restype = C.c_double
         L.lgref_destroy.argtypes = [C.c_void_p]
+        if hasattr(L, "lgref_set_scalar"):
+            L.lgref_set_scalar.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+            L.lgref_set_scalar.restype = C.c_int
+            L.lgref_get_scalar.argtypes = [C.c_void_p, C.c_char_p, _dp]
+            L.lgref_get_scalar.restype = C.c_int
+
+    def set_scalar(self, h, name, value):
+        """BmiLGAR::SetValue(name, &value) for a scalar double variable (calibratable parameters)."""
+        if self.lib.lgref_set_scalar(h, name.encode(), float(value)) != 0:
+            raise KeyError(name)
+
+    def get_scalar(self, h, name):
+        v = C.c_double(0.0)
+        if self.lib.lgref_get_scalar(h, name.encode(), C.byref(v)) != 0:
+            raise KeyError(name)
+        return v.value
 
     def create(self, config_path):
         cfg = absolutize_config(config_path)

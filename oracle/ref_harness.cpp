@@ -90,6 +90,27 @@ int lgref_update(void* h, double precip_mm_h, double pet_mm_h) {
   return 0;
 }
 
+// SetValue / GetValuePtr of a scalar double variable by name (calibratable parameters, src/bmi_lgar.cxx:1372-1421,1455).
+// returns 0 ok, 1 = unknown variable
+int lgref_set_scalar(void* h, const char* name, double value) {
+  RefCol* c = (RefCol*)h;
+  try {
+    c->model.SetValue(std::string(name), &value);
+  } catch (std::exception&) {
+    return 1;
+  }
+  return 0;
+}
+int lgref_get_scalar(void* h, const char* name, double* value) {
+  RefCol* c = (RefCol*)h;
+  try {
+    *value = *static_cast<double*>(c->model.GetValuePtr(std::string(name)));
+  } catch (std::exception&) {
+    return 1;
+  }
+  return 0;
+}
+
 // the 11 BMI output scalars (order of src/bmi_main_lgar.cxx:63-73) + conceptual_reservoir_storage, in m
 void lgref_get_scalars(void* h, double* out12) {
   RefCol* c = (RefCol*)h;
