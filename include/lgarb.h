@@ -136,7 +136,10 @@ int lgarb_synchronize(lgarb_engine* e);
  * the first Update of a run configured with calib_params=true (update_calibratable_parameters, :916-1078): theta
  * of every front is recomputed from its psi, the change of stored water is reported as volchange_calib by
  * lgarb_get_global_mass_balance, and never afterwards (the reference clears its flag, :187-190).  Millions of
- * columns with millions of parameter sets is the calibration use of the engine. */
+ * columns with millions of parameter sets is the calibration use of the engine.
+ * soil_temperature_profile (K): [n_columns][num_cells_temp] (grid 4) when the configuration says sft_coupled=true
+ * (cells at the depths of soil_z); the frozen factors of src/lgar.cxx:1109-1149 are recomputed from it before the next
+ * step.  Ignored without SFT coupling, like the reference's one unused cell. */
 int lgarb_set_value(lgarb_engine* e, const char* name, const void* src);
 int lgarb_set_value_range(lgarb_engine* e, const char* name, int64_t col0, int64_t ncol, const void* src);
 int lgarb_set_value_device(lgarb_engine* e, const char* name, const void* d_src);

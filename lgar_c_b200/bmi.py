@@ -240,8 +240,12 @@ class BmiLGARBatch:
     # -- variables (reference GetValue / SetValue, src/bmi_lgar.cxx:1307,1455) ---------------------
     def set_value(self, name, src):
         a = np.ascontiguousarray(src, dtype=np.float64)
-        if a.size != self.n_columns:
-            raise LgarbError(f"{name}: expected {self.n_columns} items, got {a.size}")
+        if name == "soil_temperature_profile":     # [n_columns][num_cells_temp] (grid 4)
+            want = self.get_grid_size(4)
+        else:
+            want = self.n_columns
+        if a.size != want:
+            raise LgarbError(f"{name}: expected {want} items, got {a.size}")
         self._ck(self._L.lgarb_set_value(self._h, name.encode(), _ptr(a)))
 
     def set_value_device(self, name, d_ptr):

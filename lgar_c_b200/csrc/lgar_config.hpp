@@ -33,6 +33,7 @@ struct ParsedConfig {
   std::vector<double> layer_thickness;
   std::vector<int> layer_soil_type;
   std::vector<double> giuh_hourly;
+  std::vector<double> soil_z;  // depths of the soil temperature cells (SFT coupling), in the unit of the layer thicknesses
   std::string soil_params_file;
   double initial_psi = 0, wilting_point_psi = 0, field_capacity_psi = 0;
   double a = 0, b = 0, frac_to_CR = 0, a_slow = 0, b_slow = 0, frac_slow = 0, spf_factor = 0.98;
@@ -135,6 +136,7 @@ inline ParsedConfig parse_config(const std::string& config_file) {
     }
     else if (key == "forcing_resolution") { c.forcing_resolution_h = to_hours(std::stod(val), unit); s_fr = true; }
     else if (key == "sft_coupled") { c.sft_coupled = parse_bool(key, val, false); }
+    else if (key == "soil_z") { c.soil_z = read_vector(val); }  // lgar.cxx:390-400
     else if (key == "ponded_depth_max") { c.ponded_depth_max = fmax(std::stod(val), 0.0); }
     else if (key == "calib_params") { c.calib_params = parse_bool(key, val, false); }
   }
@@ -163,7 +165,8 @@ inline ParsedConfig parse_config(const std::string& config_file) {
     c.a = pow(10.0, c.a);
     if (s_as) c.a_slow = pow(10.0, c.a_slow);
   }
-  if (c.sft_coupled) throw std::runtime_error("sft_coupled=true is out of scope for this engine (frozen_factor == 1)");
+  if (c.sft_coupled && c.soil_z.empty())  // lgar.cxx:946-952
+    throw std::runtime_error("The configuration file '" + config_file + "' does not set soil_z.");
   return c;
 }
 

@@ -71,6 +71,10 @@ struct lgarb_engine {
   std::vector<double> calib_soil[15];     // [layer 1..3][smcmax, smcmin, vg_n, vg_alpha, Ksat] -> [ncol], allocated when first set
   double calib_glob[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // field_capacity, ponded_depth_max, a, b, frac_to_CR, a_slow, b_slow, frac_slow, spf_factor
   std::vector<double> volchange_calib;    // [ncol] cm, change of stored water by the parameter update
+  // SFT coupling (sft_coupled=true): soil temperature profile per column -> frozen_factor per layer (lgar.cxx:1109-1149)
+  std::vector<double> soil_temperature;   // [ncol][num_cells_temp] K, zero until set (lgar.cxx:947)
+  double* d_ff = nullptr;                 // [LGAR_MAXL+1][stride]
+  bool ff_dirty = false;
   int device = 0;
   int64_t ncol = 0, stride = 0;
   int num_layers = 0;
@@ -230,6 +234,9 @@ void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int d
   e->col_thick.clear();
   if (types_in) e->col_types.assign(types_in, types_in + (size_t)ncol * L);
   if (thick_in) e->col_thick.assign(thick_in, thick_in + (size_t)ncol * L);
+  e->soil_temperature.clear();
+  e->d_ff = nullptr;
+  e->ff_dirty = false;
   e->calib_pending = pc.calib_params;  // lgar.cxx:742: applied once, at the first Update
   e->calib_touched = false;
   for (auto& v : e->calib_soil) v.clear();
@@ -273,6 +280,13 @@ void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int d
   e->d_stage_i = e->dalloc<int32_t>(st);
   e->d_classes = e->dalloc<LgarColumnClass>(e->classes.size(), false);
   d.classes = e->d_classes;
+  d.ff = nullptr;
+  if (pc.sft_coupled) {
+    e->soil_temperature.assign((size_t)ncol * pc.soil_z.size(), 0.0);
+    e->d_ff = e->dalloc<double>(st * (LGAR_MAXL + 1));
+    d.ff = e->d_ff;
+    e->ff_dirty = true;  // the first Update computes the factors from the (zero) profile like the reference does
+  }
   d.precip = e->d_precip;
   d.pet = e->d_pet;
   CUDA_TRY(cudaMemcpyAsync(e->d_classes, e->classes.data(), e->classes.size() * sizeof(LgarColumnClass), cudaMemcpyHostToDevice, e->stream));
@@ -508,6 +522,41 @@ void apply_calibration(lgarb_engine* e) {
   CUDA_TRY(cudaStreamSynchronize(e->stream));
 }
 
+// frozen_factor_hydraulic_conductivity (lgar.cxx:1109-1149) for every column: layer-averaged soil temperature ->
+// exp(-10 (273.15 - T)) clamped to [0.05, 1].  Host side with libm like the reference; the cell cursor runs on from
+// layer to layer as it does there.
+void update_frozen_factors(lgarb_engine* e) {
+  if (!e->pc.sft_coupled || !e->ff_dirty) return;
+  const std::vector<double>& z = e->pc.soil_z;
+  const int ncell = (int)z.size(), L = e->num_layers;
+  const int64_t ncol = e->ncol;
+  const size_t st = (size_t)e->stride;
+  std::vector<double> ff((size_t)(LGAR_MAXL + 1) * st, 1.0);
+  for (int64_t col = 0; col < ncol; col++) {
+    const LgarColumnClass& cc = e->classes[e->class_of[col]];
+    if (cc.invalid_soil_type) continue;
+    const double* T = e->soil_temperature.data() + (size_t)col * ncell;
+    int c = 0;
+    for (int layer = 1; layer <= L; layer++) {
+      double layer_temp = 0.0;
+      int count = 0;
+      while (c < ncell && z[c] <= cc.cum[layer]) {
+        layer_temp += T[c];
+        c++;
+        count++;
+      }
+      if (count == 0) throw std::runtime_error("soil_z has no temperature cell inside soil layer " + std::to_string(layer));  // assert (count > 0), lgar.cxx:1131
+      layer_temp /= count;
+      double factor = exp(-10 * (273.15 - layer_temp));
+      factor = fmax(fmin(factor, 1.0), 0.05);
+      ff[(size_t)layer * st + (size_t)col] = factor;
+    }
+  }
+  CUDA_TRY(cudaMemcpyAsync(e->d_ff, ff.data(), ff.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->ff_dirty = false;
+}
+
 void launch_step(lgarb_engine* e, const double* d_precip, const double* d_pet, const LgarSinks& sinks) {
   LgarDeviceState d = e->d;
   d.precip = d_precip;
@@ -643,7 +692,16 @@ void set_value_range(lgarb_engine* e, const std::string& name, int64_t col0, int
   double* plane = nullptr;
   if (name == "precipitation_rate") plane = e->d_precip;
   else if (name == "potential_evapotranspiration_rate") plane = e->d_pet;
-  else if (name == "soil_temperature_profile") return;  // accepted and ignored: SFT coupling is out of scope (frozen_factor == 1)
+  else if (name == "soil_temperature_profile") {
+    // [ncol][num_cells_temp] K (grid 4, src/bmi_lgar.cxx:1144); without SFT coupling the reference keeps one unused cell
+    if (!e->pc.sft_coupled) return;
+    const size_t ncell = e->pc.soil_z.size();
+    double* dst = e->soil_temperature.data() + (size_t)col0 * ncell;
+    if (src_is_device) CUDA_TRY(cudaMemcpy(dst, src, (size_t)ncol * ncell * sizeof(double), cudaMemcpyDeviceToHost));
+    else memcpy(dst, src, (size_t)ncol * ncell * sizeof(double));
+    e->ff_dirty = true;
+    return;
+  }
   else if (calib_soil_index(name) >= 0 || calib_glob_index(name) >= 0) {
     // SetValue on a calibratable parameter writes lgar_calib_params (src/bmi_lgar.cxx:1455-1467); the values take
     // effect at the first Update of a run configured with calib_params=true (:187-190) and never afterwards
@@ -757,6 +815,7 @@ int lgarb_update(lgarb_engine* e) {
   LGARB_GUARD(e, {
     require_init(e);
     apply_calibration(e);
+    update_frozen_factors(e);
     LgarSinks sinks;
     memset(&sinks, 0, sizeof(sinks));
     launch_step(e, e->d_precip, e->d_pet, sinks);
@@ -978,9 +1037,10 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
   LGARB_GUARD(e, {
     require_init(e);
     apply_calibration(e);
+    update_frozen_factors(e);  // an SFT-coupled run keeps the current temperature profile for the whole call
     if (n_steps < 0 || !d_precip || !d_pet || series_stride < e->ncol) throw std::runtime_error("bad forcing series");
     if ((d_sinks || d_nfronts_sink) && sink_stride < e->ncol) throw std::runtime_error("bad sink stride");
-    if (!e->use_window) {
+    if (!e->use_window || e->pc.sft_coupled) {  // the window schedulers run uncoupled columns only
       for (int64_t t = 0; t < n_steps; t++) {
         LgarSinks sinks;
         for (int k = 0; k < LGAR_NOUT; k++) sinks.p[k] = (d_sinks && d_sinks[k]) ? d_sinks[k] + t * sink_stride : nullptr;
@@ -1328,7 +1388,7 @@ int lgarb_get_grid_size(const lgarb_engine* e, int grid, int64_t* size) {
     if (grid == 0 || grid == 1) *size = e->ncol;
     else if (grid == 2) *size = e->ncol * e->num_layers;
     else if (grid == 3) *size = e->ncol * LGAR_W;  // padded; the reference's is the live front count
-    else if (grid == 4) *size = 1;                  // num_cells_temp without SFT (lgar.cxx:956-958)
+    else if (grid == 4) *size = e->pc.sft_coupled ? (int64_t)e->pc.soil_z.size() * e->ncol : e->ncol;  // num_cells_temp per column (1 without SFT, lgar.cxx:956-958)
     else *size = -1;
   });
 }

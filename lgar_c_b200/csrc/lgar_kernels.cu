@@ -480,6 +480,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
           G.c.cfg = &cfg;
           G.c.cls = G.cls;
           G.c.f = &G.f;
+          G.c.ff = lg_ff_ones;
           if (STAGE == LG_ST_FRONT)
             lg_stage_front(G);
           else
@@ -508,6 +509,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         L.c.cfg = &cfg;
         L.c.cls = L.cls;
         L.c.f = &L.f;
+        L.c.ff = lg_ff_ones;
         if (STAGE == LG_ST_FRONT)
           lg_stage_front(L);
         else
@@ -602,6 +604,7 @@ __global__ void __launch_bounds__(LGAR_RUN_THREADS, LGAR_MB_RUN) lgar_wave_run_k
       L.c.cfg = &cfg;
       L.c.cls = L.cls;
       L.c.f = &L.f;
+      L.c.ff = lg_ff_ones;
       st = entry;
     }
     int next = -1;
@@ -743,6 +746,7 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
     L.c.cfg = &cfg;
     L.c.cls = L.cls;
     L.c.f = &L.f;
+    L.c.ff = lg_ff_ones;
     while (L.stage != LG_ST_DONE) {
       switch (L.stage) {
         case LG_ST_FETCH: lg_stage_fetch(cfg, d, w, L, fsp); break;

@@ -608,7 +608,7 @@ LG_FN_NOINLINE bool lg_move_end(LgLane& L) {
       const LgarLayer& sk = cls.lay[f.layer[i]];
       double Se = lg_Se_from_theta(f.theta[i], sk);
       if (f.psi[i] > 1.0) f.psi[i] = lg_h_from_Se(Se, sk);
-      f.K[i] = lg_K_from_Se(Se, sk);
+      f.K[i] = lg_K_from_Se(Se, sk, c.ff[f.layer[i]] * sk.Ksat);  // lgar.cxx:1836
     }
     if (f.n == 1) {
       if (f.depth[0] != cls.cum[1]) f.depth[0] = cls.cum[1];
@@ -837,6 +837,7 @@ LG_FN_NOINLINE void lg_stage_head(const LgarConfig& cfg, const LgarDeviceState& 
   L.c.cfg = &cfg;
   L.c.cls = L.cls;
   L.c.f = &L.f;
+  L.c.ff = lg_ff_ones;  // the window schedulers run uncoupled columns only (the engine steps SFT-coupled runs hour by hour)
   L.c.status = 0;
   L.volon_ts = L.s.volon;
   L.volend_sub = L.s.storage;

@@ -80,7 +80,16 @@ struct LgCtx {
   const LgarColumnClass* cls;
   LgFronts* f;
   int status;
+  // frozen_factor[layer] of the SFT coupling (1-based; reference lgar.cxx:1109-1149), all 1.0 unless the run is
+  // coupled.  The places that use it -- and the three that do not (quirk Q11) -- follow the reference one by one;
+  // x * 1.0 == x, so an uncoupled run is bit for bit what it was without the factor.
+  const double* ff;
 };
+#ifdef LGAR_HOSTSIM
+static const double lg_ff_ones[LGAR_MAXL + 2] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+#else
+__device__ const double lg_ff_ones[LGAR_MAXL + 2] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // L1: van Genuchten constitutive relations, reference src/soil_funcs.cxx
@@ -136,8 +145,9 @@ LG_FN_NOINLINE double lg_Se_from_h(double h, const LgarLayer& s) {
 }
 #endif
 // calc_K_from_Se, soil_funcs.cxx:164-167 (pow(x,2.0) -> x*x)
-LG_FN_NOINLINE double lg_K_from_Se(double Se, const LgarLayer& s) {
-  return s.Ksat * sqrt(Se) * lg_sq(1.0 - lg_pow(1.0 - lg_pow(Se, s.inv_m), s.m));
+// Ksat is an argument: the reference passes Ks * frozen_factor[layer] at some call sites and plain Ks at others
+LG_FN_NOINLINE double lg_K_from_Se(double Se, const LgarLayer& s, double Ksat) {
+  return Ksat * sqrt(Se) * lg_sq(1.0 - lg_pow(1.0 - lg_pow(Se, s.inv_m), s.m));
 }
 // calc_h_from_Se, soil_funcs.cxx:172-179
 LG_FN_NOINLINE double lg_h_from_Se(double Se, const LgarLayer& s) {
@@ -149,7 +159,7 @@ LG_FN_NOINLINE double lg_h_from_Se(double Se, const LgarLayer& s) {
 LG_FN double lg_Se_from_theta(double theta, const LgarLayer& s) { return (theta - s.theta_r) / s.de; }
 
 // calc_Geff, soil_funcs.cxx:34-140.  Closed form: Se_f from theta1, Se_i from theta2.
-LG_FN_NOINLINE double lg_Geff(const LgarConfig& cfg, double theta1, double theta2, const LgarLayer& s) {
+LG_FN_NOINLINE double lg_Geff(const LgarConfig& cfg, double theta1, double theta2, const LgarLayer& s, double Ksat) {
   if (!cfg.use_closed_form_G) {
     double Se_i = lg_Se_from_theta(theta1, s);
     double Se_f = lg_Se_from_theta(theta2, s);
@@ -158,11 +168,11 @@ LG_FN_NOINLINE double lg_Geff(const LgarConfig& cfg, double theta1, double theta
     double dh = (h_i - h_f) / (double)cfg.nint;
     dh = dh * 0.01;
     double Geff = 0.0;
-    double K1 = lg_K_from_Se(Se_i, s);
+    double K1 = lg_K_from_Se(Se_i, s, Ksat);
     double h2 = h_f + dh;
     while (h2 < h_i) {
       double Se2 = lg_Se_from_h(h2, s);
-      double K2 = lg_K_from_Se(Se2, s);
+      double K2 = lg_K_from_Se(Se2, s, Ksat);
       if ((K1 - K2) / K2 > 0.02)
         dh = dh * 0.5;
       else
@@ -171,7 +181,7 @@ LG_FN_NOINLINE double lg_Geff(const LgarConfig& cfg, double theta1, double theta
       K1 = K2;
       h2 += dh;
     }
-    return fabs(Geff / s.Ksat);
+    return fabs(Geff / Ksat);
   } else {
     double Se_f = lg_Se_from_theta(theta1, s);
     double Se_i = lg_Se_from_theta(theta2, s);
@@ -214,7 +224,7 @@ LG_FN_NOINLINE int lg_front_delete(LgCtx& c, int idx) {
         f.psi[i] = f.psi[wf];
         f.theta[i] = lg_theta_from_h(f.psi[i], sp);
         double Se = lg_Se_from_theta(f.theta[i], sp);
-        f.K[i] = lg_K_from_Se(Se, sp);
+        f.K[i] = lg_K_from_Se(Se, sp, sp.Ksat);  // un-frozen Ks in the reference (linked_list.cxx:283, quirk Q11)
       }
     }
   }
@@ -483,7 +493,7 @@ LG_FN_NOINLINE void lg_merge(LgCtx& c) {
       const LgarLayer& sp = c.cls->lay[f.layer[cur]];
       double Se = lg_Se_from_theta(f.theta[cur], sp);
       f.psi[cur] = lg_h_from_Se(Se, sp);
-      f.K[cur] = lg_K_from_Se(Se, sp);
+      f.K[cur] = lg_K_from_Se(Se, sp, sp.Ksat * c.ff[f.layer[cur]]);  // lgar.cxx:1927
       lg_front_delete(c, nx);
     }
     cur = cur + 1;
@@ -522,7 +532,7 @@ LG_FN_NOINLINE void lg_cross_layer_boundary(LgCtx& c) {
       double overshot_depth = f.depth[cur] - f.depth[nx];
       double Se = lg_Se_from_theta(f.theta[cur], sp);
       f.psi[cur] = lg_h_from_Se(Se, sp);
-      f.K[cur] = lg_K_from_Se(Se, sp);
+      f.K[cur] = lg_K_from_Se(Se, sp, sp.Ksat * c.ff[layer_num]);  // lgar.cxx:1997,2023
       double theta_new = lg_theta_from_h(f.psi[cur], spn);
       double mbal_correction = overshot_depth * (current_theta - f.theta[nx]);
       double mbal_Z = mbal_correction / (theta_new - f.theta[nn]);
@@ -553,7 +563,7 @@ LG_FN_NOINLINE void lg_cross_layer_boundary(LgCtx& c) {
       f.theta[i] = lg_theta_from_h(f.psi[i], sk);
     }
     double Se = lg_Se_from_theta(f.theta[i], sk);
-    f.K[i] = lg_K_from_Se(Se, sk);
+    f.K[i] = lg_K_from_Se(Se, sk, sk.Ksat);  // un-frozen Ks in the reference (lgar.cxx:2071,2080, quirk Q11)
   }
   if (!theta_correction_necessary) return;
   for (int wf = f.n - 1; wf != 0; wf--) {  // :2090-2159
@@ -626,7 +636,7 @@ LG_FN_NOINLINE double lg_cross_domain_boundary(LgCtx& c) {
       f.theta[nx] = f.theta[cur];
       double Se_k = lg_Se_from_theta(f.theta[cur], sp);
       f.psi[nx] = lg_h_from_Se(Se_k, sp);
-      f.K[nx] = lg_K_from_Se(Se_k, sp);
+      f.K[nx] = lg_K_from_Se(Se_k, sp, sp.Ksat * c.ff[f.layer[cur]]);  // lgar.cxx:2225-2230
       lg_front_delete(c, cur);
       bottom_flux += flux_temp;
       break;
@@ -907,7 +917,7 @@ LG_FN_NOINLINE double lg_move_wetting_fronts(LgCtx& c, double timestep_h, double
     const LgarLayer& sk = cls.lay[f.layer[i]];
     double Se = lg_Se_from_theta(f.theta[i], sk);
     if (f.psi[i] > 1.0) f.psi[i] = lg_h_from_Se(Se, sk);
-    f.K[i] = lg_K_from_Se(Se, sk);
+    f.K[i] = lg_K_from_Se(Se, sk, c.ff[f.layer[i]] * sk.Ksat);  // :1836
   }
   if (f.n == 1) {  // :1858-1863
     if (f.depth[0] != cum[1]) f.depth[0] = cum[1];
@@ -927,17 +937,20 @@ LG_FN_NOINLINE double lg_insert_water(LgCtx& c, double timestep_h, double AET_de
   const int fdi = wf_fd_demand - 1;
   const int layer_fp = f.layer[fdi];
   const LgarLayer& sp = cls.lay[layer_fp];
+  // Ks of the infiltrating layer times the frozen factor of the layer of the TOP front (lgar.cxx:2384,2401, quirk Q4)
+  const double Ksat = sp.Ksat * c.ff[f.layer[0]];
   double Geff;
   if (f.n == cls.num_layers)
     Geff = 0.0;
   else
-    Geff = lg_Geff(cfg, f.theta[fdi + 1], sp.theta_e, sp);
+    Geff = lg_Geff(cfg, f.theta[fdi + 1], sp.theta_e, sp, Ksat);
   if (layer_fp == 1) {
-    f_p = sp.Ksat * (1 + (Geff + h_p) / f.depth[fdi]);
+    f_p = Ksat * (1 + (Geff + h_p) / f.depth[fdi]);
   } else {
-    double bottom_sum = (f.depth[fdi] - cum[layer_fp - 1]) / sp.Ksat;
-    for (int k = 1; k < layer_fp; k++) bottom_sum += (cum[layer_fp - k] - cum[layer_fp - (k + 1)]) / cls.lay[layer_fp - k].Ksat;
-    f_p = (f.depth[fdi] / bottom_sum) + ((Geff + h_p) * sp.Ksat / (f.depth[fdi]));
+    double bottom_sum = (f.depth[fdi] - cum[layer_fp - 1]) / Ksat;
+    for (int k = 1; k < layer_fp; k++)
+      bottom_sum += (cum[layer_fp - k] - cum[layer_fp - (k + 1)]) / (cls.lay[layer_fp - k].Ksat * c.ff[layer_fp - k]);  // :2420
+    f_p = (f.depth[fdi] / bottom_sum) + ((Geff + h_p) * Ksat / (f.depth[fdi]));
   }
   double current_mass = lg_mass_bal(c);
   double cap = (cls.max_storage + free_drainage_cm + AET_demand_cm - current_mass) / timestep_h;
@@ -969,8 +982,9 @@ LG_FN_NOINLINE double lg_calc_dry_depth(LgCtx& c, double timestep_h) {
   const LgFronts& f = *c.f;
   const int layer_num = f.layer[0];
   const LgarLayer& sp = c.cls->lay[layer_num];
-  double tau = timestep_h * sp.Ksat / (sp.theta_e - f.theta[0]);
-  double Geff = lg_Geff(*c.cfg, f.theta[0], sp.theta_e, sp);
+  const double Ksat = sp.Ksat * c.ff[layer_num];  // lgar.cxx:2602
+  double tau = timestep_h * Ksat / (sp.theta_e - f.theta[0]);
+  double Geff = lg_Geff(*c.cfg, f.theta[0], sp.theta_e, sp, Ksat);
   double dry_depth = 0.5 * (tau + sqrt(tau * tau + 4.0 * tau * Geff));
   return fmin(c.cls->cum[layer_num], dry_depth);
 }
@@ -995,7 +1009,7 @@ LG_FN_NOINLINE void lg_create_surficial_front(LgCtx& c, double* ponded_depth_cm,
   if (c.status & LGAR_FAIL_OVERFLOW) return;
   double Se = lg_Se_from_theta(theta_new, sp);
   f.psi[0] = lg_h_from_Se(Se, sp);
-  f.K[0] = lg_K_from_Se(Se, sp);
+  f.K[0] = lg_K_from_Se(Se, sp, sp.Ksat * c.ff[1]) * c.ff[1];  // the factor is applied twice in the reference (lgar.cxx:2542,2547, quirk Q11)
   f.dzdt[0] = 0.0;
   if (f.n > 1) {
     bool had_to_merge = false;
@@ -1044,11 +1058,12 @@ LG_FN_NOINLINE void lg_dzdt_calc(LgCtx& c, double h_p, double subtimestep_h, boo
       c.status |= LGAR_FAIL_THETA_ORDER;
       return;
     }
-    double Geff = lg_Geff(*c.cfg, theta1, theta2, sp);
+    const double Ksat = sp.Ksat * c.ff[layer_num];  // lgar.cxx:2824
+    double Geff = lg_Geff(*c.cfg, theta1, theta2, sp, Ksat);
     double delta_theta = f.theta[i] - f.theta[i + 1];
     if (layer_num == 1) {
       if (delta_theta > 0)
-        dzdt = 1.0 / delta_theta * (sp.Ksat * (Geff + h_p) / f.depth[i] + f.K[i]);
+        dzdt = 1.0 / delta_theta * (Ksat * (Geff + h_p) / f.depth[i] + f.K[i]);
       else
         dzdt = 0.0;
     } else {
@@ -1056,11 +1071,11 @@ LG_FN_NOINLINE void lg_dzdt_calc(LgCtx& c, double h_p, double subtimestep_h, boo
       for (int k = 1; k < layer_num; k++) {  // quirk Q3: K of layer (layer_num-k) with the thickness of layer k
         const LgarLayer& sl = cls.lay[layer_num - k];
         double theta_prev = lg_theta_from_h(f.psi[i], sl);
-        double K_prev = lg_K_from_Se(lg_Se_from_theta(theta_prev, sl), sl);
+        double K_prev = lg_K_from_Se(lg_Se_from_theta(theta_prev, sl), sl, sl.Ksat * c.ff[layer_num - k]);  // :2877
         denominator += (cum[k] - cum[k - 1]) / K_prev;
       }
       if (delta_theta > 0)
-        dzdt = (1.0 / delta_theta) * ((f.depth[i] / denominator) + sp.Ksat * (Geff + h_p) / f.depth[i]);
+        dzdt = (1.0 / delta_theta) * ((f.depth[i] / denominator) + Ksat * (Geff + h_p) / f.depth[i]);
       else
         dzdt = 0.0;
     }
@@ -1256,12 +1271,13 @@ LG_FN_NOINLINE void lg_step_cached(const LgarConfig& cfg, LgScalars& s, const Lg
 
 // A forcing step that computes fluxes (bmi_lgar.cxx:356-805 with cache_fluxes == false).
 LG_FN_NOINLINE void lg_step_active(const LgarConfig& cfg, const LgarColumnClass& cls, LgScalars& s, LgFronts& f, const LgPrologue& pro,
-                                   double precip_mm_h, double pet_mm_h, LgStepVols& v) {
+                                   double precip_mm_h, double pet_mm_h, LgStepVols& v, const double* frozen_factor) {
   LgCtx c;
   c.cfg = &cfg;
   c.cls = &cls;
   c.f = &f;
   c.status = 0;
+  c.ff = frozen_factor;
   const double dt = pro.subtimestep_h;
   const int num_layers = cls.num_layers;
   double volon_ts = s.volon;

@@ -244,7 +244,14 @@ LG_FN_NOINLINE void lg_active_column(const LgarConfig& cfg, const LgarDeviceStat
     LgFronts f;
     load_fronts(d, col, f);
     s.cache_fluxes = 0;
-    lg_step_active(cfg, *cls, s, f, pro, P, E, v);
+    // SFT coupling: this column's frozen factors of the step (set by the engine from soil_temperature_profile)
+    double ff[LGAR_MAXL + 2];
+    const double* ffp = lg_ff_ones;
+    if (d.ff) {
+      for (int k = 0; k <= LGAR_MAXL; k++) ff[k] = d.ff[(int64_t)k * d.stride + col];
+      ffp = ff;
+    }
+    lg_step_active(cfg, *cls, s, f, pro, P, E, v, ffp);
     store_scalars(d, col, s, true);
     store_fronts(d, col, f);
   }

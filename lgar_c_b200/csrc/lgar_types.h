@@ -117,6 +117,7 @@ struct LgarDeviceState {
   double* cum;                  // [LGAR_NCUM][stride]
   double* out;                  // [LGAR_NOUT][stride] last step, metres
   const LgarColumnClass* classes;
+  const double* ff;             // null, or [LGAR_MAXL+1][stride] frozen_factor per layer (1-based) of the SFT coupling
   // per-step forcing (mm/h)
   const double* precip;
   const double* pet;

@@ -389,6 +389,13 @@ class RefHarness:
         if self.lib.lgref_set_scalar(h, name.encode(), float(value)) != 0:
             raise KeyError(name)
 
+    def set_array(self, h, name, values):
+        """BmiLGAR::SetValue(name, values) for an array variable (soil_temperature_profile)."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        self.lib.lgref_set_array.argtypes = [C.c_void_p, C.c_char_p, _dp]
+        if self.lib.lgref_set_array(h, name.encode(), _as_dp(v)) != 0:
+            raise KeyError(name)
+
     def get_scalar(self, h, name):
         v = C.c_double(0.0)
         if self.lib.lgref_get_scalar(h, name.encode(), C.byref(v)) != 0:

@@ -101,6 +101,16 @@ int lgref_set_scalar(void* h, const char* name, double value) {
   }
   return 0;
 }
+// SetValue of an array variable (soil_temperature_profile of the SFT coupling): copies GetVarNbytes(name) bytes
+int lgref_set_array(void* h, const char* name, double* values) {
+  RefCol* c = (RefCol*)h;
+  try {
+    c->model.SetValue(std::string(name), values);
+  } catch (std::exception&) {
+    return 1;
+  }
+  return 0;
+}
 int lgref_get_scalar(void* h, const char* name, double* value) {
   RefCol* c = (RefCol*)h;
   try {
