@@ -104,6 +104,7 @@ struct lgarb_engine {
   int wave_quantum = 64, wave_pairs = 4, wave_corr_pairs = 1;
   int wave_finish_below = 16384;
   int finish_lane_stride = 4;  // finishing kernel: one slot per this many lanes
+  int update_wave_min_cols = 1 << 30;  // lgarb_update: batches of at least this many columns take the wavefront kernels
   int wave_windows = 0;  // windows run so far (profiling range selection)
   int wave_escalate_below = 8192;
   int wave_corr_quantum = 64;  // correction-search trips per launch (scaled with the psi-search quantum when that escalates)
@@ -774,6 +775,7 @@ int lgarb_create(lgarb_engine** out) {
   knob("LGARB_WAVE_CORR_PAIRS", (*out)->wave_corr_pairs);
   knob("LGARB_WAVE_FINISH_BELOW", (*out)->wave_finish_below);
   knob("LGARB_FINISH_LANE_STRIDE", (*out)->finish_lane_stride);
+  knob("LGARB_UPDATE_WAVE_MIN_COLS", (*out)->update_wave_min_cols);
   knob("LGARB_WAVE_ESCALATE_BELOW", (*out)->wave_escalate_below);
   knob("LGARB_WAVE_CORR_QUANTUM", (*out)->wave_corr_quantum);
   knob("LGARB_RUN_QUANTUM", (*out)->run_inline_quantum);
@@ -816,9 +818,16 @@ int lgarb_update(lgarb_engine* e) {
     require_init(e);
     apply_calibration(e);
     update_frozen_factors(e);
-    LgarSinks sinks;
-    memset(&sinks, 0, sizeof(sinks));
-    launch_step(e, e->d_precip, e->d_pet, sinks);
+    if (e->use_window >= 3 && !e->pc.sft_coupled && e->ncol >= e->update_wave_min_cols) {
+      // Large batch: one forcing hour as a window of one step through the wavefront kernels.  The kernel pair below
+      // makes every active column of the hour wait for the slowest psi search in its warp; the stage kernels do not.
+      if (lgarb_update_steps_device(e, 1, e->d_precip, e->d_pet, e->stride, nullptr, e->stride, nullptr) != LGARB_SUCCESS)
+        throw std::runtime_error(e->last_error);
+    } else {
+      LgarSinks sinks;
+      memset(&sinks, 0, sizeof(sinks));
+      launch_step(e, e->d_precip, e->d_pet, sinks);
+    }
     CUDA_TRY(cudaStreamSynchronize(e->stream));
   });
 }

@@ -102,3 +102,82 @@ def test_scheduling_does_not_change_results(cuda_device, tmp_path):
         assert np.array_equal(m0, m1, equal_nan=True) and np.array_equal(v0, v1, equal_nan=True)
         for k in ("depth", "theta", "psi", "K", "dzdt", "layer", "to_bottom", "nfronts"):
             assert np.array_equal(f0[k], f1[k], equal_nan=True), k
+
+
+def test_full_size_shard_properties(cuda_device, oracle, tmp_path):
+    """BASELINE.json's bench size (one GPU's share of config 5: 1 250 000 columns) for 240 forcing hours, checked through
+    properties that do not need the oracle on every column: (a) columns are independent -- 3 000 of them re-run alone
+    in a small batch give bit-identical outputs, fronts and balances; (b) the global mass balance of every column
+    that was not frozen closes (|error| <= 1e-6 cm, the reference prints ~1e-7 after a year); (c) 400 of the re-run
+    columns are diffed against the oracle; (d) frozen columns are rare and are columns the oracle stops on too."""
+    import torch
+    import bench
+    import lgar_c_b200
+    ncol, T = 1_250_000, 240
+    cfg = bench.write_workload_config(tmp_path)
+    soils, layers = bench.column_soils(0, ncol), bench.column_layers(0, ncol)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(20261020)
+    u1 = torch.rand((T, ncol), generator=gen, device="cuda", dtype=torch.float64)
+    u2 = torch.rand((T, ncol), generator=gen, device="cuda", dtype=torch.float64)
+    dP = torch.where(u1 < 0.03, torch.clamp(-2.5 * torch.log1p(-u2), max=170.0), torch.zeros_like(u1))
+    del u1, u2
+    dE = torch.from_numpy(bench.pet_series(np.arange(T))).cuda()[:, None].expand(T, ncol).contiguous()
+    b = lgar_c_b200.BmiLGARBatch()
+    b.initialize(cfg, ncol, 0, soils, layers)
+    q = torch.zeros((T, ncol), dtype=torch.float64, device="cuda")
+    st_series = torch.zeros((T, ncol), dtype=torch.float64, device="cuda")
+    nfs = torch.zeros((T, ncol), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    b.update_steps_device(T, dP.data_ptr(), dE.data_ptr(), ncol, {"total_discharge": q.data_ptr(), "soil_storage": st_series.data_ptr()}, ncol, nfs.data_ptr())
+    b.synchronize()
+    status = b.get_status()
+    frozen = np.nonzero(status & lgar_c_b200.STATUS_FAIL_MASK)[0]
+    assert len(frozen) <= ncol // 20000, f"{len(frozen)} frozen columns"
+    # (b) every other column closes its global balance
+    worst = 0.0
+    for c0 in range(0, ncol, 250_000):
+        gm = b.get_global_mass_balance(c0, 250_000)
+        ok = (status[c0:c0 + 250_000] & lgar_c_b200.STATUS_FAIL_MASK) == 0
+        assert np.all(np.isfinite(gm[ok]))
+        worst = max(worst, float(np.abs(gm[ok, 15]).max()))
+    assert worst <= 1e-6, f"global mass balance error {worst:.3e} cm"
+    # (a) independence: a sample (plus the frozen columns) alone in a small batch
+    sample = np.unique(np.concatenate([np.random.default_rng(5).choice(ncol, 3000, replace=False), frozen]))
+    idx = torch.from_numpy(sample).cuda()
+    sP, sE = dP[:, idx].contiguous(), dE[:, idx].contiguous()
+    b2 = lgar_c_b200.BmiLGARBatch()
+    b2.initialize(cfg, len(sample), 0, soils[sample], layers[sample])
+    q2 = torch.zeros((T, len(sample)), dtype=torch.float64, device="cuda")
+    s2 = torch.zeros((T, len(sample)), dtype=torch.float64, device="cuda")
+    n2 = torch.zeros((T, len(sample)), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    b2.update_steps_device(T, sP.data_ptr(), sE.data_ptr(), len(sample), {"total_discharge": q2.data_ptr(), "soil_storage": s2.data_ptr()}, len(sample), n2.data_ptr())
+    b2.synchronize()
+    assert torch.equal(n2, nfs[:, idx])
+    assert np.array_equal(q2.cpu().numpy(), q[:, idx].cpu().numpy(), equal_nan=True)
+    assert np.array_equal(s2.cpu().numpy(), st_series[:, idx].cpu().numpy(), equal_nan=True)
+    assert np.array_equal(b2.get_status(), status[sample])
+    f1 = b2.get_fronts()
+    for c0 in range(0, len(sample), 1000):   # final fronts of the sample inside the big batch
+        for j in range(c0, min(c0 + 1000, len(sample)), 97):
+            fb = b.get_fronts(int(sample[j]), 1)
+            for k in ("depth", "theta", "psi", "K", "dzdt", "layer", "to_bottom", "nfronts"):
+                assert np.array_equal(fb[k][0], f1[k][j], equal_nan=True), (k, int(sample[j]))
+    # (c), (d) oracle on part of the sample and on every frozen column
+    hP, hE = sP.cpu().numpy(), sE.cpu().numpy()
+    hq, hn = q2.cpu().numpy(), n2.cpu().numpy()
+    pick = np.unique(np.concatenate([np.arange(0, len(sample), max(1, len(sample) // 400)), np.nonzero(np.isin(sample, frozen))[0]]))
+    for j in pick:
+        c = int(sample[j])
+        p = oracle.params_from_config(cfg, layer_soil_type=[int(x) for x in soils[c]], layer_thickness=[float(x) for x in layers[c]])
+        s = oracle.new_state(p)
+        r = oracle.run_series(p, s, hP[:, j], hE[:, j], cap=16, want_fronts=False)
+        done = r["done"]
+        if status[c] & lgar_c_b200.STATUS_FAIL_MASK:
+            assert done < T and (s.status & 0xFFFF) == (status[c] & 0xFFFF), f"column {c}: status {status[c]:#x} vs oracle {s.status:#x} at {done}"
+        else:
+            assert done == T, f"column {c}: oracle stopped at {done}"
+        assert np.array_equal(hn[:done, j], r["nfronts"][:done]), f"column {c}: front counts differ"
+        g, w = hq[:done, j], r["scalars"][:done, 6]
+        assert np.all(np.abs(g - w) <= 1e-9 * np.maximum(np.abs(g), np.abs(w)) + 1e-14), f"column {c}: total_discharge differs"
