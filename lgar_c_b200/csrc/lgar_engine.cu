@@ -611,10 +611,6 @@ void d2h(lgarb_engine* e, void* dst, const void* src, size_t bytes) {
   CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
 }
-void h2d(lgarb_engine* e, void* dst, const void* src, size_t bytes) {
-  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream));
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
-}
 
 int var_grid(const std::string& name) {  // bmi_lgar.cxx:1112-1154
   if (name == "soil_storage_model" || name == "soil_num_wetting_fronts") return 0;
