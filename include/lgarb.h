@@ -34,7 +34,7 @@ extern "C" {
 
 #define LGARB_SUCCESS 0
 #define LGARB_FAILURE 1
-#define LGARB_MAX_FRONTS 16 /* front capacity per column; overflow sets LGARB_STATUS_FRONT_OVERFLOW */
+#define LGARB_MAX_FRONTS 32 /* front capacity per column; overflow sets LGARB_STATUS_FRONT_OVERFLOW */
 #define LGARB_MAX_LAYERS 4
 #define LGARB_NUM_OUTPUT_SCALARS 12
 

@@ -14,7 +14,7 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-MAX_FRONTS = 16
+MAX_FRONTS = 32
 MAX_LAYERS = 4
 STATUS_FAIL_MASK = 0xFFFF
 OUTPUT_SCALARS = [

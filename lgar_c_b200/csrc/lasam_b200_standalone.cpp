@@ -228,8 +228,8 @@ int main(int argc, char** argv) {
     if (!o.forcing_bin.empty()) die("--layers reads the forcing CSV of the configuration file");
     const int64_t nf = (int64_t)E1.size();
     std::vector<double> p(N), pe(N), val(N);
-    std::vector<double> depth((size_t)N * 16), theta((size_t)N * 16), psi((size_t)N * 16);
-    std::vector<int32_t> layer((size_t)N * 16), nfr(N);
+    std::vector<double> depth((size_t)N * LGARB_MAX_FRONTS), theta((size_t)N * LGARB_MAX_FRONTS), psi((size_t)N * LGARB_MAX_FRONTS);
+    std::vector<int32_t> layer((size_t)N * LGARB_MAX_FRONTS), nfr(N);
     for (int64_t t = 0; t < nsteps; t++) {
       for (int64_t c = 0; c < N; c++) {
         const int64_t src = (t + c * o.shift) % nf;
@@ -252,7 +252,7 @@ int main(int argc, char** argv) {
         fprintf(flay[w], "# Timestep = %d, %s \n", (int)t, time[(t + c * o.shift) % nf].c_str());
         fprintf(flay[w], "[");
         for (int i = 0; i < nfr[c]; i++)  // write_state, bmi_main_lgar.cxx:266-283 (depth and psi in mm)
-          fprintf(flay[w], "%s(%lf,%lf,%d,%d,%lf)", i ? "|" : "", depth[c * 16 + i] * 10., theta[c * 16 + i], layer[c * 16 + i], i + 1, psi[c * 16 + i] * 10.);
+          fprintf(flay[w], "%s(%lf,%lf,%d,%d,%lf)", i ? "|" : "", depth[c * LGARB_MAX_FRONTS + i] * 10., theta[c * LGARB_MAX_FRONTS + i], layer[c * LGARB_MAX_FRONTS + i], i + 1, psi[c * LGARB_MAX_FRONTS + i] * 10.);
         fprintf(flay[w], "]\n");
       }
     }

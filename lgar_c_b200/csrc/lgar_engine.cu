@@ -102,6 +102,12 @@ struct lgarb_engine {
   LgarWave wave;
   bool wave_ready = false;
   int wave_quantum = 64, wave_pairs = 4, wave_corr_pairs = 1;
+  // correction searches on a side stream: the CORR kernel of a round (few slots, a long serial FP64 chain per slot) runs
+  // beside FETCH/HEAD/FRONT/SEARCH of the same round and is joined before TAIL; 0 = CORR and a second TAIL at the end of
+  // the round on the main stream
+  int wave_corr_async = 1;
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t side_ev[2] = {nullptr, nullptr};
   int wave_finish_below = 16384;
   int finish_lane_stride = 4;  // finishing kernel: one slot per this many lanes
   int update_wave_min_cols = 1 << 30;  // lgarb_update: batches of at least this many columns take the wavefront kernels
@@ -168,6 +174,12 @@ struct lgarb_engine {
     if (h_pinned) cudaFreeHost(h_pinned);
     h_pinned = nullptr;
     h_pinned_bytes = 0;
+    for (int i = 0; i < 2; i++) {
+      if (side_ev[i]) cudaEventDestroy(side_ev[i]);
+      side_ev[i] = nullptr;
+    }
+    if (side_stream) cudaStreamDestroy(side_stream);
+    side_stream = nullptr;
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
     initialized = false;
@@ -261,7 +273,7 @@ void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int d
   d.psi = e->dalloc<double>(st * LGAR_W);
   d.K = e->dalloc<double>(st * LGAR_W);
   d.dzdt = e->dalloc<double>(st * LGAR_W);
-  d.fflags = e->dalloc<unsigned long long>(st);
+  d.fflags = e->dalloc<unsigned long long>(st * LGAR_FW);
   d.nfront = e->dalloc<int32_t>(st);
   d.scal = e->dalloc<double>(st * LGAR_NSCAL);
   d.bits = e->dalloc<int32_t>(st);
@@ -418,9 +430,11 @@ void apply_calibration(lgarb_engine* e) {
 
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   std::vector<int32_t> nf((size_t)ncol);
-  std::vector<unsigned long long> fl((size_t)ncol);
+  std::vector<unsigned long long> fl((size_t)ncol * LGAR_FW);  // [word][column]
   CUDA_TRY(cudaMemcpy(nf.data(), e->d.nfront, (size_t)ncol * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(fl.data(), e->d.fflags, (size_t)ncol * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  for (int wd = 0; wd < LGAR_FW; wd++)
+    CUDA_TRY(cudaMemcpy(fl.data() + (size_t)wd * ncol, e->d.fflags + (size_t)wd * st, (size_t)ncol * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  auto nibble = [&](int64_t c, int i) { return (int)((fl[(size_t)(i >> 4) * ncol + c] >> (4 * (i & 15))) & 0xF); };
   int maxnf = 0;
   for (int64_t c = 0; c < ncol; c++) maxnf = std::max(maxnf, (int)nf[c]);
   std::vector<double> depth((size_t)maxnf * ncol), theta((size_t)maxnf * ncol), psi((size_t)maxnf * ncol);
@@ -433,11 +447,11 @@ void apply_calibration(lgarb_engine* e) {
     double sum = 0.0;
     const int n = nf[c];
     for (int i = 0; i < n; i++) {
-      const int li = (int)((fl[c] >> (4 * i)) & 7);
+      const int li = nibble(c, i) & 7;
       const double base = cum[li - 1];
       const double th = theta[(size_t)i * ncol + c], dp = depth[(size_t)i * ncol + c];
       if (i + 1 < n) {
-        const int ln = (int)((fl[c] >> (4 * (i + 1))) & 7);
+        const int ln = nibble(c, i + 1) & 7;
         if (ln == li) sum += (dp - base) * (th - theta[(size_t)(i + 1) * ncol + c]);
         else sum += (dp - base) * th;
       } else {
@@ -470,7 +484,7 @@ void apply_calibration(lgarb_engine* e) {
       for (int k = 1; k <= L; k++) rows[k] = e->soils[types[k - 1]];
       const double before = mass(c, old.cum);
       for (int i = 0; i < nf[c]; i++) {
-        const int layer = (int)((fl[c] >> (4 * i)) & 7);
+        const int layer = nibble(c, i) & 7;
         if (layer <= 3) {
           auto val = [&](int f) {
             const int idx = (layer - 1) * 5 + f;
@@ -769,6 +783,7 @@ int lgarb_create(lgarb_engine** out) {
   knob("LGARB_WAVE_QUANTUM", (*out)->wave_quantum);
   knob("LGARB_WAVE_PAIRS", (*out)->wave_pairs);
   knob("LGARB_WAVE_CORR_PAIRS", (*out)->wave_corr_pairs);
+  knob("LGARB_WAVE_CORR_ASYNC", (*out)->wave_corr_async);
   knob("LGARB_WAVE_FINISH_BELOW", (*out)->wave_finish_below);
   knob("LGARB_FINISH_LANE_STRIDE", (*out)->finish_lane_stride);
   knob("LGARB_UPDATE_WAVE_MIN_COLS", (*out)->update_wave_min_cols);
@@ -850,6 +865,10 @@ void ensure_wave(lgarb_engine* e) {
     for (int b = 0; b < 2; b++) wv.queue[s][b] = e->dalloc<int32_t>((size_t)wv.nslots, false);
   wv.qcount = e->dalloc<int32_t>(LGAR_NSTAGE * 2);
   wv.done_columns = e->dalloc<int32_t>(1);
+  if (!e->side_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->side_ev[i], cudaEventDisableTiming));
+  }
   e->wave_ready = true;
 }
 
@@ -887,6 +906,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
     }
   } ncu_stop{ncu_whole_window, e->stream};
   std::vector<std::pair<cudaEvent_t, int>> dbg_evs;
+  cudaStream_t launch_stream = e->stream;
   auto launch = [&](int stage) {
     const int consume = par[stage];
     par[stage] ^= 1;
@@ -899,7 +919,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       dbg_evs.back().second = stage;
     }
     CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, stage == LG_ST_CORR ? std::max(1, quantum * e->wave_corr_quantum / e->wave_quantum) : quantum, in_flight,
-                                    e->stream));
+                                    launch_stream));
     e->launches += 2;
   };
   auto launch_q = [&](int stage, int q) {  // SEARCH / CORR with an explicit quantum
@@ -979,6 +999,19 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       cudaProfilerStart();
     }
     const bool new_steps = cnt[LG_ST_FETCH] + cnt[LG_ST_HEAD] > 0;
+    const bool corr_async = e->use_window == 3 && e->wave_corr_async && !dbg_on;
+    bool corr_forked = false;
+    if (corr_async && cnt[LG_ST_CORR] > 0) {
+      // CORR consumes what TAIL queued in the previous round and appends to the TAIL queue; nothing else on the main
+      // stream touches the CORR queues before the join, and appends to the TAIL queue are atomic
+      CUDA_TRY(cudaEventRecord(e->side_ev[0], e->stream));
+      CUDA_TRY(cudaStreamWaitEvent(e->side_stream, e->side_ev[0], 0));
+      launch_stream = e->side_stream;
+      launch(LG_ST_CORR);
+      launch_stream = e->stream;
+      CUDA_TRY(cudaEventRecord(e->side_ev[1], e->side_stream));
+      corr_forked = true;
+    }
     if (e->use_window == 4) {
       // step kernel: FETCH, RUN (whole steps, searches inline up to the quantum), then the parked long searches
       // (compacted, `run_search_quantum` trips per launch) and the steps they hand back
@@ -1002,8 +1035,9 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       }
     }
     if (e->use_window != 4) {
+      if (corr_forked) CUDA_TRY(cudaStreamWaitEvent(e->stream, e->side_ev[1], 0));
       launch(LG_ST_TAIL);
-      for (int k = 0; k < e->wave_corr_pairs; k++) {
+      for (int k = 0; k < (corr_async ? 0 : e->wave_corr_pairs); k++) {
         launch(LG_ST_CORR);
         launch(LG_ST_TAIL);
       }
@@ -1456,11 +1490,12 @@ int lgarb_get_fronts(lgarb_engine* e, int64_t col0, int64_t ncol, double* depth_
     d2h(e, nf.data(), e->d.nfront + col0, (size_t)ncol * sizeof(int32_t));
     if (nfronts) memcpy(nfronts, nf.data(), (size_t)ncol * sizeof(int32_t));
     if (layer_num || to_bottom) {
-      std::vector<unsigned long long> fl((size_t)ncol);
-      d2h(e, fl.data(), e->d.fflags + col0, (size_t)ncol * sizeof(unsigned long long));
+      std::vector<unsigned long long> fl((size_t)ncol * LGAR_FW);  // [word][column]
+      for (int wd = 0; wd < LGAR_FW; wd++)
+        d2h(e, fl.data() + (size_t)wd * ncol, e->d.fflags + (size_t)wd * e->stride + col0, (size_t)ncol * sizeof(unsigned long long));
       for (int64_t c = 0; c < ncol; c++)
         for (int i = 0; i < LGAR_W; i++) {
-          int nib = (i < nf[c]) ? (int)((fl[c] >> (4 * i)) & 0xF) : 0;
+          int nib = (i < nf[c]) ? (int)((fl[(size_t)(i >> 4) * ncol + c] >> (4 * (i & 15))) & 0xF) : 0;
           if (layer_num) layer_num[c * LGAR_W + i] = (i < nf[c]) ? (nib & 7) : 0;
           if (to_bottom) to_bottom[c * LGAR_W + i] = (i < nf[c]) ? (nib >> 3) : 0;
         }

@@ -327,17 +327,21 @@ struct alignas(32) LgLaneSlot {
 };
 
 // Parts of the lane record (lgar_lanes.cuh) a stage moves between HBM and its thread-private copy.  The front
-// arrays have capacity LGAR_W = 16 but a column carries 4-5 fronts on average: only the live prefix of each
+// arrays have capacity LGAR_W = 32 but a column carries 4-5 fronts on average: only the live prefix of each
 // array travels (counts kept in the record's first sector), which removes about a third of the context traffic.
 enum { LG_PART_STATE = 1, LG_PART_STEP = 2, LG_PART_OLD = 4, LG_PART_SEARCH = 8, LG_PART_ALL = 15 };
 constexpr int kOffF = (int)offsetof(LgLane, f), kOffPro = (int)offsetof(LgLane, pro), kOffOld = (int)offsetof(LgLane, old),
               kOffQ = (int)offsetof(LgLane, q);
 constexpr int kFrontTail = (int)offsetof(LgFronts, layer);  // layer[], tb[], n behind the five double arrays
 static_assert(kOffF % 32 == 0 && kOffPro % 32 == 0 && kOffOld % 32 == 0 && kOffQ % 32 == 0 && sizeof(LgLaneSlot) % 32 == 0, "LgLane layout");
-static_assert(offsetof(LgFronts, depth) == 0 && offsetof(LgFronts, theta) == 128 && offsetof(LgFronts, psi) == 256 && offsetof(LgFronts, K) == 384 &&
-                  offsetof(LgFronts, dzdt) == 512 && kFrontTail == 640 && kOffPro - kOffF - kFrontTail == 64 && LGAR_W == 16,
+constexpr int kPitch = 8 * LGAR_W;                           // bytes between the arrays of LgFronts / LgOld
+constexpr int kFrontTailBytes = kOffPro - kOffF - kFrontTail;  // layer[], tb[], n (+ padding up to `pro`)
+static_assert(offsetof(LgFronts, depth) == 0 && offsetof(LgFronts, theta) == kPitch && offsetof(LgFronts, psi) == 2 * kPitch &&
+                  offsetof(LgFronts, K) == 3 * kPitch && offsetof(LgFronts, dzdt) == 4 * kPitch && kFrontTail == 5 * kPitch &&
+                  kFrontTailBytes % 32 == 0 && kFrontTailBytes >= 2 * LGAR_W + 4 && kPitch % 32 == 0,
               "LgFronts layout");
-static_assert(offsetof(LgOld, theta) == 128 && offsetof(LgOld, psi) == 256 && offsetof(LgOld, n) == 384 && kOffQ - kOffOld == 416, "LgOld layout");
+static_assert(offsetof(LgOld, theta) == kPitch && offsetof(LgOld, psi) == 2 * kPitch && offsetof(LgOld, n) == 3 * kPitch && kOffQ - kOffOld == 3 * kPitch + 32,
+              "LgOld layout");
 static_assert(offsetof(LgLane, nold_stored) < 32, "front counts must sit in the first sector of the record");
 
 template <int PARTS>
@@ -349,14 +353,14 @@ __device__ __forceinline__ void lane_load(LgLaneSlot* S, const LgLaneSlot* G) {
   if (PARTS & LG_PART_STATE) {
     ctx_load<kOffF - 32>(reinterpret_cast<LgLaneSlot*>(l + 32), reinterpret_cast<const LgLaneSlot*>(g + 32));
 #pragma unroll
-    for (int a = 0; a < 5; a++) ctx_load_n(l + kOffF + 128 * a, g + kOffF + 128 * a, cf);
-    ctx_load<64>(reinterpret_cast<LgLaneSlot*>(l + kOffF + kFrontTail), reinterpret_cast<const LgLaneSlot*>(g + kOffF + kFrontTail));
+    for (int a = 0; a < 5; a++) ctx_load_n(l + kOffF + kPitch * a, g + kOffF + kPitch * a, cf);
+    ctx_load<kFrontTailBytes>(reinterpret_cast<LgLaneSlot*>(l + kOffF + kFrontTail), reinterpret_cast<const LgLaneSlot*>(g + kOffF + kFrontTail));
   }
   if (PARTS & LG_PART_STEP) ctx_load<kOffOld - kOffPro>(reinterpret_cast<LgLaneSlot*>(l + kOffPro), reinterpret_cast<const LgLaneSlot*>(g + kOffPro));
   if (PARTS & LG_PART_OLD) {
 #pragma unroll
-    for (int a = 0; a < 3; a++) ctx_load_n(l + kOffOld + 128 * a, g + kOffOld + 128 * a, co);
-    ctx_load<32>(reinterpret_cast<LgLaneSlot*>(l + kOffOld + 384), reinterpret_cast<const LgLaneSlot*>(g + kOffOld + 384));
+    for (int a = 0; a < 3; a++) ctx_load_n(l + kOffOld + kPitch * a, g + kOffOld + kPitch * a, co);
+    ctx_load<32>(reinterpret_cast<LgLaneSlot*>(l + kOffOld + 3 * kPitch), reinterpret_cast<const LgLaneSlot*>(g + kOffOld + 3 * kPitch));
   }
   if (PARTS & LG_PART_SEARCH)
     ctx_load<(int)sizeof(LgLaneSlot) - kOffQ>(reinterpret_cast<LgLaneSlot*>(l + kOffQ), reinterpret_cast<const LgLaneSlot*>(g + kOffQ));
@@ -378,14 +382,14 @@ __device__ __forceinline__ void lane_store(LgLaneSlot* G, LgLaneSlot* S) {
   if (PARTS & LG_PART_STATE) {
     ctx_store<kOffF - 32>(reinterpret_cast<LgLaneSlot*>(g + 32), reinterpret_cast<const LgLaneSlot*>(l + 32));
 #pragma unroll
-    for (int a = 0; a < 5; a++) ctx_store_n(g + kOffF + 128 * a, l + kOffF + 128 * a, cf);
-    ctx_store<64>(reinterpret_cast<LgLaneSlot*>(g + kOffF + kFrontTail), reinterpret_cast<const LgLaneSlot*>(l + kOffF + kFrontTail));
+    for (int a = 0; a < 5; a++) ctx_store_n(g + kOffF + kPitch * a, l + kOffF + kPitch * a, cf);
+    ctx_store<kFrontTailBytes>(reinterpret_cast<LgLaneSlot*>(g + kOffF + kFrontTail), reinterpret_cast<const LgLaneSlot*>(l + kOffF + kFrontTail));
   }
   if (PARTS & LG_PART_STEP) ctx_store<kOffOld - kOffPro>(reinterpret_cast<LgLaneSlot*>(g + kOffPro), reinterpret_cast<const LgLaneSlot*>(l + kOffPro));
   if (PARTS & LG_PART_OLD) {
 #pragma unroll
-    for (int a = 0; a < 3; a++) ctx_store_n(g + kOffOld + 128 * a, l + kOffOld + 128 * a, co);
-    ctx_store<32>(reinterpret_cast<LgLaneSlot*>(g + kOffOld + 384), reinterpret_cast<const LgLaneSlot*>(l + kOffOld + 384));
+    for (int a = 0; a < 3; a++) ctx_store_n(g + kOffOld + kPitch * a, l + kOffOld + kPitch * a, co);
+    ctx_store<32>(reinterpret_cast<LgLaneSlot*>(g + kOffOld + 3 * kPitch), reinterpret_cast<const LgLaneSlot*>(l + kOffOld + 3 * kPitch));
   }
   if (PARTS & LG_PART_SEARCH)
     ctx_store<(int)sizeof(LgLaneSlot) - kOffQ>(reinterpret_cast<LgLaneSlot*>(g + kOffQ), reinterpret_cast<const LgLaneSlot*>(l + kOffQ));
@@ -448,15 +452,15 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         struct alignas(32) FrontsBuf { LgFronts f; } fb;
         char* l = reinterpret_cast<char*>(&fb);
         char* g = reinterpret_cast<char*>(&G.f);
-        ctx_load<64>(reinterpret_cast<FrontsBuf*>(l + kFrontTail), reinterpret_cast<const FrontsBuf*>(g + kFrontTail));
+        ctx_load<kFrontTailBytes>(reinterpret_cast<FrontsBuf*>(l + kFrontTail), reinterpret_cast<const FrontsBuf*>(g + kFrontTail));
         const int cf = (fb.f.n + 3) >> 2;
 #pragma unroll
-        for (int a = 0; a < 3; a++) ctx_load_n(l + 128 * a, g + 128 * a, cf);
+        for (int a = 0; a < 3; a++) ctx_load_n(l + kPitch * a, g + kPitch * a, cf);
         const LgarColumnClass* cls = G.cls;
         for (int it = 0; it < quantum && !k.done; it++) lg_corr_iter(k, fb.f, *cls);
         G.k = k;
 #pragma unroll
-        for (int a = 1; a < 3; a++) ctx_store_n(g + 128 * a, l + 128 * a, cf);
+        for (int a = 1; a < 3; a++) ctx_store_n(g + kPitch * a, l + kPitch * a, cf);
         next = k.done ? LG_ST_TAIL : LG_ST_CORR;
       }
     } else if (STAGE == LG_ST_FETCH) {

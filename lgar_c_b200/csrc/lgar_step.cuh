@@ -60,17 +60,18 @@ LG_FN_NOINLINE void store_scalars(const LgarDeviceState& d, int64_t col, const L
 
 LG_FN_NOINLINE void load_fronts(const LgarDeviceState& d, int64_t col, LgFronts& f) {
   const int n = d.nfront[col];
-  const unsigned long long fl = d.fflags[col];
+  unsigned long long fl = d.fflags[col];
   f.n = n;
 #pragma unroll 1
   for (int i = 0; i < n; i++) {
+    if (i && !(i & 15)) fl = d.fflags[(int64_t)(i >> 4) * d.stride + col];
     const int64_t o = (int64_t)i * d.stride + col;
     f.depth[i] = d.depth[o];
     f.theta[i] = d.theta[o];
     f.psi[i] = d.psi[o];
     f.K[i] = d.K[o];
     f.dzdt[i] = d.dzdt[o];
-    const int nib = (int)((fl >> (4 * i)) & 0xF);
+    const int nib = (int)((fl >> (4 * (i & 15))) & 0xF);
     f.layer[i] = (signed char)(nib & 7);
     f.tb[i] = (signed char)(nib >> 3);
   }
@@ -86,9 +87,13 @@ LG_FN_NOINLINE void store_fronts(const LgarDeviceState& d, int64_t col, const Lg
     d.psi[o] = f.psi[i];
     d.K[o] = f.K[i];
     d.dzdt[o] = f.dzdt[i];
-    fl |= (unsigned long long)((f.layer[i] & 7) | ((f.tb[i] ? 1 : 0) << 3)) << (4 * i);
+    if (i && !(i & 15)) {
+      d.fflags[(int64_t)((i >> 4) - 1) * d.stride + col] = fl;
+      fl = 0ull;
+    }
+    fl |= (unsigned long long)((f.layer[i] & 7) | ((f.tb[i] ? 1 : 0) << 3)) << (4 * (i & 15));
   }
-  d.fflags[col] = fl;
+  d.fflags[(int64_t)(f.n > 0 ? (f.n - 1) >> 4 : 0) * d.stride + col] = fl;
   d.nfront[col] = f.n;
 }
 

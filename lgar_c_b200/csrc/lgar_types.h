@@ -13,7 +13,10 @@
 
 #include <stdint.h>
 
-#define LGAR_W 16        // front capacity per column (reference max observed: 14)
+#define LGAR_W 32        // front capacity per column.  The shipped configs stay below 15, but a full year of
+                         // BASELINE config 5 reaches 19 fronts in a 10 000-column sample (tools/parity_sampling_full.py; the
+                         // tail falls by ~2.3x per front, so ~27 over 10 M columns): 16 froze 0.2 % of the columns.
+#define LGAR_FW (LGAR_W / 16)  // 64-bit flag words per column (16 nibbles each)
 #define LGAR_MAXL 4      // soil layers per column (reference MAX_NUM_SOIL_LAYERS, all.hxx:38)
 #define LGAR_MAXG 32     // GIUH ordinates after re-sampling (lgar.cxx:918-929)
 #define LGAR_NOUT 12     // per-step scalar outputs (bmi_lgar.hxx:168-181)
@@ -107,7 +110,7 @@ struct LgarDeviceState {
   int64_t ncol, stride;
   // fronts [LGAR_W][stride]
   double *depth, *theta, *psi, *K, *dzdt;
-  unsigned long long* fflags;   // [stride] 16 nibbles: layer | to_bottom<<3 for slot i at bits 4i..4i+3
+  unsigned long long* fflags;   // [LGAR_FW][stride] nibbles layer | to_bottom<<3: front i in word i/16 at bits 4(i%16)..4(i%16)+3
   int32_t* nfront;              // [stride]
   double* scal;                 // [LGAR_NSCAL][stride]
   int32_t* bits;                // [stride] bit0 cache_fluxes, bit1 runoff_in_prev_step, bits 8..15 cache_count

@@ -349,8 +349,11 @@ def write_config(base_config, out_path, **replace) -> Path:
 class RefHarness:
     """The unmodified reference behind oracle/ref_harness.cpp."""
 
-    def __init__(self):
-        so = HERE / "_ref" / "liblgar_ref.so"
+    def __init__(self, so=None):
+        if so is not None:
+            so = Path(so)
+        else:
+            so = HERE / "_ref" / "liblgar_ref.so"
         if not so.exists():
             so = build_ref()
         if so is None or not Path(so).exists():

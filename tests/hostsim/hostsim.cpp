@@ -34,14 +34,15 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
     const int64_t st = 1;
     std::vector<double> depth(LGAR_W), theta(LGAR_W), psi(LGAR_W), K(LGAR_W), dzdt(LGAR_W), scal(LGAR_NSCAL), giuhq(LGAR_MAXG), cum(LGAR_NCUM),
         out(LGAR_NOUT);
-    unsigned long long fflags = 0;
+    unsigned long long fflags_w[LGAR_FW] = {0};  // stride 1: word w of the column at fflags_w[w]
+    unsigned long long& fflags = fflags_w[0];
     int32_t nf = 0, bits = 1 << 8, status = 0, class_id = 0, work[1], work_count[2];
     double p1, e1;
     LgarDeviceState d;
     memset(&d, 0, sizeof(d));
     d.ncol = 1; d.stride = st;
     d.depth = depth.data(); d.theta = theta.data(); d.psi = psi.data(); d.K = K.data(); d.dzdt = dzdt.data();
-    d.fflags = &fflags; d.nfront = &nf; d.scal = scal.data(); d.bits = &bits; d.status = &status; d.class_id = &class_id;
+    d.fflags = fflags_w; d.nfront = &nf; d.scal = scal.data(); d.bits = &bits; d.status = &status; d.class_id = &class_id;
     d.giuhq = giuhq.data(); d.cum = cum.data(); d.out = out.data(); d.classes = &cls; d.precip = &p1; d.pet = &e1;
     d.work = work; d.work_count = work_count;
     if (!cls.invalid_soil_type) {
@@ -103,7 +104,7 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
         for (int i = 0; i < nf && i < cap; i++) {
           double* q = fronts + ((size_t)t * cap + i) * 5;
           q[0] = depth[i]; q[1] = theta[i]; q[2] = psi[i]; q[3] = K[i]; q[4] = dzdt[i];
-          int nib = (int)((fflags >> (4 * i)) & 0xF);
+          int nib = (int)((fflags_w[i >> 4] >> (4 * (i & 15))) & 0xF);
           flags[(size_t)t * cap + i] = (nib & 7) | ((nib >> 3) << 8);
         }
       }
@@ -120,7 +121,7 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
         for (int i = 0; i < nf && i < cap; i++) {
           double* q = fronts + ((size_t)t * cap + i) * 5;
           q[0] = depth[i]; q[1] = theta[i]; q[2] = psi[i]; q[3] = K[i]; q[4] = dzdt[i];
-          int nib = (int)((fflags >> (4 * i)) & 0xF);
+          int nib = (int)((fflags_w[i >> 4] >> (4 * (i & 15))) & 0xF);
           flags[(size_t)t * cap + i] = (nib & 7) | ((nib >> 3) << 8);
         }
       }

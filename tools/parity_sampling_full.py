@@ -20,6 +20,9 @@ soils / layering / forcing depend on its GLOBAL index in the config only, so the
 
 Test infrastructure: this is one of the places that may execute oracle/.  --selftest replaces the engine by the
 unmodified reference (oracle/_ref) on a tiny sample so that the bookkeeping can be exercised without a GPU.
+--selfnoise replaces it by the SAME unmodified reference sources compiled with FMA contraction allowed
+(oracle/_ref/liblgar_ref_fma.so, `make -C oracle ref_fma`): the deviations it reports are those between two legitimate
+builds of the reference itself -- the floor under the 1e-9 bar.
 """
 from __future__ import annotations
 
@@ -288,27 +291,28 @@ def run_engine(cfgobj: Config, ids: np.ndarray, pos: np.ndarray, T: int, chunk: 
     return hP, hE, scal, nf, status_all[pos], final, info
 
 
-def run_selftest(cfgobj: Config, sample: np.ndarray, T: int):
-    """No GPU: the 'engine' is the unmodified reference (oracle/_ref)."""
+def _ref_worker(rng_):
+    """columns [j0, j1) of the sample through one build of the unmodified reference"""
     from oracle.oracle_py import RefHarness
-    ref = RefHarness()
-    ns = len(sample)
-    import torch
-    hP, hE = (x.numpy() for x in cfgobj.forcing(torch.from_numpy(sample), 0, T))
-    scal = np.empty((T, 12, ns))
-    nf = np.empty((T, ns), dtype=np.int32)
-    final = {k: np.zeros((ns, 16)) for k in ("depth", "theta", "psi", "K", "dzdt")}
-    final.update(layer=np.zeros((ns, 16), dtype=np.int32), to_bottom=np.zeros((ns, 16), dtype=np.int32), nfronts=np.zeros(ns, dtype=np.int32))
-    soils, layers = cfgobj.soils(sample), cfgobj.layers(sample)
+    j0, j1 = rng_
+    cfgobj, sample, hP, hE, so = _G["cfg"], _G["sample"], _G["hP"], _G["hE"], _G["ref_so"]
+    ref = RefHarness(so)
+    T = hP.shape[0]
+    n_ = j1 - j0
+    scal = np.empty((T, 12, n_))
+    nf = np.empty((T, n_), dtype=np.int32)
+    final = {k: np.zeros((n_, 32)) for k in ("depth", "theta", "psi", "K", "dzdt")}
+    final.update(layer=np.zeros((n_, 32), dtype=np.int32), to_bottom=np.zeros((n_, 32), dtype=np.int32), nfronts=np.zeros(n_, dtype=np.int32))
+    soils, layers = cfgobj.soils(sample[j0:j1]), cfgobj.layers(sample[j0:j1])
     tmp = Path(tempfile.mkdtemp())
-    for j in range(ns):
+    for j in range(n_):
         rep = {}
         if soils is not None:
             rep["layer_soil_type"] = ",".join(map(str, soils[j]))
         if layers is not None:
             rep["layer_thickness"] = ",".join(map(str, layers[j])) + "[cm]"
-        h = ref.create(write_config(cfgobj.cfg, tmp / f"c{j}.txt", **rep))
-        r = ref.run_series(h, hP[:, j], hE[:, j], cap=16)
+        h = ref.create(write_config(cfgobj.cfg, tmp / f"c{j0 + j}.txt", **rep))
+        r = ref.run_series(h, hP[:, j0 + j], hE[:, j0 + j], cap=32)
         assert r["done"] == T
         scal[:, :, j], nf[:, j] = r["scalars"], r["nfronts"]
         n = int(r["nfronts"][-1])
@@ -318,7 +322,24 @@ def run_selftest(cfgobj: Config, sample: np.ndarray, T: int):
         final["layer"][j, :n] = r["flags"][-1][:n] & 0xFF
         final["to_bottom"][j, :n] = r["flags"][-1][:n] >> 8
         ref.destroy(h)
-    return hP, hE, scal, nf, np.zeros(ns, dtype=np.int32), final, dict(batch_columns=ns, engine="oracle/_ref (selftest)")
+    return scal, nf, final
+
+
+def run_selftest(cfgobj: Config, sample: np.ndarray, T: int, so=None, cores=1):
+    """No GPU: the 'engine' is the unmodified reference (oracle/_ref), or with `so` another build of it."""
+    import torch
+    ns = len(sample)
+    hP, hE = (x.numpy() for x in cfgobj.forcing(torch.from_numpy(sample), 0, T))
+    _G.update(cfg=cfgobj, sample=sample, hP=hP, hE=hE, ref_so=so)
+    step = max(1, (ns + 4 * cores - 1) // (4 * cores))
+    jobs = [(j, min(j + step, ns)) for j in range(0, ns, step)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        parts = pool.map(_ref_worker, jobs)
+    scal = np.concatenate([p[0] for p in parts], axis=2)
+    nf = np.concatenate([p[1] for p in parts], axis=1)
+    final = {k: np.concatenate([p[2][k] for p in parts], axis=0) for k in parts[0][2]}
+    name = "oracle/_ref (selftest)" if so is None else f"unmodified reference, other build: {Path(so).name}"
+    return hP, hE, scal, nf, np.zeros(ns, dtype=np.int32), final, dict(batch_columns=ns, engine=name)
 
 
 def main():
@@ -331,6 +352,9 @@ def main():
     ap.add_argument("--mode", type=int, default=3)
     ap.add_argument("--cores", type=int, default=0)
     ap.add_argument("--selftest", action="store_true")
+    ap.add_argument("--selfnoise", action="store_true",
+                    help="no GPU: diff the reference built with FMA contraction (make -C oracle ref_fma) against the oracle -- how far two "
+                         "legitimate builds of the reference itself drift apart on the same sample")
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "parity_full.json"))
     a = ap.parse_args()
     cores = a.cores or bench.host_cores()
@@ -341,8 +365,9 @@ def main():
         c = Config(num, tmp)
         T = a.steps or c.steps
         sample = np.sort(np.random.default_rng(99).choice(c.n_total, a.sample, replace=False)).astype(np.int64)
-        if a.selftest:
-            hP, hE, scal, nf, status, final, info = run_selftest(c, sample, T)
+        if a.selftest or a.selfnoise:
+            so = ROOT / "oracle" / "_ref" / "liblgar_ref_fma.so" if a.selfnoise else None
+            hP, hE, scal, nf, status, final, info = run_selftest(c, sample, T, so, cores)
         else:
             filler = np.random.default_rng(100 + num).choice(c.n_total, max(0, a.batch - a.sample), replace=False).astype(np.int64)
             ids = np.unique(np.concatenate([sample, filler]))
