@@ -12,8 +12,9 @@ LGAR + nonlinear reservoir + GIUH, closed-form G, adaptive sub-step, flux cachin
 forcing: wet hour with probability 0.03, intensity Exp(mean 2.5 mm/h) capped at 170, PET =
 0.21*max(0,1+cos(2pi(h-14)/24))*(1+0.5 sin(2pi d/365)) mm/h.
 
-A bench "step" is one simulated day: --hours-per-step (24) consecutive Update() calls over every
-column of the rank.  Before warm-up every column is spun up for --spinup-hours so that the timed
+A bench "step" is two simulated days: --hours-per-step (48) consecutive Update() calls over every
+column of the rank; the timed region is ONE multi-step call of steps x 48 hours (throughput grows with
+the length of the call, DESIGN.md section 7: 2.8e8 at 48 h, 4.2e8 at 240 h, 4.9e8 at 480 h).  Before warm-up every column is spun up for --spinup-hours so that the timed
 region sees a developed wetting-front population rather than the 3-front initial state.
 
 value   = column-timesteps / s, device-timed (CUDA events on the engine's stream), forcing resident
@@ -44,6 +45,9 @@ DATA = ROOT / "data"
 PH_LAYERS = (44.0, 131.0, 25.0)   # data/configs/config_lasam_Phillipsburg.txt
 BU_LAYERS = (18.0, 76.0, 135.0)   # data/configs/config_lasam_Bushland.txt
 N_GIUH = 5
+# DRAM bytes per column-timestep of the default scheduler: ncu over every launch of one timed window (profiles/, see the
+# roofline block in main)
+TRAFFIC_B_PER_UNIT = 3152.8
 
 
 # --------------------------------------------------------------------------------------------------
@@ -242,9 +246,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--columns", type=int, default=1_250_000, help="columns per GPU")
-    ap.add_argument("--hours-per-step", type=int, default=24)
+    ap.add_argument("--hours-per-step", type=int, default=48)
     ap.add_argument("--spinup-hours", type=int, default=720)
-    ap.add_argument("--e2e-hours", type=int, default=240)
+    ap.add_argument("--e2e-hours", type=int, default=384)
+    ap.add_argument("--e2e-chunks", type=int, default=2, help="chunks of the streamed host-buffer call")
     ap.add_argument("--cpu-cols-per-core", type=int, default=2048)
     ap.add_argument("--cpu-hours", type=int, default=2880)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -385,7 +390,7 @@ def main():
         # the multi-step verb with HOST buffers: forcing of `nh` hours in from pinned host memory, one output
         # series (total_discharge, ngen's usual main_output_variable) back to pinned host memory, all inside
         nh = min(args.e2e_hours, R * H)
-        nh2 = min(2 * nh, R * H)          # the streamed call runs over more hours; one set of pinned buffers serves both
+        nh2 = nh                           # the streamed call runs over the same hours; one set of pinned buffers serves both
         hP = torch.empty((nh2, ncol), dtype=torch.float64).pin_memory()
         hE = torch.empty((nh2, ncol), dtype=torch.float64).pin_memory()
         hP.copy_(dP[:nh2])
@@ -401,9 +406,9 @@ def main():
         if dist is not None:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         single = world * ncol * nh / float(t_e.item())
-        # the streamed verb: nh2 hours in two chunks, the forcing copy of the second chunk and the output copy of
-        # the first overlap the computation (lgarb_update_steps_host_stream)
-        ch2 = (nh2 + 1) // 2
+        # the streamed verb: nh2 hours in chunks, the forcing copy of the next chunk and the output copy of the
+        # previous one overlap the computation (lgarb_update_steps_host_stream)
+        ch2 = (nh2 + args.e2e_chunks - 1) // max(1, args.e2e_chunks)
         # warm-up: allocates the two staging buffers per direction (chunk-sized) and the copy streams
         b.update_steps_host_stream(hP.numpy()[:ch2 + 1], hE.numpy()[:ch2 + 1], {"total_discharge": hQ.numpy()[:ch2 + 1]}, chunk_steps=ch2)
         barrier()
@@ -419,7 +424,7 @@ def main():
                "h2d_bytes_per_step": 2 * 8 * ncol * H, "d2h_bytes_per_step": 8 * ncol * H,
                "verb": "lgarb_update_steps_host_stream" if streamed >= single else "lgarb_update_steps_host",
                "single_call": {"value": single, "hours_per_call": nh, "verb": "lgarb_update_steps_host"},
-               "streamed": {"value": streamed, "hours_per_call": nh2, "chunk_hours": (nh2 + 1) // 2, "verb": "lgarb_update_steps_host_stream"},
+               "streamed": {"value": streamed, "hours_per_call": nh2, "chunk_hours": ch2, "verb": "lgarb_update_steps_host_stream"},
                "note": "precipitation_rate + potential_evapotranspiration_rate series from pinned host memory, total_discharge series back to "
                        "pinned host memory, all copies inside the timed call; single_call copies, computes, copies back; streamed overlaps the "
                        "copies of neighbouring chunks with the computation; value = the faster of the two public verbs; bytes are per bench "
@@ -479,7 +484,7 @@ def main():
     # DRAM bytes per launch unit from the committed ncu capture of one whole timed window of this command in mode 3
     # (profiles/r1_session2_ncu_summary.md section 1: dram__bytes_read.sum + dram__bytes_write.sum over the 2 706 launches
     # of a 240 h window of 1.25 M columns = 945.8 GB = 3 153 B per column-timestep); null for any other configuration
-    traffic = 3152.8 * units if (args.mode == 3 and ms_w > 0 and H == 24) else None
+    traffic = TRAFFIC_B_PER_UNIT * units if (args.mode == 3 and ms_w > 0) else None
     share_ncu = ({"TAIL": 0.291, "SEARCH": 0.157, "HEAD": 0.151, "FRONT": 0.112, "FETCH": 0.098, "finish": 0.095, "CORR": 0.088}
                  if (args.mode == 3 and ms_w > 0) else None)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -487,10 +492,18 @@ def main():
                 "stage_time_share_ncu": share_ncu, "peak_source": peak_src, "algorithmic_bytes_per_unit": B_unit,
                 "units_per_launch": units, "avg_launch_ms": dur_s * 1e3, "kernel_time_share": share,
                 "mean_fronts": mean_fronts, "active_fraction": active_frac,
-                "note": "unit = one column-timestep; a launch = one bench step (one simulated day of every column; the stage kernels of a "
+                "note": "unit = one column-timestep; a launch = one bench step (--hours-per-step forcing hours of every column; the stage kernels of a "
                         "window are timed together with CUDA events on the engine stream); B = 88*mean_fronts + 428 bytes (SURVEY.md 8d). "
                         "Measured DRAM traffic is 4x the algorithmic bytes (step contexts crossing HBM at every stage boundary); the path is "
                         "latency/divergence bound, not HBM bound: DESIGN.md section 4.4"}
+
+    # secondary roofline: FP64 pipe peak from a DFMA microbenchmark on this GPU; what the stage kernels use of
+    # it is an ncu counter (sm__inst_executed_pipe_fp64, profiles/): 38 % in SEARCH, below 15 % elsewhere
+    try:
+        roofline["fp64_peak_tflops_measured"] = b.measure_fp64_peak(40.0)
+    except Exception as ex:  # diagnostics only
+        roofline["fp64_peak_tflops_measured"] = None
+        print(f"bench.py: DFMA microbenchmark failed: {ex}", file=sys.stderr)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

@@ -241,6 +241,9 @@ int lgarb_set_profiling(lgarb_engine* e, int on);
 int lgarb_get_profile(lgarb_engine* e, double* out6);
 /* the CUDA stream the engine launches on (cudaStream_t), for callers that time with events */
 void* lgarb_get_stream(lgarb_engine* e);
+/* FP64 roofline denominator ("not in MEASURED_PEAKS"): dependent-free DFMA chains on every SM of the
+ * engine's device for about `ms` milliseconds; *tflops = 2 * DFMAs / time, timed with CUDA events. */
+int lgarb_measure_fp64_peak(lgarb_engine* e, double ms, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -116,6 +116,7 @@ def _load():
         "lgarb_get_launch_count": ([vp], i64),
         "lgarb_get_last_active_count": ([vp], i64),
         "lgarb_get_stream": ([vp], vp),
+        "lgarb_measure_fp64_peak": ([vp, C.c_double, dp], C.c_int),
         "lgarb_set_profiling": ([vp, C.c_int], C.c_int),
         "lgarb_get_profile": ([vp, dp], C.c_int),
     }
@@ -448,6 +449,12 @@ class BmiLGARBatch:
         self._ck(self._L.lgarb_get_profile(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
         return dict(ms_stream=out[0], ms_active=out[1], steps=int(out[2]), active_colsteps=int(out[3]), front_sum=int(out[4]),
                     ms_window=out[5])
+
+    def measure_fp64_peak(self, ms: float = 50.0) -> float:
+        """DFMA microbenchmark on the engine's device: TFLOP/s of the FP64 pipe (secondary roofline)."""
+        out = C.c_double(0.0)
+        self._ck(self._L.lgarb_measure_fp64_peak(self._h, float(ms), C.byref(out)))
+        return out.value
 
     def get_stream(self) -> int:
         return int(self._L.lgarb_get_stream(self._h) or 0)

@@ -865,6 +865,7 @@ void ensure_wave(lgarb_engine* e) {
     for (int b = 0; b < 2; b++) wv.queue[s][b] = e->dalloc<int32_t>((size_t)wv.nslots, false);
   wv.qcount = e->dalloc<int32_t>(LGAR_NSTAGE * 2);
   wv.done_columns = e->dalloc<int32_t>(1);
+  wv.cursor = e->dalloc<int32_t>(1);
   if (!e->side_stream) {
     CUDA_TRY(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->side_ev[i], cudaEventDisableTiming));
@@ -966,7 +967,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
   int cnt[LGAR_NSTAGE] = {wv.nslots, 0, 0, 0, 0, 0};
   for (int64_t round = 0;; round++) {
     if (round > 0) {
-      CUDA_TRY(cudaMemcpyAsync(h_cnt, wv.qcount, 2 * LGAR_NSTAGE * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(lgar_launch_wave_poll(wv, h_cnt, e->stream));
       CUDA_TRY(cudaStreamSynchronize(e->stream));
       in_flight = 0;
       for (int s = 0; s < LGAR_NSTAGE; s++) {
@@ -1643,5 +1644,40 @@ int lgarb_get_profile(lgarb_engine* e, double* out6) {
 }
 
 void* lgarb_get_stream(lgarb_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int lgarb_measure_fp64_peak(lgarb_engine* e, double ms, double* tflops) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (!tflops) throw std::runtime_error("null result pointer");
+    int sms = 148;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+    const int blocks = sms * 8;
+    double* sink = e->d_stage;  // any device double; the kernel never writes it in practice
+    cudaEvent_t ev[2];
+    CUDA_TRY(cudaEventCreate(&ev[0]));
+    CUDA_TRY(cudaEventCreate(&ev[1]));
+    auto run = [&](int iters) {
+      CUDA_TRY(cudaEventRecord(ev[0], e->stream));
+      CUDA_TRY(lgar_launch_dfma(sink, blocks, iters, e->stream));
+      CUDA_TRY(cudaEventRecord(ev[1], e->stream));
+      CUDA_TRY(cudaEventSynchronize(ev[1]));
+      float t = 0;
+      CUDA_TRY(cudaEventElapsedTime(&t, ev[0], ev[1]));
+      return (double)t;
+    };
+    run(256);  // warm-up
+    int iters = 2048;
+    double t = run(iters);
+    const double want = ms > 0 ? ms : 50.0;
+    if (t > 0 && t < want) {
+      iters = (int)std::min<double>(1e8, iters * want / t);
+      t = run(iters);
+    }
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    e->launches += 3;
+    *tflops = 2.0 * 64.0 * (double)iters * 256.0 * blocks / (t * 1e-3) / 1e12;
+  });
+}
 
 }  // extern "C"

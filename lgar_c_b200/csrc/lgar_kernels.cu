@@ -539,6 +539,98 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
   }
 }
 
+// ---- FETCH with per-lane refill -------------------------------------------------------------------------
+// FETCH walks a column through the hours that replay cached fluxes until it needs an active step.  The walks are heavy
+// tailed (a dry spell is tens to hundreds of hours, a wet one a single hour), so with one queue entry per thread a warp
+// waits for its longest walk: ncu 3.8 of 32 lanes per instruction.  Here a lane that has finished its walk takes the next
+// queue entry while its neighbours keep walking (one warp-aggregated atomicAdd on a cursor per refill), so a warp's time is
+// the MEAN walk of what it handles, not the maximum; the forcing of the next hour is requested before the current hour is
+// computed.  The arithmetic per hour is lg_resident_hour(), the body lg_advance_resident() loops over: bit-identical.
+__global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w,
+                                                              const __grid_constant__ LgarWave wv, int consume, unsigned append_mask) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int n = wv.qcount[LG_ST_FETCH * 2 + consume];
+  const int lane = threadIdx.x & 31;
+  const int K = w.K;
+  LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
+  unsigned long long front_sum = 0;
+  unsigned long long* fsp = w.prof ? &front_sum : nullptr;
+  bool have = false, exhausted = false;
+  int slot = 0, t = 0, nf = 0;
+  int64_t col = 0;
+  LgScalars s;
+  LgEpi ep;
+  double Pn = 0.0, En = 0.0;  // forcing of hour t, requested one hour ahead
+  for (;;) {
+    if (!exhausted) {
+      const unsigned need = __ballot_sync(FULL, !have);
+      if (need) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(wv.cursor, __popc(need));
+        base = __shfl_sync(FULL, base, 0);
+        exhausted = base + __popc(need) >= n;
+        const int idx = base + __popc(need & ((1u << lane) - 1));
+        if (!have && idx < n) {
+          slot = wv.queue[LG_ST_FETCH][consume][idx];
+          LgLane& G = slots[slot].L;
+          col = G.col;
+          t = G.t;
+          nf = G.f.n;
+          s = G.s;
+          ep = G.ep;
+          have = true;
+          if (t < K && G.cls->invalid_soil_type) t = lg_advance_resident(cfg, d, w, G.cls, col, t, nf, s, ep, fsp);  // Q = precip: no walk
+          if (t < K) {
+            Pn = w.precip[(int64_t)t * w.series_stride + col];
+            En = w.pet[(int64_t)t * w.series_stride + col];
+          }
+        }
+      }
+    }
+    if (!__any_sync(FULL, have)) break;
+    int next = -1;
+    if (have) {
+      bool ended = t >= K;
+      if (!ended) {
+        const double P = Pn, E = En;
+        if (t + 1 < K) {
+          Pn = w.precip[(int64_t)(t + 1) * w.series_stride + col];
+          En = w.pet[(int64_t)(t + 1) * w.series_stride + col];
+        }
+        if (lg_resident_hour(cfg, d, w, col, t, nf, s, ep, fsp, P, E)) {
+          t++;
+          ended = t >= K;
+        } else {
+          ended = true;
+        }
+      }
+      if (ended) {
+        LgLane& G = slots[slot].L;
+        G.s = s;
+        G.ep = ep;
+        G.t = t;
+        if (t < K) {
+          G.stage = LG_ST_HEAD;
+          next = LG_ST_HEAD;
+        } else {  // this column has finished the window (lg_stage_fetch, slot == column)
+          lg_lane_export(cfg, d, col, G);
+          if (w.done_columns) atomicAdd(w.done_columns, 1);
+          if (w.work_trace) {
+            w.work_trace[col] = G.tr_iters;
+            w.work_trace[w.trace_stride + col] = G.tr_kcyc;
+          }
+          G.col = -1;
+          G.stage = LG_ST_DONE;
+          next = LG_ST_DONE;
+        }
+        have = false;
+      }
+    }
+    wave_push(wv, append_mask, LG_ST_HEAD, next == LG_ST_HEAD, slot);
+  }
+  if (w.prof && front_sum) atomicAdd(w.prof, front_sum);
+}
+
 // ---- step kernel (mode 4) ----------------------------------------------------------------------------
 // The stage kernels above move a context of 1.2-1.7 KB between HBM and the SM at every stage boundary (about
 // 11 KB per active column-step, plus the same again through thread-private memory) and a step crosses ~13
@@ -779,12 +871,111 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
   }
 }
 
+// Finishing kernel, converged variant: every lane of a warp owns a slot and the warp executes ONE stage at a time for the
+// lanes that are in it, going round the stages in program order (FETCH, HEAD, FRONT, SEARCH, TAIL, CORR; empty ones are
+// skipped), so a lane is served at least once per cycle and a plain step rides one cycle from FETCH to TAIL.  The variant
+// above leaves each lane to its own `switch`: the (up to 8) lanes of a warp sit in different stages and the hardware runs
+// them one after the other -- the serial chain of a column then costs the SUM of what its warp neighbours do.
+__global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_vote_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int quantum) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
+  int total = 0;
+  for (int q = 0; q < 2 * LGAR_NSTAGE; q++) total += wv.qcount[q];
+  unsigned long long front_sum = 0, active_sum = 0;
+  unsigned long long* fsp = w.prof ? &front_sum : nullptr;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i0 = (gtid & ~31); i0 < total; i0 += gridDim.x * blockDim.x) {  // warp-uniform trip count
+    const int i = i0 + (threadIdx.x & 31);
+    int j = i, slot = -1, stage = LG_ST_DONE;
+    if (i < total)
+      for (int q = 0; q < 2 * LGAR_NSTAGE; q++) {  // item i of the concatenation of all queues
+        const int n = wv.qcount[q];
+        if (j < n) {
+          slot = wv.queue[q >> 1][q & 1][j];
+          stage = q >> 1;
+          break;
+        }
+        j -= n;
+      }
+    LgLaneSlot S;
+    LgLane& L = S.L;
+    if (slot >= 0) {
+      lane_load<LG_PART_ALL>(&S, &slots[slot]);
+      L.c.cfg = &cfg;
+      L.c.cls = L.cls;
+      L.c.f = &L.f;
+      L.c.ff = lg_ff_ones;
+    }
+    L.stage = stage;  // the queue a slot sits in is authoritative
+    int cur = LGAR_NSTAGE - 1;
+    for (;;) {
+      unsigned m[LGAR_NSTAGE];
+      unsigned any = 0;
+#pragma unroll
+      for (int s = 0; s < LGAR_NSTAGE; s++) {
+        m[s] = __ballot_sync(FULL, L.stage == s);
+        any |= m[s];
+      }
+      if (!any) break;
+#pragma unroll 1
+      for (int k = 0; k < LGAR_NSTAGE; k++) {  // next non-empty stage after the one just run
+        cur = (cur + 1 == LGAR_NSTAGE) ? 0 : cur + 1;
+        if (m[cur]) break;
+      }
+      if (L.stage == cur) {
+        switch (cur) {
+          case LG_ST_FETCH: lg_stage_fetch(cfg, d, w, L, fsp); break;
+          case LG_ST_HEAD:
+            lg_stage_head(cfg, d, w, L, fsp);
+            active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
+            break;
+          case LG_ST_FRONT: lg_stage_front(L); break;
+          case LG_ST_SEARCH:
+            for (int it = 0; it < quantum && !L.q.done; it++) lg_search_iter(L.q, *L.cls);
+            if (L.q.done) {
+              L.resume = true;
+              L.stage = LG_ST_FRONT;
+            }
+            break;
+          case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, fsp); break;
+          default:
+            for (int it = 0; it < quantum && !L.k.done; it++) lg_corr_iter(L.k, L.f, *L.cls);
+            if (L.k.done) L.stage = LG_ST_TAIL;
+            break;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (w.prof) {
+    if (front_sum) atomicAdd(w.prof, front_sum);
+    if (active_sum) atomicAdd(w.prof + 1, active_sum);
+  }
+}
+
+// Queue counts to the host through mapped pinned memory: a cudaMemcpyAsync of these 48 bytes would queue behind whatever
+// bulk device-to-host copy (output series of the previous chunk of a streamed call) occupies the copy engine.
+__global__ void lgar_wave_poll_kernel(const int32_t* qcount, int32_t* host_counts) {
+  if (threadIdx.x < 2 * LGAR_NSTAGE) host_counts[threadIdx.x] = qcount[threadIdx.x];
+  __threadfence_system();
+}
+cudaError_t lgar_launch_wave_poll(const LgarWave& wv, int32_t* host_counts, cudaStream_t stream) {
+  lgar_wave_poll_kernel<<<1, 32, 0, stream>>>(wv.qcount, host_counts);
+  return cudaGetLastError();
+}
+
 __global__ void lgar_wave_clear_kernel(LgarWave wv) {
   if (threadIdx.x < 2 * LGAR_NSTAGE) wv.qcount[threadIdx.x] = 0;
 }
 
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
                                     int lane_stride, cudaStream_t stream) {
+  if (lane_stride <= 0) {  // converged variant, -lane_stride = search trips per turn (0: default)
+    const int blocks = std::max(1, std::min((in_flight + 127) / 128, 148 * 16));
+    lgar_wave_finish_vote_kernel<<<blocks, 128, 0, stream>>>(cfg, d, w, wv, lane_stride < 0 ? -lane_stride : 128);
+    lgar_wave_clear_kernel<<<1, 32, 0, stream>>>(wv);
+    return cudaGetLastError();
+  }
   lane_stride = std::max(1, std::min(lane_stride, 32));
   const int blocks = std::max(1, std::min((int)(((int64_t)in_flight * lane_stride + 127) / 128), 148 * 16));
   lgar_wave_finish_kernel<<<blocks, 128, 0, stream>>>(cfg, d, w, wv, lane_stride);
@@ -814,8 +1005,11 @@ __global__ void lgar_wave_init_kernel(const __grid_constant__ LgarConfig cfg, co
   if (blockIdx.x == 0 && threadIdx.x == 0) *wv.done_columns = 0;
 }
 
-// reset the consumed queue's count after its kernel ran
-__global__ void lgar_wave_reset_kernel(int32_t* count) { *count = 0; }
+// reset the consumed queue's count (and the FETCH cursor) after its kernel ran
+__global__ void lgar_wave_reset_kernel(int32_t* count, int32_t* cursor) {
+  *count = 0;
+  if (cursor) *cursor = 0;
+}
 
 cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWave& wv, int slot_is_column, cudaStream_t stream) {
   lgar_wave_init_kernel<<<(wv.nslots + 255) / 256, 256, 0, stream>>>(cfg, d, wv, slot_is_column);
@@ -844,19 +1038,48 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
     cudaFuncSetAttribute(lgar_wave_kernel<LG_ST_TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   }
   const size_t sm = (size_t)smem[stage];
+  static const int fetch_refill = getenv("LGARB_FETCH_REFILL") ? atoi(getenv("LGARB_FETCH_REFILL")) : 8;  // 0: one queue entry per thread; n: refill kernel, n resident blocks per SM
+  const bool refill = stage == LG_ST_FETCH && fetch_refill && w.slot_is_column;
   switch (stage) {
-    case LG_ST_FETCH: lgar_wave_kernel<LG_ST_FETCH><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+    case LG_ST_FETCH:
+      if (refill)
+        lgar_wave_fetch_kernel<<<std::min(blocks, 148 * fetch_refill), 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask);
+      else
+        lgar_wave_kernel<LG_ST_FETCH><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum);
+      break;
     case LG_ST_HEAD: lgar_wave_kernel<LG_ST_HEAD><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
     case LG_ST_FRONT: lgar_wave_kernel<LG_ST_FRONT><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
     case LG_ST_SEARCH: lgar_wave_kernel<LG_ST_SEARCH><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
     case LG_ST_CORR: lgar_wave_kernel<LG_ST_CORR><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
     default: lgar_wave_kernel<LG_ST_TAIL><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
   }
-  lgar_wave_reset_kernel<<<1, 1, 0, stream>>>(wv.qcount + stage * 2 + consume);
+  lgar_wave_reset_kernel<<<1, 1, 0, stream>>>(wv.qcount + stage * 2 + consume, refill ? wv.cursor : nullptr);
   return cudaGetLastError();
 }
 
 size_t lgar_lane_context_bytes() { return sizeof(LgLaneSlot); }
+
+// FP64 pipe microbenchmark: 8 independent fused multiply-add chains per thread (asm: -fmad=false must not split them)
+__global__ void __launch_bounds__(256) lgar_dfma_kernel(double* sink, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-7;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      asm volatile("fma.rn.f64 %0, %0, %8, %9;\n\tfma.rn.f64 %1, %1, %8, %9;\n\tfma.rn.f64 %2, %2, %8, %9;\n\tfma.rn.f64 %3, %3, %8, %9;\n\t"
+                   "fma.rn.f64 %4, %4, %8, %9;\n\tfma.rn.f64 %5, %5, %8, %9;\n\tfma.rn.f64 %6, %6, %8, %9;\n\tfma.rn.f64 %7, %7, %8, %9;"
+                   : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3), "+d"(a4), "+d"(a5), "+d"(a6), "+d"(a7)
+                   : "d"(m), "d"(c));
+    }
+  }
+  const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (r == 123.456) sink[0] = r;
+}
+cudaError_t lgar_launch_dfma(double* sink, int blocks, int iters, cudaStream_t stream) {
+  lgar_dfma_kernel<<<blocks, 256, 0, stream>>>(sink, iters);
+  return cudaGetLastError();
+}
 
 // Gather per-front BMI arrays into a caller-facing [ncol][LGAR_W] layout (pad = NaN).
 __global__ void lgar_gather_fronts_kernel(LgarDeviceState d, int which, double scale, double* dst, int64_t col0, int64_t ncol) {

@@ -50,6 +50,7 @@ struct LgarWave {
   int32_t* qcount;             // [LGAR_NSTAGE][2]
   int32_t nslots;
   int32_t* done_columns;       // columns that finished their window
+  int32_t* cursor;             // FETCH kernel: next queue entry to hand out (zero between launches)
 };
 
 #ifndef LGAR_HOSTSIM
@@ -62,6 +63,8 @@ cudaError_t lgar_launch_wave_run(const LgarConfig& cfg, const LgarDeviceState& d
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
                                     int lane_stride, cudaStream_t stream);
 cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWave& wv, int slot_is_column, cudaStream_t stream);
+// the 12 queue counts into pinned host memory (device-visible under unified addressing), no copy engine involved
+cudaError_t lgar_launch_wave_poll(const LgarWave& wv, int32_t* host_counts, cudaStream_t stream);
 size_t lgar_lane_context_bytes();
 // mode 1: warp-tile window kernel; mode 2: per-lane staged program (lgar_lanes.cuh)
 cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream, int mode);
@@ -77,6 +80,8 @@ cudaError_t lgar_launch_gather_fronts(const LgarDeviceState& d, int which, doubl
                                       cudaStream_t stream);
 cudaError_t lgar_launch_gather_layers(const LgarDeviceState& d, double* dst, int64_t col0, int64_t ncol, int L, cudaStream_t stream);
 int lgar_active_kernel_max_blocks_per_sm();
+// DFMA microbenchmark: `iters` trips of 8 independent FMA chains per thread on blocks x 256 threads; sink keeps the result alive
+cudaError_t lgar_launch_dfma(double* sink, int blocks, int iters, cudaStream_t stream);
 #endif
 
 #endif

@@ -421,6 +421,28 @@ LG_FN_NOINLINE int lg_advance_column(const LgarConfig& cfg, const LgarDeviceStat
   return t;
 }
 
+// One hour of that walk for a resident column: false if hour t needs the full Update() (nothing has been changed then),
+// true if it was finished from the scalars by replaying the cached fluxes (bmi_lgar.cxx:260-318,683-695).
+LG_FN bool lg_resident_hour(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int64_t col, int t, int nf, LgScalars& s,
+                            LgEpi& ep, unsigned long long* front_sum, double P, double E) {
+  LgStepVols v;
+  zero_vols(v);
+  if (!(s.status & LGAR_FAIL_MASK)) {
+    const LgPrologue pro = lg_prologue_inl(cfg, s, P);
+    if (!pro.cache_fluxes || w.force_all_active) return false;
+    if (cfg.adaptive_timestep) s.timestep_h = pro.subtimestep_h;
+    s.cache_fluxes = 1;
+    s.cache_count = pro.cache_count;
+    adjust_forcing(cfg, P, E, s.status);
+    lg_step_cached_inl(cfg, s, pro, P, E, v);
+    if (!(fabs(v.local_mb) <= cfg.mbal_tol)) s.status |= (isnan(v.local_mb) ? LGAR_FAIL_NAN : LGAR_FAIL_MBAL);
+  }
+  lg_epi_step(cfg, d, w, t, col, ep, v, s.status, t == w.K - 1);
+  if (w.nf_sink) w.nf_sink[(int64_t)t * w.sink_stride + col] = nf;
+  if (front_sum) *front_sum += (unsigned)nf;
+  return true;
+}
+
 // The same walk for a column whose scalars, GIUH queue and cumulative volumes are resident in its lane
 // record (lgar_lanes.cuh): nothing is read from or written to the SoA state.
 LG_FN int lg_advance_resident(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarColumnClass* cls, int64_t col, int t,
@@ -445,22 +467,8 @@ LG_FN int lg_advance_resident(const LgarConfig& cfg, const LgarDeviceState& d, c
     return K;
   }
   for (; t < K; t++) {
-    double P = w.precip[(int64_t)t * w.series_stride + col], E = w.pet[(int64_t)t * w.series_stride + col];
-    LgStepVols v;
-    zero_vols(v);
-    if (!(s.status & LGAR_FAIL_MASK)) {
-      const LgPrologue pro = lg_prologue_inl(cfg, s, P);
-      if (!pro.cache_fluxes || w.force_all_active) break;
-      if (cfg.adaptive_timestep) s.timestep_h = pro.subtimestep_h;
-      s.cache_fluxes = 1;
-      s.cache_count = pro.cache_count;
-      adjust_forcing(cfg, P, E, s.status);
-      lg_step_cached_inl(cfg, s, pro, P, E, v);
-      if (!(fabs(v.local_mb) <= cfg.mbal_tol)) s.status |= (isnan(v.local_mb) ? LGAR_FAIL_NAN : LGAR_FAIL_MBAL);
-    }
-    lg_epi_step(cfg, d, w, t, col, ep, v, s.status, t == K - 1);
-    if (w.nf_sink) w.nf_sink[(int64_t)t * w.sink_stride + col] = nf;
-    if (front_sum) *front_sum += (unsigned)nf;
+    const double P = w.precip[(int64_t)t * w.series_stride + col], E = w.pet[(int64_t)t * w.series_stride + col];
+    if (!lg_resident_hour(cfg, d, w, col, t, nf, s, ep, front_sum, P, E)) break;
   }
   return t;
 }

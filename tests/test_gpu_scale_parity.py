@@ -181,3 +181,27 @@ def test_full_size_shard_properties(cuda_device, oracle, tmp_path):
         assert np.array_equal(hn[:done, j], r["nfronts"][:done]), f"column {c}: front counts differ"
         g, w = hq[:done, j], r["scalars"][:done, 6]
         assert np.all(np.abs(g - w) <= 1e-9 * np.maximum(np.abs(g), np.abs(w)) + 1e-14), f"column {c}: total_discharge differs"
+
+
+# config-5 columns (global ids) whose front list grows beyond 16 in the first 7400 hours of the year: the oracle of the
+# 10 000-column full-duration sample (tools/parity_sampling_full.py) reaches 17-19 fronts there
+DEEP_FRONT_COLUMNS = [1598581, 1978823, 5021247, 5588097, 8081421, 8308783, 8471861]
+
+
+def test_more_than_16_fronts(cuda_device, oracle, tmp_path):
+    """A full year of BASELINE config 5 takes 0.2 % of the columns past 16 wetting fronts (19 in a 10 000-column sample):
+    the front capacity (LGARB_MAX_FRONTS = 32, two flag words per column) must carry them, step by step as the oracle."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import parity_sampling_full as pf
+    c = pf.Config(5, tmp_path)
+    ids = np.array(DEEP_FRONT_COLUMNS, dtype=np.int64)
+    T = 7400
+    hP, hE, scal, nf, status, final, info = pf.run_engine(c, ids, np.arange(len(ids)), T, 1850, 3)
+    assert info["frozen_columns_in_batch"] == 0
+    assert nf.max() >= 19 and (nf.max(axis=0) > 16).all(), nf.max(axis=0)
+    r = pf.diff_against_oracle(c, ids, hP, hE, scal, nf, status, final, 2)
+    assert r["front_count_mismatch_columns"] == 0 and r["failure_mismatch_columns"] == 0, r["examples"]
+    assert r["final_front_flag_mismatch_columns"] == 0 and r["final_front_field_mismatch_columns"] == 0
+    assert max(v["columns_outside_bar"] for v in r["scalars"].values()) == 0, r["examples"]

@@ -67,3 +67,30 @@ def test_kernel_text_matches_golden(hostsim, name, force, tmp_path):
     for i, t in enumerate(g["ck_steps"]):
         if t < n:
             assert_fronts_close(fr[t], fl[t], g["ck_fronts"][i], g["ck_flags"][i], int(nf[t]), f"{name}@{t}", rtol=1e-10)
+
+
+def test_more_than_16_fronts(hostsim, tmp_path):
+    """Column 5588097 of BASELINE config 5 reaches 19 wetting fronts at hour 5641 of the year (tools/parity_sampling_full.py):
+    the kernel text with its 32-front capacity and two flag words must follow the oracle through it."""
+    import sys
+    import torch
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import parity_sampling_full as pf
+    from oracle.oracle_py import Oracle, write_config
+    c = pf.Config(5, tmp_path)
+    ids = np.array([5588097], dtype=np.int64)
+    T = 5800
+    P, E = (x.numpy()[:, 0] for x in c.forcing(torch.from_numpy(ids), 0, T))
+    cfg = write_config(c.cfg, tmp_path / "deep.txt", layer_soil_type=",".join(map(str, c.soils(ids)[0])),
+                       layer_thickness=",".join(map(str, c.layers(ids)[0])) + "[cm]")
+    orc = Oracle()
+    p = orc.params_from_config(cfg)
+    s = orc.new_state(p)
+    o = orc.run_series(p, s, P, E, cap=32)
+    for force in (0, 4):
+        done, scal, nf, fr, fl, status = run(hostsim, cfg, P, E, force, cap=32)
+        assert done == T == o["done"] and status & 0xFFFF == 0
+        assert nf.max() == 19 and np.array_equal(nf, o["nfronts"])
+        assert_scalars_close(scal, o["scalars"], "config5 column 5588097", rtol=1e-9)
+        t = T - 1 if force else int(np.argmax(nf))
+        assert_fronts_close(fr[t], fl[t], o["fronts"][t], o["flags"][t], int(nf[t]), f"deep@{t}", rtol=1e-9)
