@@ -106,6 +106,9 @@ struct lgarb_engine {
   // beside FETCH/HEAD/FRONT/SEARCH of the same round and is joined before TAIL; 0 = CORR and a second TAIL at the end of
   // the round on the main stream
   int wave_corr_async = 1;
+  // experiment, off (measured slower): SEARCH by one warp per slot (lg_search_warp) in rounds with at most this many slots
+  // in flight; trips per launch = warp_search_mult x the thread-per-slot quantum
+  int warp_search_below = 0, warp_search_mult = 16;
   cudaStream_t side_stream = nullptr;
   cudaEvent_t side_ev[2] = {nullptr, nullptr};
   int wave_finish_below = 16384;
@@ -784,6 +787,8 @@ int lgarb_create(lgarb_engine** out) {
   knob("LGARB_WAVE_PAIRS", (*out)->wave_pairs);
   knob("LGARB_WAVE_CORR_PAIRS", (*out)->wave_corr_pairs);
   knob("LGARB_WAVE_CORR_ASYNC", (*out)->wave_corr_async);
+  knob("LGARB_WARP_SEARCH_BELOW", (*out)->warp_search_below);
+  knob("LGARB_WARP_SEARCH_MULT", (*out)->warp_search_mult);
   knob("LGARB_WAVE_FINISH_BELOW", (*out)->wave_finish_below);
   knob("LGARB_FINISH_LANE_STRIDE", (*out)->finish_lane_stride);
   knob("LGARB_UPDATE_WAVE_MIN_COLS", (*out)->update_wave_min_cols);
@@ -919,8 +924,11 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       cudaEventRecord(dbg_evs.back().first, e->stream);
       dbg_evs.back().second = stage;
     }
-    CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, stage == LG_ST_CORR ? std::max(1, quantum * e->wave_corr_quantum / e->wave_quantum) : quantum, in_flight,
-                                    launch_stream));
+    if (stage == LG_ST_SEARCH && e->use_window == 3 && in_flight <= e->warp_search_below)
+      CUDA_TRY(lgar_launch_wave_search_warp(wv, consume, mask, (int)std::min<int64_t>((int64_t)quantum * e->warp_search_mult, 1 << 30), in_flight, launch_stream));
+    else
+      CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, stage == LG_ST_CORR ? std::max(1, quantum * e->wave_corr_quantum / e->wave_quantum) : quantum, in_flight,
+                                      launch_stream));
     e->launches += 2;
   };
   auto launch_q = [&](int stage, int q) {  // SEARCH / CORR with an explicit quantum

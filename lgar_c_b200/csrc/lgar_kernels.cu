@@ -539,6 +539,35 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
   }
 }
 
+// ---- SEARCH, one warp per slot ------------------------------------------------------------------------
+// When the SEARCH queue is short (drop-out rounds: a few thousand searches, the long ones among them) a thread per
+// search leaves the machine empty and every launch waits for `quantum` dependent trips.  Here a warp takes one search and
+// runs it 32 trips at a time (lg_search_warp, lgar_lanes.cuh): the same numbers, ~12 x fewer dependent instructions.
+// MEASURED SLOWER and therefore off by default (LGARB_WARP_SEARCH_BELOW=0): most searches end within a few trips (mean
+// 41), and a warp step costs ~1 300 instructions whether it commits 32 trips or 3 -- 4.8e8 -> 4.5e8 column-steps/s with
+// the kernel used below 65 536 slots in flight, 4.1e8 below 262 144, 1.8e8 always; letting the warp take over only the
+// searches that have already run 192 trips was no better (2.1e8: the take-over holds the round up).  Kept, with its test,
+// as the record of that experiment.
+__global__ void __launch_bounds__(128) lgar_wave_search_warp_kernel(const __grid_constant__ LgarWave wv, int consume, unsigned append_mask, int quantum) {
+  const int n = wv.qcount[LG_ST_SEARCH * 2 + consume];
+  LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
+    const int slot = wv.queue[LG_ST_SEARCH][consume][i];
+    LgLane& G = slots[slot].L;
+    LgSearch q = G.q;  // every lane reads the same record
+    const LgarColumnClass* cls = G.cls;
+    lg_search_warp(q, *cls, quantum);
+    if (lane == 0) {
+      G.q = q;
+      if (q.done) G.resume = true;
+    }
+    wave_push(wv, append_mask, LG_ST_FRONT, lane == 0 && q.done, slot);
+    wave_push(wv, append_mask, LG_ST_SEARCH, lane == 0 && !q.done, slot);
+  }
+}
+
 // ---- FETCH with per-lane refill -------------------------------------------------------------------------
 // FETCH walks a column through the hours that replay cached fluxes until it needs an active step.  The walks are heavy
 // tailed (a dry spell is tens to hundreds of hours, a wet one a single hour), so with one queue entry per thread a warp
@@ -1054,6 +1083,14 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
     default: lgar_wave_kernel<LG_ST_TAIL><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
   }
   lgar_wave_reset_kernel<<<1, 1, 0, stream>>>(wv.qcount + stage * 2 + consume, refill ? wv.cursor : nullptr);
+  return cudaGetLastError();
+}
+
+cudaError_t lgar_launch_wave_search_warp(const LgarWave& wv, int consume, unsigned append_mask, int quantum, int max_items, cudaStream_t stream) {
+  const int64_t threads = (int64_t)std::min(wv.nslots, max_items) * 32;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((threads + 127) / 128, 148 * 16));
+  lgar_wave_search_warp_kernel<<<blocks, 128, 0, stream>>>(wv, consume, append_mask, quantum);
+  lgar_wave_reset_kernel<<<1, 1, 0, stream>>>(wv.qcount + LG_ST_SEARCH * 2 + consume, nullptr);
   return cudaGetLastError();
 }
 

@@ -65,6 +65,8 @@ cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState
 cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWave& wv, int slot_is_column, cudaStream_t stream);
 // the 12 queue counts into pinned host memory (device-visible under unified addressing), no copy engine involved
 cudaError_t lgar_launch_wave_poll(const LgarWave& wv, int32_t* host_counts, cudaStream_t stream);
+// SEARCH with one warp per slot (short queues): same queue protocol as lgar_launch_wave_stage(LG_ST_SEARCH)
+cudaError_t lgar_launch_wave_search_warp(const LgarWave& wv, int consume, unsigned append_mask, int quantum, int max_items, cudaStream_t stream);
 size_t lgar_lane_context_bytes();
 // mode 1: warp-tile window kernel; mode 2: per-lane staged program (lgar_lanes.cuh)
 cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream, int mode);

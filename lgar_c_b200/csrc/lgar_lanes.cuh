@@ -122,10 +122,14 @@ LG_FN bool lg_search_init(LgLane& L, int layer_num, double psi_cm, double new_ma
   return true;
 }
 
-// one trip of the while loop; sets q.done when the loop would exit
-LG_FN void lg_search_iter(LgSearch& q, const LgarColumnClass& cls) {
+// One trip of the while loop (lgar.cxx:2990-3090) in three parts, so that the warp-cooperative search below executes
+// exactly the arithmetic of the per-thread one:
+//   pre : the psi / step-size recurrence.  It needs the outcome of the previous trip only as one bit (`up`: the mass found
+//         was larger than the prior mass), everything else is a function of the trip count and of psi itself
+//   eval: theta(psi) of the layers above and the mass they hold -- the expensive part (exp/log per layer)
+//   post: the seven exit conditions
+LG_FN void lg_search_pre(LgSearch& q, bool up) {
   const int first_thresh = LG_MAX_ITER_MBAL / 100, second_thresh = LG_MAX_ITER_MBAL / 10;
-  const int layer_num = q.layer_num;
   q.iter++;
   if (q.iter > first_thresh && !q.aug) {
     q.factor = q.factor * 100;
@@ -135,7 +139,7 @@ LG_FN void lg_search_iter(LgSearch& q, const LgarColumnClass& cls) {
     q.factor = q.factor * 100;
     q.aug_extreme = true;
   }
-  if (q.new_mass > q.prior_mass) {
+  if (up) {
     q.psi_loc += 0.1 * q.factor;
     q.switched = false;
   } else {
@@ -152,6 +156,9 @@ LG_FN void lg_search_iter(LgSearch& q, const LgarColumnClass& cls) {
     q.psi_loc = 0.0;
     q.factor = q.factor * 0.5;
   }
+}
+LG_FN void lg_search_eval(LgSearch& q, const LgarColumnClass& cls) {
+  const int layer_num = q.layer_num;
   const double lnpsi = lg_lnh(q.psi_loc);
   q.theta = lg_theta_from_lnh(lnpsi, cls.lay[layer_num]);
   double mass_layers = 0.0;
@@ -162,6 +169,9 @@ LG_FN void lg_search_iter(LgSearch& q, const LgarColumnClass& cls) {
   }
   q.new_mass = mass_layers;
   q.delta_mass = fabs(q.new_mass - q.prior_mass);
+}
+LG_FN void lg_search_post(LgSearch& q) {
+  const int first_thresh = LG_MAX_ITER_MBAL / 100;
   bool brk = false;
   if (fabs(q.psi_loc - q.psi_prev) < 1E-15 && q.factor < 1E-13) brk = true;
   if (!brk) {
@@ -177,6 +187,83 @@ LG_FN void lg_search_iter(LgSearch& q, const LgarColumnClass& cls) {
   if (!brk) q.delta_mass_prev = q.delta_mass;
   if (brk || !(q.delta_mass > LG_MBAL_TOL)) q.done = true;
 }
+// one trip; sets q.done when the loop would exit
+LG_FN void lg_search_iter(LgSearch& q, const LgarColumnClass& cls) {
+  lg_search_pre(q, q.new_mass > q.prior_mass);
+  lg_search_eval(q, cls);
+  lg_search_post(q);
+}
+
+#ifndef LGAR_HOSTSIM
+// Warp-cooperative psi search: up to `max_trips` trips of ONE search by the 32 lanes of a warp, 32 trips at a time.
+// Every lane holds the same LgSearch on entry and on return.  Lane j runs the cheap recurrence (lg_search_pre) j+1 times
+// under the assumption that trips 0..j-1 all leave the direction of the search as it is, evaluates the mass at ITS psi
+// (the 3 x exp/log that dominate a trip) and applies the exit conditions with its left neighbour's mass difference and
+// the run length of "no mass change" trips (ballot).  The first lane whose trip ends the search or turns it round is
+// where the sequential loop would be after that many trips: its state is broadcast and the warp goes on from there.  A
+// search of 10^4 trips (the tail that sets the length of a window) takes ~300 warp steps instead of 10^4 dependent
+// trips; the numbers are those of lg_search_iter bit for bit, whatever the grouping.
+__device__ __forceinline__ double lg_shfl(double v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
+__device__ __noinline__ void lg_search_warp(LgSearch& q, const LgarColumnClass& cls, int max_trips) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  int budget = max_trips;
+  while (!q.done && budget > 0) {
+    const bool up = q.new_mass > q.prior_mass;
+    LgSearch s = q;
+#pragma unroll 1
+    for (int i = 0; i <= lane; i++) lg_search_pre(s, up);
+    lg_search_eval(s, cls);
+    // exit conditions of this lane's trip (lg_search_post with the neighbours' values)
+    double dprev = __shfl_up_sync(FULL, s.delta_mass, 1);
+    if (lane == 0) dprev = q.delta_mass_prev;
+    const bool brk1 = fabs(s.psi_loc - s.psi_prev) < 1E-15 && s.factor < 1E-13;
+    const bool nochange = fabs(s.delta_mass - dprev) < 1E-15;
+    const unsigned ncm = __ballot_sync(FULL, nochange);
+    // consecutive no-change trips ending at this lane; if the run reaches lane 0 it continues the count carried in
+    const unsigned inv = ~(ncm << (31 - lane));   // bit 31 = this lane, downwards = lanes to the left
+    const int run = __clz((int)inv);                // leading ones of (ncm << (31-lane))
+    int count = (run > lane) ? lane + 1 + q.count_no_mass_change : run;
+    int count_prev = __shfl_up_sync(FULL, count, 1);
+    if (lane == 0) count_prev = q.count_no_mass_change;
+    bool brk = brk1;
+    if (!brk1) {
+      const int first_thresh = LG_MAX_ITER_MBAL / 100;
+      if (count == 5 && s.precip_mass_to_add < 1.E-12) brk = true;
+      else if (s.iter > LG_MAX_ITER_MBAL) brk = true;
+      else if ((s.psi_loc > LG_PSI_UPPER_LIM) && (s.iter > first_thresh)) brk = true;
+      else if (s.psi_loc <= 0 && s.psi_prev < 0) brk = true;
+    } else {
+      count = count_prev;  // the count is not touched when the first condition breaks
+    }
+    const bool done = brk || !(s.delta_mass > LG_MBAL_TOL);
+    const bool stop = done || ((s.new_mass > s.prior_mass) != up) || (lane + 1 >= budget);
+    const unsigned sm = __ballot_sync(FULL, stop);
+    const int jl = sm ? (__ffs(sm) - 1) : 31;
+    s.count_no_mass_change = count;
+    s.delta_mass_prev = brk ? dprev : s.delta_mass;
+    s.done = done;
+    // the state after trip jl is the state of the sequential loop
+    q.psi_loc = lg_shfl(s.psi_loc, jl);
+    q.factor = lg_shfl(s.factor, jl);
+    q.psi_prev = lg_shfl(s.psi_prev, jl);
+    q.delta_mass = lg_shfl(s.delta_mass, jl);
+    q.delta_mass_prev = lg_shfl(s.delta_mass_prev, jl);
+    q.new_mass = lg_shfl(s.new_mass, jl);
+    q.theta = lg_shfl(s.theta, jl);
+    q.iter = __shfl_sync(FULL, s.iter, jl);
+    q.count_no_mass_change = __shfl_sync(FULL, s.count_no_mass_change, jl);
+    const int flags = (s.switched ? 1 : 0) | (s.wanted_to_saturate ? 2 : 0) | (s.aug ? 4 : 0) | (s.aug_extreme ? 8 : 0) | (s.done ? 16 : 0);
+    const int fj = __shfl_sync(FULL, flags, jl);
+    q.switched = fj & 1;
+    q.wanted_to_saturate = (fj & 2) != 0;
+    q.aug = (fj & 4) != 0;
+    q.aug_extreme = (fj & 8) != 0;
+    q.done = (fj & 16) != 0;
+    budget -= jl + 1;
+  }
+}
+#endif
 
 // what follows the loop in lgar_theta_mass_balance (lgar.cxx:3096-3110); only after an iterated search
 LG_FN void lg_search_finish(LgLane& L) {

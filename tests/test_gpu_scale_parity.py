@@ -69,7 +69,10 @@ def test_scheduling_does_not_change_results(cuda_device, tmp_path):
     """A column's trajectory must not depend on how the wavefront scheduler interleaves it with the
     others: the bench workload on 200 000 columns x 2 windows, run with (a) the defaults, (b) no
     finishing kernel and a tiny search quantum, (c) the finishing kernel taking over early, and
-    (d) the warp-tile window kernel (mode 1) -- every output, status word and front bit-identical."""
+    (d) the warp-tile window kernel (mode 1), (e) the opt-in scheduler variants that are read from the environment when an
+    engine is created (correction searches on the main stream, warp-cooperative psi search lg_search_warp, converged
+    finishing kernel) -- every output, status word and front bit-identical."""
+    import os
     import torch
     import bench
     import lgar_c_b200
@@ -80,8 +83,17 @@ def test_scheduling_does_not_change_results(cuda_device, tmp_path):
     P[10:14] = np.maximum(P[10:14], 8.0)     # a storm on every column: the whole batch active at once
     dP, dE = torch.from_numpy(P).cuda(), torch.from_numpy(E).cuda()
     res = []
-    for mode, wave in ((3, None), (4, None), (4, (64, 4, 150_000)), (3, (4, 1, 0)), (3, (64, 4, 150_000)), (1, None)):
-        b = lgar_c_b200.BmiLGARBatch()
+    variants = [(3, None, {}), (4, None, {}), (4, (64, 4, 150_000), {}), (3, (4, 1, 0), {}), (3, (64, 4, 150_000), {}), (1, None, {}),
+                (3, None, {"LGARB_WAVE_CORR_ASYNC": "0"}),
+                (3, None, {"LGARB_WARP_SEARCH_BELOW": "1000000000", "LGARB_WARP_SEARCH_MULT": "3"}),
+                (3, (64, 4, 150_000), {"LGARB_FINISH_LANE_STRIDE": "-48"})]
+    for mode, wave, env in variants:
+        os.environ.update(env)
+        try:
+            b = lgar_c_b200.BmiLGARBatch()
+        finally:
+            for k in env:
+                del os.environ[k]
         b.initialize(cfg, ncol, 0, soils, layers)
         b.set_window_mode(mode)
         if wave is not None:
