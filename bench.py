@@ -47,7 +47,7 @@ BU_LAYERS = (18.0, 76.0, 135.0)   # data/configs/config_lasam_Bushland.txt
 N_GIUH = 5
 # DRAM bytes per column-timestep of the default scheduler: ncu over every launch of one timed window (profiles/, see the
 # roofline block in main)
-TRAFFIC_B_PER_UNIT = 3152.8
+TRAFFIC_B_PER_UNIT = 3416.4
 
 
 # --------------------------------------------------------------------------------------------------
@@ -257,6 +257,15 @@ def main():
     ap.add_argument("--finish-below", type=int, default=-1, help="wavefront: slots in flight below which the finishing kernel takes over (-1: engine default)")
     ap.add_argument("--mode", type=int, default=3, help="4 step kernel + parked searches, 3 wavefront kernels, 2 lanes kernel, 1 warp-tile window kernel, 0 one kernel pair per forcing hour")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints
+    # "NCCL version ..." there whatever NCCL_DEBUG_FILE says) are sent to stderr, the line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -285,7 +294,7 @@ def main():
                                  "sample": f"{cores} processes x {cpc} columns x {H} h per step, spin-up {min(args.spinup_hours, 240)} h; "
                                            "SetValue x2 -> Update -> GetValue(total_discharge) per column-step, no file I/O"},
                 "e2e": {"value": val, "unit": "column-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -467,7 +476,7 @@ def main():
     B_nofront = B_full - 2 * 44 * mean_fronts
     ms_s, ms_a, ms_w = prof["ms_stream"], prof["ms_active"], prof["ms_window"]
     if ms_w > 0:  # window mode: one kernel per bench step (H forcing hours for every column)
-        dominant = {4: "lgar_wave_run_kernel (+ FETCH/SEARCH/CORR stage kernels)", 3: "lgar_wave_kernel<*> (5 stage kernels)", 2: "lgar_lanes_kernel", 1: "lgar_window_kernel"}[args.mode]
+        dominant = {4: "lgar_wave_run_kernel (+ FETCH/SEARCH/CORR stage kernels)", 3: "lgar_wave_kernel<*> + lgar_wave_fetch_kernel (6 stage kernels)", 2: "lgar_lanes_kernel", 1: "lgar_window_kernel"}[args.mode]
         units = ncol * H
         B_unit = B_full
         dur_s = ms_w * 1e-3 / args.steps  # per bench step (one day of every column); mode 3 runs all steps in one call
@@ -482,19 +491,19 @@ def main():
     bytes_per_launch = units * B_unit
     achieved = bytes_per_launch / dur_s / 1e9
     # DRAM bytes per launch unit from the committed ncu capture of one whole timed window of this command in mode 3
-    # (profiles/r1_session2_ncu_summary.md section 1: dram__bytes_read.sum + dram__bytes_write.sum over the 2 706 launches
-    # of a 240 h window of 1.25 M columns = 945.8 GB = 3 153 B per column-timestep); null for any other configuration
+    # (profiles/r1_window_launches.csv, tools/prof_window.sh: dram__bytes_read.sum + dram__bytes_write.sum over the 2 725
+    # launches of a 240 h window of 1.25 M columns = 1 024.9 GB = 3 416 B per column-timestep); null for any other mode
     traffic = TRAFFIC_B_PER_UNIT * units if (args.mode == 3 and ms_w > 0) else None
-    share_ncu = ({"TAIL": 0.291, "SEARCH": 0.157, "HEAD": 0.151, "FRONT": 0.112, "FETCH": 0.098, "finish": 0.095, "CORR": 0.088}
+    share_ncu = ({"TAIL": 0.283, "HEAD": 0.162, "SEARCH": 0.157, "FRONT": 0.121, "finish": 0.115, "CORR": 0.089, "FETCH": 0.066}
                  if (args.mode == 3 and ms_w > 0) else None)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "traffic_source": "ncu, profiles/r1_session2_ncu_summary.md section 1" if traffic else None,
+                "traffic": traffic, "traffic_source": "ncu launch list of one 240 h window, profiles/r1_window_launches.csv (r1_session3_ncu_summary.md)" if traffic else None,
                 "stage_time_share_ncu": share_ncu, "peak_source": peak_src, "algorithmic_bytes_per_unit": B_unit,
                 "units_per_launch": units, "avg_launch_ms": dur_s * 1e3, "kernel_time_share": share,
                 "mean_fronts": mean_fronts, "active_fraction": active_frac,
                 "note": "unit = one column-timestep; a launch = one bench step (--hours-per-step forcing hours of every column; the stage kernels of a "
                         "window are timed together with CUDA events on the engine stream); B = 88*mean_fronts + 428 bytes (SURVEY.md 8d). "
-                        "Measured DRAM traffic is 4x the algorithmic bytes (step contexts crossing HBM at every stage boundary); the path is "
+                        "Measured DRAM traffic is 4.3x the algorithmic bytes (step contexts crossing HBM at every stage boundary); the path is "
                         "latency/divergence bound, not HBM bound: DESIGN.md section 4.4"}
 
     # secondary roofline: FP64 pipe peak from a DFMA microbenchmark on this GPU; what the stage kernels use of
@@ -520,7 +529,7 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": workload, "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "failed_columns": n_failed, "max_abs_global_mass_balance_cm": max_global_balance,
             "target": {"colsteps_per_s_per_gpu": 1.25e9, "frac_of_target": value / world / 1.25e9}}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
