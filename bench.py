@@ -437,7 +437,7 @@ def main():
                "note": "precipitation_rate + potential_evapotranspiration_rate series from pinned host memory, total_discharge series back to "
                        "pinned host memory, all copies inside the timed call; single_call copies, computes, copies back; streamed overlaps the "
                        "copies of neighbouring chunks with the computation; value = the faster of the two public verbs; bytes are per bench "
-                       "step (one day) per rank"}
+                       "step (--hours-per-step forcing hours) per rank"}
         # and the classic hour-by-hour BMI loop, for reference
         hq1 = torch.empty(ncol, dtype=torch.float64).pin_memory().numpy()
         t0 = time.perf_counter()
