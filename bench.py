@@ -191,6 +191,72 @@ def run_cpu(kind: str, cores: int, cols_per_core: int, spin_h: int, blocks):
     return per_block
 
 
+def _exe_worker(args):
+    """One process = one core: runs the reference's standalone executable once per column of its share (config file +
+    forcing CSV in, data_variables.csv / data_layers.csv out, as the executable does).  Returns wall seconds of the runs."""
+    wid, ncol, col0, hours, cfg_dir = args
+    exe = ROOT / "oracle" / "_ref" / "lasam_standalone"
+    soils = column_soils(col0, ncol)
+    layers = column_layers(col0, ncol)
+    base = (Path(cfg_dir) / "bench_config5.txt").read_text()
+    P, E = host_forcing(ncol, 0, hours, 1000 + wid)
+    stamp = (np.datetime64("2016-10-01T00:00:00") + np.arange(hours).astype("timedelta64[h]")).astype(str)
+    total = 0.0
+    for c in range(ncol):
+        d = Path(cfg_dir) / f"exe_w{wid}_{c}"
+        d.mkdir()
+        with open(d / "forcing.csv", "w") as f:
+            f.write("Time,P(mm/h),PET(mm/h)\n")
+            for t in range(hours):
+                f.write(f"{stamp[t].replace('T', ' ')},{float(P[t, c])!r},{float(E[t, c])!r}\n")
+        txt = base.replace("layer_soil_type=1,2,3", "layer_soil_type=" + ",".join(map(str, soils[c])))
+        lines = [("layer_thickness=" + ",".join(map(str, layers[c])) + "[cm]") if l.startswith("layer_thickness=")
+                 else (f"endtime={hours}[hr]" if l.startswith("endtime=") else l) for l in txt.splitlines()]
+        lines.append(f"forcing_file={d / 'forcing.csv'}")
+        (d / "config.txt").write_text("\n".join(lines) + "\n")
+        t0 = time.perf_counter()
+        r = subprocess.run([str(exe), str(d / "config.txt")], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        total += time.perf_counter() - t0
+        if r.returncode != 0 or not (d / "data_variables.csv").exists():
+            return -1.0
+    return total
+
+
+def run_standalone_exe(cores: int, cols_per_core: int, hours: int):
+    """BASELINE.md section 4, baseline A (what north_star words): the reference's unmodified standalone executable run
+    column-parallel as independent processes, one per host core.  Returns column-timesteps/s over all cores, or None."""
+    import multiprocessing as mp
+    import shutil
+    if not (ROOT / "oracle" / "_ref" / "lasam_standalone").exists():
+        return None
+    tmp = tempfile.mkdtemp(prefix="lgar_exe_")
+    try:
+        write_workload_config(Path(tmp))
+        jobs = [(w, cols_per_core, w * cols_per_core, hours, tmp) for w in range(cores)]
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_exe_worker, jobs)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    if min(res) <= 0:
+        return None
+    return cores * cols_per_core * hours / max(res)
+
+
+def standalone_exe_entry(cores: int, cols_per_core: int = 32, hours: int = 2880):
+    """cpu_baseline.standalone_executable: baseline A of BASELINE.md section 4 beside the in-process harness (baseline B)."""
+    try:
+        v = run_standalone_exe(cores, cols_per_core, hours)
+    except Exception as ex:  # a reported extra, never fatal
+        print(f"bench.py: standalone executable baseline failed: {ex}", file=sys.stderr)
+        v = None
+    if v is None:
+        return None
+    return {"value": v, "unit": "column-timesteps/s", "cores": cores, "kind": "reference",
+            "sample": f"oracle/_ref/lasam_standalone (unmodified src/bmi_main_lgar.cxx), {cores} processes x {cols_per_core} runs x {hours} h, "
+                      "one column per run with its own config file and forcing CSV, data_variables.csv + data_layers.csv written "
+                      "(file I/O included: that is what the executable does)"}
+
+
 def cpu_kind() -> str:
     return "reference" if (ROOT / "oracle" / "_ref" / "liblgar_ref.so").exists() else "port"
 
@@ -294,6 +360,7 @@ def main():
                                  "sample": f"{cores} processes x {cpc} columns x {H} h per step, spin-up {min(args.spinup_hours, 240)} h; "
                                            "SetValue x2 -> Update -> GetValue(total_discharge) per column-step, no file I/O"},
                 "e2e": {"value": val, "unit": "column-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        line["cpu_baseline"]["standalone_executable"] = standalone_exe_entry(cores)
         emit(line)
         return 0
 
@@ -523,6 +590,7 @@ def main():
         cpu = {"value": cores * cpc * args.cpu_hours / float(per_block.sum()), "unit": "column-timesteps/s", "cores": cores, "kind": kind,
                "sample": f"{cores} processes x {cpc} columns x {args.cpu_hours} h of the same workload after a 240 h spin-up; "
                          "SetValue x2 -> Update -> GetValue(total_discharge) per column-step, no file I/O"}
+        cpu["standalone_executable"] = standalone_exe_entry(cores)
 
     line = {"metric": "column-timesteps/sec", "value": value, "unit": "column-timesteps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
