@@ -257,6 +257,25 @@ def standalone_exe_entry(cores: int, cols_per_core: int = 32, hours: int = 2880)
                       "(file I/O included: that is what the executable does)"}
 
 
+def host_memory_bytes() -> int:
+    """memory this process tree may use: the cgroup limit if there is one, else what the host reports as available"""
+    lim = None
+    for f in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = Path(f).read_text().strip()
+            if v.isdigit() and int(v) < (1 << 60):
+                lim = int(v)
+                break
+        except OSError:
+            pass
+    try:
+        import psutil
+        avail = int(psutil.virtual_memory().available)
+    except Exception:
+        avail = 64 << 30
+    return min(lim, avail) if lim else avail
+
+
 def cpu_kind() -> str:
     return "reference" if (ROOT / "oracle" / "_ref" / "liblgar_ref.so").exists() else "port"
 
@@ -466,6 +485,8 @@ def main():
         # the multi-step verb with HOST buffers: forcing of `nh` hours in from pinned host memory, one output
         # series (total_discharge, ngen's usual main_output_variable) back to pinned host memory, all inside
         nh = min(args.e2e_hours, R * H)
+        # three pinned [hours][columns] f64 series per rank: keep all ranks of the box within half of the host memory
+        nh = max(H, min(nh, int(0.5 * host_memory_bytes() / max(1, world) / (3 * 8 * ncol))))
         nh2 = nh                           # the streamed call runs over the same hours; one set of pinned buffers serves both
         hP = torch.empty((nh2, ncol), dtype=torch.float64).pin_memory()
         hE = torch.empty((nh2, ncol), dtype=torch.float64).pin_memory()
