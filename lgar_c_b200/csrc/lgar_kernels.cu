@@ -905,6 +905,9 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
 // skipped), so a lane is served at least once per cycle and a plain step rides one cycle from FETCH to TAIL.  The variant
 // above leaves each lane to its own `switch`: the (up to 8) lanes of a warp sit in different stages and the hardware runs
 // them one after the other -- the serial chain of a column then costs the SUM of what its warp neighbours do.
+#ifndef LGAR_COOP_AFTER
+#define LGAR_COOP_AFTER 256   // trips a search must have behind it before its warp takes it over (finishing kernel)
+#endif
 __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_vote_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int quantum) {
   const unsigned FULL = 0xFFFFFFFFu;
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
@@ -951,7 +954,29 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_vote_ker
         cur = (cur + 1 == LGAR_NSTAGE) ? 0 : cur + 1;
         if (m[cur]) break;
       }
-      if (L.stage == cur) {
+      if (cur == LG_ST_SEARCH) {
+        // every searching lane runs `quantum` trips of its own search (the mean search takes 41).  A search that has then
+        // been going for LGAR_COOP_AFTER trips or more is one of the monsters (10^3 - 10^5 trips: a single one is 5-50 ms of
+        // dependent FP64 work for one thread, and this kernel lasts as long as the longest chain of them): the whole warp
+        // finishes it, 32 trips at a time (lg_search_warp, same numbers).
+        const bool mine = L.stage == LG_ST_SEARCH;
+        if (mine)
+          for (int it = 0; it < quantum && !L.q.done; it++) lg_search_iter(L.q, *L.cls);
+        unsigned ms = __ballot_sync(FULL, mine && !L.q.done && L.q.iter >= LGAR_COOP_AFTER);
+        while (ms) {
+          const int src = __ffs(ms) - 1;
+          ms &= ms - 1;
+          LgSearch qq = L.q;
+          lg_search_bcast(qq, src);
+          const LgarColumnClass* cp = reinterpret_cast<const LgarColumnClass*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(L.cls), src));
+          lg_search_warp(qq, *cp, 1 << 30);
+          if ((threadIdx.x & 31) == src) L.q = qq;
+        }
+        if (mine && L.q.done) {
+          L.resume = true;
+          L.stage = LG_ST_FRONT;
+        }
+      } else if (L.stage == cur) {
         switch (cur) {
           case LG_ST_FETCH: lg_stage_fetch(cfg, d, w, L, fsp); break;
           case LG_ST_HEAD:
@@ -959,13 +984,6 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_vote_ker
             active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
             break;
           case LG_ST_FRONT: lg_stage_front(L); break;
-          case LG_ST_SEARCH:
-            for (int it = 0; it < quantum && !L.q.done; it++) lg_search_iter(L.q, *L.cls);
-            if (L.q.done) {
-              L.resume = true;
-              L.stage = LG_ST_FRONT;
-            }
-            break;
           case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, fsp); break;
           default:
             for (int it = 0; it < quantum && !L.k.done; it++) lg_corr_iter(L.k, L.f, *L.cls);

@@ -263,6 +263,24 @@ __device__ __noinline__ void lg_search_warp(LgSearch& q, const LgarColumnClass& 
     budget -= jl + 1;
   }
 }
+// the search record of lane `src` to every lane of the warp
+__device__ __forceinline__ void lg_search_bcast(LgSearch& q, int src) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  q.psi_loc = lg_shfl(q.psi_loc, src); q.factor = lg_shfl(q.factor, src); q.psi_prev = lg_shfl(q.psi_prev, src);
+  q.delta_mass = lg_shfl(q.delta_mass, src); q.delta_mass_prev = lg_shfl(q.delta_mass_prev, src);
+  q.new_mass = lg_shfl(q.new_mass, src); q.prior_mass = lg_shfl(q.prior_mass, src);
+  q.precip_mass_to_add = lg_shfl(q.precip_mass_to_add, src); q.theta = lg_shfl(q.theta, src);
+#pragma unroll
+  for (int k = 0; k <= LGAR_MAXL; k++) {
+    q.dth[k] = lg_shfl(q.dth[k], src);
+    q.dz[k] = lg_shfl(q.dz[k], src);
+  }
+  q.layer_num = __shfl_sync(FULL, q.layer_num, src); q.iter = __shfl_sync(FULL, q.iter, src);
+  q.count_no_mass_change = __shfl_sync(FULL, q.count_no_mass_change, src);
+  const int flags = (q.switched ? 1 : 0) | (q.wanted_to_saturate ? 2 : 0) | (q.aug ? 4 : 0) | (q.aug_extreme ? 8 : 0) | (q.done ? 16 : 0);
+  const int fj = __shfl_sync(FULL, flags, src);
+  q.switched = fj & 1; q.wanted_to_saturate = (fj & 2) != 0; q.aug = (fj & 4) != 0; q.aug_extreme = (fj & 8) != 0; q.done = (fj & 16) != 0;
+}
 #endif
 
 // what follows the loop in lgar_theta_mass_balance (lgar.cxx:3096-3110); only after an iterated search
