@@ -1,0 +1,43 @@
+"""bench.py's CPU side: the reference arm prints ONE JSON line with the keys the driver reads, the standalone-executable
+baseline runs, and the helper that bounds the pinned e2e buffers returns something sensible.  No GPU."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+
+HAVE_REF = (ROOT / "oracle" / "_ref" / "liblgar_ref.so").exists() or (ROOT / "oracle" / "liblgar_oracle.so").exists()
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="no CPU oracle built")
+def test_reference_arm_prints_one_json_line():
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-cols-per-core", "2",
+                        "--hours-per-step", "24", "--spinup-hours", "24"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "column-timesteps/sec" and line["unit"] == "column-timesteps/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1 and line["warmup"] == 0
+    assert line["config"]["workload"] == "config5-shard" and line["dtype"] == "f64"
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.skipif(not (ROOT / "oracle" / "_ref" / "lasam_standalone").exists(), reason="reference executable not built")
+def test_standalone_executable_baseline_runs():
+    v = bench.run_standalone_exe(2, 2, 72)
+    assert v is not None and v > 0
+    e = bench.standalone_exe_entry(1, 1, 48)
+    assert e["kind"] == "reference" and e["cores"] == 1 and e["value"] > 0
+
+
+def test_host_memory_helper():
+    m = bench.host_memory_bytes()
+    assert 1 << 28 < m < 1 << 50
