@@ -41,3 +41,19 @@ def test_standalone_executable_baseline_runs():
 def test_host_memory_helper():
     m = bench.host_memory_bytes()
     assert 1 << 28 < m < 1 << 50
+
+
+@pytest.mark.skipif(not (ROOT / "oracle" / "_ref" / "liblgar_ref.so").exists(), reason="reference harness not built")
+def test_parity_sampling_tool_selftest(tmp_path):
+    """tools/parity_sampling_full.py with the unmodified reference standing in for the engine: the bookkeeping of the
+    full-duration parity report (forcing of configs 3/4/5 by global column id, per-step diff, final fronts) must find nothing."""
+    out = tmp_path / "pf.json"
+    r = subprocess.run([sys.executable, str(ROOT / "tools" / "parity_sampling_full.py"), "--selftest", "--sample", "3", "--steps", "150",
+                        "--cores", "2", "--configs", "3,4,5", "--out", str(out)], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rep = json.loads(out.read_text())
+    for name in ("config3", "config4", "config5"):
+        c = rep["configs"][name]
+        assert c["column_steps_diffed"] == 450 and c["front_count_mismatch_columns"] == 0 and c["failure_mismatch_columns"] == 0
+        assert c["final_front_flag_mismatch_columns"] == 0 and c["final_front_field_mismatch_columns"] == 0
+        assert all(v["columns_outside_bar"] == 0 for v in c["scalars"].values())
