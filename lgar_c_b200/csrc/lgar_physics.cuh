@@ -144,10 +144,19 @@ LG_FN_NOINLINE double lg_Se_from_h(double h, const LgarLayer& s) {
   return lg_exp(-s.m * lg_log(1.0 + lg_exp(s.n * (s.ln_alpha + lg_log(h)))));
 }
 #endif
-// calc_K_from_Se, soil_funcs.cxx:164-167 (pow(x,2.0) -> x*x)
+// pow(x, 2.0) (soil_funcs.cxx:166) and pow(x, 3.0) (aet.cxx:60): products in the default build, the library function in the
+// parity-first builds (a pow that is not correctly rounded can differ from the product in the last bit)
+#if defined(LGAR_ACCURATE_POW) || defined(LGAR_EXACT_POW)
+LG_FN double lg_pow2(double x) { return lg_pow(x, 2.0); }
+LG_FN double lg_pow3(double x) { return lg_pow(x, 3.0); }
+#else
+LG_FN double lg_pow2(double x) { return x * x; }
+LG_FN double lg_pow3(double x) { return x * x * x; }
+#endif
+// calc_K_from_Se, soil_funcs.cxx:164-167
 // Ksat is an argument: the reference passes Ks * frozen_factor[layer] at some call sites and plain Ks at others
 LG_FN_NOINLINE double lg_K_from_Se(double Se, const LgarLayer& s, double Ksat) {
-  return Ksat * sqrt(Se) * lg_sq(1.0 - lg_pow(1.0 - lg_pow(Se, s.inv_m), s.m));
+  return Ksat * sqrt(Se) * lg_pow2(1.0 - lg_pow(1.0 - lg_pow(Se, s.inv_m), s.m));
 }
 // calc_h_from_Se, soil_funcs.cxx:172-179
 LG_FN_NOINLINE double lg_h_from_Se(double Se, const LgarLayer& s) {
@@ -1101,7 +1110,7 @@ LG_FN double lg_calc_aet(const LgCtx& c, double PET_cm_per_h, double dt_h) {
   double aet = 0.0;
   if (f.psi[0] < 1.E6) {
     double r = f.psi[0] / c.cls->psi_50_cm[f.layer[0]];
-    double h_ratio = 1.0 + r * r * r;
+    double h_ratio = 1.0 + lg_pow3(r);
     aet = PET_cm_per_h * (1 / h_ratio) * dt_h;
     if (aet < 0)
       aet = 0.0;

@@ -69,7 +69,41 @@ def test_kernel_text_matches_golden(hostsim, name, force, tmp_path):
             assert_fronts_close(fr[t], fl[t], g["ck_fronts"][i], g["ck_flags"][i], int(nf[t]), f"{name}@{t}", rtol=1e-10)
 
 
-def test_more_than_16_fronts(hostsim, tmp_path):
+@pytest.fixture(scope="module")
+def hostsim_libm_pow():
+    """The same kernel text with x^y = the library pow (-DLGAR_ACCURATE_POW; on the host that is glibc's pow, the function
+    the reference calls) and pow(x,2)/pow(x,3) through it as well."""
+    so = HS / "libhostsim_acc.so"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-DLGAR_ACCURATE_POW", "-o", str(so),
+                           str(HS / "hostsim.cpp")])
+    lib = C.CDLL(str(so))
+    lib.hostsim_run_series.argtypes = [C.c_char_p, _ip, _dp, C.c_int, _dp, _dp, _dp, _ip, C.c_int, _dp, _ip, C.c_int, _ip, C.c_char_p, C.c_int]
+    lib.hostsim_run_series.restype = C.c_int
+    return lib
+
+
+@pytest.mark.parametrize("force", [0, 4])
+@pytest.mark.parametrize("name", STANDARD + RANDOM)
+def test_kernel_text_with_library_pow_is_bit_exact(hostsim_libm_pow, name, force, tmp_path):
+    """With the reference's own pow underneath, the kernel text (hour-by-hour functions, force 0; staged lane program,
+    force 4) reproduces the unmodified reference BIT FOR BIT on every golden case: all 12 per-step scalars, front counts,
+    and depth/theta/psi/K/dzdt/layer/to_bottom of every front at the checkpoints.  So the only thing between the engine
+    and the reference is the evaluation of x^y (exp(y log x) on the device, <= 1e-14 relative per call) --
+    the logic, the order of the arithmetic and every quirk of SURVEY.md 8c are identical."""
+    g = load_golden(name)
+    n = min(len(g["precip"]), 3000)
+    done, scal, nf, fr, fl, status = run(hostsim_libm_pow, config_for(name, tmp_path), g["precip"][:n], g["pet"][:n], force)
+    assert done == n and status & 0xFFFF == 0
+    assert np.array_equal(nf, g["nfronts"][:n])
+    assert np.array_equal(scal, g["scalars"][:n]), f"{name}: {np.count_nonzero(scal != g['scalars'][:n])} scalars differ in the last bits"
+    for i, t in enumerate(g["ck_steps"]):
+        if t < n and (force == 0 or t == n - 1):   # the window modes export the fronts at the end of the window only
+            k = int(nf[t])
+            assert np.array_equal(fl[t][:k], g["ck_flags"][i][:k])
+            assert np.array_equal(fr[t][:k], g["ck_fronts"][i][:k]), f"{name}@{t}: front fields differ in the last bits"
+
+
+def test_more_than_16_fronts(hostsim, hostsim_libm_pow, tmp_path):
     """Column 5588097 of BASELINE config 5 reaches 19 wetting fronts at hour 5641 of the year (tools/parity_sampling_full.py):
     the kernel text with its 32-front capacity and two flag words must follow the oracle through it."""
     import sys
@@ -94,3 +128,7 @@ def test_more_than_16_fronts(hostsim, tmp_path):
         assert_scalars_close(scal, o["scalars"], "config5 column 5588097", rtol=1e-9)
         t = T - 1 if force else int(np.argmax(nf))
         assert_fronts_close(fr[t], fl[t], o["fronts"][t], o["flags"][t], int(nf[t]), f"deep@{t}", rtol=1e-9)
+        # and bit for bit with the library pow underneath (the oracle calls the same glibc pow as the reference)
+        done, scal, nf, fr, fl, status = run(hostsim_libm_pow, cfg, P, E, force, cap=32)
+        assert done == T and np.array_equal(nf, o["nfronts"]) and np.array_equal(scal, o["scalars"])
+        assert np.array_equal(fr[t][:int(nf[t])], o["fronts"][t][:int(nf[t])])
