@@ -1,0 +1,143 @@
+// lgar_c_b200/csrc/lgar_ctx.cuh -- the lane record's way between HBM and a stage's own copy: queue append, 256-bit
+// context copies, the parts of the record each stage moves.  Shared by lgar_kernels.cu (stage kernels, finishing kernels)
+// and lgar_finish_smem.cu (finishing kernel with the records in shared memory).
+#pragma once
+#include <cstddef>
+
+#include "lgar_lanes.cuh"
+
+namespace {
+
+__device__ __forceinline__ void wave_push(const LgarWave& wv, unsigned append_mask, int stage, bool pred, int slot) {
+  const unsigned m = __ballot_sync(__activemask(), pred);
+  if (!pred) return;
+  const int buf = (append_mask >> stage) & 1;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(wv.qcount + stage * 2 + buf, __popc(m));
+  base = __shfl_sync(m, base, leader);
+  wv.queue[stage][buf][base + __popc(m & ((1u << lane) - 1))] = slot;
+}
+
+// Context copy between HBM and thread-private memory.  The HBM side moves 32 bytes per lane per instruction
+// (LDG/STG.E.256, new on sm_100): a lane's record is contiguous, so every access is one full 32-byte sector --
+// with 16-byte accesses each sector is requested twice (ncu: lts write sectors = 2x the bytes stored).
+// NBYTES = leading part of the record to move.
+template <int NBYTES, typename T>
+__device__ __forceinline__ void ctx_load(T* local_dst, const T* global_src) {
+  static_assert(NBYTES % 32 == 0 && NBYTES <= (int)sizeof(T), "context part must be a multiple of 32 bytes");
+  const char* g = reinterpret_cast<const char*>(global_src);
+  ulonglong2* l = reinterpret_cast<ulonglong2*>(local_dst);
+#pragma unroll 8
+  for (int i = 0; i < NBYTES / 32; i++) {
+    unsigned long long a, b, c, e;
+    asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(e) : "l"(g + 32 * i));
+    l[2 * i] = make_ulonglong2(a, b);
+    l[2 * i + 1] = make_ulonglong2(c, e);
+  }
+}
+template <int NBYTES, typename T>
+__device__ __forceinline__ void ctx_store(T* global_dst, const T* local_src) {
+  static_assert(NBYTES % 32 == 0 && NBYTES <= (int)sizeof(T), "context part must be a multiple of 32 bytes");
+  char* g = reinterpret_cast<char*>(global_dst);
+  const ulonglong2* l = reinterpret_cast<const ulonglong2*>(local_src);
+#pragma unroll 8
+  for (int i = 0; i < NBYTES / 32; i++) {
+    const ulonglong2 x = l[2 * i], y = l[2 * i + 1];
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(g + 32 * i), "l"(x.x), "l"(x.y), "l"(y.x), "l"(y.y) : "memory");
+  }
+}
+
+// dynamic-length variants (nchunks 32-byte chunks)
+__device__ __forceinline__ void ctx_load_n(char* l, const char* g, int nchunks) {
+#pragma unroll 1
+  for (int i = 0; i < nchunks; i++) {
+    unsigned long long a, b, c, e;
+    asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(e) : "l"(g + 32 * i));
+    reinterpret_cast<ulonglong2*>(l)[2 * i] = make_ulonglong2(a, b);
+    reinterpret_cast<ulonglong2*>(l)[2 * i + 1] = make_ulonglong2(c, e);
+  }
+}
+__device__ __forceinline__ void ctx_store_n(char* g, const char* l, int nchunks) {
+#pragma unroll 1
+  for (int i = 0; i < nchunks; i++) {
+    const ulonglong2 x = reinterpret_cast<const ulonglong2*>(l)[2 * i], y = reinterpret_cast<const ulonglong2*>(l)[2 * i + 1];
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(g + 32 * i), "l"(x.x), "l"(x.y), "l"(y.x), "l"(y.y) : "memory");
+  }
+}
+
+}  // namespace
+
+struct alignas(32) LgLaneSlot {
+  LgLane L;
+};
+
+// Parts of the lane record (lgar_lanes.cuh) a stage moves between HBM and its thread-private copy.  The front
+// arrays have capacity LGAR_W = 32 but a column carries 4-5 fronts on average: only the live prefix of each
+// array travels (counts kept in the record's first sector), which removes about a third of the context traffic.
+enum { LG_PART_STATE = 1, LG_PART_STEP = 2, LG_PART_OLD = 4, LG_PART_SEARCH = 8, LG_PART_ALL = 15 };
+constexpr int kOffF = (int)offsetof(LgLane, f), kOffPro = (int)offsetof(LgLane, pro), kOffOld = (int)offsetof(LgLane, old),
+              kOffQ = (int)offsetof(LgLane, q);
+constexpr int kFrontTail = (int)offsetof(LgFronts, layer);  // layer[], tb[], n behind the five double arrays
+static_assert(kOffF % 32 == 0 && kOffPro % 32 == 0 && kOffOld % 32 == 0 && kOffQ % 32 == 0 && sizeof(LgLaneSlot) % 32 == 0, "LgLane layout");
+constexpr int kPitch = 8 * LGAR_W;                           // bytes between the arrays of LgFronts / LgOld
+constexpr int kFrontTailBytes = kOffPro - kOffF - kFrontTail;  // layer[], tb[], n (+ padding up to `pro`)
+static_assert(offsetof(LgFronts, depth) == 0 && offsetof(LgFronts, theta) == kPitch && offsetof(LgFronts, psi) == 2 * kPitch &&
+                  offsetof(LgFronts, K) == 3 * kPitch && offsetof(LgFronts, dzdt) == 4 * kPitch && kFrontTail == 5 * kPitch &&
+                  kFrontTailBytes % 32 == 0 && kFrontTailBytes >= 2 * LGAR_W + 4 && kPitch % 32 == 0,
+              "LgFronts layout");
+static_assert(offsetof(LgOld, theta) == kPitch && offsetof(LgOld, psi) == 2 * kPitch && offsetof(LgOld, n) == 3 * kPitch && kOffQ - kOffOld == 3 * kPitch + 32,
+              "LgOld layout");
+static_assert(offsetof(LgLane, nold_stored) < 32, "front counts must sit in the first sector of the record");
+
+template <int PARTS>
+__device__ __forceinline__ void lane_load(LgLaneSlot* S, const LgLaneSlot* G) {
+  char* l = reinterpret_cast<char*>(S);
+  const char* g = reinterpret_cast<const char*>(G);
+  ctx_load<32>(S, G);  // first sector: stage, hour, column, class, front counts
+  const int cf = (S->L.nf_stored + 3) >> 2, co = (S->L.nold_stored + 3) >> 2;
+  if (PARTS & LG_PART_STATE) {
+    ctx_load<kOffF - 32>(reinterpret_cast<LgLaneSlot*>(l + 32), reinterpret_cast<const LgLaneSlot*>(g + 32));
+#pragma unroll
+    for (int a = 0; a < 5; a++) ctx_load_n(l + kOffF + kPitch * a, g + kOffF + kPitch * a, cf);
+    ctx_load<kFrontTailBytes>(reinterpret_cast<LgLaneSlot*>(l + kOffF + kFrontTail), reinterpret_cast<const LgLaneSlot*>(g + kOffF + kFrontTail));
+  }
+  if (PARTS & LG_PART_STEP) ctx_load<kOffOld - kOffPro>(reinterpret_cast<LgLaneSlot*>(l + kOffPro), reinterpret_cast<const LgLaneSlot*>(g + kOffPro));
+  if (PARTS & LG_PART_OLD) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) ctx_load_n(l + kOffOld + kPitch * a, g + kOffOld + kPitch * a, co);
+    ctx_load<32>(reinterpret_cast<LgLaneSlot*>(l + kOffOld + 3 * kPitch), reinterpret_cast<const LgLaneSlot*>(g + kOffOld + 3 * kPitch));
+  }
+  if (PARTS & LG_PART_SEARCH)
+    ctx_load<(int)sizeof(LgLaneSlot) - kOffQ>(reinterpret_cast<LgLaneSlot*>(l + kOffQ), reinterpret_cast<const LgLaneSlot*>(g + kOffQ));
+#ifdef LGAR_POISON  // validation build: whatever was not moved must never be read
+  if (PARTS & LG_PART_STATE)
+    for (int i = 4 * cf; i < LGAR_W; i++) S->L.f.depth[i] = S->L.f.theta[i] = S->L.f.psi[i] = S->L.f.K[i] = S->L.f.dzdt[i] = LG_NAN;
+  if (PARTS & LG_PART_OLD)
+    for (int i = 4 * co; i < LGAR_W; i++) S->L.old.depth[i] = S->L.old.theta[i] = S->L.old.psi[i] = LG_NAN;
+#endif
+}
+template <int PARTS>
+__device__ __forceinline__ void lane_store(LgLaneSlot* G, LgLaneSlot* S) {
+  const char* l = reinterpret_cast<const char*>(S);
+  char* g = reinterpret_cast<char*>(G);
+  if (PARTS & LG_PART_STATE) S->L.nf_stored = S->L.f.n;
+  if (PARTS & LG_PART_OLD) S->L.nold_stored = S->L.old.n;
+  const int cf = (S->L.nf_stored + 3) >> 2, co = (S->L.nold_stored + 3) >> 2;
+  ctx_store<32>(G, S);
+  if (PARTS & LG_PART_STATE) {
+    ctx_store<kOffF - 32>(reinterpret_cast<LgLaneSlot*>(g + 32), reinterpret_cast<const LgLaneSlot*>(l + 32));
+#pragma unroll
+    for (int a = 0; a < 5; a++) ctx_store_n(g + kOffF + kPitch * a, l + kOffF + kPitch * a, cf);
+    ctx_store<kFrontTailBytes>(reinterpret_cast<LgLaneSlot*>(g + kOffF + kFrontTail), reinterpret_cast<const LgLaneSlot*>(l + kOffF + kFrontTail));
+  }
+  if (PARTS & LG_PART_STEP) ctx_store<kOffOld - kOffPro>(reinterpret_cast<LgLaneSlot*>(g + kOffPro), reinterpret_cast<const LgLaneSlot*>(l + kOffPro));
+  if (PARTS & LG_PART_OLD) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) ctx_store_n(g + kOffOld + kPitch * a, l + kOffOld + kPitch * a, co);
+    ctx_store<32>(reinterpret_cast<LgLaneSlot*>(g + kOffOld + 3 * kPitch), reinterpret_cast<const LgLaneSlot*>(l + kOffOld + 3 * kPitch));
+  }
+  if (PARTS & LG_PART_SEARCH)
+    ctx_store<(int)sizeof(LgLaneSlot) - kOffQ>(reinterpret_cast<LgLaneSlot*>(g + kOffQ), reinterpret_cast<const LgLaneSlot*>(l + kOffQ));
+}

@@ -113,6 +113,7 @@ struct lgarb_engine {
   cudaEvent_t side_ev[2] = {nullptr, nullptr};
   int wave_finish_below = 16384;
   int finish_lane_stride = 4;  // finishing kernel: one slot per this many lanes
+  int finish_smem = 0;         // finishing kernel keeps the lane records in shared memory (opt-in until measured)
   int update_wave_min_cols = 1 << 30;  // lgarb_update: batches of at least this many columns take the wavefront kernels
   int wave_windows = 0;  // windows run so far (profiling range selection)
   int wave_escalate_below = 8192;
@@ -791,6 +792,7 @@ int lgarb_create(lgarb_engine** out) {
   knob("LGARB_WARP_SEARCH_MULT", (*out)->warp_search_mult);
   knob("LGARB_WAVE_FINISH_BELOW", (*out)->wave_finish_below);
   knob("LGARB_FINISH_LANE_STRIDE", (*out)->finish_lane_stride);
+  knob("LGARB_FINISH_SMEM", (*out)->finish_smem);
   knob("LGARB_UPDATE_WAVE_MIN_COLS", (*out)->update_wave_min_cols);
   knob("LGARB_WAVE_ESCALATE_BELOW", (*out)->wave_escalate_below);
   knob("LGARB_WAVE_CORR_QUANTUM", (*out)->wave_corr_quantum);
@@ -985,7 +987,10 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       if (in_flight == 0) break;
       if (in_flight <= e->wave_finish_below) {  // the stragglers: one thread per slot runs its column to the end of the window
         if (debug) cudaEventRecord(dbg[0], e->stream);
-        CUDA_TRY(lgar_launch_wave_finish(e->cfg, e->d, w, wv, in_flight, e->finish_lane_stride, e->stream));
+        if (e->finish_smem && e->finish_lane_stride > 0)
+          CUDA_TRY(lgar_launch_wave_finish_smem(e->cfg, e->d, w, wv, in_flight, e->finish_lane_stride, e->stream));
+        else
+          CUDA_TRY(lgar_launch_wave_finish(e->cfg, e->d, w, wv, in_flight, e->finish_lane_stride, e->stream));
         e->launches += 2;
         if (debug) {
           cudaEventRecord(dbg[1], e->stream);

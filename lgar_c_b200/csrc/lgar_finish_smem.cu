@@ -1,0 +1,106 @@
+// lgar_c_b200/csrc/lgar_finish_smem.cu -- finishing kernel of the wavefront scheduler with the lane records in SHARED memory
+// (opt-in: LGARB_FINISH_SMEM=1; default off until it has been measured on a B200).
+//
+// lgar_wave_finish_kernel (lgar_kernels.cu) keeps the record of its slot in a 3.3 KB thread-private variable.  Local memory
+// is interleaved by lane -- a 128-byte line holds one word of each of the 32 lanes of a warp -- so a warp's records occupy
+// 32 x 3.3 KB = 104 KB of L1 however many of its lanes own a slot, 420 KB per block: the records live in L2 and every access
+// of the serial chain that sets the length of that kernel pays an L2 round trip.  Here a block
+// keeps its 128 / lane_stride records in dynamic shared memory (pitch 103 x 32 bytes: 32-byte aligned for the record's
+// alignas(32) members, and an odd number of 32-byte units so that the owners of a warp's slots fall on different banks,
+// two-way at worst).  The stage functions and their arithmetic are those of the kernel in lgar_kernels.cu; results are bit
+// for bit the same (tests/test_gpu_parity.py::test_scheduling_invariance runs this variant beside the others).
+//
+// A translation unit of its own on purpose: the device functions of lgar_lanes.cuh are inlined per module by cost, and one
+// more caller inside lgar_kernels.cu changed the SASS of every measured kernel there.
+#define LGAR_TU_LOCAL 1
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "lgar_ctx.cuh"
+#include "lgar_kernels.h"
+
+constexpr int kFinishSmemPitch = (((int)sizeof(LgLaneSlot) / 32) | 1) * 32;
+static_assert(kFinishSmemPitch >= (int)sizeof(LgLaneSlot) && kFinishSmemPitch % 64 == 32, "shared pitch: holds a record, odd multiple of 32 bytes");
+
+__global__ void __launch_bounds__(128) lgar_wave_finish_smem_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int lane_stride) {
+  extern __shared__ __align__(128) unsigned char lg_finish_smem[];
+  LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
+  int total = 0;
+  for (int q = 0; q < 2 * LGAR_NSTAGE; q++) total += wv.qcount[q];
+  unsigned long long front_sum = 0, active_sum = 0;
+  unsigned long long* fsp = w.prof ? &front_sum : nullptr;
+  if (threadIdx.x % lane_stride != 0) return;  // lane_stride divides the block size (launcher); no block-wide barrier below
+  const int per_block = blockDim.x / lane_stride;
+  LgLaneSlot& S = *reinterpret_cast<LgLaneSlot*>(lg_finish_smem + (size_t)(threadIdx.x / lane_stride) * kFinishSmemPitch);
+  for (int i = blockIdx.x * per_block + threadIdx.x / lane_stride; i < total; i += gridDim.x * per_block) {
+    int j = i, slot = -1, stage = LG_ST_DONE;
+    for (int q = 0; q < 2 * LGAR_NSTAGE; q++) {  // item i of the concatenation of all queues
+      const int n = wv.qcount[q];
+      if (j < n) {
+        slot = wv.queue[q >> 1][q & 1][j];
+        stage = q >> 1;
+        break;
+      }
+      j -= n;
+    }
+    if (slot < 0) continue;
+    lane_load<LG_PART_ALL>(&S, &slots[slot]);
+    LgLane& L = S.L;
+    L.stage = stage;  // the queue a slot sits in is authoritative: the partial-context stages do not rewrite L.stage
+    L.c.cfg = &cfg;
+    L.c.cls = L.cls;
+    L.c.f = &L.f;
+    L.c.ff = lg_ff_ones;
+    while (L.stage != LG_ST_DONE) {
+      switch (L.stage) {
+        case LG_ST_FETCH: lg_stage_fetch(cfg, d, w, L, fsp); break;
+        case LG_ST_HEAD:
+          lg_stage_head(cfg, d, w, L, fsp);
+          active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
+          break;
+        case LG_ST_FRONT: lg_stage_front(L); break;
+        case LG_ST_SEARCH: {
+          LgSearch q = L.q;  // the 176-byte search record in registers / thread-private memory for the trips
+          while (!q.done) lg_search_iter(q, *L.cls);
+          L.q = q;
+          L.resume = true;
+          L.stage = LG_ST_FRONT;
+          break;
+        }
+        case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, fsp); break;
+        case LG_ST_CORR:
+          while (!L.k.done) lg_corr_iter(L.k, L.f, *L.cls);
+          L.stage = LG_ST_TAIL;
+          break;
+        default: L.stage = LG_ST_DONE; break;
+      }
+    }
+  }
+  if (w.prof) {
+    if (front_sum) atomicAdd(w.prof, front_sum);
+    if (active_sum) atomicAdd(w.prof + 1, active_sum);
+  }
+}
+
+static __global__ void lgar_wave_clear_smem_kernel(LgarWave wv) {
+  if (threadIdx.x < 2 * LGAR_NSTAGE) wv.qcount[threadIdx.x] = 0;
+}
+
+cudaError_t lgar_launch_wave_finish_smem(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
+                                         int lane_stride, cudaStream_t stream) {
+  int ls = 2;  // a power of two in [2, 32]: 64 records (206 KB) per block at most
+  while (ls < lane_stride && ls < 32) ls *= 2;
+  const int per_block = 128 / ls;
+  const int bytes = per_block * kFinishSmemPitch;
+  static int configured = -1;  // largest dynamic size opted in to so far (one device per process)
+  if (bytes > configured) {
+    cudaError_t rc = cudaFuncSetAttribute(lgar_wave_finish_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (rc != cudaSuccess) return rc;
+    configured = bytes;
+  }
+  const int blocks = std::max(1, std::min((in_flight + per_block - 1) / per_block, 148 * 16));
+  lgar_wave_finish_smem_kernel<<<blocks, 128, bytes, stream>>>(cfg, d, w, wv, ls);
+  lgar_wave_clear_smem_kernel<<<1, 32, 0, stream>>>(wv);
+  return cudaGetLastError();
+}

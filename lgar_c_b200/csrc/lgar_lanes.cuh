@@ -204,7 +204,7 @@ LG_FN void lg_search_iter(LgSearch& q, const LgarColumnClass& cls) {
 // search of 10^4 trips (the tail that sets the length of a window) takes ~300 warp steps instead of 10^4 dependent
 // trips; the numbers are those of lg_search_iter bit for bit, whatever the grouping.
 __device__ __forceinline__ double lg_shfl(double v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
-__device__ __noinline__ void lg_search_warp(LgSearch& q, const LgarColumnClass& cls, int max_trips) {
+LG_FN_NOINLINE void lg_search_warp(LgSearch& q, const LgarColumnClass& cls, int max_trips) {
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   int budget = max_trips;

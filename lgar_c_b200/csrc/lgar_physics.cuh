@@ -27,7 +27,11 @@
 using std::exp; using std::fabs; using std::fmax; using std::fmin; using std::isinf; using std::isnan; using std::log; using std::sqrt;
 #else
 #define LG_FN __device__ __forceinline__
+#ifdef LGAR_TU_LOCAL   // a second translation unit that includes the physics (lgar_finish_smem.cu): internal linkage
+#define LG_FN_NOINLINE static __device__ __noinline__
+#else
 #define LG_FN_NOINLINE __device__ __noinline__
+#endif
 // Lanes that entered a function together meet again at LG_RECONVERGE before the expensive common part.  Without it
 // a function with an early exit in a divergent loop runs its common tail once per group of lanes (ncu source
 // view of the TAIL kernel: the K/psi refresh of lg_move_end ran at 17 of 32 lanes before its own loop divergence).
@@ -87,6 +91,8 @@ struct LgCtx {
 };
 #ifdef LGAR_HOSTSIM
 static const double lg_ff_ones[LGAR_MAXL + 2] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+#elif defined(LGAR_TU_LOCAL)
+static __device__ const double lg_ff_ones[LGAR_MAXL + 2] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
 #else
 __device__ const double lg_ff_ones[LGAR_MAXL + 2] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
 #endif
