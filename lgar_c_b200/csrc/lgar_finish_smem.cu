@@ -31,9 +31,10 @@ __global__ void __launch_bounds__(128) lgar_wave_finish_smem_kernel(const __grid
   unsigned long long front_sum = 0, active_sum = 0;
   unsigned long long* fsp = w.prof ? &front_sum : nullptr;
   if (threadIdx.x % lane_stride != 0) return;  // lane_stride divides the block size (launcher); no block-wide barrier below
-  const int per_block = blockDim.x / lane_stride;
   LgLaneSlot& S = *reinterpret_cast<LgLaneSlot*>(lg_finish_smem + (size_t)(threadIdx.x / lane_stride) * kFinishSmemPitch);
-  for (int i = blockIdx.x * per_block + threadIdx.x / lane_stride; i < total; i += gridDim.x * per_block) {
+  // persistent blocks (the launcher sizes the grid to what is resident at once); a thread that has finished its column takes
+  // the next item from the cursor, so a block is not held up by the order the items happen to sit in
+  for (int i = atomicAdd(wv.cursor, 1); i < total; i = atomicAdd(wv.cursor, 1)) {
     int j = i, slot = -1, stage = LG_ST_DONE;
     for (int q = 0; q < 2 * LGAR_NSTAGE; q++) {  // item i of the concatenation of all queues
       const int n = wv.qcount[q];
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(128) lgar_wave_finish_smem_kernel(const __grid
 
 static __global__ void lgar_wave_clear_smem_kernel(LgarWave wv) {
   if (threadIdx.x < 2 * LGAR_NSTAGE) wv.qcount[threadIdx.x] = 0;
+  if (threadIdx.x == 0) *wv.cursor = 0;  // zero between launches (the FETCH kernel relies on it)
 }
 
 cudaError_t lgar_launch_wave_finish_smem(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
@@ -99,7 +101,10 @@ cudaError_t lgar_launch_wave_finish_smem(const LgarConfig& cfg, const LgarDevice
     if (rc != cudaSuccess) return rc;
     configured = bytes;
   }
-  const int blocks = std::max(1, std::min((in_flight + per_block - 1) / per_block, 148 * 16));
+  const int resident = std::max(1, (227 * 1024) / (bytes + 1024));  // blocks per SM that fit the shared memory
+  const int blocks = std::max(1, std::min((in_flight + per_block - 1) / per_block, 148 * resident));
+  cudaError_t rc = cudaMemsetAsync(wv.cursor, 0, sizeof(int32_t), stream);
+  if (rc != cudaSuccess) return rc;
   lgar_wave_finish_smem_kernel<<<blocks, 128, bytes, stream>>>(cfg, d, w, wv, ls);
   lgar_wave_clear_smem_kernel<<<1, 32, 0, stream>>>(wv);
   return cudaGetLastError();
