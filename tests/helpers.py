@@ -69,3 +69,31 @@ def assert_fronts_close(got, gflags, want, wflags, n, what="", rtol=RTOL):
         err = np.abs(g[:, j] - w[:, j])
         tol = tolj * np.maximum(np.abs(g[:, j]), np.abs(w[:, j])) + 1e-13
         assert np.all(err <= tol), f"{what}: front field {j} differs: {g[:, j]} vs {w[:, j]}"
+
+
+# Physics sanity of BASELINE config 2: the reference validates its synthetic cases by overlaying them on
+# HYDRUS-1D and LGAR-Py (tests/plot_synthetic_examples.ipynb, no asserted thresholds).  A fresh build of the reference is within
+# 1.43 / 5.31 mm (HYDRUS) and 1.21 / 2.61 mm (LGAR-Py) of their soil water storage on synth_1 / synth_2; the bars below are
+# those distances with a margin.  Fixtures: tests/golden/physics_synth_{1,2}.npz (tools/make_physics_golden.py).
+PHYSICS_BARS_MM = {"synth_1": dict(hydrus_storage=2.0, py_storage=1.5, cum_runoff=1.5),
+                   "synth_2": dict(hydrus_storage=6.0, py_storage=3.0, cum_runoff=1.5)}
+
+
+def assert_physics_sanity(name, storage_m, runoff_m, step_min=5.0):
+    """storage_m / runoff_m: per-step soil_storage and surface_runoff [m] of one column of synth_1 or synth_2.  Step i is
+    compared with the independent solutions at time i * step_min, the notebook's alignment."""
+    p = np.load(GOLDEN / f"physics_{name}.npz")
+    bars = PHYSICS_BARS_MM[name]
+    stor = np.asarray(storage_m, dtype=np.float64) * 1000.0
+    cum_ro = np.cumsum(np.asarray(runoff_m, dtype=np.float64)) * 1000.0
+    n = len(stor)
+    t = np.arange(n) * step_min
+    hs = np.interp(t, p["hydrus_time_min"], p["hydrus_storage_mm"])
+    d_h = float(np.abs(stor - hs).max())
+    assert d_h <= bars["hydrus_storage"], f"{name}: soil water storage is {d_h:.2f} mm from HYDRUS-1D (bar {bars['hydrus_storage']} mm)"
+    m = min(n, len(p["py_storage_mm"]))
+    d_p = float(np.abs(stor[:m] - p["py_storage_mm"][:m]).max())
+    assert d_p <= bars["py_storage"], f"{name}: soil water storage is {d_p:.2f} mm from LGAR-Py (bar {bars['py_storage']} mm)"
+    for label, total in (("HYDRUS-1D", float(p["hydrus_cum_runoff_mm"][-1])), ("LGAR-Py", float(np.sum(p["py_runoff_mm"])))):
+        assert abs(cum_ro[-1] - total) <= bars["cum_runoff"], f"{name}: cumulative runoff {cum_ro[-1]:.2f} mm vs {label} {total:.2f} mm"
+    return d_h, d_p

@@ -271,6 +271,34 @@ def test_replicated_columns_are_identical_100k(cuda_device, tmp_path):
     assert np.abs(mb[:, 15]).max() < 1e-6     # global balance closes (reference: 1.9e-9 cm on this case)
 
 
+@pytest.mark.parametrize("name", ["synth_1", "synth_2"])
+def test_synthetic_cases_100k_against_hydrus_and_lgar_py(cuda_device, name, tmp_path):
+    """BASELINE config 2 in full: synth_1 / synth_2 replicated to 100 000 columns, per-step soil_storage and surface_runoff of
+    every column identical to column 0, column 0 within 1e-9 of the reference's golden vector and within the millimetre-level
+    bars of the HYDRUS-1D and LGAR-Py solutions the reference ships (helpers.assert_physics_sanity)."""
+    from helpers import assert_physics_sanity
+    g = load_golden(name)
+    cfg = config_for(name, tmp_path)
+    import torch
+    import lgar_c_b200
+    ncol, T = 100_000, len(g["precip"])
+    b = lgar_c_b200.BmiLGARBatch()
+    b.initialize(cfg, ncol)
+    dP = torch.from_numpy(np.repeat(g["precip"][:, None], ncol, axis=1).copy()).cuda()
+    dE = torch.from_numpy(np.repeat(g["pet"][:, None], ncol, axis=1).copy()).cuda()
+    stor = torch.zeros((T, ncol), dtype=torch.float64, device="cuda")
+    ro = torch.zeros((T, ncol), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()  # the engine runs on its own stream: inputs/sinks made by torch must be complete
+    b.update_steps_device(T, dP.data_ptr(), dE.data_ptr(), ncol, {"soil_storage": stor.data_ptr(), "surface_runoff": ro.data_ptr()}, ncol)
+    b.synchronize()
+    s, r = stor.cpu().numpy(), ro.cpu().numpy()
+    assert (s == s[:, :1]).all() and (r == r[:, :1]).all()
+    for got, k in ((s[:, 0], 5), (r[:, 0], 3)):
+        want = g["scalars"][:, k]
+        assert np.all(np.abs(got - want) <= RTOL * np.maximum(np.abs(got), np.abs(want)) + 1e-14), f"{name}: scalar {k} leaves the 1e-9 bar"
+    assert_physics_sanity(name, s[:, 0], r[:, 0])
+
+
 def test_bmi_variable_access_semantics(cuda_device, tmp_path):
     import lgar_c_b200
     b = lgar_c_b200.BmiLGARBatch()
