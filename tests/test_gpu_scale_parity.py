@@ -70,8 +70,6 @@ def test_bench_workload_sample_against_oracle(cuda_device, oracle, tmp_path):
 def _assert_scheduling_variants_agree(tmp_path, variants):
     """Runs the bench workload on 200 000 columns x 2 windows once per (window mode, wave parameters, environment) variant and
     requires every output, status word and front to be bit-identical to the first variant's."""
-
-    import os
     import torch
     import bench
     import lgar_c_b200
