@@ -113,7 +113,8 @@ struct lgarb_engine {
   cudaEvent_t side_ev[2] = {nullptr, nullptr};
   int wave_finish_below = 16384;
   int finish_lane_stride = 4;  // finishing kernel: one slot per this many lanes
-  int finish_smem = 0;         // finishing kernel keeps the lane records in shared memory (opt-in until measured)
+  int finish_smem = 0;         // finishing kernel keeps the lane records in shared memory (opt-in until measured): 1 = one
+                               // slot per finish_lane_stride lanes, 2 = converged (one stage at a time per warp, lanes refill)
   int update_wave_min_cols = 1 << 30;  // lgarb_update: batches of at least this many columns take the wavefront kernels
   int wave_windows = 0;  // windows run so far (profiling range selection)
   int wave_escalate_below = 8192;
@@ -987,7 +988,9 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       if (in_flight == 0) break;
       if (in_flight <= e->wave_finish_below) {  // the stragglers: one thread per slot runs its column to the end of the window
         if (debug) cudaEventRecord(dbg[0], e->stream);
-        if (e->finish_smem && e->finish_lane_stride > 0)
+        if (e->finish_smem == 2)  // converged, records in shared memory; a negative lane stride = search trips per turn
+          CUDA_TRY(lgar_launch_wave_finish_smem(e->cfg, e->d, w, wv, in_flight, std::min(e->finish_lane_stride, 0), e->stream));
+        else if (e->finish_smem && e->finish_lane_stride > 0)
           CUDA_TRY(lgar_launch_wave_finish_smem(e->cfg, e->d, w, wv, in_flight, e->finish_lane_stride, e->stream));
         else
           CUDA_TRY(lgar_launch_wave_finish(e->cfg, e->d, w, wv, in_flight, e->finish_lane_stride, e->stream));

@@ -84,6 +84,102 @@ __global__ void __launch_bounds__(128) lgar_wave_finish_smem_kernel(const __grid
   }
 }
 
+// Converged variant with the records in shared memory (LGARB_FINISH_SMEM=2): one warp per block, every lane owns a record
+// (32 x 3 296 B = 103 KB, two blocks per SM), the warp executes ONE stage at a time for the lanes that are in it and goes
+// round the stages in program order -- lgar_wave_finish_vote_kernel of lgar_kernels.cu without the thread-private records --
+// and a lane whose column has finished the window takes the next item from the cursor, so the warp stays full until the
+// items run out.  With LGARB_WAVE_FINISH_BELOW above the column count this kernel runs the WHOLE window on chip: it is the
+// measurement of what DESIGN.md section 10 item 1 proposes (step context on chip, ~2-4 warps per SM, no context traffic at
+// stage boundaries), at the price of today's 32-front record size.
+__global__ void __launch_bounds__(32) lgar_wave_finish_vote_smem_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int quantum) {
+  extern __shared__ __align__(128) unsigned char lg_finish_smem[];
+  const unsigned FULL = 0xFFFFFFFFu;
+  LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
+  int total = 0;
+  for (int q = 0; q < 2 * LGAR_NSTAGE; q++) total += wv.qcount[q];
+  unsigned long long front_sum = 0, active_sum = 0;
+  unsigned long long* fsp = w.prof ? &front_sum : nullptr;
+  LgLaneSlot& S = *reinterpret_cast<LgLaneSlot*>(lg_finish_smem + (size_t)threadIdx.x * kFinishSmemPitch);  // blockDim.x == 32
+  LgLane& L = S.L;
+  L.stage = LG_ST_DONE;
+  bool exhausted = false;
+  int cur = LGAR_NSTAGE - 1;
+  for (;;) {
+    if (L.stage == LG_ST_DONE && !exhausted) {  // refill: the next item of the concatenation of all queues
+      int j = atomicAdd(wv.cursor, 1);
+      if (j < total) {
+        int slot = -1, stage = LG_ST_DONE;
+        for (int q = 0; q < 2 * LGAR_NSTAGE; q++) {
+          const int n = wv.qcount[q];
+          if (j < n) {
+            slot = wv.queue[q >> 1][q & 1][j];
+            stage = q >> 1;
+            break;
+          }
+          j -= n;
+        }
+        if (slot >= 0) {
+          lane_load<LG_PART_ALL>(&S, &slots[slot]);
+          L.c.cfg = &cfg;
+          L.c.cls = L.cls;
+          L.c.f = &L.f;
+          L.c.ff = lg_ff_ones;
+          L.stage = stage;  // the queue a slot sits in is authoritative
+        }
+      } else {
+        exhausted = true;
+      }
+    }
+    __syncwarp();
+    unsigned m[LGAR_NSTAGE];
+    unsigned any = 0;
+#pragma unroll
+    for (int s = 0; s < LGAR_NSTAGE; s++) {
+      m[s] = __ballot_sync(FULL, L.stage == s);
+      any |= m[s];
+    }
+    if (!any) {
+      if (__all_sync(FULL, exhausted)) break;
+      continue;  // some lane has just been told there is nothing left, or refills next turn
+    }
+#pragma unroll 1
+    for (int k = 0; k < LGAR_NSTAGE; k++) {  // next non-empty stage after the one just run
+      cur = (cur + 1 == LGAR_NSTAGE) ? 0 : cur + 1;
+      if (m[cur]) break;
+    }
+    if (L.stage == cur) {
+      switch (cur) {
+        case LG_ST_FETCH: lg_stage_fetch(cfg, d, w, L, fsp); break;
+        case LG_ST_HEAD:
+          lg_stage_head(cfg, d, w, L, fsp);
+          active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
+          break;
+        case LG_ST_FRONT: lg_stage_front(L); break;
+        case LG_ST_SEARCH: {
+          LgSearch q = L.q;  // the search record in registers / thread-private memory for the trips
+          for (int it = 0; it < quantum && !q.done; it++) lg_search_iter(q, *L.cls);
+          L.q = q;
+          if (q.done) {
+            L.resume = true;
+            L.stage = LG_ST_FRONT;
+          }
+          break;
+        }
+        case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, fsp); break;
+        default:
+          for (int it = 0; it < quantum && !L.k.done; it++) lg_corr_iter(L.k, L.f, *L.cls);
+          if (L.k.done) L.stage = LG_ST_TAIL;
+          break;
+      }
+    }
+    __syncwarp();
+  }
+  if (w.prof) {
+    if (front_sum) atomicAdd(w.prof, front_sum);
+    if (active_sum) atomicAdd(w.prof + 1, active_sum);
+  }
+}
+
 static __global__ void lgar_wave_clear_smem_kernel(LgarWave wv) {
   if (threadIdx.x < 2 * LGAR_NSTAGE) wv.qcount[threadIdx.x] = 0;
   if (threadIdx.x == 0) *wv.cursor = 0;  // zero between launches (the FETCH kernel relies on it)
@@ -91,6 +187,22 @@ static __global__ void lgar_wave_clear_smem_kernel(LgarWave wv) {
 
 cudaError_t lgar_launch_wave_finish_smem(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
                                          int lane_stride, cudaStream_t stream) {
+  if (lane_stride <= 0) {  // converged variant: one warp per block, -lane_stride = search trips per turn (0: 128)
+    const int bytes = 32 * kFinishSmemPitch;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t rc = cudaFuncSetAttribute(lgar_wave_finish_vote_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (rc != cudaSuccess) return rc;
+      configured = true;
+    }
+    const int resident = std::max(1, (227 * 1024) / (bytes + 1024));
+    const int blocks = std::max(1, std::min((in_flight + 31) / 32, 148 * resident));
+    cudaError_t rc = cudaMemsetAsync(wv.cursor, 0, sizeof(int32_t), stream);
+    if (rc != cudaSuccess) return rc;
+    lgar_wave_finish_vote_smem_kernel<<<blocks, 32, bytes, stream>>>(cfg, d, w, wv, lane_stride < 0 ? -lane_stride : 128);
+    lgar_wave_clear_smem_kernel<<<1, 32, 0, stream>>>(wv);
+    return cudaGetLastError();
+  }
   int ls = 2;  // a power of two in [2, 32]: 64 records (206 KB) per block at most
   while (ls < lane_stride && ls < 32) ls *= 2;
   const int per_block = 128 / ls;

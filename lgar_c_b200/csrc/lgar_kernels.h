@@ -62,7 +62,8 @@ cudaError_t lgar_launch_wave_run(const LgarConfig& cfg, const LgarDeviceState& d
                                  unsigned append_mask, int quantum, int corr_quantum, int keep, int max_items, cudaStream_t stream);
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
                                     int lane_stride, cudaStream_t stream);
-// the same with the lane records in shared memory (lgar_finish_smem.cu); lane_stride is rounded up to a power of two in [2, 32]
+// the same with the lane records in shared memory (lgar_finish_smem.cu); lane_stride is rounded up to a power of two in [2, 32];
+// lane_stride <= 0: converged variant (one warp per block, every lane a record, lanes refill), -lane_stride = search trips per turn
 cudaError_t lgar_launch_wave_finish_smem(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
                                          int lane_stride, cudaStream_t stream);
 cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWave& wv, int slot_is_column, cudaStream_t stream);

@@ -128,11 +128,16 @@ def test_scheduling_does_not_change_results(cuda_device, tmp_path):
 def test_experimental_scheduler_variants_do_not_change_results(cuda_device, tmp_path):
     """Opt-in variants that have not been through a GPU yet and are therefore not part of the default suite: the finishing
     kernel with its lane records in shared memory (lgar_finish_smem.cu, LGARB_FINISH_SMEM=1), taking over early (150 000
-    slots) and late (defaults), with one slot per 4 and per 2 lanes."""
+    slots) and late (defaults), with one slot per 4 and per 2 lanes, and its converged form (LGARB_FINISH_SMEM=2) up to running
+    the whole window on chip."""
     variants = [(3, None, {}),
                 (3, (64, 4, 150_000), {"LGARB_FINISH_SMEM": "1"}),
                 (3, None, {"LGARB_FINISH_SMEM": "1", "LGARB_FINISH_LANE_STRIDE": "2"}),
-                (3, (64, 4, 20_000), {"LGARB_FINISH_SMEM": "1", "LGARB_FINISH_LANE_STRIDE": "8"})]
+                (3, (64, 4, 20_000), {"LGARB_FINISH_SMEM": "1", "LGARB_FINISH_LANE_STRIDE": "8"}),
+                # converged variant (one warp per block, every lane a record, lanes refill): late, early, and the WHOLE window on chip
+                (3, None, {"LGARB_FINISH_SMEM": "2"}),
+                (3, (64, 4, 150_000), {"LGARB_FINISH_SMEM": "2", "LGARB_FINISH_LANE_STRIDE": "-32"}),
+                (3, (64, 4, 1_000_000_000), {"LGARB_FINISH_SMEM": "2"})]
     _assert_scheduling_variants_agree(tmp_path, variants)
 
 

@@ -20,3 +20,10 @@ for below in 16384 32768 65536 131072 262144; do
     run "smem   stride $st below $below" LGARB_FINISH_SMEM=1 LGARB_FINISH_LANE_STRIDE=$st LGARB_WAVE_FINISH_BELOW=$below
   done
 done
+# 3. the converged shared-memory kernel (LGARB_FINISH_SMEM=2): as a finishing kernel, and running the WHOLE window on chip
+#    (hand-over threshold above the column count) -- the measurement behind DESIGN.md section 10 item 1
+for below in 16384 65536 262144 2000000; do
+  for q in 0 -32 -512; do
+    run "vote-smem quantum ${q#-} below $below" LGARB_FINISH_SMEM=2 LGARB_FINISH_LANE_STRIDE=$q LGARB_WAVE_FINISH_BELOW=$below
+  done
+done
