@@ -152,7 +152,7 @@ LG_FN_NOINLINE double lg_Se_from_h(double h, const LgarLayer& s) {
 #endif
 // pow(x, 2.0) (soil_funcs.cxx:166) and pow(x, 3.0) (aet.cxx:60): products in the default build, the library function in the
 // parity-first builds (a pow that is not correctly rounded can differ from the product in the last bit)
-#if defined(LGAR_ACCURATE_POW) || defined(LGAR_EXACT_POW)
+#ifdef LGAR_ACCURATE_POW
 LG_FN double lg_pow2(double x) { return lg_pow(x, 2.0); }
 LG_FN double lg_pow3(double x) { return lg_pow(x, 3.0); }
 #else

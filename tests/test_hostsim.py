@@ -136,14 +136,17 @@ def test_more_than_16_fronts(hostsim, hostsim_libm_pow, tmp_path):
 
 @pytest.mark.parametrize("args", [["--config", "5", "--columns", "48", "--hours", "400"],
                                   ["--config", "4", "--columns", "16", "--hours", "300"],
-                                  ["--config", "3", "--columns", "8", "--hours", "120", "--stress"]])
+                                  ["--config", "3", "--columns", "8", "--hours", "120", "--stress"],
+                                  ["--config", "5", "--columns", "24", "--hours", "400", "--reference"]])
 def test_bitexact_sampling_tool(args):
     """tools/bitexact_sample.py at a small size: random columns of BASELINE configs 3/4/5 (and the stress variant: 300 s
-    sub-steps, no flux caching, numeric Geff) -- the kernel text with the library pow equals the oracle bit for bit in both
-    program forms.  The full-size runs (10 000 columns x the full duration per config) are in profiles/r1_bitexact_sample_*.json."""
+    sub-steps, no flux caching, numeric Geff) -- the kernel text with the library pow equals the oracle, and with --reference
+    the UNMODIFIED reference itself, bit for bit in both program forms.  The full-size runs (10 000 columns x the full duration per config) are in profiles/r1_bitexact_sample_*.json."""
     import json
     import sys
     tool = Path(__file__).resolve().parent.parent / "tools" / "bitexact_sample.py"
+    if "--reference" in args and not (tool.parent.parent / "oracle" / "_ref" / "liblgar_ref.so").exists():
+        pytest.skip("oracle/_ref (the unmodified reference, built where /root/reference exists) is not here")
     r = subprocess.run([sys.executable, str(tool), "--cores", "2"] + args, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     rep = json.loads(r.stdout[r.stdout.index("{"):])

@@ -14,7 +14,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tools")); sys.path.insert(0, str(ROOT / "tests"))
 import parity_sampling_full as pf  # noqa: E402
-from oracle.oracle_py import Oracle, write_config  # noqa: E402
+from oracle.oracle_py import Oracle, RefHarness, write_config  # noqa: E402
 
 HS = ROOT / "tests" / "hostsim"
 _dp = C.POINTER(C.c_double); _ip = C.POINTER(C.c_int)
@@ -54,10 +54,16 @@ def work(rng):
         for k, v in _G["extra"].items():
             over[k] = v
         cfg = write_config(c.cfg, tmp / f"col{j}.txt", **over)
-        p = orc.params_from_config(cfg)
-        s = orc.new_state(p)
         Pj, Ej = np.ascontiguousarray(P[:, j]), np.ascontiguousarray(E[:, j])
-        o = orc.run_series(p, s, Pj, Ej, cap=32)
+        if _G["reference"]:   # the UNMODIFIED reference (oracle/_ref, one BmiLGAR object) instead of the plain-C oracle
+            ref = _G.get("ref") or _G.setdefault("ref", RefHarness())
+            h = ref.create(cfg)
+            o = ref.run_series(h, Pj, Ej, cap=32)
+            ref.destroy(h)
+        else:
+            p = orc.params_from_config(cfg)
+            s = orc.new_state(p)
+            o = orc.run_series(p, s, Pj, Ej, cap=32)
         rec = dict(column=int(ids[j]), soils=[int(x) for x in soils[j - j0]] if soils is not None else None, oracle_done=int(o["done"]), max_fronts=int(o["nfronts"][:o["done"]].max()) if o["done"] else 0)
         for force in (0, 4):
             done, scal, nf, fr, fl, st = run_hostsim(lib, cfg, Pj, Ej, force)
@@ -82,6 +88,7 @@ def main():
     ap.add_argument("--hours", type=int, default=2000)
     ap.add_argument("--cores", type=int, default=8)
     ap.add_argument("--stress", action="store_true", help="SURVEY.md 8d stress variant: 300 s sub-steps, no flux caching, numeric Geff")
+    ap.add_argument("--reference", action="store_true", help="compare with the unmodified reference (oracle/_ref) instead of the oracle")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     import torch
@@ -92,13 +99,13 @@ def main():
     ids = np.sort(np.random.default_rng(2026).choice(c.n_total, a.columns, replace=False)).astype(np.int64)
     P, E = (x.numpy() for x in c.forcing(torch.from_numpy(ids), 0, a.hours))
     extra = {"timestep": "300[sec]", "allow_flux_caching": "false", "use_closed_form_G": "false"} if a.stress else {}
-    _G.update(c=c, ids=ids, P=P, E=E, tmp=tmp, extra=extra)
+    _G.update(c=c, ids=ids, P=P, E=E, tmp=tmp, extra=extra, reference=a.reference)
     step = max(1, a.columns // (4 * a.cores))
     jobs = [(j, min(j + step, a.columns)) for j in range(0, a.columns, step)]
     with mp.get_context("fork").Pool(a.cores) as pool:
         recs = [r for part in pool.map(work, jobs) for r in part]
     bad = [r for r in recs if not (r["bit_equal_force0"] and r["bit_equal_force4"])]
-    rep = dict(config=a.config, stress_variant=bool(a.stress), columns=a.columns, hours=a.hours, column_steps=int(sum(r["oracle_done"] for r in recs)),
+    rep = dict(config=a.config, against="unmodified reference (oracle/_ref)" if a.reference else "oracle", stress_variant=bool(a.stress), columns=a.columns, hours=a.hours, column_steps=int(sum(r["oracle_done"] for r in recs)),
                columns_the_oracle_stops_early=int(sum(r["oracle_done"] < a.hours for r in recs)),
                max_fronts=int(max(r["max_fronts"] for r in recs)),
                bit_equal_columns_hourly=int(sum(r["bit_equal_force0"] for r in recs)),
