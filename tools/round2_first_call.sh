@@ -27,3 +27,12 @@ for below in 16384 65536 262144 2000000; do
     run "vote-smem quantum ${q#-} below $below" LGARB_FINISH_SMEM=2 LGARB_FINISH_LANE_STRIDE=$q LGARB_WAVE_FINISH_BELOW=$below
   done
 done
+# 4. one `ncu --set full` capture each of the default finishing kernel and of the two shared-memory ones (timed window 8 of
+#    the profiling command of tools/prof_window.sh; the finishing kernel is the last launch of a window)
+B="python bench.py --mode 3 --no-e2e --no-cpu-baseline --spinup-hours 240 --steps 5"
+export LGARB_NCU_WINDOW=8 LGARB_NCU_ROUND=-2
+for v in "local" "smem1 LGARB_FINISH_SMEM=1" "smem2 LGARB_FINISH_SMEM=2"; do
+  set -- $v; name=$1; shift
+  env "$@" timeout 600 ncu --profile-from-start off --set full --import-source on --clock-control none --kernel-name regex:lgar_wave_finish \
+      -o gpurun_out/r2_finish_$name $B > gpurun_out/r2_finish_$name.log 2>&1 || echo "ncu capture $name failed"
+done
