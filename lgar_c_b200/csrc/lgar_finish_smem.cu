@@ -189,12 +189,9 @@ cudaError_t lgar_launch_wave_finish_smem(const LgarConfig& cfg, const LgarDevice
                                          int lane_stride, cudaStream_t stream) {
   if (lane_stride <= 0) {  // converged variant: one warp per block, -lane_stride = search trips per turn (0: 128)
     const int bytes = 32 * kFinishSmemPitch;
-    static bool configured = false;
-    if (!configured) {
-      cudaError_t rc = cudaFuncSetAttribute(lgar_wave_finish_vote_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-      if (rc != cudaSuccess) return rc;
-      configured = true;
-    }
+    // per launch (once per window): the attribute belongs to the current device, and engines may live on several
+    cudaError_t rc0 = cudaFuncSetAttribute(lgar_wave_finish_vote_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (rc0 != cudaSuccess) return rc0;
     const int resident = std::max(1, (227 * 1024) / (bytes + 1024));
     const int blocks = std::max(1, std::min((in_flight + 31) / 32, 148 * resident));
     cudaError_t rc = cudaMemsetAsync(wv.cursor, 0, sizeof(int32_t), stream);
@@ -207,12 +204,8 @@ cudaError_t lgar_launch_wave_finish_smem(const LgarConfig& cfg, const LgarDevice
   while (ls < lane_stride && ls < 32) ls *= 2;
   const int per_block = 128 / ls;
   const int bytes = per_block * kFinishSmemPitch;
-  static int configured = -1;  // largest dynamic size opted in to so far (one device per process)
-  if (bytes > configured) {
-    cudaError_t rc = cudaFuncSetAttribute(lgar_wave_finish_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (rc != cudaSuccess) return rc;
-    configured = bytes;
-  }
+  cudaError_t rc0 = cudaFuncSetAttribute(lgar_wave_finish_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (rc0 != cudaSuccess) return rc0;
   const int resident = std::max(1, (227 * 1024) / (bytes + 1024));  // blocks per SM that fit the shared memory
   const int blocks = std::max(1, std::min((in_flight + per_block - 1) / per_block, 148 * resident));
   cudaError_t rc = cudaMemsetAsync(wv.cursor, 0, sizeof(int32_t), stream);
