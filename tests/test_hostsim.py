@@ -151,3 +151,24 @@ def test_bitexact_sampling_tool(args):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     rep = json.loads(r.stdout[r.stdout.index("{"):])
     assert rep["bit_equal_columns_hourly"] == rep["columns"] == rep["bit_equal_columns_lanes"] and not rep["not_bit_equal"]
+
+
+def test_kernel_text_under_sanitizers(tmp_path):
+    """The reference's CI builds with -fsanitize=address,undefined (.github/workflows/build_and_run_tests.yml:35-56).  The same
+    for the kernel text: physics + staged lane program compiled for the host with both sanitizers and run through the golden
+    cases in all six program forms and through the 19-front column (fixed-capacity front arrays, nibble-packed flag words, the
+    live-prefix bookkeeping: the places where an index error would hide on a GPU)."""
+    import os
+    import sys
+    rt = []
+    for name in ("libasan.so", "libubsan.so"):
+        path = subprocess.run(["gcc", f"-print-file-name={name}"], capture_output=True, text=True).stdout.strip()
+        if not os.path.isabs(path):
+            pytest.skip(f"{name} is not installed")
+        rt.append(path)
+    so = tmp_path / "libhostsim_san.so"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-DLGAR_ACCURATE_POW",
+                           "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-o", str(so), str(HS / "hostsim.cpp")])
+    env = dict(os.environ, LD_PRELOAD=":".join(rt), ASAN_OPTIONS="detect_leaks=0:abort_on_error=1", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+    r = subprocess.run([sys.executable, str(HS / "sanitizer_run.py"), str(so)], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "sanitizers clean" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
