@@ -102,6 +102,7 @@ inline ParsedConfig parse_config(const std::string& config_file) {
     std::string unit = "";
     if (loc_u >= 0) unit = line.substr(loc_u, line.find("]") + 1);  // (pos, len) exactly as lgar.cxx:323
     std::string val = (loc_u >= 0) ? line.substr(loc_eq, loc_u - loc_eq) : line.substr(loc_eq);
+    try {  // std::stod on a malformed number: name the key instead of reporting "stod"
     if (key == "layer_thickness") { c.layer_thickness = read_vector(val); s_thick = true; }
     else if (key == "layer_soil_type") { for (double v : read_vector(val)) c.layer_soil_type.push_back((int)v); s_soil = true; }
     else if (key == "giuh_ordinates") { c.giuh_hourly = read_vector(val); s_giuh = true; }
@@ -139,6 +140,11 @@ inline ParsedConfig parse_config(const std::string& config_file) {
     else if (key == "soil_z") { c.soil_z = read_vector(val); }  // lgar.cxx:390-400
     else if (key == "ponded_depth_max") { c.ponded_depth_max = fmax(std::stod(val), 0.0); }
     else if (key == "calib_params") { c.calib_params = parse_bool(key, val, false); }
+    } catch (const std::invalid_argument&) {
+      throw std::runtime_error("The configuration file '" + config_file + "': cannot read the value '" + val + "' of " + key + " as a number.");
+    } catch (const std::out_of_range&) {
+      throw std::runtime_error("The configuration file '" + config_file + "': the value '" + val + "' of " + key + " is out of range.");
+    }
   }
   auto need = [&](bool ok, const char* what) {
     if (!ok) throw std::runtime_error("The configuration file '" + config_file + "' does not set " + what + ".");

@@ -20,6 +20,8 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
   try {
     ParsedConfig pc = parse_config(cfg_path);
     const int L = (int)pc.layer_thickness.size();
+    if (L < 1 || L > LGAR_MAXL) throw std::runtime_error("unsupported number of layers");                                 // do_initialize, lgar_engine.cu
+    if ((int)pc.layer_soil_type.size() != L) throw std::runtime_error("layer_soil_type and layer_thickness differ in length");
     std::vector<SoilRow> soils;
     read_soil_file(pc.soil_params_file, pc.num_soil_types, pc.wilting_point_psi, pc.log_mode, soils, cfg_path);
     LgarConfig cfg = make_engine_config(pc);

@@ -41,4 +41,44 @@ for force in (0, 4):
     done, scal, nf, fr, fl, st = th.run(lib, cfg, P, E, force, cap=32)
     assert done == T and nf.max() == 19
     steps += T
-print(f"sanitizers clean over {steps} column-steps")
+# malformed configurations through the product's host-side reader (lgar_c_b200/csrc/lgar_config.hpp, the file lgar_engine.cu
+# parses with): a clean error with a message, never a crash.  (key overrides, expected: None = must run, else text in the message)
+from oracle.oracle_py import DATA, absolutize_config  # noqa: E402
+base = absolutize_config(DATA / "configs" / "config_lasam_Phillipsburg.txt", out_dir=tmp)
+bad = {
+    "missing layer_thickness": (dict(layer_thickness=None), "does not set layer_thickness"),
+    "missing soil file key": (dict(soil_params_file=None), "does not set soil_params_file"),
+    "soil file absent": (dict(soil_params_file="/nonexistent/soils.dat"), "Can't open input file"),
+    "more soil types than layers": (dict(layer_soil_type="13,14,15,16"), "differ in length"),
+    "fewer soil types than layers": (dict(layer_soil_type="13,14"), "differ in length"),
+    "five layers": (dict(layer_thickness="10,10,10,10,10[cm]", layer_soil_type="1,2,3,4,5"), "layers"),
+    "soil type beyond the table (invalid soil: precipitation passes through)": (dict(layer_soil_type="13,14,99"), None),
+    "soil type zero": (dict(layer_soil_type="0,14,15"), ">= 1"),
+    "40 GIUH ordinates": (dict(giuh_ordinates=",".join(["0.025"] * 40)), "GIUH"),
+    "no GIUH ordinates": (dict(giuh_ordinates=None), "does not set giuh_ordinates"),
+    "malformed number": (dict(initial_psi="abc[cm]"), "initial_psi"),
+    "zero timestep": (dict(timestep="0[sec]"), "must be positive"),
+    "missing timestep": (dict(timestep=None), "does not set timestep"),
+    "missing forcing_resolution": (dict(forcing_resolution=None), "does not set forcing_resolution"),
+    "empty file": (None, "does not set"),
+}
+P = np.array([0.0, 5.0, 20.0, 0.0, 0.0, 1.0] * 4)
+E = np.full(24, 0.1)
+for k, (name, (rep, expect)) in enumerate(bad.items()):
+    path = tmp / f"bad{k}.txt"
+    if rep is None:
+        path.write_text("")
+    else:
+        write_config(base, path, **rep)
+    n = len(P)
+    scal = np.zeros((n, 12)); nf = np.zeros(n, dtype=np.int32); fr = np.zeros((n, 32, 5)); fl = np.zeros((n, 32), dtype=np.int32)
+    st = C.c_int(0)
+    err = C.create_string_buffer(512)
+    done = lib.hostsim_run_series(str(path).encode(), None, None, n, P.ctypes.data_as(th._dp), E.ctypes.data_as(th._dp), scal.ctypes.data_as(th._dp),
+                                  nf.ctypes.data_as(th._ip), 32, fr.ctypes.data_as(th._dp), fl.ctypes.data_as(th._ip), 0, C.byref(st), err, 512)
+    msg = err.value.decode()
+    if expect is None:
+        assert done == n, (name, done, msg)
+    else:
+        assert done < 0 and expect in msg, (name, done, msg)
+print(f"sanitizers clean over {steps} column-steps and {len(bad)} malformed configurations")

@@ -157,7 +157,8 @@ def test_kernel_text_under_sanitizers(tmp_path):
     """The reference's CI builds with -fsanitize=address,undefined (.github/workflows/build_and_run_tests.yml:35-56).  The same
     for the kernel text: physics + staged lane program compiled for the host with both sanitizers and run through the golden
     cases in all six program forms and through the 19-front column (fixed-capacity front arrays, nibble-packed flag words, the
-    live-prefix bookkeeping: the places where an index error would hide on a GPU)."""
+    live-prefix bookkeeping: the places where an index error would hide on a GPU), and malformed configuration files through the
+    product's host-side reader (lgar_config.hpp): a clean error that names the key, never a crash."""
     import os
     import sys
     rt = []
