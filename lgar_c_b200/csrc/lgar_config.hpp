@@ -283,6 +283,16 @@ inline void fill_class_layers(LgarColumnClass& c, const ParsedConfig& pc, const 
   }
 }
 
+// What do_initialize (lgar_engine.cu) requires of a column's soil types and layer thicknesses before it builds a class row;
+// shared with the host build of the kernel text (tests/hostsim) so that both reject the same inputs.
+inline void check_column_class(const ParsedConfig& pc, int soils_in_file, int L, const int* types, const double* thick) {
+  for (int k = 0; k < L; k++) {
+    if (types[k] > soils_in_file && types[k] <= pc.num_soil_types)  // lgar.cxx:814-820
+      throw std::runtime_error("Soil type is less than max_valid_soil_types but is greater than the number of lines in the soil data file.");
+    if (!(thick[k] > 0)) throw std::runtime_error("layer thickness must be positive");
+  }
+}
+
 inline LgarColumnClass make_class(const ParsedConfig& pc, const std::vector<SoilRow>& soils, int num_layers, const int* types, const double* thick) {
   LgarColumnClass c;
   memset(&c, 0, sizeof(c));

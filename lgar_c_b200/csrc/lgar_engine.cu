@@ -231,11 +231,7 @@ void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int d
     }
     auto it = seen.find(key);
     if (it == seen.end()) {
-      for (int k = 0; k < L; k++) {
-        if (types[k] > nread && types[k] <= pc.num_soil_types)  // lgar.cxx:814-820
-          throw std::runtime_error("Soil type is less than max_valid_soil_types but is greater than the number of lines in the soil data file.");
-        if (!(thick[k] > 0)) throw std::runtime_error("layer thickness must be positive");
-      }
+      check_column_class(pc, nread, L, types.data(), thick.data());
       int id = (int)e->classes.size();
       e->classes.push_back(make_class(pc, e->soils, L, types.data(), thick.data()));
       it = seen.emplace(key, id).first;

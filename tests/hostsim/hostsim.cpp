@@ -23,7 +23,7 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
     if (L < 1 || L > LGAR_MAXL) throw std::runtime_error("unsupported number of layers");                                 // do_initialize, lgar_engine.cu
     if ((int)pc.layer_soil_type.size() != L) throw std::runtime_error("layer_soil_type and layer_thickness differ in length");
     std::vector<SoilRow> soils;
-    read_soil_file(pc.soil_params_file, pc.num_soil_types, pc.wilting_point_psi, pc.log_mode, soils, cfg_path);
+    const int nread = read_soil_file(pc.soil_params_file, pc.num_soil_types, pc.wilting_point_psi, pc.log_mode, soils, cfg_path);
     LgarConfig cfg = make_engine_config(pc);
     std::vector<int> types(L);
     std::vector<double> thick(L);
@@ -31,6 +31,7 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
       types[k] = types_in ? types_in[k] : pc.layer_soil_type[k];
       thick[k] = thick_in ? thick_in[k] : pc.layer_thickness[k];
     }
+    check_column_class(pc, nread, L, types.data(), thick.data());
     LgarColumnClass cls = make_class(pc, soils, L, types.data(), thick.data());
 
     const int64_t st = 1;

@@ -81,4 +81,30 @@ for k, (name, (rep, expect)) in enumerate(bad.items()):
         assert done == n, (name, done, msg)
     else:
         assert done < 0 and expect in msg, (name, done, msg)
-print(f"sanitizers clean over {steps} column-steps and {len(bad)} malformed configurations")
+# malformed soil-parameter files (lgar_read_vG_param_file, lgar.cxx:2675-2760 -> read_soil_file): too few rows is the
+# reference's "greater than the number of lines in the soil data file" error; rows that sscanf cannot read inherit the previous
+# row (quirk Q2), physically impossible rows run into a per-column status -- nothing may crash
+good = (DATA / "vG_default_params.dat").read_text().splitlines()
+soil_files = {
+    "empty": ("", "number of lines"),
+    "header only": (good[0] + "\n", "number of lines"),
+    "5 rows only": ("\n".join(good[:6]) + "\n", "number of lines"),
+    "row with missing columns": ("\n".join(good[:14] + ['"Broken" 0.05 0.4'] + good[15:]) + "\n", None),
+    "non-numeric row": ("\n".join(good[:14] + ['"Broken" a b c d e'] + good[15:]) + "\n", None),
+    "n = 1 (m = 0)": ("\n".join(good[:13] + ['"Flat" 0.05 0.40 0.01 1.0 0.5'] + good[14:]) + "\n", None),
+    "theta_r > theta_e": ("\n".join(good[:13] + ['"Inv" 0.45 0.40 0.01 1.5 0.5'] + good[14:]) + "\n", None),
+    "5 000-character name": ("\n".join(good[:13] + ['"' + "x" * 5000 + '" 0.05 0.40 0.01 1.5 0.5'] + good[14:]) + "\n", None),
+}
+for k, (name, (text, expect)) in enumerate(soil_files.items()):
+    sf = tmp / f"soil{k}.dat"
+    sf.write_text(text)
+    path = write_config(base, tmp / f"badsoil{k}.txt", soil_params_file=str(sf))
+    n = len(P)
+    scal = np.zeros((n, 12)); nf = np.zeros(n, dtype=np.int32); fr = np.zeros((n, 32, 5)); fl = np.zeros((n, 32), dtype=np.int32)
+    st = C.c_int(0)
+    err = C.create_string_buffer(512)
+    done = lib.hostsim_run_series(str(path).encode(), None, None, n, P.ctypes.data_as(th._dp), E.ctypes.data_as(th._dp), scal.ctypes.data_as(th._dp),
+                                  nf.ctypes.data_as(th._ip), 32, fr.ctypes.data_as(th._dp), fl.ctypes.data_as(th._ip), 0, C.byref(st), err, 512)
+    if expect is not None:
+        assert done < 0 and expect in err.value.decode(), (name, done, err.value.decode())
+print(f"sanitizers clean over {steps} column-steps, {len(bad)} malformed configurations and {len(soil_files)} malformed soil files")
