@@ -173,3 +173,10 @@ def test_kernel_text_under_sanitizers(tmp_path):
     env = dict(os.environ, LD_PRELOAD=":".join(rt), ASAN_OPTIONS="detect_leaks=0:abort_on_error=1", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
     r = subprocess.run([sys.executable, str(HS / "sanitizer_run.py"), str(so)], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "sanitizers clean" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+    # the checker itself: the plain-C oracle built the same way, every golden case bit for bit and the 19-front column
+    oso = tmp_path / "liblgar_oracle_san.so"
+    root = HS.parent.parent
+    subprocess.check_call(["gcc", "-std=c11", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-fsanitize=address,undefined",
+                           "-fno-sanitize-recover=undefined", "-o", str(oso), str(root / "oracle" / "lgar_oracle.c"), "-lm"])
+    r = subprocess.run([sys.executable, str(HS / "sanitizer_run_oracle.py")], env=dict(env, LGAR_ORACLE_SO=str(oso)), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "oracle: sanitizers clean" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
