@@ -118,7 +118,13 @@ LG_FN_NOINLINE double lg_exp(double x) { return exp(x); }
 LG_FN_NOINLINE double lg_log(double x) { return log(x); }
 #ifdef LGAR_ACCURATE_POW
 // parity-first build: the library pow (<= 1-2 ulp, ~4x the instructions), out of line so the code stays small
+#if defined(LGAR_HOSTSIM) && defined(LGAR_POWL_POW)
+// host experiment (tools/bitexact_sample.py --powl): a pow of different provenance but of glibc's class of accuracy -- the x87
+// long-double powl (64-bit significand) rounded to double, i.e. the correctly rounded result in all but ~1e-3 of the calls
+LG_FN_NOINLINE double lg_pow(double x, double y) { return (double)powl((long double)x, (long double)y); }
+#else
 LG_FN_NOINLINE double lg_pow(double x, double y) { return pow(x, y); }
+#endif
 LG_FN double lg_theta_from_lnh(double lnh, const LgarLayer& s) {  // lnh carries h itself in this build
   return 1.0 / (lg_pow(1.0 + lg_pow(s.alpha * lnh, s.n), s.m)) * s.de + s.theta_r;
 }

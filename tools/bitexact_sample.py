@@ -22,7 +22,7 @@ _G = {}
 
 
 def load_lib():
-    lib = C.CDLL(str(HS / ("libhostsim.so" if _G.get("device_pow") else "libhostsim_acc.so")))
+    lib = C.CDLL(str(HS / ("libhostsim_powl.so" if _G.get("powl") else "libhostsim.so" if _G.get("device_pow") else "libhostsim_acc.so")))
     lib.hostsim_run_series.argtypes = [C.c_char_p, _ip, _dp, C.c_int, _dp, _dp, _dp, _ip, C.c_int, _dp, _ip, C.c_int, _ip, C.c_char_p, C.c_int]
     lib.hostsim_run_series.restype = C.c_int
     return lib
@@ -105,10 +105,16 @@ def main():
     ap.add_argument("--reference", action="store_true", help="compare with the unmodified reference (oracle/_ref) instead of the oracle")
     ap.add_argument("--device-pow", action="store_true", help="the kernel text as the GPU build has it, x^y = exp(y log x) (with glibc's exp/log): "
                     "reports how far that substitution alone takes the columns from the oracle / reference instead of requiring bit equality")
+    ap.add_argument("--powl", action="store_true", help="with --device-pow: x^y = (double)powl(x, y) instead of exp(y log x) -- an accurate pow "
+                    "that is NOT glibc's pow: how far does a different implementation of the same accuracy class take the columns?")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     import torch
-    if a.device_pow:
+    if a.powl:
+        a.device_pow = True
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-DLGAR_ACCURATE_POW", "-DLGAR_POWL_POW", "-o",
+                               str(HS / "libhostsim_powl.so"), str(HS / "hostsim.cpp")])
+    elif a.device_pow:
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-o", str(HS / "libhostsim.so"), str(HS / "hostsim.cpp")])
     else:
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-DLGAR_ACCURATE_POW", "-o",
@@ -118,7 +124,7 @@ def main():
     ids = np.sort(np.random.default_rng(a.seed).choice(c.n_total, a.columns, replace=False)).astype(np.int64)
     P, E = (x.numpy() for x in c.forcing(torch.from_numpy(ids), 0, a.hours))
     extra = {"timestep": "300[sec]", "allow_flux_caching": "false", "use_closed_form_G": "false"} if a.stress else {}
-    _G.update(c=c, ids=ids, P=P, E=E, tmp=tmp, extra=extra, reference=a.reference, device_pow=a.device_pow)
+    _G.update(c=c, ids=ids, P=P, E=E, tmp=tmp, extra=extra, reference=a.reference, device_pow=a.device_pow, powl=a.powl)
     step = max(1, a.columns // (4 * a.cores))
     jobs = [(j, min(j + step, a.columns)) for j in range(0, a.columns, step)]
     with mp.get_context("fork").Pool(a.cores) as pool:
@@ -131,7 +137,7 @@ def main():
                bit_equal_columns_lanes=int(sum(r["bit_equal_force4"] for r in recs)), not_bit_equal=bad[:50])
     if a.device_pow:
         devs = [r["dev_force0"] for r in recs if "dev_force0" in r]
-        rep["pow_form"] = "exp(y log x), glibc exp/log"
+        rep["pow_form"] = "(double)powl(x, y)" if a.powl else "exp(y log x), glibc exp/log"
         rep["device_pow_deviation"] = dict(
             columns_with_a_front_count_difference=int(sum(not d["front_counts_equal"] for d in devs)),
             columns_with_scalars_outside_the_bar=int(sum(d["scalars_outside_bar"] > 0 for d in devs)),
