@@ -17,6 +17,7 @@
 #define LGAR_PHYSICS_CUH
 
 #include "lgar_types.h"
+#include "lgar_pow.cuh"
 
 #ifdef LGAR_HOSTSIM
 #include <cmath>
@@ -102,43 +103,25 @@ __device__ const double lg_ff_ones[LGAR_MAXL + 2] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.
 // ------------------------------------------------------------------------------------------------
 LG_FN double lg_sq(double x) { return x * x; }
 
-// x^y for x >= 0 as exp(y*log(x)).  The reference calls libm pow(); CUDA's pow() costs ~370 thread
-// instructions per call on sm_100a (ncu, profiles/r1_window_pow.md) because it carries log(x) in
-// extended precision.  exp(y*log x) is ~4x cheaper and differs from pow by <= |y log x| * 2^-52
-// (<= 1e-14 relative on this path) -- five orders below the 1e-9 parity bar and the same kind of
-// last-bits noise as CUDA pow vs glibc pow.  Edge cases used on the path: 0^y = 0 (y > 0), 0^-y = inf,
-// 1^y = 1, inf^y = inf, negative base = NaN -- all follow from log/exp.
+// x^y.  The reference calls libm pow() everywhere (soil_funcs.cxx:147-187, aet.cxx:60, conceptual_reservoir.cxx:19-35), and the
+// engine returns the same double: lgar_pow.cuh restates the host library's table-driven algorithm operation for operation
+// (bit-identical to glibc's pow on 3e8 samples, tests/test_pow_exact.py), so that what separated the engine from the reference
+// in round 1 -- exp(y log x), a few ulp from pow in most calls, enough to end a psi search one trip apart --
+// is gone.
 //
-// Code size matters as much as instruction count here: with every exp/log inlined the lanes kernel
-// was 437 KB of SASS and warps, each at a different place of the column program, stalled 26 of 34
-// cycles per instruction on instruction fetch (ncu smsp__average_warps_issue_stalled_no_instruction,
-// profiles/r1_lanes_icache.md).  So exp and log exist ONCE as out-of-line functions and the soil
-// functions are out of line too; only the psi-search iteration keeps its own inlined copies.
+// Build variants (measurement and cross-checks only):
+//   -DLGAR_FAST_POW      round 1's exp(y log x) with log(psi) shared by the layers of a search trip
+//   -DLGAR_ACCURATE_POW  the library pow of the compiling toolchain (CUDA's on the device; glibc's in the host build of the
+//                        kernel text, tests/hostsim -- the function the reference itself calls)
+//
+// Code size matters as much as instruction count here: with every soil function inlined the lanes kernel of round 1 was 437 KB
+// of SASS and warps, each at a different place of the column program, stalled 26 of 34 cycles per instruction on instruction
+// fetch (profiles/r1_ncu_summary.md).  So pow exists ONCE as an out-of-line function and the soil functions are out of line
+// too; only the psi-search iteration inlines the common case (lgp_try_pow) and calls the full function for the rest.
+#if defined(LGAR_FAST_POW)
 LG_FN_NOINLINE double lg_exp(double x) { return exp(x); }
 LG_FN_NOINLINE double lg_log(double x) { return log(x); }
-#ifdef LGAR_ACCURATE_POW
-// parity-first build: the library pow (<= 1-2 ulp, ~4x the instructions), out of line so the code stays small
-#if defined(LGAR_HOSTSIM) && defined(LGAR_POWL_POW)
-// host experiment (tools/bitexact_sample.py --powl): a pow of different provenance but of glibc's class of accuracy -- the x87
-// long-double powl (64-bit significand) rounded to double, i.e. the correctly rounded result in all but ~1e-3 of the calls
-LG_FN_NOINLINE double lg_pow(double x, double y) { return (double)powl((long double)x, (long double)y); }
-#else
-LG_FN_NOINLINE double lg_pow(double x, double y) { return pow(x, y); }
-#endif
-LG_FN double lg_theta_from_lnh(double lnh, const LgarLayer& s) {  // lnh carries h itself in this build
-  return 1.0 / (lg_pow(1.0 + lg_pow(s.alpha * lnh, s.n), s.m)) * s.de + s.theta_r;
-}
-LG_FN double lg_lnh(double h) { return h; }
-LG_FN_NOINLINE double lg_theta_from_h(double h, const LgarLayer& s) {
-  return 1.0 / (lg_pow(1.0 + lg_pow(s.alpha * h, s.n), s.m)) * s.de + s.theta_r;
-}
-LG_FN_NOINLINE double lg_Se_from_h(double h, const LgarLayer& s) {
-  if (fabs(h) < 1.0E-10) return 1.0;
-  return 1.0 / (lg_pow(1.0 + lg_pow(s.alpha * h, s.n), s.m));
-}
-#else
 LG_FN double lg_pow(double x, double y) { return lg_exp(y * lg_log(x)); }
-
 // calc_theta_from_h with log(h) supplied, fully inlined: the psi search evaluates every layer at the same psi
 LG_FN double lg_theta_from_lnh(double lnh, const LgarLayer& s) {
   const double y = exp(s.n * (s.ln_alpha + lnh));       // (alpha*h)^n
@@ -155,15 +138,46 @@ LG_FN_NOINLINE double lg_Se_from_h(double h, const LgarLayer& s) {
   if (fabs(h) < 1.0E-10) return 1.0;
   return lg_exp(-s.m * lg_log(1.0 + lg_exp(s.n * (s.ln_alpha + lg_log(h)))));
 }
-#endif
-// pow(x, 2.0) (soil_funcs.cxx:166) and pow(x, 3.0) (aet.cxx:60): products in the default build, the library function in the
-// parity-first builds (a pow that is not correctly rounded can differ from the product in the last bit)
-#ifdef LGAR_ACCURATE_POW
-LG_FN double lg_pow2(double x) { return lg_pow(x, 2.0); }
-LG_FN double lg_pow3(double x) { return lg_pow(x, 3.0); }
-#else
 LG_FN double lg_pow2(double x) { return x * x; }
 LG_FN double lg_pow3(double x) { return x * x * x; }
+#else
+#if defined(LGAR_ACCURATE_POW)
+#if defined(LGAR_HOSTSIM) && defined(LGAR_POWL_POW)
+// host experiment (tools/bitexact_sample.py --powl): a pow of different provenance but of glibc's class of accuracy -- the x87
+// long-double powl (64-bit significand) rounded to double, i.e. the correctly rounded result in all but ~1e-3 of the calls
+LG_FN_NOINLINE double lg_pow(double x, double y) { return (double)powl((long double)x, (long double)y); }
+#else
+LG_FN_NOINLINE double lg_pow(double x, double y) { return pow(x, y); }
+#endif
+LG_FN double lg_pow_hot(double x, double y) { return lg_pow(x, y); }
+#else
+LG_FN_NOINLINE double lg_pow(double x, double y) { return lgp_pow(x, y); }
+LG_FN double lg_pow_hot(double x, double y) {
+  double r;
+  if (lgp_try_pow(x, y, &r)) return r;
+  return lg_pow(x, y);
+}
+#endif
+// calc_theta_from_h inside the psi search ("lnh" carries h itself in these builds: every layer needs its own log(alpha h))
+LG_FN double lg_theta_from_lnh(double lnh, const LgarLayer& s) {
+  return 1.0 / (lg_pow_hot(1.0 + lg_pow_hot(s.alpha * lnh, s.n), s.m)) * s.de + s.theta_r;
+}
+LG_FN double lg_lnh(double h) { return h; }
+// calc_theta_from_h, soil_funcs.cxx:147-150
+LG_FN_NOINLINE double lg_theta_from_h(double h, const LgarLayer& s) {
+  return 1.0 / (lg_pow(1.0 + lg_pow(s.alpha * h, s.n), s.m)) * s.de + s.theta_r;
+}
+// calc_Se_from_h, soil_funcs.cxx:155-159
+LG_FN_NOINLINE double lg_Se_from_h(double h, const LgarLayer& s) {
+  if (fabs(h) < 1.0E-10) return 1.0;
+  return 1.0 / (lg_pow(1.0 + lg_pow(s.alpha * h, s.n), s.m));
+}
+// pow(x, 2.0) (soil_funcs.cxx:166): the reference's compiler folds a pow with the constant exponent 2.0 into x*x (GCC does so at
+// every optimisation level that inlines builtins; the disassembly of calc_K_from_Se in oracle/_ref shows two calls of pow and one
+// mulsd x,x), and the true pow(x, 2.0) differs from the product in the last bit now and then.  pow(x, 3.0) (aet.cxx:60) stays
+// a call of pow in the reference's object code, so it is one here.
+LG_FN double lg_pow2(double x) { return x * x; }
+LG_FN double lg_pow3(double x) { return lg_pow(x, 3.0); }
 #endif
 // calc_K_from_Se, soil_funcs.cxx:164-167
 // Ksat is an argument: the reference passes Ks * frozen_factor[layer] at some call sites and plain Ks at others

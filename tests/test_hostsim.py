@@ -1,7 +1,8 @@
 """The kernel TEXT (lgar_c_b200/csrc/lgar_physics.cuh + lgar_step.cuh) compiled for the host by
 tests/hostsim and run against the oracle: a CPU-side check of the device code's logic (slot
 arithmetic, the two-kernel split, the epilogue).  Test infrastructure only -- the product library
-contains no host path.  Remaining differences: x^y evaluated as exp(y log x) instead of libm pow (<= 1e-14 relative per call)."""
+contains no host path.  With lgar_pow.cuh underneath (the default build: the host library's pow restated operation for operation)
+the kernel text reproduces the reference bit for bit; nothing is left to a tolerance."""
 import ctypes as C
 import subprocess
 from pathlib import Path
@@ -63,10 +64,13 @@ def test_kernel_text_matches_golden(hostsim, name, force, tmp_path):
     done, scal, nf, fr, fl, status = run(hostsim, config_for(name, tmp_path), g["precip"][:n], g["pet"][:n], force)
     assert done == n and status & 0xFFFF == 0
     assert np.array_equal(nf, g["nfronts"][:n]), "front counts differ from the reference"
-    assert_scalars_close(scal, g["scalars"][:n], name, rtol=1e-10)
+    # the default build's pow IS the reference's (lgar_pow.cuh): no tolerance
+    assert np.array_equal(scal, g["scalars"][:n]), f"{name}: {np.count_nonzero(scal != g['scalars'][:n])} scalars differ in the last bits"
     for i, t in enumerate(g["ck_steps"]):
         if t < n:
-            assert_fronts_close(fr[t], fl[t], g["ck_fronts"][i], g["ck_flags"][i], int(nf[t]), f"{name}@{t}", rtol=1e-10)
+            k = int(nf[t])
+            assert np.array_equal(fl[t][:k], g["ck_flags"][i][:k])
+            assert np.array_equal(fr[t][:k], g["ck_fronts"][i][:k]), f"{name}@{t}: front fields differ in the last bits"
 
 
 @pytest.fixture(scope="module")
@@ -125,9 +129,10 @@ def test_more_than_16_fronts(hostsim, hostsim_libm_pow, tmp_path):
         done, scal, nf, fr, fl, status = run(hostsim, cfg, P, E, force, cap=32)
         assert done == T == o["done"] and status & 0xFFFF == 0
         assert nf.max() == 19 and np.array_equal(nf, o["nfronts"])
-        assert_scalars_close(scal, o["scalars"], "config5 column 5588097", rtol=1e-9)
+        assert np.array_equal(scal, o["scalars"]), "config5 column 5588097"
         t = T - 1 if force else int(np.argmax(nf))
-        assert_fronts_close(fr[t], fl[t], o["fronts"][t], o["flags"][t], int(nf[t]), f"deep@{t}", rtol=1e-9)
+        assert np.array_equal(fl[t][:int(nf[t])], o["flags"][t][:int(nf[t])])
+        assert np.array_equal(fr[t][:int(nf[t])], o["fronts"][t][:int(nf[t])])
         # and bit for bit with the library pow underneath (the oracle calls the same glibc pow as the reference)
         done, scal, nf, fr, fl, status = run(hostsim_libm_pow, cfg, P, E, force, cap=32)
         assert done == T and np.array_equal(nf, o["nfronts"]) and np.array_equal(scal, o["scalars"])

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Is x^y really the only difference between the kernel text and the reference?  The kernel text compiled for the host with
-the library pow (tests/hostsim, -DLGAR_ACCURATE_POW: glibc's pow, the function the reference and the oracle call) against
-the oracle, BIT FOR BIT, on a random sample of columns of a BASELINE config (3, 4 or 5: random soil triples, both layerings,
+"""Does the kernel text reproduce the reference bit for bit?  The kernel text compiled for the host (tests/hostsim) in its DEFAULT
+build -- x^y through lgar_pow.cuh, the host library's pow restated operation for operation, exactly what the GPU executes --
+or, with --libm-pow, with the library pow itself (-DLGAR_ACCURATE_POW: glibc's pow, the function the reference and the oracle
+call) against the oracle, BIT FOR BIT, on a random sample of columns of a BASELINE config (3, 4 or 5: random soil triples, both layerings,
 shifted / synthetic forcing) -- every per-step scalar, every front count, the fronts of the last step -- in both program
 forms (hour-by-hour functions, staged lane program).  Any rare-path logic difference (deep columns, domain-bottom crossings,
 10^4-trip searches ...) would show here as a first differing step; 1e-9 comparisons on the GPU cannot see one.
@@ -22,7 +23,7 @@ _G = {}
 
 
 def load_lib():
-    lib = C.CDLL(str(HS / ("libhostsim_powl.so" if _G.get("powl") else "libhostsim.so" if _G.get("device_pow") else "libhostsim_acc.so")))
+    lib = C.CDLL(str(HS / ("libhostsim_powl.so" if _G.get("powl") else "libhostsim_fast.so" if _G.get("device_pow") else "libhostsim_acc.so" if _G.get("libm_pow") else "libhostsim.so")))
     lib.hostsim_run_series.argtypes = [C.c_char_p, _ip, _dp, C.c_int, _dp, _dp, _dp, _ip, C.c_int, _dp, _ip, C.c_int, _ip, C.c_char_p, C.c_int]
     lib.hostsim_run_series.restype = C.c_int
     return lib
@@ -103,7 +104,8 @@ def main():
     ap.add_argument("--seed", type=int, default=2026, help="sample seed; 99 draws the columns of tools/parity_sampling_full.py (the GPU report)")
     ap.add_argument("--stress", action="store_true", help="SURVEY.md 8d stress variant: 300 s sub-steps, no flux caching, numeric Geff")
     ap.add_argument("--reference", action="store_true", help="compare with the unmodified reference (oracle/_ref) instead of the oracle")
-    ap.add_argument("--device-pow", action="store_true", help="the kernel text as the GPU build has it, x^y = exp(y log x) (with glibc's exp/log): "
+    ap.add_argument("--libm-pow", action="store_true", help="x^y = the host library's pow itself instead of its restatement in lgar_pow.cuh")
+    ap.add_argument("--device-pow", action="store_true", help="the kernel text as round 1's GPU build had it (-DLGAR_FAST_POW), x^y = exp(y log x) (with glibc's exp/log): "
                     "reports how far that substitution alone takes the columns from the oracle / reference instead of requiring bit equality")
     ap.add_argument("--powl", action="store_true", help="with --device-pow: x^y = (double)powl(x, y) instead of exp(y log x) -- an accurate pow "
                     "that is NOT glibc's pow: how far does a different implementation of the same accuracy class take the columns?")
@@ -115,22 +117,24 @@ def main():
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-DLGAR_ACCURATE_POW", "-DLGAR_POWL_POW", "-o",
                                str(HS / "libhostsim_powl.so"), str(HS / "hostsim.cpp")])
     elif a.device_pow:
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-o", str(HS / "libhostsim.so"), str(HS / "hostsim.cpp")])
-    else:
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-DLGAR_FAST_POW", "-o", str(HS / "libhostsim_fast.so"), str(HS / "hostsim.cpp")])
+    elif a.libm_pow:
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-DLGAR_ACCURATE_POW", "-o",
                                str(HS / "libhostsim_acc.so"), str(HS / "hostsim.cpp")])
+    else:
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-o", str(HS / "libhostsim.so"), str(HS / "hostsim.cpp")])
     tmp = Path(tempfile.mkdtemp())
     c = pf.Config(a.config, tmp)
     ids = np.sort(np.random.default_rng(a.seed).choice(c.n_total, a.columns, replace=False)).astype(np.int64)
     P, E = (x.numpy() for x in c.forcing(torch.from_numpy(ids), 0, a.hours))
     extra = {"timestep": "300[sec]", "allow_flux_caching": "false", "use_closed_form_G": "false"} if a.stress else {}
-    _G.update(c=c, ids=ids, P=P, E=E, tmp=tmp, extra=extra, reference=a.reference, device_pow=a.device_pow, powl=a.powl)
+    _G.update(c=c, ids=ids, P=P, E=E, tmp=tmp, extra=extra, reference=a.reference, device_pow=a.device_pow, powl=a.powl, libm_pow=a.libm_pow)
     step = max(1, a.columns // (4 * a.cores))
     jobs = [(j, min(j + step, a.columns)) for j in range(0, a.columns, step)]
     with mp.get_context("fork").Pool(a.cores) as pool:
         recs = [r for part in pool.map(work, jobs) for r in part]
     bad = [r for r in recs if not (r["bit_equal_force0"] and r["bit_equal_force4"])]
-    rep = dict(config=a.config, sample_seed=a.seed, against="unmodified reference (oracle/_ref)" if a.reference else "oracle", stress_variant=bool(a.stress), columns=a.columns, hours=a.hours, column_steps=int(sum(r["oracle_done"] for r in recs)),
+    rep = dict(pow="host library pow" if a.libm_pow else "lgar_pow.cuh (the engine's)" if not a.device_pow else "see pow_form", config=a.config, sample_seed=a.seed, against="unmodified reference (oracle/_ref)" if a.reference else "oracle", stress_variant=bool(a.stress), columns=a.columns, hours=a.hours, column_steps=int(sum(r["oracle_done"] for r in recs)),
                columns_the_oracle_stops_early=int(sum(r["oracle_done"] < a.hours for r in recs)),
                max_fronts=int(max(r["max_fronts"] for r in recs)),
                bit_equal_columns_hourly=int(sum(r["bit_equal_force0"] for r in recs)),
