@@ -131,8 +131,8 @@ class BmiLGARB200 : public bmi::Bmi {
   }
   static bool is_front_array(const std::string& n) { return n == "soil_moisture_wetting_fronts" || n == "soil_depth_wetting_fronts"; }
   int num_fronts() {
-    int n = 0;
-    ck(lgarb_get_value(e_, "soil_num_wetting_fronts", &n));
+    int n = 0;  // column 0 only: lgarb_get_value would copy n_columns int32 values into this one int
+    ck(lgarb_get_value_range(e_, "soil_num_wetting_fronts", 0, 1, &n));
     return n;
   }
 };

@@ -244,6 +244,11 @@ void* lgarb_get_stream(lgarb_engine* e);
 /* FP64 roofline denominator ("not in MEASURED_PEAKS"): dependent-free DFMA chains on every SM of the
  * engine's device for about `ms` milliseconds; *tflops = 2 * DFMAs / time, timed with CUDA events. */
 int lgarb_measure_fp64_peak(lgarb_engine* e, double ms, double* tflops);
+/* The engine's x^y on the device for n pairs of host doubles (out[i] = x[i]^y[i]): the function that stands in for the libm pow
+ * the reference calls (reference src/soil_funcs.cxx:147-187), exposed so that a test can compare it with the host's pow bit for
+ * bit.  which = 0: the out-of-line function every cold call site uses, 1: the inlined common case of the psi search with its
+ * fall-back to the former. */
+int lgarb_debug_pow(lgarb_engine* e, int64_t n, const double* x, const double* y, double* out, int which);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,17 @@ OUTPUT_SCALARS = [
 ]
 
 
+def _config_num_layers(config_file):
+    """number of entries of layer_thickness in a reference configuration file (reference src/lgar.cxx:321-349)"""
+    try:
+        for line in open(config_file):
+            if line.split("=")[0].strip() == "layer_thickness":
+                return len([t for t in line.split("=", 1)[1].split("[")[0].split(",") if t.strip()])
+    except OSError:
+        pass
+    return -1
+
+
 class LgarbError(RuntimeError):
     pass
 
@@ -117,6 +128,7 @@ def _load():
         "lgarb_get_last_active_count": ([vp], i64),
         "lgarb_get_stream": ([vp], vp),
         "lgarb_measure_fp64_peak": ([vp, C.c_double, dp], C.c_int),
+        "lgarb_debug_pow": ([vp, C.c_int64, dp, dp, dp, C.c_int], C.c_int),
         "lgarb_set_profiling": ([vp, C.c_int], C.c_int),
         "lgarb_get_profile": ([vp, dp], C.c_int),
     }
@@ -171,6 +183,13 @@ class BmiLGARBatch:
             tk = np.ascontiguousarray(layer_thickness_cm, dtype=np.float64)
             if tk.shape[0] != n_columns:
                 raise LgarbError("layer_thickness_cm must be [n_columns][num_layers]")
+        if st is not None and tk is not None and (st.ndim != 2 or st.shape != tk.shape):
+            raise LgarbError("layer_soil_type and layer_thickness_cm must both be [n_columns][num_layers]")
+        for a in (st, tk):
+            # the C side indexes [column * num_layers + layer] with num_layers taken from the configuration file: check it
+            # BEFORE the call so that a wrong second dimension is an error and not an out-of-bounds read
+            if a is not None and (a.ndim != 2 or a.shape[1] != (_config_num_layers(config_file) if _config_num_layers(config_file) > 0 else a.shape[1])):
+                raise LgarbError("per-column layer arrays must be [n_columns][num_layers of the configuration]")
         self._ck(self._L.lgarb_initialize_columns(self._h, str(config_file).encode(), int(n_columns), int(device), _ptr(st), _ptr(tk)))
         self.n_columns = int(n_columns)
         self.num_layers = self._L.lgarb_get_num_layers(self._h)
@@ -203,10 +222,12 @@ class BmiLGARBatch:
         filled in place (or a list of names: arrays are allocated and returned)."""
         P = np.ascontiguousarray(precip, dtype=np.float64)
         E = np.ascontiguousarray(pet, dtype=np.float64)
+        self._check_series(P, E)
         n_steps = P.shape[0]
         if not isinstance(outputs, dict):
             outputs = {n: np.empty((n_steps, self.n_columns)) for n in outputs}
         names = list(outputs)
+        self._check_outputs(outputs, n_steps, np.float64)
         cn = (C.c_char_p * len(names))(*[n.encode() for n in names])
         cp = (C.c_void_p * len(names))(*[outputs[n].ctypes.data for n in names])
         self._ck(self._L.lgarb_update_steps_host(self._h, int(n_steps), _ptr(P), _ptr(E), len(names), cn, cp))
@@ -221,19 +242,28 @@ class BmiLGARBatch:
         in32 = P.dtype == np.float32
         P = np.ascontiguousarray(P, dtype=np.float32 if in32 else np.float64)
         E = np.ascontiguousarray(pet, dtype=P.dtype)
+        self._check_series(P, E)
         n_steps = P.shape[0]
         out32 = np.dtype(output_dtype) == np.float32
         if not isinstance(outputs, dict):
             outputs = {n: np.empty((n_steps, self.n_columns), dtype=np.float32 if out32 else np.float64) for n in outputs}
         names = list(outputs)
-        for n in names:
-            if outputs[n].dtype != (np.float32 if out32 else np.float64) or not outputs[n].flags.c_contiguous:
-                raise LgarbError(f"output array {n}: wrong dtype or not contiguous")
+        self._check_outputs(outputs, n_steps, np.float32 if out32 else np.float64)
         cn = (C.c_char_p * len(names))(*[n.encode() for n in names])
         cp = (C.c_void_p * len(names))(*[outputs[n].ctypes.data for n in names])
         self._ck(self._L.lgarb_update_steps_host_stream(self._h, int(n_steps), int(chunk_steps), 1 if in32 else 0, _ptr(P), _ptr(E),
                                                         len(names), cn, 1 if out32 else 0, cp))
         return outputs
+
+    def _check_series(self, P, E):
+        # a wrong shape would be an out-of-bounds read on the native side
+        if P.ndim != 2 or P.shape[1] != self.n_columns or E.shape != P.shape:
+            raise LgarbError(f"precip and pet must both be [n_steps][{self.n_columns}], got {P.shape} and {E.shape}")
+
+    def _check_outputs(self, outputs, n_steps, dtype):
+        for n, a in outputs.items():
+            if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags.c_contiguous or a.shape != (n_steps, self.n_columns):
+                raise LgarbError(f"output array {n}: must be a C-contiguous {np.dtype(dtype).name} array of shape ({n_steps}, {self.n_columns})")
 
     def synchronize(self):
         self._ck(self._L.lgarb_synchronize(self._h))
@@ -407,7 +437,8 @@ class BmiLGARBatch:
         self._ck(self._L.lgarb_set_force_all_active(self._h, int(bool(on))))
 
     def set_window_mode(self, mode):
-        """2 lanes kernel (default), 1 warp-tile window kernel, 0 hour-by-hour kernel pairs."""
+        """Scheduler of the multi-step verbs: 5 FETCH + STEP kernels, whole active steps per thread (default); 3 six stage kernels
+        with queues between them; 2 lanes kernel; 1 warp-tile window kernel; 0 hour-by-hour kernel pairs.  All bit-identical."""
         self._ck(self._L.lgarb_set_window_mode(self._h, int(mode)))
 
     def set_wave_params(self, search_quantum=0, front_search_pairs=0, finish_below=-1):
@@ -455,6 +486,16 @@ class BmiLGARBatch:
         out = C.c_double(0.0)
         self._ck(self._L.lgarb_measure_fp64_peak(self._h, float(ms), C.byref(out)))
         return out.value
+
+    def debug_pow(self, x, y, which=0):
+        """The engine's device pow on host arrays (lgarb_debug_pow): for the test that compares it with the host's pow."""
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+        if x.shape != y.shape:
+            raise LgarbError("x and y must have the same number of items")
+        out = np.empty_like(x)
+        self._ck(self._L.lgarb_debug_pow(self._h, x.size, _ptr(x), _ptr(y), _ptr(out), int(which)))
+        return out
 
     def get_stream(self) -> int:
         return int(self._L.lgarb_get_stream(self._h) or 0)

@@ -107,7 +107,10 @@ inline ParsedConfig parse_config(const std::string& config_file) {
     else if (key == "layer_soil_type") { for (double v : read_vector(val)) c.layer_soil_type.push_back((int)v); s_soil = true; }
     else if (key == "giuh_ordinates") { c.giuh_hourly = read_vector(val); s_giuh = true; }
     else if (key == "initial_psi") { c.initial_psi = std::stod(val); s_psi = true; }
-    else if (key == "max_valid_soil_types") { c.num_soil_types = std::min(std::stoi(val), MAX_NUM_SOIL_TYPES); }
+    else if (key == "max_valid_soil_types") {
+      c.num_soil_types = std::min(std::stoi(val), MAX_NUM_SOIL_TYPES);
+      if (c.num_soil_types < 1) throw std::runtime_error("max_valid_soil_types must be at least 1");  // the soil table has one row per type, 1-based
+    }
     else if (key == "soil_params_file") { c.soil_params_file = val; s_file = true; }
     else if (key == "wilting_point_psi") { c.wilting_point_psi = std::stod(val); s_wp = true; }
     else if (key == "field_capacity_psi") { c.field_capacity_psi = std::stod(val); s_fc = true; }
@@ -198,12 +201,17 @@ inline int read_soil_file(const std::string& path, int num_soil_types, double wi
                           const std::string& config_file = "") {
   FILE* fp = open_relative(path, config_file);
   if (!fp) throw std::runtime_error("Can't open input file named " + path);
+  if (num_soil_types < 1) {
+    fclose(fp);
+    throw std::runtime_error("max_valid_soil_types must be at least 1");
+  }
   table.assign(num_soil_types + 1, SoilRow());
   char jstr[256], soil_name[256];
   double theta_e = 0, theta_r = 0, vg_n = 0, vg_alpha = 0, Ksat = 0;
   int nread = 0, soil = 1;
   if (!fgets(jstr, 255, fp)) { fclose(fp); return 0; }
   while (fgets(jstr, 255, fp) != NULL) {
+    if (soil > num_soil_types) break;  // never write past the table, whatever the caller passed
     sscanf(jstr, "%s %lf %lf %lf %lf %lf", soil_name, &theta_r, &theta_e, &vg_alpha, &vg_n, &Ksat);
     SoilRow& s = table[soil];
     if (soil > 1) { s.lambda = table[soil - 1].lambda; s.psib = table[soil - 1].psib; }
@@ -267,6 +275,11 @@ inline void fill_class_layers(LgarColumnClass& c, const ParsedConfig& pc, const 
     l.thick = c.cum[k] - c.cum[k - 1];
     l.h_min = s.h_min;
     l.ln_alpha = log(s.alpha);
+    {  // max |d theta / d h| = de m n t (1+t)^(-m-1) / h at t = (alpha h)^n = m
+      const double hs = pow(s.m, 1.0 / s.n) / s.alpha;
+      const double v = (s.theta_e - s.theta_r) * s.m * s.n * s.m * pow(1.0 + s.m, -s.m - 1.0) / hs;
+      l.slope_max = (v == v && v > 0.0) ? v : 1e300;
+    }
     c.min_storage += s.theta_r * (c.cum[k] - c.cum[k - 1]);
     c.max_storage += s.theta_e * (c.cum[k] - c.cum[k - 1]);
     c.largest_Ks = fmax(s.Ksat, c.largest_Ks);

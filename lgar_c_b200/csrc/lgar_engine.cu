@@ -76,6 +76,7 @@ struct lgarb_engine {
   double* d_ff = nullptr;                 // [LGAR_MAXL+1][stride]
   bool ff_dirty = false;
   int device = 0;
+  bool has_device = false;  // `device` is the CUDA device this engine's memory and streams live on
   int64_t ncol = 0, stride = 0;
   int num_layers = 0;
   ParsedConfig pc;
@@ -93,7 +94,7 @@ struct lgarb_engine {
   cudaStream_t stream = nullptr;
   int active_blocks = 0;
   int window_blocks = 0;
-  int use_window = 3;          // multi-step runs: 3 = wavefront kernels, 2 = lanes kernel, 1 = warp-tile window kernel, 0 = hour-by-hour kernel pairs
+  int use_window = 5;          // multi-step runs: 5 = FETCH + STEP kernels (whole steps per thread), 3 = six stage kernels, 2 = lanes kernel, 1 = warp-tile window kernel, 0 = hour-by-hour kernel pairs
   int lanes_blocks = 0;
   unsigned int* d_work_trace = nullptr;  // [2][stride], allocated by lgarb_set_work_trace
   double* d_host_series = nullptr;  // staging of lgarb_update_steps_host
@@ -106,23 +107,17 @@ struct lgarb_engine {
   // beside FETCH/HEAD/FRONT/SEARCH of the same round and is joined before TAIL; 0 = CORR and a second TAIL at the end of
   // the round on the main stream
   int wave_corr_async = 1;
-  // experiment, off (measured slower): SEARCH by one warp per slot (lg_search_warp) in rounds with at most this many slots
-  // in flight; trips per launch = warp_search_mult x the thread-per-slot quantum
-  int warp_search_below = 0, warp_search_mult = 16;
   cudaStream_t side_stream = nullptr;
   cudaEvent_t side_ev[2] = {nullptr, nullptr};
   int wave_finish_below = 16384;
   int finish_lane_stride = 4;  // finishing kernel: one slot per this many lanes
-  int finish_smem = 0;         // finishing kernel keeps the lane records in shared memory (opt-in until measured): 1 = one
-                               // slot per finish_lane_stride lanes, 2 = converged (one stage at a time per warp, lanes refill)
+  int sm_count = 0;            // multiprocessors of the device: grids are sized in multiples of it
   int update_wave_min_cols = 1 << 30;  // lgarb_update: batches of at least this many columns take the wavefront kernels
   int wave_windows = 0;  // windows run so far (profiling range selection)
   int wave_escalate_below = 8192;
   int wave_corr_quantum = 64;  // correction-search trips per launch (scaled with the psi-search quantum when that escalates)
   int64_t wave_max_slots = 16777216;  // 2.8 KB of context per slot
   int64_t wave_rounds = 0;
-  // step kernel (mode 4)
-  int run_inline_quantum = 16, run_inline_corr_quantum = 16, run_search_quantum = 128, run_corr_quantum = 64, run_pairs = 1, run_keep = 8;
   int32_t* d_tile_counter = nullptr;
   cudaEvent_t win_ev[2] = {nullptr, nullptr};
   double prof_ms_window = 0;
@@ -188,13 +183,25 @@ struct lgarb_engine {
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
     initialized = false;
+    has_device = false;
   }
 };
 
 namespace {
 
+void do_initialize_body(lgarb_engine* e, const char* config_file, int64_t ncol, int device, const int32_t* types_in, const double* thick_in);
+// A failed initialisation (out of memory at a large n_columns is the likely one) must not keep the stream and the allocations it
+// already made: the engine is released, so that a retry with a smaller batch starts from a clean device.
 void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int device, const int32_t* types_in, const double* thick_in) {
-  if (e->initialized) e->release();
+  try {
+    do_initialize_body(e, config_file, ncol, device, types_in, thick_in);
+  } catch (...) {
+    e->release();
+    throw;
+  }
+}
+void do_initialize_body(lgarb_engine* e, const char* config_file, int64_t ncol, int device, const int32_t* types_in, const double* thick_in) {
+  e->release();  // tolerates an engine that was never (or only partly) initialised
   if (ncol <= 0) throw std::runtime_error("n_columns must be positive");
   if (ncol > 0x7FFFFFF0LL) throw std::runtime_error("n_columns must fit in int32");
   int ndev = 0;
@@ -204,6 +211,7 @@ void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int d
   if (device < 0 || device >= ndev) throw std::runtime_error("invalid CUDA device ordinal");
   CUDA_TRY(cudaSetDevice(device));
   e->device = device;
+  e->has_device = true;
   e->pc = parse_config(config_file);
   const ParsedConfig& pc = e->pc;
   const int L = (int)pc.layer_thickness.size();
@@ -356,6 +364,7 @@ void do_initialize(lgarb_engine* e, const char* config_file, int64_t ncol, int d
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   int per_sm = lgar_active_kernel_max_blocks_per_sm();
   if (per_sm < 1) per_sm = 1;
+  e->sm_count = prop.multiProcessorCount;
   e->active_blocks = prop.multiProcessorCount * per_sm;  // persistent: a whole number of waves of the SM count
   int wper_sm = lgar_window_kernel_max_blocks_per_sm();
   if (wper_sm < 1) wper_sm = 1;
@@ -758,8 +767,24 @@ void copy_str(char* dst, int cap, const std::string& s) {
 
 }  // namespace
 
+// CUDA's current device is a property of the calling THREAD: every entry point that touches CUDA makes the engine's device
+// current for the duration of the call and puts the caller's back afterwards, so that two engines on two GPUs in one process, or
+// a call from another thread than the one that initialised the engine, allocate and launch where the engine lives.
+struct LgarbDeviceGuard {
+  int prev = -1;
+  explicit LgarbDeviceGuard(const lgarb_engine* e) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (e && e->has_device && e->device != prev) cudaSetDevice(e->device);
+  }
+  ~LgarbDeviceGuard() {
+    int now = -1;
+    if (prev >= 0 && cudaGetDevice(&now) == cudaSuccess && now != prev) cudaSetDevice(prev);
+  }
+};
+
 #define LGARB_GUARD(e, ...)                                   \
   try {                                                       \
+    LgarbDeviceGuard lgarb_device_guard_(e);                  \
     __VA_ARGS__;                                              \
     return LGARB_SUCCESS;                                     \
   } catch (const std::exception& ex) {                        \
@@ -785,27 +810,21 @@ int lgarb_create(lgarb_engine** out) {
   knob("LGARB_WAVE_PAIRS", (*out)->wave_pairs);
   knob("LGARB_WAVE_CORR_PAIRS", (*out)->wave_corr_pairs);
   knob("LGARB_WAVE_CORR_ASYNC", (*out)->wave_corr_async);
-  knob("LGARB_WARP_SEARCH_BELOW", (*out)->warp_search_below);
-  knob("LGARB_WARP_SEARCH_MULT", (*out)->warp_search_mult);
   knob("LGARB_WAVE_FINISH_BELOW", (*out)->wave_finish_below);
   knob("LGARB_FINISH_LANE_STRIDE", (*out)->finish_lane_stride);
-  knob("LGARB_FINISH_SMEM", (*out)->finish_smem);
   knob("LGARB_UPDATE_WAVE_MIN_COLS", (*out)->update_wave_min_cols);
   knob("LGARB_WAVE_ESCALATE_BELOW", (*out)->wave_escalate_below);
   knob("LGARB_WAVE_CORR_QUANTUM", (*out)->wave_corr_quantum);
-  knob("LGARB_RUN_QUANTUM", (*out)->run_inline_quantum);
-  knob("LGARB_RUN_CORR_QUANTUM", (*out)->run_inline_corr_quantum);
-  knob("LGARB_RUN_SEARCH_QUANTUM", (*out)->run_search_quantum);
-  knob("LGARB_RUN_PAIRS", (*out)->run_pairs);
-  knob("LGARB_RUN_KEEP", (*out)->run_keep);
-  knob("LGARB_RUN_BIG_CORR_QUANTUM", (*out)->run_corr_quantum);
   knob("LGARB_WINDOW_MODE", (*out)->use_window);
   return LGARB_SUCCESS;
 }
 
 int lgarb_destroy(lgarb_engine* e) {
   if (!e) return LGARB_FAILURE;
-  if (e->initialized) e->release();
+  {
+    LgarbDeviceGuard guard(e);
+    e->release();  // unconditionally: also what a failed initialisation may have left
+  }
   delete e;
   return LGARB_SUCCESS;
 }
@@ -861,18 +880,28 @@ void ensure_wave(lgarb_engine* e) {
   LgarWave& wv = e->wave;
   memset(&wv, 0, sizeof(wv));
   wv.nslots = (int32_t)std::min<int64_t>(e->ncol, e->wave_max_slots);
-  void* p = nullptr;
-  CUDA_TRY(cudaMalloc(&p, (size_t)wv.nslots * lgar_lane_context_bytes()));
-  e->allocs.push_back(p);
-  wv.ctx = (LgLane*)p;
-  for (int s = 0; s < LGAR_NSTAGE; s++)
-    for (int b = 0; b < 2; b++) wv.queue[s][b] = e->dalloc<int32_t>((size_t)wv.nslots, false);
-  wv.qcount = e->dalloc<int32_t>(LGAR_NSTAGE * 2);
-  wv.done_columns = e->dalloc<int32_t>(1);
-  wv.cursor = e->dalloc<int32_t>(1);
-  if (!e->side_stream) {
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->side_ev[i], cudaEventDisableTiming));
+  const size_t mark = e->allocs.size();
+  try {
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, (size_t)wv.nslots * lgar_lane_context_bytes()));
+    e->allocs.push_back(p);
+    wv.ctx = (LgLane*)p;
+    for (int s = 0; s < LGAR_NSTAGE; s++)
+      for (int b = 0; b < 2; b++) wv.queue[s][b] = e->dalloc<int32_t>((size_t)wv.nslots, false);
+    wv.qcount = e->dalloc<int32_t>(LGAR_NSTAGE * 2);
+    wv.done_columns = e->dalloc<int32_t>(1);
+    wv.cursor = e->dalloc<int32_t>(1);
+    if (!e->side_stream) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->side_ev[i], cudaEventDisableTiming));
+    }
+  } catch (...) {  // a retry must not pile up what this attempt allocated
+    while (e->allocs.size() > mark) {
+      cudaFree(e->allocs.back());
+      e->allocs.pop_back();
+    }
+    memset(&wv, 0, sizeof(wv));
+    throw;
   }
   e->wave_ready = true;
 }
@@ -923,33 +952,13 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       cudaEventRecord(dbg_evs.back().first, e->stream);
       dbg_evs.back().second = stage;
     }
-    if (stage == LG_ST_SEARCH && e->use_window == 3 && in_flight <= e->warp_search_below)
-      CUDA_TRY(lgar_launch_wave_search_warp(wv, consume, mask, (int)std::min<int64_t>((int64_t)quantum * e->warp_search_mult, 1 << 30), in_flight, launch_stream));
-    else
-      CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, stage == LG_ST_CORR ? std::max(1, quantum * e->wave_corr_quantum / e->wave_quantum) : quantum, in_flight,
-                                      launch_stream));
+    CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, stage == LG_ST_CORR ? std::max(1, quantum * e->wave_corr_quantum / e->wave_quantum) : quantum, in_flight,
+                                    e->sm_count, launch_stream));
     e->launches += 2;
   };
-  auto launch_q = [&](int stage, int q) {  // SEARCH / CORR with an explicit quantum
-    const int consume = par[stage];
-    par[stage] ^= 1;
-    unsigned mask = 0;
-    for (int s = 0; s < LGAR_NSTAGE; s++) mask |= (unsigned)par[s] << s;
-    if (dbg_on) {
-      dbg_evs.emplace_back();
-      cudaEventCreate(&dbg_evs.back().first);
-      cudaEventRecord(dbg_evs.back().first, e->stream);
-      dbg_evs.back().second = stage;
-    }
-    CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, q, in_flight, e->stream));
-    e->launches += 2;
-  };
-  auto launch_run = [&](int q, int qc) {  // the step kernel consumes the HEAD, FRONT and TAIL queues
-    unsigned consume_mask = 0;
-    for (int s : {LG_ST_HEAD, LG_ST_FRONT, LG_ST_TAIL}) {
-      consume_mask |= (unsigned)par[s] << s;
-      par[s] ^= 1;
-    }
+  auto launch_step = [&]() {  // the STEP kernel consumes the HEAD queue and appends to the FETCH queue
+    const int consume = par[LG_ST_HEAD];
+    par[LG_ST_HEAD] ^= 1;
     unsigned mask = 0;
     for (int s = 0; s < LGAR_NSTAGE; s++) mask |= (unsigned)par[s] << s;
     if (dbg_on) {
@@ -958,7 +967,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       cudaEventRecord(dbg_evs.back().first, e->stream);
       dbg_evs.back().second = LG_ST_HEAD;  // booked under HEAD in the debug line
     }
-    CUDA_TRY(lgar_launch_wave_run(e->cfg, e->d, w, wv, consume_mask, mask, q, qc, e->run_keep, in_flight, e->stream));
+    CUDA_TRY(lgar_launch_wave_step(e->cfg, e->d, w, wv, consume, mask, in_flight, e->sm_count, e->stream));
     e->launches += 2;
   };
   int32_t* h_cnt = (int32_t*)e->pinned(64 * sizeof(int32_t));
@@ -984,12 +993,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       if (in_flight == 0) break;
       if (in_flight <= e->wave_finish_below) {  // the stragglers: one thread per slot runs its column to the end of the window
         if (debug) cudaEventRecord(dbg[0], e->stream);
-        if (e->finish_smem == 2)  // converged, records in shared memory; a negative lane stride = search trips per turn
-          CUDA_TRY(lgar_launch_wave_finish_smem(e->cfg, e->d, w, wv, in_flight, std::min(e->finish_lane_stride, 0), e->stream));
-        else if (e->finish_smem && e->finish_lane_stride > 0)
-          CUDA_TRY(lgar_launch_wave_finish_smem(e->cfg, e->d, w, wv, in_flight, e->finish_lane_stride, e->stream));
-        else
-          CUDA_TRY(lgar_launch_wave_finish(e->cfg, e->d, w, wv, in_flight, e->finish_lane_stride, e->stream));
+        CUDA_TRY(lgar_launch_wave_finish(e->cfg, e->d, w, wv, in_flight, e->finish_lane_stride, e->sm_count, e->stream));
         e->launches += 2;
         if (debug) {
           cudaEventRecord(dbg[1], e->stream);
@@ -1025,29 +1029,22 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       CUDA_TRY(cudaEventRecord(e->side_ev[1], e->side_stream));
       corr_forked = true;
     }
-    if (e->use_window == 4) {
-      // step kernel: FETCH, RUN (whole steps, searches inline up to the quantum), then the parked long searches
-      // (compacted, `run_search_quantum` trips per launch) and the steps they hand back
-      const int qbig = std::max(1, (int)((int64_t)e->run_search_quantum * quantum / e->wave_quantum));
+    if (e->use_window == 5) {
+      // whole steps per thread: FETCH walks the columns to their next active hour, STEP runs that hour
       if (cnt[LG_ST_FETCH] > 0) launch(LG_ST_FETCH);
-      launch_run(e->run_inline_quantum, e->run_inline_corr_quantum);
-      for (int k = 0; k < e->run_pairs; k++) {
-        launch_q(LG_ST_SEARCH, qbig);
-        launch_q(LG_ST_CORR, std::max(1, (int)((int64_t)e->run_corr_quantum * quantum / e->wave_quantum)));
-        launch_run(e->run_inline_quantum, e->run_inline_corr_quantum);
-      }
+      launch_step();
     } else if (new_steps) {
       launch(LG_ST_FETCH);
       launch(LG_ST_HEAD);  // runs the first stretch of the front loop too
     }
-    if (e->use_window != 4 && (new_steps || cnt[LG_ST_FRONT] + cnt[LG_ST_SEARCH] > 0)) {
+    if (e->use_window != 5 && (new_steps || cnt[LG_ST_FRONT] + cnt[LG_ST_SEARCH] > 0)) {
       if (cnt[LG_ST_FRONT] > 0) launch(LG_ST_FRONT);
       for (int k = 0; k < e->wave_pairs; k++) {
         launch(LG_ST_SEARCH);
         launch(LG_ST_FRONT);
       }
     }
-    if (e->use_window != 4) {
+    if (e->use_window != 5) {
       if (corr_forked) CUDA_TRY(cudaStreamWaitEvent(e->stream, e->side_ev[1], 0));
       launch(LG_ST_TAIL);
       for (int k = 0; k < (corr_async ? 0 : e->wave_corr_pairs); k++) {
@@ -1593,7 +1590,7 @@ int lgarb_get_warp_times(lgarb_engine* e, uint32_t* out16384) {
     d2h(e, out16384, e->d_work_trace + 2 * e->stride + 64, 2 * 8192 * sizeof(uint32_t));
   });
 }
-int lgarb_set_window_mode(lgarb_engine* e, int mode) { LGARB_GUARD(e, e->use_window = (mode < 0 || mode > 4) ? 3 : mode); }
+int lgarb_set_window_mode(lgarb_engine* e, int mode) { LGARB_GUARD(e, e->use_window = (mode < 0 || mode > 5 || mode == 4) ? 5 : mode); }
 int lgarb_set_wave_params(lgarb_engine* e, int search_quantum, int front_search_pairs, int finish_below) {
   LGARB_GUARD(e, {
     if (search_quantum > 0) e->wave_quantum = search_quantum;
@@ -1656,6 +1653,24 @@ int lgarb_get_profile(lgarb_engine* e, double* out6) {
 }
 
 void* lgarb_get_stream(lgarb_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int lgarb_debug_pow(lgarb_engine* e, int64_t n, const double* x, const double* y, double* out, int which) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (n < 0 || !x || !y || !out) throw std::runtime_error("bad arguments");
+    if (n == 0) return LGARB_SUCCESS;
+    double* dbuf = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&dbuf, (size_t)n * 3 * sizeof(double)));
+    cudaError_t err = cudaMemcpyAsync(dbuf, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(dbuf + n, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) err = lgar_launch_debug_pow(dbuf, dbuf + n, dbuf + 2 * n, n, which, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(out, dbuf + 2 * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(dbuf);
+    e->launches += 1;
+    CUDA_TRY(err);
+  });
+}
 
 int lgarb_measure_fp64_peak(lgarb_engine* e, double ms, double* tflops) {
   LGARB_GUARD(e, {

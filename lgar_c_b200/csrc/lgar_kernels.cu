@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_lanes_kernel(const _
     if (st == chosen) {
       if (chosen == LG_ST_SEARCH) {
         const int keep = (n_search >= LGAR_SEARCH_MIN) ? LGAR_SEARCH_MIN : 1;
+        if (!L.q.done) lg_search_some(L.q, *L.cls, 0);  // the fast path (lgar_search.cuh); plain trips below if it declined
         for (int it = 0; it < LGAR_SEARCH_QUANTUM; it++) {
           if (!L.q.done) {
             lg_search_iter(L.q, *L.cls);
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         LgLane& G = slots[slot].L;
         LgSearch q = G.q;
         const LgarColumnClass* cls = G.cls;
-        for (int it = 0; it < quantum && !q.done; it++) lg_search_iter(q, *cls);
+        lg_search_some(q, *cls, quantum);
         G.q = q;
         if (q.done) G.resume = true;
         next = q.done ? LG_ST_FRONT : LG_ST_SEARCH;
@@ -405,35 +406,6 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
   }
 }
 
-// ---- SEARCH, one warp per slot ------------------------------------------------------------------------
-// When the SEARCH queue is short (drop-out rounds: a few thousand searches, the long ones among them) a thread per
-// search leaves the machine empty and every launch waits for `quantum` dependent trips.  Here a warp takes one search and
-// runs it 32 trips at a time (lg_search_warp, lgar_lanes.cuh): the same numbers, ~12 x fewer dependent instructions.
-// MEASURED SLOWER and therefore off by default (LGARB_WARP_SEARCH_BELOW=0): most searches end within a few trips (mean
-// 41), and a warp step costs ~1 300 instructions whether it commits 32 trips or 3 -- 4.8e8 -> 4.5e8 column-steps/s with
-// the kernel used below 65 536 slots in flight, 4.1e8 below 262 144, 1.8e8 always; letting the warp take over only the
-// searches that have already run 192 trips was no better (2.1e8: the take-over holds the round up).  Kept, with its test,
-// as the record of that experiment.
-__global__ void __launch_bounds__(128) lgar_wave_search_warp_kernel(const __grid_constant__ LgarWave wv, int consume, unsigned append_mask, int quantum) {
-  const int n = wv.qcount[LG_ST_SEARCH * 2 + consume];
-  LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
-  const int lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
-    const int slot = wv.queue[LG_ST_SEARCH][consume][i];
-    LgLane& G = slots[slot].L;
-    LgSearch q = G.q;  // every lane reads the same record
-    const LgarColumnClass* cls = G.cls;
-    lg_search_warp(q, *cls, quantum);
-    if (lane == 0) {
-      G.q = q;
-      if (q.done) G.resume = true;
-    }
-    wave_push(wv, append_mask, LG_ST_FRONT, lane == 0 && q.done, slot);
-    wave_push(wv, append_mask, LG_ST_SEARCH, lane == 0 && !q.done, slot);
-  }
-}
-
 // ---- FETCH with per-lane refill -------------------------------------------------------------------------
 // FETCH walks a column through the hours that replay cached fluxes until it needs an active step.  The walks are heavy
 // tailed (a dry spell is tens to hundreds of hours, a wet one a single hour), so with one queue entry per thread a warp
@@ -526,157 +498,37 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
   if (w.prof && front_sum) atomicAdd(w.prof, front_sum);
 }
 
-// ---- step kernel (mode 4) ----------------------------------------------------------------------------
-// The stage kernels above move a context of 1.2-1.7 KB between HBM and the SM at every stage boundary (about
-// 11 KB per active column-step, plus the same again through thread-private memory) and a step crosses ~13
-// kernel boundaries, so a round never takes less than ~1.6 ms however few slots are left (ncu, round 1 of a
-// bench window: HEAD/FRONT/TAIL are 70 % of the round at 5-20 % issue utilisation).  Here a thread keeps its
-// slot for as much of the step as the psi searches allow: it takes a slot from the HEAD queue (new step), the
-// FRONT queue (a parked search has finished) or the TAIL queue (a parked correction search has finished),
-// loads what that entry point needs and runs the staged program of lgar_lanes.cuh to the end of the step.
-// The warp executes ONE stage at a time for the lanes that are in it (vote below): everything that is not a
-// search first, so that lanes meet again in the search loop; the searches then iterate converged for at most
-// `quantum` trips.  A lane whose search is not finished by then -- the heavy tail: mean 41 trips, max > 10^4 --
-// parks its context in HBM and queues for the SEARCH / CORR kernels, which iterate compacted and converged
-// with a large quantum and hand the slot back through the FRONT / TAIL queue.  A step that never exceeds the
-// quantum (the common case) costs one state read and one state write.
-#ifndef LGAR_RUN_THREADS
-#define LGAR_RUN_THREADS 256
+__global__ void lgar_wave_reset_kernel(int32_t* count, int32_t* cursor);
+
+// ---- STEP kernel (mode 5) ------------------------------------------------------------------------------
+// What forced the step into six stage kernels was the psi search: 32-128 dependent trips of two pow per layer, heavy tailed to
+// 10^4 (median 7 theta evaluations per active step, mean 115, max > 20 000), so lanes that ran whole steps side by side kept
+// 2.5 of 32 lanes busy.  With the fast path of lgar_search.cuh a search is ~10 evaluations plus a cheap replay whatever its
+// trip count, and an active step is a piece of work of bounded, similar size for every lane.  So a thread takes a slot from
+// the HEAD queue, loads the column STATE (scalars, epilogue state, live fronts: ~0.6 KB), runs the whole step -- sub-cycles,
+// front loop, searches, corrections, reservoir, GIUH, outputs -- and stores the state back: the 1.2-1.7 KB step context that the
+// stage kernels carried through HBM at every stage boundary (4.4 x the algorithmic DRAM bytes in round 1) never leaves the
+// thread.  Rounds are FETCH, STEP.
+#ifndef LGAR_MB_STEP
+#define LGAR_MB_STEP 0
 #endif
-#ifndef LGAR_MB_RUN
-#define LGAR_MB_RUN 0
-#endif
-#ifndef LGAR_RUN_BLOCKSYNC
-#define LGAR_RUN_BLOCKSYNC 1
-#endif
-__global__ void __launch_bounds__(LGAR_RUN_THREADS, LGAR_MB_RUN) lgar_wave_run_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv,
-                                                                                      unsigned consume_mask, unsigned append_mask, int quantum, int corr_quantum, int keep) {
-  const unsigned FULL = 0xFFFFFFFFu;
-  const int cH = (consume_mask >> LG_ST_HEAD) & 1, cF = (consume_mask >> LG_ST_FRONT) & 1, cT = (consume_mask >> LG_ST_TAIL) & 1;
-  const int nH = wv.qcount[LG_ST_HEAD * 2 + cH], nF = wv.qcount[LG_ST_FRONT * 2 + cF], nT = wv.qcount[LG_ST_TAIL * 2 + cT];
-  // every queue starts on a warp boundary: the lanes of a warp enter at the same point of the program
-  const int eH = (nH + 31) & ~31, eF = (nF + 31) & ~31, eT = (nT + 31) & ~31;
-  const int total = eH + eF + eT;
+__global__ void __launch_bounds__(128, LGAR_MB_STEP) lgar_wave_step_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int consume,
+                                                                           unsigned append_mask) {
+  const int n = wv.qcount[LG_ST_HEAD * 2 + consume];
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
   unsigned long long front_sum = 0, active_sum = 0;
   unsigned long long* fsp = w.prof ? &front_sum : nullptr;
-#if LGAR_RUN_BLOCKSYNC
-  // block-wide vote (one barrier per turn): every warp of the block runs the same stage at the same time, so the
-  // SM fetches one stage's code at a time (ncu on the warp-level vote: 57 % of the stall cycles were
-  // instruction fetch, 20 warps per SM each somewhere else in 300 KB of SASS)
-  __shared__ unsigned s_present[2][LGAR_RUN_THREADS / 32];
-  int vote_buf = 0;
-  const int btotal = (total + LGAR_RUN_THREADS - 1) / LGAR_RUN_THREADS * LGAR_RUN_THREADS;
-#else
-  const int btotal = total;
-#endif
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < btotal; i += gridDim.x * blockDim.x) {
-    int entry, j;
-    if (i < eH) {
-      entry = LG_ST_HEAD; j = i;
-    } else if (i < eH + eF) {
-      entry = LG_ST_FRONT; j = i - eH;
-    } else {
-      entry = LG_ST_TAIL; j = i - eH - eF;
-    }
-    const int nq = entry == LG_ST_HEAD ? nH : entry == LG_ST_FRONT ? nF : nT;
-    const bool valid = j < nq;
-    const int slot = valid ? wv.queue[entry][entry == LG_ST_HEAD ? cH : entry == LG_ST_FRONT ? cF : cT][j] : 0;
-    LgLaneSlot S;
-    LgLane& L = S.L;
-    int st = LG_ST_DONE;   // DONE = this lane has nothing (more) to run in this pass
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31); i += gridDim.x * blockDim.x) {
+    const bool valid = i < n;
+    const int slot = valid ? wv.queue[LG_ST_HEAD][consume][i] : 0;
     if (valid) {
-      if (entry == LG_ST_HEAD)
-        lane_load<LG_PART_STATE>(&S, &slots[slot]);
-      else if (entry == LG_ST_FRONT)
-        lane_load<LG_PART_ALL>(&S, &slots[slot]);
-      else
-        lane_load<LG_PART_STATE | LG_PART_STEP>(&S, &slots[slot]);
-      L.c.cfg = &cfg;
-      L.c.cls = L.cls;
-      L.c.f = &L.f;
-      L.c.ff = lg_ff_ones;
-      st = entry;
+      LgLaneSlot S;
+      lane_load<LG_PART_STATE>(&S, &slots[slot]);
+      lg_stage_step(cfg, d, w, S.L, fsp);
+      active_sum += S.L.s.cache_fluxes ? 0 : 1;
+      lane_store<LG_PART_STATE>(&slots[slot], &S);
     }
-    int next = -1;
-    for (;;) {
-      const unsigned m_head = __ballot_sync(FULL, st == LG_ST_HEAD);
-      const unsigned m_front = __ballot_sync(FULL, st == LG_ST_FRONT);
-      const unsigned m_search = __ballot_sync(FULL, st == LG_ST_SEARCH);
-      const unsigned m_tail = __ballot_sync(FULL, st == LG_ST_TAIL);
-      const unsigned m_corr = __ballot_sync(FULL, st == LG_ST_CORR);
-#if LGAR_RUN_BLOCKSYNC
-      if ((threadIdx.x & 31) == 0)
-        s_present[vote_buf][threadIdx.x >> 5] = (m_head ? 1u : 0u) | (m_front ? 2u : 0u) | (m_search ? 4u : 0u) | (m_tail ? 8u : 0u) | (m_corr ? 16u : 0u);
-      __syncthreads();
-      unsigned present = 0;
-#pragma unroll
-      for (int wi = 0; wi < LGAR_RUN_THREADS / 32; wi++) present |= s_present[vote_buf][wi];
-      vote_buf ^= 1;
-      if (!present) break;
-      const int chosen = (present & 1u) ? LG_ST_HEAD : (present & 2u) ? LG_ST_FRONT : (present & 4u) ? LG_ST_SEARCH : (present & 8u) ? LG_ST_TAIL : LG_ST_CORR;
-#else
-      if (!(m_head | m_front | m_search | m_tail | m_corr)) break;
-      const int chosen = m_head ? LG_ST_HEAD : m_front ? LG_ST_FRONT : m_search ? LG_ST_SEARCH : m_tail ? LG_ST_TAIL : LG_ST_CORR;
-#endif
-      if (chosen == LG_ST_HEAD) {
-        if (st == LG_ST_HEAD) {
-          lg_stage_head(cfg, d, w, L, fsp);
-          active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
-          st = L.stage;
-          if (st == LG_ST_FETCH) { next = LG_ST_FETCH; st = LG_ST_DONE; }
-        }
-      } else if (chosen == LG_ST_FRONT) {
-        if (st == LG_ST_FRONT) {
-          lg_stage_front(L);
-          st = L.stage;
-        }
-      } else if (chosen == LG_ST_SEARCH) {
-        if (st == LG_ST_SEARCH) {
-          for (int it = 0; it < quantum; it++) {
-            if (!L.q.done) lg_search_iter(L.q, *L.cls);
-            if (__popc(__ballot_sync(m_search, !L.q.done)) < keep) break;
-          }
-          if (L.q.done) {
-            L.resume = true;
-            st = LG_ST_FRONT;
-          } else {
-            next = LG_ST_SEARCH;   // park: the SEARCH kernel continues this search
-            st = LG_ST_DONE;
-          }
-        }
-      } else if (chosen == LG_ST_TAIL) {
-        if (st == LG_ST_TAIL) {
-          lg_stage_tail(cfg, d, w, L, fsp);
-          st = L.stage;
-          if (st == LG_ST_FETCH) { next = LG_ST_FETCH; st = LG_ST_DONE; }
-        }
-      } else {
-        if (st == LG_ST_CORR) {
-          for (int it = 0; it < corr_quantum; it++) {
-            if (!L.k.done) lg_corr_iter(L.k, L.f, *L.cls);
-            if (__popc(__ballot_sync(m_corr, !L.k.done)) < keep) break;
-          }
-          if (L.k.done) {
-            st = LG_ST_TAIL;
-          } else {
-            next = LG_ST_CORR;   // park: the CORR kernel continues
-            st = LG_ST_DONE;
-          }
-        }
-      }
-    }
-    if (valid) {
-      if (next == LG_ST_FETCH)
-        lane_store<LG_PART_STATE>(&slots[slot], &S);   // the step is over: only the column state lives on
-      else if (next == LG_ST_CORR)
-        lane_store<LG_PART_STATE | LG_PART_STEP>(&slots[slot], &S);
-      else
-        lane_store<LG_PART_ALL>(&slots[slot], &S);
-    }
-    wave_push(wv, append_mask, LG_ST_FETCH, valid && next == LG_ST_FETCH, slot);
-    wave_push(wv, append_mask, LG_ST_SEARCH, valid && next == LG_ST_SEARCH, slot);
-    wave_push(wv, append_mask, LG_ST_CORR, valid && next == LG_ST_CORR, slot);
+    wave_push(wv, append_mask, LG_ST_FETCH, valid, slot);
   }
   if (w.prof) {
     if (front_sum) atomicAdd(w.prof, front_sum);
@@ -684,16 +536,11 @@ __global__ void __launch_bounds__(LGAR_RUN_THREADS, LGAR_MB_RUN) lgar_wave_run_k
   }
 }
 
-__global__ void lgar_wave_reset3_kernel(int32_t* a, int32_t* b, int32_t* c) { *a = 0; *b = 0; *c = 0; }
-
-cudaError_t lgar_launch_wave_run(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, unsigned consume_mask,
-                                 unsigned append_mask, int quantum, int corr_quantum, int keep, int max_items, cudaStream_t stream) {
-  const int items = std::min(wv.nslots, max_items) + 96;  // three queues, each padded to a warp
-  const int blocks = std::max(1, std::min((items + LGAR_RUN_THREADS - 1) / LGAR_RUN_THREADS, 148 * 16));
-  lgar_wave_run_kernel<<<blocks, LGAR_RUN_THREADS, 0, stream>>>(cfg, d, w, wv, consume_mask, append_mask, quantum, corr_quantum, keep);
-  lgar_wave_reset3_kernel<<<1, 1, 0, stream>>>(wv.qcount + LG_ST_HEAD * 2 + ((consume_mask >> LG_ST_HEAD) & 1),
-                                               wv.qcount + LG_ST_FRONT * 2 + ((consume_mask >> LG_ST_FRONT) & 1),
-                                               wv.qcount + LG_ST_TAIL * 2 + ((consume_mask >> LG_ST_TAIL) & 1));
+cudaError_t lgar_launch_wave_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int consume, unsigned append_mask,
+                                  int max_items, int sm_count, cudaStream_t stream) {
+  const int blocks = std::max(1, std::min((std::min(wv.nslots, max_items) + 127) / 128, sm_count * 16));
+  lgar_wave_step_kernel<<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask);
+  lgar_wave_reset_kernel<<<1, 1, 0, stream>>>(wv.qcount + LG_ST_HEAD * 2 + consume, nullptr);
   return cudaGetLastError();
 }
 
@@ -747,7 +594,7 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
           break;
         case LG_ST_FRONT: lg_stage_front(L); break;
         case LG_ST_SEARCH:
-          while (!L.q.done) lg_search_iter(L.q, *L.cls);
+          lg_search_run(L.q, *L.cls);
           L.resume = true;
           L.stage = LG_ST_FRONT;
           break;
@@ -758,106 +605,6 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
           break;
         default: L.stage = LG_ST_DONE; break;
       }
-    }
-  }
-  if (w.prof) {
-    if (front_sum) atomicAdd(w.prof, front_sum);
-    if (active_sum) atomicAdd(w.prof + 1, active_sum);
-  }
-}
-
-// Finishing kernel, converged variant: every lane of a warp owns a slot and the warp executes ONE stage at a time for the
-// lanes that are in it, going round the stages in program order (FETCH, HEAD, FRONT, SEARCH, TAIL, CORR; empty ones are
-// skipped), so a lane is served at least once per cycle and a plain step rides one cycle from FETCH to TAIL.  The variant
-// above leaves each lane to its own `switch`: the (up to 8) lanes of a warp sit in different stages and the hardware runs
-// them one after the other -- the serial chain of a column then costs the SUM of what its warp neighbours do.
-#ifndef LGAR_COOP_AFTER
-#define LGAR_COOP_AFTER 256   // trips a search must have behind it before its warp takes it over (finishing kernel)
-#endif
-__global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_vote_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int quantum) {
-  const unsigned FULL = 0xFFFFFFFFu;
-  LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
-  int total = 0;
-  for (int q = 0; q < 2 * LGAR_NSTAGE; q++) total += wv.qcount[q];
-  unsigned long long front_sum = 0, active_sum = 0;
-  unsigned long long* fsp = w.prof ? &front_sum : nullptr;
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int i0 = (gtid & ~31); i0 < total; i0 += gridDim.x * blockDim.x) {  // warp-uniform trip count
-    const int i = i0 + (threadIdx.x & 31);
-    int j = i, slot = -1, stage = LG_ST_DONE;
-    if (i < total)
-      for (int q = 0; q < 2 * LGAR_NSTAGE; q++) {  // item i of the concatenation of all queues
-        const int n = wv.qcount[q];
-        if (j < n) {
-          slot = wv.queue[q >> 1][q & 1][j];
-          stage = q >> 1;
-          break;
-        }
-        j -= n;
-      }
-    LgLaneSlot S;
-    LgLane& L = S.L;
-    if (slot >= 0) {
-      lane_load<LG_PART_ALL>(&S, &slots[slot]);
-      L.c.cfg = &cfg;
-      L.c.cls = L.cls;
-      L.c.f = &L.f;
-      L.c.ff = lg_ff_ones;
-    }
-    L.stage = stage;  // the queue a slot sits in is authoritative
-    int cur = LGAR_NSTAGE - 1;
-    for (;;) {
-      unsigned m[LGAR_NSTAGE];
-      unsigned any = 0;
-#pragma unroll
-      for (int s = 0; s < LGAR_NSTAGE; s++) {
-        m[s] = __ballot_sync(FULL, L.stage == s);
-        any |= m[s];
-      }
-      if (!any) break;
-#pragma unroll 1
-      for (int k = 0; k < LGAR_NSTAGE; k++) {  // next non-empty stage after the one just run
-        cur = (cur + 1 == LGAR_NSTAGE) ? 0 : cur + 1;
-        if (m[cur]) break;
-      }
-      if (cur == LG_ST_SEARCH) {
-        // every searching lane runs `quantum` trips of its own search (the mean search takes 41).  A search that has then
-        // been going for LGAR_COOP_AFTER trips or more is one of the monsters (10^3 - 10^5 trips: a single one is 5-50 ms of
-        // dependent FP64 work for one thread, and this kernel lasts as long as the longest chain of them): the whole warp
-        // finishes it, 32 trips at a time (lg_search_warp, same numbers).
-        const bool mine = L.stage == LG_ST_SEARCH;
-        if (mine)
-          for (int it = 0; it < quantum && !L.q.done; it++) lg_search_iter(L.q, *L.cls);
-        unsigned ms = __ballot_sync(FULL, mine && !L.q.done && L.q.iter >= LGAR_COOP_AFTER);
-        while (ms) {
-          const int src = __ffs(ms) - 1;
-          ms &= ms - 1;
-          LgSearch qq = L.q;
-          lg_search_bcast(qq, src);
-          const LgarColumnClass* cp = reinterpret_cast<const LgarColumnClass*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(L.cls), src));
-          lg_search_warp(qq, *cp, 1 << 30);
-          if ((threadIdx.x & 31) == src) L.q = qq;
-        }
-        if (mine && L.q.done) {
-          L.resume = true;
-          L.stage = LG_ST_FRONT;
-        }
-      } else if (L.stage == cur) {
-        switch (cur) {
-          case LG_ST_FETCH: lg_stage_fetch(cfg, d, w, L, fsp); break;
-          case LG_ST_HEAD:
-            lg_stage_head(cfg, d, w, L, fsp);
-            active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
-            break;
-          case LG_ST_FRONT: lg_stage_front(L); break;
-          case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, fsp); break;
-          default:
-            for (int it = 0; it < quantum && !L.k.done; it++) lg_corr_iter(L.k, L.f, *L.cls);
-            if (L.k.done) L.stage = LG_ST_TAIL;
-            break;
-        }
-      }
-      __syncwarp();
     }
   }
   if (w.prof) {
@@ -882,15 +629,9 @@ __global__ void lgar_wave_clear_kernel(LgarWave wv) {
 }
 
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
-                                    int lane_stride, cudaStream_t stream) {
-  if (lane_stride <= 0) {  // converged variant, -lane_stride = search trips per turn (0: default)
-    const int blocks = std::max(1, std::min((in_flight + 127) / 128, 148 * 16));
-    lgar_wave_finish_vote_kernel<<<blocks, 128, 0, stream>>>(cfg, d, w, wv, lane_stride < 0 ? -lane_stride : 128);
-    lgar_wave_clear_kernel<<<1, 32, 0, stream>>>(wv);
-    return cudaGetLastError();
-  }
+                                    int lane_stride, int sm_count, cudaStream_t stream) {
   lane_stride = std::max(1, std::min(lane_stride, 32));
-  const int blocks = std::max(1, std::min((int)(((int64_t)in_flight * lane_stride + 127) / 128), 148 * 16));
+  const int blocks = std::max(1, std::min((int)(((int64_t)in_flight * lane_stride + 127) / 128), sm_count * 16));
   lgar_wave_finish_kernel<<<blocks, 128, 0, stream>>>(cfg, d, w, wv, lane_stride);
   lgar_wave_clear_kernel<<<1, 32, 0, stream>>>(wv);
   return cudaGetLastError();
@@ -930,9 +671,9 @@ cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& 
 }
 
 cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int stage, int consume,
-                                   unsigned append_mask, int quantum, int max_items, cudaStream_t stream) {
+                                   unsigned append_mask, int quantum, int max_items, int sm_count, cudaStream_t stream) {
   // grid-stride over the queue; max_items (slots in flight at the start of the round) bounds every queue
-  const int blocks = std::max(1, std::min((std::min(wv.nslots, max_items) + 127) / 128, 148 * 16));
+  const int blocks = std::max(1, std::min((std::min(wv.nslots, max_items) + 127) / 128, sm_count * 16));
   // Unused dynamic shared memory caps the resident blocks per SM of a stage (experiments on how much thread-private
   // context the L2 can hold: LGARB_WAVE_SMEM_<stage index>=bytes).
   static int smem[LGAR_NSTAGE] = {-1, -1, -1, -1, -1, -1};
@@ -956,7 +697,7 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
   switch (stage) {
     case LG_ST_FETCH:
       if (refill)
-        lgar_wave_fetch_kernel<<<std::min(blocks, 148 * fetch_refill), 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask);
+        lgar_wave_fetch_kernel<<<std::min(blocks, sm_count * fetch_refill), 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask);
       else
         lgar_wave_kernel<LG_ST_FETCH><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum);
       break;
@@ -967,14 +708,6 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
     default: lgar_wave_kernel<LG_ST_TAIL><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
   }
   lgar_wave_reset_kernel<<<1, 1, 0, stream>>>(wv.qcount + stage * 2 + consume, refill ? wv.cursor : nullptr);
-  return cudaGetLastError();
-}
-
-cudaError_t lgar_launch_wave_search_warp(const LgarWave& wv, int consume, unsigned append_mask, int quantum, int max_items, cudaStream_t stream) {
-  const int64_t threads = (int64_t)std::min(wv.nslots, max_items) * 32;
-  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((threads + 127) / 128, 148 * 16));
-  lgar_wave_search_warp_kernel<<<blocks, 128, 0, stream>>>(wv, consume, append_mask, quantum);
-  lgar_wave_reset_kernel<<<1, 1, 0, stream>>>(wv.qcount + LG_ST_SEARCH * 2 + consume, nullptr);
   return cudaGetLastError();
 }
 
@@ -999,6 +732,16 @@ __global__ void __launch_bounds__(256) lgar_dfma_kernel(double* sink, int iters)
 }
 cudaError_t lgar_launch_dfma(double* sink, int blocks, int iters, cudaStream_t stream) {
   lgar_dfma_kernel<<<blocks, 256, 0, stream>>>(sink, iters);
+  return cudaGetLastError();
+}
+
+// x^y as the physics evaluates it, element by element (lgarb_debug_pow: compared with the host's pow by the tests)
+__global__ void lgar_debug_pow_kernel(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out, int64_t n, int which) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = which ? lg_pow_hot(x[i], y[i]) : lg_pow(x[i], y[i]);
+}
+cudaError_t lgar_launch_debug_pow(const double* x, const double* y, double* out, int64_t n, int which, cudaStream_t stream) {
+  lgar_debug_pow_kernel<<<1184, 256, 0, stream>>>(x, y, out, n, which);
   return cudaGetLastError();
 }
 

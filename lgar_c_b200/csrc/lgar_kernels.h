@@ -54,23 +54,18 @@ struct LgarWave {
 };
 
 #ifndef LGAR_HOSTSIM
-// one launch of the kernel of `stage`, consuming queue[stage][consume]; append_mask bit s = buffer of stage s to append to
+// one launch of the kernel of `stage`, consuming queue[stage][consume]; append_mask bit s = buffer of stage s to append to;
+// sm_count: multiprocessors of the device (grids are sized in multiples of it)
 cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int stage, int consume,
-                                   unsigned append_mask, int quantum, int max_items, cudaStream_t stream);
-// mode 4: one launch of the step kernel, consuming queue[s][(consume_mask >> s) & 1] for s = HEAD, FRONT, TAIL
-cudaError_t lgar_launch_wave_run(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, unsigned consume_mask,
-                                 unsigned append_mask, int quantum, int corr_quantum, int keep, int max_items, cudaStream_t stream);
+                                   unsigned append_mask, int quantum, int max_items, int sm_count, cudaStream_t stream);
+// mode 5: one launch of the STEP kernel (whole active steps), consuming queue[HEAD][consume] and appending to the FETCH queue
+cudaError_t lgar_launch_wave_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int consume, unsigned append_mask,
+                                  int max_items, int sm_count, cudaStream_t stream);
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
-                                    int lane_stride, cudaStream_t stream);
-// the same with the lane records in shared memory (lgar_finish_smem.cu); lane_stride is rounded up to a power of two in [2, 32];
-// lane_stride <= 0: converged variant (one warp per block, every lane a record, lanes refill), -lane_stride = search trips per turn
-cudaError_t lgar_launch_wave_finish_smem(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
-                                         int lane_stride, cudaStream_t stream);
+                                    int lane_stride, int sm_count, cudaStream_t stream);
 cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWave& wv, int slot_is_column, cudaStream_t stream);
 // the 12 queue counts into pinned host memory (device-visible under unified addressing), no copy engine involved
 cudaError_t lgar_launch_wave_poll(const LgarWave& wv, int32_t* host_counts, cudaStream_t stream);
-// SEARCH with one warp per slot (short queues): same queue protocol as lgar_launch_wave_stage(LG_ST_SEARCH)
-cudaError_t lgar_launch_wave_search_warp(const LgarWave& wv, int consume, unsigned append_mask, int quantum, int max_items, cudaStream_t stream);
 size_t lgar_lane_context_bytes();
 // mode 1: warp-tile window kernel; mode 2: per-lane staged program (lgar_lanes.cuh)
 cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream, int mode);
@@ -88,6 +83,8 @@ cudaError_t lgar_launch_gather_layers(const LgarDeviceState& d, double* dst, int
 int lgar_active_kernel_max_blocks_per_sm();
 // DFMA microbenchmark: `iters` trips of 8 independent FMA chains per thread on blocks x 256 threads; sink keeps the result alive
 cudaError_t lgar_launch_dfma(double* sink, int blocks, int iters, cudaStream_t stream);
+// out[i] = x[i]^y[i] with the physics' pow (which = 0: out-of-line function, 1: inlined common case + fall-back)
+cudaError_t lgar_launch_debug_pow(const double* x, const double* y, double* out, int64_t n, int which, cudaStream_t stream);
 #endif
 
 #endif

@@ -25,21 +25,6 @@
 #include "lgar_step.cuh"
 
 
-struct LgSearch {  // one psi search in flight
-  double psi_loc, factor, psi_prev, delta_mass, delta_mass_prev, new_mass, prior_mass, precip_mass_to_add, theta;
-  double dth[LGAR_MAXL + 1], dz[LGAR_MAXL + 1];
-  int layer_num, iter, count_no_mass_change;
-  bool switched, wanted_to_saturate, aug, aug_extreme, done;
-};
-
-// one correction search in flight (lgar_theta_mass_balance_correction, lgar.cxx:3262-3435): it works on the
-// live front list, so the CORR stage carries the fronts with it
-struct LgCorr {
-  double psi_loc, factor, psi_prev, delta_mass, delta_mass_prev, new_mass, prior_mass;
-  int cur, iter, count_no_mass_change;
-  bool switched, aug, aug_extreme, done;
-};
-
 // The lane record.  Its head is the column's STATE (scalars, GIUH queue, cumulative volumes, front list): it is
 // imported from the SoA arrays when the lane takes the column and exported when the column has finished its
 // window (lg_lane_import/export), so between those two points no stage touches the SoA state -- the wavefront
@@ -96,102 +81,13 @@ LG_FN_NOINLINE void lg_lane_export(const LgarConfig& cfg, const LgarDeviceState&
 // returns true when the search has to iterate (otherwise q.theta is final)
 LG_FN bool lg_search_init(LgLane& L, int layer_num, double psi_cm, double new_mass, double prior_mass) {
   LgSearch& q = L.q;
-  q.layer_num = layer_num;
-  q.psi_loc = psi_cm;
-  q.new_mass = new_mass;
-  q.prior_mass = prior_mass;
-  q.precip_mass_to_add = L.precip_mass_to_add;
-  q.delta_mass = fabs(new_mass - prior_mass);
-  q.factor = fmax(1.0, psi_cm / 10.0);
-  if (psi_cm > 1.E4) q.factor = psi_cm;
-  q.switched = false;
-  q.theta = 0;
-  q.psi_prev = psi_cm;
-  q.delta_mass_prev = q.delta_mass;
-  q.count_no_mass_change = 0;
-  q.wanted_to_saturate = false;
-  q.iter = 0;
-  q.aug = false;
-  q.aug_extreme = false;
-  q.done = false;
+  lg_search_setup(q, layer_num, psi_cm, new_mass, prior_mass, L.precip_mass_to_add);
   if (q.delta_mass <= LG_MBAL_TOL) {
     q.theta = lg_theta_from_h(psi_cm, L.cls->lay[layer_num]);
     q.done = true;
     return false;
   }
   return true;
-}
-
-// One trip of the while loop (lgar.cxx:2990-3090) in three parts, so that the warp-cooperative search below executes
-// exactly the arithmetic of the per-thread one:
-//   pre : the psi / step-size recurrence.  It needs the outcome of the previous trip only as one bit (`up`: the mass found
-//         was larger than the prior mass), everything else is a function of the trip count and of psi itself
-//   eval: theta(psi) of the layers above and the mass they hold -- the expensive part (exp/log per layer)
-//   post: the seven exit conditions
-LG_FN void lg_search_pre(LgSearch& q, bool up) {
-  const int first_thresh = LG_MAX_ITER_MBAL / 100, second_thresh = LG_MAX_ITER_MBAL / 10;
-  q.iter++;
-  if (q.iter > first_thresh && !q.aug) {
-    q.factor = q.factor * 100;
-    q.aug = true;
-  }
-  if (q.iter > second_thresh && !q.aug_extreme) {
-    q.factor = q.factor * 100;
-    q.aug_extreme = true;
-  }
-  if (up) {
-    q.psi_loc += 0.1 * q.factor;
-    q.switched = false;
-  } else {
-    if (!q.switched) {
-      q.switched = true;
-      q.factor = q.factor * 0.1;
-    }
-    q.psi_prev = q.psi_loc;
-    q.psi_loc -= 0.1 * q.factor;
-    if (q.psi_loc < 0.0) q.wanted_to_saturate = true;
-    if (q.psi_loc < 0 && q.psi_prev != 0) q.psi_loc = q.psi_prev * 0.1;
-  }
-  if (q.psi_loc < 0.0) {
-    q.psi_loc = 0.0;
-    q.factor = q.factor * 0.5;
-  }
-}
-LG_FN void lg_search_eval(LgSearch& q, const LgarColumnClass& cls) {
-  const int layer_num = q.layer_num;
-  const double lnpsi = lg_lnh(q.psi_loc);
-  q.theta = lg_theta_from_lnh(lnpsi, cls.lay[layer_num]);
-  double mass_layers = 0.0;
-  mass_layers += q.dz[layer_num] * (q.theta - q.dth[layer_num]);
-  for (int k = 1; k < layer_num; k++) {
-    double theta_layer = lg_theta_from_lnh(lnpsi, cls.lay[k]);
-    mass_layers += q.dz[k] * (theta_layer - q.dth[k]);
-  }
-  q.new_mass = mass_layers;
-  q.delta_mass = fabs(q.new_mass - q.prior_mass);
-}
-LG_FN void lg_search_post(LgSearch& q) {
-  const int first_thresh = LG_MAX_ITER_MBAL / 100;
-  bool brk = false;
-  if (fabs(q.psi_loc - q.psi_prev) < 1E-15 && q.factor < 1E-13) brk = true;
-  if (!brk) {
-    if (fabs(q.delta_mass - q.delta_mass_prev) < 1E-15)
-      q.count_no_mass_change++;
-    else
-      q.count_no_mass_change = 0;
-    if (q.count_no_mass_change == 5 && q.precip_mass_to_add < 1.E-12) brk = true;
-    else if (q.iter > LG_MAX_ITER_MBAL) brk = true;
-    else if ((q.psi_loc > LG_PSI_UPPER_LIM) && (q.iter > first_thresh)) brk = true;
-    else if (q.psi_loc <= 0 && q.psi_prev < 0) brk = true;
-  }
-  if (!brk) q.delta_mass_prev = q.delta_mass;
-  if (brk || !(q.delta_mass > LG_MBAL_TOL)) q.done = true;
-}
-// one trip; sets q.done when the loop would exit
-LG_FN void lg_search_iter(LgSearch& q, const LgarColumnClass& cls) {
-  lg_search_pre(q, q.new_mass > q.prior_mass);
-  lg_search_eval(q, cls);
-  lg_search_post(q);
 }
 
 #ifndef LGAR_HOSTSIM
@@ -541,6 +437,7 @@ LG_FN_NOINLINE bool lg_corr_init(LgLane& L, int front_num, double prior_mass) {
   k.count_no_mass_change = 0;
   k.aug = false;
   k.aug_extreme = false;
+  k.no_ff = false;
   k.done = !(k.delta_mass > LG_MBAL_TOL);
   return !k.done;
 }
@@ -973,6 +870,27 @@ LG_FN_NOINLINE void lg_stage_tail(const LgarConfig& cfg, const LgarDeviceState& 
   if (front_sum) *front_sum += (unsigned)L.f.n;
   L.t = t + 1;
   L.stage = LG_ST_FETCH;
+}
+
+// STEP: a whole active step in one go -- HEAD, the front loop with its psi searches run where they arise (lg_search_run: ~10
+// evaluations each since the fast path of lgar_search.cuh, so there is nothing left to park), TAIL with its correction searches.
+// Ends in FETCH.  The step context never leaves the thread.
+LG_FN_NOINLINE void lg_stage_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, LgLane& L, unsigned long long* front_sum) {
+  lg_stage_head(cfg, d, w, L, front_sum);
+  while (L.stage != LG_ST_FETCH) {
+    if (L.stage == LG_ST_FRONT) {
+      while (lg_move_fronts(L)) {
+        lg_search_run(L.q, *L.cls);
+        L.resume = true;
+      }
+      L.stage = LG_ST_TAIL;
+    } else if (L.stage == LG_ST_TAIL) {
+      lg_stage_tail(cfg, d, w, L, front_sum);
+    } else {
+      while (!L.k.done) lg_corr_iter(L.k, L.f, *L.cls);
+      L.stage = LG_ST_TAIL;
+    }
+  }
 }
 
 // FETCH: walk the resident column through the hours that need no flux computation; when it has finished the

@@ -228,6 +228,8 @@ LG_FN_NOINLINE double lg_Geff(const LgarConfig& cfg, double theta1, double theta
   }
 }
 
+#include "lgar_search.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // L0: list behaviour on fixed slots, reference src/linked_list.cxx
 // ------------------------------------------------------------------------------------------------
@@ -344,74 +346,17 @@ LG_FN_NOINLINE double lg_theta_mass_balance(LgCtx& c, int layer_num, double psi_
                                             const double* dz) {
   const LgarColumnClass& cls = *c.cls;
   const LgarLayer& sp = cls.lay[layer_num];
-  double psi_loc = psi_cm;
-  double delta_mass = fabs(new_mass - prior_mass);
-  double factor = fmax(1.0, psi_cm / 10.0);
-  if (psi_cm > 1.E4) factor = psi_cm;
-  bool switched = false;
-  double theta = 0;
-  double psi_prev = psi_loc;
-  double delta_mass_prev = delta_mass;
-  int count_no_mass_change = 0;
-  bool wanted_to_saturate = false;
-  int iter = 0;
-  bool aug = false, aug_extreme = false;
-  const int first_thresh = LG_MAX_ITER_MBAL / 100, second_thresh = LG_MAX_ITER_MBAL / 10;
-
-  if (delta_mass <= LG_MBAL_TOL) return lg_theta_from_h(psi_loc, sp);
-
-  while (delta_mass > LG_MBAL_TOL) {
-    iter++;
-    if (iter > first_thresh && !aug) {
-      factor = factor * 100;
-      aug = true;
-    }
-    if (iter > second_thresh && !aug_extreme) {
-      factor = factor * 100;
-      aug_extreme = true;
-    }
-    if (new_mass > prior_mass) {
-      psi_loc += 0.1 * factor;
-      switched = false;
-    } else {
-      if (!switched) {
-        switched = true;
-        factor = factor * 0.1;
-      }
-      psi_prev = psi_loc;
-      psi_loc -= 0.1 * factor;
-      if (psi_loc < 0.0) wanted_to_saturate = true;
-      if (psi_loc < 0 && psi_prev != 0) psi_loc = psi_prev * 0.1;
-    }
-    if (psi_loc < 0.0) {
-      psi_loc = 0.0;
-      factor = factor * 0.5;
-    }
-    const double lnpsi = lg_lnh(psi_loc);
-    theta = lg_theta_from_lnh(lnpsi, sp);
-    double mass_layers = 0.0;
-    mass_layers += dz[layer_num] * (theta - dth[layer_num]);
-    for (int k = 1; k < layer_num; k++) {
-      double theta_layer = lg_theta_from_lnh(lnpsi, cls.lay[k]);
-      mass_layers += dz[k] * (theta_layer - dth[k]);
-    }
-    new_mass = mass_layers;
-    delta_mass = fabs(new_mass - prior_mass);
-
-    if (fabs(psi_loc - psi_prev) < 1E-15 && factor < 1E-13) break;
-    if (fabs(delta_mass - delta_mass_prev) < 1E-15)
-      count_no_mass_change++;
-    else
-      count_no_mass_change = 0;
-    if (count_no_mass_change == 5 && precip_mass_to_add < 1.E-12) break;
-    if (iter > LG_MAX_ITER_MBAL) break;
-    if ((psi_loc > LG_PSI_UPPER_LIM) && (iter > first_thresh)) break;
-    if (psi_loc <= 0 && psi_prev < 0) break;
-    delta_mass_prev = delta_mass;
+  LgSearch q;
+  lg_search_setup(q, layer_num, psi_cm, new_mass, prior_mass, precip_mass_to_add);
+  for (int k = 1; k <= layer_num; k++) {
+    q.dth[k] = dth[k];
+    q.dz[k] = dz[k];
   }
-  if ((delta_mass > LG_MBAL_TOL) && (!wanted_to_saturate)) *AET_demand_cm = *AET_demand_cm - fabs(delta_mass - LG_MBAL_TOL);
-  if ((theta >= sp.theta_e) && (psi_loc != 0.0)) *AET_demand_cm = 0.0;
-  return theta;
+  if (q.delta_mass <= LG_MBAL_TOL) return lg_theta_from_h(psi_cm, sp);
+  lg_search_run(q, cls);
+  if ((q.delta_mass > LG_MBAL_TOL) && (!q.wanted_to_saturate)) *AET_demand_cm = *AET_demand_cm - fabs(q.delta_mass - LG_MBAL_TOL);
+  if ((q.theta >= sp.theta_e) && (q.psi_loc != 0.0)) *AET_demand_cm = 0.0;
+  return q.theta;
 }
 
 // lgar_theta_mass_balance_correction, lgar.cxx:3262-3435 (front_num 1-based)

@@ -1,0 +1,458 @@
+// lgar_c_b200/csrc/lgar_search.cuh -- the two psi searches of the reference, and how the engine gets through them fast.
+//
+// lgar_theta_mass_balance (reference src/lgar.cxx:2952-3112) and lgar_theta_mass_balance_correction (:3262-3435) look for the
+// capillary head psi at which the water held by a set of fronts equals a prior mass, by a decimal DIGIT search: psi moves in
+// steps of 0.1*factor, the step shrinks by 10 whenever the search turns from "too wet" to "too dry", and it stops when the mass
+// is within 1e-10 cm (or on one of six other conditions).  The result is whatever psi the walk stops at, so it is defined by the
+// walk itself and has to be reproduced trip for trip.  On the bench workload EVERY iterated search takes
+// 32-128 trips (mean 85, tail to 10^4; tools/search_trip_histogram.py) and 90 % of all theta(psi) evaluations of a run -- i.e.
+// of all pow calls -- happen inside these trips.
+//
+// A trip consists of a cheap recurrence (the new psi and step: a dozen operations, needs from the previous trip only ONE BIT,
+// "the mass found was larger than the prior mass") and an expensive evaluation (two pow per soil layer).  The mass is a
+// decreasing function of psi, so that bit is known without evaluating anything whenever psi is outside a small bracket [a, b]
+// around the root.  lg_digit_ff therefore
+//   1. finds the root by a safeguarded Newton iteration (the slope comes out of the same two pow values as theta),
+//   2. evaluates the mass at a = root - 1.3 w and b = root + 1.3 w (w = tolerance / slope) WITH THE TRIP'S OWN ARITHMETIC and
+//      checks that it is above prior + tolerance + margin at a and below prior - tolerance - margin at b,
+//   3. replays the walk: every trip runs the recurrence exactly; a trip whose psi lies at or below a (at or above b) is known to
+//      find "too wet" ("too dry") and a mass error above the tolerance, so its evaluation is skipped; a trip inside (a, b), or one
+//      that meets one of the psi-only exit conditions, is evaluated exactly as the reference does.  The walk ends on an exactly
+//      evaluated trip, so theta, psi, the mass error and the trip count are those of the reference bit for bit.
+// ~12 evaluations instead of 85, and no heavy tail: a 10^4-trip search costs 10^4 cheap recurrences.
+//
+// What makes a skipped trip safe:
+//   * the computed mass is monotone in psi up to the rounding of two pow and a few products per layer: <= 5e-16 in theta, times
+//     the layer thickness (<= 200 cm), three layers: 3e-13 cm.  The bracket test carries a margin of 2e-12 (LG_FF_MARGIN).
+//   * the "mass did not change for five trips" exit (count_no_mass_change == 5) looks at |delta_k - delta_{k-1}| < 1e-15.  For two
+//     consecutive trips on the same side of the root inside a zone Z where |d mass / d psi| >= g, the change is at least
+//     g |psi_k - psi_{k-1}|; if that is >= 1e-12 (LG_FF_NOSTALL) the test is false for certain.  g is a rigorous lower bound:
+//     each layer's |d theta / d psi| is unimodal in psi, so its minimum over Z is at an end of Z.  Where that argument does not
+//     apply (opposite sides, outside Z, step too small) the counter is carried as an INTERVAL [clo, chi]; if the interval ever
+//     straddles 5 while the exit is armed, the search is restarted from its saved state and walked the plain way.
+//   * every other exit condition depends on psi, the step and the trip count only and is evaluated exactly on every trip.
+// Whenever anything is not certain -- no root in (0, inf), slope 0, bracket test fails, dz < 0, n <= 1 -- the fast path declines
+// and the plain walk runs.  tests/test_hostsim.py runs both on every search of every golden case and compares the final records
+// bit for bit (-DLGAR_FF_VERIFY); tools/bitexact_sample.py does the same against the unmodified reference over full years.
+#ifndef LGAR_SEARCH_CUH
+#define LGAR_SEARCH_CUH
+
+#ifdef LGAR_HOSTSIM
+#define LG_MFN inline
+#define LG_MFN_NOINLINE inline
+#else
+#define LG_MFN __device__ __forceinline__
+#define LG_MFN_NOINLINE __device__ __noinline__
+#endif
+
+struct LgSearch {  // one psi search in flight (lgar_theta_mass_balance)
+  double psi_loc, factor, psi_prev, delta_mass, delta_mass_prev, new_mass, prior_mass, precip_mass_to_add, theta;
+  double dth[LGAR_MAXL + 1], dz[LGAR_MAXL + 1];
+  int layer_num, iter, count_no_mass_change;
+  bool switched, wanted_to_saturate, aug, aug_extreme, done, no_ff;
+};
+
+// one correction search in flight (lgar_theta_mass_balance_correction, lgar.cxx:3262-3435): it works on the
+// live front list, so the CORR stage carries the fronts with it
+struct LgCorr {
+  double psi_loc, factor, psi_prev, delta_mass, delta_mass_prev, new_mass, prior_mass;
+  int cur, iter, count_no_mass_change;
+  bool switched, aug, aug_extreme, done, no_ff;
+};
+
+#ifdef LGAR_FF_STATS   // host-side instrumentation (tests/hostsim): how the searches went
+struct LgFfStats { long long searches, ff_done, declined, fallback, evals_ff, evals_plain, trips, verify_bad; };
+static LgFfStats lg_ff_stats;
+#define LG_FF_COUNT(field, n) (lg_ff_stats.field += (n))
+#else
+#define LG_FF_COUNT(field, n) ((void)0)
+#endif
+
+LG_FN void lg_q_note_negative(LgSearch& q) { q.wanted_to_saturate = true; }
+LG_FN void lg_q_note_negative(LgCorr&) {}
+
+// The psi / step-size recurrence of one trip (lgar.cxx:2990-3033, :3311-3338).  It needs the outcome of the previous trip only
+// as one bit (`up`: the mass found was larger than the prior mass).
+template <class Q>
+LG_FN void lg_digit_pre(Q& q, bool up) {
+  const int first_thresh = LG_MAX_ITER_MBAL / 100, second_thresh = LG_MAX_ITER_MBAL / 10;
+  q.iter++;
+  if (q.iter > first_thresh && !q.aug) {
+    q.factor = q.factor * 100;
+    q.aug = true;
+  }
+  if (q.iter > second_thresh && !q.aug_extreme) {
+    q.factor = q.factor * 100;
+    q.aug_extreme = true;
+  }
+  if (up) {
+    q.psi_loc += 0.1 * q.factor;
+    q.switched = false;
+  } else {
+    if (!q.switched) {
+      q.switched = true;
+      q.factor = q.factor * 0.1;
+    }
+    q.psi_prev = q.psi_loc;
+    q.psi_loc -= 0.1 * q.factor;
+    if (q.psi_loc < 0.0) lg_q_note_negative(q);
+    if (q.psi_loc < 0 && q.psi_prev != 0) q.psi_loc = q.psi_prev * 0.1;
+  }
+  if (q.psi_loc < 0.0) {
+    q.psi_loc = 0.0;
+    q.factor = q.factor * 0.5;
+  }
+}
+
+// the exit conditions that do not look at the mass (lgar.cxx:3063,3078-3086)
+template <class Q>
+LG_FN bool lg_digit_brk_first(const Q& q) { return fabs(q.psi_loc - q.psi_prev) < 1E-15 && q.factor < 1E-13; }
+template <class Q>
+LG_FN bool lg_digit_brk_other(const Q& q) {
+  const int first_thresh = LG_MAX_ITER_MBAL / 100;
+  return (q.iter > LG_MAX_ITER_MBAL) || ((q.psi_loc > LG_PSI_UPPER_LIM) && (q.iter > first_thresh)) || (q.psi_loc <= 0 && q.psi_prev < 0);
+}
+
+// the exits of one trip after its evaluation; `gate`: the five-trips-without-change exit is armed
+template <class Q>
+LG_FN void lg_digit_post(Q& q, bool gate) {
+  bool brk = lg_digit_brk_first(q);
+  if (!brk) {
+    if (fabs(q.delta_mass - q.delta_mass_prev) < 1E-15)
+      q.count_no_mass_change++;
+    else
+      q.count_no_mass_change = 0;
+    if (q.count_no_mass_change == 5 && gate) brk = true;
+    else brk = lg_digit_brk_other(q);
+  }
+  if (!brk) q.delta_mass_prev = q.delta_mass;
+  if (brk || !(q.delta_mass > LG_MBAL_TOL)) q.done = true;
+}
+
+#if !defined(LGAR_FAST_POW)
+// theta(h) exactly as lg_theta_from_lnh computes it, and |d theta / d h| from the same two pow values (an estimate: it steers
+// the root finder and bounds mass changes from below with a factor 2 in hand, it never enters a result)
+LG_FN double lg_theta_and_slope(double h, const LgarLayer& s, double* slope, bool* past_mode) {
+  const double t = lg_pow_hot(s.alpha * h, s.n);
+  *past_mode = t > s.m;   // |d theta / d h| is unimodal in h with its maximum where (alpha h)^n = m
+  const double onep = 1.0 + t;
+  const double inv = 1.0 / (lg_pow_hot(onep, s.m));
+  double sl = (h > 0.0) ? s.de * s.m * s.n * t * inv / (h * onep) : 0.0;
+  if (!(sl >= 0.0) || sl > 1e300) sl = 0.0;
+  *slope = sl;
+  return inv * s.de + s.theta_r;
+}
+
+// Two trips on opposite sides of the root: are their mass errors certainly more than 1e-15 apart?  The root lies in (a, b), so a
+// psi at distance d from [a, b] has an error between g d and G (d + b - a) (slope bounds over the zone).
+LG_FN bool lg_ff_apart(double x, double y, double a, double b, double g, double G) {
+  const double dx = (x <= a) ? a - x : (x >= b ? x - b : 0.0), dy = (y <= a) ? a - y : (y >= b ? y - b : 0.0);
+  const double wd = b - a;
+  return (g * dx > G * (dy + wd) + 1.0e-12) || (g * dy > G * (dx + wd) + 1.0e-12);
+}
+
+#define LG_FF_MARGIN 2.0e-12
+#define LG_FF_NOSTALL 1.0e-12
+#define LG_FF_MAX_NEWTON 16
+
+// Ev: the mass model of a search.
+//   double mass(double psi, double* sl, unsigned* past)   the mass a trip at psi computes (bit for bit), sl[k] = |d mass/d psi| of
+//                                         term k, bit k of *past: term k is beyond the maximum of its |slope|
+//   double term_slope_max(int k)          upper bound of sl[k] over all psi
+//   int    terms()                        number of terms of sl
+//   void   trip(Q& q)                     the evaluation of a trip at q.psi_loc: q.new_mass, q.delta_mass (and what else it sets)
+//   bool   monotone()                     the model is one this fast path may be used on
+// Returns true when the search is finished (q.done, final record as the plain walk leaves it), false when the fast path
+// declined: q is then untouched except q.no_ff.
+template <class Q, class Ev>
+LG_FN bool lg_digit_ff(Q& q, Ev& ev, const bool gate) {
+  const Q q0 = q;
+  const double prior = q.prior_mass;
+  const double TOL = LG_MBAL_TOL;
+  q.no_ff = true;
+  if (!ev.monotone()) return false;
+  const int nt = ev.terms();
+  double sl[Ev::kMaxTerms], slz[2][Ev::kMaxTerms];
+  // ---- 1. root of f(psi) = mass(psi) - prior ----
+  const double x0 = q.psi_loc;
+  if (!(x0 > 0.0) || !(x0 < 1e300)) return false;
+  double lo = -1.0, hi = -1.0;  // f(lo) > 0 > f(hi); -1: not known yet
+  unsigned pasta = 0, pastb = 0;
+  double x = x0, root = 0.0, sroot = 0.0;
+  bool found = false;
+  int evals = 0;
+  for (int it = 0; it < LG_FF_MAX_NEWTON; it++) {
+    double* sp = sl;
+    unsigned pm;
+    const double fx = ev.mass(x, sp, &pm) - prior;
+    evals++;
+    double sx = 0.0;
+    for (int k = 0; k < nt; k++) sx += sp[k];
+    if (!(fx == fx)) break;
+    if (fabs(fx) <= 0.25 * TOL) {
+      root = x;
+      sroot = sx;
+      found = true;
+      break;
+    }
+    if (fx > 0.0) lo = x; else hi = x;
+    double xn = (sx > 0.0) ? x + fx / sx : (fx > 0.0 ? 2.0 * x : 0.5 * x);
+    if (!(xn == xn)) break;
+    if (xn > 4.0 * x) xn = 4.0 * x;
+    if (xn < 0.25 * x) xn = 0.25 * x;
+    if (lo > 0.0 && hi > 0.0) {
+      if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+      if (!(xn > lo && xn < hi)) break;  // the bracket has closed to neighbouring doubles without meeting the tolerance
+    }
+    if (xn < 1e-300 || xn > 1e300) break;
+    x = xn;
+  }
+  if (!found || !(sroot > 0.0)) {
+    LG_FF_COUNT(declined, 1);
+    LG_FF_COUNT(evals_ff, evals);
+    q = q0;
+    q.no_ff = true;
+    return false;
+  }
+  // ---- 2. the bracket: mass error above the tolerance (with margin) at a, below minus the tolerance at b ----
+  const double w = TOL / sroot;
+  double a = 0.0, b = 0.0, sla[Ev::kMaxTerms], slb[Ev::kMaxTerms];
+  bool ok = false;
+  for (int tr = 0, mul = 1; tr < 3 && !ok; tr++, mul *= 2) {
+    a = root - 1.3 * mul * w;
+    b = root + 1.3 * mul * w;
+    if (!(a > 0.0) || !(a < root) || !(b > root)) break;
+    const double fa = ev.mass(a, sla, &pasta) - prior;
+    const double fb = ev.mass(b, slb, &pastb) - prior;
+    evals += 2;
+    ok = (fa >= TOL + LG_FF_MARGIN) && (fb <= -(TOL + LG_FF_MARGIN));
+  }
+  if (!ok) {
+    LG_FF_COUNT(declined, 1);
+    LG_FF_COUNT(evals_ff, evals);
+    q = q0;
+    q.no_ff = true;
+    return false;
+  }
+  // ---- 3. the walk ----
+  // Zone Z = [zlo, zhi] with slope bounds g <= |d mass / d psi| <= G on it; only the armed no-change exit needs it.  It is laid
+  // round a pair of trips when that pair has to be told apart (2 evaluations), and kept while the walk stays inside it -- after
+  // the first turn of the search every later trip lies within one step of the root, so one or two zones serve a whole search.
+  double zlo = 0.0, zhi = -1.0, g = 0.0, G = 0.0;
+  int zones = 0;
+  int clo = q.count_no_mass_change, chi = q.count_no_mass_change;
+  // The record the walk starts from carries a mass the CALLER computed (from stored thetas, possibly clamped), not mass(x0):
+  // the first pair of trips is never certified (prev_psi = NaN fails every comparison).
+  double prev_psi = lgp_double(0x7ff8000000000000ULL);
+  int prev_side = (q.new_mass > prior) ? 1 : -1;
+  bool prev_exact = true;  // q.delta_mass_prev is the exact value of the state the walk starts from
+  for (;;) {
+    lg_digit_pre(q, q.new_mass > prior);
+    LG_FF_COUNT(trips, 1);
+    const double psi = q.psi_loc;
+    const int side = (psi <= a) ? 1 : (psi >= b) ? -1 : 0;
+    const bool psi_exit = lg_digit_brk_first(q) || lg_digit_brk_other(q);
+    const bool skip = side != 0 && !psi_exit;
+    int cur_side = side;
+    if (!skip) {
+      ev.trip(q);
+      evals++;
+      cur_side = (q.new_mass > prior) ? 1 : -1;
+    }
+    const bool first = !skip && lg_digit_brk_first(q);
+    bool brk = first;
+    if (gate && !first) {
+      // the no-change counter after this trip
+      if (!skip && prev_exact) {
+        if (fabs(q.delta_mass - q.delta_mass_prev) < 1E-15) {
+          clo++;
+          chi++;
+        } else {
+          clo = chi = 0;
+        }
+      } else {
+        // at least one of the two mass errors is not known: can they be within 1e-15 of each other?  Not if both trips lie in a
+        // zone with slope bounds and are far enough apart (same side), or at clearly different distances from the root
+        // (opposite sides).  Both errors are above the tolerance here (a skipped trip by the bracket, an exact one because the
+        // search goes on), so on the same side |delta_k - delta_{k-1}| is the change of the mass itself.
+        bool apart = false;
+        if (prev_psi == prev_psi && (skip || q.delta_mass > TOL)) {
+          for (int pass = 0; pass < 2 && !apart; pass++) {
+            const bool inz = psi >= zlo && psi <= zhi && prev_psi >= zlo && prev_psi <= zhi;
+            if (inz) apart = (cur_side == prev_side) ? (g * fabs(psi - prev_psi) >= LG_FF_NOSTALL) : lg_ff_apart(psi, prev_psi, a, b, g, G);
+            if (apart || pass == 1 || zones >= 8) break;
+            if (inz && !(G > 1.5 * g)) break;  // the bounds are as tight as they get: this pair simply is not told apart
+            // lay a new zone round this pair and the bracket, with room for one more step in the direction of the walk
+            const double step = fabs(psi - prev_psi);
+            const double pad_lo = (psi < prev_psi ? 1.01 : 0.11) * step, pad_hi = (psi > prev_psi ? 1.01 : 0.11) * step;
+            double nlo = fmin(fmin(psi, prev_psi), a) - pad_lo, nhi = fmax(fmax(psi, prev_psi), b) + pad_hi;
+            if (!(nlo > 0.5 * fmin(fmin(psi, prev_psi), a))) nlo = 0.5 * fmin(fmin(psi, prev_psi), a);
+            if (!(nlo > 0.0) || !(nhi < 1e300)) break;
+            unsigned p0 = 0, p1 = 0;
+            (void)ev.mass(nlo, slz[0], &p0);
+            (void)ev.mass(nhi, slz[1], &p1);
+            evals += 2;
+            zones++;
+            g = 0.0;
+            G = 0.0;
+            for (int k = 0; k < nt; k++) {
+              g += fmin(slz[0][k], slz[1][k]);
+              G += (((p0 ^ p1) >> k) & 1u) ? ev.term_slope_max(k) : fmax(slz[0][k], slz[1][k]);
+            }
+            g *= 0.9;
+            G *= 1.1;
+            zlo = nlo;
+            zhi = nhi;
+          }
+        }
+        if (apart) {
+          clo = chi = 0;
+        } else {
+          clo = 0;
+          chi++;
+#ifdef LGAR_FF_DEBUG
+          if (chi >= 5) fprintf(stderr, "ff fallback: iter %d psi %.17g prev %.17g a %.17g b %.17g zlo %g zhi %g g %g G %g side %d prev_side %d factor %g root %.17g w %g zones %d\n", q.iter, psi, prev_psi, a, b, zlo, zhi, g, G, cur_side, prev_side, q.factor, root, w, zones);
+#endif
+        }
+      }
+      if (!skip && clo == 5 && chi == 5) brk = true;
+      else if (clo <= 5 && chi >= 5) break;  // the no-change exit can neither be ruled out nor confirmed: walk the plain way
+    }
+    if (skip) {
+      q.new_mass = (side > 0) ? prior + 1.0 : prior - 1.0;  // only its order relative to the prior mass is read
+      prev_psi = psi;
+      prev_side = side;
+      prev_exact = false;
+      continue;
+    }
+    if (!brk) brk = !first && lg_digit_brk_other(q);
+    if (!brk) q.delta_mass_prev = q.delta_mass;
+    if (brk || !(q.delta_mass > TOL)) {
+      q.done = true;
+      q.count_no_mass_change = clo;
+      LG_FF_COUNT(ff_done, 1);
+      LG_FF_COUNT(evals_ff, evals);
+      return true;
+    }
+    prev_psi = psi;
+    prev_side = cur_side;
+    prev_exact = true;
+  }
+  LG_FF_COUNT(fallback, 1);
+  LG_FF_COUNT(evals_ff, evals);
+  q = q0;
+  q.no_ff = true;
+  return false;
+}
+#endif  // !LGAR_FAST_POW
+
+// ---- lgar_theta_mass_balance: the mass of the layers above and of the front's own layer at one psi ----------------------
+LG_FN void lg_search_eval(LgSearch& q, const LgarColumnClass& cls) {
+  const int layer_num = q.layer_num;
+  const double lnpsi = lg_lnh(q.psi_loc);
+  q.theta = lg_theta_from_lnh(lnpsi, cls.lay[layer_num]);
+  double mass_layers = 0.0;
+  mass_layers += q.dz[layer_num] * (q.theta - q.dth[layer_num]);
+  for (int k = 1; k < layer_num; k++) {
+    double theta_layer = lg_theta_from_lnh(lnpsi, cls.lay[k]);
+    mass_layers += q.dz[k] * (theta_layer - q.dth[k]);
+  }
+  q.new_mass = mass_layers;
+  q.delta_mass = fabs(q.new_mass - q.prior_mass);
+}
+// the initial record of a search (lgar.cxx:2961-2983)
+LG_FN void lg_search_setup(LgSearch& q, int layer_num, double psi_cm, double new_mass, double prior_mass, double precip_mass_to_add) {
+  q.layer_num = layer_num;
+  q.psi_loc = psi_cm;
+  q.new_mass = new_mass;
+  q.prior_mass = prior_mass;
+  q.precip_mass_to_add = precip_mass_to_add;
+  q.delta_mass = fabs(new_mass - prior_mass);
+  q.factor = fmax(1.0, psi_cm / 10.0);
+  if (psi_cm > 1.E4) q.factor = psi_cm;
+  q.switched = false;
+  q.theta = 0;
+  q.psi_prev = psi_cm;
+  q.delta_mass_prev = q.delta_mass;
+  q.count_no_mass_change = 0;
+  q.wanted_to_saturate = false;
+  q.iter = 0;
+  q.aug = false;
+  q.aug_extreme = false;
+  q.done = false;
+  q.no_ff = false;
+}
+LG_FN void lg_search_pre(LgSearch& q, bool up) { lg_digit_pre(q, up); }
+LG_FN void lg_search_post(LgSearch& q) { lg_digit_post(q, q.precip_mass_to_add < 1.E-12); }
+// one trip; sets q.done when the loop would exit
+LG_FN void lg_search_iter(LgSearch& q, const LgarColumnClass& cls) {
+  lg_digit_pre(q, q.new_mass > q.prior_mass);
+  lg_search_eval(q, cls);
+  lg_search_post(q);
+  LG_FF_COUNT(evals_plain, 1);
+}
+
+#if !defined(LGAR_FAST_POW)
+struct LgSearchModel {
+  static constexpr int kMaxTerms = LGAR_MAXL + 1;
+  const LgSearch* q;
+  const LgarColumnClass* cls;
+  LG_MFN bool monotone() const {
+    for (int k = 1; k <= q->layer_num; k++)
+      if (!(q->dz[k] >= 0.0) || !(cls->lay[k].n > 1.0) || !(cls->lay[k].alpha > 0.0) || !(cls->lay[k].de > 0.0)) return false;
+    return true;
+  }
+  LG_MFN int terms() const { return q->layer_num; }
+  LG_MFN double term_slope_max(int k) const { const int l = k == 0 ? q->layer_num : k; return q->dz[l] * cls->lay[l].slope_max; }
+  LG_MFN_NOINLINE double mass(double psi, double* sl, unsigned* past) const {   // lg_search_eval at psi (out of line: six call sites)
+    const int layer_num = q->layer_num;
+    double s;
+    bool pm;
+    unsigned pb = 0;
+    const double theta = lg_theta_and_slope(psi, cls->lay[layer_num], &s, &pm);
+    pb |= pm ? 1u : 0u;
+    sl[0] = q->dz[layer_num] * s;
+    double mass_layers = 0.0;
+    mass_layers += q->dz[layer_num] * (theta - q->dth[layer_num]);
+    for (int k = 1; k < layer_num; k++) {
+      const double theta_layer = lg_theta_and_slope(psi, cls->lay[k], &s, &pm);
+      pb |= pm ? (1u << k) : 0u;
+      sl[k] = q->dz[k] * s;
+      mass_layers += q->dz[k] * (theta_layer - q->dth[k]);
+    }
+    *past = pb;
+    return mass_layers;
+  }
+  LG_MFN void trip(LgSearch& qq) const { lg_search_eval(qq, *cls); }
+};
+#endif
+
+// A freshly initialised search (lg_search_init returned true) through the fast path, then at most `quantum` plain trips of
+// whatever is left (nothing, unless the fast path declined).
+LG_FN void lg_search_some(LgSearch& q, const LgarColumnClass& cls, int quantum) {
+#if !defined(LGAR_FAST_POW) && !defined(LGAR_NO_FF)
+  if (!q.no_ff && q.iter == 0) {
+    LgSearchModel ev{&q, &cls};
+    if (lg_digit_ff(q, ev, q.precip_mass_to_add < 1.E-12)) return;
+  }
+#endif
+  for (int it = 0; it < quantum && !q.done; it++) lg_search_iter(q, cls);
+}
+
+// the whole search to q.done
+LG_FN_NOINLINE void lg_search_run(LgSearch& q, const LgarColumnClass& cls) {
+  LG_FF_COUNT(searches, 1);
+#ifdef LGAR_FF_VERIFY
+  LgSearch ref = q;
+  while (!ref.done) lg_search_iter(ref, cls);
+  const bool fresh = !q.no_ff && q.iter == 0;
+#endif
+  while (!q.done) lg_search_some(q, cls, 1 << 30);
+#ifdef LGAR_FF_VERIFY
+  if (fresh && !(lgp_bits(ref.psi_loc) == lgp_bits(q.psi_loc) && lgp_bits(ref.theta) == lgp_bits(q.theta) && lgp_bits(ref.delta_mass) == lgp_bits(q.delta_mass) &&
+                 lgp_bits(ref.new_mass) == lgp_bits(q.new_mass) && ref.iter == q.iter && ref.wanted_to_saturate == q.wanted_to_saturate))
+    LG_FF_COUNT(verify_bad, 1);
+#endif
+}
+
+#endif

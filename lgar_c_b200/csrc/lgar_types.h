@@ -75,7 +75,8 @@ struct LgarLayer {
   double theta_min;  // theta(PSI_UPPER_LIM = 1e7)             (lgar.cxx:3222)
   double thick;      // cum[k]-cum[k-1]
   double h_min;      // kept for completeness (unused on the path, soil_funcs.cxx:59-61)
-  double ln_alpha;   // log(alpha): (alpha*h)^n is evaluated as exp(n*(ln_alpha + log h)), log h shared by all layers
+  double ln_alpha;   // log(alpha): (alpha*h)^n is evaluated as exp(n*(ln_alpha + log h)) in the -DLGAR_FAST_POW build
+  double slope_max;  // max over h of |d theta / d h| (at (alpha h)^n = m); bounds mass changes in the fast path of the psi searches, never a result
 };
 
 struct LgarColumnClass {

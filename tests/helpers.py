@@ -13,18 +13,14 @@ GOLDEN = ROOT / "tests" / "golden"
 STANDARD = ["unittest", "synth_0", "synth_1", "synth_2", "Phillipsburg", "Phillipsburg_with_reservoir", "Bushland"]
 RANDOM = [f"rand_{i}" for i in range(12)]
 
-# parity bar (BASELINE.json north_star): <= 1e-9 relative per step, front counts exact.
+# Parity bar.  BASELINE.json's north_star asks for <= 1e-9 relative per step and exact front counts.  Since round 2 the engine's
+# pow returns the host library's double (lgar_c_b200/csrc/lgar_pow.cuh) and nothing else on the path is rounded differently on
+# the device (IEEE division and square root, no FMA contraction), so the tests ask for MORE than the bar: every per-step scalar,
+# every front field and every cumulative volume must equal the reference's BIT FOR BIT (NaN == NaN).  Round 1's floors
+# (2e-12 m on AET / percolation, 1e-7 on psi and K, 1e-6 on dZ/dt) are gone.  RTOL stays for the comparisons with quantities that
+# are not outputs of the reference (HYDRUS / LGAR-Py physics bars, printed totals).
 RTOL = 1e-9
-ATOL_M = 1e-14        # metres; floor for quantities that are exactly or nearly zero
-MBAL_ATOL_M = 1e-11   # the local mass-balance residual is ~1e-12 cm noise: compared absolutely
-# The reference's psi searches accept any psi whose mass error is <= MBAL_ITERATIVE_TOLERANCE = 1e-10 cm
-# (src/lgar.cxx:64,2990) and book what is left of it into AET (:3096-3108) or the bottom flux (:1746-1751).
-# Those two fluxes are therefore only DEFINED to 1e-10 cm = 1e-12 m by the reference's own algorithm: two
-# correct libm's (glibc pow vs CUDA exp/log, 1 ulp apart) can stop a search one trip apart.  Measured on
-# 1.8e6 column-steps of the bench workload: worst |dAET| = 1.1e-12 m, identical for a build that calls the
-# CUDA library pow() (tools/scale_parity_stats.py).  Floor for these two: 2 x the iterative tolerance.
-RESIDUAL_ATOL_M = 2e-12
-RESIDUAL_SCALARS = (2, 8)   # actual_evapotranspiration, percolation
+EXACT = True
 
 
 def load_golden(name):
@@ -43,17 +39,26 @@ def config_for(name, tmpdir=None) -> Path:
     return absolutize_config(p, out_dir=tmpdir)
 
 
+def _first_diff(g, w):
+    bad = ~((g == w) | (np.isnan(g) & np.isnan(w)))
+    i = int(np.argmax(bad))
+    rel = np.abs(g.flat[i] - w.flat[i]) / (abs(w.flat[i]) + 1e-300)
+    return int(bad.sum()), i, g.flat[i], w.flat[i], rel
+
+
 def assert_scalars_close(got, want, what="", rtol=RTOL):
+    """got/want: [steps][12] per-step BMI scalars in metres.  Bit for bit (see EXACT above)."""
     got = np.asarray(got)
     want = np.asarray(want)
     assert got.shape == want.shape, (what, got.shape, want.shape)
     for k in range(want.shape[-1]):
-        g, w = got[..., k], want[..., k]
-        if k == 10:  # mass_balance
-            err = np.abs(g - w)
-            assert np.all(err <= MBAL_ATOL_M), f"{what}: mass_balance differs by {err.max():.3e} m at step {int(np.argmax(err))}"
+        g, w = np.ascontiguousarray(got[..., k]), np.ascontiguousarray(want[..., k])
+        if EXACT:
+            if not np.array_equal(g, w, equal_nan=True):
+                n, i, a, b, rel = _first_diff(g, w)
+                raise AssertionError(f"{what}: scalar {k}: {n} values differ from the reference, first at step {i}: got {a!r} want {b!r} (rel {rel:.3e})")
             continue
-        tol = rtol * np.maximum(np.abs(g), np.abs(w)) + (RESIDUAL_ATOL_M if k in RESIDUAL_SCALARS else ATOL_M)
+        tol = rtol * np.maximum(np.abs(g), np.abs(w)) + (1e-11 if k == 10 else 1e-14)
         err = np.abs(g - w)
         bad = err > tol
         assert not bad.any(), (f"{what}: scalar {k} differs at step {int(np.argmax(bad))}: got {g.flat[np.argmax(bad)]!r} "
@@ -61,13 +66,15 @@ def assert_scalars_close(got, want, what="", rtol=RTOL):
 
 
 def assert_fronts_close(got, gflags, want, wflags, n, what="", rtol=RTOL):
-    """got/want: [cap][5] depth,theta,psi,K,dzdt ; flags layer|to_bottom<<8 ; n fronts."""
+    """got/want: [cap][5] depth,theta,psi,K,dzdt ; flags layer|to_bottom<<8 ; n fronts.  Bit for bit (see EXACT above)."""
     assert np.array_equal(gflags[:n], wflags[:n]), f"{what}: layer/to_bottom differ: {gflags[:n]} vs {wflags[:n]}"
-    g, w = got[:n], want[:n]
-    # depth, theta, psi to 1e-9 relative; K and dzdt are derived through pow chains that amplify (K ~ Se^p): 1e-7
-    for j, tolj in ((0, rtol), (1, rtol), (2, rtol * 100), (3, rtol * 100), (4, rtol * 1000)):
+    g, w = np.ascontiguousarray(got[:n]), np.ascontiguousarray(want[:n])
+    if EXACT:
+        assert np.array_equal(g, w, equal_nan=True), f"{what}: front fields differ in the last bits:\n{g}\nvs\n{w}\n{g - w}"
+        return
+    for j in range(5):
         err = np.abs(g[:, j] - w[:, j])
-        tol = tolj * np.maximum(np.abs(g[:, j]), np.abs(w[:, j])) + 1e-13
+        tol = rtol * np.maximum(np.abs(g[:, j]), np.abs(w[:, j])) + 1e-13
         assert np.all(err <= tol), f"{what}: front field {j} differs: {g[:, j]} vs {w[:, j]}"
 
 

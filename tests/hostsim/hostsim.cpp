@@ -14,6 +14,16 @@
 
 using namespace lgarhost;
 
+#ifdef LGAR_FF_STATS
+// how the psi searches went (searches, finished by the fast path, declined, fallbacks, evaluations fast/plain, trips, verify mismatches)
+extern "C" void hostsim_ff_stats(long long* out8, int reset) {
+  const long long v[8] = {lg_ff_stats.searches, lg_ff_stats.ff_done, lg_ff_stats.declined, lg_ff_stats.fallback, lg_ff_stats.evals_ff,
+                          lg_ff_stats.evals_plain, lg_ff_stats.trips, lg_ff_stats.verify_bad};
+  for (int i = 0; i < 8; i++) out8[i] = v[i];
+  if (reset) lg_ff_stats = LgFfStats{};
+}
+#endif
+
 extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, const double* thick_in, int nsteps, const double* P,
                                   const double* E, double* scalars, int* nfronts, int cap, double* fronts, int* flags,
                                   int force_all_active, int* status_out, char* err, int errcap) {
@@ -72,18 +82,22 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
       w.nf_sink = nfs.data();
       if (force_all_active >= 4) {
         // lane-program emulation: one lane walks the stages of lgar_lanes.cuh
-        w.force_all_active = (force_all_active == 5);
+        w.force_all_active = (force_all_active == 5 || force_all_active == 7);
         int32_t counter = 0;
         w.tile_counter = &counter;
         static LgLane L;  // large: keep it off the stack
         L.stage = LG_ST_FETCH; L.col = -1; L.t = nsteps;
         while (L.stage != LG_ST_DONE) {
+          if (force_all_active >= 6 && L.stage == LG_ST_HEAD) {  // fused step (the STEP kernel of the wavefront scheduler)
+            lg_stage_step(cfg, d, w, L, nullptr);
+            continue;
+          }
           switch (L.stage) {
             case LG_ST_FETCH: lg_stage_fetch(cfg, d, w, L, nullptr); break;
             case LG_ST_HEAD: lg_stage_head(cfg, d, w, L, nullptr); break;
             case LG_ST_FRONT: lg_stage_front(L); break;
             case LG_ST_SEARCH:
-              while (!L.q.done) lg_search_iter(L.q, *L.cls);
+              lg_search_run(L.q, *L.cls);
               L.resume = true; L.stage = LG_ST_FRONT; break;
             case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, nullptr); break;
             case LG_ST_CORR:

@@ -42,7 +42,14 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 import bench  # noqa: E402
 from oracle.oracle_py import Oracle, SCALAR_NAMES, absolutize_config, read_forcing, write_config  # noqa: E402
-from helpers import ATOL_M, MBAL_ATOL_M, RESIDUAL_ATOL_M, RESIDUAL_SCALARS, RTOL  # noqa: E402
+from helpers import RTOL  # noqa: E402
+
+# north_star's bar: 1e-9 relative per step, front counts exact.  No absolute floors: a value that should be zero must be zero.
+# The one exception is the per-step mass-balance residual, which is rounding noise around zero (~1e-12 cm) and is compared
+# absolutely as SURVEY.md 8c prescribes.  Beside the bar the report counts what the engine is built for since round 2: columns
+# whose every scalar of every step EQUALS the oracle's bit for bit.
+ATOL_M = 0.0
+MBAL_ATOL_M = 1e-11
 
 DATA = ROOT / "data"
 
@@ -161,7 +168,7 @@ def _oracle_worker(rng_):
     wr, wa = np.zeros(12), np.zeros(12)
     viol = np.zeros(12, dtype=np.int64)          # columns with any step outside the parity bar, per scalar
     viol_steps = np.zeros(12, dtype=np.int64)
-    res = dict(nf_mismatch=0, fail_mismatch=0, frozen=0, steps=0, front_field_mismatch=0, flags_mismatch=0, examples=[])
+    res = dict(nf_mismatch=0, fail_mismatch=0, frozen=0, steps=0, front_field_mismatch=0, flags_mismatch=0, bit_equal=0, final_fronts_bit_equal=0, examples=[])
     for j in range(j0, j1):
         kw = {}
         if soils is not None:
@@ -194,10 +201,9 @@ def _oracle_worker(rng_):
         wr = np.maximum(wr, np.nan_to_num(rel).max(axis=0, initial=0.0))
         wa = np.maximum(wa, np.nan_to_num(err).max(axis=0, initial=0.0))
         tol = RTOL * mag + ATOL_M
-        for k in RESIDUAL_SCALARS:
-            tol[:, k] = RTOL * mag[:, k] + RESIDUAL_ATOL_M
         tol[:, 10] = MBAL_ATOL_M
         bad = ~(err <= tol)
+        res["bit_equal"] += int(done == T and np.array_equal(g, w, equal_nan=True) and np.array_equal(nf[:done, j], r["nfronts"][:done]))
         viol += bad.any(axis=0)
         viol_steps += bad.sum(axis=0)
         if bad.any() and len(res["examples"]) < 8:
@@ -210,11 +216,14 @@ def _oracle_worker(rng_):
             if n != len(flags) or not np.array_equal((fin["layer"][j][:n] | (fin["to_bottom"][j][:n] << 8)).astype(np.int32), flags):
                 res["flags_mismatch"] += 1
             else:
-                for q, (name, tl) in enumerate((("depth", RTOL), ("theta", RTOL), ("psi", RTOL * 100), ("K", RTOL * 100), ("dzdt", RTOL * 1000))):
+                eq = True
+                for q, name in enumerate(("depth", "theta", "psi", "K", "dzdt")):
                     a, b_ = fin[name][j][:n], arr[:, q]
-                    if not np.all(np.abs(a - b_) <= tl * np.maximum(np.abs(a), np.abs(b_)) + 1e-13):
+                    eq = eq and np.array_equal(a, b_)
+                    if not np.all(np.abs(a - b_) <= RTOL * np.maximum(np.abs(a), np.abs(b_))):
                         res["front_field_mismatch"] += 1
                         break
+                res["final_fronts_bit_equal"] += int(eq)
     res.update(worst_rel=wr, worst_abs=wa, viol=viol, viol_steps=viol_steps)
     return res
 
@@ -234,6 +243,8 @@ def diff_against_oracle(cfgobj, sample, hP, hE, scal, nf, status, final, cores):
                frozen_columns_in_sample=int(sum(p["frozen"] for p in parts)),
                final_front_flag_mismatch_columns=int(sum(p["flags_mismatch"] for p in parts)),
                final_front_field_mismatch_columns=int(sum(p["front_field_mismatch"] for p in parts)),
+               columns_bit_equal_every_scalar_every_step=int(sum(p["bit_equal"] for p in parts)),
+               columns_with_bit_equal_final_fronts=int(sum(p["final_fronts_bit_equal"] for p in parts)),
                oracle_seconds=dt, oracle_cores=cores, scalars={}, examples=[e for p in parts for e in p["examples"]][:12])
     wr = np.max([p["worst_rel"] for p in parts], axis=0)
     wa = np.max([p["worst_abs"] for p in parts], axis=0)
@@ -349,7 +360,7 @@ def main():
     ap.add_argument("--batch", type=int, default=250_000)
     ap.add_argument("--chunk", type=int, default=240)
     ap.add_argument("--steps", type=int, default=0, help="0: the config's full duration")
-    ap.add_argument("--mode", type=int, default=3)
+    ap.add_argument("--mode", type=int, default=5)
     ap.add_argument("--cores", type=int, default=0)
     ap.add_argument("--selftest", action="store_true")
     ap.add_argument("--selfnoise", action="store_true",
@@ -359,7 +370,7 @@ def main():
     a = ap.parse_args()
     cores = a.cores or bench.host_cores()
     tmp = Path(tempfile.mkdtemp(prefix="lgar_parity_"))
-    report = dict(tool="tools/parity_sampling_full.py", sample_seed=99, bar=dict(rtol=RTOL, atol_m=ATOL_M, residual_atol_m=RESIDUAL_ATOL_M,
+    report = dict(tool="tools/parity_sampling_full.py", sample_seed=99, bar=dict(rtol=RTOL, atol_m=ATOL_M,
                   mass_balance_atol_m=MBAL_ATOL_M, front_counts="exact"), configs={})
     for num in [int(x) for x in a.configs.split(",")]:
         c = Config(num, tmp)
