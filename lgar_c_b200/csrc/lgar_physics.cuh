@@ -122,6 +122,7 @@ LG_FN double lg_sq(double x) { return x * x; }
 LG_FN_NOINLINE double lg_exp(double x) { return exp(x); }
 LG_FN_NOINLINE double lg_log(double x) { return log(x); }
 LG_FN double lg_pow(double x, double y) { return lg_exp(y * lg_log(x)); }
+LG_FN double lg_pow_hot(double x, double y) { return lg_pow(x, y); }
 // calc_theta_from_h with log(h) supplied, fully inlined: the psi search evaluates every layer at the same psi
 LG_FN double lg_theta_from_lnh(double lnh, const LgarLayer& s) {
   const double y = exp(s.n * (s.ln_alpha + lnh));       // (alpha*h)^n
