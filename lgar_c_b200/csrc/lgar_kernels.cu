@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
 #pragma unroll
         for (int a = 0; a < 3; a++) ctx_load_n(l + kPitch * a, g + kPitch * a, cf);
         const LgarColumnClass* cls = G.cls;
-        for (int it = 0; it < quantum && !k.done; it++) lg_corr_iter(k, fb.f, *cls);
+        lg_corr_some(k, fb.f, *cls, quantum);
         G.k = k;
 #pragma unroll
         for (int a = 1; a < 3; a++) ctx_store_n(g + kPitch * a, l + kPitch * a, cf);
@@ -510,7 +510,7 @@ __global__ void lgar_wave_reset_kernel(int32_t* count, int32_t* cursor);
 // stage kernels carried through HBM at every stage boundary (4.4 x the algorithmic DRAM bytes in round 1) never leaves the
 // thread.  Rounds are FETCH, STEP.
 #ifndef LGAR_MB_STEP
-#define LGAR_MB_STEP 0
+#define LGAR_MB_STEP 4
 #endif
 __global__ void __launch_bounds__(128, LGAR_MB_STEP) lgar_wave_step_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int consume,
                                                                            unsigned append_mask) {
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
           break;
         case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, fsp); break;
         case LG_ST_CORR:
-          while (!L.k.done) lg_corr_iter(L.k, L.f, *L.cls);
+          lg_corr_run(L.k, L.f, *L.cls);
           L.stage = LG_ST_TAIL;
           break;
         default: L.stage = LG_ST_DONE; break;

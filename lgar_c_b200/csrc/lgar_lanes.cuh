@@ -442,87 +442,6 @@ LG_FN_NOINLINE bool lg_corr_init(LgLane& L, int front_num, double prior_mass) {
   return !k.done;
 }
 
-// one trip of the loop on the live front list
-LG_FN void lg_corr_iter(LgCorr& k, LgFronts& f, const LgarColumnClass& cls) {
-  const int first_thresh = LG_MAX_ITER_MBAL / 100, second_thresh = LG_MAX_ITER_MBAL / 10;
-  const int cur = k.cur;
-  k.iter++;
-  if (k.iter > first_thresh && !k.aug) {
-    k.factor = k.factor * 100;
-    k.aug = true;
-  }
-  if (k.iter > second_thresh && !k.aug_extreme) {
-    k.factor = k.factor * 100;
-    k.aug_extreme = true;
-  }
-  if (k.new_mass > k.prior_mass) {
-    k.psi_loc += 0.1 * k.factor;
-    k.switched = false;
-  } else {
-    if (!k.switched) {
-      k.switched = true;
-      k.factor = k.factor * 0.1;
-    }
-    k.psi_prev = k.psi_loc;
-    k.psi_loc -= 0.1 * k.factor;
-    if (k.psi_loc < 0 && k.psi_prev != 0) k.psi_loc = k.psi_prev * 0.1;
-  }
-  if (k.psi_loc < 0.0) {
-    k.psi_loc = 0.0;
-    k.factor = k.factor * 0.5;
-  }
-  const double lnpsi = lg_lnh(k.psi_loc);
-  // the fronts that take the new psi: `cur`, the to-bottom fronts chained below it and the first free
-  // front after such a chain (lgar.cxx:3340-3375; every psi in the chain is a copy of psi_loc).  One
-  // loop = one inlined theta(psi) instead of three: the kernel drops from 235 to ~130 registers.
-  int last = cur;
-  {
-    int nx = cur + 1;
-    while (nx < f.n && f.tb[nx]) {
-      last = nx;
-      nx++;
-    }
-    if (nx < f.n && f.tb[last]) last = nx;  // tb[nx] is false here
-  }
-#pragma unroll 1
-  for (int j = cur; j <= last; j++) {
-    f.psi[j] = k.psi_loc;
-    f.theta[j] = lg_theta_from_lnh(lnpsi, cls.lay[f.layer[j]]);
-  }
-  {  // lgar_calc_mass_bal, lgar.cxx:2632-2668
-    const double* cum = cls.cum;
-    double sum = 0.0;
-#pragma unroll 1
-    for (int i = 0; i < f.n; i++) {
-      double base = cum[f.layer[i] - 1];
-      if (i + 1 < f.n) {
-        if (f.layer[i + 1] == f.layer[i])
-          sum += (f.depth[i] - base) * (f.theta[i] - f.theta[i + 1]);
-        else
-          sum += (f.depth[i] - base) * f.theta[i];
-      } else {
-        sum += f.theta[i] * (f.depth[i] - base);
-      }
-    }
-    k.new_mass = sum;
-  }
-  k.delta_mass = fabs(k.new_mass - k.prior_mass);
-  bool brk = false;
-  if (fabs(k.psi_loc - k.psi_prev) < 1E-15 && k.factor < 1E-13) brk = true;
-  if (!brk) {
-    if (fabs(k.delta_mass - k.delta_mass_prev) < 1E-15)
-      k.count_no_mass_change++;
-    else
-      k.count_no_mass_change = 0;
-    if (k.count_no_mass_change == 5) brk = true;
-    else if (k.iter > LG_MAX_ITER_MBAL) brk = true;
-    else if (k.psi_loc <= 0 && k.psi_prev < 0) brk = true;
-    else if ((k.psi_loc > LG_PSI_UPPER_LIM) && (k.iter > first_thresh)) brk = true;
-  }
-  if (!brk) k.delta_mass_prev = k.delta_mass;
-  if (brk || !(k.delta_mass > LG_MBAL_TOL)) k.done = true;
-}
-
 // lgar_fix_dry_over_wet_wetting_fronts (lgar.cxx:2260-2307), resumable around its correction search.
 // Returns true when a correction search has to iterate.
 LG_FN_NOINLINE bool lg_fix_run(LgLane& L) {
@@ -887,7 +806,7 @@ LG_FN_NOINLINE void lg_stage_step(const LgarConfig& cfg, const LgarDeviceState& 
     } else if (L.stage == LG_ST_TAIL) {
       lg_stage_tail(cfg, d, w, L, front_sum);
     } else {
-      while (!L.k.done) lg_corr_iter(L.k, L.f, *L.cls);
+      lg_corr_run(L.k, L.f, *L.cls);
       L.stage = LG_ST_TAIL;
     }
   }

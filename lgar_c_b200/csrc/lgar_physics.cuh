@@ -380,77 +380,25 @@ LG_FN_NOINLINE void lg_theta_mass_balance_correction(LgCtx& c, int front_num, do
       break;
     }
   }
-  double new_mass = lg_mass_bal(c);
-  double psi_cm = f.psi[cur];
-  double psi_loc = psi_cm;
-  double delta_mass = fabs(new_mass - prior_mass);
-  double factor = fmax(1.0, psi_cm / 10.0);
-  if (psi_cm > 1.E4) factor = psi_cm;
-  bool switched = false;
-  double psi_prev = psi_loc;
-  double delta_mass_prev = delta_mass;
-  int count_no_mass_change = 0;
-  int iter = 0;
-  bool aug = false, aug_extreme = false;
-  const int first_thresh = LG_MAX_ITER_MBAL / 100, second_thresh = LG_MAX_ITER_MBAL / 10;
-
-  while (delta_mass > LG_MBAL_TOL) {
-    iter++;
-    if (iter > first_thresh && !aug) {
-      factor = factor * 100;
-      aug = true;
-    }
-    if (iter > second_thresh && !aug_extreme) {
-      factor = factor * 100;
-      aug_extreme = true;
-    }
-    if (new_mass > prior_mass) {
-      psi_loc += 0.1 * factor;
-      switched = false;
-    } else {
-      if (!switched) {
-        switched = true;
-        factor = factor * 0.1;
-      }
-      psi_prev = psi_loc;
-      psi_loc -= 0.1 * factor;
-      if (psi_loc < 0 && psi_prev != 0) psi_loc = psi_prev * 0.1;
-    }
-    if (psi_loc < 0.0) {
-      psi_loc = 0.0;
-      factor = factor * 0.5;
-    }
-    f.psi[cur] = psi_loc;
-    f.theta[cur] = lg_theta_from_h(psi_loc, cls.lay[f.layer[cur]]);
-    int nx = cur + 1, before = cur;
-    if (nx < f.n) {
-      while (f.tb[nx]) {
-        f.psi[nx] = f.psi[before];
-        f.theta[nx] = lg_theta_from_h(f.psi[nx], cls.lay[f.layer[nx]]);
-        before = nx;
-        nx = nx + 1;
-        if (nx >= f.n) break;
-      }
-      if (nx < f.n) {
-        if (!f.tb[nx] && f.tb[before]) {
-          f.psi[nx] = f.psi[before];
-          f.theta[nx] = lg_theta_from_h(f.psi[nx], cls.lay[f.layer[nx]]);
-        }
-      }
-    }
-    new_mass = lg_mass_bal(c);
-    delta_mass = fabs(new_mass - prior_mass);
-    if (fabs(psi_loc - psi_prev) < 1E-15 && factor < 1E-13) break;
-    if (fabs(delta_mass - delta_mass_prev) < 1E-15)
-      count_no_mass_change++;
-    else
-      count_no_mass_change = 0;
-    if (count_no_mass_change == 5) break;
-    if (iter > LG_MAX_ITER_MBAL) break;
-    if (psi_loc <= 0 && psi_prev < 0) break;
-    if ((psi_loc > LG_PSI_UPPER_LIM) && (iter > first_thresh)) break;
-    delta_mass_prev = delta_mass;
-  }
+  LgCorr k;
+  k.cur = cur;
+  k.iter = 0;
+  k.new_mass = lg_mass_bal(c);
+  const double psi_cm = f.psi[cur];
+  k.psi_loc = psi_cm;
+  k.prior_mass = prior_mass;
+  k.delta_mass = fabs(k.new_mass - prior_mass);
+  k.factor = fmax(1.0, psi_cm / 10.0);
+  if (psi_cm > 1.E4) k.factor = psi_cm;
+  k.switched = false;
+  k.psi_prev = psi_cm;
+  k.delta_mass_prev = k.delta_mass;
+  k.count_no_mass_change = 0;
+  k.aug = false;
+  k.aug_extreme = false;
+  k.no_ff = false;
+  k.done = !(k.delta_mass > LG_MBAL_TOL);
+  if (!k.done) lg_corr_run(k, f, cls);
 }
 
 // lgar_merge_wetting_fronts, lgar.cxx:1875-1953

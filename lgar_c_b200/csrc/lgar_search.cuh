@@ -455,4 +455,137 @@ LG_FN_NOINLINE void lg_search_run(LgSearch& q, const LgarColumnClass& cls) {
 #endif
 }
 
+// ---- lgar_theta_mass_balance_correction (lgar.cxx:3262-3435) --------------------------------------------------------------
+// The evaluation of one trip on the live front list: the fronts that take the new psi are `cur`, the to-bottom fronts chained
+// below it and the first free front after such a chain (lgar.cxx:3340-3375; every psi in the chain is a copy of psi_loc), then
+// the mass of the whole list (lgar_calc_mass_bal, lgar.cxx:2632-2668).
+LG_FN int lg_corr_chain_end(const LgFronts& f, int cur) {
+  int last = cur;
+  int nx = cur + 1;
+  while (nx < f.n && f.tb[nx]) {
+    last = nx;
+    nx++;
+  }
+  if (nx < f.n && f.tb[last]) last = nx;  // tb[nx] is false here
+  return last;
+}
+LG_FN double lg_corr_list_mass(const LgFronts& f, const LgarColumnClass& cls) {
+  const double* cum = cls.cum;
+  double sum = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < f.n; i++) {
+    double base = cum[f.layer[i] - 1];
+    if (i + 1 < f.n) {
+      if (f.layer[i + 1] == f.layer[i])
+        sum += (f.depth[i] - base) * (f.theta[i] - f.theta[i + 1]);
+      else
+        sum += (f.depth[i] - base) * f.theta[i];
+    } else {
+      sum += f.theta[i] * (f.depth[i] - base);
+    }
+  }
+  return sum;
+}
+LG_FN void lg_corr_eval(LgCorr& k, LgFronts& f, const LgarColumnClass& cls) {
+  const int cur = k.cur;
+  const double lnpsi = lg_lnh(k.psi_loc);
+  const int last = lg_corr_chain_end(f, cur);
+#pragma unroll 1
+  for (int j = cur; j <= last; j++) {
+    f.psi[j] = k.psi_loc;
+    f.theta[j] = lg_theta_from_lnh(lnpsi, cls.lay[f.layer[j]]);
+  }
+  k.new_mass = lg_corr_list_mass(f, cls);
+  k.delta_mass = fabs(k.new_mass - k.prior_mass);
+}
+// one trip of the loop
+LG_FN void lg_corr_iter(LgCorr& k, LgFronts& f, const LgarColumnClass& cls) {
+  lg_digit_pre(k, k.new_mass > k.prior_mass);
+  lg_corr_eval(k, f, cls);
+  lg_digit_post(k, true);  // the five-trips-without-change exit is always armed here (lgar.cxx:3418)
+}
+
+#if !defined(LGAR_FAST_POW)
+// The mass model of the correction search for the fast path of lgar_search.cuh.  The list mass is linear in the thetas of the
+// chain fronts; front j of the chain carries the coefficient (depth_j - top of its layer), minus the same of front j-1 when that
+// one is in the same layer.  Terms are grouped by soil layer (one unimodal |d theta / d psi| per layer).
+struct LgCorrModel {
+  static constexpr int kMaxTerms = LGAR_MAXL + 1;
+  LgCorr* k;
+  LgFronts* f;
+  const LgarColumnClass* cls;
+  int last;
+  double coef[LGAR_MAXL + 1];
+  bool ok;
+  LG_MFN void init() {
+    const LgFronts& F = *f;
+    last = lg_corr_chain_end(F, k->cur);
+    ok = true;
+    for (int l = 0; l <= LGAR_MAXL; l++) coef[l] = 0.0;
+    for (int j = k->cur; j <= last; j++) {
+      const int l = F.layer[j];
+      const LgarLayer& s = cls->lay[l];
+      double c = F.depth[j] - cls->cum[l - 1];
+      if (j > 0 && F.layer[j - 1] == l) c -= F.depth[j - 1] - cls->cum[l - 1];
+      if (!(c >= 0.0) || !(s.n > 1.0) || !(s.alpha > 0.0) || !(s.de > 0.0)) ok = false;
+      coef[l] += c;
+    }
+  }
+  LG_MFN bool monotone() const { return ok; }
+  LG_MFN int terms() const { return LGAR_MAXL + 1; }
+  LG_MFN double term_slope_max(int t) const { return coef[t] * cls->lay[t].slope_max; }
+  LG_MFN_NOINLINE double mass(double psi, double* sl, unsigned* past) const {   // lg_corr_eval at psi
+    LgFronts& F = *f;
+    for (int l = 0; l <= LGAR_MAXL; l++) sl[l] = 0.0;
+    unsigned pb = 0;
+#pragma unroll 1
+    for (int j = k->cur; j <= last; j++) {
+      const int l = F.layer[j];
+      double s;
+      bool pm;
+      F.psi[j] = psi;
+      F.theta[j] = lg_theta_and_slope(psi, cls->lay[l], &s, &pm);
+      sl[l] = coef[l] * s;
+      pb |= pm ? (1u << l) : 0u;
+    }
+    *past = pb;
+    return lg_corr_list_mass(F, *cls);
+  }
+  LG_MFN void trip(LgCorr& kk) const { lg_corr_eval(kk, *f, *cls); }
+};
+#endif
+
+// A freshly initialised correction search (lg_corr_init returned true) through the fast path, then at most `quantum` plain
+// trips of whatever is left.
+LG_FN void lg_corr_some(LgCorr& k, LgFronts& f, const LgarColumnClass& cls, int quantum) {
+#if !defined(LGAR_FAST_POW) && !defined(LGAR_NO_FF)
+  if (!k.no_ff && k.iter == 0) {
+    LgCorrModel ev;
+    ev.k = &k;
+    ev.f = &f;
+    ev.cls = &cls;
+    ev.init();
+    if (lg_digit_ff(k, ev, true)) return;
+  }
+#endif
+  for (int it = 0; it < quantum && !k.done; it++) lg_corr_iter(k, f, cls);
+}
+// the whole correction search to k.done
+LG_FN_NOINLINE void lg_corr_run(LgCorr& k, LgFronts& f, const LgarColumnClass& cls) {
+#ifdef LGAR_FF_VERIFY
+  LgCorr ref = k;
+  static LgFronts fref;
+  fref = f;
+  while (!ref.done) lg_corr_iter(ref, fref, cls);
+  const bool fresh = !k.no_ff && k.iter == 0;
+  LG_FF_COUNT(searches, 1);
+#endif
+  while (!k.done) lg_corr_some(k, f, cls, 1 << 30);
+#ifdef LGAR_FF_VERIFY
+  bool same = lgp_bits(ref.psi_loc) == lgp_bits(k.psi_loc) && lgp_bits(ref.delta_mass) == lgp_bits(k.delta_mass) && lgp_bits(ref.new_mass) == lgp_bits(k.new_mass) && ref.iter == k.iter;
+  for (int i = 0; i < f.n; i++) same = same && lgp_bits(fref.theta[i]) == lgp_bits(f.theta[i]) && lgp_bits(fref.psi[i]) == lgp_bits(f.psi[i]);
+  if (fresh && !same) LG_FF_COUNT(verify_bad, 1);
+#endif
+}
+
 #endif

@@ -101,7 +101,7 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
               L.resume = true; L.stage = LG_ST_FRONT; break;
             case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, nullptr); break;
             case LG_ST_CORR:
-              while (!L.k.done) lg_corr_iter(L.k, L.f, *L.cls);
+              lg_corr_run(L.k, L.f, *L.cls);
               L.stage = LG_ST_TAIL; break;
           }
         }

@@ -74,6 +74,31 @@ def test_kernel_text_matches_golden(hostsim, name, force, tmp_path):
             assert np.array_equal(fr[t][:k], g["ck_fronts"][i][:k]), f"{name}@{t}: front fields differ in the last bits"
 
 
+def test_fast_search_path_reproduces_the_plain_walk(tmp_path):
+    """lgar_search.cuh: every psi search and every correction search of every golden case through BOTH the fast path (root by
+    Newton, bracket, replay of the digit walk with the evaluations outside the bracket skipped) and the plain trip-by-trip walk
+    of the reference (-DLGAR_FF_VERIFY): the final records -- psi, theta, mass error, trip count, the fronts a correction search
+    rewrites -- must be equal bit for bit, and the fast path must be what actually runs (>= 95 % of the searches finished by it)."""
+    so = tmp_path / "libhostsim_ffv.so"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-DLGAR_FF_STATS", "-DLGAR_FF_VERIFY", "-o", str(so),
+                           str(HS / "hostsim.cpp")])
+    lib = C.CDLL(str(so))
+    lib.hostsim_run_series.argtypes = [C.c_char_p, _ip, _dp, C.c_int, _dp, _dp, _dp, _ip, C.c_int, _dp, _ip, C.c_int, _ip, C.c_char_p, C.c_int]
+    lib.hostsim_run_series.restype = C.c_int
+    for name in STANDARD + RANDOM:
+        g = load_golden(name)
+        n = min(len(g["precip"]), 3000)
+        for force in (0, 4, 6):
+            done, scal, nf, fr, fl, status = run(lib, config_for(name, tmp_path), g["precip"][:n], g["pet"][:n], force)
+            assert done == n and np.array_equal(nf, g["nfronts"][:n]) and np.array_equal(scal, g["scalars"][:n]), (name, force)
+    st = (C.c_longlong * 8)()
+    lib.hostsim_ff_stats(st, 0)
+    searches, ff_done, declined, fallback, evals_ff, _, trips, verify_bad = list(st)
+    assert verify_bad == 0, f"{verify_bad} searches ended differently through the fast path"
+    assert searches > 10_000 and ff_done >= 0.95 * searches, (searches, ff_done, declined, fallback)
+    assert evals_ff < 0.35 * trips, "the fast path evaluates more than a third of the trips it replays"
+
+
 @pytest.fixture(scope="module")
 def hostsim_libm_pow():
     """The same kernel text with x^y = the library pow (-DLGAR_ACCURATE_POW; on the host that is glibc's pow, the function
