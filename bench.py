@@ -340,7 +340,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--finish-below", type=int, default=-1, help="wavefront: slots in flight below which the finishing kernel takes over (-1: engine default)")
-    ap.add_argument("--mode", type=int, default=5, help="5 FETCH + STEP kernels (whole active steps per thread), 3 six stage kernels, 2 lanes kernel, 1 warp-tile window kernel, 0 one kernel pair per forcing hour")
+    ap.add_argument("--mode", type=int, default=3, help="3 six stage kernels with queues between them, 2 lanes kernel, 1 warp-tile window kernel, 0 one kernel pair per forcing hour")
     args = ap.parse_args()
     # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints
     # "NCCL version ..." there whatever NCCL_DEBUG_FILE says) are sent to stderr, the line goes to the saved descriptor
@@ -564,7 +564,7 @@ def main():
     B_nofront = B_full - 2 * 44 * mean_fronts
     ms_s, ms_a, ms_w = prof["ms_stream"], prof["ms_active"], prof["ms_window"]
     if ms_w > 0:  # window mode: one kernel per bench step (H forcing hours for every column)
-        dominant = {5: "lgar_wave_step_kernel (+ lgar_wave_fetch_kernel)", 3: "lgar_wave_kernel<*> + lgar_wave_fetch_kernel (6 stage kernels)", 2: "lgar_lanes_kernel", 1: "lgar_window_kernel"}[args.mode]
+        dominant = {3: "lgar_wave_kernel<*> + lgar_wave_fetch_kernel (6 stage kernels)", 2: "lgar_lanes_kernel", 1: "lgar_window_kernel"}[args.mode]
         units = ncol * H
         B_unit = B_full
         dur_s = ms_w * 1e-3 / args.steps  # per bench step (one day of every column); mode 3 runs all steps in one call

@@ -128,7 +128,7 @@ def _load():
         "lgarb_get_last_active_count": ([vp], i64),
         "lgarb_get_stream": ([vp], vp),
         "lgarb_measure_fp64_peak": ([vp, C.c_double, dp], C.c_int),
-        "lgarb_debug_pow": ([vp, C.c_int64, dp, dp, dp, C.c_int], C.c_int),
+        "lgarb_debug_pow": ([vp, C.c_int64, vp, vp, vp, C.c_int], C.c_int),
         "lgarb_set_profiling": ([vp, C.c_int], C.c_int),
         "lgarb_get_profile": ([vp, dp], C.c_int),
     }
@@ -437,8 +437,8 @@ class BmiLGARBatch:
         self._ck(self._L.lgarb_set_force_all_active(self._h, int(bool(on))))
 
     def set_window_mode(self, mode):
-        """Scheduler of the multi-step verbs: 5 FETCH + STEP kernels, whole active steps per thread (default); 3 six stage kernels
-        with queues between them; 2 lanes kernel; 1 warp-tile window kernel; 0 hour-by-hour kernel pairs.  All bit-identical."""
+        """Scheduler of the multi-step verbs: 3 six stage kernels with queues between them (default); 2 lanes kernel; 1 warp-tile
+        window kernel; 0 hour-by-hour kernel pairs.  All bit-identical."""
         self._ck(self._L.lgarb_set_window_mode(self._h, int(mode)))
 
     def set_wave_params(self, search_quantum=0, front_search_pairs=0, finish_below=-1):

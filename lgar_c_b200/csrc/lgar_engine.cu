@@ -94,7 +94,7 @@ struct lgarb_engine {
   cudaStream_t stream = nullptr;
   int active_blocks = 0;
   int window_blocks = 0;
-  int use_window = 5;          // multi-step runs: 5 = FETCH + STEP kernels (whole steps per thread), 3 = six stage kernels, 2 = lanes kernel, 1 = warp-tile window kernel, 0 = hour-by-hour kernel pairs
+  int use_window = 3;          // multi-step runs: 3 = six stage kernels with queues between them, 2 = lanes kernel, 1 = warp-tile window kernel, 0 = hour-by-hour kernel pairs
   int lanes_blocks = 0;
   unsigned int* d_work_trace = nullptr;  // [2][stride], allocated by lgarb_set_work_trace
   double* d_host_series = nullptr;  // staging of lgarb_update_steps_host
@@ -956,20 +956,6 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
                                     e->sm_count, launch_stream));
     e->launches += 2;
   };
-  auto launch_step = [&]() {  // the STEP kernel consumes the HEAD queue and appends to the FETCH queue
-    const int consume = par[LG_ST_HEAD];
-    par[LG_ST_HEAD] ^= 1;
-    unsigned mask = 0;
-    for (int s = 0; s < LGAR_NSTAGE; s++) mask |= (unsigned)par[s] << s;
-    if (dbg_on) {
-      dbg_evs.emplace_back();
-      cudaEventCreate(&dbg_evs.back().first);
-      cudaEventRecord(dbg_evs.back().first, e->stream);
-      dbg_evs.back().second = LG_ST_HEAD;  // booked under HEAD in the debug line
-    }
-    CUDA_TRY(lgar_launch_wave_step(e->cfg, e->d, w, wv, consume, mask, in_flight, e->sm_count, e->stream));
-    e->launches += 2;
-  };
   int32_t* h_cnt = (int32_t*)e->pinned(64 * sizeof(int32_t));
   const bool debug = getenv("LGARB_WAVE_DEBUG") != nullptr;
   cudaEvent_t dbg[2];
@@ -1029,22 +1015,18 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       CUDA_TRY(cudaEventRecord(e->side_ev[1], e->side_stream));
       corr_forked = true;
     }
-    if (e->use_window == 5) {
-      // whole steps per thread: FETCH walks the columns to their next active hour, STEP runs that hour
-      if (cnt[LG_ST_FETCH] > 0) launch(LG_ST_FETCH);
-      launch_step();
-    } else if (new_steps) {
+    if (new_steps) {
       launch(LG_ST_FETCH);
       launch(LG_ST_HEAD);  // runs the first stretch of the front loop too
     }
-    if (e->use_window != 5 && (new_steps || cnt[LG_ST_FRONT] + cnt[LG_ST_SEARCH] > 0)) {
+    if (new_steps || cnt[LG_ST_FRONT] + cnt[LG_ST_SEARCH] > 0) {
       if (cnt[LG_ST_FRONT] > 0) launch(LG_ST_FRONT);
       for (int k = 0; k < e->wave_pairs; k++) {
         launch(LG_ST_SEARCH);
         launch(LG_ST_FRONT);
       }
     }
-    if (e->use_window != 5) {
+    {
       if (corr_forked) CUDA_TRY(cudaStreamWaitEvent(e->stream, e->side_ev[1], 0));
       launch(LG_ST_TAIL);
       for (int k = 0; k < (corr_async ? 0 : e->wave_corr_pairs); k++) {
@@ -1590,7 +1572,7 @@ int lgarb_get_warp_times(lgarb_engine* e, uint32_t* out16384) {
     d2h(e, out16384, e->d_work_trace + 2 * e->stride + 64, 2 * 8192 * sizeof(uint32_t));
   });
 }
-int lgarb_set_window_mode(lgarb_engine* e, int mode) { LGARB_GUARD(e, e->use_window = (mode < 0 || mode > 5 || mode == 4) ? 5 : mode); }
+int lgarb_set_window_mode(lgarb_engine* e, int mode) { LGARB_GUARD(e, e->use_window = (mode < 0 || mode > 3) ? 3 : mode); }
 int lgarb_set_wave_params(lgarb_engine* e, int search_quantum, int front_search_pairs, int finish_below) {
   LGARB_GUARD(e, {
     if (search_quantum > 0) e->wave_quantum = search_quantum;

@@ -498,52 +498,6 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
   if (w.prof && front_sum) atomicAdd(w.prof, front_sum);
 }
 
-__global__ void lgar_wave_reset_kernel(int32_t* count, int32_t* cursor);
-
-// ---- STEP kernel (mode 5) ------------------------------------------------------------------------------
-// What forced the step into six stage kernels was the psi search: 32-128 dependent trips of two pow per layer, heavy tailed to
-// 10^4 (median 7 theta evaluations per active step, mean 115, max > 20 000), so lanes that ran whole steps side by side kept
-// 2.5 of 32 lanes busy.  With the fast path of lgar_search.cuh a search is ~10 evaluations plus a cheap replay whatever its
-// trip count, and an active step is a piece of work of bounded, similar size for every lane.  So a thread takes a slot from
-// the HEAD queue, loads the column STATE (scalars, epilogue state, live fronts: ~0.6 KB), runs the whole step -- sub-cycles,
-// front loop, searches, corrections, reservoir, GIUH, outputs -- and stores the state back: the 1.2-1.7 KB step context that the
-// stage kernels carried through HBM at every stage boundary (4.4 x the algorithmic DRAM bytes in round 1) never leaves the
-// thread.  Rounds are FETCH, STEP.
-#ifndef LGAR_MB_STEP
-#define LGAR_MB_STEP 4
-#endif
-__global__ void __launch_bounds__(128, LGAR_MB_STEP) lgar_wave_step_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int consume,
-                                                                           unsigned append_mask) {
-  const int n = wv.qcount[LG_ST_HEAD * 2 + consume];
-  LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
-  unsigned long long front_sum = 0, active_sum = 0;
-  unsigned long long* fsp = w.prof ? &front_sum : nullptr;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31); i += gridDim.x * blockDim.x) {
-    const bool valid = i < n;
-    const int slot = valid ? wv.queue[LG_ST_HEAD][consume][i] : 0;
-    if (valid) {
-      LgLaneSlot S;
-      lane_load<LG_PART_STATE>(&S, &slots[slot]);
-      lg_stage_step(cfg, d, w, S.L, fsp);
-      active_sum += S.L.s.cache_fluxes ? 0 : 1;
-      lane_store<LG_PART_STATE>(&slots[slot], &S);
-    }
-    wave_push(wv, append_mask, LG_ST_FETCH, valid, slot);
-  }
-  if (w.prof) {
-    if (front_sum) atomicAdd(w.prof, front_sum);
-    if (active_sum) atomicAdd(w.prof + 1, active_sum);
-  }
-}
-
-cudaError_t lgar_launch_wave_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int consume, unsigned append_mask,
-                                  int max_items, int sm_count, cudaStream_t stream) {
-  const int blocks = std::max(1, std::min((std::min(wv.nslots, max_items) + 127) / 128, sm_count * 16));
-  lgar_wave_step_kernel<<<blocks, 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask);
-  lgar_wave_reset_kernel<<<1, 1, 0, stream>>>(wv.qcount + LG_ST_HEAD * 2 + consume, nullptr);
-  return cudaGetLastError();
-}
-
 // Finishing kernel: when only a few slots are left in flight (the columns that are active in almost every
 // hour of the window), a round of ~13 launches costs ~2.5 ms whatever it processes.  Here every remaining
 // slot is taken by one thread which runs its column through all stages to the end of the window without

@@ -58,9 +58,6 @@ struct LgarWave {
 // sm_count: multiprocessors of the device (grids are sized in multiples of it)
 cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int stage, int consume,
                                    unsigned append_mask, int quantum, int max_items, int sm_count, cudaStream_t stream);
-// mode 5: one launch of the STEP kernel (whole active steps), consuming queue[HEAD][consume] and appending to the FETCH queue
-cudaError_t lgar_launch_wave_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int consume, unsigned append_mask,
-                                  int max_items, int sm_count, cudaStream_t stream);
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
                                     int lane_stride, int sm_count, cudaStream_t stream);
 cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWave& wv, int slot_is_column, cudaStream_t stream);

@@ -791,27 +791,6 @@ LG_FN_NOINLINE void lg_stage_tail(const LgarConfig& cfg, const LgarDeviceState& 
   L.stage = LG_ST_FETCH;
 }
 
-// STEP: a whole active step in one go -- HEAD, the front loop with its psi searches run where they arise (lg_search_run: ~10
-// evaluations each since the fast path of lgar_search.cuh, so there is nothing left to park), TAIL with its correction searches.
-// Ends in FETCH.  The step context never leaves the thread.
-LG_FN_NOINLINE void lg_stage_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, LgLane& L, unsigned long long* front_sum) {
-  lg_stage_head(cfg, d, w, L, front_sum);
-  while (L.stage != LG_ST_FETCH) {
-    if (L.stage == LG_ST_FRONT) {
-      while (lg_move_fronts(L)) {
-        lg_search_run(L.q, *L.cls);
-        L.resume = true;
-      }
-      L.stage = LG_ST_TAIL;
-    } else if (L.stage == LG_ST_TAIL) {
-      lg_stage_tail(cfg, d, w, L, front_sum);
-    } else {
-      lg_corr_run(L.k, L.f, *L.cls);
-      L.stage = LG_ST_TAIL;
-    }
-  }
-}
-
 // FETCH: walk the resident column through the hours that need no flux computation; when it has finished the
 // window write its state back and (unless the slot is bound to one column) take the next column.  Ends in
 // HEAD (active step at hour L.t) or DONE.  L may live in HBM: the hot loop works on register copies.

@@ -50,6 +50,7 @@ struct LgSearch {  // one psi search in flight (lgar_theta_mass_balance)
   double dth[LGAR_MAXL + 1], dz[LGAR_MAXL + 1];
   int layer_num, iter, count_no_mass_change;
   bool switched, wanted_to_saturate, aug, aug_extreme, done, no_ff;
+  LG_MFN void theta_store(double th) { theta = th; }
 };
 
 // one correction search in flight (lgar_theta_mass_balance_correction, lgar.cxx:3262-3435): it works on the
@@ -58,6 +59,7 @@ struct LgCorr {
   double psi_loc, factor, psi_prev, delta_mass, delta_mass_prev, new_mass, prior_mass;
   int cur, iter, count_no_mass_change;
   bool switched, aug, aug_extreme, done, no_ff;
+  LG_MFN void theta_store(double) {}  // the correction search keeps its thetas in the front list
 };
 
 #ifdef LGAR_FF_STATS   // host-side instrumentation (tests/hostsim): how the searches went
@@ -156,190 +158,247 @@ LG_FN bool lg_ff_apart(double x, double y, double a, double b, double g, double 
 #define LG_FF_MAX_NEWTON 16
 
 // Ev: the mass model of a search.
-//   double mass(double psi, double* sl, unsigned* past)   the mass a trip at psi computes (bit for bit), sl[k] = |d mass/d psi| of
-//                                         term k, bit k of *past: term k is beyond the maximum of its |slope|
+//   double eval(double psi, double* sl, unsigned* past, double* theta)
+//                                         the mass a trip at psi computes (bit for bit; *theta: what the trip stores as theta),
+//                                         sl[k] = |d mass/d psi| of term k, bit k of *past: term k is beyond the maximum of its |slope|
 //   double term_slope_max(int k)          upper bound of sl[k] over all psi
 //   int    terms()                        number of terms of sl
-//   void   trip(Q& q)                     the evaluation of a trip at q.psi_loc: q.new_mass, q.delta_mass (and what else it sets)
 //   bool   monotone()                     the model is one this fast path may be used on
 // Returns true when the search is finished (q.done, final record as the plain walk leaves it), false when the fast path
 // declined: q is then untouched except q.no_ff.
+//
+// Shape of the code.  32 searches run side by side in a warp, and an evaluation (two pow per layer, ~600 instructions) is the
+// only expensive thing here, so ALL evaluations -- Newton steps, the two bracket points, zone ends, the exactly evaluated trips
+// -- go through ONE call site at the top of one loop; between two evaluations each lane runs its own cheap bookkeeping (the
+// recurrences of the skipped trips) and comes back to the call site.  Written the straightforward way (evaluate where the need
+// arises) the lanes of a warp reach their handful of exact trips at different points of the walk and the warp pays for the union:
+// measured on the B200, the six stage kernels fell from 4.3e8 to 1.8e8 column-timesteps/s (profiles/r2_call1_summary.md).
 template <class Q, class Ev>
 LG_FN bool lg_digit_ff(Q& q, Ev& ev, const bool gate) {
   const Q q0 = q;
   const double prior = q.prior_mass;
   const double TOL = LG_MBAL_TOL;
   q.no_ff = true;
-  if (!ev.monotone()) return false;
-  const int nt = ev.terms();
-  double sl[Ev::kMaxTerms], slz[2][Ev::kMaxTerms];
-  // ---- 1. root of f(psi) = mass(psi) - prior ----
   const double x0 = q.psi_loc;
-  if (!(x0 > 0.0) || !(x0 < 1e300)) return false;
+  if (!ev.monotone() || !(x0 > 0.0) || !(x0 < 1e300)) return false;
+  const int nt = ev.terms();
+  double sl[Ev::kMaxTerms], slz[Ev::kMaxTerms];
+  enum { S_NEWTON, S_BR_A, S_BR_B, S_ZONE_LO, S_ZONE_HI, S_TRIP };
+  enum { W_BEGIN, W_AFTER_EVAL, W_BOOK, W_RECHECK };
+  enum { R_RUNNING, R_DONE, R_DECLINED, R_FALLBACK };
+  int st = S_NEWTON, wphase = W_BEGIN, result = R_RUNNING;
+  double xr = x0;  // where the next evaluation is wanted
+  // root finder
   double lo = -1.0, hi = -1.0;  // f(lo) > 0 > f(hi); -1: not known yet
-  unsigned pasta = 0, pastb = 0;
-  double x = x0, root = 0.0, sroot = 0.0;
-  bool found = false;
-  int evals = 0;
-  for (int it = 0; it < LG_FF_MAX_NEWTON; it++) {
-    double* sp = sl;
-    unsigned pm;
-    const double fx = ev.mass(x, sp, &pm) - prior;
-    evals++;
-    double sx = 0.0;
-    for (int k = 0; k < nt; k++) sx += sp[k];
-    if (!(fx == fx)) break;
-    if (fabs(fx) <= 0.25 * TOL) {
-      root = x;
-      sroot = sx;
-      found = true;
-      break;
-    }
-    if (fx > 0.0) lo = x; else hi = x;
-    double xn = (sx > 0.0) ? x + fx / sx : (fx > 0.0 ? 2.0 * x : 0.5 * x);
-    if (!(xn == xn)) break;
-    if (xn > 4.0 * x) xn = 4.0 * x;
-    if (xn < 0.25 * x) xn = 0.25 * x;
-    if (lo > 0.0 && hi > 0.0) {
-      if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-      if (!(xn > lo && xn < hi)) break;  // the bracket has closed to neighbouring doubles without meeting the tolerance
-    }
-    if (xn < 1e-300 || xn > 1e300) break;
-    x = xn;
-  }
-  if (!found || !(sroot > 0.0)) {
-    LG_FF_COUNT(declined, 1);
-    LG_FF_COUNT(evals_ff, evals);
-    q = q0;
-    q.no_ff = true;
-    return false;
-  }
-  // ---- 2. the bracket: mass error above the tolerance (with margin) at a, below minus the tolerance at b ----
-  const double w = TOL / sroot;
-  double a = 0.0, b = 0.0, sla[Ev::kMaxTerms], slb[Ev::kMaxTerms];
-  bool ok = false;
-  for (int tr = 0, mul = 1; tr < 3 && !ok; tr++, mul *= 2) {
-    a = root - 1.3 * mul * w;
-    b = root + 1.3 * mul * w;
-    if (!(a > 0.0) || !(a < root) || !(b > root)) break;
-    const double fa = ev.mass(a, sla, &pasta) - prior;
-    const double fb = ev.mass(b, slb, &pastb) - prior;
-    evals += 2;
-    ok = (fa >= TOL + LG_FF_MARGIN) && (fb <= -(TOL + LG_FF_MARGIN));
-  }
-  if (!ok) {
-    LG_FF_COUNT(declined, 1);
-    LG_FF_COUNT(evals_ff, evals);
-    q = q0;
-    q.no_ff = true;
-    return false;
-  }
-  // ---- 3. the walk ----
-  // Zone Z = [zlo, zhi] with slope bounds g <= |d mass / d psi| <= G on it; only the armed no-change exit needs it.  It is laid
+  int newton_it = 0;
+  // bracket
+  double root = 0.0, w = 0.0, a = 0.0, b = 0.0, fa = 0.0;
+  int tries = 0;
+  double mul = 1.0;
+  // zone Z = [zlo, zhi] with slope bounds g <= |d mass / d psi| <= G on it; only the armed no-change exit needs it.  It is laid
   // round a pair of trips when that pair has to be told apart (2 evaluations), and kept while the walk stays inside it -- after
   // the first turn of the search every later trip lies within one step of the root, so one or two zones serve a whole search.
-  double zlo = 0.0, zhi = -1.0, g = 0.0, G = 0.0;
+  double zlo = 0.0, zhi = -1.0, g = 0.0, G = 0.0, nlo = 0.0, nhi = 0.0;
+  unsigned pz0 = 0;
   int zones = 0;
+  // walk
   int clo = q.count_no_mass_change, chi = q.count_no_mass_change;
   // The record the walk starts from carries a mass the CALLER computed (from stored thetas, possibly clamped), not mass(x0):
   // the first pair of trips is never certified (prev_psi = NaN fails every comparison).
-  double prev_psi = lgp_double(0x7ff8000000000000ULL);
-  int prev_side = (q.new_mass > prior) ? 1 : -1;
+  double prev_psi = lgp_double(0x7ff8000000000000ULL), psi = 0.0;
+  int prev_side = (q.new_mass > prior) ? 1 : -1, side = 0, cur_side = 0;
   bool prev_exact = true;  // q.delta_mass_prev is the exact value of the state the walk starts from
-  for (;;) {
-    lg_digit_pre(q, q.new_mass > prior);
-    LG_FF_COUNT(trips, 1);
-    const double psi = q.psi_loc;
-    const int side = (psi <= a) ? 1 : (psi >= b) ? -1 : 0;
-    const bool psi_exit = lg_digit_brk_first(q) || lg_digit_brk_other(q);
-    const bool skip = side != 0 && !psi_exit;
-    int cur_side = side;
-    if (!skip) {
-      ev.trip(q);
-      evals++;
-      cur_side = (q.new_mass > prior) ? 1 : -1;
-    }
-    const bool first = !skip && lg_digit_brk_first(q);
-    bool brk = first;
-    if (gate && !first) {
-      // the no-change counter after this trip
-      if (!skip && prev_exact) {
-        if (fabs(q.delta_mass - q.delta_mass_prev) < 1E-15) {
-          clo++;
-          chi++;
-        } else {
-          clo = chi = 0;
+  bool skip = false;
+  int evals = 0;
+
+  // runs the walk until it needs an evaluation (returns true: st, xr set) or is over (returns false: result set)
+  auto advance = [&]() -> bool {
+    for (;;) {
+      if (wphase == W_BEGIN) {
+        lg_digit_pre(q, q.new_mass > prior);
+        LG_FF_COUNT(trips, 1);
+        psi = q.psi_loc;
+        side = (psi <= a) ? 1 : (psi >= b) ? -1 : 0;
+        const bool psi_exit = lg_digit_brk_first(q) || lg_digit_brk_other(q);
+        skip = side != 0 && !psi_exit;
+        cur_side = side;
+        if (!skip) {  // a trip inside the bracket, or one that ends the search: evaluated as the reference does
+          st = S_TRIP;
+          xr = psi;
+          wphase = W_AFTER_EVAL;
+          return true;
         }
-      } else {
-        // at least one of the two mass errors is not known: can they be within 1e-15 of each other?  Not if both trips lie in a
-        // zone with slope bounds and are far enough apart (same side), or at clearly different distances from the root
-        // (opposite sides).  Both errors are above the tolerance here (a skipped trip by the bracket, an exact one because the
-        // search goes on), so on the same side |delta_k - delta_{k-1}| is the change of the mass itself.
-        bool apart = false;
-        if (prev_psi == prev_psi && (skip || q.delta_mass > TOL)) {
-          for (int pass = 0; pass < 2 && !apart; pass++) {
+        wphase = W_BOOK;
+      }
+      if (wphase == W_AFTER_EVAL) {
+        cur_side = (q.new_mass > prior) ? 1 : -1;
+        wphase = W_BOOK;
+      }
+      // W_BOOK / W_RECHECK: the no-change counter after this trip, then the end of the trip
+      const bool first = !skip && lg_digit_brk_first(q);
+      bool brk = first;
+      if (gate && !first) {
+        if (!skip && prev_exact) {
+          if (fabs(q.delta_mass - q.delta_mass_prev) < 1E-15) {
+            clo++;
+            chi++;
+          } else {
+            clo = chi = 0;
+          }
+        } else {
+          // at least one of the two mass errors is not known: can they be within 1e-15 of each other?  Not if both trips lie in a
+          // zone with slope bounds and are far enough apart (same side), or at clearly different distances from the root
+          // (opposite sides).  Both errors are above the tolerance here (a skipped trip by the bracket, an exact one because the
+          // search goes on), so on the same side |delta_k - delta_{k-1}| is the change of the mass itself.
+          bool apart = false;
+          if (prev_psi == prev_psi && (skip || q.delta_mass > TOL)) {
             const bool inz = psi >= zlo && psi <= zhi && prev_psi >= zlo && prev_psi <= zhi;
             if (inz) apart = (cur_side == prev_side) ? (g * fabs(psi - prev_psi) >= LG_FF_NOSTALL) : lg_ff_apart(psi, prev_psi, a, b, g, G);
-            if (apart || pass == 1 || zones >= 8) break;
-            if (inz && !(G > 1.5 * g)) break;  // the bounds are as tight as they get: this pair simply is not told apart
-            // lay a new zone round this pair and the bracket, with room for one more step in the direction of the walk
-            const double step = fabs(psi - prev_psi);
-            const double pad_lo = (psi < prev_psi ? 1.01 : 0.11) * step, pad_hi = (psi > prev_psi ? 1.01 : 0.11) * step;
-            double nlo = fmin(fmin(psi, prev_psi), a) - pad_lo, nhi = fmax(fmax(psi, prev_psi), b) + pad_hi;
-            if (!(nlo > 0.5 * fmin(fmin(psi, prev_psi), a))) nlo = 0.5 * fmin(fmin(psi, prev_psi), a);
-            if (!(nlo > 0.0) || !(nhi < 1e300)) break;
-            unsigned p0 = 0, p1 = 0;
-            (void)ev.mass(nlo, slz[0], &p0);
-            (void)ev.mass(nhi, slz[1], &p1);
-            evals += 2;
-            zones++;
-            g = 0.0;
-            G = 0.0;
-            for (int k = 0; k < nt; k++) {
-              g += fmin(slz[0][k], slz[1][k]);
-              G += (((p0 ^ p1) >> k) & 1u) ? ev.term_slope_max(k) : fmax(slz[0][k], slz[1][k]);
+            if (!apart && wphase == W_BOOK && zones < 8 && !(inz && !(G > 1.5 * g))) {
+              // lay a new zone round this pair and the bracket, with room for one more step in the direction of the walk
+              const double step = fabs(psi - prev_psi);
+              const double pad_lo = (psi < prev_psi ? 1.01 : 0.11) * step, pad_hi = (psi > prev_psi ? 1.01 : 0.11) * step;
+              nlo = fmin(fmin(psi, prev_psi), a) - pad_lo;
+              nhi = fmax(fmax(psi, prev_psi), b) + pad_hi;
+              if (!(nlo > 0.5 * fmin(fmin(psi, prev_psi), a))) nlo = 0.5 * fmin(fmin(psi, prev_psi), a);
+              if (nlo > 0.0 && nhi < 1e300) {
+                st = S_ZONE_LO;
+                xr = nlo;
+                wphase = W_RECHECK;  // where the walk resumes once both ends of the zone are evaluated
+                return true;
+              }
             }
-            g *= 0.9;
-            G *= 1.1;
-            zlo = nlo;
-            zhi = nhi;
+          }
+          if (apart) {
+            clo = chi = 0;
+          } else {
+            clo = 0;
+            chi++;
           }
         }
-        if (apart) {
-          clo = chi = 0;
-        } else {
-          clo = 0;
-          chi++;
-#ifdef LGAR_FF_DEBUG
-          if (chi >= 5) fprintf(stderr, "ff fallback: iter %d psi %.17g prev %.17g a %.17g b %.17g zlo %g zhi %g g %g G %g side %d prev_side %d factor %g root %.17g w %g zones %d\n", q.iter, psi, prev_psi, a, b, zlo, zhi, g, G, cur_side, prev_side, q.factor, root, w, zones);
-#endif
+        if (!skip && clo == 5 && chi == 5) {
+          brk = true;
+        } else if (clo <= 5 && chi >= 5) {  // the no-change exit can neither be ruled out nor confirmed: walk the plain way
+          result = R_FALLBACK;
+          return false;
         }
       }
-      if (!skip && clo == 5 && chi == 5) brk = true;
-      else if (clo <= 5 && chi >= 5) break;  // the no-change exit can neither be ruled out nor confirmed: walk the plain way
-    }
-    if (skip) {
-      q.new_mass = (side > 0) ? prior + 1.0 : prior - 1.0;  // only its order relative to the prior mass is read
+      wphase = W_BEGIN;
+      if (skip) {
+        q.new_mass = (side > 0) ? prior + 1.0 : prior - 1.0;  // only its order relative to the prior mass is read
+        prev_psi = psi;
+        prev_side = side;
+        prev_exact = false;
+        continue;
+      }
+      if (!brk) brk = !first && lg_digit_brk_other(q);
+      if (!brk) q.delta_mass_prev = q.delta_mass;
+      if (brk || !(q.delta_mass > TOL)) {
+        q.done = true;
+        q.count_no_mass_change = clo;
+        result = R_DONE;
+        return false;
+      }
       prev_psi = psi;
-      prev_side = side;
-      prev_exact = false;
-      continue;
+      prev_side = cur_side;
+      prev_exact = true;
     }
-    if (!brk) brk = !first && lg_digit_brk_other(q);
-    if (!brk) q.delta_mass_prev = q.delta_mass;
-    if (brk || !(q.delta_mass > TOL)) {
-      q.done = true;
-      q.count_no_mass_change = clo;
-      LG_FF_COUNT(ff_done, 1);
-      LG_FF_COUNT(evals_ff, evals);
-      return true;
+  };
+
+  for (;;) {
+    // ---- the one evaluation site ----
+    unsigned pm = 0;
+    double th = 0.0;
+    const double m = ev.eval(xr, st == S_ZONE_HI ? slz : sl, &pm, &th);
+    evals++;
+    bool more = true;
+    if (st == S_NEWTON) {
+      // root of f(psi) = mass(psi) - prior by a safeguarded Newton iteration, started at the current psi
+      const double fx = m - prior;
+      double sx = 0.0;
+      for (int k = 0; k < nt; k++) sx += sl[k];
+      if (!(fx == fx)) {
+        result = R_DECLINED;
+        more = false;
+      } else if (fabs(fx) <= 0.25 * TOL) {
+        root = xr;
+        w = (sx > 0.0) ? TOL / sx : 0.0;
+        a = root - 1.3 * w;
+        b = root + 1.3 * w;
+        if (!(sx > 0.0) || !(a > 0.0) || !(a < root) || !(b > root)) {
+          result = R_DECLINED;
+          more = false;
+        } else {
+          st = S_BR_A;
+          xr = a;
+        }
+      } else {
+        if (fx > 0.0) lo = xr; else hi = xr;
+        double xn = (sx > 0.0) ? xr + fx / sx : (fx > 0.0 ? 2.0 * xr : 0.5 * xr);  // f decreases: f' = -sx
+        if (xn > 4.0 * xr) xn = 4.0 * xr;
+        if (xn < 0.25 * xr) xn = 0.25 * xr;
+        if (lo > 0.0 && hi > 0.0 && !(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+        newton_it++;
+        if (!(xn == xn) || newton_it >= LG_FF_MAX_NEWTON || xn < 1e-300 || xn > 1e300 || (lo > 0.0 && hi > 0.0 && !(xn > lo && xn < hi))) {
+          result = R_DECLINED;  // no root in reach (the search is heading for psi = 0 or for the upper limit), or a bracket closed
+          more = false;         // to neighbouring doubles without meeting a quarter of the tolerance
+        } else {
+          xr = xn;
+        }
+      }
+    } else if (st == S_BR_A) {
+      // the bracket: mass error above the tolerance (with margin) at a, below minus the tolerance at b
+      fa = m - prior;
+      st = S_BR_B;
+      xr = b;
+    } else if (st == S_BR_B) {
+      const double fb = m - prior;
+      if ((fa >= TOL + LG_FF_MARGIN) && (fb <= -(TOL + LG_FF_MARGIN))) {
+        more = advance();
+      } else {
+        tries++;
+        mul *= 2.0;
+        a = root - 1.3 * mul * w;
+        b = root + 1.3 * mul * w;
+        if (tries >= 3 || !(a > 0.0)) {
+          result = R_DECLINED;
+          more = false;
+        } else {
+          st = S_BR_A;
+          xr = a;
+        }
+      }
+    } else if (st == S_ZONE_LO) {
+      pz0 = pm;
+      st = S_ZONE_HI;
+      xr = nhi;
+    } else if (st == S_ZONE_HI) {
+      g = 0.0;
+      G = 0.0;
+      for (int k = 0; k < nt; k++) {
+        g += fmin(sl[k], slz[k]);
+        G += (((pz0 ^ pm) >> k) & 1u) ? ev.term_slope_max(k) : fmax(sl[k], slz[k]);
+      }
+      g *= 0.9;
+      G *= 1.1;
+      zlo = nlo;
+      zhi = nhi;
+      zones++;
+      more = advance();
+    } else {  // S_TRIP: the evaluation of the trip at q.psi_loc
+      q.theta_store(th);
+      q.new_mass = m;
+      q.delta_mass = fabs(m - prior);
+      more = advance();
     }
-    prev_psi = psi;
-    prev_side = cur_side;
-    prev_exact = true;
+    if (!more) break;
   }
-  LG_FF_COUNT(fallback, 1);
   LG_FF_COUNT(evals_ff, evals);
+  if (result == R_DONE) {
+    LG_FF_COUNT(ff_done, 1);
+    return true;
+  }
+  if (result == R_DECLINED) LG_FF_COUNT(declined, 1); else LG_FF_COUNT(fallback, 1);
   q = q0;
   q.no_ff = true;
   return false;
@@ -404,12 +463,13 @@ struct LgSearchModel {
   }
   LG_MFN int terms() const { return q->layer_num; }
   LG_MFN double term_slope_max(int k) const { const int l = k == 0 ? q->layer_num : k; return q->dz[l] * cls->lay[l].slope_max; }
-  LG_MFN_NOINLINE double mass(double psi, double* sl, unsigned* past) const {   // lg_search_eval at psi (out of line: six call sites)
+  LG_MFN_NOINLINE double eval(double psi, double* sl, unsigned* past, double* theta_out) const {   // lg_search_eval at psi
     const int layer_num = q->layer_num;
     double s;
     bool pm;
     unsigned pb = 0;
     const double theta = lg_theta_and_slope(psi, cls->lay[layer_num], &s, &pm);
+    *theta_out = theta;
     pb |= pm ? 1u : 0u;
     sl[0] = q->dz[layer_num] * s;
     double mass_layers = 0.0;
@@ -423,7 +483,6 @@ struct LgSearchModel {
     *past = pb;
     return mass_layers;
   }
-  LG_MFN void trip(LgSearch& qq) const { lg_search_eval(qq, *cls); }
 };
 #endif
 
@@ -534,8 +593,9 @@ struct LgCorrModel {
   LG_MFN bool monotone() const { return ok; }
   LG_MFN int terms() const { return LGAR_MAXL + 1; }
   LG_MFN double term_slope_max(int t) const { return coef[t] * cls->lay[t].slope_max; }
-  LG_MFN_NOINLINE double mass(double psi, double* sl, unsigned* past) const {   // lg_corr_eval at psi
+  LG_MFN_NOINLINE double eval(double psi, double* sl, unsigned* past, double* theta_out) const {   // lg_corr_eval at psi
     LgFronts& F = *f;
+    *theta_out = 0.0;
     for (int l = 0; l <= LGAR_MAXL; l++) sl[l] = 0.0;
     unsigned pb = 0;
 #pragma unroll 1
@@ -551,7 +611,6 @@ struct LgCorrModel {
     *past = pb;
     return lg_corr_list_mass(F, *cls);
   }
-  LG_MFN void trip(LgCorr& kk) const { lg_corr_eval(kk, *f, *cls); }
 };
 #endif
 

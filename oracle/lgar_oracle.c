@@ -373,6 +373,16 @@ static double theta_mass_balance(ctx_t* c, int layer_num, double psi_cm, double 
     delta_mass_prev = delta_mass;
   }
 
+  { /* which exit ended the loop (instrumentation; the conditions are those of the loop, in its order) */
+    lgo_state* st = c->s;
+    st->n_path[LGO_PATH_SEARCH]++;
+    if (!(delta_mass > MBAL_ITERATIVE_TOLERANCE)) st->n_path[LGO_PATH_SEARCH_CONVERGED]++;
+    else if (fabs(psi_cm_loc - psi_cm_loc_prev) < 1E-15 && factor < 1E-13) st->n_path[LGO_PATH_SEARCH_STEP_EXIT]++;
+    else if (count_no_mass_change == break_no_mass_change && precip_mass_to_add < 1.E-12) st->n_path[LGO_PATH_SEARCH_NOCHANGE]++;
+    else if (iter > MAX_ITER_MBAL_LOOP) st->n_path[LGO_PATH_SEARCH_MAXITER]++;
+    else if ((psi_cm_loc > PSI_UPPER_LIM) && (iter > first_speedup_thresh)) st->n_path[LGO_PATH_SEARCH_PSI_UPPER]++;
+    else st->n_path[LGO_PATH_SEARCH_PSI_ZERO]++;
+  }
   if ((delta_mass > MBAL_ITERATIVE_TOLERANCE) && (!wanted_to_saturate_flag))
     *AET_demand_cm = *AET_demand_cm - fabs(delta_mass - MBAL_ITERATIVE_TOLERANCE);
   if ((theta >= sp->theta_e) && (psi_cm_loc != 0.0)) *AET_demand_cm = 0.0;
@@ -592,6 +602,7 @@ static void cross_layer_boundary(ctx_t* c) {
         prior_mass = mass_bal(c);
         if (ct->depth > cum[num_layers] && ct->layer == num_layers && wf == front_for_cross) {
           double current_mass;
+          s->n_path[LGO_PATH_CROSS_LAYER_BOTTOM]++;
           ct->depth = cum[num_layers] + 1.E-6;
           theta_mass_balance_correction(c, wf, prior_mass);
           current_mass = mass_bal(c);
@@ -735,6 +746,7 @@ static void clean_redundant_fronts(ctx_t* c) {
   for (wf = 1; wf != s->n; wf++) {
     int nx = cur + 1;
     if ((s->f[cur].layer == s->f[nx].layer) && (fabs(s->f[cur].theta - s->f[nx].theta) < THRESHOLD_NO_MOISTURE_DIFF)) {
+      s->n_path[LGO_PATH_CLEAN_REDUNDANT]++;
       front_delete(c, cur);
       break;
     }
@@ -848,6 +860,7 @@ static double move_wetting_fronts(ctx_t* c, double timestep_h, double* free_drai
             double mass_before = mass_bal(c) - s->f[ci].depth * (s->f[ci].theta -
                                  (prior_mass / s->f[ci].depth + s->f[ni].theta));
             double mass_after;
+            s->n_path[LGO_PATH_THETA_R_DELETE]++;
             front_delete(c, ci); /* `current` becomes the old `next`, which now sits at index ci */
             mass_after = mass_bal(c);
             *AET_demand_cm = *AET_demand_cm - fabs(mass_before - mass_after);
@@ -917,6 +930,7 @@ static double move_wetting_fronts(ctx_t* c, double timestep_h, double* free_drai
             factor = factor / fabs(s->f[fdi].theta - s->f[fdi + 1].theta);
         }
         depth_new = s->f[fdi].depth;
+        if (fabs(mass_balance_error) > MBAL_ITERATIVE_TOLERANCE) s->n_path[LGO_PATH_SATURATED_DEPTH]++;
         while (fabs(mass_balance_error) > MBAL_ITERATIVE_TOLERANCE) {
           iter++;
           if (iter > MAX_ITER_SATURATION_MBAL_LOOP) {
@@ -967,6 +981,7 @@ static double move_wetting_fronts(ctx_t* c, double timestep_h, double* free_drai
   correction = correction_type_surf(c);
   while (correction != 0) {
     if (s->status & (LGO_FAIL_LIST | LGO_FAIL_OVERFLOW)) break;
+    s->n_path[correction == 1 ? LGO_PATH_MERGE : correction == 2 ? LGO_PATH_CROSS_LAYER : correction == 3 ? LGO_PATH_CROSS_BOTTOM : LGO_PATH_DRY_OVER_WET]++;
     if (correction == 1) merge_wetting_fronts(c);
     if (correction == 2) {
       double mass_before = mass_bal(c), mass_after;
@@ -1093,6 +1108,8 @@ static void create_surficial_front(ctx_t* c, double* ponded_depth_cm, double* vo
   double theta_e = sp->theta_e, theta_r = sp->theta_r;
   double delta_theta = theta_e - theta1;
   double theta_new, Se;
+  int lgo_path_note_ = (int)(c->s->n_path[LGO_PATH_SURFICIAL]++);
+  (void)lgo_path_note_;
   if (dry_depth * delta_theta > (*ponded_depth_cm)) {
     *volin = *ponded_depth_cm;
     theta_new = fmin(theta1 + (*ponded_depth_cm) / dry_depth, theta_e);
@@ -1438,6 +1455,7 @@ int lgo_update(const lgo_params* p, lgo_state* s, double precipitation_mm_per_h,
       double theta_e, theta_above_which_precip_contribs_to_GW, delta_theta, dry_depth;
 
       s->n_active_substeps++;
+      s->n_path[LGO_PATH_ACTIVE_STEP]++;
       for (k = 1; k < num_layers + 1; k++)
         min_storage += p->soil[k].theta_r * (p->cum_thickness[k] - p->cum_thickness[k - 1]);
       wf_free_drainage_demand = wf_free_drainage(c);

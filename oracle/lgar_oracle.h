@@ -72,6 +72,30 @@ typedef struct {
   double giuh[LGO_MAX_GIUH];   /* 0-based copy (bmi_lgar.cxx:105-107) */
 } lgo_params;
 
+/* path counters: evidence that the tests reach the reference's rare branches (reference file:line in the comments) */
+enum {
+  LGO_PATH_MERGE = 0,          /* lgar_merge_wetting_fronts, lgar.cxx:1875-1953 (correction type 1) */
+  LGO_PATH_CROSS_LAYER,        /* lgar_wetting_fronts_cross_layer_boundary, :1963-2167 (type 2) */
+  LGO_PATH_CROSS_BOTTOM,       /* lgar_wetting_front_cross_domain_boundary, :2176-2251 (type 3) */
+  LGO_PATH_DRY_OVER_WET,       /* lgar_fix_dry_over_wet_wetting_fronts, :2260-2307 (type 4) */
+  LGO_PATH_THETA_R_DELETE,     /* front deleted because theta < theta_r, :1519-1537 */
+  LGO_PATH_SATURATED_DEPTH,    /* saturated front deepened until the mass balance closes, :1687-1723 */
+  LGO_PATH_CROSS_LAYER_BOTTOM, /* layer crossing that also passes the domain bottom: depth search, :2090-2159 */
+  LGO_PATH_SURFICIAL,          /* lgar_create_surficial_front, :2490-2568 */
+  LGO_PATH_CLEAN_REDUNDANT,    /* lgar_clean_redundant_fronts deletes a front, :3171-3195 */
+  LGO_PATH_SEARCH,             /* lgar_theta_mass_balance iterates, :2990 */
+  LGO_PATH_SEARCH_CONVERGED,   /* ... and ends within the tolerance */
+  LGO_PATH_SEARCH_STEP_EXIT,   /* ... on |psi - psi_prev| < 1e-15 and factor < 1e-13, :3063 */
+  LGO_PATH_SEARCH_NOCHANGE,    /* ... on five trips without mass change, :3070-3076 */
+  LGO_PATH_SEARCH_MAXITER,     /* ... on the trip limit, :3078 */
+  LGO_PATH_SEARCH_PSI_UPPER,   /* ... on psi > 1e7 after 1000 trips, :3081 */
+  LGO_PATH_SEARCH_PSI_ZERO,    /* ... on psi <= 0 twice, :3084 */
+  LGO_PATH_CORR_SEARCH,        /* lgar_theta_mass_balance_correction iterates, :3307 */
+  LGO_PATH_CACHED_STEP,        /* sub-step that replays cached fluxes, bmi_lgar.cxx:683-695 */
+  LGO_PATH_ACTIVE_STEP,        /* sub-step that computes fluxes */
+  LGO_NPATH = 24
+};
+
 /* everything that survives between Update() calls (SURVEY.md a-S) */
 typedef struct {
   int n;
@@ -91,6 +115,8 @@ typedef struct {
   int status;
   /* instrumentation (not part of the model) */
   long long n_theta_calls, n_tmb_iters, n_active_substeps;
+  /* how often each rare path of the reference ran (same numbering as LGAR_PATH_* in lgar_c_b200/csrc/lgar_types.h) */
+  long long n_path[LGO_NPATH];
 } lgo_state;
 
 /* order of the 12 per-step scalars, all in metres (bmi_lgar.cxx:882-893):

@@ -88,6 +88,7 @@ class State(C.Structure):
         ("timesteps", C.c_longlong),
         ("status", C.c_int),
         ("n_theta_calls", C.c_longlong), ("n_tmb_iters", C.c_longlong), ("n_active_substeps", C.c_longlong),
+        ("n_path", C.c_longlong * 24),
     ]
 
 

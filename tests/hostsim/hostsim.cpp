@@ -82,16 +82,12 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
       w.nf_sink = nfs.data();
       if (force_all_active >= 4) {
         // lane-program emulation: one lane walks the stages of lgar_lanes.cuh
-        w.force_all_active = (force_all_active == 5 || force_all_active == 7);
+        w.force_all_active = (force_all_active == 5);
         int32_t counter = 0;
         w.tile_counter = &counter;
         static LgLane L;  // large: keep it off the stack
         L.stage = LG_ST_FETCH; L.col = -1; L.t = nsteps;
         while (L.stage != LG_ST_DONE) {
-          if (force_all_active >= 6 && L.stage == LG_ST_HEAD) {  // fused step (the STEP kernel of the wavefront scheduler)
-            lg_stage_step(cfg, d, w, L, nullptr);
-            continue;
-          }
           switch (L.stage) {
             case LG_ST_FETCH: lg_stage_fetch(cfg, d, w, L, nullptr); break;
             case LG_ST_HEAD: lg_stage_head(cfg, d, w, L, nullptr); break;

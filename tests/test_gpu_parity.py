@@ -151,7 +151,7 @@ def test_window_and_lanes_kernels_equal_hourly_kernels(cuda_device, tmp_path):
     Pm = np.ascontiguousarray(np.stack([np.roll(g["precip"], -int(s))[:T] for s in shifts], axis=1))
     Em = np.ascontiguousarray(np.stack([np.roll(g["pet"], -int(s))[:T] for s in shifts], axis=1))
     res = []
-    for window in (5, 3, 2, 1, 0):
+    for window in (3, 2, 1, 0):
         b = lgar_c_b200.BmiLGARBatch()
         b.initialize(cfg, ncol)
         b.set_window_mode(window)

@@ -40,13 +40,12 @@ def run(lib, cfg, P, E, force, cap=16):
     return done, scal, nf, fr, fl, st.value
 
 
-@pytest.mark.parametrize("mode", [2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("mode", [2, 3, 4, 5])
 @pytest.mark.parametrize("name", STANDARD + RANDOM)
 def test_window_stepping_equals_hourly_stepping(hostsim, name, mode, tmp_path):
     """The window kernel's per-column functions (modes 2/3: advance through cached hours in registers,
-    active step at the column's own hour), the staged lane program of lgar_lanes.cuh (modes 4/5:
-    FETCH/HEAD/FRONT/SEARCH/TAIL) and its fused form (modes 6/7: FETCH + lg_stage_step, what the STEP kernel runs) must
-    reproduce hour-by-hour stepping bit for bit."""
+    active step at the column's own hour) and the staged lane program of lgar_lanes.cuh (modes 4/5:
+    FETCH/HEAD/FRONT/SEARCH/TAIL) must reproduce hour-by-hour stepping bit for bit."""
     g = load_golden(name)
     n = min(len(g["precip"]), 2000)
     cfg = config_for(name, tmp_path)
@@ -88,7 +87,7 @@ def test_fast_search_path_reproduces_the_plain_walk(tmp_path):
     for name in STANDARD + RANDOM:
         g = load_golden(name)
         n = min(len(g["precip"]), 3000)
-        for force in (0, 4, 6):
+        for force in (0, 4):
             done, scal, nf, fr, fl, status = run(lib, config_for(name, tmp_path), g["precip"][:n], g["pet"][:n], force)
             assert done == n and np.array_equal(nf, g["nfronts"][:n]) and np.array_equal(scal, g["scalars"][:n]), (name, force)
     st = (C.c_longlong * 8)()

@@ -360,7 +360,7 @@ def main():
     ap.add_argument("--batch", type=int, default=250_000)
     ap.add_argument("--chunk", type=int, default=240)
     ap.add_argument("--steps", type=int, default=0, help="0: the config's full duration")
-    ap.add_argument("--mode", type=int, default=5)
+    ap.add_argument("--mode", type=int, default=3)
     ap.add_argument("--cores", type=int, default=0)
     ap.add_argument("--selftest", action="store_true")
     ap.add_argument("--selfnoise", action="store_true",
