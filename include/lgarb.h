@@ -249,6 +249,12 @@ int lgarb_measure_fp64_peak(lgarb_engine* e, double ms, double* tflops);
  * bit.  which = 0: the out-of-line function every cold call site uses, 1: the inlined common case of the psi search with its
  * fall-back to the former. */
 int lgarb_debug_pow(lgarb_engine* e, int64_t n, const double* x, const double* y, double* out, int which);
+/* Path counters: how often the rare branches of the reference ran since they were switched on (merge, layer crossing, domain
+ * bottom crossing, dry-over-wet, theta < theta_r deletion, saturated-front depth loop, ..., every exit of the psi search; the
+ * LGAR_PATH_* numbering of lgar_c_b200/csrc/lgar_types.h = LGO_PATH_* of oracle/lgar_oracle.h; reference src/lgar.cxx:1519-1537,
+ * 1687-1723,1875-2307,3063-3086,3116-3195).  Evidence for tests, off by default (one predicated atomic per rare event when on). */
+int lgarb_set_path_counters(lgarb_engine* e, int on);
+int lgarb_get_path_counters(lgarb_engine* e, uint64_t* out, int n);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,12 @@ def _config_num_layers(config_file):
     return -1
 
 
+# lgar_c_b200/csrc/lgar_types.h LGAR_PATH_* (= oracle/lgar_oracle.h LGO_PATH_*)
+PATH_NAMES = ("merge", "cross_layer", "cross_bottom", "dry_over_wet", "theta_r_delete", "saturated_depth", "cross_layer_bottom", "surficial",
+              "clean_redundant", "search", "search_converged", "search_step_exit", "search_nochange", "search_maxiter", "search_psi_upper",
+              "search_psi_zero", "corr_search", "cached_step", "active_step")
+
+
 class LgarbError(RuntimeError):
     pass
 
@@ -129,6 +135,8 @@ def _load():
         "lgarb_get_stream": ([vp], vp),
         "lgarb_measure_fp64_peak": ([vp, C.c_double, dp], C.c_int),
         "lgarb_debug_pow": ([vp, C.c_int64, vp, vp, vp, C.c_int], C.c_int),
+        "lgarb_set_path_counters": ([vp, C.c_int], C.c_int),
+        "lgarb_get_path_counters": ([vp, C.POINTER(C.c_uint64), C.c_int], C.c_int),
         "lgarb_set_profiling": ([vp, C.c_int], C.c_int),
         "lgarb_get_profile": ([vp, dp], C.c_int),
     }
@@ -486,6 +494,15 @@ class BmiLGARBatch:
         out = C.c_double(0.0)
         self._ck(self._L.lgarb_measure_fp64_peak(self._h, float(ms), C.byref(out)))
         return out.value
+
+    def set_path_counters(self, on=True):
+        self._ck(self._L.lgarb_set_path_counters(self._h, int(bool(on))))
+
+    def get_path_counters(self):
+        """dict name -> count of the rare paths of the reference taken since set_path_counters(True) (lgar_types.h LGAR_PATH_*)"""
+        out = (C.c_uint64 * len(PATH_NAMES))()
+        self._ck(self._L.lgarb_get_path_counters(self._h, out, len(PATH_NAMES)))
+        return dict(zip(PATH_NAMES, [int(x) for x in out]))
 
     def debug_pow(self, x, y, which=0):
         """The engine's device pow on host arrays (lgarb_debug_pow): for the test that compares it with the host's pow."""

@@ -110,6 +110,8 @@ struct lgarb_engine {
   cudaStream_t side_stream = nullptr;
   cudaEvent_t side_ev[2] = {nullptr, nullptr};
   int wave_finish_below = 16384;
+  int wave_ff_below = 65536;   // rounds with at most this many slots in flight run their psi searches through the fast path (lgar_search.cuh)
+  unsigned long long* d_paths = nullptr;  // [LGAR_NPATH] path counters, allocated by lgarb_set_path_counters
   int finish_lane_stride = 4;  // finishing kernel: one slot per this many lanes
   int sm_count = 0;            // multiprocessors of the device: grids are sized in multiples of it
   int update_wave_min_cols = 1 << 30;  // lgarb_update: batches of at least this many columns take the wavefront kernels
@@ -155,6 +157,7 @@ struct lgarb_engine {
   void release() {
     if (stream) cudaStreamSynchronize(stream);
     d_work_trace = nullptr;
+    d_paths = nullptr;
     wave_ready = false;
     if (d_host_series) cudaFree(d_host_series);
     d_host_series = nullptr;
@@ -586,6 +589,7 @@ void launch_step(lgarb_engine* e, const double* d_precip, const double* d_pet, c
   LgarDeviceState d = e->d;
   d.precip = d_precip;
   d.pet = d_pet;
+  d.paths = e->d_paths;
   cudaEvent_t* ev = nullptr;
   if (e->profiling) {
     if (e->ev_used + 3 > e->ev_pool.size()) {
@@ -811,6 +815,7 @@ int lgarb_create(lgarb_engine** out) {
   knob("LGARB_WAVE_CORR_PAIRS", (*out)->wave_corr_pairs);
   knob("LGARB_WAVE_CORR_ASYNC", (*out)->wave_corr_async);
   knob("LGARB_WAVE_FINISH_BELOW", (*out)->wave_finish_below);
+  knob("LGARB_WAVE_FF_BELOW", (*out)->wave_ff_below);
   knob("LGARB_FINISH_LANE_STRIDE", (*out)->finish_lane_stride);
   knob("LGARB_UPDATE_WAVE_MIN_COLS", (*out)->update_wave_min_cols);
   knob("LGARB_WAVE_ESCALATE_BELOW", (*out)->wave_escalate_below);
@@ -912,6 +917,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
   const LgarWave& wv = e->wave;
   w.tile_counter = e->d_tile_counter;
   w.done_columns = wv.done_columns;
+  w.paths = e->d_paths;
   CUDA_TRY(cudaMemsetAsync(e->d_tile_counter, 0, sizeof(int32_t), e->stream));
   w.slot_is_column = (wv.nslots == e->ncol) ? 1 : 0;
   CUDA_TRY(lgar_launch_wave_init(e->cfg, e->d, wv, w.slot_is_column, e->stream));
@@ -979,6 +985,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       if (in_flight == 0) break;
       if (in_flight <= e->wave_finish_below) {  // the stragglers: one thread per slot runs its column to the end of the window
         if (debug) cudaEventRecord(dbg[0], e->stream);
+        w.use_ff = 1;
         CUDA_TRY(lgar_launch_wave_finish(e->cfg, e->d, w, wv, in_flight, e->finish_lane_stride, e->sm_count, e->stream));
         e->launches += 2;
         if (debug) {
@@ -1001,6 +1008,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       cudaStreamSynchronize(e->stream);
       cudaProfilerStart();
     }
+    w.use_ff = in_flight <= e->wave_ff_below ? 1 : 0;  // the lambdas above launch with `w` as it is now
     const bool new_steps = cnt[LG_ST_FETCH] + cnt[LG_ST_HEAD] > 0;
     const bool corr_async = e->use_window == 3 && e->wave_corr_async && !dbg_on;
     bool corr_forked = false;
@@ -1570,6 +1578,25 @@ int lgarb_get_warp_times(lgarb_engine* e, uint32_t* out16384) {
     require_init(e);
     if (!e->d_work_trace) throw std::runtime_error("work trace is off");
     d2h(e, out16384, e->d_work_trace + 2 * e->stride + 64, 2 * 8192 * sizeof(uint32_t));
+  });
+}
+int lgarb_set_path_counters(lgarb_engine* e, int on) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (on && !e->d_paths) e->d_paths = e->dalloc<unsigned long long>(LGAR_NPATH);
+    if (on) CUDA_TRY(cudaMemsetAsync(e->d_paths, 0, LGAR_NPATH * sizeof(unsigned long long), e->stream));
+    if (!on) e->d_paths = nullptr;  // the buffer stays in the engine's allocation list until release
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+  });
+}
+int lgarb_get_path_counters(lgarb_engine* e, uint64_t* out, int n) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (!out || n < 0) throw std::runtime_error("bad arguments");
+    if (!e->d_paths) throw std::runtime_error("path counters are off (lgarb_set_path_counters)");
+    unsigned long long h[LGAR_NPATH];
+    d2h(e, h, e->d_paths, sizeof(h));
+    for (int i = 0; i < n; i++) out[i] = i < LGAR_NPATH ? (uint64_t)h[i] : 0;
   });
 }
 int lgarb_set_window_mode(lgarb_engine* e, int mode) { LGARB_GUARD(e, e->use_window = (mode < 0 || mode > 3) ? 3 : mode); }

@@ -180,7 +180,6 @@ __global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_lanes_kernel(const _
     if (st == chosen) {
       if (chosen == LG_ST_SEARCH) {
         const int keep = (n_search >= LGAR_SEARCH_MIN) ? LGAR_SEARCH_MIN : 1;
-        if (!L.q.done) lg_search_some(L.q, *L.cls, 0);  // the fast path (lgar_search.cuh); plain trips below if it declined
         for (int it = 0; it < LGAR_SEARCH_QUANTUM; it++) {
           if (!L.q.done) {
             lg_search_iter(L.q, *L.cls);
@@ -306,7 +305,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         LgLane& G = slots[slot].L;
         LgSearch q = G.q;
         const LgarColumnClass* cls = G.cls;
-        lg_search_some(q, *cls, quantum);
+        lg_search_some(q, *cls, quantum, w.use_ff != 0);
         G.q = q;
         if (q.done) G.resume = true;
         next = q.done ? LG_ST_FRONT : LG_ST_SEARCH;
@@ -324,7 +323,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
 #pragma unroll
         for (int a = 0; a < 3; a++) ctx_load_n(l + kPitch * a, g + kPitch * a, cf);
         const LgarColumnClass* cls = G.cls;
-        lg_corr_some(k, fb.f, *cls, quantum);
+        lg_corr_some(k, fb.f, *cls, quantum, w.use_ff != 0);
         G.k = k;
 #pragma unroll
         for (int a = 1; a < 3; a++) ctx_store_n(g + kPitch * a, l + kPitch * a, cf);
@@ -352,6 +351,8 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
           G.c.cls = G.cls;
           G.c.f = &G.f;
           G.c.ff = lg_ff_ones;
+          G.c.paths = w.paths;
+          G.c.use_ff = w.use_ff != 0;
           if (STAGE == LG_ST_FRONT)
             lg_stage_front(G);
           else
@@ -381,6 +382,8 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         L.c.cls = L.cls;
         L.c.f = &L.f;
         L.c.ff = lg_ff_ones;
+        L.c.paths = w.paths;
+        L.c.use_ff = w.use_ff != 0;
         if (STAGE == LG_ST_FRONT)
           lg_stage_front(L);
         else
@@ -539,6 +542,8 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
     L.c.cls = L.cls;
     L.c.f = &L.f;
     L.c.ff = lg_ff_ones;
+    L.c.paths = w.paths;
+    L.c.use_ff = true;  // latency regime: see lg_search_some
     while (L.stage != LG_ST_DONE) {
       switch (L.stage) {
         case LG_ST_FETCH: lg_stage_fetch(cfg, d, w, L, fsp); break;
@@ -548,13 +553,13 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
           break;
         case LG_ST_FRONT: lg_stage_front(L); break;
         case LG_ST_SEARCH:
-          lg_search_run(L.q, *L.cls);
+          lg_search_run(L.q, *L.cls, true);
           L.resume = true;
           L.stage = LG_ST_FRONT;
           break;
         case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, fsp); break;
         case LG_ST_CORR:
-          lg_corr_run(L.k, L.f, *L.cls);
+          lg_corr_run(L.k, L.f, *L.cls, true);
           L.stage = LG_ST_TAIL;
           break;
         default: L.stage = LG_ST_DONE; break;

@@ -33,6 +33,8 @@ struct LgarWindow {
   int32_t* done_columns;  // nullable: += 1 whenever a column finishes its window (wavefront scheduler)
   unsigned int* work_trace;  // nullable: [2][stride] per column: psi-search trips, kilo-cycles in the non-search stages (lanes kernel)
   int64_t trace_stride;
+  unsigned long long* paths;  // nullable: [LGAR_NPATH] path counters (lgarb_set_path_counters)
+  int use_ff;                 // psi searches inside a stage take the fast path of lgar_search.cuh (few slots in flight)
 };
 #define LGAR_TILE 256            // columns owned by one warp at a time
 #define LGAR_WINDOW_THREADS 128

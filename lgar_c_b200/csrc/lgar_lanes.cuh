@@ -183,6 +183,7 @@ __device__ __forceinline__ void lg_search_bcast(LgSearch& q, int src) {
 LG_FN void lg_search_finish(LgLane& L) {
   const LgSearch& q = L.q;
   if (q.iter == 0) return;
+  lg_path_search_exit(L.c, q);
   if ((q.delta_mass > LG_MBAL_TOL) && (!q.wanted_to_saturate)) L.AET = L.AET - fabs(q.delta_mass - LG_MBAL_TOL);
   if ((q.theta >= L.cls->lay[q.layer_num].theta_e) && (q.psi_loc != 0.0)) L.AET = 0.0;
 }
@@ -216,6 +217,7 @@ LG_FN_NOINLINE void lg_move_top_block(LgLane& L) {
   if (fabs(f.theta[fdi] - theta_e_k1) < 1E-15) {
     double current_mass = lg_mass_bal(c);
     double mass_balance_error = fabs(current_mass - mass_timestep);
+    if (fabs(mass_balance_error) > LG_MBAL_TOL) LG_PATH(c, LGAR_PATH_SATURATED_DEPTH);
     double factor = 1.0;
     if (fdi + 1 < f.n) {
       if (fabs(f.theta[fdi] - f.theta[fdi + 1]) < 0.01) factor = factor / fabs(f.theta[fdi] - f.theta[fdi + 1]);
@@ -347,6 +349,7 @@ LG_FN_NOINLINE bool lg_move_fronts(LgLane& L) {
           } else {
             double th = prior_mass / f.depth[ci] + f.theta[ni];
             if (th < sp.theta_r) {  // :1519-1537
+              LG_PATH(c, LGAR_PATH_THETA_R_DELETE);
               double mass_before = lg_mass_bal(c) - f.depth[ci] * (f.theta[ci] - th);
               lg_front_delete(c, ci);
               double mass_after = lg_mass_bal(c);
@@ -439,6 +442,7 @@ LG_FN_NOINLINE bool lg_corr_init(LgLane& L, int front_num, double prior_mass) {
   k.aug_extreme = false;
   k.no_ff = false;
   k.done = !(k.delta_mass > LG_MBAL_TOL);
+  if (!k.done) LG_PATH(c, LGAR_PATH_CORR_SEARCH);
   return !k.done;
 }
 
@@ -493,6 +497,7 @@ LG_FN_NOINLINE bool lg_move_end(LgLane& L) {
     if (c.status & (LGAR_FAIL_LIST | LGAR_FAIL_OVERFLOW)) break;
     if (L.me_phase == 1) {
       const int correction = L.me_correction;
+      LG_PATH(c, correction == 1 ? LGAR_PATH_MERGE : correction == 2 ? LGAR_PATH_CROSS_LAYER : correction == 3 ? LGAR_PATH_CROSS_BOTTOM : LGAR_PATH_DRY_OVER_WET);
       if (correction == 1) lg_merge(c);
       if (correction == 2) {
         double mass_before = lg_mass_bal(c);
@@ -549,6 +554,7 @@ LG_FN_NOINLINE void lg_cycle_begin(const LgarConfig& cfg, LgLane& L) {
   const double dt = L.pro.subtimestep_h;
   LgCycle& cy = L.cy;
   lg_cycle_head(cfg, s, cy, L.P, L.E, dt, L.volon_ts, L.PET_rate, L.ponded);
+  LG_PATH(c, LGAR_PATH_ACTIVE_STEP);
   L.old.n = f.n;
   for (int i = 0; i < f.n; i++) {
     L.old.depth[i] = f.depth[i];
@@ -745,6 +751,7 @@ LG_FN_NOINLINE void lg_stage_head(const LgarConfig& cfg, const LgarDeviceState& 
   zero_vols(L.v);
   if (L.pro.cache_fluxes) {
     L.s.cache_fluxes = 1;
+    if (w.paths) { LgCtx pc; pc.paths = w.paths; LG_PATH(pc, LGAR_PATH_CACHED_STEP); }
     lg_step_cached(cfg, L.s, L.pro, P, E, L.v);
     if (!(fabs(L.v.local_mb) <= cfg.mbal_tol)) L.s.status |= (isnan(L.v.local_mb) ? LGAR_FAIL_NAN : LGAR_FAIL_MBAL);
     lg_epi_step(cfg, d, w, t, col, L.ep, L.v, L.s.status, t == w.K - 1);
@@ -759,6 +766,8 @@ LG_FN_NOINLINE void lg_stage_head(const LgarConfig& cfg, const LgarDeviceState& 
   L.c.cls = L.cls;
   L.c.f = &L.f;
   L.c.ff = lg_ff_ones;  // the window schedulers run uncoupled columns only (the engine steps SFT-coupled runs hour by hour)
+  L.c.paths = w.paths;
+  L.c.use_ff = w.use_ff != 0;
   L.c.status = 0;
   L.volon_ts = L.s.volon;
   L.volend_sub = L.s.storage;

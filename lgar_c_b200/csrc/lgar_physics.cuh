@@ -89,7 +89,14 @@ struct LgCtx {
   // coupled.  The places that use it -- and the three that do not (quirk Q11) -- follow the reference one by one;
   // x * 1.0 == x, so an uncoupled run is bit for bit what it was without the factor.
   const double* ff;
+  unsigned long long* paths;  // null, or [LGAR_NPATH] counters of the rare paths taken (lgarb_set_path_counters)
+  bool use_ff;                // psi searches take the fast path of lgar_search.cuh (a latency tool, see there)
 };
+#ifdef LGAR_HOSTSIM
+#define LG_PATH(ctx, id) do { if ((ctx).paths) (ctx).paths[id]++; } while (0)
+#else
+#define LG_PATH(ctx, id) do { if ((ctx).paths) atomicAdd((ctx).paths + (id), 1ULL); } while (0)
+#endif
 #ifdef LGAR_HOSTSIM
 static const double lg_ff_ones[LGAR_MAXL + 2] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
 #elif defined(LGAR_TU_LOCAL)
@@ -231,6 +238,20 @@ LG_FN_NOINLINE double lg_Geff(const LgarConfig& cfg, double theta1, double theta
 
 #include "lgar_search.cuh"
 
+// which exit ended an iterated psi search (instrumentation: the conditions are those of the loop, in its order)
+LG_FN void lg_path_search_exit(LgCtx& c, const LgSearch& q) {
+  if (!c.paths) return;
+  LG_PATH(c, LGAR_PATH_SEARCH);
+  int id;
+  if (!(q.delta_mass > LG_MBAL_TOL)) id = LGAR_PATH_SEARCH_CONVERGED;
+  else if (lg_digit_brk_first(q)) id = LGAR_PATH_SEARCH_STEP_EXIT;
+  else if (q.count_no_mass_change == 5 && q.precip_mass_to_add < 1.E-12) id = LGAR_PATH_SEARCH_NOCHANGE;
+  else if (q.iter > LG_MAX_ITER_MBAL) id = LGAR_PATH_SEARCH_MAXITER;
+  else if ((q.psi_loc > LG_PSI_UPPER_LIM) && (q.iter > LG_MAX_ITER_MBAL / 100)) id = LGAR_PATH_SEARCH_PSI_UPPER;
+  else id = LGAR_PATH_SEARCH_PSI_ZERO;
+  LG_PATH(c, id);
+}
+
 // ------------------------------------------------------------------------------------------------
 // L0: list behaviour on fixed slots, reference src/linked_list.cxx
 // ------------------------------------------------------------------------------------------------
@@ -354,7 +375,8 @@ LG_FN_NOINLINE double lg_theta_mass_balance(LgCtx& c, int layer_num, double psi_
     q.dz[k] = dz[k];
   }
   if (q.delta_mass <= LG_MBAL_TOL) return lg_theta_from_h(psi_cm, sp);
-  lg_search_run(q, cls);
+  lg_search_run(q, cls, c.use_ff);
+  lg_path_search_exit(c, q);
   if ((q.delta_mass > LG_MBAL_TOL) && (!q.wanted_to_saturate)) *AET_demand_cm = *AET_demand_cm - fabs(q.delta_mass - LG_MBAL_TOL);
   if ((q.theta >= sp.theta_e) && (q.psi_loc != 0.0)) *AET_demand_cm = 0.0;
   return q.theta;
@@ -398,7 +420,10 @@ LG_FN_NOINLINE void lg_theta_mass_balance_correction(LgCtx& c, int front_num, do
   k.aug_extreme = false;
   k.no_ff = false;
   k.done = !(k.delta_mass > LG_MBAL_TOL);
-  if (!k.done) lg_corr_run(k, f, cls);
+  if (!k.done) {
+    LG_PATH(c, LGAR_PATH_CORR_SEARCH);
+    lg_corr_run(k, f, cls, c.use_ff);
+  }
 }
 
 // lgar_merge_wetting_fronts, lgar.cxx:1875-1953
@@ -503,6 +528,7 @@ LG_FN_NOINLINE void lg_cross_layer_boundary(LgCtx& c) {
     }
     double prior_mass = lg_mass_bal(c);
     if (f.depth[i] > cum[num_layers] && f.layer[i] == num_layers && wf == front_for_cross) {
+      LG_PATH(c, LGAR_PATH_CROSS_LAYER_BOTTOM);
       f.depth[i] = cum[num_layers] + 1.E-6;
       lg_theta_mass_balance_correction(c, wf, prior_mass);
       double current_mass = lg_mass_bal(c);
@@ -635,6 +661,7 @@ LG_FN_NOINLINE void lg_clean_redundant(LgCtx& c) {
   for (int wf = 1; wf != f.n; wf++) {
     int nx = cur + 1;
     if ((f.layer[cur] == f.layer[nx]) && (fabs(f.theta[cur] - f.theta[nx]) < LG_THRESHOLD_NO_MOISTURE_DIFF)) {
+      LG_PATH(c, LGAR_PATH_CLEAN_REDUNDANT);
       lg_front_delete(c, cur);
       break;
     }
@@ -720,6 +747,7 @@ LG_FN_NOINLINE double lg_move_wetting_fronts(LgCtx& c, double timestep_h, double
         } else {
           double th = prior_mass / f.depth[ci] + f.theta[ni];
           if (th < sp.theta_r) {  // :1519-1537
+            LG_PATH(c, LGAR_PATH_THETA_R_DELETE);
             double mass_before = lg_mass_bal(c) - f.depth[ci] * (f.theta[ci] - th);
             lg_front_delete(c, ci);
             double mass_after = lg_mass_bal(c);
@@ -775,6 +803,7 @@ LG_FN_NOINLINE double lg_move_wetting_fronts(LgCtx& c, double timestep_h, double
         double depth_new = f.depth[fdi];
         int iter = 0;
         const int speedup_thresh = LG_MAX_ITER_SAT / 10;
+        if (fabs(mass_balance_error) > LG_MBAL_TOL) LG_PATH(c, LGAR_PATH_SATURATED_DEPTH);
         while (fabs(mass_balance_error) > LG_MBAL_TOL) {
           iter++;
           if (iter > LG_MAX_ITER_SAT) {
@@ -823,6 +852,7 @@ LG_FN_NOINLINE double lg_move_wetting_fronts(LgCtx& c, double timestep_h, double
   int correction = lg_correction_type(c);
   while (correction != 0) {
     if (c.status & (LGAR_FAIL_LIST | LGAR_FAIL_OVERFLOW)) break;
+    LG_PATH(c, correction == 1 ? LGAR_PATH_MERGE : correction == 2 ? LGAR_PATH_CROSS_LAYER : correction == 3 ? LGAR_PATH_CROSS_BOTTOM : LGAR_PATH_DRY_OVER_WET);
     if (correction == 1) lg_merge(c);
     if (correction == 2) {
       double mass_before = lg_mass_bal(c);
@@ -920,6 +950,7 @@ LG_FN_NOINLINE double lg_calc_dry_depth(LgCtx& c, double timestep_h) {
 
 // lgar_create_surficial_front, lgar.cxx:2490-2568
 LG_FN_NOINLINE void lg_create_surficial_front(LgCtx& c, double* ponded_depth_cm, double* volin, double dry_depth, double theta1) {
+  LG_PATH(c, LGAR_PATH_SURFICIAL);
   LgFronts& f = *c.f;
   const LgarLayer& sp = c.cls->lay[1];
   double delta_theta = sp.theta_e - theta1;
@@ -1200,8 +1231,10 @@ LG_FN_NOINLINE void lg_step_cached(const LgarConfig& cfg, LgScalars& s, const Lg
 
 // A forcing step that computes fluxes (bmi_lgar.cxx:356-805 with cache_fluxes == false).
 LG_FN_NOINLINE void lg_step_active(const LgarConfig& cfg, const LgarColumnClass& cls, LgScalars& s, LgFronts& f, const LgPrologue& pro,
-                                   double precip_mm_h, double pet_mm_h, LgStepVols& v, const double* frozen_factor) {
+                                   double precip_mm_h, double pet_mm_h, LgStepVols& v, const double* frozen_factor, unsigned long long* paths = nullptr, bool use_ff = false) {
   LgCtx c;
+  c.paths = paths;
+  c.use_ff = use_ff;
   c.cfg = &cfg;
   c.cls = &cls;
   c.f = &f;
@@ -1215,6 +1248,7 @@ LG_FN_NOINLINE void lg_step_active(const LgarConfig& cfg, const LgarColumnClass&
   LgOld old;
 
   for (int cycle = 1; cycle <= pro.subcycles; cycle++) {
+    LG_PATH(c, LGAR_PATH_ACTIVE_STEP);
     LgCycle cy;
     double PET_rate, ponded;
     lg_cycle_head(cfg, s, cy, precip_mm_h, pet_mm_h, dt, volon_ts, PET_rate, ponded);

@@ -486,11 +486,15 @@ struct LgSearchModel {
 };
 #endif
 
-// A freshly initialised search (lg_search_init returned true) through the fast path, then at most `quantum` plain trips of
-// whatever is left (nothing, unless the fast path declined).
-LG_FN void lg_search_some(LgSearch& q, const LgarColumnClass& cls, int quantum) {
+// A search in flight: through the fast path if `use_ff` (from whatever trip the walk has reached), then at most `quantum` plain
+// trips of whatever is left.  Where the fast path pays: it does ~10 evaluations where the plain walk does ~70, but the lanes of a
+// warp walking plainly are CONVERGED and compacted (the SEARCH stage kernel runs at ~65 % of the FP64 peak), while the fast
+// path's bookkeeping diverges -- measured on the B200, bulk rounds are 2.1 x SLOWER with it (profiles/r2_call2_summary.md).
+// It is a latency tool: the engine turns it on when few slots are in flight (drop-out rounds, finishing kernel), where a round
+// lasts as long as its longest search and a 10^4-trip monster is 10^4 cheap recurrences instead of 10^4 evaluations.
+LG_FN void lg_search_some(LgSearch& q, const LgarColumnClass& cls, int quantum, bool use_ff) {
 #if !defined(LGAR_FAST_POW) && !defined(LGAR_NO_FF)
-  if (!q.no_ff && q.iter == 0) {
+  if (use_ff && !q.no_ff) {  // from whatever trip the walk has reached: the record is a complete state of it
     LgSearchModel ev{&q, &cls};
     if (lg_digit_ff(q, ev, q.precip_mass_to_add < 1.E-12)) return;
   }
@@ -499,14 +503,14 @@ LG_FN void lg_search_some(LgSearch& q, const LgarColumnClass& cls, int quantum) 
 }
 
 // the whole search to q.done
-LG_FN_NOINLINE void lg_search_run(LgSearch& q, const LgarColumnClass& cls) {
+LG_FN_NOINLINE void lg_search_run(LgSearch& q, const LgarColumnClass& cls, bool use_ff) {
   LG_FF_COUNT(searches, 1);
 #ifdef LGAR_FF_VERIFY
   LgSearch ref = q;
   while (!ref.done) lg_search_iter(ref, cls);
-  const bool fresh = !q.no_ff && q.iter == 0;
+  const bool fresh = use_ff && !q.no_ff;
 #endif
-  while (!q.done) lg_search_some(q, cls, 1 << 30);
+  while (!q.done) lg_search_some(q, cls, 1 << 30, use_ff);
 #ifdef LGAR_FF_VERIFY
   if (fresh && !(lgp_bits(ref.psi_loc) == lgp_bits(q.psi_loc) && lgp_bits(ref.theta) == lgp_bits(q.theta) && lgp_bits(ref.delta_mass) == lgp_bits(q.delta_mass) &&
                  lgp_bits(ref.new_mass) == lgp_bits(q.new_mass) && ref.iter == q.iter && ref.wanted_to_saturate == q.wanted_to_saturate))
@@ -616,9 +620,9 @@ struct LgCorrModel {
 
 // A freshly initialised correction search (lg_corr_init returned true) through the fast path, then at most `quantum` plain
 // trips of whatever is left.
-LG_FN void lg_corr_some(LgCorr& k, LgFronts& f, const LgarColumnClass& cls, int quantum) {
+LG_FN void lg_corr_some(LgCorr& k, LgFronts& f, const LgarColumnClass& cls, int quantum, bool use_ff) {
 #if !defined(LGAR_FAST_POW) && !defined(LGAR_NO_FF)
-  if (!k.no_ff && k.iter == 0) {
+  if (use_ff && !k.no_ff) {
     LgCorrModel ev;
     ev.k = &k;
     ev.f = &f;
@@ -630,16 +634,16 @@ LG_FN void lg_corr_some(LgCorr& k, LgFronts& f, const LgarColumnClass& cls, int 
   for (int it = 0; it < quantum && !k.done; it++) lg_corr_iter(k, f, cls);
 }
 // the whole correction search to k.done
-LG_FN_NOINLINE void lg_corr_run(LgCorr& k, LgFronts& f, const LgarColumnClass& cls) {
+LG_FN_NOINLINE void lg_corr_run(LgCorr& k, LgFronts& f, const LgarColumnClass& cls, bool use_ff) {
 #ifdef LGAR_FF_VERIFY
   LgCorr ref = k;
   static LgFronts fref;
   fref = f;
   while (!ref.done) lg_corr_iter(ref, fref, cls);
-  const bool fresh = !k.no_ff && k.iter == 0;
+  const bool fresh = use_ff && !k.no_ff;
   LG_FF_COUNT(searches, 1);
 #endif
-  while (!k.done) lg_corr_some(k, f, cls, 1 << 30);
+  while (!k.done) lg_corr_some(k, f, cls, 1 << 30, use_ff);
 #ifdef LGAR_FF_VERIFY
   bool same = lgp_bits(ref.psi_loc) == lgp_bits(k.psi_loc) && lgp_bits(ref.delta_mass) == lgp_bits(k.delta_mass) && lgp_bits(ref.new_mass) == lgp_bits(k.new_mass) && ref.iter == k.iter;
   for (int i = 0; i < f.n; i++) same = same && lgp_bits(fref.theta[i]) == lgp_bits(f.theta[i]) && lgp_bits(fref.psi[i]) == lgp_bits(f.psi[i]);

@@ -221,6 +221,7 @@ LG_FN bool lg_stream_column(const LgarConfig& cfg, const LgarDeviceState& d, con
   adjust_forcing(cfg, P, E, s.status);
   LgStepVols v;
   zero_vols(v);
+  if (d.paths) { LgCtx pc; pc.paths = d.paths; LG_PATH(pc, LGAR_PATH_CACHED_STEP); }
   lg_step_cached(cfg, s, pro, P, E, v);
   if (!(fabs(v.local_mb) <= cfg.mbal_tol)) s.status |= (isnan(v.local_mb) ? LGAR_FAIL_NAN : LGAR_FAIL_MBAL);
   store_scalars(d, col, s, false);
@@ -256,7 +257,7 @@ LG_FN_NOINLINE void lg_active_column(const LgarConfig& cfg, const LgarDeviceStat
       for (int k = 0; k <= LGAR_MAXL; k++) ff[k] = d.ff[(int64_t)k * d.stride + col];
       ffp = ff;
     }
-    lg_step_active(cfg, *cls, s, f, pro, P, E, v, ffp);
+    lg_step_active(cfg, *cls, s, f, pro, P, E, v, ffp, d.paths, d.use_ff != 0);
     store_scalars(d, col, s, true);
     store_fronts(d, col, f);
   }
@@ -434,6 +435,7 @@ LG_FN bool lg_resident_hour(const LgarConfig& cfg, const LgarDeviceState& d, con
     s.cache_fluxes = 1;
     s.cache_count = pro.cache_count;
     adjust_forcing(cfg, P, E, s.status);
+    if (w.paths) { LgCtx pc; pc.paths = w.paths; LG_PATH(pc, LGAR_PATH_CACHED_STEP); }
     lg_step_cached_inl(cfg, s, pro, P, E, v);
     if (!(fabs(v.local_mb) <= cfg.mbal_tol)) s.status |= (isnan(v.local_mb) ? LGAR_FAIL_NAN : LGAR_FAIL_MBAL);
   }

@@ -38,6 +38,31 @@
 #define LGAR_FAIL_MASK 0xFFFF
 #define LGAR_WARN_NEG_FORCING 0x10000
 
+// Path counters (lgarb_set_path_counters): how often each rare branch of the reference ran -- the evidence that the tests reach
+// them.  Same numbering as LGO_PATH_* of oracle/lgar_oracle.h, so the engine's counts can be compared with the oracle's.
+enum {
+  LGAR_PATH_MERGE = 0,          // lgar_merge_wetting_fronts, lgar.cxx:1875-1953 (correction type 1)
+  LGAR_PATH_CROSS_LAYER,        // lgar_wetting_fronts_cross_layer_boundary, :1963-2167 (type 2)
+  LGAR_PATH_CROSS_BOTTOM,       // lgar_wetting_front_cross_domain_boundary, :2176-2251 (type 3)
+  LGAR_PATH_DRY_OVER_WET,       // lgar_fix_dry_over_wet_wetting_fronts, :2260-2307 (type 4)
+  LGAR_PATH_THETA_R_DELETE,     // front deleted because theta < theta_r, :1519-1537
+  LGAR_PATH_SATURATED_DEPTH,    // saturated front deepened until the mass balance closes, :1687-1723
+  LGAR_PATH_CROSS_LAYER_BOTTOM, // layer crossing that also passes the domain bottom: depth search, :2090-2159
+  LGAR_PATH_SURFICIAL,          // lgar_create_surficial_front, :2490-2568
+  LGAR_PATH_CLEAN_REDUNDANT,    // lgar_clean_redundant_fronts deletes a front, :3171-3195
+  LGAR_PATH_SEARCH,             // lgar_theta_mass_balance iterates, :2990
+  LGAR_PATH_SEARCH_CONVERGED,   // ... and ends within the tolerance
+  LGAR_PATH_SEARCH_STEP_EXIT,   // ... on |psi - psi_prev| < 1e-15 and factor < 1e-13, :3063
+  LGAR_PATH_SEARCH_NOCHANGE,    // ... on five trips without mass change, :3070-3076
+  LGAR_PATH_SEARCH_MAXITER,     // ... on the trip limit, :3078
+  LGAR_PATH_SEARCH_PSI_UPPER,   // ... on psi > 1e7 after 1000 trips, :3081
+  LGAR_PATH_SEARCH_PSI_ZERO,    // ... on psi <= 0 twice, :3084
+  LGAR_PATH_CORR_SEARCH,        // lgar_theta_mass_balance_correction iterates, :3307
+  LGAR_PATH_CACHED_STEP,        // sub-step that replays cached fluxes, bmi_lgar.cxx:683-695
+  LGAR_PATH_ACTIVE_STEP,        // sub-step that computes fluxes
+  LGAR_NPATH = 24
+};
+
 // order of the per-step scalar outputs, metres (bmi_lgar.cxx:882-893)
 enum {
   LGAR_OUT_PRECIP = 0, LGAR_OUT_PET, LGAR_OUT_AET, LGAR_OUT_RUNOFF, LGAR_OUT_GIUH_RUNOFF,
@@ -128,6 +153,8 @@ struct LgarDeviceState {
   // work list for the active kernel
   int32_t* work;                // [stride]
   int32_t* work_count;          // [2]: count, cursor
+  unsigned long long* paths;    // null, or [LGAR_NPATH] path counters (lgarb_set_path_counters)
+  int32_t use_ff;               // hour-by-hour kernels: psi searches take the fast path of lgar_search.cuh
 };
 
 #endif

@@ -424,6 +424,7 @@ static void theta_mass_balance_correction(ctx_t* c, int front_num, double prior_
   psi_cm_loc_prev = psi_cm_loc;
   delta_mass_prev = delta_mass;
 
+  if (delta_mass > MBAL_ITERATIVE_TOLERANCE) c->s->n_path[LGO_PATH_CORR_SEARCH]++;
   while (delta_mass > MBAL_ITERATIVE_TOLERANCE) {
     int nx, before;
     iter++;
@@ -1395,6 +1396,7 @@ int lgo_update(const lgo_params* p, lgo_state* s, double precipitation_mm_per_h,
   }
   if (caching_at_start && !s->cache_fluxes) switch_caching = 1;
   if (s->cache_fluxes) s->cache_count++;
+  if (s->cache_fluxes) s->n_path[LGO_PATH_CACHED_STEP]++;
 
   subcycles = (int)(p->forcing_resolution_h / s->timestep_h + 1.0e-08);
 

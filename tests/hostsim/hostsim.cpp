@@ -14,6 +14,16 @@
 
 using namespace lgarhost;
 
+// psi searches through the fast path of lgar_search.cuh (1, default) or the plain trip-by-trip walk (0)
+static int hostsim_use_ff = 1;
+extern "C" void hostsim_set_use_ff(int on) { hostsim_use_ff = on; }
+// path counters (LGAR_PATH_* of lgar_types.h), accumulated over every run since the last reset
+static unsigned long long hostsim_paths[LGAR_NPATH];
+extern "C" void hostsim_get_paths(unsigned long long* out, int reset) {
+  for (int i = 0; i < LGAR_NPATH; i++) out[i] = hostsim_paths[i];
+  if (reset) memset(hostsim_paths, 0, sizeof(hostsim_paths));
+}
+
 #ifdef LGAR_FF_STATS
 // how the psi searches went (searches, finished by the fast path, declined, fallbacks, evaluations fast/plain, trips, verify mismatches)
 extern "C" void hostsim_ff_stats(long long* out8, int reset) {
@@ -58,6 +68,7 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
     d.fflags = fflags_w; d.nfront = &nf; d.scal = scal.data(); d.bits = &bits; d.status = &status; d.class_id = &class_id;
     d.giuhq = giuhq.data(); d.cum = cum.data(); d.out = out.data(); d.classes = &cls; d.precip = &p1; d.pet = &e1;
     d.work = work; d.work_count = work_count;
+    d.paths = hostsim_paths; d.use_ff = hostsim_use_ff;
     if (!cls.invalid_soil_type) {
       for (int k = 0; k < L; k++) {
         depth[k] = cls.cum[k + 1]; theta[k] = cls.initial_theta[k + 1]; psi[k] = pc.initial_psi; K[k] = cls.initial_K[k + 1]; dzdt[k] = 0.0;
@@ -79,6 +90,8 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
       w.precip = P; w.pet = E; w.series_stride = 1; w.sink_stride = 1; w.K = nsteps; w.force_all_active = (force_all_active == 3);
       for (int k = 0; k < LGAR_NOUT; k++) w.sinks.p[k] = sk.data() + (size_t)k * nsteps;
       w.has_sinks = 1;
+      w.use_ff = hostsim_use_ff;
+      w.paths = hostsim_paths;
       w.nf_sink = nfs.data();
       if (force_all_active >= 4) {
         // lane-program emulation: one lane walks the stages of lgar_lanes.cuh
@@ -93,11 +106,11 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
             case LG_ST_HEAD: lg_stage_head(cfg, d, w, L, nullptr); break;
             case LG_ST_FRONT: lg_stage_front(L); break;
             case LG_ST_SEARCH:
-              lg_search_run(L.q, *L.cls);
+              lg_search_run(L.q, *L.cls, hostsim_use_ff != 0);
               L.resume = true; L.stage = LG_ST_FRONT; break;
             case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, nullptr); break;
             case LG_ST_CORR:
-              lg_corr_run(L.k, L.f, *L.cls);
+              lg_corr_run(L.k, L.f, *L.cls, hostsim_use_ff != 0);
               L.stage = LG_ST_TAIL; break;
           }
         }

@@ -242,3 +242,112 @@ def test_more_than_16_fronts(cuda_device, oracle, tmp_path):
     assert r["front_count_mismatch_columns"] == 0 and r["failure_mismatch_columns"] == 0, r["examples"]
     assert r["final_front_flag_mismatch_columns"] == 0 and r["final_front_field_mismatch_columns"] == 0
     assert max(v["columns_outside_bar"] for v in r["scalars"].values()) == 0, r["examples"]
+
+
+def _run_config_columns(num, ids, T, tmp_path, counters=True):
+    """BASELINE config `num` for the global column ids `ids` over T forcing steps on the GPU: per-step scalars [T][12][n],
+    front counts [T][n], the forcing the engine was fed, the engine."""
+    import sys
+    import torch
+    import lgar_c_b200
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent.parent / "tools"))
+    import parity_sampling_full as pf
+    c = pf.Config(num, tmp_path)
+    ids = np.asarray(ids, dtype=np.int64)
+    n = len(ids)
+    b = lgar_c_b200.BmiLGARBatch()
+    b.initialize(c.cfg, n, 0, c.soils(ids), c.layers(ids))
+    if counters:
+        b.set_path_counters(True)
+    dP, dE = c.forcing(torch.from_numpy(ids).cuda(), 0, T)
+    sinks = torch.zeros((12, T, n), dtype=torch.float64, device="cuda")
+    nfs = torch.zeros((T, n), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    b.update_steps_device(T, dP.data_ptr(), dE.data_ptr(), n, {nm: sinks[k].data_ptr() for k, nm in enumerate(lgar_c_b200.OUTPUT_SCALARS)}, n, nfs.data_ptr())
+    b.synchronize()
+    return c, b, sinks.cpu().numpy().transpose(1, 0, 2), nfs.cpu().numpy(), dP.cpu().numpy(), dE.cpu().numpy()
+
+
+def _oracle_column(oracle, c, cid, P, E):
+    soils, layers = c.soils(np.array([cid])), c.layers(np.array([cid]))
+    kw = {}
+    if soils is not None:
+        kw["layer_soil_type"] = [int(x) for x in soils[0]]
+    if layers is not None:
+        kw["layer_thickness"] = [float(x) for x in layers[0]]
+    p = oracle.params_from_config(c.cfg, **kw)
+    s = oracle.new_state(p)
+    r = oracle.run_series(p, s, np.ascontiguousarray(P), np.ascontiguousarray(E), cap=32)
+    return r, s
+
+
+# Round 1's full-duration sampling (profiles/r1_parity_sampling_full.json) found, with x^y = exp(y log x) on the device: config 5
+# column 8 416 695 splitting its front count from the oracle's at step 2 662, column 9 271 602 outside 1e-9 in AET for 15 steps,
+# and 59 config-4 columns outside 1e-9 in surface_runoff (the twelve listed there below).  With the host library's pow restated
+# on the device (lgar_pow.cuh) every one of them is bit-identical to the oracle for the whole duration.
+R1_CONFIG5_OFFENDERS = [8416695, 9271602, 5588097]   # + the 19-front column
+R1_CONFIG4_OFFENDERS = [111221, 196626, 211082, 250681, 252734, 261016, 340747, 462633, 471584, 586152, 587606, 643728]
+# columns of the seed-99 sample that take the rare branches (tools/path_scan.py): theta < theta_r deletion, domain-bottom
+# crossing with the depth search of a crossing front, saturated-front depth loop
+RARE_PATH_COLUMNS = {5: [88278, 96160, 11932], 4: [35301, 419274, 12347], 3: [3085, 29707, 342466, 1192]}
+
+
+@pytest.mark.parametrize("num,ids,T", [(5, R1_CONFIG5_OFFENDERS + RARE_PATH_COLUMNS[5], 8760), (4, R1_CONFIG4_OFFENDERS + RARE_PATH_COLUMNS[4], 7500),
+                                       (3, RARE_PATH_COLUMNS[3], 8333)])
+def test_round1_offenders_and_rare_paths_full_duration(cuda_device, oracle, tmp_path, num, ids, T):
+    """The columns on which round 1 left north_star's bar, and columns that take the reference's rare branches, over the FULL
+    duration of their BASELINE config: every scalar of every step, every front count and the final fronts equal the oracle's
+    bit for bit; and the engine's path counters (lgarb_get_path_counters) equal the oracle's, branch by branch -- merge, layer
+    crossing, domain-bottom crossing, dry-over-wet, theta < theta_r deletion, saturated-front depth loop, crossing + bottom depth
+    search, every exit of the psi search (reference src/lgar.cxx:1519-1537,1687-1723,1875-2307,3063-3086)."""
+    c, b, scal, nf, P, E = _run_config_columns(num, ids, T, tmp_path)
+    assert (b.get_status() & 0xFFFF == 0).all()
+    fr = b.get_fronts()
+    want_paths = np.zeros(24, dtype=np.int64)
+    for j, cid in enumerate(ids):
+        r, s = _oracle_column(oracle, c, cid, P[:, j], E[:, j])
+        assert r["done"] == T
+        assert np.array_equal(nf[:, j], r["nfronts"]), f"config {num} column {cid}: front count differs at step {int(np.argmax(nf[:, j] != r['nfronts']))}"
+        assert_scalars_close(scal[:, :, j], r["scalars"], f"config {num} column {cid}")
+        n = int(fr["nfronts"][j])
+        arr = np.stack([fr[k][j] for k in ("depth", "theta", "psi", "K", "dzdt")], axis=1)
+        flags = (fr["layer"][j] | (fr["to_bottom"][j] << 8)).astype(np.int32)
+        assert_fronts_close(arr, flags, r["fronts"][-1], r["flags"][-1], n, f"config {num} column {cid} final fronts")
+        want_paths += np.array(s.n_path[:])
+    got = b.get_path_counters()
+    import lgar_c_b200.bmi as bmi
+    for i, name in enumerate(bmi.PATH_NAMES):
+        assert got[name] == want_paths[i], f"config {num}: path {name}: engine {got[name]} oracle {want_paths[i]}"
+    must = ["merge", "cross_layer", "cross_bottom", "dry_over_wet", "saturated_depth", "cross_layer_bottom", "surficial", "search", "search_converged",
+            "corr_search", "cached_step", "active_step"] + (["theta_r_delete"] if num in (3, 5) else [])
+    for name in must:
+        assert got[name] > 0, f"config {num}: the run never took path {name}"
+
+
+def test_search_exits_other_than_convergence(cuda_device, oracle, tmp_path):
+    """The psi search ends on `|psi - psi_prev| < 1e-15 and factor < 1e-13` (reference src/lgar.cxx:3063) in the synthetic cases
+    (3 of 4 900 searches of the golden cases); the engine must take that exit where the oracle does."""
+    from helpers import load_golden, config_for
+    import lgar_c_b200
+    import torch
+    want = 0
+    got = 0
+    for name in ("synth_0", "synth_1", "synth_2", "unittest"):
+        g = load_golden(name)
+        cfg = config_for(name, tmp_path)
+        T = len(g["precip"])
+        b = lgar_c_b200.BmiLGARBatch()
+        b.initialize(cfg, 1)
+        b.set_path_counters(True)
+        dP, dE = torch.from_numpy(g["precip"][:, None].copy()).cuda(), torch.from_numpy(g["pet"][:, None].copy()).cuda()
+        torch.cuda.synchronize()
+        b.update_steps_device(T, dP.data_ptr(), dE.data_ptr(), 1)
+        b.synchronize()
+        p = oracle.params_from_config(cfg)
+        s = oracle.new_state(p)
+        oracle.run_series(p, s, g["precip"], g["pet"], want_fronts=False)
+        pc = b.get_path_counters()
+        assert pc["search_step_exit"] == s.n_path[11] and pc["search"] == s.n_path[9], name
+        want += s.n_path[11]
+        got += pc["search_step_exit"]
+    assert got == want and got > 0

@@ -98,6 +98,34 @@ def test_fast_search_path_reproduces_the_plain_walk(tmp_path):
     assert evals_ff < 0.35 * trips, "the fast path evaluates more than a third of the trips it replays"
 
 
+@pytest.mark.parametrize("force,ff", [(0, 1), (0, 0), (4, 1), (4, 0)])
+def test_path_counters_equal_the_oracles(hostsim, oracle, force, ff, tmp_path):
+    """The kernel text's path counters (LGAR_PATH_* of lgar_types.h: merge, layer crossing, domain-bottom crossing, dry-over-wet,
+    theta < theta_r deletion, saturated-front depth loop, surficial front, every exit of the psi search, correction searches,
+    cached / active steps) against the oracle's (LGO_PATH_*), summed over all golden cases: equal branch by branch, in both
+    program forms, with the psi searches through the fast path and through the plain walk."""
+    hostsim.hostsim_set_use_ff(ff)
+    buf = (C.c_ulonglong * 24)()
+    hostsim.hostsim_get_paths(buf, 1)
+    want = np.zeros(24, dtype=np.int64)
+    for name in STANDARD + RANDOM:
+        g = load_golden(name)
+        n = min(len(g["precip"]), 3000)
+        cfg = config_for(name, tmp_path)
+        done, scal, nf, fr, fl, st = run(hostsim, cfg, g["precip"][:n], g["pet"][:n], force)
+        assert done == n and np.array_equal(scal, g["scalars"][:n])
+        p = oracle.params_from_config(cfg)
+        s = oracle.new_state(p)
+        oracle.run_series(p, s, np.ascontiguousarray(g["precip"][:n]), np.ascontiguousarray(g["pet"][:n]), want_fronts=False)
+        want += np.array(s.n_path[:])
+    hostsim.hostsim_get_paths(buf, 1)
+    hostsim.hostsim_set_use_ff(1)
+    got = np.array(buf[:], dtype=np.int64)
+    assert np.array_equal(got, want), (got, want)
+    for i in (0, 1, 2, 3, 5, 7, 9, 10, 11, 16, 17, 18):   # what the golden cases reach (the others: tests/test_gpu_scale_parity.py)
+        assert got[i] > 0, i
+
+
 @pytest.fixture(scope="module")
 def hostsim_libm_pow():
     """The same kernel text with x^y = the library pow (-DLGAR_ACCURATE_POW; on the host that is glibc's pow, the function
