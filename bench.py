@@ -45,9 +45,9 @@ DATA = ROOT / "data"
 PH_LAYERS = (44.0, 131.0, 25.0)   # data/configs/config_lasam_Phillipsburg.txt
 BU_LAYERS = (18.0, 76.0, 135.0)   # data/configs/config_lasam_Bushland.txt
 N_GIUH = 5
-# DRAM bytes per column-timestep of the default scheduler: ncu over every launch of one timed window (profiles/, see the
-# roofline block in main)
-TRAFFIC_B_PER_UNIT = 3416.4
+# Measured DRAM traffic and stage shares come from a committed ncu capture (profiles/r2_window_profile.json), keyed to the sha256
+# of the liblgarb.so it was taken with: a line printed by another build says so instead of repeating stale numbers.
+WINDOW_PROFILE = ROOT / "profiles" / "r2_window_profile.json"
 
 
 # --------------------------------------------------------------------------------------------------
@@ -104,8 +104,71 @@ def pet_series(hours: np.ndarray) -> np.ndarray:
     return 0.21 * np.maximum(0.0, 1.0 + np.cos(2 * np.pi * (h - 14) / 24.0)) * (1.0 + 0.5 * np.sin(2 * np.pi * d / 365.0))
 
 
+# ---- the synthetic forcing of config 5, ONE definition for both arms and for the parity tools ---------------------------------
+# Counter based: hour h of global column c draws two 64-bit hashes keyed by (c, h); the first decides wet / dry (probability
+# 0.03), the second picks the intensity from a 65 536-entry table of the Exp(mean 2.5 mm/h) quantile function capped at 170 mm/h.
+# The table is made once with numpy on the host in either arm and only INDEXED on the device, so the device (torch int64
+# arithmetic) and the host (numpy uint64) produce the same doubles bit for bit -- no transcendental is evaluated twice.
+_FORCING_C = 777 * 0x100000001B3
+
+
+def exp_intensity_table() -> np.ndarray:
+    k = np.arange(65536, dtype=np.float64)
+    return np.minimum(-2.5 * np.log1p(-(k + 0.5) / 65536.0), 170.0)
+
+
+def forcing_np(ids: np.ndarray, hour0: int, nhours: int):
+    """[nhours][len(ids)] precipitation and PET (mm/h) of the global columns `ids` for hours [hour0, hour0 + nhours)"""
+    t = np.arange(hour0, hour0 + nhours, dtype=np.uint64)
+    c = np.asarray(ids).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        key = (c[None, :] * np.uint64(1000003) + t[:, None]) * np.uint64(2) + np.uint64(_FORCING_C & 0xFFFFFFFFFFFFFFFF)
+        h1 = splitmix64(key)
+        h2 = splitmix64(key + np.uint64(1))
+    wet = (h1 >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0) < 0.03
+    P = np.where(wet, exp_intensity_table()[(h2 >> np.uint64(48)).astype(np.int64)], 0.0)
+    E = np.repeat(pet_series(np.arange(hour0, hour0 + nhours))[:, None], len(c), axis=1)
+    return np.ascontiguousarray(P), np.ascontiguousarray(E)
+
+
+def _i64(x: int) -> int:
+    x &= 0xFFFFFFFFFFFFFFFF
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def _lsr(x, k):
+    return (x >> k) & ((1 << (64 - k)) - 1)
+
+
+def _splitmix64_t(x):
+    """splitmix64 on torch int64 tensors (wrapping multiply, logical shifts)"""
+    z = x + _i64(0x9E3779B97F4A7C15)
+    z = (z ^ _lsr(z, 30)) * _i64(0xBF58476D1CE4E5B9)
+    z = (z ^ _lsr(z, 27)) * _i64(0x94D049BB133111EB)
+    return z ^ _lsr(z, 31)
+
+
+_LUT_DEV = {}
+
+
+def forcing_torch(ids_t, hour0: int, nhours: int):
+    """forcing_np on the device of the int64 tensor `ids_t`: the same doubles"""
+    import torch
+    dev = ids_t.device
+    if dev not in _LUT_DEV:
+        _LUT_DEV[dev] = torch.from_numpy(exp_intensity_table()).to(dev)
+    t = torch.arange(hour0, hour0 + nhours, dtype=torch.int64, device=dev)
+    key = (ids_t[None, :] * 1000003 + t[:, None]) * 2 + _i64(_FORCING_C)
+    h1 = _splitmix64_t(key)
+    h2 = _splitmix64_t(key + 1)
+    wet = _lsr(h1, 11).to(torch.float64) * (1.0 / 9007199254740992.0) < 0.03
+    P = torch.where(wet, _LUT_DEV[dev][_lsr(h2, 48)], torch.zeros((), dtype=torch.float64, device=dev))
+    pet = torch.from_numpy(pet_series(np.arange(hour0, hour0 + nhours))).to(dev)
+    return P.contiguous(), pet[:, None].expand(nhours, ids_t.shape[0]).contiguous()
+
+
 def host_forcing(ncol: int, hour0: int, nhours: int, seed: int):
-    """numpy version of the synthetic forcing (used by the CPU arm)."""
+    """numpy version of round 1's forcing (a numpy generator per worker): kept for tests/test_gpu_scale_parity.py"""
     rng = np.random.default_rng([777, seed, hour0])
     u1 = rng.random((nhours, ncol))
     u2 = rng.random((nhours, ncol))
@@ -164,13 +227,14 @@ def _cpu_worker(args):
                 orc.lib.lgo_run_series(C.byref(ps[c]), C.byref(ss[c]), P.shape[0], np.ascontiguousarray(P[:, c]).ctypes.data_as(C.POINTER(C.c_double)),
                                        np.ascontiguousarray(E[:, c]).ctypes.data_as(C.POINTER(C.c_double)), None, None, 0, None, None)
             return time.perf_counter() - t0
+    ids = np.arange(col0, col0 + ncol, dtype=np.int64)   # the same global columns, hours and forcing as the B200 arm
     hour = 0
     if spin_h:
-        P, E = host_forcing(ncol, hour, spin_h, wid)
+        P, E = forcing_np(ids, hour, spin_h)
         advance(P, E)
         hour += spin_h
     for nh, timed in blocks:
-        P, E = host_forcing(ncol, hour, nh, wid)
+        P, E = forcing_np(ids, hour, nh)
         dt = advance(P, E)
         hour += nh
         if timed:
@@ -199,7 +263,7 @@ def _exe_worker(args):
     soils = column_soils(col0, ncol)
     layers = column_layers(col0, ncol)
     base = (Path(cfg_dir) / "bench_config5.txt").read_text()
-    P, E = host_forcing(ncol, 0, hours, 1000 + wid)
+    P, E = forcing_np(np.arange(col0, col0 + ncol, dtype=np.int64), 0, hours)
     stamp = (np.datetime64("2016-10-01T00:00:00") + np.arange(hours).astype("timedelta64[h]")).astype(str)
     total = 0.0
     for c in range(ncol):
@@ -324,13 +388,168 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------------
+# pieces of the B200 arm
+# --------------------------------------------------------------------------------------------------
+def lib_sha256() -> str:
+    import hashlib
+    from lgar_c_b200.bmi import library_path
+    return hashlib.sha256(Path(library_path()).read_bytes()).hexdigest()
+
+
+def committed_window_profile():
+    """(traffic bytes per column-timestep, stage time shares, source) of the committed ncu capture if it belongs to this build"""
+    try:
+        p = json.loads(WINDOW_PROFILE.read_text())
+    except Exception:
+        return None, None, "no committed capture (profiles/r2_window_profile.json)"
+    if p.get("lib_sha256") != lib_sha256():
+        return None, None, f"the committed capture ({WINDOW_PROFILE.name}) was taken with another build of liblgarb.so"
+    return p.get("dram_bytes_per_column_timestep"), p.get("stage_time_share"), f"{WINDOW_PROFILE.name}: {p.get('source', '')}"
+
+
+def timed_call(b, ext, nh, dP, dE, stride):
+    """one lgarb_update_steps_device call of nh hours, device-timed on the engine's stream; returns milliseconds"""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    b.update_steps_device(nh, dP.data_ptr(), dE.data_ptr(), stride)
+    e1.record(ext)
+    e1.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def parity_block(cfgobj, ids, T, chunk, dev_index, cores, mode, what):
+    """The engine on the global columns `ids` of a BASELINE config for T forcing steps from the initial state, all 12 BMI scalars
+    and the front count of every step captured, diffed against the oracle on the host cores (tools/parity_sampling_full.py:
+    one of the places that may execute oracle/ -- as the checker).  Returns the JSON `parity` block."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    import parity_sampling_full as pf
+    pos = np.arange(len(ids))
+    hP, hE, scal, nf, status, final, info = pf.run_engine(cfgobj, ids, pos, T, chunk, mode)
+    r = pf.diff_against_oracle(cfgobj, ids, hP, hE, scal, nf, status, final, cores)
+    worst = max(v["worst_rel"] for v in r["scalars"].values())
+    return {"what": what, "columns": int(len(ids)), "steps_per_column": int(T), "column_steps_diffed": r["column_steps_diffed"],
+            "front_count_mismatch_columns": r["front_count_mismatch_columns"], "failure_mismatch_columns": r["failure_mismatch_columns"],
+            "columns_outside_1e-9": int(max(v["columns_outside_bar"] for v in r["scalars"].values())),
+            "columns_bit_equal_every_scalar_every_step": r["columns_bit_equal_every_scalar_every_step"],
+            "columns_with_bit_equal_final_fronts": r["columns_with_bit_equal_final_fronts"], "worst_rel": worst,
+            "frozen_columns_in_sample": r["frozen_columns_in_sample"], "oracle_cores": cores, "oracle_seconds": r["oracle_seconds"],
+            "bar": "1e-9 relative per step, no absolute floor (mass_balance residual: 1e-11 m absolute), front counts exact"}
+
+
+def run_config_workload(args, emit, rank, world, local_rank):
+    """--workload config3|config4|config5: the BASELINE config at its stated size over its full duration, this rank owning a
+    contiguous block of its columns: one timed pass (no output capture, forcing of a chunk resident before its call is timed) and
+    one parity pass over the seed-99 sample of the config's column range that falls into this rank's block."""
+    import torch
+    import lgar_c_b200
+    sys.path.insert(0, str(ROOT / "tools"))
+    import parity_sampling_full as pf
+    num = int(args.workload[-1])
+    tmp = Path(tempfile.mkdtemp(prefix="lgar_bench_"))
+    c = pf.Config(num, tmp)
+    n_total = args.columns_total or c.n_total
+    T = args.hours or c.steps
+    per = (n_total + world - 1) // world
+    col0, col1 = rank * per, min(n_total, (rank + 1) * per)
+    ids = np.arange(col0, col1, dtype=np.int64)
+    ncol = len(ids)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    b = lgar_c_b200.BmiLGARBatch()
+    b.initialize(c.cfg, ncol, local_rank, c.soils(ids), c.layers(ids))
+    b.set_window_mode(args.mode)
+    ext = torch.cuda.ExternalStream(b.get_stream(), device=dev)
+    dids = torch.from_numpy(ids).to(dev)
+    chunk = args.chunk_hours
+    sampler = ClockSampler(local_rank)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = b.get_launch_count()
+    ms = 0.0
+    for t0 in range(0, T, chunk):
+        nt = min(chunk, T - t0)
+        dP, dE = c.forcing(dids, t0, nt)      # generated on the device, resident before the timed call
+        torch.cuda.synchronize()
+        ms += timed_call(b, ext, nt, dP, dE, ncol)
+        del dP, dE
+    sampler.stop_flag.set()
+    launches = b.get_launch_count() - launches0
+    st = b.get_status()
+    n_failed = int(np.count_nonzero(st & lgar_c_b200.STATUS_FAIL_MASK))
+    gm = b.get_global_mass_balance()
+    ok = (st & lgar_c_b200.STATUS_FAIL_MASK) == 0
+    worst_gmb = float(np.abs(gm[ok, 15]).max()) if ok.any() else float("nan")
+    b.finalize()
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(ncol) * T, float(n_failed)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    value = float(tot[0].item()) / (float(t_ms.item()) * 1e-3)
+    # parity pass: the seed-99 sample of the whole config that lies in this rank's block, full duration
+    parity = None
+    if not args.no_parity:
+        sample = np.sort(np.random.default_rng(99).choice(c.n_total, args.parity_sample, replace=False)).astype(np.int64)
+        mine = sample[(sample >= col0) & (sample < col1)]
+        if len(mine):
+            parity = parity_block(c, mine, T, min(chunk, 240), local_rank, host_cores() // max(1, world), args.mode,
+                                  f"seed-99 sample of config {num} ({args.parity_sample} of {c.n_total} columns) in this rank's block, full duration, "
+                                  "in an engine of their own (a column's result does not depend on its batch: tests/test_gpu_scale_parity.py)")
+        if dist is not None:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, parity)
+            if rank == 0:
+                parts = [p for p in gathered if p]
+                parity = {k: (sum(p[k] for p in parts) if isinstance(parts[0][k], int) and k not in ("steps_per_column", "oracle_cores") else parts[0][k]) for k in parts[0]}
+                parity["worst_rel"] = max(p["worst_rel"] for p in parts)
+    if rank == 0:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        Bunit = 88 * 4.07 + 428
+        achieved = value / world * Bunit / 1e9
+        emit({"metric": "column-timesteps/sec", "value": value, "unit": "column-timesteps/s", "n_gpus": world, "steps": int(T), "warmup": 0,
+              "ms_per_step": float(t_ms.item()) / T, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+              "config": {"workload": args.workload, "columns_total": int(n_total), "columns_per_gpu": int(per), "forcing_steps": int(T), "chunk_hours": chunk,
+                         "what": f"BASELINE config {num} at its stated size over its full duration from the initial state, one call per chunk of forcing "
+                                 "(generated on the device and resident before the call is timed), no output capture in the timed pass",
+                         "l2": "inputs larger than L2: a chunk of forcing is > 10 GB per rank"},
+              "clocks": sampler.summary(), "gpu_launches": int(launches), "failed_columns": int(tot[1].item()),
+              "max_abs_global_mass_balance_cm": worst_gmb, "parity": parity, "e2e": None,
+              "roofline": {"bound": "hbm", "kernel": "window scheduler (six stage kernels)", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                           "traffic": None, "algorithmic_bytes_per_unit": Bunit,
+                           "note": "whole-path figure: B = 88 * 4.07 + 428 bytes per column-timestep (SURVEY.md 8d at the bench workload's mean front count) "
+                                   "x column-timesteps / device time; per-stage figures: the default workload's line"},
+              "target": {"colsteps_per_s_per_gpu": 1.25e9, "frac_of_target": value / world / 1.25e9}})
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--columns", type=int, default=1_250_000, help="columns per GPU")
+    ap.add_argument("--workload", default="config5-shard", choices=["config5-shard", "config3", "config4", "config5"],
+                    help="config5-shard: one GPU's share of BASELINE config 5, K steps of 48 h after a spin-up (the headline line); "
+                         "config3/4/5: the BASELINE config at its stated size over its full duration, with the seed-99 parity sample in the job")
+    ap.add_argument("--columns", type=int, default=1_250_000, help="columns per GPU (config5-shard)")
+    ap.add_argument("--columns-total", type=int, default=0, help="config3/4/5: total columns (0: the config's stated size)")
+    ap.add_argument("--hours", type=int, default=0, help="config3/4/5: forcing steps (0: the config's full duration)")
+    ap.add_argument("--chunk-hours", type=int, default=1460, help="config3/4/5 and the full-year extra: forcing hours per call")
+    ap.add_argument("--parity-sample", type=int, default=10_000)
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--hours-per-step", type=int, default=48)
     ap.add_argument("--spinup-hours", type=int, default=720)
     ap.add_argument("--e2e-hours", type=int, default=384)
@@ -339,6 +558,7 @@ def main():
     ap.add_argument("--cpu-hours", type=int, default=2880)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip value_by_call_hours, the full-year run, the stage timing window and the parity block")
     ap.add_argument("--finish-below", type=int, default=-1, help="wavefront: slots in flight below which the finishing kernel takes over (-1: engine default)")
     ap.add_argument("--mode", type=int, default=3, help="3 six stage kernels with queues between them, 2 lanes kernel, 1 warp-tile window kernel, 0 one kernel pair per forcing hour")
     args = ap.parse_args()
@@ -358,17 +578,22 @@ def main():
     workload = {"workload": "config5-shard", "columns_per_gpu": args.columns, "layers": 3, "giuh_ordinates": N_GIUH,
                 "hours_per_step": H, "spinup_hours": args.spinup_hours, "flags": "Phillipsburg_with_reservoir (CASAM)",
                 "soils": "12 parsed rows of vG_params_stat_nom_ordered.dat, i.i.d. per column and layer",
-                "forcing": "synthetic hourly, P(wet)=0.03, Exp(2.5 mm/h) cap 170, diurnal/seasonal PET",
+                "forcing": "synthetic hourly, P(wet)=0.03, Exp(2.5 mm/h) cap 170, diurnal/seasonal PET; counter-based, keyed by (global column, hour): "
+                           "both arms and the parity block compute the same doubles (bench.forcing_np / forcing_torch)",
+                "timed_region": "hours [spinup + warmup*H, + steps*H) of the simulation in ONE multi-step call, forcing resident in HBM",
                 "l2": "inputs larger than L2: state + one day of forcing > 1 GB per rank, nothing is reused between hours"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
+        if args.workload != "config5-shard":
+            emit({"impl": "reference", "unavailable": "the reference arm times the headline workload (config5-shard) only"})
+            return 0
         kind = cpu_kind()
         cores = host_cores()
         cpc = args.cpu_cols_per_core
         blocks = [(H, False)] * args.warmup + [(H, True)] * args.steps
-        per_block = run_cpu(kind, cores, cpc, min(args.spinup_hours, 240), blocks)
+        per_block = run_cpu(kind, cores, cpc, args.spinup_hours, blocks)
         total_s = float(per_block.sum())
         colsteps = cores * cpc * H * args.steps
         val = colsteps / total_s
@@ -376,7 +601,8 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
                 "cpu_baseline": {"value": val, "unit": "column-timesteps/s", "cores": cores, "kind": kind,
-                                 "sample": f"{cores} processes x {cpc} columns x {H} h per step, spin-up {min(args.spinup_hours, 240)} h; "
+                                 "sample": f"global columns 0..{cores * cpc - 1} of the workload ({cores} processes x {cpc} columns), the same hours as the B200 arm: "
+                                           f"{args.spinup_hours} h spin-up, {args.warmup} warm-up and {args.steps} timed steps of {H} h, the same forcing values; "
                                            "SetValue x2 -> Update -> GetValue(total_discharge) per column-step, no file I/O"},
                 "e2e": {"value": val, "unit": "column-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         line["cpu_baseline"]["standalone_executable"] = standalone_exe_entry(cores)
@@ -388,6 +614,8 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU path; use --impl reference for the CPU arm)")
+    if args.workload != "config5-shard":
+        return run_config_workload(args, emit, rank, world, local_rank)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -407,39 +635,22 @@ def main():
     if args.finish_below >= 0:
         b.set_wave_params(0, 0, args.finish_below)
     ext = torch.cuda.ExternalStream(b.get_stream(), device=dev)
-
-    # forcing ring on the device: R day-blocks, each [H][ncol]
-    # the timed region is ONE multi-step call (steps*H hours), so its forcing must be contiguous: the ring
-    # holds at least `steps` day-blocks (bounded: 8 bytes * 2 * H * ncol per block)
-    R = max(2, args.steps, min(args.warmup + args.steps, 16))
-    if R * H * ncol * 16 > 60e9:
+    dids = torch.arange(col0, col0 + ncol, dtype=torch.int64, device=dev)
+    if args.steps * H * ncol * 16 > 60e9:
         raise SystemExit("bench.py: steps*hours_per_step*columns needs more than 60 GB of forcing; lower --steps or --columns")
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(777 * 1000003 + rank)
-    dP = torch.empty((R * H, ncol), dtype=torch.float64, device=dev)
-    dE = torch.empty((R * H, ncol), dtype=torch.float64, device=dev)
-    pet = torch.from_numpy(pet_series(np.arange(R * H))).to(dev)
-    for blk in range(R):
-        u1 = torch.rand((H, ncol), generator=gen, device=dev, dtype=torch.float64)
-        u2 = torch.rand((H, ncol), generator=gen, device=dev, dtype=torch.float64)
-        sl = slice(blk * H, (blk + 1) * H)
-        dP[sl] = torch.where(u1 < 0.03, torch.clamp(-2.5 * torch.log1p(-u2), max=170.0), torch.zeros_like(u1))
-        dE[sl] = pet[sl, None].expand(H, ncol)
-        del u1, u2
+
+    # spin-up and warm-up: one call per step of H hours, forcing generated per call
+    hour = 0
+    for _ in range(max(0, args.spinup_hours // H) + args.warmup):
+        dP, dE = forcing_torch(dids, hour, H)
+        torch.cuda.synchronize()
+        b.update_steps_device(H, dP.data_ptr(), dE.data_ptr(), ncol)
+        b.synchronize()
+        hour += H
+        del dP, dE
+    # the forcing of the whole timed region, resident before the clock starts
+    dP, dE = forcing_torch(dids, hour, H * args.steps)
     torch.cuda.synchronize()
-
-    def run_block(blk):
-        o = (blk % R) * H
-        b.update_steps_device(H, dP[o].data_ptr(), dE[o].data_ptr(), ncol)
-
-    blk = 0
-    for _ in range(max(0, args.spinup_hours // H)):
-        run_block(blk)
-        blk += 1
-    for _ in range(args.warmup):
-        run_block(blk)
-        blk += 1
-    b.synchronize()
 
     def barrier():
         if dist is not None:
@@ -456,15 +667,14 @@ def main():
     if args.mode >= 3:
         # one call for the whole timed region: columns run ahead of each other across day boundaries
         b.update_steps_device(H * args.steps, dP.data_ptr(), dE.data_ptr(), ncol)
-        blk += args.steps
     else:
-        for _ in range(args.steps):
-            run_block(blk)
-            blk += 1
+        for k in range(args.steps):
+            b.update_steps_device(H, dP[k * H].data_ptr(), dE[k * H].data_ptr(), ncol)
     ev1.record(ext)
     ev1.synchronize()
     barrier()
     sampler.stop_flag.set()
+    hour += H * args.steps
     ms = ev0.elapsed_time(ev1)
     prof = b.get_profile()
     b.set_profiling(False)
@@ -484,13 +694,13 @@ def main():
     if not args.no_e2e:
         # the multi-step verb with HOST buffers: forcing of `nh` hours in from pinned host memory, one output
         # series (total_discharge, ngen's usual main_output_variable) back to pinned host memory, all inside
-        nh = min(args.e2e_hours, R * H)
+        nh = min(args.e2e_hours, H * args.steps)
         # three pinned [hours][columns] f64 series per rank: keep all ranks of the box within half of the host memory
         nh = max(H, min(nh, int(0.5 * host_memory_bytes() / max(1, world) / (3 * 8 * ncol))))
         nh2 = nh                           # the streamed call runs over the same hours; one set of pinned buffers serves both
         hP = torch.empty((nh2, ncol), dtype=torch.float64).pin_memory()
         hE = torch.empty((nh2, ncol), dtype=torch.float64).pin_memory()
-        hP.copy_(dP[:nh2])
+        hP.copy_(dP[:nh2])                 # the values do not matter for the timing: any hours of the workload
         hE.copy_(dE[:nh2])
         hQ = torch.empty((nh2, ncol), dtype=torch.float64).pin_memory()
         b.update_steps_host(hP.numpy()[:H], hE.numpy()[:H], {"total_discharge": hQ.numpy()[:H]})  # warm-up: allocates the staging
@@ -538,12 +748,89 @@ def main():
         torch.cuda.synchronize()
         e2e["hourly_bmi_loop"] = {"value": ncol * nhh / (time.perf_counter() - t0), "unit": "column-timesteps/s (this rank)",
                                   "note": "SetValue x2, Update, GetValue(total_discharge) per forcing hour with host buffers"}
+        del hP, hE, hQ
 
-    # ---- end-of-run gather of per-column summaries over NCCL (outside every timed region) -------
-    from lgar_c_b200.sharding import gather_summaries
-    summary = torch.from_numpy(b.get_global_mass_balance(0, min(ncol, 65536))[:, [3, 15]].copy()).to(dev)
-    summary = gather_summaries(summary, dist, dst=0)
-    max_global_balance = float(summary[:, 1].abs().nan_to_num().max().item()) if summary is not None else 0.0
+    # ---- what a caller gets for other call lengths, live stage times, a full year, parity in the job (N = 1) ----
+    extras = world == 1 and not args.no_extras and args.mode >= 3
+    by_call, stage_times, full_year, parity = None, None, None, None
+    if extras:
+        by_call = {}
+        for nh in (48, 240, 960):
+            if nh > H * args.steps:
+                del dP, dE
+                dP, dE = forcing_torch(dids, hour, nh)
+            torch.cuda.synchronize()
+            by_call[str(nh)] = ncol * nh / (timed_call(b, ext, nh, dP, dE, ncol) * 1e-3)
+            hour += nh
+        # stage times of one 240 h window, CUDA events round every stage launch (lgarb_set_stage_timing)
+        b.set_stage_timing(True)
+        torch.cuda.synchronize()
+        ms240 = timed_call(b, ext, 240, dP, dE, ncol)
+        hour += 240
+        stt = b.get_stage_times()
+        b.set_stage_timing(False)
+        tot_ms = sum(v[0] for v in stt.values())
+        stage_times = {"window_hours": 240, "window_ms": ms240,
+                       "stages": {k: {"ms": v[0], "launches": v[1], "share_of_stage_time": v[0] / tot_ms if tot_ms else None} for k, v in stt.items()},
+                       "note": "one extra 240 h call after the timed region with an event pair round every stage launch; CORR runs on a side stream beside "
+                               "the other stages, so the stage times add up to more than the window"}
+    # ---- end-of-run gather over NVLink (NCCL): the terms of lgar_global_mass_balance (reference src/lgar.cxx:1162-1216) of EVERY
+    # column of every rank onto rank 0, and the all-reduced balance totals; outside the step timing, timed on its own ----
+    gm = b.get_global_mass_balance()                      # [ncol][16] cm, host
+    ok = (st & lgar_c_b200.STATUS_FAIL_MASK) == 0
+    max_global_balance = float(np.abs(gm[ok, 15]).max()) if ok.any() else None
+    gather = None
+    if dist is not None:
+        from lgar_c_b200.sharding import gather_summaries, reduce_totals
+        summ = torch.from_numpy(gm).to(dev)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        allsum = gather_summaries(summ, dist, dst=0)
+        totals = reduce_totals(torch.nan_to_num(summ).sum(dim=0), dist)
+        g1.record()
+        g1.synchronize()
+        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        mgb = torch.tensor([max_global_balance or 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(mgb, op=dist.ReduceOp.MAX)
+        max_global_balance = float(mgb.item())
+        if rank == 0:
+            gather = {"ms": float(gms.item()), "columns": int(allsum.shape[0]), "values_per_column": int(allsum.shape[1]), "bytes_received": int(allsum.numel() * 8 * (world - 1) // world),
+                      "totals_cm": {"precip": float(totals[1].item()), "infiltration": float(totals[2].item()), "AET": float(totals[7].item()), "discharge": float(totals[10].item())},
+                      "what": "NCCL gather of the 16 terms of the global mass balance of every column of every rank onto rank 0 + all-reduce of their sums, device-timed, max over ranks"}
+        del summ, allsum
+    del dP, dE
+    b.finalize()
+    torch.cuda.empty_cache()
+    if extras:
+        # the full year of the config-5 shard from the initial state, forcing generated chunk by chunk (untimed) and resident before its call
+        b2 = lgar_c_b200.BmiLGARBatch()
+        b2.initialize(cfg, ncol, local_rank, column_soils(col0, ncol), column_layers(col0, ncol))
+        b2.set_window_mode(args.mode)
+        ext2 = torch.cuda.ExternalStream(b2.get_stream(), device=dev)
+        yms, T = 0.0, 8760
+        for t0 in range(0, T, args.chunk_hours):
+            nt = min(args.chunk_hours, T - t0)
+            dP, dE = forcing_torch(dids, t0, nt)
+            torch.cuda.synchronize()
+            yms += timed_call(b2, ext2, nt, dP, dE, ncol)
+            del dP, dE
+        st2 = b2.get_status()
+        full_year = {"value": ncol * T / (yms * 1e-3), "unit": "column-timesteps/s", "hours": T, "chunk_hours": args.chunk_hours, "device_seconds": yms * 1e-3,
+                     "failed_columns": int(np.count_nonzero(st2 & lgar_c_b200.STATUS_FAIL_MASK)),
+                     "note": "BASELINE config 5's one-year run for this GPU's 1.25 M columns from the initial state, one call per chunk of forcing"}
+        by_call["8760"] = full_year["value"]
+        b2.finalize()
+        torch.cuda.empty_cache()
+        # parity in the job: 512 columns of this shard over the hours the timed engine has simulated, against the oracle
+        sys.path.insert(0, str(ROOT / "tools"))
+        import parity_sampling_full as pf
+        sample = col0 + np.sort(np.random.default_rng(99).choice(ncol, 512, replace=False)).astype(np.int64)
+        Tp = args.spinup_hours + (args.warmup + args.steps) * H
+        parity = parity_block(pf.Config(5, tmp), sample, Tp, 240, local_rank, host_cores(), args.mode,
+                              f"512 columns of this shard (seed 99) over the {Tp} h the timed engine simulated (spin-up, warm-up, timed region), in an engine "
+                              "of their own; the 10 000-column full-duration samples of configs 3/4/5: --workload config3|config4|config5")
 
     if rank != 0:
         if dist is not None:
@@ -563,12 +850,25 @@ def main():
     B_full = 16 + 12 * L + 2 * (44 * mean_fronts + 88 + 8 * (NG + 1)) + 104      # 88*n_wf + 428
     B_nofront = B_full - 2 * 44 * mean_fronts
     ms_s, ms_a, ms_w = prof["ms_stream"], prof["ms_active"], prof["ms_window"]
-    if ms_w > 0:  # window mode: one kernel per bench step (H forcing hours for every column)
-        dominant = {3: "lgar_wave_kernel<*> + lgar_wave_fetch_kernel (6 stage kernels)", 2: "lgar_lanes_kernel", 1: "lgar_window_kernel"}[args.mode]
+    traffic_unit, share_ncu, traffic_src = committed_window_profile()
+    dominant_block = None
+    if ms_w > 0:  # window mode: the whole timed call is one window
         units = ncol * H
         B_unit = B_full
-        dur_s = ms_w * 1e-3 / args.steps  # per bench step (one day of every column); mode 3 runs all steps in one call
-        share = {dominant: 1.0}
+        dur_s = ms_w * 1e-3 / args.steps  # per bench step (H forcing hours of every column)
+        dominant = "window scheduler: " + {3: "lgar_wave_kernel<FETCH..CORR> + lgar_wave_fetch_kernel + lgar_wave_finish_kernel", 2: "lgar_lanes_kernel", 1: "lgar_window_kernel"}[args.mode]
+        share = None
+        if stage_times:
+            st_ = stage_times["stages"]
+            top = max(st_, key=lambda k: st_[k]["ms"])
+            names = {"FETCH": "lgar_wave_fetch_kernel", "HEAD": "lgar_wave_kernel<1> (HEAD)", "FRONT": "lgar_wave_kernel<2> (FRONT)", "SEARCH": "lgar_wave_kernel<3> (SEARCH)",
+                     "TAIL": "lgar_wave_kernel<4> (TAIL)", "CORR": "lgar_wave_kernel<5> (CORR)", "FINISH": "lgar_wave_finish_kernel"}
+            share = {names[k]: v["share_of_stage_time"] for k, v in st_.items()}
+            u240 = ncol * 240
+            dominant_block = {"kernel": names[top], "share_of_stage_time": st_[top]["share_of_stage_time"], "launches_per_240h_window": st_[top]["launches"],
+                              "avg_launch_ms": st_[top]["ms"] / max(1, st_[top]["launches"]), "ms_per_240h_window": st_[top]["ms"],
+                              "achieved_gbs_if_it_were_the_whole_path": u240 * B_unit / (st_[top]["ms"] * 1e-3) / 1e9,
+                              "note": "the kernel with the largest share of the stage time of a 240 h window, timed live with CUDA events on its stream"}
     else:
         dominant = "lgar_step_active_kernel" if ms_a >= ms_s else "lgar_step_stream_kernel"
         if dominant == "lgar_step_active_kernel":
@@ -578,26 +878,22 @@ def main():
         share = {"lgar_step_stream_kernel": ms_s / (ms_s + ms_a), "lgar_step_active_kernel": ms_a / (ms_s + ms_a)}
     bytes_per_launch = units * B_unit
     achieved = bytes_per_launch / dur_s / 1e9
-    # DRAM bytes per launch unit from the committed ncu capture of one whole timed window of this command in mode 3
-    # (profiles/r1_window_launches.csv, tools/prof_window.sh: dram__bytes_read.sum + dram__bytes_write.sum over the 2 725
-    # launches of a 240 h window of 1.25 M columns = 1 024.9 GB = 3 416 B per column-timestep); null for any other mode
-    traffic = TRAFFIC_B_PER_UNIT * units if (args.mode == 3 and ms_w > 0) else None
-    share_ncu = ({"TAIL": 0.283, "HEAD": 0.162, "SEARCH": 0.157, "FRONT": 0.121, "finish": 0.115, "CORR": 0.089, "FETCH": 0.066}
-                 if (args.mode == 3 and ms_w > 0) else None)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "traffic_source": "ncu launch list of one 240 h window, profiles/r1_window_launches.csv (r1_session3_ncu_summary.md)" if traffic else None,
+                "traffic": traffic_unit * units if (traffic_unit and args.mode == 3 and ms_w > 0) else None, "traffic_source": traffic_src,
                 "stage_time_share_ncu": share_ncu, "peak_source": peak_src, "algorithmic_bytes_per_unit": B_unit,
-                "units_per_launch": units, "avg_launch_ms": dur_s * 1e3, "kernel_time_share": share,
+                "units_per_launch": units, "avg_launch_ms": dur_s * 1e3, "kernel_time_share": share, "dominant": dominant_block,
                 "mean_fronts": mean_fronts, "active_fraction": active_frac,
                 "note": "unit = one column-timestep; a launch = one bench step (--hours-per-step forcing hours of every column; the stage kernels of a "
-                        "window are timed together with CUDA events on the engine stream); B = 88*mean_fronts + 428 bytes (SURVEY.md 8d). "
-                        "Measured DRAM traffic is 4.3x the algorithmic bytes (step contexts crossing HBM at every stage boundary); the path is "
-                        "latency/divergence bound, not HBM bound: DESIGN.md section 4.4"}
+                        "window are timed together with CUDA events on the engine stream); B = 88*mean_fronts + 428 bytes (SURVEY.md 8d); "
+                        "`frac` is the whole-path figure, `dominant` the stage kernel with the largest live share; the path is latency/divergence "
+                        "bound, not HBM bound: DESIGN.md section 4.4"}
 
-    # secondary roofline: FP64 pipe peak from a DFMA microbenchmark on this GPU; what the stage kernels use of
-    # it is an ncu counter (sm__inst_executed_pipe_fp64, profiles/): 38 % in SEARCH, below 15 % elsewhere
+    # secondary roofline: FP64 pipe peak from a DFMA microbenchmark on this GPU
     try:
-        roofline["fp64_peak_tflops_measured"] = b.measure_fp64_peak(40.0)
+        bb = lgar_c_b200.BmiLGARBatch()
+        bb.initialize(cfg, 32, local_rank)
+        roofline["fp64_peak_tflops_measured"] = bb.measure_fp64_peak(40.0)
+        bb.finalize()
     except Exception as ex:  # diagnostics only
         roofline["fp64_peak_tflops_measured"] = None
         print(f"bench.py: DFMA microbenchmark failed: {ex}", file=sys.stderr)
@@ -609,14 +905,15 @@ def main():
         cpc = args.cpu_cols_per_core
         per_block = run_cpu(kind, cores, cpc, 240, [(args.cpu_hours, True)])
         cpu = {"value": cores * cpc * args.cpu_hours / float(per_block.sum()), "unit": "column-timesteps/s", "cores": cores, "kind": kind,
-               "sample": f"{cores} processes x {cpc} columns x {args.cpu_hours} h of the same workload after a 240 h spin-up; "
-                         "SetValue x2 -> Update -> GetValue(total_discharge) per column-step, no file I/O"}
+               "sample": f"global columns 0..{cores * cpc - 1} of the workload ({cores} processes x {cpc} columns) x {args.cpu_hours} h after a 240 h spin-up, "
+                         "the workload's own forcing values; SetValue x2 -> Update -> GetValue(total_discharge) per column-step, no file I/O"}
         cpu["standalone_executable"] = standalone_exe_entry(cores)
 
     line = {"metric": "column-timesteps/sec", "value": value, "unit": "column-timesteps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload, "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "failed_columns": n_failed, "max_abs_global_mass_balance_cm": max_global_balance,
+            "gather": gather, "value_by_call_hours": by_call, "full_year": full_year, "stage_times": stage_times, "parity": parity, "lib_sha256": lib_sha256(),
             "target": {"colsteps_per_s_per_gpu": 1.25e9, "frac_of_target": value / world / 1.25e9}}
     emit(line)
     if dist is not None:

@@ -253,6 +253,12 @@ int lgarb_debug_pow(lgarb_engine* e, int64_t n, const double* x, const double* y
  * bottom crossing, dry-over-wet, theta < theta_r deletion, saturated-front depth loop, ..., every exit of the psi search; the
  * LGAR_PATH_* numbering of lgar_c_b200/csrc/lgar_types.h = LGO_PATH_* of oracle/lgar_oracle.h; reference src/lgar.cxx:1519-1537,
  * 1687-1723,1875-2307,3063-3086,3116-3195).  Evidence for tests, off by default (one predicated atomic per rare event when on). */
+/* Stage timing of the multi-step verbs: with it on, every launch of a stage kernel (FETCH, HEAD, FRONT, SEARCH, TAIL, CORR) and of
+ * the finishing kernel is bracketed by a CUDA event pair on the stream it is launched on; lgarb_get_stage_times returns the
+ * accumulated milliseconds and launch counts per stage (7 entries each, the finishing kernel last) and clears nothing.  The
+ * correction searches run on a side stream beside the main one, so the sum of the stage times may exceed the window's time. */
+int lgarb_set_stage_timing(lgarb_engine* e, int on);
+int lgarb_get_stage_times(lgarb_engine* e, double* ms7, int64_t* launches7);
 int lgarb_set_path_counters(lgarb_engine* e, int on);
 int lgarb_get_path_counters(lgarb_engine* e, uint64_t* out, int n);
 

@@ -136,6 +136,8 @@ def _load():
         "lgarb_measure_fp64_peak": ([vp, C.c_double, dp], C.c_int),
         "lgarb_debug_pow": ([vp, C.c_int64, vp, vp, vp, C.c_int], C.c_int),
         "lgarb_set_path_counters": ([vp, C.c_int], C.c_int),
+        "lgarb_set_stage_timing": ([vp, C.c_int], C.c_int),
+        "lgarb_get_stage_times": ([vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)], C.c_int),
         "lgarb_get_path_counters": ([vp, C.POINTER(C.c_uint64), C.c_int], C.c_int),
         "lgarb_set_profiling": ([vp, C.c_int], C.c_int),
         "lgarb_get_profile": ([vp, dp], C.c_int),
@@ -494,6 +496,16 @@ class BmiLGARBatch:
         out = C.c_double(0.0)
         self._ck(self._L.lgarb_measure_fp64_peak(self._h, float(ms), C.byref(out)))
         return out.value
+
+    def set_stage_timing(self, on=True):
+        self._ck(self._L.lgarb_set_stage_timing(self._h, int(bool(on))))
+
+    def get_stage_times(self):
+        """{stage: (milliseconds, launches)} accumulated since set_stage_timing(True): FETCH, HEAD, FRONT, SEARCH, TAIL, CORR, FINISH"""
+        ms = (C.c_double * 7)()
+        n = (C.c_int64 * 7)()
+        self._ck(self._L.lgarb_get_stage_times(self._h, ms, n))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("FETCH", "HEAD", "FRONT", "SEARCH", "TAIL", "CORR", "FINISH"))}
 
     def set_path_counters(self, on=True):
         self._ck(self._L.lgarb_set_path_counters(self._h, int(bool(on))))

@@ -242,9 +242,7 @@ inline LgarConfig make_engine_config(const ParsedConfig& pc) {
   g.free_drainage_enabled = pc.free_drainage_enabled; g.free_drainage_to_CR = pc.free_drainage_to_CR;
   g.PET_affects_precip = pc.PET_affects_precip;
   g.nint = 120;  // lgar.cxx:992
-  g.ponded_depth_max_cm = pc.ponded_depth_max;
-  g.a = pc.a; g.b = pc.b; g.frac_to_CR = pc.frac_to_CR; g.a_slow = pc.a_slow; g.b_slow = pc.b_slow; g.frac_slow = pc.frac_slow;
-  g.spf_factor = pc.spf_factor; g.mbal_tol = pc.mbal_tol;
+  g.mbal_tol = pc.mbal_tol;
   g.timestep_h = pc.timestep_h; g.forcing_resolution_h = pc.forcing_resolution_h;
   g.initial_psi_cm = pc.initial_psi; g.wilting_point_psi_cm = pc.wilting_point_psi; g.field_capacity_psi_cm = pc.field_capacity_psi;
   int factor = int(1.0 / pc.forcing_resolution_h);
@@ -306,9 +304,17 @@ inline void check_column_class(const ParsedConfig& pc, int soils_in_file, int L,
   }
 }
 
+// reservoir / preferential-flow / ponding parameters of a class row from the (possibly calibrated) configuration values
+inline void fill_class_params(LgarColumnClass& c, const ParsedConfig& pc) {
+  c.par.a = pc.a; c.par.b = pc.b; c.par.frac_to_CR = pc.frac_to_CR;
+  c.par.a_slow = pc.a_slow; c.par.b_slow = pc.b_slow; c.par.frac_slow = pc.frac_slow;
+  c.par.spf_factor = pc.spf_factor; c.par.ponded_depth_max_cm = pc.ponded_depth_max;
+}
+
 inline LgarColumnClass make_class(const ParsedConfig& pc, const std::vector<SoilRow>& soils, int num_layers, const int* types, const double* thick) {
   LgarColumnClass c;
   memset(&c, 0, sizeof(c));
+  fill_class_params(c, pc);
   const int L = num_layers;
   c.num_layers = L;
   c.cum[0] = 0.0;
@@ -332,6 +338,7 @@ inline LgarColumnClass make_class(const ParsedConfig& pc, const std::vector<Soil
 inline LgarColumnClass make_class_from_rows(const ParsedConfig& pc, const SoilRow* rows, int num_layers, const double* thick) {
   LgarColumnClass c;
   memset(&c, 0, sizeof(c));
+  fill_class_params(c, pc);
   c.num_layers = num_layers;
   c.cum[0] = 0.0;
   for (int k = 1; k <= num_layers; k++) c.cum[k] = c.cum[k - 1] + thick[k - 1];

@@ -69,7 +69,8 @@ struct lgarb_engine {
   std::vector<double> col_thick;          // [ncol][L] layer thicknesses (empty: the configuration's)
   bool calib_pending = false, calib_touched = false;
   std::vector<double> calib_soil[15];     // [layer 1..3][smcmax, smcmin, vg_n, vg_alpha, Ksat] -> [ncol], allocated when first set
-  double calib_glob[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // field_capacity, ponded_depth_max, a, b, frac_to_CR, a_slow, b_slow, frac_slow, spf_factor
+  double calib_glob[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // field_capacity, ponded_depth_max, a, b, frac_to_CR, a_slow, b_slow, frac_slow, spf_factor: what Initialize() gives every column
+  std::vector<double> calib_glob_col[9];  // the same per column ([ncol], allocated when first set): every column may carry its own set
   std::vector<double> volchange_calib;    // [ncol] cm, change of stored water by the parameter update
   // SFT coupling (sft_coupled=true): soil temperature profile per column -> frozen_factor per layer (lgar.cxx:1109-1149)
   std::vector<double> soil_temperature;   // [ncol][num_cells_temp] K, zero until set (lgar.cxx:947)
@@ -127,6 +128,12 @@ struct lgarb_engine {
   int force_all_active = 0;
   int64_t steps = 0;
   int64_t launches = 0;
+  // stage timing (lgarb_set_stage_timing): an event pair round every stage launch of the window scheduler, resolved lazily
+  bool stage_timing = false;
+  struct StageEv { cudaEvent_t a, b; int stage; };
+  std::vector<StageEv> stage_evs;
+  double stage_ms[LGAR_NSTAGE + 1] = {0, 0, 0, 0, 0, 0, 0};   // FETCH, HEAD, FRONT, SEARCH, TAIL, CORR, finishing kernel
+  int64_t stage_launches[LGAR_NSTAGE + 1] = {0, 0, 0, 0, 0, 0, 0};
   // profiling (lgarb_set_profiling): event triples per step, resolved lazily
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -164,6 +171,12 @@ struct lgarb_engine {
     host_series_cap = 0;
     free_stream_bufs(sbufs);
     sbufs = nullptr;
+    for (auto& se : stage_evs) {
+      cudaEventDestroy(se.a);
+      cudaEventDestroy(se.b);
+    }
+    stage_evs.clear();
+    stage_timing = false;
     for (cudaEvent_t x : ev_pool) cudaEventDestroy(x);
     for (int i = 0; i < 2; i++) {
       if (win_ev[i]) cudaEventDestroy(win_ev[i]);
@@ -265,6 +278,7 @@ void do_initialize_body(lgarb_engine* e, const char* config_file, int64_t ncol, 
   e->calib_pending = pc.calib_params;  // lgar.cxx:742: applied once, at the first Update
   e->calib_touched = false;
   for (auto& v : e->calib_soil) v.clear();
+  for (auto& v : e->calib_glob_col) v.clear();
   e->volchange_calib.clear();
   {  // lgar.cxx:105-113
     const double g0[9] = {pc.field_capacity_psi, pc.ponded_depth_max, pc.a, pc.b, pc.frac_to_CR, pc.a_slow, pc.b_slow, pc.frac_slow, pc.spf_factor};
@@ -419,27 +433,32 @@ void apply_calibration(lgarb_engine* e) {
   const int L = e->num_layers;
   const int64_t ncol = e->ncol;
   const size_t st = (size_t)e->stride;
-  // parameters that do not depend on the layer (:1031-1049)
-  pc.field_capacity_psi = e->calib_glob[0];
-  pc.ponded_depth_max = e->calib_glob[1];
-  pc.a = e->calib_glob[2];
-  pc.b = e->calib_glob[3];
-  pc.frac_to_CR = e->calib_glob[4];
-  pc.spf_factor = e->calib_glob[8];
-  if (pc0.frac_slow) {
-    pc.a_slow = e->calib_glob[5];
-    pc.b_slow = e->calib_glob[6];
-    pc.frac_slow = e->calib_glob[7];
-  }
-  if (pc.log_mode) {
-    pc.a = pow(10.0, e->calib_glob[2]);
-    if (pc0.frac_slow) pc.a_slow = pow(10.0, e->calib_glob[5]);
-  }
-  LgarConfig& g = e->cfg;
-  g.field_capacity_psi_cm = pc.field_capacity_psi;
-  g.ponded_depth_max_cm = pc.ponded_depth_max;
-  g.a = pc.a; g.b = pc.b; g.frac_to_CR = pc.frac_to_CR; g.spf_factor = pc.spf_factor;
-  g.a_slow = pc.a_slow; g.b_slow = pc.b_slow; g.frac_slow = pc.frac_slow;
+  // parameters that do not depend on the layer (:1031-1049): per column, written into a scratch copy of the configuration from
+  // which the column's class row is made
+  ParsedConfig pcc = pc0;
+  auto glob = [&](int gi, int64_t c) { return e->calib_glob_col[gi].empty() ? e->calib_glob[gi] : e->calib_glob_col[gi][(size_t)c]; };
+  auto column_config = [&](int64_t c) {
+    pcc.field_capacity_psi = glob(0, c);
+    pcc.ponded_depth_max = glob(1, c);
+    pcc.a = glob(2, c);
+    pcc.b = glob(3, c);
+    pcc.frac_to_CR = glob(4, c);
+    pcc.spf_factor = glob(8, c);
+    if (pc0.frac_slow) {
+      pcc.a_slow = glob(5, c);
+      pcc.b_slow = glob(6, c);
+      pcc.frac_slow = glob(7, c);
+    }
+    if (pc0.log_mode) {
+      pcc.a = pow(10.0, glob(2, c));
+      if (pc0.frac_slow) pcc.a_slow = pow(10.0, glob(5, c));
+    }
+  };
+  column_config(0);
+  // the batch-level copy keeps column 0's values (what the metadata verbs report when every column has the same set)
+  pc.field_capacity_psi = pcc.field_capacity_psi; pc.ponded_depth_max = pcc.ponded_depth_max; pc.a = pcc.a; pc.b = pcc.b;
+  pc.frac_to_CR = pcc.frac_to_CR; pc.spf_factor = pcc.spf_factor; pc.a_slow = pcc.a_slow; pc.b_slow = pcc.b_slow; pc.frac_slow = pcc.frac_slow;
+  e->cfg.field_capacity_psi_cm = pc.field_capacity_psi;
 
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   std::vector<int32_t> nf((size_t)ncol);
@@ -488,6 +507,7 @@ void apply_calibration(lgarb_engine* e) {
       thick[k] = e->col_thick.empty() ? pc.layer_thickness[k] : e->col_thick[(size_t)c * L + k];
     }
     std::vector<double> key;
+    column_config(c);
     if (old.invalid_soil_type) {  // no fronts, precipitation passes through: the class stays what it is
       key.assign(1, -1.0 - e->class_of[c]);
     } else {
@@ -523,6 +543,10 @@ void apply_calibration(lgarb_engine* e) {
       e->volchange_calib[(size_t)c] = after - before;
       storage[(size_t)c] = after;
       for (int k = 0; k < L; k++) key.push_back(thick[k]);
+      {
+        const double gk[9] = {pcc.field_capacity_psi, pcc.ponded_depth_max, pcc.a, pcc.b, pcc.frac_to_CR, pcc.a_slow, pcc.b_slow, pcc.frac_slow, pcc.spf_factor};
+        key.insert(key.end(), gk, gk + 9);
+      }
       for (int k = 1; k <= L; k++) {
         const SoilRow& r = rows[k];
         const double f[10] = {r.theta_r, r.theta_e, r.alpha, r.n, r.m, r.lambda, r.psib, r.h_min, r.Ksat, r.theta_wp};
@@ -532,7 +556,7 @@ void apply_calibration(lgarb_engine* e) {
     auto it = seen.find(key);
     if (it == seen.end()) {
       const int id = (int)classes.size();
-      classes.push_back(old.invalid_soil_type ? old : make_class_from_rows(pc, rows.data(), L, thick.data()));
+      classes.push_back(old.invalid_soil_type ? old : make_class_from_rows(pcc, rows.data(), L, thick.data()));
       it = seen.emplace(std::move(key), id).first;
     }
     class_of[(size_t)c] = it->second;
@@ -702,7 +726,8 @@ void get_value_range(lgarb_engine* e, const std::string& name, int64_t col0, int
     if (si >= 0 || gi >= 0) {
       std::vector<double> v((size_t)ncol);
       for (int64_t c = 0; c < ncol; c++)
-        v[(size_t)c] = gi >= 0 ? e->calib_glob[gi] : e->calib_soil[si].empty() ? calib_soil_initial(e, si, col0 + c) : e->calib_soil[si][(size_t)(col0 + c)];
+        v[(size_t)c] = gi >= 0 ? (e->calib_glob_col[gi].empty() ? e->calib_glob[gi] : e->calib_glob_col[gi][(size_t)(col0 + c)])
+                               : e->calib_soil[si].empty() ? calib_soil_initial(e, si, col0 + c) : e->calib_soil[si][(size_t)(col0 + c)];
       if (dest_is_device) CUDA_TRY(cudaMemcpy(dest, v.data(), (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice));
       else memcpy(dest, v.data(), (size_t)ncol * sizeof(double));
       return;
@@ -748,11 +773,10 @@ void set_value_range(lgarb_engine* e, const std::string& name, int64_t col0, int
       }
       for (int64_t c = 0; c < ncol; c++) a[(size_t)(col0 + c)] = v[(size_t)c];
     } else {
-      // the reservoir / ponding / field-capacity parameters are kernel constants of the batch
-      for (int64_t c = 1; c < ncol; c++)
-        if (v[(size_t)c] != v[0]) throw std::runtime_error("variable " + name + " must have the same value for every column of a batch");
-      if (ncol != e->ncol && v[0] != e->calib_glob[gi]) throw std::runtime_error("variable " + name + " can only be set for the whole batch");
-      e->calib_glob[gi] = v[0];
+      // reservoir / ponding / field-capacity parameters: per column like the soil parameters (they live in the class row)
+      std::vector<double>& a = e->calib_glob_col[gi];
+      if (a.empty()) a.assign((size_t)e->ncol, e->calib_glob[gi]);
+      for (int64_t c = 0; c < ncol; c++) a[(size_t)(col0 + c)] = v[(size_t)c];
     }
     e->calib_touched = true;
     return;
@@ -857,7 +881,7 @@ int lgarb_update(lgarb_engine* e) {
     require_init(e);
     apply_calibration(e);
     update_frozen_factors(e);
-    if (e->use_window >= 3 && !e->pc.sft_coupled && e->ncol >= e->update_wave_min_cols) {
+    if (e->use_window >= 3 && e->ncol >= e->update_wave_min_cols) {
       // Large batch: one forcing hour as a window of one step through the wavefront kernels.  The kernel pair below
       // makes every active column of the hour wait for the slowest psi search in its warp; the stage kernels do not.
       if (lgarb_update_steps_device(e, 1, e->d_precip, e->d_pet, e->stride, nullptr, e->stride, nullptr) != LGARB_SUCCESS)
@@ -958,8 +982,18 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       cudaEventRecord(dbg_evs.back().first, e->stream);
       dbg_evs.back().second = stage;
     }
+    lgarb_engine::StageEv se{nullptr, nullptr, stage};
+    if (e->stage_timing) {
+      CUDA_TRY(cudaEventCreate(&se.a));
+      CUDA_TRY(cudaEventCreate(&se.b));
+      CUDA_TRY(cudaEventRecord(se.a, launch_stream));
+    }
     CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, stage == LG_ST_CORR ? std::max(1, quantum * e->wave_corr_quantum / e->wave_quantum) : quantum, in_flight,
                                     e->sm_count, launch_stream));
+    if (e->stage_timing) {
+      CUDA_TRY(cudaEventRecord(se.b, launch_stream));
+      e->stage_evs.push_back(se);
+    }
     e->launches += 2;
   };
   int32_t* h_cnt = (int32_t*)e->pinned(64 * sizeof(int32_t));
@@ -986,7 +1020,17 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       if (in_flight <= e->wave_finish_below) {  // the stragglers: one thread per slot runs its column to the end of the window
         if (debug) cudaEventRecord(dbg[0], e->stream);
         w.use_ff = 1;
+        lgarb_engine::StageEv se{nullptr, nullptr, LGAR_NSTAGE};
+        if (e->stage_timing) {
+          CUDA_TRY(cudaEventCreate(&se.a));
+          CUDA_TRY(cudaEventCreate(&se.b));
+          CUDA_TRY(cudaEventRecord(se.a, e->stream));
+        }
         CUDA_TRY(lgar_launch_wave_finish(e->cfg, e->d, w, wv, in_flight, e->finish_lane_stride, e->sm_count, e->stream));
+        if (e->stage_timing) {
+          CUDA_TRY(cudaEventRecord(se.b, e->stream));
+          e->stage_evs.push_back(se);
+        }
         e->launches += 2;
         if (debug) {
           cudaEventRecord(dbg[1], e->stream);
@@ -1079,7 +1123,7 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
     update_frozen_factors(e);  // an SFT-coupled run keeps the current temperature profile for the whole call
     if (n_steps < 0 || !d_precip || !d_pet || series_stride < e->ncol) throw std::runtime_error("bad forcing series");
     if ((d_sinks || d_nfronts_sink) && sink_stride < e->ncol) throw std::runtime_error("bad sink stride");
-    if (!e->use_window || e->pc.sft_coupled) {  // the window schedulers run uncoupled columns only
+    if (!e->use_window || (e->pc.sft_coupled && e->use_window != 3)) {  // SFT-coupled runs: hour by hour, or the stage kernels (frozen factors per lane record)
       for (int64_t t = 0; t < n_steps; t++) {
         LgarSinks sinks;
         for (int k = 0; k < LGAR_NOUT; k++) sinks.p[k] = (d_sinks && d_sinks[k]) ? d_sinks[k] + t * sink_stride : nullptr;
@@ -1578,6 +1622,44 @@ int lgarb_get_warp_times(lgarb_engine* e, uint32_t* out16384) {
     require_init(e);
     if (!e->d_work_trace) throw std::runtime_error("work trace is off");
     d2h(e, out16384, e->d_work_trace + 2 * e->stride + 64, 2 * 8192 * sizeof(uint32_t));
+  });
+}
+int lgarb_set_stage_timing(lgarb_engine* e, int on) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (e->side_stream) CUDA_TRY(cudaStreamSynchronize(e->side_stream));
+    for (auto& se : e->stage_evs) {
+      cudaEventDestroy(se.a);
+      cudaEventDestroy(se.b);
+    }
+    e->stage_evs.clear();
+    for (int s = 0; s <= LGAR_NSTAGE; s++) {
+      e->stage_ms[s] = 0.0;
+      e->stage_launches[s] = 0;
+    }
+    e->stage_timing = on != 0;
+  });
+}
+int lgarb_get_stage_times(lgarb_engine* e, double* ms7, int64_t* launches7) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (!ms7 || !launches7) throw std::runtime_error("null result pointer");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (e->side_stream) CUDA_TRY(cudaStreamSynchronize(e->side_stream));
+    for (auto& se : e->stage_evs) {
+      float ms = 0;
+      CUDA_TRY(cudaEventElapsedTime(&ms, se.a, se.b));
+      e->stage_ms[se.stage] += ms;
+      e->stage_launches[se.stage] += 1;
+      cudaEventDestroy(se.a);
+      cudaEventDestroy(se.b);
+    }
+    e->stage_evs.clear();
+    for (int s = 0; s <= LGAR_NSTAGE; s++) {
+      ms7[s] = e->stage_ms[s];
+      launches7[s] = e->stage_launches[s];
+    }
   });
 }
 int lgarb_set_path_counters(lgarb_engine* e, int on) {

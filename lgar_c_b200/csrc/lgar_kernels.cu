@@ -289,7 +289,9 @@ constexpr int wave_min_blocks(int stage) {
   return stage == LG_ST_FETCH ? LGAR_MB_FETCH : stage == LG_ST_HEAD ? LGAR_MB_HEAD : stage == LG_ST_FRONT ? LGAR_MB_FRONT
        : stage == LG_ST_SEARCH ? LGAR_MB_SEARCH : stage == LG_ST_TAIL ? LGAR_MB_TAIL : LGAR_MB_CORR;
 }
-template <int STAGE>
+// FF: the SEARCH / CORR stages take the fast path of lgar_search.cuh (few slots in flight: a latency tool).  A template parameter,
+// not an argument: the plain instantiation must not carry the fast path's registers (occupancy of the bulk rounds).
+template <int STAGE, bool FF = false>
 __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int consume,
                                                         unsigned append_mask, int quantum) {
   const int n = wv.qcount[STAGE * 2 + consume];
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         LgLane& G = slots[slot].L;
         LgSearch q = G.q;
         const LgarColumnClass* cls = G.cls;
-        lg_search_some(q, *cls, quantum, w.use_ff != 0);
+        lg_search_some(q, *cls, quantum, FF);
         G.q = q;
         if (q.done) G.resume = true;
         next = q.done ? LG_ST_FRONT : LG_ST_SEARCH;
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
 #pragma unroll
         for (int a = 0; a < 3; a++) ctx_load_n(l + kPitch * a, g + kPitch * a, cf);
         const LgarColumnClass* cls = G.cls;
-        lg_corr_some(k, fb.f, *cls, quantum, w.use_ff != 0);
+        lg_corr_some(k, fb.f, *cls, quantum, FF);
         G.k = k;
 #pragma unroll
         for (int a = 1; a < 3; a++) ctx_store_n(g + kPitch * a, l + kPitch * a, cf);
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
           G.c.cfg = &cfg;
           G.c.cls = G.cls;
           G.c.f = &G.f;
-          G.c.ff = lg_ff_ones;
+          G.c.ff = G.ffv;
           G.c.paths = w.paths;
           G.c.use_ff = w.use_ff != 0;
           if (STAGE == LG_ST_FRONT)
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         L.c.cfg = &cfg;
         L.c.cls = L.cls;
         L.c.f = &L.f;
-        L.c.ff = lg_ff_ones;
+        L.c.ff = L.ffv;
         L.c.paths = w.paths;
         L.c.use_ff = w.use_ff != 0;
         if (STAGE == LG_ST_FRONT)
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
     L.c.cfg = &cfg;
     L.c.cls = L.cls;
     L.c.f = &L.f;
-    L.c.ff = lg_ff_ones;
+    L.c.ff = L.ffv;
     L.c.paths = w.paths;
     L.c.use_ff = true;  // latency regime: see lg_search_some
     while (L.stage != LG_ST_DONE) {
@@ -633,24 +635,7 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
                                    unsigned append_mask, int quantum, int max_items, int sm_count, cudaStream_t stream) {
   // grid-stride over the queue; max_items (slots in flight at the start of the round) bounds every queue
   const int blocks = std::max(1, std::min((std::min(wv.nslots, max_items) + 127) / 128, sm_count * 16));
-  // Unused dynamic shared memory caps the resident blocks per SM of a stage (experiments on how much thread-private
-  // context the L2 can hold: LGARB_WAVE_SMEM_<stage index>=bytes).
-  static int smem[LGAR_NSTAGE] = {-1, -1, -1, -1, -1, -1};
-  if (smem[0] < 0) {
-    for (int s = 0; s < LGAR_NSTAGE; s++) {
-      char name[32];
-      snprintf(name, sizeof(name), "LGARB_WAVE_SMEM_%d", s);
-      const char* v = getenv(name);
-      smem[s] = v ? atoi(v) : 0;
-    }
-    cudaFuncSetAttribute(lgar_wave_kernel<LG_ST_FETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(lgar_wave_kernel<LG_ST_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(lgar_wave_kernel<LG_ST_FRONT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(lgar_wave_kernel<LG_ST_SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(lgar_wave_kernel<LG_ST_CORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(lgar_wave_kernel<LG_ST_TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  }
-  const size_t sm = (size_t)smem[stage];
+  const size_t sm = 0;
   static const int fetch_refill = getenv("LGARB_FETCH_REFILL") ? atoi(getenv("LGARB_FETCH_REFILL")) : 8;  // 0: one queue entry per thread; n: refill kernel, n resident blocks per SM
   const bool refill = stage == LG_ST_FETCH && fetch_refill && w.slot_is_column;
   switch (stage) {
@@ -662,8 +647,14 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
       break;
     case LG_ST_HEAD: lgar_wave_kernel<LG_ST_HEAD><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
     case LG_ST_FRONT: lgar_wave_kernel<LG_ST_FRONT><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
-    case LG_ST_SEARCH: lgar_wave_kernel<LG_ST_SEARCH><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
-    case LG_ST_CORR: lgar_wave_kernel<LG_ST_CORR><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
+    case LG_ST_SEARCH:
+      if (w.use_ff) lgar_wave_kernel<LG_ST_SEARCH, true><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum);
+      else lgar_wave_kernel<LG_ST_SEARCH><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum);
+      break;
+    case LG_ST_CORR:
+      if (w.use_ff) lgar_wave_kernel<LG_ST_CORR, true><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum);
+      else lgar_wave_kernel<LG_ST_CORR><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum);
+      break;
     default: lgar_wave_kernel<LG_ST_TAIL><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
   }
   lgar_wave_reset_kernel<<<1, 1, 0, stream>>>(wv.qcount + stage * 2 + consume, refill ? wv.cursor : nullptr);

@@ -39,6 +39,7 @@ struct LgLane {
   int nf_stored, nold_stored;  // front counts the record was last stored with: only that prefix of the arrays is moved
   LgCtx c;
   alignas(16) LgScalars s;
+  double ffv[LGAR_MAXL + 2];  // frozen_factor per layer (1-based) of this column for the window: all 1.0 unless the run is SFT-coupled
   LgEpi ep;
   alignas(32) LgFronts f;
   // ---- step context (locals of lg_step_active) ----
@@ -70,6 +71,9 @@ LG_FN_NOINLINE void lg_lane_import(const LgarConfig& cfg, const LgarDeviceState&
   lg_epi_load(cfg, d, col, L.ep);
   L.nf_stored = L.f.n;
   L.nold_stored = 0;
+  // SFT coupling: the column's frozen factors stay what they are for the whole window (lgarb_set_value("soil_temperature_profile")
+  // between two calls changes them for the next one)
+  for (int k = 0; k < LGAR_MAXL + 2; k++) L.ffv[k] = (d.ff && k >= 1 && k <= LGAR_MAXL) ? d.ff[(int64_t)k * d.stride + col] : 1.0;
 }
 LG_FN_NOINLINE void lg_lane_export(const LgarConfig& cfg, const LgarDeviceState& d, int64_t col, const LgLane& L) {
   store_scalars(d, col, L.s, true);
@@ -624,7 +628,7 @@ LG_FN_NOINLINE void lg_cycle_begin(const LgarConfig& cfg, LgLane& L) {
   L.volon_ts = L.volon_ts > LG_SMALL_EPS ? L.volon_ts : 0.0;
   const double theta_e_top = cls.lay[f.layer[0]].theta_e;
   const bool top_saturated = (f.theta[0] + LG_SMALL_EPS) >= theta_e_top;
-  cy.top_near_sat = f.theta[0] > theta_e_top * cfg.spf_factor;
+  cy.top_near_sat = f.theta[0] > theta_e_top * cls.par.spf_factor;
   bool create = (precip_prev_sub == 0.0 && cy.precip_sub > 0.0 && L.volon_ts == 0) ||
                 ((cy.precip_sub > 0.0 || L.volon_ts > 0) && (f.n == cls.num_layers));
   if (top_saturated || L.volon_ts > 0.0) create = false;
@@ -643,14 +647,14 @@ LG_FN_NOINLINE void lg_cycle_begin(const LgarConfig& cfg, LgLane& L) {
       L.volon_sub = L.ponded;
       if (L.runoff < 0) c.status |= LGAR_FAIL_NEG_RUNOFF;
     } else {  // :619-632
-      if (L.ponded < cfg.ponded_depth_max_cm) {
+      if (L.ponded < cls.par.ponded_depth_max_cm) {
         L.volon_sub = L.ponded;
         L.ponded = 0.0;
         L.runoff = 0.0;
       } else {
-        L.runoff = (L.ponded - cfg.ponded_depth_max_cm);
-        L.volon_sub = cfg.ponded_depth_max_cm;
-        L.ponded = cfg.ponded_depth_max_cm;
+        L.runoff = (L.ponded - cls.par.ponded_depth_max_cm);
+        L.volon_sub = cls.par.ponded_depth_max_cm;
+        L.ponded = cls.par.ponded_depth_max_cm;
       }
     }
     if (!(c.status & LGAR_FAIL_MASK))
@@ -680,14 +684,14 @@ LG_FN_NOINLINE int lg_cycle_end(const LgarConfig& cfg, LgLane& L) {
   if (L.create) {  // :565-576, then the bookkeeping branch :619-632
     double dry_depth = lg_calc_dry_depth(c, dt);
     lg_create_surficial_front(c, &L.ponded, &L.volin, dry_depth, f.theta[0]);
-    if (L.ponded < cfg.ponded_depth_max_cm) {
+    if (L.ponded < cls.par.ponded_depth_max_cm) {
       L.volon_sub = L.ponded;
       L.ponded = 0.0;
       L.runoff = 0.0;
     } else {
-      L.runoff = (L.ponded - cfg.ponded_depth_max_cm);
-      L.volon_sub = cfg.ponded_depth_max_cm;
-      L.ponded = cfg.ponded_depth_max_cm;
+      L.runoff = (L.ponded - cls.par.ponded_depth_max_cm);
+      L.volon_sub = cls.par.ponded_depth_max_cm;
+      L.ponded = cls.par.ponded_depth_max_cm;
     }
   }
   if (!(c.status & LGAR_FAIL_MASK)) {
@@ -765,7 +769,7 @@ LG_FN_NOINLINE void lg_stage_head(const LgarConfig& cfg, const LgarDeviceState& 
   L.c.cfg = &cfg;
   L.c.cls = L.cls;
   L.c.f = &L.f;
-  L.c.ff = lg_ff_ones;  // the window schedulers run uncoupled columns only (the engine steps SFT-coupled runs hour by hour)
+  L.c.ff = L.ffv;
   L.c.paths = w.paths;
   L.c.use_ff = w.use_ff != 0;
   L.c.status = 0;

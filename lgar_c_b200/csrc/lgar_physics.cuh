@@ -78,6 +78,7 @@ struct LgScalars {
   double timestep_h, storage, fd_dzdt;
   int cache_fluxes, cache_count, runoff_prev;
   int status;
+  const LgarColumnParams* rp;  // the column's reservoir / preferential-flow / ponding parameters (class row), set by load_scalars
 };
 
 struct LgCtx {
@@ -92,6 +93,15 @@ struct LgCtx {
   unsigned long long* paths;  // null, or [LGAR_NPATH] counters of the rare paths taken (lgarb_set_path_counters)
   bool use_ff;                // psi searches take the fast path of lgar_search.cuh (a latency tool, see there)
 };
+// The searches that run INSIDE a step function (hour-by-hour kernels; the rare correction search of a layer crossing at the domain
+// bottom inside TAIL) walk the plain way on the device: the fast path's registers would be charged to every kernel that can reach
+// it (SEARCH 115 -> 168, CORR 62 -> 146 registers when it was reachable from them unconditionally).  The host build of the kernel
+// text honours the flag, so the CPU suite exercises both.
+#ifdef LGAR_HOSTSIM
+#define LG_STRAIGHT_FF(ctx) ((ctx).use_ff)
+#else
+#define LG_STRAIGHT_FF(ctx) false
+#endif
 #ifdef LGAR_HOSTSIM
 #define LG_PATH(ctx, id) do { if ((ctx).paths) (ctx).paths[id]++; } while (0)
 #else
@@ -375,7 +385,7 @@ LG_FN_NOINLINE double lg_theta_mass_balance(LgCtx& c, int layer_num, double psi_
     q.dz[k] = dz[k];
   }
   if (q.delta_mass <= LG_MBAL_TOL) return lg_theta_from_h(psi_cm, sp);
-  lg_search_run(q, cls, c.use_ff);
+  lg_search_run(q, cls, LG_STRAIGHT_FF(c));
   lg_path_search_exit(c, q);
   if ((q.delta_mass > LG_MBAL_TOL) && (!q.wanted_to_saturate)) *AET_demand_cm = *AET_demand_cm - fabs(q.delta_mass - LG_MBAL_TOL);
   if ((q.theta >= sp.theta_e) && (q.psi_loc != 0.0)) *AET_demand_cm = 0.0;
@@ -422,7 +432,7 @@ LG_FN_NOINLINE void lg_theta_mass_balance_correction(LgCtx& c, int front_num, do
   k.done = !(k.delta_mass > LG_MBAL_TOL);
   if (!k.done) {
     LG_PATH(c, LGAR_PATH_CORR_SEARCH);
-    lg_corr_run(k, f, cls, c.use_ff);
+    lg_corr_run(k, f, cls, LG_STRAIGHT_FF(c));
   }
 }
 
@@ -916,14 +926,15 @@ LG_FN_NOINLINE double lg_insert_water(LgCtx& c, double timestep_h, double AET_de
   if (f_p > cap) f_p = cap;
   double ponded_temp = fmax(*ponded_depth_cm - f_p * timestep_h - 0.0, 0.0);
   double fp_cm = f_p * timestep_h + 0.0 / timestep_h;
-  if (cfg.ponded_depth_max_cm > 0.0) {
-    if (ponded_temp < cfg.ponded_depth_max_cm) {
+  const double ponded_depth_max_cm = cls.par.ponded_depth_max_cm;
+  if (ponded_depth_max_cm > 0.0) {
+    if (ponded_temp < ponded_depth_max_cm) {
       *volin = fmin(*ponded_depth_cm, fp_cm);
       *ponded_depth_cm = *ponded_depth_cm - *volin;
       return 0.0;
-    } else if (ponded_temp > cfg.ponded_depth_max_cm) {
-      runoff = ponded_temp - cfg.ponded_depth_max_cm;
-      *ponded_depth_cm = cfg.ponded_depth_max_cm;
+    } else if (ponded_temp > ponded_depth_max_cm) {
+      runoff = ponded_temp - ponded_depth_max_cm;
+      *ponded_depth_cm = ponded_depth_max_cm;
       *volin = fp_cm;
       return runoff;
     }
@@ -1072,7 +1083,7 @@ LG_FN double lg_calc_aet(const LgCtx& c, double PET_cm_per_h, double dt_h) {
 }
 
 // calc_CR_Q, src/conceptual_reservoir.cxx:7-45
-LG_FN double lg_calc_CR_Q_inl(const LgarConfig& cfg, double dt, double in_cm_per_h, double* fast, double* slow) {
+LG_FN double lg_calc_CR_Q_inl(const LgarColumnParams& cfg, double dt, double in_cm_per_h, double* fast, double* slow) {
   double input_slow = in_cm_per_h * cfg.frac_slow;
   double input_fast = in_cm_per_h - input_slow;
   double Q_fast = 0.0;
@@ -1095,7 +1106,7 @@ LG_FN double lg_calc_CR_Q_inl(const LgarConfig& cfg, double dt, double in_cm_per
   }
   return Q_fast + Q_slow;
 }
-LG_FN_NOINLINE double lg_calc_CR_Q(const LgarConfig& cfg, double dt, double in_cm_per_h, double* fast, double* slow) { return lg_calc_CR_Q_inl(cfg, dt, in_cm_per_h, fast, slow); }
+LG_FN_NOINLINE double lg_calc_CR_Q(const LgarColumnParams& cfg, double dt, double in_cm_per_h, double* fast, double* slow) { return lg_calc_CR_Q_inl(cfg, dt, in_cm_per_h, fast, slow); }
 
 // ------------------------------------------------------------------------------------------------
 // L3: BmiLGAR::Update(), reference src/bmi_lgar.cxx:133-895
@@ -1162,7 +1173,7 @@ struct LgCycle {
 LG_FN double lg_cycle_tail_inl(const LgarConfig& cfg, LgScalars& s, LgCycle& cy, double dt, double volend, LgStepVols& v) {
   s.precip_prev = cy.precip_sub;
   double volCRstart = s.cr_fast + s.cr_slow;
-  double volQ_CR = lg_calc_CR_Q_inl(cfg, dt, cy.precip_for_CR + cy.ponded_flux_for_CR + cy.fd_for_CR / dt, &s.cr_fast, &s.cr_slow);
+  double volQ_CR = lg_calc_CR_Q_inl(*s.rp, dt, cy.precip_for_CR + cy.ponded_flux_for_CR + cy.fd_for_CR / dt, &s.cr_fast, &s.cr_slow);
   v.volQ_CR += volQ_CR;
   double volCRend = s.cr_fast + s.cr_slow;
   v.volCRend = volCRend;
@@ -1188,10 +1199,11 @@ LG_FN void lg_cycle_head(const LgarConfig& cfg, const LgScalars& s, LgCycle& cy,
   cy.precip_rate = precip_mm_h * 0.1;
   if (s.runoff_prev) {
     double total = cy.precip_rate;
-    cy.precip_for_CR = cfg.frac_to_CR * total;
-    cy.precip_rate = (1.0 - cfg.frac_to_CR) * total;
-    cy.ponded_flux_for_CR = volon_ts / dt * cfg.frac_to_CR;
-    volon_ts = volon_ts * (1 - cfg.frac_to_CR);
+    const double frac_to_CR = s.rp->frac_to_CR;
+    cy.precip_for_CR = frac_to_CR * total;
+    cy.precip_rate = (1.0 - frac_to_CR) * total;
+    cy.ponded_flux_for_CR = volon_ts / dt * frac_to_CR;
+    volon_ts = volon_ts * (1 - frac_to_CR);
   }
   cy.AET = 0.0;
   cy.volin = 0.0;
@@ -1322,7 +1334,7 @@ LG_FN_NOINLINE void lg_step_active(const LgarConfig& cfg, const LgarColumnClass&
     // create a surficial front? :522-535 (quirk Q8)
     const double theta_e_top = cls.lay[f.layer[0]].theta_e;
     const bool top_saturated = (f.theta[0] + LG_SMALL_EPS) >= theta_e_top;
-    cy.top_near_sat = f.theta[0] > theta_e_top * cfg.spf_factor;
+    cy.top_near_sat = f.theta[0] > theta_e_top * cls.par.spf_factor;
     bool create = (precip_prev_sub == 0.0 && cy.precip_sub > 0.0 && volon_ts == 0) ||
                   ((cy.precip_sub > 0.0 || volon_ts > 0) && (f.n == num_layers));
     if (top_saturated || volon_ts > 0.0) create = false;
@@ -1339,14 +1351,14 @@ LG_FN_NOINLINE void lg_step_active(const LgarConfig& cfg, const LgarColumnClass&
       volon_sub = ponded;
       if (runoff < 0) c.status |= LGAR_FAIL_NEG_RUNOFF;
     } else {  // :619-632
-      if (ponded < cfg.ponded_depth_max_cm) {
+      if (ponded < cls.par.ponded_depth_max_cm) {
         volon_sub = ponded;
         ponded = 0.0;
         runoff = 0.0;
       } else {
-        runoff = (ponded - cfg.ponded_depth_max_cm);
-        volon_sub = cfg.ponded_depth_max_cm;
-        ponded = cfg.ponded_depth_max_cm;
+        runoff = (ponded - cls.par.ponded_depth_max_cm);
+        volon_sub = cls.par.ponded_depth_max_cm;
+        ponded = cls.par.ponded_depth_max_cm;
       }
     }
     if (!create && !(c.status & LGAR_FAIL_MASK)) {  // :638-652

@@ -172,7 +172,7 @@ LG_FN bool lg_ff_apart(double x, double y, double a, double b, double g, double 
 // -- go through ONE call site at the top of one loop; between two evaluations each lane runs its own cheap bookkeeping (the
 // recurrences of the skipped trips) and comes back to the call site.  Written the straightforward way (evaluate where the need
 // arises) the lanes of a warp reach their handful of exact trips at different points of the walk and the warp pays for the union:
-// measured on the B200, the six stage kernels fell from 4.3e8 to 1.8e8 column-timesteps/s (profiles/r2_call1_summary.md).
+// measured on the B200, the six stage kernels fell from 4.3e8 to 1.8e8 column-timesteps/s (profiles/r2_call1_call2_summary.md).
 template <class Q, class Ev>
 LG_FN bool lg_digit_ff(Q& q, Ev& ev, const bool gate) {
   const Q q0 = q;
@@ -183,7 +183,7 @@ LG_FN bool lg_digit_ff(Q& q, Ev& ev, const bool gate) {
   if (!ev.monotone() || !(x0 > 0.0) || !(x0 < 1e300)) return false;
   const int nt = ev.terms();
   double sl[Ev::kMaxTerms], slz[Ev::kMaxTerms];
-  enum { S_NEWTON, S_BR_A, S_BR_B, S_ZONE_LO, S_ZONE_HI, S_TRIP };
+  enum { S_NEWTON, S_BR_A, S_BR_B, S_ZONE_LO, S_ZONE_HI, S_TRIP, S_TRIP_AGAIN };
   enum { W_BEGIN, W_AFTER_EVAL, W_BOOK, W_RECHECK };
   enum { R_RUNNING, R_DONE, R_DECLINED, R_FALLBACK };
   int st = S_NEWTON, wphase = W_BEGIN, result = R_RUNNING;
@@ -384,6 +384,15 @@ LG_FN bool lg_digit_ff(Q& q, Ev& ev, const bool gate) {
       zlo = nlo;
       zhi = nhi;
       zones++;
+      if (!skip && Ev::kEvalHasSideEffects) {
+        // the model's evaluation writes into the live state (the correction search sets theta and psi of its chain of fronts): the
+        // zone ends have just overwritten what the exactly evaluated trip left there -- evaluate the trip once more
+        st = S_TRIP_AGAIN;
+        xr = psi;
+      } else {
+        more = advance();
+      }
+    } else if (st == S_TRIP_AGAIN) {
       more = advance();
     } else {  // S_TRIP: the evaluation of the trip at q.psi_loc
       q.theta_store(th);
@@ -454,6 +463,7 @@ LG_FN void lg_search_iter(LgSearch& q, const LgarColumnClass& cls) {
 #if !defined(LGAR_FAST_POW)
 struct LgSearchModel {
   static constexpr int kMaxTerms = LGAR_MAXL + 1;
+  static constexpr bool kEvalHasSideEffects = false;
   const LgSearch* q;
   const LgarColumnClass* cls;
   LG_MFN bool monotone() const {
@@ -489,7 +499,7 @@ struct LgSearchModel {
 // A search in flight: through the fast path if `use_ff` (from whatever trip the walk has reached), then at most `quantum` plain
 // trips of whatever is left.  Where the fast path pays: it does ~10 evaluations where the plain walk does ~70, but the lanes of a
 // warp walking plainly are CONVERGED and compacted (the SEARCH stage kernel runs at ~65 % of the FP64 peak), while the fast
-// path's bookkeeping diverges -- measured on the B200, bulk rounds are 2.1 x SLOWER with it (profiles/r2_call2_summary.md).
+// path's bookkeeping diverges -- measured on the B200, bulk rounds are 2.1 x SLOWER with it (profiles/r2_call1_call2_summary.md).
 // It is a latency tool: the engine turns it on when few slots are in flight (drop-out rounds, finishing kernel), where a round
 // lasts as long as its longest search and a 10^4-trip monster is 10^4 cheap recurrences instead of 10^4 evaluations.
 LG_FN void lg_search_some(LgSearch& q, const LgarColumnClass& cls, int quantum, bool use_ff) {
@@ -574,6 +584,7 @@ LG_FN void lg_corr_iter(LgCorr& k, LgFronts& f, const LgarColumnClass& cls) {
 // one is in the same layer.  Terms are grouped by soil layer (one unimodal |d theta / d psi| per layer).
 struct LgCorrModel {
   static constexpr int kMaxTerms = LGAR_MAXL + 1;
+  static constexpr bool kEvalHasSideEffects = true;   // eval() writes theta and psi of the chain into the front list
   LgCorr* k;
   LgFronts* f;
   const LgarColumnClass* cls;

@@ -35,6 +35,7 @@ LG_FN_NOINLINE void load_scalars(const LgarDeviceState& d, int64_t col, LgScalar
   s.runoff_prev = (b >> 1) & 1;
   s.cache_count = (b >> 8) & 0xFF;
   s.status = d.status[col];
+  s.rp = &d.classes[d.class_id[col]].par;
 }
 
 LG_FN_NOINLINE void store_scalars(const LgarDeviceState& d, int64_t col, const LgScalars& s, bool active) {

@@ -104,6 +104,13 @@ struct LgarLayer {
   double slope_max;  // max over h of |d theta / d h| (at (alpha h)^n = m); bounds mass changes in the fast path of the psi searches, never a result
 };
 
+// Parameters that the reference keeps per model object and lets a calibrator set through SetValue (src/bmi_lgar.cxx:1032-1049,
+// 1403-1420): nonlinear reservoir, preferential-flow split and ponding.  Part of the class row, so every column can carry its own
+// set (a calibration run = one column per parameter set).
+struct LgarColumnParams {
+  double a, b, frac_to_CR, a_slow, b_slow, frac_slow, spf_factor, ponded_depth_max_cm;
+};
+
 struct LgarColumnClass {
   int32_t num_layers;
   int32_t invalid_soil_type;         // Q = precip shortcut (bmi_lgar.cxx:145-179)
@@ -115,6 +122,7 @@ struct LgarColumnClass {
   double psi_50_cm[LGAR_MAXL + 1];   // calc_aet's psi_wp_cm for a head front in layer k (aet.cxx:47-57)
   double initial_theta[LGAR_MAXL + 1];
   double initial_K[LGAR_MAXL + 1];
+  LgarColumnParams par;
 };
 
 // engine-wide configuration (uniform per engine instance = per "bin")
@@ -122,8 +130,6 @@ struct LgarConfig {
   int32_t use_closed_form_G, adaptive_timestep, allow_flux_caching;
   int32_t free_drainage_enabled, free_drainage_to_CR, PET_affects_precip;
   int32_t nint, num_giuh;
-  double ponded_depth_max_cm;
-  double a, b, frac_to_CR, a_slow, b_slow, frac_slow, spf_factor;
   double mbal_tol;
   double timestep_h;            // config "timestep" (= minimum_timestep_h)
   double forcing_resolution_h;

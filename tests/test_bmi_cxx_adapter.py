@@ -1,13 +1,15 @@
-"""The header-only C++ BMI adapter (include/bmi_lgarb200.hxx) compiles against the CSDMS bmi.hxx the
-reference ships, links with liblgarb.so and answers the metadata questions of the reference's unit test
-(tests/main_unit_test_bmi.cxx:46-379) without a device; with a device it repeats the known-answer step."""
+"""The header-only C++ BMI adapter (include/bmi_lgarb200.hxx) compiles against the CSDMS bmi.hxx (the reference's copy where
+/root/reference exists, else tests/bmi_min/bmi.hxx, the same interface written from the BMI 2.0 specification), links with
+liblgarb.so and answers the metadata questions of the reference's unit test (tests/main_unit_test_bmi.cxx:46-379) without a
+device; on the GPU box (-m gpu) it runs Initialize / SetValue / Update / GetValue / Finalize and repeats the reference's
+known-answer step (tests/main_unit_test_bmi.cxx:424-568), for one column and for a batch of columns."""
 import subprocess
 from pathlib import Path
 
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
-BMI_DIRS = [Path("/root/reference/bmi")]
+BMI_DIRS = [Path("/root/reference/bmi"), ROOT / "tests" / "bmi_min"]
 
 SRC = r'''
 #include <cstdio>
@@ -46,6 +48,23 @@ int main(int argc, char** argv) {
     m->Finalize();
   }
   bmi_model_destroy(m);
+  if (argc > 2) {  // a batch of columns behind the same class: scalar variables are [n_columns], per-front arrays padded to 32
+    const int nc = 5;
+    BmiLGARB200 mb(nc, 0);
+    mb.Initialize(argv[1]);
+    double p[nc], pet[nc], inf[nc];
+    for (int c = 0; c < nc; c++) { p[c] = 1.896 * (c + 1) / nc; pet[c] = 0.104; }
+    mb.SetValue("precipitation_rate", p);
+    mb.SetValue("potential_evapotranspiration_rate", pet);
+    mb.Update();
+    expect(mb.GetVarNbytes("infiltration") == 8 * nc && mb.GetGridSize(1) == nc, "batch sizes");
+    mb.GetValue("infiltration", inf);
+    expect(std::fabs(inf[nc - 1] * 1000 - 1.896) < 1e-5 && inf[0] < inf[nc - 1] && inf[0] > 0, "batch infiltration");
+    int shape[2] = {-1, -1};
+    mb.GetGridShape(3, shape);   // must not overflow a stack int with n_columns values (round 1 advisory)
+    expect(shape[1] == 4, "grid shape of column 0");
+    mb.Finalize();
+  }
   printf(fails ? "FAILED\n" : "OK\n");
   return fails;
 }
@@ -69,4 +88,13 @@ def _build(tmp_path):
 def test_adapter_compiles_and_answers_metadata(tmp_path):
     exe = _build(tmp_path)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_adapter_runs_the_reference_known_answer_step_on_the_device(cuda_device, tmp_path):
+    from helpers import config_for
+    exe = _build(tmp_path)
+    cfg = config_for("unittest", tmp_path)
+    out = subprocess.run([str(exe), str(cfg), "batch"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr

@@ -1,5 +1,6 @@
 """Calibratable parameters through SetValue (reference src/bmi_lgar.cxx:916-1078,1372-1421):
-per-column soil parameter sets and batch-wide reservoir / ponding / field-capacity parameters, applied at the first
+per-column soil parameter sets AND per-column reservoir / preferential-flow / ponding / field-capacity parameters (a, b,
+frac_to_CR, spf_factor, ponded_depth_max, field_capacity; reference src/bmi_lgar.cxx:1032-1049,1403-1420), applied at the first
 Update of a run configured with calib_params=true.  Checked against the UNMODIFIED reference (oracle/_ref, one
 BmiLGAR object per parameter set) step by step: the 12 BMI scalars, the front counts, the final fronts and
 volchange_calib of the global mass balance."""
@@ -20,9 +21,18 @@ SOIL_SETS = [   # name -> value, per parameter set; anything not listed keeps th
     {"smcmax_1": 0.40, "smcmin_1": 0.08, "van_genuchten_alpha_2": 0.006, "hydraulic_conductivity_1": 0.3, "smcmax_3": 0.5},
 ]
 GLOBALS = {"a": 0.002, "b": 2.2, "frac_to_CR": 0.15, "spf_factor": 0.8, "field_capacity": 300.0, "ponded_depth_max": 0.4}
+# the same parameters, a different set for every parameter set of a batch (a calibration run: one column per candidate)
+GLOBAL_SETS = [
+    {},
+    {"a": 0.002, "b": 2.2, "frac_to_CR": 0.15, "spf_factor": 0.8, "field_capacity": 300.0, "ponded_depth_max": 0.4},
+    {"a": 0.0005, "b": 3.0, "frac_to_CR": 0.35},
+    {"spf_factor": 0.95, "ponded_depth_max": 1.5, "field_capacity": 250.0},
+    {"a": 0.004, "b": 1.8, "frac_to_CR": 0.05, "spf_factor": 0.7, "ponded_depth_max": 0.05},
+    {"b": 2.8, "field_capacity": 400.0},
+]
 
 
-def run_case(ref, tmp_path, cfg_keys, soil_sets, glob, T=500, reps=3):
+def run_case(ref, tmp_path, cfg_keys, soil_sets, glob, T=500, reps=3, glob_sets=None):
     import torch
     import lgar_c_b200
     g = load_golden("Phillipsburg_with_reservoir")
@@ -49,8 +59,16 @@ def run_case(ref, tmp_path, cfg_keys, soil_sets, glob, T=500, reps=3):
     for n, x in glob.items():
         b.set_value(n, np.full(ncol, x))
         assert np.all(b.get_value(n) == x)
-    with pytest.raises(lgar_c_b200.LgarbError):           # the reservoir parameters are constants of the batch
-        b.set_value("b", np.linspace(2.0, 3.0, ncol))
+    if glob_sets is not None:                              # a different reservoir / ponding set per column
+        gnames = sorted({n for s in glob_sets for n in s})
+        ginitial = {n: b.get_value(n) for n in gnames}
+        for n in gnames:
+            v = ginitial[n].copy()
+            for c in range(ncol):
+                if n in glob_sets[c % nset]:
+                    v[c] = glob_sets[c % nset][n]
+            b.set_value(n, v)
+            assert np.array_equal(b.get_value(n), v)
     dP, dE = torch.from_numpy(Pm).cuda(), torch.from_numpy(Em).cuda()
     sinks = torch.zeros((12, T, ncol), dtype=torch.float64, device="cuda")
     nfs = torch.zeros((T, ncol), dtype=torch.int32, device="cuda")
@@ -70,6 +88,9 @@ def run_case(ref, tmp_path, cfg_keys, soil_sets, glob, T=500, reps=3):
             ref.set_scalar(h, n, x)
         for n, x in glob.items():
             ref.set_scalar(h, n, x)
+        if glob_sets is not None:
+            for n, x in glob_sets[c % nset].items():
+                ref.set_scalar(h, n, x)
         r = ref.run_series(h, Pm[:, c], Em[:, c], cap=16)
         assert r["done"] == T, f"reference stopped at step {r['done']} for parameter set {c % nset}"
         assert np.array_equal(nf[:, c], r["nfronts"]), f"column {c}: front counts differ"
@@ -87,6 +108,12 @@ def run_case(ref, tmp_path, cfg_keys, soil_sets, glob, T=500, reps=3):
 def test_per_column_soil_parameter_sets(cuda_device, ref, tmp_path):
     gm = run_case(ref, tmp_path, {}, SOIL_SETS, GLOBALS)
     assert np.count_nonzero(gm[:, 13]) >= 12             # the parameter update did change the stored water
+
+
+def test_per_column_reservoir_and_ponding_parameter_sets(cuda_device, ref, tmp_path):
+    """Every column its own (a, b, frac_to_CR, spf_factor, ponded_depth_max, field_capacity) on top of its own soil parameters:
+    each against one unmodified BmiLGAR object that was given the same values through SetValue."""
+    run_case(ref, tmp_path, {}, SOIL_SETS, {}, glob_sets=GLOBAL_SETS)
 
 
 def test_layers_sharing_a_soil_type(cuda_device, ref, tmp_path):

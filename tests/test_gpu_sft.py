@@ -77,3 +77,56 @@ def test_sft_coupled_columns_against_reference(cuda_device, ref, tmp_path, close
     b0.initialize(absolutize_config(base0, out_dir=tmp_path), ncol)
     out0 = b0.update_steps_host(np.ascontiguousarray(Pm), np.ascontiguousarray(Em), ["soil_storage"])
     assert np.max(np.abs(out0["soil_storage"] - got[:, 5, :])) > 1e-4
+
+
+def test_sft_coupled_columns_in_the_window_path(cuda_device, ref, tmp_path):
+    """SFT-coupled columns through the MULTI-STEP verbs (the stage kernels; round 1 stepped coupled runs hour by hour only): the
+    temperature profile is set once per window of 24 forcing hours -- a temperature series per window -- and the window runs with
+    each column's frozen factors carried in its lane record.  Against the unmodified reference fed the same profiles at the same
+    hours: per-step scalars, front counts and final fronts bit for bit; and identical to the engine's own hour-by-hour path."""
+    import torch
+    import lgar_c_b200
+    g = load_golden("Phillipsburg_with_reservoir")
+    base = write_config(DATA / "configs" / "config_lasam_Phillipsburg_with_reservoir.txt", tmp_path / "sftw.txt", sft_coupled="true", soil_z=SOIL_Z)
+    cfg = absolutize_config(base, out_dir=tmp_path)
+    ncol, T, ncell, W = 40, 720, 20, 24
+    shifts = np.arange(ncol) * 211 + 40
+    Pm = np.ascontiguousarray(np.stack([np.roll(g["precip"], -int(s))[:T] for s in shifts], axis=1))
+    Em = np.ascontiguousarray(np.stack([np.roll(g["pet"], -int(s))[:T] for s in shifts], axis=1))
+    Tm = temperatures(ncol, T, ncell)
+    res = {}
+    for mode in (3, 0):
+        b = lgar_c_b200.BmiLGARBatch()
+        b.initialize(cfg, ncol)
+        b.set_window_mode(mode)
+        dP, dE = torch.from_numpy(Pm).cuda(), torch.from_numpy(Em).cuda()
+        sinks = torch.zeros((12, T, ncol), dtype=torch.float64, device="cuda")
+        nfs = torch.zeros((T, ncol), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        for t0 in range(0, T, W):
+            if t0 > 0:   # the first window runs on the zero profile the reference starts with
+                b.set_value("soil_temperature_profile", Tm[t0])
+            b.update_steps_device(W, dP[t0].data_ptr(), dE[t0].data_ptr(), ncol,
+                                  {n: sinks[k, t0].data_ptr() for k, n in enumerate(lgar_c_b200.OUTPUT_SCALARS)}, ncol, nfs[t0].data_ptr())
+        b.synchronize()
+        assert (b.get_status() & lgar_c_b200.STATUS_FAIL_MASK == 0).all()
+        res[mode] = (sinks.cpu().numpy().transpose(1, 0, 2), nfs.cpu().numpy(), b.get_fronts())
+    got, nf, fr = res[3]
+    assert np.array_equal(got, res[0][0]) and np.array_equal(nf, res[0][1])
+    for c in range(0, ncol, 3):
+        h = ref.create(cfg)
+        want = np.zeros((T, 12))
+        nfw = np.zeros(T, dtype=np.int32)
+        for t0 in range(0, T, W):
+            if t0 > 0:
+                ref.set_array(h, "soil_temperature_profile", Tm[t0, c])
+            r = ref.run_series(h, Pm[t0:t0 + W, c], Em[t0:t0 + W, c], cap=16)
+            assert r["done"] == W
+            want[t0:t0 + W], nfw[t0:t0 + W] = r["scalars"], r["nfronts"]
+        assert np.array_equal(nf[:, c], nfw), f"column {c}"
+        assert_scalars_close(got[:, :, c], want, f"column {c}")
+        n_end = int(nfw[-1])
+        arr = np.stack([fr[k][c] for k in ("depth", "theta", "psi", "K", "dzdt")], axis=1)
+        flags = (fr["layer"][c] | (fr["to_bottom"][c] << 8)).astype(np.int32)
+        assert_fronts_close(arr, flags, r["fronts"][-1], r["flags"][-1], n_end, f"column {c} final fronts")
+        ref.destroy(h)

@@ -121,12 +121,7 @@ class Config:
                 mult = 0.5 + _u01(_splitmix64_t(ids_t + _i64(2024 * 0x100000001B3)))
                 P = P * mult[None, :]
             return P.contiguous(), E.contiguous()
-        key = (ids_t[None, :] * 1000003 + t[:, None]) * 2 + _i64(777 * 0x100000001B3)
-        u1 = _u01(_splitmix64_t(key))
-        u2 = _u01(_splitmix64_t(key + 1))
-        P = torch.where(u1 < 0.03, torch.clamp(-2.5 * torch.log1p(-u2), max=170.0), torch.zeros_like(u1))
-        pet = torch.from_numpy(bench.pet_series(np.arange(t0, t0 + nt))).to(dev)
-        return P.contiguous(), pet[:, None].expand(nt, ids_t.shape[0]).contiguous()
+        return bench.forcing_torch(ids_t, t0, nt)   # the bench workload's forcing: one definition (bench.py), same doubles on host and device
 
 
 def _i64(x: int) -> int:
