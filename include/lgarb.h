@@ -230,6 +230,13 @@ int lgarb_get_warp_times(lgarb_engine* e, uint32_t* out16384);
 /* number of kernels launched by this engine so far, and columns routed to the active kernel in
  * the last step */
 int64_t lgarb_get_launch_count(const lgarb_engine* e);
+/* Express lane of the window scheduler (lgar_c_b200/csrc/lgar_express.cu): slots whose columns are active in nearly every hour
+ * leave the rounds and are run to the end of the window by a kernel that keeps their records in shared memory.  Scheduling
+ * only: results do not depend on it.  on: 0/1; first_round: first round that admits; factor_x4: a slot at hour t of the window
+ * in round r is admitted if t <= r * factor_x4 / 4; cap_permille: at most this share of the columns per window; negative
+ * arguments leave a value as it is.  lgarb_get_express_count: columns that took the express lane so far. */
+int lgarb_set_express_params(lgarb_engine* e, int on, int first_round, int factor_x4, int cap_permille);
+int64_t lgarb_get_express_count(const lgarb_engine* e);
 int64_t lgarb_get_last_active_count(lgarb_engine* e);
 /* Per-kernel device timing with CUDA events recorded on the engine's own stream (the only place
  * they can see its kernels).  lgarb_set_profiling(e, 1) starts a fresh accumulation;

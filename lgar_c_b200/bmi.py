@@ -131,6 +131,8 @@ def _load():
         "lgarb_get_stage_profile": ([vp, vp], C.c_int),
         "lgarb_get_warp_times": ([vp, vp], C.c_int),
         "lgarb_get_launch_count": ([vp], i64),
+        "lgarb_set_express_params": ([vp, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
+        "lgarb_get_express_count": ([vp], i64),
         "lgarb_get_last_active_count": ([vp], i64),
         "lgarb_get_stream": ([vp], vp),
         "lgarb_measure_fp64_peak": ([vp, C.c_double, dp], C.c_int),
@@ -447,8 +449,8 @@ class BmiLGARBatch:
         self._ck(self._L.lgarb_set_force_all_active(self._h, int(bool(on))))
 
     def set_window_mode(self, mode):
-        """Scheduler of the multi-step verbs: 3 six stage kernels with queues between them (default); 2 lanes kernel; 1 warp-tile
-        window kernel; 0 hour-by-hour kernel pairs.  All bit-identical."""
+        """Scheduler of the multi-step verbs: 3 six stage kernels with queues between them (default); 1 warp-tile window
+        kernel; 0 hour-by-hour kernel pairs.  All bit-identical.  (2, 4, 5 of earlier rounds were measured slower and removed.)"""
         self._ck(self._L.lgarb_set_window_mode(self._h, int(mode)))
 
     def set_wave_params(self, search_quantum=0, front_search_pairs=0, finish_below=-1):
@@ -477,6 +479,13 @@ class BmiLGARBatch:
 
     def get_launch_count(self):
         return self._L.lgarb_get_launch_count(self._h)
+
+    def set_express_params(self, on=-1, first_round=-1, factor_x4=-1, cap_permille=-1):
+        """Express lane of the window scheduler (scheduling only; negative = leave as it is)."""
+        self._ck(self._L.lgarb_set_express_params(self._h, int(on), int(first_round), int(factor_x4), int(cap_permille)))
+
+    def get_express_count(self):
+        return self._L.lgarb_get_express_count(self._h)
 
     def get_last_active_count(self):
         return self._L.lgarb_get_last_active_count(self._h)

@@ -130,129 +130,11 @@ __global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_window_kernel(const 
   }
 }
 
-// ---- lanes kernel -----------------------------------------------------------------------------------
-// K forcing hours per launch; every LANE runs its own stream of columns (atomic counter) and hours and
-// is in one stage of the resumable program of lgar_lanes.cuh.  The warp picks one stage per turn:
-// the psi search whenever at least LGAR_SEARCH_MIN lanes are in it (they iterate converged, up to
-// LGAR_SEARCH_QUANTUM trips or until too few are left), otherwise the most populated of the other
-// stages.  No shared memory, no barrier of any scope.
-#define LGAR_SEARCH_MIN 12
-#define LGAR_SEARCH_QUANTUM 32
-__global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_lanes_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w) {
-  const unsigned FULL = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31;
-  LgLane L;
-  L.stage = LG_ST_FETCH;
-  L.col = -1;
-  L.t = w.K;
-  L.resume = false;
-  L.tr_iters = 0;
-  L.tr_kcyc = 0;
-  unsigned long long front_sum = 0, active_sum = 0;
-  unsigned long long* fsp = w.prof ? &front_sum : nullptr;
-  unsigned long long sp_cyc[5] = {0, 0, 0, 0, 0}, sp_calls[5] = {0, 0, 0, 0, 0}, sp_lanes[5] = {0, 0, 0, 0, 0};
-  unsigned long long gt0 = 0;
-  if (w.work_trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
-  for (;;) {
-    const int st = L.stage;
-    const unsigned m_search = __ballot_sync(FULL, st == LG_ST_SEARCH);
-    const unsigned m_front = __ballot_sync(FULL, st == LG_ST_FRONT);
-    const unsigned m_tail = __ballot_sync(FULL, st == LG_ST_TAIL);
-    const unsigned m_head = __ballot_sync(FULL, st == LG_ST_HEAD);
-    const unsigned m_fetch = __ballot_sync(FULL, st == LG_ST_FETCH);
-    const unsigned m_corr = __ballot_sync(FULL, st == LG_ST_CORR);
-    if (!(m_search | m_front | m_tail | m_head | m_fetch | m_corr)) break;  // every lane is DONE
-    const int n_search = __popc(m_search), n_front = __popc(m_front), n_tail = __popc(m_tail), n_head = __popc(m_head),
-              n_fetch = __popc(m_fetch), n_corr = __popc(m_corr);
-    int chosen;
-    if (n_search >= LGAR_SEARCH_MIN || (m_search && !(m_front | m_tail | m_head | m_fetch | m_corr))) {
-      chosen = LG_ST_SEARCH;
-    } else if (n_corr >= LGAR_SEARCH_MIN || (m_corr && !(m_front | m_tail | m_head | m_fetch))) {
-      chosen = LG_ST_CORR;
-    } else {  // most populated of the other stages; ties go to the stage closest to the search
-      chosen = LG_ST_FRONT;
-      int best = n_front;
-      if (n_tail > best) { best = n_tail; chosen = LG_ST_TAIL; }
-      if (n_head > best) { best = n_head; chosen = LG_ST_HEAD; }
-      if (n_fetch > best) { best = n_fetch; chosen = LG_ST_FETCH; }
-    }
-    const long long sp_t0 = w.work_trace ? clock64() : 0;
-    if (st == chosen) {
-      if (chosen == LG_ST_SEARCH) {
-        const int keep = (n_search >= LGAR_SEARCH_MIN) ? LGAR_SEARCH_MIN : 1;
-        for (int it = 0; it < LGAR_SEARCH_QUANTUM; it++) {
-          if (!L.q.done) {
-            lg_search_iter(L.q, *L.cls);
-            L.tr_iters++;
-          }
-          if (__popc(__ballot_sync(m_search, !L.q.done)) < keep) break;
-        }
-        if (L.q.done) {
-          L.resume = true;
-          L.stage = LG_ST_FRONT;
-        }
-      } else if (chosen == LG_ST_CORR) {
-        const int keep = (n_corr >= LGAR_SEARCH_MIN) ? LGAR_SEARCH_MIN : 1;
-        for (int it = 0; it < LGAR_SEARCH_QUANTUM; it++) {
-          if (!L.k.done) lg_corr_iter(L.k, L.f, *L.cls);
-          if (__popc(__ballot_sync(m_corr, !L.k.done)) < keep) break;
-        }
-        if (L.k.done) L.stage = LG_ST_TAIL;
-      } else {
-        const long long c0 = w.work_trace ? clock64() : 0;
-        if (chosen == LG_ST_FRONT) {
-          lg_stage_front(L);
-        } else if (chosen == LG_ST_TAIL) {
-          lg_stage_tail(cfg, d, w, L, fsp);
-        } else if (chosen == LG_ST_HEAD) {
-          lg_stage_head(cfg, d, w, L, fsp);
-          active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
-        } else {
-          lg_stage_fetch(cfg, d, w, L, fsp);
-        }
-        if (w.work_trace && chosen != LG_ST_FETCH) L.tr_kcyc += (unsigned int)((clock64() - c0) >> 10);
-      }
-    }
-    if (w.work_trace) {
-      __syncwarp();
-      const int np = chosen == LG_ST_SEARCH ? n_search : chosen == LG_ST_FRONT ? n_front : chosen == LG_ST_TAIL ? n_tail : chosen == LG_ST_HEAD ? n_head : chosen == LG_ST_CORR ? n_corr : n_fetch;
-      const int slot_ = chosen == LG_ST_CORR ? LG_ST_TAIL : chosen;  // the profile has five slots: CORR is booked under TAIL
-      sp_cyc[slot_] += (unsigned long long)(clock64() - sp_t0);
-      sp_calls[slot_] += 1;
-      sp_lanes[slot_] += np;
-    }
-  }
-  if (w.work_trace && lane == 0) {
-    unsigned long long gt1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
-    const int gw = (blockIdx.x * LGAR_WINDOW_THREADS + threadIdx.x) >> 5;
-    if (gw < 8192) {
-      w.work_trace[2 * w.trace_stride + 64 + gw] = (unsigned int)((gt1 - gt0) / 1000ull);          // warp lifetime, us
-      w.work_trace[2 * w.trace_stride + 64 + 8192 + gw] = (unsigned int)((gt0 / 1000ull) & 0xFFFFFFFFull);  // start, us (mod 2^32)
-    }
-    unsigned long long* sp = (unsigned long long*)(w.work_trace + 2 * w.trace_stride);
-    for (int k = 0; k < 5; k++) {
-      atomicAdd(sp + k, sp_cyc[k]);
-      atomicAdd(sp + 5 + k, sp_calls[k]);
-      atomicAdd(sp + 10 + k, sp_lanes[k]);
-    }
-  }
-  if (w.prof) {
-    for (int o = 16; o > 0; o >>= 1) {
-      front_sum += __shfl_down_sync(FULL, front_sum, o);
-      active_sum += __shfl_down_sync(FULL, active_sum, o);
-    }
-    if (lane == 0) {
-      atomicAdd(w.prof, front_sum);
-      atomicAdd(w.prof + 1, active_sum);
-    }
-  }
-}
-
 // ---- wavefront kernels (mode 3) -------------------------------------------------------------------------
-// The lanes kernel proved the staged program right but ran at 0.2 instructions/clock/scheduler: its
-// code (206-437 KB of SASS) does not fit the 32 KB L1.5 instruction cache and every warp sits somewhere
-// else in it (ncu: 26 of 34 stall cycles per instruction are instruction fetch).  Here every stage is
+// A single kernel running the staged program of lgar_lanes.cuh per lane (round 1's "lanes kernel", removed in round 2) proved
+// the program right but ran at 0.2 instructions/clock/scheduler: its code (206-437 KB of SASS) does not fit the 32 KB L1.5
+// instruction cache and every warp sits somewhere else in it (ncu: 26 of 34 stall cycles per instruction are instruction
+// fetch).  Here every stage is
 // its own small kernel; the context of an in-flight column-step (LgLane) is parked in HBM between
 // stages and stages hand slots to each other through compacted queues, so every kernel runs full warps
 // over one short piece of code.  The host enqueues rounds of FETCH, HEAD, (FRONT, SEARCH) x n, TAIL
@@ -419,7 +301,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
 // the MEAN walk of what it handles, not the maximum; the forcing of the next hour is requested before the current hour is
 // computed.  The arithmetic per hour is lg_resident_hour(), the body lg_advance_resident() loops over: bit-identical.
 __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w,
-                                                              const __grid_constant__ LgarWave wv, int consume, unsigned append_mask) {
+                                                              const __grid_constant__ LgarWave wv, int consume, unsigned append_mask, const LgarExpressAdmit xa) {
   const unsigned FULL = 0xFFFFFFFFu;
   const int n = wv.qcount[LG_ST_FETCH * 2 + consume];
   const int lane = threadIdx.x & 31;
@@ -484,6 +366,13 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
         if (t < K) {
           G.stage = LG_ST_HEAD;
           next = LG_ST_HEAD;
+          // Express lane (lgar_express.cu): a slot that has advanced few hours for the rounds it has been through sits in a
+          // column that is active in (nearly) every hour; it leaves the rounds here.  The cap is read without a lock: it may be
+          // overshot by the lanes in flight, the queue holds every slot.
+          if (t <= xa.admit_t && K - t >= xa.min_left && *(volatile int32_t*)wv.xcount < xa.cap) {
+            wv.xqueue[atomicAdd(wv.xcount, 1)] = slot;
+            next = -1;
+          }
         } else {  // this column has finished the window (lg_stage_fetch, slot == column)
           lg_lane_export(cfg, d, col, G);
           if (w.done_columns) atomicAdd(w.done_columns, 1);
@@ -512,7 +401,7 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
 #ifndef LGAR_MB_FINISH
 #define LGAR_MB_FINISH 0
 #endif
-__global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int lane_stride) {
+__global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int lane_stride, int use_ff) {
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
   int total = 0;
   for (int q = 0; q < 2 * LGAR_NSTAGE; q++) total += wv.qcount[q];
@@ -545,7 +434,7 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
     L.c.f = &L.f;
     L.c.ff = L.ffv;
     L.c.paths = w.paths;
-    L.c.use_ff = true;  // latency regime: see lg_search_some
+    L.c.use_ff = use_ff != 0;  // latency regime: see lg_search_some
     while (L.stage != LG_ST_DONE) {
       switch (L.stage) {
         case LG_ST_FETCH: lg_stage_fetch(cfg, d, w, L, fsp); break;
@@ -555,13 +444,13 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
           break;
         case LG_ST_FRONT: lg_stage_front(L); break;
         case LG_ST_SEARCH:
-          lg_search_run(L.q, *L.cls, true);
+          lg_search_run(L.q, *L.cls, use_ff != 0);
           L.resume = true;
           L.stage = LG_ST_FRONT;
           break;
         case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, fsp); break;
         case LG_ST_CORR:
-          lg_corr_run(L.k, L.f, *L.cls, true);
+          lg_corr_run(L.k, L.f, *L.cls, use_ff != 0);
           L.stage = LG_ST_TAIL;
           break;
         default: L.stage = LG_ST_DONE; break;
@@ -576,12 +465,13 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
 
 // Queue counts to the host through mapped pinned memory: a cudaMemcpyAsync of these 48 bytes would queue behind whatever
 // bulk device-to-host copy (output series of the previous chunk of a streamed call) occupies the copy engine.
-__global__ void lgar_wave_poll_kernel(const int32_t* qcount, int32_t* host_counts) {
+__global__ void lgar_wave_poll_kernel(const int32_t* qcount, const int32_t* xcount, int32_t* host_counts) {
   if (threadIdx.x < 2 * LGAR_NSTAGE) host_counts[threadIdx.x] = qcount[threadIdx.x];
+  if (threadIdx.x == 2 * LGAR_NSTAGE) host_counts[threadIdx.x] = *xcount;
   __threadfence_system();
 }
 cudaError_t lgar_launch_wave_poll(const LgarWave& wv, int32_t* host_counts, cudaStream_t stream) {
-  lgar_wave_poll_kernel<<<1, 32, 0, stream>>>(wv.qcount, host_counts);
+  lgar_wave_poll_kernel<<<1, 32, 0, stream>>>(wv.qcount, wv.xcount, host_counts);
   return cudaGetLastError();
 }
 
@@ -590,10 +480,10 @@ __global__ void lgar_wave_clear_kernel(LgarWave wv) {
 }
 
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
-                                    int lane_stride, int sm_count, cudaStream_t stream) {
+                                    int lane_stride, int use_ff, int sm_count, cudaStream_t stream) {
   lane_stride = std::max(1, std::min(lane_stride, 32));
   const int blocks = std::max(1, std::min((int)(((int64_t)in_flight * lane_stride + 127) / 128), sm_count * 16));
-  lgar_wave_finish_kernel<<<blocks, 128, 0, stream>>>(cfg, d, w, wv, lane_stride);
+  lgar_wave_finish_kernel<<<blocks, 128, 0, stream>>>(cfg, d, w, wv, lane_stride, use_ff);
   lgar_wave_clear_kernel<<<1, 32, 0, stream>>>(wv);
   return cudaGetLastError();
 }
@@ -617,7 +507,10 @@ __global__ void lgar_wave_init_kernel(const __grid_constant__ LgarConfig cfg, co
     wv.queue[LG_ST_FETCH][0][i] = i;
   }
   if (blockIdx.x == 0 && threadIdx.x < LGAR_NSTAGE * 2) wv.qcount[threadIdx.x] = (threadIdx.x == LG_ST_FETCH * 2) ? wv.nslots : 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *wv.done_columns = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *wv.done_columns = 0;
+    *wv.xcount = 0;
+  }
 }
 
 // reset the consumed queue's count (and the FETCH cursor) after its kernel ran
@@ -632,7 +525,7 @@ cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& 
 }
 
 cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int stage, int consume,
-                                   unsigned append_mask, int quantum, int max_items, int sm_count, cudaStream_t stream) {
+                                   unsigned append_mask, int quantum, int max_items, int sm_count, const LgarExpressAdmit& xa, cudaStream_t stream) {
   // grid-stride over the queue; max_items (slots in flight at the start of the round) bounds every queue
   const int blocks = std::max(1, std::min((std::min(wv.nslots, max_items) + 127) / 128, sm_count * 16));
   const size_t sm = 0;
@@ -641,7 +534,7 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
   switch (stage) {
     case LG_ST_FETCH:
       if (refill)
-        lgar_wave_fetch_kernel<<<std::min(blocks, sm_count * fetch_refill), 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask);
+        lgar_wave_fetch_kernel<<<std::min(blocks, sm_count * fetch_refill), 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, xa);
       else
         lgar_wave_kernel<LG_ST_FETCH><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum);
       break;
@@ -759,17 +652,9 @@ cudaError_t lgar_launch_gather_layers(const LgarDeviceState& d, double* dst, int
 cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream, int mode) {
   cudaError_t err = cudaMemsetAsync(w.tile_counter, 0, sizeof(int32_t), stream);
   if (err != cudaSuccess) return err;
-  if (mode == 2)
-    lgar_lanes_kernel<<<blocks, LGAR_WINDOW_THREADS, 0, stream>>>(cfg, d, w);
-  else
-    lgar_window_kernel<<<blocks, LGAR_WINDOW_THREADS, 0, stream>>>(cfg, d, w);
+  (void)mode;  // mode 1 only: the per-lane staged kernel (mode 2, 6e7 column-timesteps/s) was removed in round 2
+  lgar_window_kernel<<<blocks, LGAR_WINDOW_THREADS, 0, stream>>>(cfg, d, w);
   return cudaGetLastError();
-}
-
-int lgar_lanes_kernel_max_blocks_per_sm() {
-  int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lgar_lanes_kernel, LGAR_WINDOW_THREADS, 0);
-  return nb;
 }
 
 int lgar_window_kernel_max_blocks_per_sm() {

@@ -53,23 +53,39 @@ struct LgarWave {
   int32_t nslots;
   int32_t* done_columns;       // columns that finished their window
   int32_t* cursor;             // FETCH kernel: next queue entry to hand out (zero between launches)
+  // express lane (lgar_express.cu): slots whose columns are active in (nearly) every hour leave the rounds and are run to the
+  // end of the window by a kernel that keeps their records in shared memory
+  int32_t* xqueue;             // [nslots] slot ids, appended by FETCH (all at the start of an active step: stage HEAD)
+  int32_t* xcount;             // entries appended this window
+  int32_t* xcursor;            // [LGAR_XSTREAMS] items handed out by the express launch that owns the cell
+};
+#define LGAR_XSTREAMS 4
+// what FETCH is told about the express lane for one round: a slot that arrives at an active step of hour t <= admit_t with at
+// least min_left hours of the window left is appended to xqueue instead of the HEAD queue (admit_t < 0: nobody is)
+struct LgarExpressAdmit {
+  int admit_t, min_left, cap;
 };
 
 #ifndef LGAR_HOSTSIM
 // one launch of the kernel of `stage`, consuming queue[stage][consume]; append_mask bit s = buffer of stage s to append to;
 // sm_count: multiprocessors of the device (grids are sized in multiples of it)
 cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int stage, int consume,
-                                   unsigned append_mask, int quantum, int max_items, int sm_count, cudaStream_t stream);
+                                   unsigned append_mask, int quantum, int max_items, int sm_count, const LgarExpressAdmit& xa, cudaStream_t stream);
+// Express / finishing kernel with the lane records in shared memory (lgar_express.cu).  xend >= 0: the entries [xbegin, xend) of
+// wv.xqueue (stage HEAD), handed out through `cursor` (one int, zeroed on `stream` before the launch).  xend < 0: finishing
+// mode -- every slot still in one of the stage queues (wv.cursor; the queue counts are cleared afterwards).  slots_per_warp:
+// 32, 16 or 8 records per warp; quantum: search trips per turn; use_ff: searches through the fast path of lgar_search.cuh.
+cudaError_t lgar_launch_wave_express(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int xbegin, int xend,
+                                     int32_t* cursor, int items, int slots_per_warp, int quantum, int use_ff, int sm_count, cudaStream_t stream);
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
-                                    int lane_stride, int sm_count, cudaStream_t stream);
+                                    int lane_stride, int use_ff, int sm_count, cudaStream_t stream);
 cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWave& wv, int slot_is_column, cudaStream_t stream);
-// the 12 queue counts into pinned host memory (device-visible under unified addressing), no copy engine involved
+// the 12 queue counts (and, at index 12, the express count) into pinned host memory (device-visible under unified addressing), no copy engine involved
 cudaError_t lgar_launch_wave_poll(const LgarWave& wv, int32_t* host_counts, cudaStream_t stream);
 size_t lgar_lane_context_bytes();
-// mode 1: warp-tile window kernel; mode 2: per-lane staged program (lgar_lanes.cuh)
+// mode 1: warp-tile window kernel
 cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream, int mode);
 int lgar_window_kernel_max_blocks_per_sm();
-int lgar_lanes_kernel_max_blocks_per_sm();
 
 // ev (nullable): three events recorded before the stream kernel, between the kernels, after the active kernel
 cudaError_t lgar_launch_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int active_blocks,

@@ -94,95 +94,6 @@ LG_FN bool lg_search_init(LgLane& L, int layer_num, double psi_cm, double new_ma
   return true;
 }
 
-#ifndef LGAR_HOSTSIM
-// Warp-cooperative psi search: up to `max_trips` trips of ONE search by the 32 lanes of a warp, 32 trips at a time.
-// Every lane holds the same LgSearch on entry and on return.  Lane j runs the cheap recurrence (lg_search_pre) j+1 times
-// under the assumption that trips 0..j-1 all leave the direction of the search as it is, evaluates the mass at ITS psi
-// (the 3 x exp/log that dominate a trip) and applies the exit conditions with its left neighbour's mass difference and
-// the run length of "no mass change" trips (ballot).  The first lane whose trip ends the search or turns it round is
-// where the sequential loop would be after that many trips: its state is broadcast and the warp goes on from there.  A
-// search of 10^4 trips (the tail that sets the length of a window) takes ~300 warp steps instead of 10^4 dependent
-// trips; the numbers are those of lg_search_iter bit for bit, whatever the grouping.
-__device__ __forceinline__ double lg_shfl(double v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
-LG_FN_NOINLINE void lg_search_warp(LgSearch& q, const LgarColumnClass& cls, int max_trips) {
-  const unsigned FULL = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31;
-  int budget = max_trips;
-  while (!q.done && budget > 0) {
-    const bool up = q.new_mass > q.prior_mass;
-    LgSearch s = q;
-#pragma unroll 1
-    for (int i = 0; i <= lane; i++) lg_search_pre(s, up);
-    lg_search_eval(s, cls);
-    // exit conditions of this lane's trip (lg_search_post with the neighbours' values)
-    double dprev = __shfl_up_sync(FULL, s.delta_mass, 1);
-    if (lane == 0) dprev = q.delta_mass_prev;
-    const bool brk1 = fabs(s.psi_loc - s.psi_prev) < 1E-15 && s.factor < 1E-13;
-    const bool nochange = fabs(s.delta_mass - dprev) < 1E-15;
-    const unsigned ncm = __ballot_sync(FULL, nochange);
-    // consecutive no-change trips ending at this lane; if the run reaches lane 0 it continues the count carried in
-    const unsigned inv = ~(ncm << (31 - lane));   // bit 31 = this lane, downwards = lanes to the left
-    const int run = __clz((int)inv);                // leading ones of (ncm << (31-lane))
-    int count = (run > lane) ? lane + 1 + q.count_no_mass_change : run;
-    int count_prev = __shfl_up_sync(FULL, count, 1);
-    if (lane == 0) count_prev = q.count_no_mass_change;
-    bool brk = brk1;
-    if (!brk1) {
-      const int first_thresh = LG_MAX_ITER_MBAL / 100;
-      if (count == 5 && s.precip_mass_to_add < 1.E-12) brk = true;
-      else if (s.iter > LG_MAX_ITER_MBAL) brk = true;
-      else if ((s.psi_loc > LG_PSI_UPPER_LIM) && (s.iter > first_thresh)) brk = true;
-      else if (s.psi_loc <= 0 && s.psi_prev < 0) brk = true;
-    } else {
-      count = count_prev;  // the count is not touched when the first condition breaks
-    }
-    const bool done = brk || !(s.delta_mass > LG_MBAL_TOL);
-    const bool stop = done || ((s.new_mass > s.prior_mass) != up) || (lane + 1 >= budget);
-    const unsigned sm = __ballot_sync(FULL, stop);
-    const int jl = sm ? (__ffs(sm) - 1) : 31;
-    s.count_no_mass_change = count;
-    s.delta_mass_prev = brk ? dprev : s.delta_mass;
-    s.done = done;
-    // the state after trip jl is the state of the sequential loop
-    q.psi_loc = lg_shfl(s.psi_loc, jl);
-    q.factor = lg_shfl(s.factor, jl);
-    q.psi_prev = lg_shfl(s.psi_prev, jl);
-    q.delta_mass = lg_shfl(s.delta_mass, jl);
-    q.delta_mass_prev = lg_shfl(s.delta_mass_prev, jl);
-    q.new_mass = lg_shfl(s.new_mass, jl);
-    q.theta = lg_shfl(s.theta, jl);
-    q.iter = __shfl_sync(FULL, s.iter, jl);
-    q.count_no_mass_change = __shfl_sync(FULL, s.count_no_mass_change, jl);
-    const int flags = (s.switched ? 1 : 0) | (s.wanted_to_saturate ? 2 : 0) | (s.aug ? 4 : 0) | (s.aug_extreme ? 8 : 0) | (s.done ? 16 : 0);
-    const int fj = __shfl_sync(FULL, flags, jl);
-    q.switched = fj & 1;
-    q.wanted_to_saturate = (fj & 2) != 0;
-    q.aug = (fj & 4) != 0;
-    q.aug_extreme = (fj & 8) != 0;
-    q.done = (fj & 16) != 0;
-    budget -= jl + 1;
-  }
-}
-// the search record of lane `src` to every lane of the warp
-__device__ __forceinline__ void lg_search_bcast(LgSearch& q, int src) {
-  const unsigned FULL = 0xFFFFFFFFu;
-  q.psi_loc = lg_shfl(q.psi_loc, src); q.factor = lg_shfl(q.factor, src); q.psi_prev = lg_shfl(q.psi_prev, src);
-  q.delta_mass = lg_shfl(q.delta_mass, src); q.delta_mass_prev = lg_shfl(q.delta_mass_prev, src);
-  q.new_mass = lg_shfl(q.new_mass, src); q.prior_mass = lg_shfl(q.prior_mass, src);
-  q.precip_mass_to_add = lg_shfl(q.precip_mass_to_add, src); q.theta = lg_shfl(q.theta, src);
-#pragma unroll
-  for (int k = 0; k <= LGAR_MAXL; k++) {
-    q.dth[k] = lg_shfl(q.dth[k], src);
-    q.dz[k] = lg_shfl(q.dz[k], src);
-  }
-  q.layer_num = __shfl_sync(FULL, q.layer_num, src); q.iter = __shfl_sync(FULL, q.iter, src);
-  q.count_no_mass_change = __shfl_sync(FULL, q.count_no_mass_change, src);
-  const int flags = (q.switched ? 1 : 0) | (q.wanted_to_saturate ? 2 : 0) | (q.aug ? 4 : 0) | (q.aug_extreme ? 8 : 0) | (q.done ? 16 : 0);
-  const int fj = __shfl_sync(FULL, flags, src);
-  q.switched = fj & 1; q.wanted_to_saturate = (fj & 2) != 0; q.aug = (fj & 4) != 0; q.aug_extreme = (fj & 8) != 0; q.done = (fj & 16) != 0;
-}
-#endif
-
 // what follows the loop in lgar_theta_mass_balance (lgar.cxx:3096-3110); only after an iterated search
 LG_FN void lg_search_finish(LgLane& L) {
   const LgSearch& q = L.q;
