@@ -560,7 +560,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip value_by_call_hours, the full-year run, the stage timing window and the parity block")
     ap.add_argument("--finish-below", type=int, default=-1, help="wavefront: slots in flight below which the finishing kernel takes over (-1: engine default)")
-    ap.add_argument("--mode", type=int, default=3, help="3 six stage kernels with queues between them, 2 lanes kernel, 1 warp-tile window kernel, 0 one kernel pair per forcing hour")
+    ap.add_argument("--mode", type=int, default=3, help="3 six stage kernels with queues between them, 1 warp-tile window kernel, 0 one kernel pair per forcing hour")
     args = ap.parse_args()
     # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints
     # "NCCL version ..." there whatever NCCL_DEBUG_FILE says) are sent to stderr, the line goes to the saved descriptor
@@ -856,13 +856,13 @@ def main():
         units = ncol * H
         B_unit = B_full
         dur_s = ms_w * 1e-3 / args.steps  # per bench step (H forcing hours of every column)
-        dominant = "window scheduler: " + {3: "lgar_wave_kernel<FETCH..CORR> + lgar_wave_fetch_kernel + lgar_wave_finish_kernel", 2: "lgar_lanes_kernel", 1: "lgar_window_kernel"}[args.mode]
+        dominant = "window scheduler: " + {3: "lgar_wave_kernel<FETCH..CORR> + lgar_wave_fetch_kernel + lgar_wave_finish_smem_kernel", 1: "lgar_window_kernel"}[args.mode]
         share = None
         if stage_times:
             st_ = stage_times["stages"]
             top = max(st_, key=lambda k: st_[k]["ms"])
             names = {"FETCH": "lgar_wave_fetch_kernel", "HEAD": "lgar_wave_kernel<1> (HEAD)", "FRONT": "lgar_wave_kernel<2> (FRONT)", "SEARCH": "lgar_wave_kernel<3> (SEARCH)",
-                     "TAIL": "lgar_wave_kernel<4> (TAIL)", "CORR": "lgar_wave_kernel<5> (CORR)", "FINISH": "lgar_wave_finish_kernel"}
+                     "TAIL": "lgar_wave_kernel<4> (TAIL)", "CORR": "lgar_wave_kernel<5> (CORR)", "FINISH": "lgar_wave_finish_smem_kernel"}
             share = {names[k]: v["share_of_stage_time"] for k, v in st_.items()}
             u240 = ncol * 240
             dominant_block = {"kernel": names[top], "share_of_stage_time": st_[top]["share_of_stage_time"], "launches_per_240h_window": st_[top]["launches"],

@@ -230,13 +230,6 @@ int lgarb_get_warp_times(lgarb_engine* e, uint32_t* out16384);
 /* number of kernels launched by this engine so far, and columns routed to the active kernel in
  * the last step */
 int64_t lgarb_get_launch_count(const lgarb_engine* e);
-/* Express lane of the window scheduler (lgar_c_b200/csrc/lgar_express.cu): slots whose columns are active in nearly every hour
- * leave the rounds and are run to the end of the window by a kernel that keeps their records in shared memory.  Scheduling
- * only: results do not depend on it.  on: 0/1; first_round: first round that admits; factor_x4: a slot at hour t of the window
- * in round r is admitted if t <= r * factor_x4 / 4; cap_permille: at most this share of the columns per window; negative
- * arguments leave a value as it is.  lgarb_get_express_count: columns that took the express lane so far. */
-int lgarb_set_express_params(lgarb_engine* e, int on, int first_round, int factor_x4, int cap_permille);
-int64_t lgarb_get_express_count(const lgarb_engine* e);
 int64_t lgarb_get_last_active_count(lgarb_engine* e);
 /* Per-kernel device timing with CUDA events recorded on the engine's own stream (the only place
  * they can see its kernels).  lgarb_set_profiling(e, 1) starts a fresh accumulation;
@@ -256,6 +249,21 @@ int lgarb_measure_fp64_peak(lgarb_engine* e, double ms, double* tflops);
  * bit.  which = 0: the out-of-line function every cold call site uses, 1: the inlined common case of the psi search with its
  * fall-back to the former. */
 int lgarb_debug_pow(lgarb_engine* e, int64_t n, const double* x, const double* y, double* out, int which);
+/* The leaf functions of the path on a FROZEN SNAPSHOT of the engine's state, element by element on the device (SURVEY.md section 7
+ * step 4): out[i] = fn(a[i], b[i]) for column i < n <= n_columns, with the soil of layer `layer` (1-based, clamped to the column's
+ * layer count) of column i's class row:
+ *   0 calc_theta_from_h(h = a)             reference src/soil_funcs.cxx:147-150
+ *   1 calc_Se_from_h(h = a)                :155-159
+ *   2 calc_K_from_Se(Se = a)               :164-167
+ *   3 calc_h_from_Se(Se = a)               :172-179
+ *   4 calc_Geff(theta1 = a, theta2 = b)    :15-131 (closed form or numeric as the configuration says)
+ *   5 lgar_calc_mass_bal of column i's current fronts          src/lgar.cxx:2632-2668
+ *   6 calc_aet(PET_cm_per_h = a, dt_h = b) on the current fronts   src/aet.cxx:17-77
+ *   7 / 8 / 9 calc_CR_Q(dt = a, input_cm_per_h = b) from the column's current reservoir storages: discharge / fast storage after /
+ *             slow storage after (the engine's state is not modified)     src/conceptual_reservoir.cxx:7-45
+ *   10 / 11   the fast / slow storage that call starts from, as it stands in the state (cm)
+ * The GIUH convolution is fused into the step epilogue and is checked through whole steps (giuh_runoff of every golden case). */
+int lgarb_debug_functions(lgarb_engine* e, int fn, int layer, int64_t n, const double* a, const double* b, double* out);
 /* Path counters: how often the rare branches of the reference ran since they were switched on (merge, layer crossing, domain
  * bottom crossing, dry-over-wet, theta < theta_r deletion, saturated-front depth loop, ..., every exit of the psi search; the
  * LGAR_PATH_* numbering of lgar_c_b200/csrc/lgar_types.h = LGO_PATH_* of oracle/lgar_oracle.h; reference src/lgar.cxx:1519-1537,

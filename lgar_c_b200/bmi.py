@@ -131,12 +131,11 @@ def _load():
         "lgarb_get_stage_profile": ([vp, vp], C.c_int),
         "lgarb_get_warp_times": ([vp, vp], C.c_int),
         "lgarb_get_launch_count": ([vp], i64),
-        "lgarb_set_express_params": ([vp, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
-        "lgarb_get_express_count": ([vp], i64),
         "lgarb_get_last_active_count": ([vp], i64),
         "lgarb_get_stream": ([vp], vp),
         "lgarb_measure_fp64_peak": ([vp, C.c_double, dp], C.c_int),
         "lgarb_debug_pow": ([vp, C.c_int64, vp, vp, vp, C.c_int], C.c_int),
+        "lgarb_debug_functions": ([vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp], C.c_int),
         "lgarb_set_path_counters": ([vp, C.c_int], C.c_int),
         "lgarb_set_stage_timing": ([vp, C.c_int], C.c_int),
         "lgarb_get_stage_times": ([vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)], C.c_int),
@@ -480,13 +479,6 @@ class BmiLGARBatch:
     def get_launch_count(self):
         return self._L.lgarb_get_launch_count(self._h)
 
-    def set_express_params(self, on=-1, first_round=-1, factor_x4=-1, cap_permille=-1):
-        """Express lane of the window scheduler (scheduling only; negative = leave as it is)."""
-        self._ck(self._L.lgarb_set_express_params(self._h, int(on), int(first_round), int(factor_x4), int(cap_permille)))
-
-    def get_express_count(self):
-        return self._L.lgarb_get_express_count(self._h)
-
     def get_last_active_count(self):
         return self._L.lgarb_get_last_active_count(self._h)
 
@@ -533,6 +525,16 @@ class BmiLGARBatch:
             raise LgarbError("x and y must have the same number of items")
         out = np.empty_like(x)
         self._ck(self._L.lgarb_debug_pow(self._h, x.size, _ptr(x), _ptr(y), _ptr(out), int(which)))
+        return out
+
+    def debug_functions(self, fn, a, b=None, layer=1):
+        """Leaf functions of the path on the engine's current state, one item per column (lgarb_debug_functions)."""
+        a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+        b = np.zeros_like(a) if b is None else np.ascontiguousarray(b, dtype=np.float64).ravel()
+        if a.shape != b.shape or a.size > self.n_columns:
+            raise LgarbError("a and b must have the same number of items, at most n_columns")
+        out = np.empty_like(a)
+        self._ck(self._L.lgarb_debug_functions(self._h, int(fn), int(layer), a.size, _ptr(a), _ptr(b), _ptr(out)))
         return out
 
     def get_stream(self) -> int:

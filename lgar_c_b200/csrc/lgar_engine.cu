@@ -115,21 +115,12 @@ struct lgarb_engine {
   // to its end inside one launch where the plain walk parks a 10^4-trip search after `quantum` trips: 4.09e8 with 65 536 against
   // 4.74e8 with 0.
   int wave_ff_below = 0;
-  // express lane (lgar_express.cu): columns that are active in nearly every hour leave the rounds and run on chip
-  int wave_express = 1;          // 0: off
-  int express_r0 = 24;           // first round that admits
-  int express_factor_x4 = 8;     // a slot at hour t of the window in round r is admitted if t <= r * factor_x4 / 4
-  int express_cap_permille = 40; // at most this share of the slots per window
-  int express_min_left = 96;     // ... and only with at least this many hours of the window left
-  int express_min_batch = 2048;  // entries that make a launch worth while (powers of two of the round index launch whatever is there)
-  int express_spw = 32;          // records per warp: 32, 16 or 8
-  int express_quantum = 64;      // search trips per turn of the warp
-  int express_ff = 0;            // searches of the express lane through the fast path
-  int finish_smem = 1;           // the finishing kernel is the express kernel (records in shared memory); 0: one thread per slot out of thread-private records
-  int finish_ff = 1;             // finishing kernel: searches through the fast path
-  cudaStream_t xstream[LGAR_XSTREAMS] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t xev[LGAR_XSTREAMS] = {nullptr, nullptr, nullptr, nullptr};
-  int64_t express_columns = 0;   // slots that took the express lane so far (lgarb_get_express_count)
+  // The finishing kernel keeps its lane records in shared memory (lgar_finish_smem.cu); 0: round 1's kernel, one thread per slot
+  // out of thread-private records.  Measured: 4.79e8 -> 5.00e8 (call of 480 h), 5.29e8 -> 5.48e8 (1 460 h).
+  int finish_smem = 1;
+  int finish_spw = 16;           // records per warp of that kernel: 32 ... 2
+  int finish_quantum = 64;       // search trips per turn of its warps
+  int finish_ff = 0;             // finishing kernel: searches through the fast path (measured: no gain either way)
   unsigned long long* d_paths = nullptr;  // [LGAR_NPATH] path counters, allocated by lgarb_set_path_counters
   int finish_lane_stride = 4;  // finishing kernel: one slot per this many lanes
   int sm_count = 0;            // multiprocessors of the device: grids are sized in multiples of it
@@ -214,12 +205,6 @@ struct lgarb_engine {
     }
     if (side_stream) cudaStreamDestroy(side_stream);
     side_stream = nullptr;
-    for (int i = 0; i < LGAR_XSTREAMS; i++) {
-      if (xev[i]) cudaEventDestroy(xev[i]);
-      xev[i] = nullptr;
-      if (xstream[i]) cudaStreamDestroy(xstream[i]);
-      xstream[i] = nullptr;
-    }
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
     initialized = false;
@@ -861,17 +846,10 @@ int lgarb_create(lgarb_engine** out) {
   knob("LGARB_WAVE_CORR_ASYNC", (*out)->wave_corr_async);
   knob("LGARB_WAVE_FINISH_BELOW", (*out)->wave_finish_below);
   knob("LGARB_WAVE_FF_BELOW", (*out)->wave_ff_below);
-  knob("LGARB_EXPRESS", (*out)->wave_express);
-  knob("LGARB_EXPRESS_R0", (*out)->express_r0);
-  knob("LGARB_EXPRESS_FACTOR_X4", (*out)->express_factor_x4);
-  knob("LGARB_EXPRESS_CAP_PERMILLE", (*out)->express_cap_permille);
-  knob("LGARB_EXPRESS_MIN_LEFT", (*out)->express_min_left);
-  knob("LGARB_EXPRESS_MIN_BATCH", (*out)->express_min_batch);
-  knob("LGARB_EXPRESS_SPW", (*out)->express_spw);
-  knob("LGARB_EXPRESS_QUANTUM", (*out)->express_quantum);
-  knob("LGARB_EXPRESS_FF", (*out)->express_ff);
   knob("LGARB_FINISH_SMEM", (*out)->finish_smem);
   knob("LGARB_FINISH_FF", (*out)->finish_ff);
+  knob("LGARB_FINISH_SPW", (*out)->finish_spw);
+  knob("LGARB_FINISH_QUANTUM", (*out)->finish_quantum);
   knob("LGARB_FINISH_LANE_STRIDE", (*out)->finish_lane_stride);
   knob("LGARB_UPDATE_WAVE_MIN_COLS", (*out)->update_wave_min_cols);
   knob("LGARB_WAVE_ESCALATE_BELOW", (*out)->wave_escalate_below);
@@ -952,13 +930,6 @@ void ensure_wave(lgarb_engine* e) {
     wv.qcount = e->dalloc<int32_t>(LGAR_NSTAGE * 2);
     wv.done_columns = e->dalloc<int32_t>(1);
     wv.cursor = e->dalloc<int32_t>(1);
-    wv.xqueue = e->dalloc<int32_t>((size_t)wv.nslots, false);
-    wv.xcount = e->dalloc<int32_t>(1);
-    wv.xcursor = e->dalloc<int32_t>(LGAR_XSTREAMS);
-    for (int i = 0; i < LGAR_XSTREAMS; i++) {
-      if (!e->xstream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&e->xstream[i], cudaStreamNonBlocking));
-      if (!e->xev[i]) CUDA_TRY(cudaEventCreateWithFlags(&e->xev[i], cudaEventDisableTiming));
-    }
     if (!e->side_stream) {
       CUDA_TRY(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
       for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->side_ev[i], cudaEventDisableTiming));
@@ -1010,32 +981,6 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
   } ncu_stop{ncu_whole_window, e->stream};
   std::vector<std::pair<cudaEvent_t, int>> dbg_evs;
   cudaStream_t launch_stream = e->stream;
-  // express lane: what FETCH is told this round, what has been launched so far
-  LgarExpressAdmit xa{-1, e->express_min_left, (int)((int64_t)wv.nslots * e->express_cap_permille / 1000)};
-  const bool express_on = e->wave_express != 0 && e->use_window == 3 && w.slot_is_column && xa.cap > 0;
-  int x_count = 0, x_launched = 0, x_next = 0;
-  bool x_used[LGAR_XSTREAMS] = {false, false, false, false};
-  auto launch_express = [&](int upto) {
-    if (upto <= x_launched) return;
-    const int k = x_next;
-    x_next = (x_next + 1) % LGAR_XSTREAMS;
-    CUDA_TRY(lgar_launch_wave_express(e->cfg, e->d, w, wv, x_launched, upto, wv.xcursor + k, upto - x_launched, e->express_spw, e->express_quantum, e->express_ff,
-                                      e->sm_count, e->xstream[k]));
-    if (dbg_on) fprintf(stderr, "[wave] express launch: entries [%d, %d) on stream %d\n", x_launched, upto, k);
-    x_used[k] = true;
-    e->launches += 1;
-    e->express_columns += upto - x_launched;
-    x_launched = upto;
-  };
-  // the caller's stream order must cover the express lane: whatever follows the window waits for it
-  auto join_express = [&]() {
-    launch_express(x_count);
-    for (int k = 0; k < LGAR_XSTREAMS; k++)
-      if (x_used[k]) {
-        CUDA_TRY(cudaEventRecord(e->xev[k], e->xstream[k]));
-        CUDA_TRY(cudaStreamWaitEvent(e->stream, e->xev[k], 0));
-      }
-  };
   auto launch = [&](int stage) {
     const int consume = par[stage];
     par[stage] ^= 1;
@@ -1054,7 +999,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       CUDA_TRY(cudaEventRecord(se.a, launch_stream));
     }
     CUDA_TRY(lgar_launch_wave_stage(e->cfg, e->d, w, wv, stage, consume, mask, stage == LG_ST_CORR ? std::max(1, quantum * e->wave_corr_quantum / e->wave_quantum) : quantum, in_flight,
-                                    e->sm_count, xa, launch_stream));
+                                    e->sm_count, launch_stream));
     if (e->stage_timing) {
       CUDA_TRY(cudaEventRecord(se.b, launch_stream));
       e->stage_evs.push_back(se);
@@ -1081,9 +1026,6 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
         cnt[s] = h_cnt[2 * s] + h_cnt[2 * s + 1];
         in_flight += cnt[s];
       }
-      x_count = std::min(h_cnt[2 * LGAR_NSTAGE], wv.nslots);
-      // every entry the host sees is complete (the poll is stream-ordered behind the FETCH that wrote it)
-      if (x_count - x_launched >= e->express_min_batch || (x_count > x_launched && (round & (round - 1)) == 0)) launch_express(x_count);
       if (in_flight == 0) break;
       if (in_flight <= e->wave_finish_below) {  // the stragglers: one thread per slot runs its column to the end of the window
         if (debug) cudaEventRecord(dbg[0], e->stream);
@@ -1095,7 +1037,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
           CUDA_TRY(cudaEventRecord(se.a, e->stream));
         }
         if (e->finish_smem)
-          CUDA_TRY(lgar_launch_wave_express(e->cfg, e->d, w, wv, 0, -1, wv.cursor, in_flight, e->express_spw, e->express_quantum, e->finish_ff, e->sm_count, e->stream));
+          CUDA_TRY(lgar_launch_wave_finish_smem(e->cfg, e->d, w, wv, in_flight, e->finish_spw, e->finish_quantum, e->finish_ff, e->sm_count, e->stream));
         else
           CUDA_TRY(lgar_launch_wave_finish(e->cfg, e->d, w, wv, in_flight, e->finish_lane_stride, e->finish_ff, e->sm_count, e->stream));
         if (e->stage_timing) {
@@ -1124,7 +1066,6 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
       cudaProfilerStart();
     }
     w.use_ff = in_flight <= e->wave_ff_below ? 1 : 0;  // the lambdas above launch with `w` as it is now
-    xa.admit_t = (express_on && round >= e->express_r0) ? (int)std::min<int64_t>(round * e->express_factor_x4 / 4, 1 << 30) : -1;
     const bool new_steps = cnt[LG_ST_FETCH] + cnt[LG_ST_HEAD] > 0;
     const bool corr_async = e->use_window == 3 && e->wave_corr_async && !dbg_on;
     bool corr_forked = false;
@@ -1180,7 +1121,6 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
               (long long)round, ms, in_flight, cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], cnt[5], st_ms[0], st_ms[1], st_ms[2], st_ms[3], st_ms[4], st_ms[5]);
     }
   }
-  join_express();
   if (debug) {
     cudaEventDestroy(dbg[0]);
     cudaEventDestroy(dbg[1]);
@@ -1769,15 +1709,6 @@ int lgarb_set_wave_params(lgarb_engine* e, int search_quantum, int front_search_
   });
 }
 int64_t lgarb_get_launch_count(const lgarb_engine* e) { return e ? e->launches : -1; }
-int lgarb_set_express_params(lgarb_engine* e, int on, int first_round, int factor_x4, int cap_permille) {
-  LGARB_GUARD(e, {
-    if (on >= 0) e->wave_express = on;
-    if (first_round >= 0) e->express_r0 = first_round;
-    if (factor_x4 >= 0) e->express_factor_x4 = factor_x4;
-    if (cap_permille >= 0) e->express_cap_permille = std::min(cap_permille, 1000);
-  });
-}
-int64_t lgarb_get_express_count(const lgarb_engine* e) { return e ? e->express_columns : -1; }
 int64_t lgarb_get_last_active_count(lgarb_engine* e) {
   if (!e || !e->initialized) return -1;
   int32_t c = -1;
@@ -1843,6 +1774,24 @@ int lgarb_debug_pow(lgarb_engine* e, int64_t n, const double* x, const double* y
     cudaError_t err = cudaMemcpyAsync(dbuf, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(dbuf + n, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess) err = lgar_launch_debug_pow(dbuf, dbuf + n, dbuf + 2 * n, n, which, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(out, dbuf + 2 * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(dbuf);
+    e->launches += 1;
+    CUDA_TRY(err);
+  });
+}
+
+int lgarb_debug_functions(lgarb_engine* e, int fn, int layer, int64_t n, const double* a, const double* b, double* out) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (n < 0 || n > e->ncol || fn < 0 || fn > 11 || !a || !b || !out) throw std::runtime_error("bad arguments");
+    if (n == 0) return LGARB_SUCCESS;
+    double* dbuf = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&dbuf, (size_t)n * 3 * sizeof(double)));
+    cudaError_t err = cudaMemcpyAsync(dbuf, a, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(dbuf + n, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) err = lgar_launch_debug_functions(e->cfg, e->d, fn, layer, n, dbuf, dbuf + n, dbuf + 2 * n, e->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(out, dbuf + 2 * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
     cudaFree(dbuf);

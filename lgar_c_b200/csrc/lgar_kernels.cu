@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
 // the MEAN walk of what it handles, not the maximum; the forcing of the next hour is requested before the current hour is
 // computed.  The arithmetic per hour is lg_resident_hour(), the body lg_advance_resident() loops over: bit-identical.
 __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w,
-                                                              const __grid_constant__ LgarWave wv, int consume, unsigned append_mask, const LgarExpressAdmit xa) {
+                                                              const __grid_constant__ LgarWave wv, int consume, unsigned append_mask) {
   const unsigned FULL = 0xFFFFFFFFu;
   const int n = wv.qcount[LG_ST_FETCH * 2 + consume];
   const int lane = threadIdx.x & 31;
@@ -366,13 +366,6 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
         if (t < K) {
           G.stage = LG_ST_HEAD;
           next = LG_ST_HEAD;
-          // Express lane (lgar_express.cu): a slot that has advanced few hours for the rounds it has been through sits in a
-          // column that is active in (nearly) every hour; it leaves the rounds here.  The cap is read without a lock: it may be
-          // overshot by the lanes in flight, the queue holds every slot.
-          if (t <= xa.admit_t && K - t >= xa.min_left && *(volatile int32_t*)wv.xcount < xa.cap) {
-            wv.xqueue[atomicAdd(wv.xcount, 1)] = slot;
-            next = -1;
-          }
         } else {  // this column has finished the window (lg_stage_fetch, slot == column)
           lg_lane_export(cfg, d, col, G);
           if (w.done_columns) atomicAdd(w.done_columns, 1);
@@ -465,13 +458,12 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
 
 // Queue counts to the host through mapped pinned memory: a cudaMemcpyAsync of these 48 bytes would queue behind whatever
 // bulk device-to-host copy (output series of the previous chunk of a streamed call) occupies the copy engine.
-__global__ void lgar_wave_poll_kernel(const int32_t* qcount, const int32_t* xcount, int32_t* host_counts) {
+__global__ void lgar_wave_poll_kernel(const int32_t* qcount, int32_t* host_counts) {
   if (threadIdx.x < 2 * LGAR_NSTAGE) host_counts[threadIdx.x] = qcount[threadIdx.x];
-  if (threadIdx.x == 2 * LGAR_NSTAGE) host_counts[threadIdx.x] = *xcount;
   __threadfence_system();
 }
 cudaError_t lgar_launch_wave_poll(const LgarWave& wv, int32_t* host_counts, cudaStream_t stream) {
-  lgar_wave_poll_kernel<<<1, 32, 0, stream>>>(wv.qcount, wv.xcount, host_counts);
+  lgar_wave_poll_kernel<<<1, 32, 0, stream>>>(wv.qcount, host_counts);
   return cudaGetLastError();
 }
 
@@ -507,10 +499,7 @@ __global__ void lgar_wave_init_kernel(const __grid_constant__ LgarConfig cfg, co
     wv.queue[LG_ST_FETCH][0][i] = i;
   }
   if (blockIdx.x == 0 && threadIdx.x < LGAR_NSTAGE * 2) wv.qcount[threadIdx.x] = (threadIdx.x == LG_ST_FETCH * 2) ? wv.nslots : 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    *wv.done_columns = 0;
-    *wv.xcount = 0;
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *wv.done_columns = 0;
 }
 
 // reset the consumed queue's count (and the FETCH cursor) after its kernel ran
@@ -525,7 +514,7 @@ cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& 
 }
 
 cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int stage, int consume,
-                                   unsigned append_mask, int quantum, int max_items, int sm_count, const LgarExpressAdmit& xa, cudaStream_t stream) {
+                                   unsigned append_mask, int quantum, int max_items, int sm_count, cudaStream_t stream) {
   // grid-stride over the queue; max_items (slots in flight at the start of the round) bounds every queue
   const int blocks = std::max(1, std::min((std::min(wv.nslots, max_items) + 127) / 128, sm_count * 16));
   const size_t sm = 0;
@@ -534,7 +523,7 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
   switch (stage) {
     case LG_ST_FETCH:
       if (refill)
-        lgar_wave_fetch_kernel<<<std::min(blocks, sm_count * fetch_refill), 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask, xa);
+        lgar_wave_fetch_kernel<<<std::min(blocks, sm_count * fetch_refill), 128, 0, stream>>>(cfg, d, w, wv, consume, append_mask);
       else
         lgar_wave_kernel<LG_ST_FETCH><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum);
       break;
@@ -585,6 +574,52 @@ __global__ void lgar_debug_pow_kernel(const double* __restrict__ x, const double
 }
 cudaError_t lgar_launch_debug_pow(const double* x, const double* y, double* out, int64_t n, int which, cudaStream_t stream) {
   lgar_debug_pow_kernel<<<1184, 256, 0, stream>>>(x, y, out, n, which);
+  return cudaGetLastError();
+}
+
+// Frozen-snapshot evaluation of the leaf functions of the path (lgarb_debug_functions): one item per
+// column, the column's class row and -- for the list functions -- its current fronts and reservoir storages.
+__global__ void lgar_debug_functions_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, int fn, int layer, int64_t n,
+                                            const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const LgarColumnClass& cls = d.classes[d.class_id[i]];
+    const int l = layer < 1 ? 1 : (layer > cls.num_layers ? cls.num_layers : layer);
+    const LgarLayer& s = cls.lay[l];
+    double r = LG_NAN;
+    if (fn == 0) r = lg_theta_from_h(a[i], s);                    // calc_theta_from_h, soil_funcs.cxx:147-150
+    else if (fn == 1) r = lg_Se_from_h(a[i], s);                  // calc_Se_from_h, :155-159
+    else if (fn == 2) r = lg_K_from_Se(a[i], s, s.Ksat);          // calc_K_from_Se, :164-167
+    else if (fn == 3) r = lg_h_from_Se(a[i], s);                  // calc_h_from_Se, :172-179
+    else if (fn == 4) r = lg_Geff(cfg, a[i], b[i], s, s.Ksat);    // calc_Geff, :15-131
+    else if (fn == 5 || fn == 6) {
+      LgFronts f;
+      load_fronts(d, i, f);
+      LgCtx c;
+      c.cfg = &cfg;
+      c.cls = &cls;
+      c.f = &f;
+      c.status = 0;
+      c.ff = lg_ff_ones;
+      c.paths = nullptr;
+      c.use_ff = false;
+      r = (fn == 5) ? lg_mass_bal(c) : lg_calc_aet(c, a[i], b[i]);  // lgar_calc_mass_bal lgar.cxx:2632-2668; calc_aet aet.cxx:17-77
+    } else if (fn >= 7 && fn <= 11) {                              // calc_CR_Q, conceptual_reservoir.cxx:7-45
+      LgScalars sc;
+      load_scalars(d, i, sc);
+      double fast = sc.cr_fast, slow = sc.cr_slow;
+      if (fn == 10) r = fast;                                      // the storages the call starts from, as they are in the state
+      else if (fn == 11) r = slow;
+      else {
+        const double Q = lg_calc_CR_Q(cls.par, a[i], b[i], &fast, &slow);
+        r = fn == 7 ? Q : fn == 8 ? fast : slow;
+      }
+    }
+    out[i] = r;
+  }
+}
+cudaError_t lgar_launch_debug_functions(const LgarConfig& cfg, const LgarDeviceState& d, int fn, int layer, int64_t n, const double* a, const double* b,
+                                        double* out, cudaStream_t stream) {
+  lgar_debug_functions_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, 4096)), 128, 0, stream>>>(cfg, d, fn, layer, n, a, b, out);
   return cudaGetLastError();
 }
 

@@ -53,34 +53,22 @@ struct LgarWave {
   int32_t nslots;
   int32_t* done_columns;       // columns that finished their window
   int32_t* cursor;             // FETCH kernel: next queue entry to hand out (zero between launches)
-  // express lane (lgar_express.cu): slots whose columns are active in (nearly) every hour leave the rounds and are run to the
-  // end of the window by a kernel that keeps their records in shared memory
-  int32_t* xqueue;             // [nslots] slot ids, appended by FETCH (all at the start of an active step: stage HEAD)
-  int32_t* xcount;             // entries appended this window
-  int32_t* xcursor;            // [LGAR_XSTREAMS] items handed out by the express launch that owns the cell
-};
-#define LGAR_XSTREAMS 4
-// what FETCH is told about the express lane for one round: a slot that arrives at an active step of hour t <= admit_t with at
-// least min_left hours of the window left is appended to xqueue instead of the HEAD queue (admit_t < 0: nobody is)
-struct LgarExpressAdmit {
-  int admit_t, min_left, cap;
 };
 
 #ifndef LGAR_HOSTSIM
 // one launch of the kernel of `stage`, consuming queue[stage][consume]; append_mask bit s = buffer of stage s to append to;
 // sm_count: multiprocessors of the device (grids are sized in multiples of it)
 cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int stage, int consume,
-                                   unsigned append_mask, int quantum, int max_items, int sm_count, const LgarExpressAdmit& xa, cudaStream_t stream);
-// Express / finishing kernel with the lane records in shared memory (lgar_express.cu).  xend >= 0: the entries [xbegin, xend) of
-// wv.xqueue (stage HEAD), handed out through `cursor` (one int, zeroed on `stream` before the launch).  xend < 0: finishing
-// mode -- every slot still in one of the stage queues (wv.cursor; the queue counts are cleared afterwards).  slots_per_warp:
-// 32, 16 or 8 records per warp; quantum: search trips per turn; use_ff: searches through the fast path of lgar_search.cuh.
-cudaError_t lgar_launch_wave_express(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int xbegin, int xend,
-                                     int32_t* cursor, int items, int slots_per_warp, int quantum, int use_ff, int sm_count, cudaStream_t stream);
+                                   unsigned append_mask, int quantum, int max_items, int sm_count, cudaStream_t stream);
+// Finishing kernel with the lane records in shared memory (lgar_finish_smem.cu): every slot still in one of the stage queues is
+// run to the end of the window.  slots_per_warp: 32 ... 2 records per warp; quantum: search trips per turn of the warp; use_ff:
+// searches through the fast path of lgar_search.cuh.  The queue counts are cleared afterwards.
+cudaError_t lgar_launch_wave_finish_smem(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
+                                         int slots_per_warp, int quantum, int use_ff, int sm_count, cudaStream_t stream);
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
                                     int lane_stride, int use_ff, int sm_count, cudaStream_t stream);
 cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWave& wv, int slot_is_column, cudaStream_t stream);
-// the 12 queue counts (and, at index 12, the express count) into pinned host memory (device-visible under unified addressing), no copy engine involved
+// the 12 queue counts into pinned host memory (device-visible under unified addressing), no copy engine involved
 cudaError_t lgar_launch_wave_poll(const LgarWave& wv, int32_t* host_counts, cudaStream_t stream);
 size_t lgar_lane_context_bytes();
 // mode 1: warp-tile window kernel
@@ -99,6 +87,9 @@ int lgar_active_kernel_max_blocks_per_sm();
 // DFMA microbenchmark: `iters` trips of 8 independent FMA chains per thread on blocks x 256 threads; sink keeps the result alive
 cudaError_t lgar_launch_dfma(double* sink, int blocks, int iters, cudaStream_t stream);
 // out[i] = x[i]^y[i] with the physics' pow (which = 0: out-of-line function, 1: inlined common case + fall-back)
+// leaf functions on a frozen snapshot: out[i] = fn(a[i], b[i]) for column i (see lgarb_debug_functions)
+cudaError_t lgar_launch_debug_functions(const LgarConfig& cfg, const LgarDeviceState& d, int fn, int layer, int64_t n, const double* a, const double* b,
+                                        double* out, cudaStream_t stream);
 cudaError_t lgar_launch_debug_pow(const double* x, const double* y, double* out, int64_t n, int which, cudaStream_t stream);
 #endif
 
