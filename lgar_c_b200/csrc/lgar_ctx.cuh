@@ -8,16 +8,62 @@
 
 namespace {
 
-__device__ __forceinline__ void wave_push(const LgarWave& wv, unsigned append_mask, int stage, bool pred, int slot) {
-  const unsigned m = __ballot_sync(__activemask(), pred);
+// bins of the stage queues (LGAR_NBIN = 4): by front count, by the layer of the searched front
+__device__ __forceinline__ int wave_bin_fronts(int n) { return n <= 3 ? 0 : n == 4 ? 1 : n <= 6 ? 2 : 3; }
+__device__ __forceinline__ int wave_bin_layers(int l) { return l <= 1 ? 0 : l >= LGAR_NBIN ? LGAR_NBIN - 1 : l - 1; }
+
+// Append `slot` to bin `bin` of the queue of stage `next` (next outside [0, LGAR_NSTAGE): nothing to append).  One atomicAdd per
+// distinct (stage, bin) among the lanes of the warp that call it together.
+__device__ __forceinline__ void wave_push(const LgarWave& wv, unsigned append_mask, int next, int bin, int slot) {
+  const bool pred = next >= 0 && next < LGAR_NSTAGE;
+  const unsigned act = __ballot_sync(__activemask(), pred);
   if (!pred) return;
-  const int buf = (append_mask >> stage) & 1;
+  const int buf = (append_mask >> next) & 1;
+  const int key = (next * 2 + buf) * LGAR_NBIN + bin;
+  const unsigned peers = __match_any_sync(act, key);
   const int lane = threadIdx.x & 31;
-  const int leader = __ffs(m) - 1;
+  const int leader = __ffs(peers) - 1;
   int base = 0;
-  if (lane == leader) base = atomicAdd(wv.qcount + stage * 2 + buf, __popc(m));
-  base = __shfl_sync(m, base, leader);
-  wv.queue[stage][buf][base + __popc(m & ((1u << lane) - 1))] = slot;
+  if (lane == leader) base = atomicAdd(wv.qcount + key, __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  wv.queue[next][buf][(size_t)bin * wv.nslots + base + __popc(peers & ((1u << lane) - 1))] = slot;
+}
+
+// The index space a consumer of queue (stage, buf) walks: the bins one after the other, each starting at a multiple of 32.
+struct WaveItems {
+  int cnt[LGAR_NBIN], voff[LGAR_NBIN + 1];
+};
+__device__ __forceinline__ WaveItems wave_items(const LgarWave& wv, int stage, int buf) {
+  WaveItems it;
+  it.voff[0] = 0;
+#pragma unroll
+  for (int b = 0; b < LGAR_NBIN; b++) {
+    it.cnt[b] = wv.qcount[(stage * 2 + buf) * LGAR_NBIN + b];
+    it.voff[b + 1] = it.voff[b] + ((it.cnt[b] + 31) & ~31);
+  }
+  return it;
+}
+// the slot at index i of that space, or -1 (padding at the end of a bin)
+__device__ __forceinline__ int wave_item(const LgarWave& wv, const WaveItems& it, int stage, int buf, int i) {
+  int slot = -1;
+#pragma unroll
+  for (int b = 0; b < LGAR_NBIN; b++) {
+    const int j = i - it.voff[b];
+    if (j >= 0 && j < it.cnt[b]) slot = wv.queue[stage][buf][(size_t)b * wv.nslots + j];
+  }
+  return slot;
+}
+// item j of the concatenation of every bin of every queue (the finishing kernels): slot and the stage it is parked in
+__device__ __forceinline__ int wave_item_any(const LgarWave& wv, int j, int* stage) {
+  for (int q = 0; q < 2 * LGAR_NSTAGE * LGAR_NBIN; q++) {
+    const int n = wv.qcount[q];
+    if (j < n) {
+      *stage = q / (2 * LGAR_NBIN);
+      return wv.queue[q / (2 * LGAR_NBIN)][(q / LGAR_NBIN) & 1][(size_t)(q % LGAR_NBIN) * wv.nslots + j];
+    }
+    j -= n;
+  }
+  return -1;
 }
 
 // Context copy between HBM and thread-private memory.  The HBM side moves 32 bytes per lane per instruction

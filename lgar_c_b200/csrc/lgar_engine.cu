@@ -926,8 +926,8 @@ void ensure_wave(lgarb_engine* e) {
     e->allocs.push_back(p);
     wv.ctx = (LgLane*)p;
     for (int s = 0; s < LGAR_NSTAGE; s++)
-      for (int b = 0; b < 2; b++) wv.queue[s][b] = e->dalloc<int32_t>((size_t)wv.nslots, false);
-    wv.qcount = e->dalloc<int32_t>(LGAR_NSTAGE * 2);
+      for (int b = 0; b < 2; b++) wv.queue[s][b] = e->dalloc<int32_t>((size_t)wv.nslots * LGAR_NBIN, false);
+    wv.qcount = e->dalloc<int32_t>(LGAR_NSTAGE * 2 * LGAR_NBIN);
     wv.done_columns = e->dalloc<int32_t>(1);
     wv.cursor = e->dalloc<int32_t>(1);
     if (!e->side_stream) {

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(32) lgar_wave_finish_smem_kernel(const __grid_
   const int lane = threadIdx.x;
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
   int total = 0;
-  for (int q = 0; q < 2 * LGAR_NSTAGE; q++) total += wv.qcount[q];
+  for (int q = 0; q < 2 * LGAR_NSTAGE * LGAR_NBIN; q++) total += wv.qcount[q];
   unsigned long long front_sum = 0, active_sum = 0;
   unsigned long long* fsp = w.prof ? &front_sum : nullptr;
   const bool owner = (lane % lane_stride) == 0;  // lane_stride 1 ... 16: 32 ... 2 records per warp
@@ -53,16 +53,8 @@ __global__ void __launch_bounds__(32) lgar_wave_finish_smem_kernel(const __grid_
     if (stage == LG_ST_DONE && !exhausted) {  // refill
       int j = atomicAdd(wv.cursor, 1);
       if (j < total) {
-        int slot = -1, st = LG_ST_DONE;
-        for (int q = 0; q < 2 * LGAR_NSTAGE; q++) {  // item j of the concatenation of all stage queues; the queue a slot sits in is its stage
-          const int n = wv.qcount[q];
-          if (j < n) {
-            slot = wv.queue[q >> 1][q & 1][j];
-            st = q >> 1;
-            break;
-          }
-          j -= n;
-        }
+        int st = LG_ST_DONE;
+        const int slot = wave_item_any(wv, j, &st);  // item j of the concatenation of all stage queues; the queue a slot sits in is its stage
         if (slot >= 0) {
           lane_load<LG_PART_ALL>(&S, &slots[slot]);
           L.c.cfg = &cfg;
@@ -129,7 +121,7 @@ __global__ void __launch_bounds__(32) lgar_wave_finish_smem_kernel(const __grid_
 }
 
 __global__ void lgar_wave_xclear_kernel(LgarWave wv) {
-  if (threadIdx.x < 2 * LGAR_NSTAGE) wv.qcount[threadIdx.x] = 0;
+  if (threadIdx.x < 2 * LGAR_NSTAGE * LGAR_NBIN) wv.qcount[threadIdx.x] = 0;
   if (threadIdx.x == 0) *wv.cursor = 0;  // zero between launches (the FETCH kernel relies on it)
 }
 
@@ -162,6 +154,6 @@ cudaError_t lgar_launch_wave_finish_smem(const LgarConfig& cfg, const LgarDevice
     lgar_wave_finish_smem_kernel<true><<<blocks, 32, bytes, stream>>>(cfg, d, w, wv, 32 / spw, quantum);
   else
     lgar_wave_finish_smem_kernel<false><<<blocks, 32, bytes, stream>>>(cfg, d, w, wv, 32 / spw, quantum);
-  lgar_wave_xclear_kernel<<<1, 32, 0, stream>>>(wv);
+  lgar_wave_xclear_kernel<<<1, 64, 0, stream>>>(wv);
   return cudaGetLastError();
 }

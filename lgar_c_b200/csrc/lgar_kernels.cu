@@ -176,14 +176,15 @@ constexpr int wave_min_blocks(int stage) {
 template <int STAGE, bool FF = false>
 __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int consume,
                                                         unsigned append_mask, int quantum) {
-  const int n = wv.qcount[STAGE * 2 + consume];
+  const WaveItems items = wave_items(wv, STAGE, consume);
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
   unsigned long long front_sum = 0, active_sum = 0;
   unsigned long long* fsp = w.prof ? &front_sum : nullptr;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31); i += gridDim.x * blockDim.x) {
-    const bool valid = i < n;
-    const int slot = valid ? wv.queue[STAGE][consume][i] : 0;
-    int next = -1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items.voff[LGAR_NBIN]; i += gridDim.x * blockDim.x) {
+    const int slot_or_pad = wave_item(wv, items, STAGE, consume, i);
+    const bool valid = slot_or_pad >= 0;
+    const int slot = valid ? slot_or_pad : 0;
+    int next = -1, bin = 0;  // bin of the queue the slot goes to next: by front count; SEARCH: by the layer of the searched front
     if (STAGE == LG_ST_SEARCH) {
       if (valid) {  // only the search record travels
         LgLane& G = slots[slot].L;
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         G.q = q;
         if (q.done) G.resume = true;
         next = q.done ? LG_ST_FRONT : LG_ST_SEARCH;
+        bin = q.done ? wave_bin_fronts(G.nf_stored) : wave_bin_layers(q.layer_num);
       }
     } else if (STAGE == LG_ST_CORR) {
       if (valid) {  // the correction record and the front list travel
@@ -212,12 +214,14 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
 #pragma unroll
         for (int a = 1; a < 3; a++) ctx_store_n(g + kPitch * a, l + kPitch * a, cf);
         next = k.done ? LG_ST_TAIL : LG_ST_CORR;
+        bin = k.done ? wave_bin_fronts(fb.f.n) : 0;
       }
     } else if (STAGE == LG_ST_FETCH) {
       if (valid) {  // works on the record in place: scalars and epilogue state through registers, nothing else is touched
         LgLane& G = slots[slot].L;
         lg_stage_fetch(cfg, d, w, G, fsp);
         next = G.stage;
+        bin = wave_bin_fronts(G.f.n);
       }
     } else if (((LGAR_INPLACE_MASK >> STAGE) & 1) != 0) {
       // The stage works on the record where it lies in HBM (through L1/L2) instead of on a thread-private copy.  The
@@ -243,6 +247,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
             lg_stage_tail(cfg, d, w, G, fsp);
         }
         next = G.stage;
+        bin = next == LG_ST_SEARCH ? wave_bin_layers(G.q.layer_num) : (next == LG_ST_CORR || next == LG_ST_FETCH) ? 0 : wave_bin_fronts(G.f.n);
         G.nf_stored = G.f.n;      // what a later stage that copies the record has to move
         if (STAGE != LG_ST_TAIL) G.nold_stored = G.old.n;
       }
@@ -274,6 +279,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
           lg_stage_tail(cfg, d, w, L, fsp);
       }
       next = L.stage;
+      bin = next == LG_ST_SEARCH ? wave_bin_layers(L.q.layer_num) : (next == LG_ST_CORR || next == LG_ST_FETCH) ? 0 : wave_bin_fronts(L.f.n);
       if (next == LG_ST_FETCH) {
         lane_store<LG_PART_STATE>(&slots[slot], &S);  // the step is over: only the column state lives on
       } else if (STAGE == LG_ST_TAIL && next == LG_ST_CORR) {
@@ -284,8 +290,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         lane_store<LG_PART_ALL>(&slots[slot], &S);
       }
     }
-#pragma unroll
-    for (int s = 0; s < LGAR_NSTAGE; s++) wave_push(wv, append_mask, s, valid && next == s, slot);
+    wave_push(wv, append_mask, valid ? next : -1, bin, slot);
   }
   if (w.prof && (STAGE == LG_ST_FETCH || STAGE == LG_ST_HEAD || STAGE == LG_ST_TAIL)) {
     if (front_sum) atomicAdd(w.prof, front_sum);
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
 __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w,
                                                               const __grid_constant__ LgarWave wv, int consume, unsigned append_mask) {
   const unsigned FULL = 0xFFFFFFFFu;
-  const int n = wv.qcount[LG_ST_FETCH * 2 + consume];
+  const int n = wv.qcount[(LG_ST_FETCH * 2 + consume) * LGAR_NBIN];  // everything that goes to FETCH goes to its bin 0
   const int lane = threadIdx.x & 31;
   const int K = w.K;
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
         have = false;
       }
     }
-    wave_push(wv, append_mask, LG_ST_HEAD, next == LG_ST_HEAD, slot);
+    wave_push(wv, append_mask, next == LG_ST_HEAD ? LG_ST_HEAD : -1, wave_bin_fronts(nf), slot);
   }
   if (w.prof && front_sum) atomicAdd(w.prof, front_sum);
 }
@@ -397,7 +402,7 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
 __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int lane_stride, int use_ff) {
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
   int total = 0;
-  for (int q = 0; q < 2 * LGAR_NSTAGE; q++) total += wv.qcount[q];
+  for (int q = 0; q < 2 * LGAR_NSTAGE * LGAR_NBIN; q++) total += wv.qcount[q];
   unsigned long long front_sum = 0, active_sum = 0;
   unsigned long long* fsp = w.prof ? &front_sum : nullptr;
   // `lane_stride` > 1: only every lane_stride-th lane of a warp takes a slot.  The lanes of a warp sit in different
@@ -407,16 +412,8 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gtid % lane_stride != 0) return;
   for (int i = gtid / lane_stride; i < total; i += gridDim.x * blockDim.x / lane_stride) {
-    int j = i, slot = -1, stage = LG_ST_DONE;
-    for (int q = 0; q < 2 * LGAR_NSTAGE; q++) {  // item i of the concatenation of all queues
-      const int n = wv.qcount[q];
-      if (j < n) {
-        slot = wv.queue[q >> 1][q & 1][j];
-        stage = q >> 1;
-        break;
-      }
-      j -= n;
-    }
+    int stage = LG_ST_DONE;
+    const int slot = wave_item_any(wv, i, &stage);  // item i of the concatenation of all queues
     if (slot < 0) continue;
     LgLaneSlot S;
     lane_load<LG_PART_ALL>(&S, &slots[slot]);
@@ -459,7 +456,11 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
 // Queue counts to the host through mapped pinned memory: a cudaMemcpyAsync of these 48 bytes would queue behind whatever
 // bulk device-to-host copy (output series of the previous chunk of a streamed call) occupies the copy engine.
 __global__ void lgar_wave_poll_kernel(const int32_t* qcount, int32_t* host_counts) {
-  if (threadIdx.x < 2 * LGAR_NSTAGE) host_counts[threadIdx.x] = qcount[threadIdx.x];
+  if (threadIdx.x < 2 * LGAR_NSTAGE) {  // the host sees one count per queue: the sum over its bins
+    int n = 0;
+    for (int b = 0; b < LGAR_NBIN; b++) n += qcount[threadIdx.x * LGAR_NBIN + b];
+    host_counts[threadIdx.x] = n;
+  }
   __threadfence_system();
 }
 cudaError_t lgar_launch_wave_poll(const LgarWave& wv, int32_t* host_counts, cudaStream_t stream) {
@@ -468,7 +469,7 @@ cudaError_t lgar_launch_wave_poll(const LgarWave& wv, int32_t* host_counts, cuda
 }
 
 __global__ void lgar_wave_clear_kernel(LgarWave wv) {
-  if (threadIdx.x < 2 * LGAR_NSTAGE) wv.qcount[threadIdx.x] = 0;
+  if (threadIdx.x < 2 * LGAR_NSTAGE * LGAR_NBIN) wv.qcount[threadIdx.x] = 0;
 }
 
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
@@ -476,7 +477,7 @@ cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState
   lane_stride = std::max(1, std::min(lane_stride, 32));
   const int blocks = std::max(1, std::min((int)(((int64_t)in_flight * lane_stride + 127) / 128), sm_count * 16));
   lgar_wave_finish_kernel<<<blocks, 128, 0, stream>>>(cfg, d, w, wv, lane_stride, use_ff);
-  lgar_wave_clear_kernel<<<1, 32, 0, stream>>>(wv);
+  lgar_wave_clear_kernel<<<1, 64, 0, stream>>>(wv);
   return cudaGetLastError();
 }
 
@@ -498,14 +499,14 @@ __global__ void lgar_wave_init_kernel(const __grid_constant__ LgarConfig cfg, co
     if (slot_is_column) lg_lane_import(cfg, d, i, L);
     wv.queue[LG_ST_FETCH][0][i] = i;
   }
-  if (blockIdx.x == 0 && threadIdx.x < LGAR_NSTAGE * 2) wv.qcount[threadIdx.x] = (threadIdx.x == LG_ST_FETCH * 2) ? wv.nslots : 0;
+  if (blockIdx.x == 0 && threadIdx.x < LGAR_NSTAGE * 2 * LGAR_NBIN) wv.qcount[threadIdx.x] = (threadIdx.x == LG_ST_FETCH * 2 * LGAR_NBIN) ? wv.nslots : 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) *wv.done_columns = 0;
 }
 
 // reset the consumed queue's count (and the FETCH cursor) after its kernel ran
 __global__ void lgar_wave_reset_kernel(int32_t* count, int32_t* cursor) {
-  *count = 0;
-  if (cursor) *cursor = 0;
+  if (threadIdx.x < LGAR_NBIN) count[threadIdx.x] = 0;  // every bin of the consumed queue
+  if (cursor && threadIdx.x == 0) *cursor = 0;
 }
 
 cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWave& wv, int slot_is_column, cudaStream_t stream) {
@@ -539,7 +540,7 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
       break;
     default: lgar_wave_kernel<LG_ST_TAIL><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
   }
-  lgar_wave_reset_kernel<<<1, 1, 0, stream>>>(wv.qcount + stage * 2 + consume, refill ? wv.cursor : nullptr);
+  lgar_wave_reset_kernel<<<1, LGAR_NBIN, 0, stream>>>(wv.qcount + (stage * 2 + consume) * LGAR_NBIN, refill ? wv.cursor : nullptr);
   return cudaGetLastError();
 }
 

@@ -46,10 +46,15 @@ struct LgLane;
 #define LGAR_NSTAGE 6
 // stages of the resumable column program (lgar_lanes.cuh)
 enum { LG_ST_FETCH = 0, LG_ST_HEAD = 1, LG_ST_FRONT = 2, LG_ST_SEARCH = 3, LG_ST_TAIL = 4, LG_ST_CORR = 5, LG_ST_DONE = 6 };
+// Every queue is kept in LGAR_NBIN bins so that the lanes of a warp work on slots that look alike: HEAD / FRONT / TAIL slots are
+// binned by their front count (the per-front loops of those stages then have the same trip count across the warp), SEARCH slots
+// by the layer of the front they search for (a trip evaluates theta in that many layers).  A consumer walks the bins one after
+// the other, each bin starting at a multiple of 32 of its index space (no warp straddles two bins).
+#define LGAR_NBIN 4
 struct LgarWave {
   LgLane* ctx;                 // [nslots]
-  int32_t* queue[LGAR_NSTAGE][2];  // slot ids
-  int32_t* qcount;             // [LGAR_NSTAGE][2]
+  int32_t* queue[LGAR_NSTAGE][2];  // [LGAR_NBIN][nslots] slot ids
+  int32_t* qcount;             // [LGAR_NSTAGE][2][LGAR_NBIN]
   int32_t nslots;
   int32_t* done_columns;       // columns that finished their window
   int32_t* cursor;             // FETCH kernel: next queue entry to hand out (zero between launches)
