@@ -809,15 +809,18 @@ def main():
         b2.initialize(cfg, ncol, local_rank, column_soils(col0, ncol), column_layers(col0, ncol))
         b2.set_window_mode(args.mode)
         ext2 = torch.cuda.ExternalStream(b2.get_stream(), device=dev)
-        yms, T = 0.0, 8760
+        yms, T, chunk_rates = 0.0, 8760, []
         for t0 in range(0, T, args.chunk_hours):
             nt = min(args.chunk_hours, T - t0)
             dP, dE = forcing_torch(dids, t0, nt)
             torch.cuda.synchronize()
-            yms += timed_call(b2, ext2, nt, dP, dE, ncol)
+            cms = timed_call(b2, ext2, nt, dP, dE, ncol)
+            yms += cms
+            chunk_rates.append(ncol * nt / (cms * 1e-3))
             del dP, dE
         st2 = b2.get_status()
         full_year = {"value": ncol * T / (yms * 1e-3), "unit": "column-timesteps/s", "hours": T, "chunk_hours": args.chunk_hours, "device_seconds": yms * 1e-3,
+                     "by_chunk": chunk_rates,
                      "failed_columns": int(np.count_nonzero(st2 & lgar_c_b200.STATUS_FAIL_MASK)),
                      "note": "BASELINE config 5's one-year run for this GPU's 1.25 M columns from the initial state, one call per chunk of forcing"}
         by_call["8760"] = full_year["value"]

@@ -9,7 +9,10 @@
 namespace {
 
 // bins of the stage queues (LGAR_NBIN = 4): by front count, by the layer of the searched front
-__device__ __forceinline__ int wave_bin_fronts(int n) { return n <= 3 ? 0 : n == 4 ? 1 : n <= 6 ? 2 : 3; }
+__device__ __forceinline__ int wave_bin_fronts(int n) {
+  const int b = n <= 3 ? 0 : n == 4 ? 1 : n <= 6 ? 2 : 3;
+  return b < LGAR_NBIN ? b : LGAR_NBIN - 1;
+}
 __device__ __forceinline__ int wave_bin_layers(int l) { return l <= 1 ? 0 : l >= LGAR_NBIN ? LGAR_NBIN - 1 : l - 1; }
 
 // Append `slot` to bin `bin` of the queue of stage `next` (next outside [0, LGAR_NSTAGE): nothing to append).  One atomicAdd per

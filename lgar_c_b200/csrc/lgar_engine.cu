@@ -109,6 +109,17 @@ struct lgarb_engine {
   int wave_corr_async = 1;
   cudaStream_t side_stream = nullptr;
   cudaEvent_t side_ev[2] = {nullptr, nullptr};
+  // Forcing on its way (lgarb_update_steps_host): the series is copied in chunks on a stream of its own while the window runs;
+  // chunk k is complete when ev[k] is, and the window may then use the hours below upto[k].  Null: everything is present.
+  struct Frontier {
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> upto;
+    size_t next = 0;
+  };
+  Frontier* frontier = nullptr;
+  cudaStream_t h2d_stream = nullptr;
+  int host_chunk_hours = 24;   // lgarb_update_steps_host: hours per chunk of the forcing copy (0: copy everything first)
+  int64_t frontier_waits = 0;  // times the scheduler had to wait for forcing
   int wave_finish_below = 16384;
   // Rounds with at most this many slots in flight run their psi searches through the fast path (lgar_search.cuh).  0: never --
   // measured (profiles/r2_call5_summary.md): a round lasts as long as its longest search, and the fast path runs every search
@@ -124,7 +135,8 @@ struct lgarb_engine {
   unsigned long long* d_paths = nullptr;  // [LGAR_NPATH] path counters, allocated by lgarb_set_path_counters
   int finish_lane_stride = 4;  // finishing kernel: one slot per this many lanes
   int sm_count = 0;            // multiprocessors of the device: grids are sized in multiples of it
-  int update_wave_min_cols = 1 << 30;  // lgarb_update: batches of at least this many columns take the wavefront kernels
+  int update_wave_min_cols = 1 << 30;  // lgarb_update: batches of at least this many columns hand their active columns to the stage kernels
+  int update_wave_slots = 262144;      // ... through this many slots
   int wave_windows = 0;  // windows run so far (profiling range selection)
   int wave_escalate_below = 8192;
   int wave_corr_quantum = 64;  // correction-search trips per launch (scaled with the psi-search quantum when that escalates)
@@ -205,6 +217,8 @@ struct lgarb_engine {
     }
     if (side_stream) cudaStreamDestroy(side_stream);
     side_stream = nullptr;
+    if (h2d_stream) cudaStreamDestroy(h2d_stream);
+    h2d_stream = nullptr;
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
     initialized = false;
@@ -831,6 +845,10 @@ struct LgarbDeviceGuard {
 
 extern "C" {
 
+namespace {
+void run_wave_window(lgarb_engine* e, LgarWindow w, int use_slots);  // one window through the stage kernels (defined below)
+}
+
 int lgarb_create(lgarb_engine** out) {
   if (!out) return LGARB_FAILURE;
   *out = new (std::nothrow) lgarb_engine();
@@ -852,6 +870,8 @@ int lgarb_create(lgarb_engine** out) {
   knob("LGARB_FINISH_QUANTUM", (*out)->finish_quantum);
   knob("LGARB_FINISH_LANE_STRIDE", (*out)->finish_lane_stride);
   knob("LGARB_UPDATE_WAVE_MIN_COLS", (*out)->update_wave_min_cols);
+  knob("LGARB_UPDATE_WAVE_SLOTS", (*out)->update_wave_slots);
+  knob("LGARB_HOST_CHUNK_HOURS", (*out)->host_chunk_hours);
   knob("LGARB_WAVE_ESCALATE_BELOW", (*out)->wave_escalate_below);
   knob("LGARB_WAVE_CORR_QUANTUM", (*out)->wave_corr_quantum);
   knob("LGARB_WINDOW_MODE", (*out)->use_window);
@@ -892,10 +912,33 @@ int lgarb_update(lgarb_engine* e) {
     apply_calibration(e);
     update_frozen_factors(e);
     if (e->use_window >= 3 && e->ncol >= e->update_wave_min_cols) {
-      // Large batch: one forcing hour as a window of one step through the wavefront kernels.  The kernel pair below
-      // makes every active column of the hour wait for the slowest psi search in its warp; the stage kernels do not.
-      if (lgarb_update_steps_device(e, 1, e->d_precip, e->d_pet, e->stride, nullptr, e->stride, nullptr) != LGARB_SUCCESS)
-        throw std::runtime_error(e->last_error);
+      // Large batch: the stream kernel finishes the columns that replay cached fluxes (84 % of the column-steps of the bench
+      // workload) from their scalars and lists the others; the listed columns then take the stage kernels as a window of one
+      // hour -- slots import a column of the list, run its step through HEAD / FRONT / SEARCH / TAIL and export it.  The
+      // active kernel of the pair below makes every listed column wait for the slowest psi search of its warp; the stage
+      // kernels do not.  (A window of one hour over ALL columns was measured in round 1: the import/export of every column costs
+      // more than it saves.)
+      LgarDeviceState d = e->d;
+      d.precip = e->d_precip;
+      d.pet = e->d_pet;
+      d.paths = e->d_paths;
+      LgarSinks sinks;
+      memset(&sinks, 0, sizeof(sinks));
+      CUDA_TRY(lgar_launch_step_stream(e->cfg, d, sinks, e->force_all_active, e->stream));
+      e->launches += 1;
+      LgarWindow w;
+      memset(&w, 0, sizeof(w));
+      w.precip = e->d_precip;
+      w.pet = e->d_pet;
+      w.series_stride = e->stride;
+      w.sink_stride = e->stride;
+      w.K = 1;
+      w.force_all_active = e->force_all_active;
+      w.col_list = e->d.work;
+      w.col_count = e->d.work_count;
+      run_wave_window(e, w, e->update_wave_slots);
+      e->steps++;
+      e->time_s += e->cfg.forcing_resolution_h * 3600.0;
     } else {
       LgarSinks sinks;
       memset(&sinks, 0, sizeof(sinks));
@@ -930,6 +973,7 @@ void ensure_wave(lgarb_engine* e) {
     wv.qcount = e->dalloc<int32_t>(LGAR_NSTAGE * 2 * LGAR_NBIN);
     wv.done_columns = e->dalloc<int32_t>(1);
     wv.cursor = e->dalloc<int32_t>(1);
+    wv.waiting = e->dalloc<int32_t>(1);
     if (!e->side_stream) {
       CUDA_TRY(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
       for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->side_ev[i], cudaEventDisableTiming));
@@ -946,14 +990,36 @@ void ensure_wave(lgarb_engine* e) {
 }
 
 // one window of K hours through the wavefront kernels
-void run_wave_window(lgarb_engine* e, LgarWindow w) {
+// use_slots > 0: that many slots draw their columns from w.col_list (or 0 .. ncol - 1) instead of slot i owning column i
+void run_wave_window(lgarb_engine* e, LgarWindow w, int use_slots) {
   ensure_wave(e);
-  const LgarWave& wv = e->wave;
+  LgarWave wv = e->wave;
+  if (use_slots > 0) wv.nslots = std::min(wv.nslots, use_slots);
   w.tile_counter = e->d_tile_counter;
   w.done_columns = wv.done_columns;
   w.paths = e->d_paths;
   CUDA_TRY(cudaMemsetAsync(e->d_tile_counter, 0, sizeof(int32_t), e->stream));
-  w.slot_is_column = (wv.nslots == e->ncol) ? 1 : 0;
+  w.slot_is_column = (use_slots <= 0 && wv.nslots == e->ncol) ? 1 : 0;
+  w.waiting = wv.waiting;
+  lgarb_engine::Frontier* fr = e->frontier;
+  int hours_present = fr ? 0 : w.K;
+  // raise the frontier to what has arrived; `block`: wait for the next chunk first (nothing can move without it)
+  auto advance_frontier = [&](bool block) {
+    if (!fr) return;
+    if (block && fr->next < fr->ev.size()) {
+      CUDA_TRY(cudaEventSynchronize(fr->ev[fr->next]));
+      e->frontier_waits++;
+    }
+    while (fr->next < fr->ev.size()) {
+      const cudaError_t q = cudaEventQuery(fr->ev[fr->next]);
+      if (q == cudaErrorNotReady) break;
+      CUDA_TRY(q);
+      hours_present = fr->upto[fr->next++];
+    }
+    if (fr->next == fr->ev.size()) hours_present = w.K;
+    w.frontier1 = hours_present >= w.K ? 0 : hours_present + 1;
+  };
+  advance_frontier(true);  // the first chunk: nothing to do before it is there
   CUDA_TRY(lgar_launch_wave_init(e->cfg, e->d, wv, w.slot_is_column, e->stream));
   e->launches += 1;
   int par[LGAR_NSTAGE] = {0, 0, 0, 0, 0, 0};
@@ -1027,7 +1093,9 @@ void run_wave_window(lgarb_engine* e, LgarWindow w) {
         in_flight += cnt[s];
       }
       if (in_flight == 0) break;
-      if (in_flight <= e->wave_finish_below) {  // the stragglers: one thread per slot runs its column to the end of the window
+      // every slot in flight is waiting for forcing: block until the next chunk is there
+      advance_frontier(hours_present < w.K && h_cnt[2 * LGAR_NSTAGE] >= in_flight);
+      if (in_flight <= e->wave_finish_below && hours_present >= w.K) {  // the stragglers: one thread per slot runs its column to the end of the window
         if (debug) cudaEventRecord(dbg[0], e->stream);
         w.use_ff = e->finish_ff;
         lgarb_engine::StageEv se{nullptr, nullptr, LGAR_NSTAGE};
@@ -1178,7 +1246,7 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
           CUDA_TRY(cudaEventRecord(e->win_ev[0], e->stream));
         }
         if (e->use_window >= 3)
-          run_wave_window(e, w);
+          run_wave_window(e, w, 0);
         else
           CUDA_TRY(lgar_launch_window(e->cfg, e->d, w, e->window_blocks, e->stream, e->use_window));
         if (e->profiling) {
@@ -1215,8 +1283,38 @@ int lgarb_update_steps_host(lgarb_engine* e, int64_t n_steps, const double* h_pr
     }
     double* dP = e->d_host_series;
     double* dE = dP + n;
-    CUDA_TRY(cudaMemcpyAsync(dP, h_precip, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(cudaMemcpyAsync(dE, h_pet, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    // The forcing travels in chunks of host_chunk_hours on a stream of its own while the window already runs on what has arrived
+    // (the wavefront scheduler walks a column no further than the frontier, run_wave_window): the copy of all but the first
+    // chunk hides behind the computation.  Hour-by-hour and single-window-kernel modes copy everything first.
+    lgarb_engine::Frontier fr;
+    struct FrontierGuard {
+      lgarb_engine* e;
+      lgarb_engine::Frontier* f;
+      ~FrontierGuard() {
+        e->frontier = nullptr;
+        for (cudaEvent_t x : f->ev) cudaEventDestroy(x);
+      }
+    } frontier_guard{e, &fr};
+    const int64_t ch = e->host_chunk_hours;
+    if (e->use_window == 3 && ch > 0 && n_steps > ch && n_steps <= LGAR_MAX_WINDOW) {
+      CUDA_TRY(cudaStreamSynchronize(e->stream));  // the staging buffers may still be read by what the caller enqueued before
+      if (!e->h2d_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
+      for (int64_t t0 = 0; t0 < n_steps; t0 += ch) {
+        const int64_t t1 = std::min(n_steps, t0 + ch);
+        const size_t off = (size_t)t0 * (size_t)e->ncol, cnt = (size_t)(t1 - t0) * (size_t)e->ncol;
+        CUDA_TRY(cudaMemcpyAsync(dP + off, h_precip + off, cnt * sizeof(double), cudaMemcpyHostToDevice, e->h2d_stream));
+        CUDA_TRY(cudaMemcpyAsync(dE + off, h_pet + off, cnt * sizeof(double), cudaMemcpyHostToDevice, e->h2d_stream));
+        cudaEvent_t ev;
+        CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        fr.ev.push_back(ev);
+        fr.upto.push_back((int)t1);
+        CUDA_TRY(cudaEventRecord(ev, e->h2d_stream));
+      }
+      e->frontier = &fr;
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(dP, h_precip, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(cudaMemcpyAsync(dE, h_pet, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    }
     double* sinks[LGAR_NOUT];
     for (int k = 0; k < LGAR_NOUT; k++) sinks[k] = nullptr;
     for (int i = 0; i < n_outputs; i++) {

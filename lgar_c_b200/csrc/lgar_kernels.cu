@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
   const unsigned FULL = 0xFFFFFFFFu;
   const int n = wv.qcount[(LG_ST_FETCH * 2 + consume) * LGAR_NBIN];  // everything that goes to FETCH goes to its bin 0
   const int lane = threadIdx.x & 31;
-  const int K = w.K;
+  const int K = w.K, Kp = lg_hours_present(w);  // end of the window, end of the forcing that has arrived
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
   unsigned long long front_sum = 0;
   unsigned long long* fsp = w.prof ? &front_sum : nullptr;
@@ -338,8 +338,8 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
           s = G.s;
           ep = G.ep;
           have = true;
-          if (t < K && G.cls->invalid_soil_type) t = lg_advance_resident(cfg, d, w, G.cls, col, t, nf, s, ep, fsp);  // Q = precip: no walk
-          if (t < K) {
+          if (t < Kp && G.cls->invalid_soil_type) t = lg_advance_resident(cfg, d, w, G.cls, col, t, nf, s, ep, fsp);  // Q = precip: no walk
+          if (t < Kp) {
             Pn = w.precip[(int64_t)t * w.series_stride + col];
             En = w.pet[(int64_t)t * w.series_stride + col];
           }
@@ -349,16 +349,16 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
     if (!__any_sync(FULL, have)) break;
     int next = -1;
     if (have) {
-      bool ended = t >= K;
+      bool ended = t >= Kp;
       if (!ended) {
         const double P = Pn, E = En;
-        if (t + 1 < K) {
+        if (t + 1 < Kp) {
           Pn = w.precip[(int64_t)(t + 1) * w.series_stride + col];
           En = w.pet[(int64_t)(t + 1) * w.series_stride + col];
         }
         if (lg_resident_hour(cfg, d, w, col, t, nf, s, ep, fsp, P, E)) {
           t++;
-          ended = t >= K;
+          ended = t >= Kp;
         } else {
           ended = true;
         }
@@ -368,9 +368,13 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
         G.s = s;
         G.ep = ep;
         G.t = t;
-        if (t < K) {
+        if (t < Kp) {
           G.stage = LG_ST_HEAD;
           next = LG_ST_HEAD;
+        } else if (t < K) {  // the forcing of hour t has not arrived yet: wait in the FETCH queue
+          if (w.waiting) atomicAdd(w.waiting, 1);
+          G.stage = LG_ST_FETCH;
+          next = LG_ST_FETCH;
         } else {  // this column has finished the window (lg_stage_fetch, slot == column)
           lg_lane_export(cfg, d, col, G);
           if (w.done_columns) atomicAdd(w.done_columns, 1);
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
         have = false;
       }
     }
-    wave_push(wv, append_mask, next == LG_ST_HEAD ? LG_ST_HEAD : -1, wave_bin_fronts(nf), slot);
+    wave_push(wv, append_mask, (next == LG_ST_HEAD || next == LG_ST_FETCH) ? next : -1, next == LG_ST_HEAD ? wave_bin_fronts(nf) : 0, slot);
   }
   if (w.prof && front_sum) atomicAdd(w.prof, front_sum);
 }
@@ -455,16 +459,20 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
 
 // Queue counts to the host through mapped pinned memory: a cudaMemcpyAsync of these 48 bytes would queue behind whatever
 // bulk device-to-host copy (output series of the previous chunk of a streamed call) occupies the copy engine.
-__global__ void lgar_wave_poll_kernel(const int32_t* qcount, int32_t* host_counts) {
+__global__ void lgar_wave_poll_kernel(const int32_t* qcount, int32_t* waiting, int32_t* host_counts) {
   if (threadIdx.x < 2 * LGAR_NSTAGE) {  // the host sees one count per queue: the sum over its bins
     int n = 0;
     for (int b = 0; b < LGAR_NBIN; b++) n += qcount[threadIdx.x * LGAR_NBIN + b];
     host_counts[threadIdx.x] = n;
   }
+  if (threadIdx.x == 2 * LGAR_NSTAGE) {  // slots left waiting for forcing since the last poll
+    host_counts[threadIdx.x] = *waiting;
+    *waiting = 0;
+  }
   __threadfence_system();
 }
 cudaError_t lgar_launch_wave_poll(const LgarWave& wv, int32_t* host_counts, cudaStream_t stream) {
-  lgar_wave_poll_kernel<<<1, 32, 0, stream>>>(wv.qcount, host_counts);
+  lgar_wave_poll_kernel<<<1, 32, 0, stream>>>(wv.qcount, wv.waiting, host_counts);
   return cudaGetLastError();
 }
 
@@ -500,7 +508,10 @@ __global__ void lgar_wave_init_kernel(const __grid_constant__ LgarConfig cfg, co
     wv.queue[LG_ST_FETCH][0][i] = i;
   }
   if (blockIdx.x == 0 && threadIdx.x < LGAR_NSTAGE * 2 * LGAR_NBIN) wv.qcount[threadIdx.x] = (threadIdx.x == LG_ST_FETCH * 2 * LGAR_NBIN) ? wv.nslots : 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *wv.done_columns = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *wv.done_columns = 0;
+    *wv.waiting = 0;
+  }
 }
 
 // reset the consumed queue's count (and the FETCH cursor) after its kernel ran
@@ -645,6 +656,13 @@ __global__ void lgar_gather_layers_kernel(LgarDeviceState d, double* dst, int64_
 }
 
 // ---- launch wrappers ------------------------------------------------------------------------------
+cudaError_t lgar_launch_step_stream(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int force_all_active, cudaStream_t stream) {
+  cudaError_t err = cudaMemsetAsync(d.work_count, 0, 2 * sizeof(int32_t), stream);
+  if (err != cudaSuccess) return err;
+  lgar_step_stream_kernel<<<(unsigned)((d.ncol + 255) / 256), 256, 0, stream>>>(cfg, d, sinks, force_all_active);
+  return cudaGetLastError();
+}
+
 cudaError_t lgar_launch_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int active_blocks,
                              int force_all_active, cudaStream_t stream, cudaEvent_t* ev) {
   cudaError_t err = cudaMemsetAsync(d.work_count, 0, 2 * sizeof(int32_t), stream);

@@ -30,6 +30,15 @@ struct LgarWindow {
   int32_t* tile_counter;  // device, zeroed before launch (tile counter / column counter)
   unsigned long long* prof;  // nullable: [0] += sum of front counts, [1] += active column-steps
   int slot_is_column;     // wavefront: slot i owns column i for the whole window (no column counter)
+  // wavefront without slot_is_column: slots draw the entries 0 .. *col_count - 1 of col_list from the counter (null: the columns
+  // 0 .. ncol - 1) -- the hour-by-hour Update() hands the work list of lgar_step_stream_kernel to the stage kernels this way
+  const int32_t* col_list;
+  const int32_t* col_count;
+  // Forcing that is still on its way (lgarb_update_steps_host copies the series in chunks while the window runs): 0 = the whole
+  // window is present, otherwise hours present so far + 1.  FETCH walks a column no further than that; a slot that gets there
+  // waits in the FETCH queue (wave scheduler only).
+  int frontier1;
+  int32_t* waiting;       // nullable: += 1 for every slot FETCH left waiting at the frontier
   int32_t* done_columns;  // nullable: += 1 whenever a column finishes its window (wavefront scheduler)
   unsigned int* work_trace;  // nullable: [2][stride] per column: psi-search trips, kilo-cycles in the non-search stages (lanes kernel)
   int64_t trace_stride;
@@ -50,7 +59,9 @@ enum { LG_ST_FETCH = 0, LG_ST_HEAD = 1, LG_ST_FRONT = 2, LG_ST_SEARCH = 3, LG_ST
 // binned by their front count (the per-front loops of those stages then have the same trip count across the warp), SEARCH slots
 // by the layer of the front they search for (a trip evaluates theta in that many layers).  A consumer walks the bins one after
 // the other, each bin starting at a multiple of 32 of its index space (no warp straddles two bins).
+#ifndef LGAR_NBIN
 #define LGAR_NBIN 4
+#endif
 struct LgarWave {
   LgLane* ctx;                 // [nslots]
   int32_t* queue[LGAR_NSTAGE][2];  // [LGAR_NBIN][nslots] slot ids
@@ -58,6 +69,7 @@ struct LgarWave {
   int32_t nslots;
   int32_t* done_columns;       // columns that finished their window
   int32_t* cursor;             // FETCH kernel: next queue entry to hand out (zero between launches)
+  int32_t* waiting;            // slots FETCH left waiting for forcing since the last poll (the poll reads and clears it)
 };
 
 #ifndef LGAR_HOSTSIM
@@ -80,6 +92,8 @@ size_t lgar_lane_context_bytes();
 cudaError_t lgar_launch_window(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, int blocks, cudaStream_t stream, int mode);
 int lgar_window_kernel_max_blocks_per_sm();
 
+// the first kernel of that pair alone: cached-flux columns are finished, the others are listed in d.work / d.work_count[0]
+cudaError_t lgar_launch_step_stream(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int force_all_active, cudaStream_t stream);
 // ev (nullable): three events recorded before the stream kernel, between the kernels, after the active kernel
 cudaError_t lgar_launch_step(const LgarConfig& cfg, const LgarDeviceState& d, const LgarSinks& sinks, int active_blocks,
                              int force_all_active, cudaStream_t stream, cudaEvent_t* ev);

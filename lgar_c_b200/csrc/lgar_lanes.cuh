@@ -737,14 +737,15 @@ LG_FN_NOINLINE void lg_stage_fetch(const LgarConfig& cfg, const LgarDeviceState&
         return;
       }
 #ifdef LGAR_HOSTSIM
-      const int64_t col = (*w.tile_counter)++;
+      const int64_t idx = (*w.tile_counter)++;
 #else
-      const int64_t col = atomicAdd(w.tile_counter, 1);
+      const int64_t idx = atomicAdd(w.tile_counter, 1);
 #endif
-      if (col >= d.ncol) {
+      if (idx >= (w.col_list ? (int64_t)*w.col_count : d.ncol)) {
         L.stage = LG_ST_DONE;
         return;
       }
+      const int64_t col = w.col_list ? (int64_t)w.col_list[idx] : idx;
       L.col = col;
       L.t = 0;
       L.tr_iters = 0;
@@ -757,8 +758,15 @@ LG_FN_NOINLINE void lg_stage_fetch(const LgarConfig& cfg, const LgarDeviceState&
     L.s = s;
     L.ep = ep;
     L.t = t1;
-    if (t1 < w.K) {
+    if (t1 < lg_hours_present(w)) {
       L.stage = LG_ST_HEAD;
+      return;
+    }
+    if (t1 < w.K) {  // the forcing of hour t1 has not arrived yet: wait in the FETCH queue
+#ifndef LGAR_HOSTSIM
+      if (w.waiting) atomicAdd(w.waiting, 1);
+#endif
+      L.stage = LG_ST_FETCH;
       return;
     }
   }

@@ -448,9 +448,11 @@ LG_FN bool lg_resident_hour(const LgarConfig& cfg, const LgarDeviceState& d, con
 
 // The same walk for a column whose scalars, GIUH queue and cumulative volumes are resident in its lane
 // record (lgar_lanes.cuh): nothing is read from or written to the SoA state.
+// forcing hours of the window that are present (LgarWindow::frontier1)
+LG_FN int lg_hours_present(const LgarWindow& w) { return w.frontier1 > 0 ? w.frontier1 - 1 : w.K; }
 LG_FN int lg_advance_resident(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarColumnClass* cls, int64_t col, int t,
                               int nf, LgScalars& s, LgEpi& ep, unsigned long long* front_sum) {
-  const int K = w.K;
+  const int K = lg_hours_present(w);  // the walk ends where the forcing ends
   if (cls->invalid_soil_type) {  // Q = precip (bmi_lgar.cxx:145-179); cumulative volumes as step_invalid()
     for (; t < K; t++) {
       const double P = w.precip[(int64_t)t * w.series_stride + col];
@@ -459,7 +461,7 @@ LG_FN int lg_advance_resident(const LgarConfig& cfg, const LgarDeviceState& d, c
 #pragma unroll
       for (int k = 0; k < LGAR_NOUT; k++) {
         const double val = (k == LGAR_OUT_PRECIP || k == LGAR_OUT_RUNOFF || k == LGAR_OUT_Q) ? pm : 0.0;
-        if (t == K - 1) d.out[k * d.stride + col] = val;
+        if (t == w.K - 1) d.out[k * d.stride + col] = val;
         if (w.sinks.p[k]) w.sinks.p[k][so] = val;
       }
       ep.cum[LGAR_CUM_PRECIP] += P * 0.1;

@@ -95,7 +95,7 @@ def test_list_functions_on_the_snapshot(snapshot):
             arr[i].K, arr[i].dzdt = fr["K"][c][i], fr["dzdt"][c][i]
             arr[i].layer, arr[i].to_bottom = int(fr["layer"][c][i]), int(fr["to_bottom"][c][i])
         want_mb[c] = L.lgo_calc_mass_bal(p.cum_thickness, arr, n)
-        want_aet[c] = L.lgo_calc_aet(pet[c], dt[c], p.wilting_point_psi_cm, p.field_capacity_psi_cm, arr, p.soil)
+        want_aet[c] = L.lgo_calc_aet(pet[c], dt[c], p.wilting_point_psi_cm, p.field_capacity_psi_cm, arr, C.byref(p.soil[int(arr[0].layer)]))  # the soil of the head front's layer
     _assert_bit_equal(b.debug_functions(5, pet), want_mb, "lgar_calc_mass_bal")
     _assert_bit_equal(b.debug_functions(6, pet, dt), want_aet, "calc_aet")
 

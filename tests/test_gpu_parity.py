@@ -213,8 +213,14 @@ def test_streamed_host_call_equals_single_call(cuda_device, tmp_path):
     Em = np.ascontiguousarray(np.stack([np.roll(g["pet"], -int(s))[:T] for s in shifts], axis=1))
     names = ["total_discharge", "soil_storage", "infiltration"]
 
-    def run(P, E, chunk=None, out_dtype=np.float64):
-        b = lgar_c_b200.BmiLGARBatch()
+    def run(P, E, chunk=None, out_dtype=np.float64, env=None):
+        import os
+        os.environ.update(env or {})
+        try:
+            b = lgar_c_b200.BmiLGARBatch()
+        finally:
+            for k in (env or {}):
+                del os.environ[k]
         b.initialize(cfg, ncol)
         if chunk is None:
             out = b.update_steps_host(P, E, names)
@@ -225,6 +231,13 @@ def test_streamed_host_call_equals_single_call(cuda_device, tmp_path):
         return out, fr
 
     ref, fr_ref = run(Pm, Em)
+    # the single call copies its forcing in chunks while the window runs (frontier of arrived hours): everything first, 7 h at a time
+    for hours in ("0", "7", "529"):
+        out, fr = run(Pm, Em, env={"LGARB_HOST_CHUNK_HOURS": hours})
+        for n in names:
+            assert np.array_equal(out[n], ref[n]), (hours, n)
+        for k in ("depth", "theta", "psi", "nfronts"):
+            assert np.array_equal(fr[k], fr_ref[k], equal_nan=True), (hours, k)
     for chunk in (0, 530, 200, 64):
         out, fr = run(Pm, Em, chunk)
         for n in names:
@@ -383,3 +396,46 @@ def test_invalid_soil_columns_pass_precip_through(cuda_device, tmp_path):
     assert q[1] == r[1] == 3.0 * 0.001 and i[1] == 0.0
     assert i[0] == i[2] and i[0] > 0.0
     assert list(b.get_value("soil_num_wetting_fronts")) == [4, 0, 4]
+
+
+def test_hourly_update_through_stage_kernels(cuda_device, tmp_path):
+    """The BMI single-step verb on a large batch (LGARB_UPDATE_WAVE_MIN_COLS: the stream kernel finishes the cached-flux columns
+    and lists the others, the listed columns take the stage kernels as a window of one hour, slots drawing columns from the
+    list) against the stream/active kernel pair: SetValue x2 -> Update -> GetValue per hour, every output of every hour, the
+    final fronts and the global balance bit-identical -- also with fewer slots than listed columns (slots take a second column)."""
+    import os
+    import bench
+    import lgar_c_b200
+    ncol, T = 20_000, 120
+    cfg = bench.write_workload_config(tmp_path)
+    soils, layers = bench.column_soils(0, ncol), bench.column_layers(0, ncol)
+    P, E = bench.host_forcing(ncol, 0, T, 2026)
+    P[30:34] = np.maximum(P[30:34], 6.0)     # a storm on every column: every column listed at once
+    res = []
+    for env in ({}, {"LGARB_UPDATE_WAVE_MIN_COLS": "0"}, {"LGARB_UPDATE_WAVE_MIN_COLS": "0", "LGARB_UPDATE_WAVE_SLOTS": "4096"}):
+        os.environ.update(env)
+        try:
+            b = lgar_c_b200.BmiLGARBatch()
+        finally:
+            for k in env:
+                del os.environ[k]
+        b.initialize(cfg, ncol, 0, soils, layers)
+        out = np.empty((T, len(lgar_c_b200.OUTPUT_SCALARS), ncol))
+        nf = np.empty((T, ncol), dtype=np.int32)
+        for t in range(T):
+            b.set_value("precipitation_rate", P[t])
+            b.set_value("potential_evapotranspiration_rate", E[t])
+            b.update()
+            for k, name in enumerate(lgar_c_b200.OUTPUT_SCALARS):
+                out[t, k] = b.get_value(name)
+            nf[t] = b.get_value("soil_num_wetting_fronts")
+        res.append((out, nf, b.get_status(), b.get_fronts(), b.get_global_mass_balance(), b.get_current_time(), b.get_launch_count()))
+        del b
+    o0, n0, s0, f0, m0, t0, l0 = res[0]
+    assert (s0 & lgar_c_b200.STATUS_FAIL_MASK == 0).all()
+    for (o1, n1, s1, f1, m1, t1, l1) in res[1:]:
+        assert l1 > l0, "the stage kernels did not run"
+        assert t1 == t0 and np.array_equal(s0, s1) and np.array_equal(n0, n1)
+        assert np.array_equal(o0, o1, equal_nan=True) and np.array_equal(m0, m1, equal_nan=True)
+        for k in ("depth", "theta", "psi", "K", "dzdt", "layer", "to_bottom", "nfronts"):
+            assert np.array_equal(f0[k], f1[k], equal_nan=True), k
