@@ -8,10 +8,15 @@
 
 namespace {
 
-// bins of the stage queues (LGAR_NBIN = 4): by front count, by the layer of the searched front
-__device__ __forceinline__ int wave_bin_fronts(int n) {
-  const int b = n <= 3 ? 0 : n == 4 ? 1 : n <= 6 ? 2 : 3;
-  return b < LGAR_NBIN ? b : LGAR_NBIN - 1;
+// bins of the stage queues: by front count (and a flag), by the layer of the searched front
+__device__ __forceinline__ int wave_bin_fronts(int n, bool flag = false) {
+#if LGAR_NBIN_N >= 6
+  int b = n <= 2 ? 0 : n == 3 ? 1 : n == 4 ? 2 : n == 5 ? 3 : n <= 7 ? 4 : 5;
+#else
+  int b = n <= 3 ? 0 : n == 4 ? 1 : n <= 6 ? 2 : 3;
+#endif
+  if (b >= LGAR_NBIN_N) b = LGAR_NBIN_N - 1;
+  return (LGAR_NBIN_FLAG > 1 && flag) ? b + LGAR_NBIN_N : b;
 }
 __device__ __forceinline__ int wave_bin_layers(int l) { return l <= 1 ? 0 : l >= LGAR_NBIN ? LGAR_NBIN - 1 : l - 1; }
 

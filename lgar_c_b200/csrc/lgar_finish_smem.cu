@@ -154,6 +154,6 @@ cudaError_t lgar_launch_wave_finish_smem(const LgarConfig& cfg, const LgarDevice
     lgar_wave_finish_smem_kernel<true><<<blocks, 32, bytes, stream>>>(cfg, d, w, wv, 32 / spw, quantum);
   else
     lgar_wave_finish_smem_kernel<false><<<blocks, 32, bytes, stream>>>(cfg, d, w, wv, 32 / spw, quantum);
-  lgar_wave_xclear_kernel<<<1, 64, 0, stream>>>(wv);
+  lgar_wave_xclear_kernel<<<1, 256, 0, stream>>>(wv);
   return cudaGetLastError();
 }

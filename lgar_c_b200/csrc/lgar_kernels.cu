@@ -214,14 +214,14 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
 #pragma unroll
         for (int a = 1; a < 3; a++) ctx_store_n(g + kPitch * a, l + kPitch * a, cf);
         next = k.done ? LG_ST_TAIL : LG_ST_CORR;
-        bin = k.done ? wave_bin_fronts(fb.f.n) : 0;
+        bin = k.done ? wave_bin_fronts(fb.f.n, G.create) : 0;
       }
     } else if (STAGE == LG_ST_FETCH) {
       if (valid) {  // works on the record in place: scalars and epilogue state through registers, nothing else is touched
         LgLane& G = slots[slot].L;
         lg_stage_fetch(cfg, d, w, G, fsp);
         next = G.stage;
-        bin = wave_bin_fronts(G.f.n);
+        bin = wave_bin_fronts(G.f.n, next == LG_ST_HEAD && w.precip[(int64_t)G.t * w.series_stride + G.col] > 0.0);
       }
     } else if (((LGAR_INPLACE_MASK >> STAGE) & 1) != 0) {
       // The stage works on the record where it lies in HBM (through L1/L2) instead of on a thread-private copy.  The
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
             lg_stage_tail(cfg, d, w, G, fsp);
         }
         next = G.stage;
-        bin = next == LG_ST_SEARCH ? wave_bin_layers(G.q.layer_num) : (next == LG_ST_CORR || next == LG_ST_FETCH) ? 0 : wave_bin_fronts(G.f.n);
+        bin = next == LG_ST_SEARCH ? wave_bin_layers(G.q.layer_num) : (next == LG_ST_CORR || next == LG_ST_FETCH) ? 0 : wave_bin_fronts(G.f.n, next == LG_ST_TAIL && G.create);
         G.nf_stored = G.f.n;      // what a later stage that copies the record has to move
         if (STAGE != LG_ST_TAIL) G.nold_stored = G.old.n;
       }
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
           lg_stage_tail(cfg, d, w, L, fsp);
       }
       next = L.stage;
-      bin = next == LG_ST_SEARCH ? wave_bin_layers(L.q.layer_num) : (next == LG_ST_CORR || next == LG_ST_FETCH) ? 0 : wave_bin_fronts(L.f.n);
+      bin = next == LG_ST_SEARCH ? wave_bin_layers(L.q.layer_num) : (next == LG_ST_CORR || next == LG_ST_FETCH) ? 0 : wave_bin_fronts(L.f.n, next == LG_ST_TAIL && L.create);
       if (next == LG_ST_FETCH) {
         lane_store<LG_PART_STATE>(&slots[slot], &S);  // the step is over: only the column state lives on
       } else if (STAGE == LG_ST_TAIL && next == LG_ST_CORR) {
@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
   LgScalars s;
   LgEpi ep;
   double Pn = 0.0, En = 0.0;  // forcing of hour t, requested one hour ahead
+  bool rain = false;          // it rains in the hour the slot stopped at (bin of the HEAD queue)
   for (;;) {
     if (!exhausted) {
       const unsigned need = __ballot_sync(FULL, !have);
@@ -352,6 +353,7 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
       bool ended = t >= Kp;
       if (!ended) {
         const double P = Pn, E = En;
+        rain = P > 0.0;
         if (t + 1 < Kp) {
           Pn = w.precip[(int64_t)(t + 1) * w.series_stride + col];
           En = w.pet[(int64_t)(t + 1) * w.series_stride + col];
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
         have = false;
       }
     }
-    wave_push(wv, append_mask, (next == LG_ST_HEAD || next == LG_ST_FETCH) ? next : -1, next == LG_ST_HEAD ? wave_bin_fronts(nf) : 0, slot);
+    wave_push(wv, append_mask, (next == LG_ST_HEAD || next == LG_ST_FETCH) ? next : -1, next == LG_ST_HEAD ? wave_bin_fronts(nf, rain) : 0, slot);
   }
   if (w.prof && front_sum) atomicAdd(w.prof, front_sum);
 }
@@ -485,7 +487,7 @@ cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState
   lane_stride = std::max(1, std::min(lane_stride, 32));
   const int blocks = std::max(1, std::min((int)(((int64_t)in_flight * lane_stride + 127) / 128), sm_count * 16));
   lgar_wave_finish_kernel<<<blocks, 128, 0, stream>>>(cfg, d, w, wv, lane_stride, use_ff);
-  lgar_wave_clear_kernel<<<1, 64, 0, stream>>>(wv);
+  lgar_wave_clear_kernel<<<1, 256, 0, stream>>>(wv);
   return cudaGetLastError();
 }
 
