@@ -9,15 +9,17 @@
 namespace {
 
 // bins of the stage queues: by front count (and a flag), by the layer of the searched front
-__device__ __forceinline__ int wave_bin_fronts(int n, bool flag = false) {
+__device__ __forceinline__ int wave_bin_fronts(int n, int flags = 0) {
 #if LGAR_NBIN_N >= 6
   int b = n <= 2 ? 0 : n == 3 ? 1 : n == 4 ? 2 : n == 5 ? 3 : n <= 7 ? 4 : 5;
 #else
   int b = n <= 3 ? 0 : n == 4 ? 1 : n <= 6 ? 2 : 3;
 #endif
   if (b >= LGAR_NBIN_N) b = LGAR_NBIN_N - 1;
-  return (LGAR_NBIN_FLAG > 1 && flag) ? b + LGAR_NBIN_N : b;
+  return b + LGAR_NBIN_N * (flags & (LGAR_NBIN_FLAG - 1));   // LGAR_NBIN_FLAG is 1, 2 or 4
 }
+// flags of a slot on its way to TAIL: bit 0 the step creates a surficial front, bit 1 the front list needs a correction
+__device__ __forceinline__ int wave_tail_flags(const LgLane& L) { return (L.create ? 1 : 0) | ((L.me_phase == 1 || L.me_phase == 2) && L.me_correction != 0 ? 2 : 0); }
 __device__ __forceinline__ int wave_bin_layers(int l) { return l <= 1 ? 0 : l >= LGAR_NBIN ? LGAR_NBIN - 1 : l - 1; }
 
 // Append `slot` to bin `bin` of the queue of stage `next` (next outside [0, LGAR_NSTAGE): nothing to append).  One atomicAdd per

@@ -131,7 +131,7 @@ struct lgarb_engine {
   int finish_smem = 1;
   int finish_spw = 16;           // records per warp of that kernel: 32 ... 2
   int finish_quantum = 64;       // search trips per turn of its warps
-  int finish_ff = 0;             // finishing kernel: searches through the fast path (measured: no gain either way)
+  int finish_ff = 1;             // finishing kernel: searches through the fast path (no difference for long windows; the hour-by-hour Update ends on the slowest search of the batch)
   unsigned long long* d_paths = nullptr;  // [LGAR_NPATH] path counters, allocated by lgarb_set_path_counters
   int finish_lane_stride = 4;  // finishing kernel: one slot per this many lanes
   int sm_count = 0;            // multiprocessors of the device: grids are sized in multiples of it

@@ -214,14 +214,14 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
 #pragma unroll
         for (int a = 1; a < 3; a++) ctx_store_n(g + kPitch * a, l + kPitch * a, cf);
         next = k.done ? LG_ST_TAIL : LG_ST_CORR;
-        bin = k.done ? wave_bin_fronts(fb.f.n, G.create) : 0;
+        bin = k.done ? wave_bin_fronts(fb.f.n, wave_tail_flags(G)) : 0;
       }
     } else if (STAGE == LG_ST_FETCH) {
       if (valid) {  // works on the record in place: scalars and epilogue state through registers, nothing else is touched
         LgLane& G = slots[slot].L;
         lg_stage_fetch(cfg, d, w, G, fsp);
         next = G.stage;
-        bin = wave_bin_fronts(G.f.n, next == LG_ST_HEAD && w.precip[(int64_t)G.t * w.series_stride + G.col] > 0.0);
+        bin = wave_bin_fronts(G.f.n, (next == LG_ST_HEAD && w.precip[(int64_t)G.t * w.series_stride + G.col] > 0.0) ? 1 : 0);
       }
     } else if (((LGAR_INPLACE_MASK >> STAGE) & 1) != 0) {
       // The stage works on the record where it lies in HBM (through L1/L2) instead of on a thread-private copy.  The
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
             lg_stage_tail(cfg, d, w, G, fsp);
         }
         next = G.stage;
-        bin = next == LG_ST_SEARCH ? wave_bin_layers(G.q.layer_num) : (next == LG_ST_CORR || next == LG_ST_FETCH) ? 0 : wave_bin_fronts(G.f.n, next == LG_ST_TAIL && G.create);
+        bin = next == LG_ST_SEARCH ? wave_bin_layers(G.q.layer_num) : (next == LG_ST_CORR || next == LG_ST_FETCH) ? 0 : wave_bin_fronts(G.f.n, next == LG_ST_TAIL ? wave_tail_flags(G) : 0);
         G.nf_stored = G.f.n;      // what a later stage that copies the record has to move
         if (STAGE != LG_ST_TAIL) G.nold_stored = G.old.n;
       }
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
           lg_stage_tail(cfg, d, w, L, fsp);
       }
       next = L.stage;
-      bin = next == LG_ST_SEARCH ? wave_bin_layers(L.q.layer_num) : (next == LG_ST_CORR || next == LG_ST_FETCH) ? 0 : wave_bin_fronts(L.f.n, next == LG_ST_TAIL && L.create);
+      bin = next == LG_ST_SEARCH ? wave_bin_layers(L.q.layer_num) : (next == LG_ST_CORR || next == LG_ST_FETCH) ? 0 : wave_bin_fronts(L.f.n, next == LG_ST_TAIL ? wave_tail_flags(L) : 0);
       if (next == LG_ST_FETCH) {
         lane_store<LG_PART_STATE>(&slots[slot], &S);  // the step is over: only the column state lives on
       } else if (STAGE == LG_ST_TAIL && next == LG_ST_CORR) {
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
         have = false;
       }
     }
-    wave_push(wv, append_mask, (next == LG_ST_HEAD || next == LG_ST_FETCH) ? next : -1, next == LG_ST_HEAD ? wave_bin_fronts(nf, rain) : 0, slot);
+    wave_push(wv, append_mask, (next == LG_ST_HEAD || next == LG_ST_FETCH) ? next : -1, next == LG_ST_HEAD ? wave_bin_fronts(nf, rain ? 1 : 0) : 0, slot);
   }
   if (w.prof && front_sum) atomicAdd(w.prof, front_sum);
 }

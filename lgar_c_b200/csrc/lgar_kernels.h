@@ -57,15 +57,16 @@ struct LgLane;
 enum { LG_ST_FETCH = 0, LG_ST_HEAD = 1, LG_ST_FRONT = 2, LG_ST_SEARCH = 3, LG_ST_TAIL = 4, LG_ST_CORR = 5, LG_ST_DONE = 6 };
 // Every queue is kept in LGAR_NBIN bins so that the lanes of a warp work on slots that look alike: HEAD / FRONT / TAIL slots are
 // binned by their front count (LGAR_NBIN_N levels: the per-front loops of those stages then have the same trip count across the
-// warp) and by a flag (LGAR_NBIN_FLAG = 2: HEAD -- it rains in the hour of the step; TAIL -- the step creates a surficial front;
-// both select a long branch), SEARCH slots by the layer of the front they search for (a trip evaluates theta in that many layers).
+// warp) and by flags (LGAR_NBIN_FLAG levels: HEAD -- it rains in the hour of the step; TAIL -- the step creates a surficial front,
+// the list needs a correction; each selects a long branch), SEARCH slots by the layer of the front they search for (a trip
+// evaluates theta in that many layers).
 // A consumer walks the bins one after the other, each bin starting at a multiple of 32 of its index space (no warp straddles
-// two bins).  Measured (profiles/r2_call8_summary.md): 1 bin 4.98e8, 2 bins 5.23e8, 4 bins 5.58e8 column-timesteps/s.
+// two bins).  Measured (profiles/r2_call8_summary.md): 1 bin 4.98e8, 2 bins 5.23e8, 4 bins 5.58e8, 6 x 2 bins 5.75e8 column-timesteps/s.
 #ifndef LGAR_NBIN_N
-#define LGAR_NBIN_N 4
+#define LGAR_NBIN_N 6
 #endif
 #ifndef LGAR_NBIN_FLAG
-#define LGAR_NBIN_FLAG 1
+#define LGAR_NBIN_FLAG 4
 #endif
 #define LGAR_NBIN (LGAR_NBIN_N * LGAR_NBIN_FLAG)
 struct LgarWave {

@@ -693,7 +693,16 @@ LG_FN_NOINLINE void lg_stage_head(const LgarConfig& cfg, const LgarDeviceState& 
 }
 
 // FRONT: front-loop iterations; ends in SEARCH or TAIL
-LG_FN void lg_stage_front(LgLane& L) { L.stage = lg_move_fronts(L) ? LG_ST_SEARCH : LG_ST_TAIL; }
+LG_FN void lg_stage_front(LgLane& L) {
+  L.stage = lg_move_fronts(L) ? LG_ST_SEARCH : LG_ST_TAIL;
+  // The front loop is over: what kind of correction the list needs first (lgar.cxx:1777-1790) is known here -- lg_move_end would
+  // find the same as its first act -- and the TAIL queue is binned by it (slots that need a merge / crossing / dry-over-wet fix
+  // take long branches of their own).
+  if (L.stage == LG_ST_TAIL && (L.nwf != 0 || L.create) && L.me_phase == 0) {
+    L.me_correction = lg_correction_type(L.c);
+    L.me_phase = 1;
+  }
+}
 
 // TAIL: ends in FRONT (next sub-cycle), CORR, or FETCH (step finished: GIUH, cumulative volumes, outputs)
 LG_FN_NOINLINE void lg_stage_tail(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, LgLane& L, unsigned long long* front_sum) {
