@@ -39,29 +39,28 @@ __device__ __forceinline__ void wave_push(const LgarWave& wv, unsigned append_ma
   wv.queue[next][buf][(size_t)bin * wv.nslots + base + __popc(peers & ((1u << lane) - 1))] = slot;
 }
 
-// The index space a consumer of queue (stage, buf) walks: the bins one after the other, each starting at a multiple of 32.
+// The index space a consumer of queue (stage, buf) walks: the bins one after the other, each starting at a multiple of 32.  The
+// table lives in shared memory (one per block, filled by its first warp): with 24 bins it would cost every thread 48 registers.
 struct WaveItems {
   int cnt[LGAR_NBIN], voff[LGAR_NBIN + 1];
 };
-__device__ __forceinline__ WaveItems wave_items(const LgarWave& wv, int stage, int buf) {
-  WaveItems it;
-  it.voff[0] = 0;
-#pragma unroll
-  for (int b = 0; b < LGAR_NBIN; b++) {
-    it.cnt[b] = wv.qcount[(stage * 2 + buf) * LGAR_NBIN + b];
-    it.voff[b + 1] = it.voff[b] + ((it.cnt[b] + 31) & ~31);
+__device__ __forceinline__ void wave_items_init(WaveItems& it, const LgarWave& wv, int stage, int buf) {
+  if (threadIdx.x == 0) {
+    it.voff[0] = 0;
+    for (int b = 0; b < LGAR_NBIN; b++) {
+      it.cnt[b] = wv.qcount[(stage * 2 + buf) * LGAR_NBIN + b];
+      it.voff[b + 1] = it.voff[b] + ((it.cnt[b] + 31) & ~31);
+    }
   }
-  return it;
+  __syncthreads();
 }
 // the slot at index i of that space, or -1 (padding at the end of a bin)
 __device__ __forceinline__ int wave_item(const LgarWave& wv, const WaveItems& it, int stage, int buf, int i) {
-  int slot = -1;
-#pragma unroll
-  for (int b = 0; b < LGAR_NBIN; b++) {
-    const int j = i - it.voff[b];
-    if (j >= 0 && j < it.cnt[b]) slot = wv.queue[stage][buf][(size_t)b * wv.nslots + j];
-  }
-  return slot;
+  int b = 0;
+#pragma unroll 1
+  while (b + 1 < LGAR_NBIN && i >= it.voff[b + 1]) b++;
+  const int j = i - it.voff[b];
+  return j < it.cnt[b] ? wv.queue[stage][buf][(size_t)b * wv.nslots + j] : -1;
 }
 // item j of the concatenation of every bin of every queue (the finishing kernels): slot and the stage it is parked in
 __device__ __forceinline__ int wave_item_any(const LgarWave& wv, int j, int* stage) {

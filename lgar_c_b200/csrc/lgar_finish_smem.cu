@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(32) lgar_wave_finish_smem_kernel(const __grid_
 }
 
 __global__ void lgar_wave_xclear_kernel(LgarWave wv) {
-  if (threadIdx.x < 2 * LGAR_NSTAGE * LGAR_NBIN) wv.qcount[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < 2 * LGAR_NSTAGE * LGAR_NBIN; i += blockDim.x) wv.qcount[i] = 0;
   if (threadIdx.x == 0) *wv.cursor = 0;  // zero between launches (the FETCH kernel relies on it)
 }
 

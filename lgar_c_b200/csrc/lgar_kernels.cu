@@ -176,7 +176,8 @@ constexpr int wave_min_blocks(int stage) {
 template <int STAGE, bool FF = false>
 __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(const __grid_constant__ LgarConfig cfg, const __grid_constant__ LgarDeviceState d, const __grid_constant__ LgarWindow w, const __grid_constant__ LgarWave wv, int consume,
                                                         unsigned append_mask, int quantum) {
-  const WaveItems items = wave_items(wv, STAGE, consume);
+  __shared__ WaveItems items;
+  wave_items_init(items, wv, STAGE, consume);
   LgLaneSlot* slots = reinterpret_cast<LgLaneSlot*>(wv.ctx);
   unsigned long long front_sum = 0, active_sum = 0;
   unsigned long long* fsp = w.prof ? &front_sum : nullptr;
@@ -479,7 +480,7 @@ cudaError_t lgar_launch_wave_poll(const LgarWave& wv, int32_t* host_counts, cuda
 }
 
 __global__ void lgar_wave_clear_kernel(LgarWave wv) {
-  if (threadIdx.x < 2 * LGAR_NSTAGE * LGAR_NBIN) wv.qcount[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < 2 * LGAR_NSTAGE * LGAR_NBIN; i += blockDim.x) wv.qcount[i] = 0;
 }
 
 cudaError_t lgar_launch_wave_finish(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, const LgarWave& wv, int in_flight,
@@ -509,7 +510,8 @@ __global__ void lgar_wave_init_kernel(const __grid_constant__ LgarConfig cfg, co
     if (slot_is_column) lg_lane_import(cfg, d, i, L);
     wv.queue[LG_ST_FETCH][0][i] = i;
   }
-  if (blockIdx.x == 0 && threadIdx.x < LGAR_NSTAGE * 2 * LGAR_NBIN) wv.qcount[threadIdx.x] = (threadIdx.x == LG_ST_FETCH * 2 * LGAR_NBIN) ? wv.nslots : 0;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < LGAR_NSTAGE * 2 * LGAR_NBIN; i += blockDim.x) wv.qcount[i] = (i == LG_ST_FETCH * 2 * LGAR_NBIN) ? wv.nslots : 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *wv.done_columns = 0;
     *wv.waiting = 0;
@@ -518,7 +520,7 @@ __global__ void lgar_wave_init_kernel(const __grid_constant__ LgarConfig cfg, co
 
 // reset the consumed queue's count (and the FETCH cursor) after its kernel ran
 __global__ void lgar_wave_reset_kernel(int32_t* count, int32_t* cursor) {
-  if (threadIdx.x < LGAR_NBIN) count[threadIdx.x] = 0;  // every bin of the consumed queue
+  for (int i = threadIdx.x; i < LGAR_NBIN; i += blockDim.x) count[i] = 0;  // every bin of the consumed queue
   if (cursor && threadIdx.x == 0) *cursor = 0;
 }
 
@@ -553,7 +555,7 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
       break;
     default: lgar_wave_kernel<LG_ST_TAIL><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
   }
-  lgar_wave_reset_kernel<<<1, LGAR_NBIN, 0, stream>>>(wv.qcount + (stage * 2 + consume) * LGAR_NBIN, refill ? wv.cursor : nullptr);
+  lgar_wave_reset_kernel<<<1, 32, 0, stream>>>(wv.qcount + (stage * 2 + consume) * LGAR_NBIN, refill ? wv.cursor : nullptr);
   return cudaGetLastError();
 }
 
