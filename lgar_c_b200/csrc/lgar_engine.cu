@@ -135,8 +135,11 @@ struct lgarb_engine {
   unsigned long long* d_paths = nullptr;  // [LGAR_NPATH] path counters, allocated by lgarb_set_path_counters
   int finish_lane_stride = 4;  // finishing kernel: one slot per this many lanes
   int sm_count = 0;            // multiprocessors of the device: grids are sized in multiples of it
-  int update_wave_min_cols = 1 << 30;  // lgarb_update: batches of at least this many columns hand their active columns to the stage kernels
+  // lgarb_update: batches of at least this many columns hand their active columns to the stage kernels (measured on 1.25 M columns,
+  // profiles/r2_call11_summary.md: 23.0 ms per hour with the stream/active kernel pair, 9.8 ms this way)
+  int update_wave_min_cols = 100000;
   int update_wave_slots = 262144;      // ... through this many slots
+  int update_wave_finish_below = 40000;  // ... with the finishing kernel taking over below this many slots in flight
   int wave_windows = 0;  // windows run so far (profiling range selection)
   int wave_escalate_below = 8192;
   int wave_corr_quantum = 64;  // correction-search trips per launch (scaled with the psi-search quantum when that escalates)
@@ -871,6 +874,7 @@ int lgarb_create(lgarb_engine** out) {
   knob("LGARB_FINISH_LANE_STRIDE", (*out)->finish_lane_stride);
   knob("LGARB_UPDATE_WAVE_MIN_COLS", (*out)->update_wave_min_cols);
   knob("LGARB_UPDATE_WAVE_SLOTS", (*out)->update_wave_slots);
+  knob("LGARB_UPDATE_WAVE_FINISH_BELOW", (*out)->update_wave_finish_below);
   knob("LGARB_HOST_CHUNK_HOURS", (*out)->host_chunk_hours);
   knob("LGARB_WAVE_ESCALATE_BELOW", (*out)->wave_escalate_below);
   knob("LGARB_WAVE_CORR_QUANTUM", (*out)->wave_corr_quantum);
@@ -1095,7 +1099,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w, int use_slots) {
       if (in_flight == 0) break;
       // every slot in flight is waiting for forcing: block until the next chunk is there
       advance_frontier(hours_present < w.K && h_cnt[2 * LGAR_NSTAGE] >= in_flight);
-      if (in_flight <= e->wave_finish_below && hours_present >= w.K) {  // the stragglers: one thread per slot runs its column to the end of the window
+      if (in_flight <= (use_slots > 0 ? std::max(e->wave_finish_below, e->update_wave_finish_below) : e->wave_finish_below) && hours_present >= w.K) {  // the stragglers: one thread per slot runs its column to the end of the window
         if (debug) cudaEventRecord(dbg[0], e->stream);
         w.use_ff = e->finish_ff;
         lgarb_engine::StageEv se{nullptr, nullptr, LGAR_NSTAGE};

@@ -164,9 +164,6 @@ __global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_window_kernel(const 
 #ifndef LGAR_MB_CORR
 #define LGAR_MB_CORR 0
 #endif
-#ifndef LGAR_INPLACE_MASK
-#define LGAR_INPLACE_MASK 0   // bit s: stage s works on the lane record in place
-#endif
 constexpr int wave_min_blocks(int stage) {
   return stage == LG_ST_FETCH ? LGAR_MB_FETCH : stage == LG_ST_HEAD ? LGAR_MB_HEAD : stage == LG_ST_FRONT ? LGAR_MB_FRONT
        : stage == LG_ST_SEARCH ? LGAR_MB_SEARCH : stage == LG_ST_TAIL ? LGAR_MB_TAIL : LGAR_MB_CORR;
@@ -223,34 +220,6 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         lg_stage_fetch(cfg, d, w, G, fsp);
         next = G.stage;
         bin = wave_bin_fronts(G.f.n, (next == LG_ST_HEAD && w.precip[(int64_t)G.t * w.series_stride + G.col] > 0.0) ? 1 : 0);
-      }
-    } else if (((LGAR_INPLACE_MASK >> STAGE) & 1) != 0) {
-      // The stage works on the record where it lies in HBM (through L1/L2) instead of on a thread-private copy.  The
-      // copy costs three trips through DRAM per context byte once the private copies of all resident threads exceed
-      // the L2 (ncu: HEAD moves 7.2 KB of DRAM traffic per slot for 2.4 KB of context); in place a byte that is read
-      // is read once and a byte that is written is written once.
-      if (valid) {
-        LgLane& G = slots[slot].L;
-        if (STAGE == LG_ST_HEAD) {
-          lg_stage_head(cfg, d, w, G, fsp);
-          active_sum += (G.stage == LG_ST_FRONT) ? 1 : 0;
-          if (G.stage == LG_ST_FRONT) lg_stage_front(G);
-        } else {
-          G.c.cfg = &cfg;
-          G.c.cls = G.cls;
-          G.c.f = &G.f;
-          G.c.ff = G.ffv;
-          G.c.paths = w.paths;
-          G.c.use_ff = w.use_ff != 0;
-          if (STAGE == LG_ST_FRONT)
-            lg_stage_front(G);
-          else
-            lg_stage_tail(cfg, d, w, G, fsp);
-        }
-        next = G.stage;
-        bin = next == LG_ST_SEARCH ? wave_bin_layers(G.q.layer_num) : (next == LG_ST_CORR || next == LG_ST_FETCH) ? 0 : wave_bin_fronts(G.f.n, next == LG_ST_TAIL ? wave_tail_flags(G) : 0);
-        G.nf_stored = G.f.n;      // what a later stage that copies the record has to move
-        if (STAGE != LG_ST_TAIL) G.nold_stored = G.old.n;
       }
     } else if (valid) {
       LgLaneSlot S;
