@@ -112,6 +112,12 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
  * copies are part of the call; it returns when the outputs are in place. */
 int lgarb_update_steps_host(lgarb_engine* e, int64_t n_steps, const double* h_precip_mm_per_h, const double* h_pet_mm_per_h,
                             int n_outputs, const char* const* output_names, double* const* h_outputs);
+/* The same with host arrays wider than this engine's batch: row t of the forcing starts at h_precip + t * forcing_pitch, row t of
+ * output i at h_outputs[i] + t * output_pitch (in elements, >= n_columns).  One engine of a multi-device group works on its block
+ * of columns of global [step][all columns] arrays this way (include/lgarb_group.h). */
+int lgarb_update_steps_host_pitched(lgarb_engine* e, int64_t n_steps, const double* h_precip_mm_per_h, const double* h_pet_mm_per_h,
+                                    int64_t forcing_pitch, int n_outputs, const char* const* output_names, double* const* h_outputs,
+                                    int64_t output_pitch);
 /* Streamed variant (forcing / output streaming; replaces the per-step CSV reader and
  * writer loop of src/bmi_main_lgar.cxx:116-157,183-262 for batched runs).  The series are cut into chunks of
  * chunk_steps hours; the host-to-device copy of chunk k+1 and the device-to-host copy of the outputs of chunk k-1
@@ -199,6 +205,8 @@ int lgarb_get_fronts(lgarb_engine* e, int64_t col0, int64_t ncol, double* depth_
  *                 volAET, volPET, volrunoff_CR, volCRend, volQ, volchange_calib, volQ_CR,
  *                 global_error */
 int lgarb_get_global_mass_balance(lgarb_engine* e, int64_t col0, int64_t ncol, double* out);
+/* the same for every column, computed and left on the device behind the engine's stream: d_out[n_columns][16] */
+int lgarb_get_global_mass_balance_device(lgarb_engine* e, double* d_out);
 
 /* The parsed soil table row the engine uses for `soil` (1-based), for checking the parser quirk
  *  against the reference: out[10] = theta_r, theta_e, alpha, n, m, lambda, psib,

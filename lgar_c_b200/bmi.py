@@ -85,6 +85,8 @@ def _load():
         "lgarb_update_until": ([vp, C.c_double], C.c_int),
         "lgarb_update_steps_device": ([vp, i64, vp, vp, i64, vp, i64, vp], C.c_int),
         "lgarb_update_steps_host": ([vp, i64, vp, vp, C.c_int, vp, vp], C.c_int),
+        "lgarb_update_steps_host_pitched": ([vp, i64, vp, vp, i64, C.c_int, vp, vp, i64], C.c_int),
+        "lgarb_get_global_mass_balance_device": ([vp, vp], C.c_int),
         "lgarb_update_steps_host_stream": ([vp, i64, i64, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp], C.c_int),
         "lgarb_synchronize": ([vp], C.c_int),
         "lgarb_set_value": ([vp, cp, vp], C.c_int),
@@ -243,6 +245,21 @@ class BmiLGARBatch:
         cp = (C.c_void_p * len(names))(*[outputs[n].ctypes.data for n in names])
         self._ck(self._L.lgarb_update_steps_host(self._h, int(n_steps), _ptr(P), _ptr(E), len(names), cn, cp))
         return outputs
+
+    def update_steps_host_block(self, precip, pet, col0, output_names=()):
+        """This engine as the owner of the columns [col0, col0 + n_columns) of GLOBAL host arrays [n_steps][n_total]
+        (lgarb_update_steps_host_pitched): forcing read from, outputs written into that block of columns.  Returns
+        {name: global array} with only the block filled (NaN elsewhere)."""
+        P = np.ascontiguousarray(precip, dtype=np.float64)
+        E = np.ascontiguousarray(pet, dtype=np.float64)
+        if P.ndim != 2 or E.shape != P.shape or col0 < 0 or col0 + self.n_columns > P.shape[1]:
+            raise LgarbError("precip and pet must both be [n_steps][n_total] with the block inside")
+        n_steps, ntot = P.shape
+        outs = {n: np.full((n_steps, ntot), np.nan) for n in output_names}
+        cn = (C.c_char_p * max(1, len(outs)))(*[n.encode() for n in outs])
+        cp = (C.c_void_p * max(1, len(outs)))(*[a.ctypes.data + 8 * col0 for a in outs.values()])
+        self._ck(self._L.lgarb_update_steps_host_pitched(self._h, int(n_steps), P.ctypes.data + 8 * col0, E.ctypes.data + 8 * col0, int(ntot), len(outs), cn, cp, int(ntot)))
+        return outs
 
     def update_steps_host_stream(self, precip, pet, outputs=(), chunk_steps=0, output_dtype=np.float64):
         """Streamed variant of update_steps_host (lgarb_update_steps_host_stream): the series are cut into chunks of

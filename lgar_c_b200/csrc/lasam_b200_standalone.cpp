@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "../../include/lgarb.h"
+#include "../../include/lgarb_group.h"
 
 namespace {
 
@@ -103,6 +104,7 @@ struct Options {
   std::string config, out_dir = ".", forcing_bin, out_bin;
   int64_t columns = 1, shift = 0, chunk = 240;
   int device = 0;
+  std::vector<int> devices;  // --devices a,b,..: the columns in contiguous blocks over these GPUs (include/lgarb_group.h)
   bool layers = false, f32 = false, quiet = false;
   std::vector<int64_t> write_columns = {0};
   std::vector<std::string> out_vars = {"total_discharge"};
@@ -120,6 +122,9 @@ Options parse(int argc, char** argv) {
     else if (a == "--shift") o.shift = std::stoll(need("--shift"));
     else if (a == "--chunk") o.chunk = std::stoll(need("--chunk"));
     else if (a == "--device") o.device = std::stoi(need("--device"));
+    else if (a == "--devices") {
+      for (auto& d : split(need("--devices"), ',')) o.devices.push_back(std::stoi(d));
+    }
     else if (a == "--out-dir") o.out_dir = need("--out-dir");
     else if (a == "--forcing-bin") o.forcing_bin = need("--forcing-bin");
     else if (a == "--out-bin") o.out_bin = need("--out-bin");
@@ -141,17 +146,93 @@ Options parse(int argc, char** argv) {
 
 std::string suffix_for(const Options& o, int64_t col) { return o.columns == 1 ? std::string() : "_c" + std::to_string(col); }
 
+// --devices: the batch in contiguous column blocks over several GPUs of the node (liblgarb_group.so).  Forcing from the CSV of the
+// configuration file with a circular shift per column, data_variables CSVs for the columns asked for, and at the end the balance
+// terms of every column gathered onto the first device over NCCL with their totals.
+int run_group(const Options& o) {
+  if (o.layers || o.f32 || !o.forcing_bin.empty() || !o.out_bin.empty()) die("--devices runs the CSV forcing with f64 CSV outputs (no --layers, --f32, --forcing-bin, --out-bin)");
+  lgarb_group* g = nullptr;
+  if (lgarb_group_create(&g, (int)o.devices.size(), o.devices.data()) != LGARB_SUCCESS) die("lgarb_group_create failed (device list)");
+  auto gck = [&](int rc, const char* what) {
+    if (rc != LGARB_SUCCESS) die(std::string(what) + ": " + lgarb_group_last_error(g));
+  };
+  gck(lgarb_group_initialize(g, o.config.c_str(), o.columns, nullptr, nullptr), "Initialize");
+  lgarb_engine* e0 = lgarb_group_engine(g, 0);
+  double endtime = 0, timestep = 0;
+  ck(e0, lgarb_get_end_time(e0, &endtime), "GetEndTime");
+  ck(e0, lgarb_get_time_step(e0, &timestep), "GetTimeStep");
+  const int64_t nsteps = (int64_t)(endtime / timestep), N = o.columns;
+  std::vector<std::string> time;
+  std::vector<double> P1, E1;
+  read_forcing_csv(forcing_file_of(o.config), time, P1, E1);
+  if (nsteps > (int64_t)E1.size()) die("nsteps exceeds the forcing data");
+  const int64_t nf = (int64_t)E1.size();
+  for (int64_t c : o.write_columns)
+    if (c < 0 || c >= N) die("--write-columns: column out of range");
+  std::vector<FILE*> fvar;
+  for (int64_t c : o.write_columns) {
+    FILE* fv = fopen((o.out_dir + "/data_variables" + suffix_for(o, c) + ".csv").c_str(), "w");
+    if (!fv) die("cannot write to " + o.out_dir);
+    fprintf(fv, "Time,");
+    for (int j = 0; j < 11; j++) fprintf(fv, "%s%s", kVarNames[j], j == 10 ? "\n" : ",");
+    fvar.push_back(fv);
+  }
+  const int nout = o.write_columns.empty() ? 0 : 11;
+  const int64_t seg = std::max<int64_t>(1, std::min<int64_t>(nsteps, (int64_t)((4ull << 30) / ((size_t)(2 + nout) * (size_t)N * 8))));
+  std::vector<double> P((size_t)seg * N), E((size_t)seg * N);
+  std::vector<std::vector<double>> outs(nout, std::vector<double>((size_t)seg * N));
+  std::vector<double*> ptrs;
+  for (auto& v : outs) ptrs.push_back(v.data());
+  for (int64_t t0 = 0; t0 < nsteps; t0 += seg) {
+    const int64_t len = std::min<int64_t>(seg, nsteps - t0);
+    for (int64_t t = 0; t < len; t++)
+      for (int64_t c = 0; c < N; c++) {
+        const int64_t src = (t0 + t + c * o.shift) % nf;
+        P[t * N + c] = P1[src];
+        E[t * N + c] = E1[src];
+      }
+    gck(lgarb_group_update_steps_host(g, len, P.data(), E.data(), nout, kVarNames, ptrs.data()), "update_steps_host");
+    for (size_t w = 0; w < o.write_columns.size(); w++) {
+      const int64_t c = o.write_columns[w];
+      for (int64_t t = 0; t < len; t++) {
+        fprintf(fvar[w], "%s,", time[(t0 + t + c * o.shift) % nf].c_str());
+        for (int j = 0; j < 11; j++) fprintf(fvar[w], "%6.15f%s", outs[j][t * N + c], j == 10 ? "\n" : ",");
+      }
+    }
+  }
+  for (FILE* f : fvar) fclose(f);
+  std::vector<double> gm((size_t)N * 16);
+  double tot[16], ms = 0.0;
+  gck(lgarb_group_gather_mass_balance(g, gm.data(), tot, &ms), "gather");
+  if (!o.quiet) {
+    double worst = 0.0;
+    for (int64_t c = 0; c < N; c++)
+      if (std::isfinite(gm[c * 16 + 15])) worst = std::fmax(worst, std::fabs(gm[c * 16 + 15]));
+    printf("columns %lld over %d devices, steps %lld, max |global mass balance| %.6e cm; totals over all columns: precipitation %.6f cm, infiltration %.6f cm, "
+           "AET %.6f cm, discharge %.6f cm (NCCL gather of %lld x 16 terms + reduce: %.3f ms on the first device)\n",
+           (long long)N, lgarb_group_num_devices(g), (long long)nsteps, worst, tot[1], tot[2], tot[8], tot[12], (long long)N, ms);
+    for (int64_t c : o.write_columns)
+      printf("column %lld: initial water %.10f cm, precipitation %.10f cm, infiltration %.10f cm, runoff %.10f cm, AET %.10f cm, final water %.10f cm, "
+             "global balance %.6e cm\n",
+             (long long)c, gm[c * 16 + 0], gm[c * 16 + 1], gm[c * 16 + 2], gm[c * 16 + 5], gm[c * 16 + 8], gm[c * 16 + 3], gm[c * 16 + 15]);
+  }
+  lgarb_group_destroy(g);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
   Options o = parse(argc, argv);
   if (o.config.empty()) {
     printf("Usage: lasam_b200_standalone CONFIGURATION_FILE [--columns N] [--shift S] [--chunk H] [--layers]\n"
-           "         [--write-columns a,b,..|none] [--out-dir DIR] [--forcing-bin FILE] [--out-bin FILE] [--out-vars v1,v2] [--f32]\n"
+           "         [--write-columns a,b,..|none] [--out-dir DIR] [--forcing-bin FILE] [--out-bin FILE] [--out-vars v1,v2] [--f32] [--devices a,b,..]\n"
            "Runs LASAM for a batch of columns on the GPU through its batched BMI (include/lgarb.h).\n"
            "Outputs are written to `data_variables.csv` (and `data_layers.csv` with --layers) for the columns asked for.\n");
     return 0;
   }
+  if (o.devices.size() > 1) return run_group(o);
+  if (o.devices.size() == 1) o.device = o.devices[0];
   lgarb_engine* e = nullptr;
   if (lgarb_create(&e) != LGARB_SUCCESS || !e) die("lgarb_create failed");
   ck(e, lgarb_initialize(e, o.config.c_str(), o.columns, o.device), "Initialize");

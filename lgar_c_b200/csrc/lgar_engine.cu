@@ -1269,9 +1269,26 @@ int lgarb_update_steps_device(lgarb_engine* e, int64_t n_steps, const double* d_
 // Host-buffer variant of the multi-step call: forcing in, chosen outputs out, copies included.
 int lgarb_update_steps_host(lgarb_engine* e, int64_t n_steps, const double* h_precip, const double* h_pet, int n_outputs,
                             const char* const* output_names, double* const* h_outputs) {
+  return lgarb_update_steps_host_pitched(e, n_steps, h_precip, h_pet, e ? e->ncol : 0, n_outputs, output_names, h_outputs, e ? e->ncol : 0);
+}
+
+// The same with host arrays that are wider than this engine's batch: row t of the forcing starts at h_precip + t * forcing_pitch,
+// row t of output i at h_outputs[i] + t * output_pitch (elements).  One engine of a multi-device group works on its block of
+// columns of global [step][all columns] arrays this way (lgar_group.cu).
+int lgarb_update_steps_host_pitched(lgarb_engine* e, int64_t n_steps, const double* h_precip, const double* h_pet, int64_t forcing_pitch, int n_outputs,
+                                    const char* const* output_names, double* const* h_outputs, int64_t output_pitch) {
   LGARB_GUARD(e, {
     require_init(e);
     if (n_steps <= 0 || !h_precip || !h_pet) throw std::runtime_error("bad forcing series");
+    if (forcing_pitch < e->ncol || (n_outputs > 0 && output_pitch < e->ncol)) throw std::runtime_error("host pitch smaller than the number of columns");
+    const size_t row = (size_t)e->ncol * sizeof(double);
+    auto h2d_rows = [&](double* dst, const double* src, int64_t t0, int64_t t1, cudaStream_t st) {
+      if (forcing_pitch == e->ncol)
+        CUDA_TRY(cudaMemcpyAsync(dst + (size_t)t0 * e->ncol, src + (size_t)t0 * e->ncol, (size_t)(t1 - t0) * row, cudaMemcpyHostToDevice, st));
+      else
+        CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)t0 * e->ncol, row, src + (size_t)t0 * forcing_pitch, (size_t)forcing_pitch * sizeof(double), row, (size_t)(t1 - t0),
+                                   cudaMemcpyHostToDevice, st));
+    };
     if (n_outputs < 0 || n_outputs > LGAR_NOUT) throw std::runtime_error("bad output count");
     const size_t n = (size_t)n_steps * (size_t)e->ncol;
     const size_t need = n * (2 + (size_t)n_outputs);
@@ -1305,9 +1322,8 @@ int lgarb_update_steps_host(lgarb_engine* e, int64_t n_steps, const double* h_pr
       if (!e->h2d_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
       for (int64_t t0 = 0; t0 < n_steps; t0 += ch) {
         const int64_t t1 = std::min(n_steps, t0 + ch);
-        const size_t off = (size_t)t0 * (size_t)e->ncol, cnt = (size_t)(t1 - t0) * (size_t)e->ncol;
-        CUDA_TRY(cudaMemcpyAsync(dP + off, h_precip + off, cnt * sizeof(double), cudaMemcpyHostToDevice, e->h2d_stream));
-        CUDA_TRY(cudaMemcpyAsync(dE + off, h_pet + off, cnt * sizeof(double), cudaMemcpyHostToDevice, e->h2d_stream));
+        h2d_rows(dP, h_precip, t0, t1, e->h2d_stream);
+        h2d_rows(dE, h_pet, t0, t1, e->h2d_stream);
         cudaEvent_t ev;
         CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         fr.ev.push_back(ev);
@@ -1316,8 +1332,8 @@ int lgarb_update_steps_host(lgarb_engine* e, int64_t n_steps, const double* h_pr
       }
       e->frontier = &fr;
     } else {
-      CUDA_TRY(cudaMemcpyAsync(dP, h_precip, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-      CUDA_TRY(cudaMemcpyAsync(dE, h_pet, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+      h2d_rows(dP, h_precip, 0, n_steps, e->stream);
+      h2d_rows(dE, h_pet, 0, n_steps, e->stream);
     }
     double* sinks[LGAR_NOUT];
     for (int k = 0; k < LGAR_NOUT; k++) sinks[k] = nullptr;
@@ -1327,8 +1343,13 @@ int lgarb_update_steps_host(lgarb_engine* e, int64_t n_steps, const double* h_pr
       sinks[k] = dE + n * (size_t)(1 + i);
     }
     if (lgarb_update_steps_device(e, n_steps, dP, dE, e->ncol, sinks, e->ncol, nullptr) != LGARB_SUCCESS) throw std::runtime_error(e->last_error);
-    for (int i = 0; i < n_outputs; i++)
-      CUDA_TRY(cudaMemcpyAsync(h_outputs[i], dE + n * (size_t)(1 + i), n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    for (int i = 0; i < n_outputs; i++) {
+      if (output_pitch == e->ncol)
+        CUDA_TRY(cudaMemcpyAsync(h_outputs[i], dE + n * (size_t)(1 + i), n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+      else
+        CUDA_TRY(cudaMemcpy2DAsync(h_outputs[i], (size_t)output_pitch * sizeof(double), dE + n * (size_t)(1 + i), row, row, (size_t)n_steps, cudaMemcpyDeviceToHost,
+                                   e->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(e->stream));
   });
 }
@@ -1694,6 +1715,22 @@ int lgarb_get_global_mass_balance(lgarb_engine* e, int64_t col0, int64_t ncol, d
       o[14] = cum[LGAR_CUM_Q_CR * n + c];
       o[15] = o[0] + o[1] - o[5] - o[8] - o[4] - o[7] - o[3] + o[13] - o[10] - o[11];  // lgar.cxx:1185
     }
+  });
+}
+
+// The same 16 terms for every column of the engine, computed and left ON THE DEVICE ([n_columns][16], cm) behind the engine's
+// stream: what a multi-device gather sends (lgar_group.cu).  Arithmetic and order are those of the host version above.
+int lgarb_get_global_mass_balance_device(lgarb_engine* e, double* d_out) {
+  LGARB_GUARD(e, {
+    require_init(e);
+    if (!d_out) throw std::runtime_error("null destination");
+    double* d_vc = nullptr;
+    if (!e->volchange_calib.empty()) {
+      d_vc = e->d_stage;  // [stride] staging of the engine
+      CUDA_TRY(cudaMemcpyAsync(d_vc, e->volchange_calib.data(), (size_t)e->ncol * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    }
+    CUDA_TRY(lgar_launch_mass_balance(e->d, e->volstart, d_vc, d_out, e->stream));
+    e->launches += 1;
   });
 }
 

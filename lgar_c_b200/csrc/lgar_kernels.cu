@@ -608,6 +608,37 @@ cudaError_t lgar_launch_debug_functions(const LgarConfig& cfg, const LgarDeviceS
   return cudaGetLastError();
 }
 
+// The 16 terms of lgar_global_mass_balance (reference src/lgar.cxx:1162-1216) of every column, [ncol][16] on the device
+// (lgarb_get_global_mass_balance_device; same order and arithmetic as the host version in lgar_engine.cu).
+__global__ void lgar_mass_balance_kernel(LgarDeviceState d, const double* __restrict__ volstart, const double* __restrict__ volchange, double* __restrict__ out) {
+  const int64_t st = d.stride;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < d.ncol; c += (int64_t)gridDim.x * blockDim.x) {
+    double o[16];
+    o[0] = volstart[c];
+    o[1] = d.cum[LGAR_CUM_PRECIP * st + c];
+    o[2] = d.cum[LGAR_CUM_IN * st + c];
+    o[3] = d.scal[LGAR_S_STORAGE * st + c];
+    o[4] = d.scal[LGAR_S_VOLON * st + c];
+    o[5] = d.cum[LGAR_CUM_RUNOFF * st + c];
+    o[6] = d.cum[LGAR_CUM_GIUH * st + c];
+    o[7] = d.cum[LGAR_CUM_RECH * st + c];
+    o[8] = d.cum[LGAR_CUM_AET * st + c];
+    o[9] = d.cum[LGAR_CUM_PET * st + c];
+    o[10] = d.cum[LGAR_CUM_RUNOFF_CR * st + c];
+    o[11] = d.scal[LGAR_S_CR_FAST * st + c] + d.scal[LGAR_S_CR_SLOW * st + c];
+    o[12] = d.cum[LGAR_CUM_Q * st + c];
+    o[13] = volchange ? volchange[c] : 0.0;
+    o[14] = d.cum[LGAR_CUM_Q_CR * st + c];
+    o[15] = o[0] + o[1] - o[5] - o[8] - o[4] - o[7] - o[3] + o[13] - o[10] - o[11];  // lgar.cxx:1185
+#pragma unroll
+    for (int k = 0; k < 16; k++) out[c * 16 + k] = o[k];
+  }
+}
+cudaError_t lgar_launch_mass_balance(const LgarDeviceState& d, const double* volstart, const double* volchange, double* out, cudaStream_t stream) {
+  lgar_mass_balance_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((d.ncol + 255) / 256, 2048)), 256, 0, stream>>>(d, volstart, volchange, out);
+  return cudaGetLastError();
+}
+
 // Gather per-front BMI arrays into a caller-facing [ncol][LGAR_W] layout (pad = NaN).
 __global__ void lgar_gather_fronts_kernel(LgarDeviceState d, int which, double scale, double* dst, int64_t col0, int64_t ncol) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

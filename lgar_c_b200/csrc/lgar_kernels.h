@@ -108,6 +108,7 @@ cudaError_t lgar_launch_step(const LgarConfig& cfg, const LgarDeviceState& d, co
 cudaError_t lgar_launch_sum_fronts(const LgarDeviceState& d, unsigned long long* acc, cudaStream_t stream);
 cudaError_t lgar_launch_gather_fronts(const LgarDeviceState& d, int which, double scale, double* dst, int64_t col0, int64_t ncol,
                                       cudaStream_t stream);
+cudaError_t lgar_launch_mass_balance(const LgarDeviceState& d, const double* volstart, const double* volchange, double* out, cudaStream_t stream);
 cudaError_t lgar_launch_gather_layers(const LgarDeviceState& d, double* dst, int64_t col0, int64_t ncol, int L, cudaStream_t stream);
 int lgar_active_kernel_max_blocks_per_sm();
 // DFMA microbenchmark: `iters` trips of 8 independent FMA chains per thread on blocks x 256 threads; sink keeps the result alive

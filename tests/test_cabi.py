@@ -84,3 +84,25 @@ def test_config_errors_are_reported_like_the_reference(tmp_path):
     b = lgar_c_b200.BmiLGARBatch()
     with pytest.raises(lgar_c_b200.LgarbError, match="does not set"):
         b.initialize(bad, 4)
+
+
+def test_group_library_exports_every_declared_symbol():
+    """include/lgarb_group.h (several GPUs behind one handle, liblgarb_group.so = liblgarb.so + NCCL): every declared symbol is
+    exported and bound; without a CUDA device a group cannot be created."""
+    import lgar_c_b200
+    from lgar_c_b200 import group
+    lgar_c_b200.build_library()
+    text = (ROOT / "include" / "lgarb_group.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(lgarb_group_[a-z_0-9]+)\s*\(", text)))
+    assert len(syms) == 11 and sorted(group.GROUP_SYMBOLS) == syms
+    try:
+        lib = group._gload()
+    except OSError as e:  # pragma: no cover
+        pytest.skip(f"libnccl not loadable here: {e}")
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/lgarb_group.h but not exported"
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(lgar_c_b200.LgarbError):
+            group.LgarGroup([0])

@@ -439,3 +439,57 @@ def test_hourly_update_through_stage_kernels(cuda_device, tmp_path):
         assert np.array_equal(o0, o1, equal_nan=True) and np.array_equal(m0, m1, equal_nan=True)
         for k in ("depth", "theta", "psi", "K", "dzdt", "layer", "to_bottom", "nfronts"):
             assert np.array_equal(f0[k], f1[k], equal_nan=True), k
+
+
+def test_engine_on_a_block_of_global_host_arrays(cuda_device, tmp_path):
+    """lgarb_update_steps_host_pitched: an engine that owns columns [col0, col0 + n) of global [step][n_total] host arrays (what
+    one device of a multi-device group does, include/lgarb_group.h) gives the outputs of an engine fed that block alone, bit for
+    bit, writes nothing outside its block, and its balance terms computed on the device equal the host version."""
+    import torch
+    import lgar_c_b200
+    g = load_golden("Phillipsburg_with_reservoir")
+    cfg = config_for("Phillipsburg_with_reservoir", tmp_path)
+    ntot, col0, ncol, T = 333, 77, 130, 300
+    shifts = (np.arange(ntot) * 7919) % 8760
+    Pm = np.ascontiguousarray(np.stack([np.roll(g["precip"], -int(s))[:T] for s in shifts], axis=1))
+    Em = np.ascontiguousarray(np.stack([np.roll(g["pet"], -int(s))[:T] for s in shifts], axis=1))
+    names = ["total_discharge", "soil_storage"]
+    a = lgar_c_b200.BmiLGARBatch()
+    a.initialize(cfg, ncol)
+    ref = a.update_steps_host(Pm[:, col0:col0 + ncol], Em[:, col0:col0 + ncol], names)
+    b = lgar_c_b200.BmiLGARBatch()
+    b.initialize(cfg, ncol)
+    out = b.update_steps_host_block(Pm, Em, col0, names)
+    for n in names:
+        assert np.array_equal(out[n][:, col0:col0 + ncol], ref[n]), n
+        assert np.isnan(out[n][:, :col0]).all() and np.isnan(out[n][:, col0 + ncol:]).all(), "wrote outside its block"
+    d_out = torch.zeros((ncol, 16), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    b._ck(b._L.lgarb_get_global_mass_balance_device(b._h, d_out.data_ptr()))
+    b.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), b.get_global_mass_balance(), equal_nan=True)
+
+
+def test_group_of_one_device(cuda_device, tmp_path):
+    """liblgarb_group.so with a single device (no NCCL traffic): the group verbs give what the engine gives."""
+    import lgar_c_b200
+    from lgar_c_b200.group import LgarGroup
+    g = load_golden("Phillipsburg_with_reservoir")
+    cfg = config_for("Phillipsburg_with_reservoir", tmp_path)
+    ncol, T = 200, 250
+    shifts = (np.arange(ncol) * 7919) % 8760
+    Pm = np.ascontiguousarray(np.stack([np.roll(g["precip"], -int(s))[:T] for s in shifts], axis=1))
+    Em = np.ascontiguousarray(np.stack([np.roll(g["pet"], -int(s))[:T] for s in shifts], axis=1))
+    a = lgar_c_b200.BmiLGARBatch()
+    a.initialize(cfg, ncol)
+    ref = a.update_steps_host(Pm, Em, ["total_discharge"])
+    grp = LgarGroup([0])
+    grp.initialize(cfg, ncol)
+    assert grp.shards() == [(0, ncol)]
+    out = grp.update_steps_host(Pm, Em, ["total_discharge"])
+    assert np.array_equal(out["total_discharge"], ref["total_discharge"])
+    gm, tot, ms = grp.gather_mass_balance()
+    want = a.get_global_mass_balance()
+    assert np.array_equal(gm, want, equal_nan=True)
+    assert np.allclose(tot, want.sum(axis=0), rtol=1e-12, atol=1e-9)
+    grp.finalize()
