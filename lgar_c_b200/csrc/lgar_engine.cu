@@ -156,8 +156,8 @@ struct lgarb_engine {
   bool stage_timing = false;
   struct StageEv { cudaEvent_t a, b; int stage; };
   std::vector<StageEv> stage_evs;
-  double stage_ms[LGAR_NSTAGE_TIMED + 1] = {0, 0, 0, 0, 0, 0, 0};   // FETCH, HEAD, FRONT, SEARCH, TAIL (+ GEFF), CORR, finishing kernel
-  int64_t stage_launches[LGAR_NSTAGE_TIMED + 1] = {0, 0, 0, 0, 0, 0, 0};
+  double stage_ms[LGAR_NSTAGE + 1] = {0, 0, 0, 0, 0, 0, 0};   // FETCH, HEAD, FRONT, SEARCH, TAIL, CORR, finishing kernel
+  int64_t stage_launches[LGAR_NSTAGE + 1] = {0, 0, 0, 0, 0, 0, 0};
   // profiling (lgarb_set_profiling): event triples per step, resolved lazily
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -1026,7 +1026,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w, int use_slots) {
   advance_frontier(true);  // the first chunk: nothing to do before it is there
   CUDA_TRY(lgar_launch_wave_init(e->cfg, e->d, wv, w.slot_is_column, e->stream));
   e->launches += 1;
-  int par[LGAR_NSTAGE] = {0, 0, 0, 0, 0, 0, 0};
+  int par[LGAR_NSTAGE] = {0, 0, 0, 0, 0, 0};
   int quantum = e->wave_quantum;
   int in_flight = wv.nslots;
   const bool dbg_on = getenv("LGARB_WAVE_DEBUG") != nullptr;
@@ -1062,7 +1062,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w, int use_slots) {
       cudaEventRecord(dbg_evs.back().first, e->stream);
       dbg_evs.back().second = stage;
     }
-    lgarb_engine::StageEv se{nullptr, nullptr, stage == LG_ST_GEFF ? LG_ST_TAIL : stage};
+    lgarb_engine::StageEv se{nullptr, nullptr, stage};
     if (e->stage_timing) {
       CUDA_TRY(cudaEventCreate(&se.a));
       CUDA_TRY(cudaEventCreate(&se.b));
@@ -1086,7 +1086,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w, int use_slots) {
   // Every round starts with the queue counts on the host (48 bytes): the number of slots in flight bounds
   // every queue of the round (grid size), empty parts of the round are not launched, and the window is over
   // when nothing is in flight.
-  int cnt[LGAR_NSTAGE] = {wv.nslots, 0, 0, 0, 0, 0, 0};
+  int cnt[LGAR_NSTAGE] = {wv.nslots, 0, 0, 0, 0, 0};
   for (int64_t round = 0;; round++) {
     if (round > 0) {
       CUDA_TRY(lgar_launch_wave_poll(wv, h_cnt, e->stream));
@@ -1102,7 +1102,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w, int use_slots) {
       if (in_flight <= (use_slots > 0 ? std::max(e->wave_finish_below, e->update_wave_finish_below) : e->wave_finish_below) && hours_present >= w.K) {  // the stragglers: one thread per slot runs its column to the end of the window
         if (debug) cudaEventRecord(dbg[0], e->stream);
         w.use_ff = e->finish_ff;
-        lgarb_engine::StageEv se{nullptr, nullptr, LGAR_NSTAGE_TIMED};
+        lgarb_engine::StageEv se{nullptr, nullptr, LGAR_NSTAGE};
         if (e->stage_timing) {
           CUDA_TRY(cudaEventCreate(&se.a));
           CUDA_TRY(cudaEventCreate(&se.b));
@@ -1170,10 +1170,6 @@ void run_wave_window(lgarb_engine* e, LgarWindow w, int use_slots) {
         launch(LG_ST_CORR);
         launch(LG_ST_TAIL);
       }
-      if (!e->cfg.use_closed_form_G) {  // numeric Geff: TAIL stops before lg_dzdt_calc, GEFF makes its calc_Geff calls, TAIL goes on
-        launch(LG_ST_GEFF);
-        launch(LG_ST_TAIL);
-      }
     }
     e->wave_rounds++;
     if (round == ncu_round) {
@@ -1185,7 +1181,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w, int use_slots) {
       cudaEventSynchronize(dbg[1]);
       float ms = 0;
       cudaEventElapsedTime(&ms, dbg[0], dbg[1]);
-      float st_ms[LGAR_NSTAGE] = {0, 0, 0, 0, 0, 0, 0};
+      float st_ms[LGAR_NSTAGE] = {0, 0, 0, 0, 0, 0};
       for (size_t i = 0; i < dbg_evs.size(); i++) {
         float x = 0;
         cudaEventElapsedTime(&x, dbg_evs[i].first, i + 1 < dbg_evs.size() ? dbg_evs[i + 1].first : dbg[1]);
@@ -1193,8 +1189,8 @@ void run_wave_window(lgarb_engine* e, LgarWindow w, int use_slots) {
       }
       for (auto& pe : dbg_evs) cudaEventDestroy(pe.first);
       dbg_evs.clear();
-      fprintf(stderr, "[wave] round %lld: %.3f ms  in flight %d  queues F=%d H=%d FR=%d S=%d T=%d C=%d G=%d  ms: FETCH %.2f HEAD %.2f FRONT %.2f SEARCH %.2f TAIL %.2f CORR %.2f GEFF %.2f\n",
-              (long long)round, ms, in_flight, cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], cnt[5], cnt[6], st_ms[0], st_ms[1], st_ms[2], st_ms[3], st_ms[4], st_ms[5], st_ms[6]);
+      fprintf(stderr, "[wave] round %lld: %.3f ms  in flight %d  queues F=%d H=%d FR=%d S=%d T=%d C=%d  ms: FETCH %.2f HEAD %.2f FRONT %.2f SEARCH %.2f TAIL %.2f CORR %.2f\n",
+              (long long)round, ms, in_flight, cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], cnt[5], st_ms[0], st_ms[1], st_ms[2], st_ms[3], st_ms[4], st_ms[5]);
     }
   }
   if (debug) {
@@ -1790,7 +1786,7 @@ int lgarb_set_stage_timing(lgarb_engine* e, int on) {
       cudaEventDestroy(se.b);
     }
     e->stage_evs.clear();
-    for (int s = 0; s <= LGAR_NSTAGE_TIMED; s++) {
+    for (int s = 0; s <= LGAR_NSTAGE; s++) {
       e->stage_ms[s] = 0.0;
       e->stage_launches[s] = 0;
     }
@@ -1812,7 +1808,7 @@ int lgarb_get_stage_times(lgarb_engine* e, double* ms7, int64_t* launches7) {
       cudaEventDestroy(se.b);
     }
     e->stage_evs.clear();
-    for (int s = 0; s <= LGAR_NSTAGE_TIMED; s++) {
+    for (int s = 0; s <= LGAR_NSTAGE; s++) {
       ms7[s] = e->stage_ms[s];
       launches7[s] = e->stage_launches[s];
     }

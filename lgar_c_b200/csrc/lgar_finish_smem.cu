@@ -105,7 +105,6 @@ __global__ void __launch_bounds__(32) lgar_wave_finish_smem_kernel(const __grid_
           break;
         }
         case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, fsp); break;
-        case LG_ST_GEFF: lg_stage_geff(cfg, L); break;  // a slot the rounds left waiting for its Geff values
         default:
           lg_corr_some(L.k, L.f, *L.cls, quantum, FF);
           if (L.k.done) L.stage = LG_ST_TAIL;

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(LGAR_WINDOW_THREADS) lgar_window_kernel(const 
 #endif
 constexpr int wave_min_blocks(int stage) {
   return stage == LG_ST_FETCH ? LGAR_MB_FETCH : stage == LG_ST_HEAD ? LGAR_MB_HEAD : stage == LG_ST_FRONT ? LGAR_MB_FRONT
-       : stage == LG_ST_SEARCH ? LGAR_MB_SEARCH : stage == LG_ST_TAIL ? LGAR_MB_TAIL : stage == LG_ST_GEFF ? 0 : LGAR_MB_CORR;
+       : stage == LG_ST_SEARCH ? LGAR_MB_SEARCH : stage == LG_ST_TAIL ? LGAR_MB_TAIL : LGAR_MB_CORR;
 }
 // FF: the SEARCH / CORR stages take the fast path of lgar_search.cuh (few slots in flight: a latency tool).  A template parameter,
 // not an argument: the plain instantiation must not carry the fast path's registers (occupancy of the bulk rounds).
@@ -214,27 +214,6 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         next = k.done ? LG_ST_TAIL : LG_ST_CORR;
         bin = k.done ? wave_bin_fronts(fb.f.n, wave_tail_flags(G)) : 0;
       }
-    } else if (STAGE == LG_ST_GEFF) {
-      if (valid) {  // theta, K, layer, to_bottom of the live fronts in; the Geff values of the pending lg_dzdt_calc out
-        LgLane& G = slots[slot].L;
-        struct alignas(32) FrontsBuf { LgFronts f; } fb;
-        char* l = reinterpret_cast<char*>(&fb);
-        char* g = reinterpret_cast<char*>(&G.f);
-        ctx_load<kFrontTailBytes>(reinterpret_cast<FrontsBuf*>(l + kFrontTail), reinterpret_cast<const FrontsBuf*>(g + kFrontTail));
-        const int cf = (fb.f.n + 3) >> 2;
-        ctx_load_n(l + kPitch * 1, g + kPitch * 1, cf);  // theta
-        ctx_load_n(l + kPitch * 3, g + kPitch * 3, cf);  // K
-        double ff[LGAR_MAXL + 2];
-#pragma unroll
-        for (int a = 0; a < LGAR_MAXL + 2; a++) ff[a] = G.ffv[a];
-        double geff[LGAR_GEFF_MAX];
-        const int ng = lg_geff_compute(cfg, *G.cls, fb.f, ff, geff, LGAR_GEFF_MAX);
-        for (int a = 0; a < ng; a++) G.geff[a] = geff[a];
-        G.geff_n = ng;
-        G.tail_phase = 2;
-        next = LG_ST_TAIL;
-        bin = wave_bin_fronts(fb.f.n, wave_tail_flags(G));
-      }
     } else if (STAGE == LG_ST_FETCH) {
       if (valid) {  // works on the record in place: scalars and epilogue state through registers, nothing else is touched
         LgLane& G = slots[slot].L;
@@ -267,14 +246,14 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
         if (STAGE == LG_ST_FRONT)
           lg_stage_front(L);
         else
-          lg_stage_tail(cfg, d, w, L, fsp, /*stage_geff=*/true);  // a no-op unless the configuration has the numeric Geff
+          lg_stage_tail(cfg, d, w, L, fsp);
       }
       next = L.stage;
       bin = next == LG_ST_SEARCH ? wave_bin_layers(L.q.layer_num) : (next == LG_ST_CORR || next == LG_ST_FETCH) ? 0 : wave_bin_fronts(L.f.n, next == LG_ST_TAIL ? wave_tail_flags(L) : 0);
       if (next == LG_ST_FETCH) {
         lane_store<LG_PART_STATE>(&slots[slot], &S);  // the step is over: only the column state lives on
-      } else if (STAGE == LG_ST_TAIL && (next == LG_ST_CORR || next == LG_ST_GEFF)) {
-        lane_store<LG_PART_STATE | LG_PART_STEP>(&slots[slot], &S);  // TAIL -> CORR / GEFF -> TAIL: neither state_previous nor the psi search is live
+      } else if (STAGE == LG_ST_TAIL && next == LG_ST_CORR) {
+        lane_store<LG_PART_STATE | LG_PART_STEP>(&slots[slot], &S);  // TAIL -> CORR -> TAIL: neither state_previous nor the psi search is live
       } else if (next == LG_ST_TAIL) {
         lane_store<LG_PART_STATE | LG_PART_STEP>(&slots[slot], &S);  // the front loop is over
       } else {
@@ -440,7 +419,6 @@ __global__ void __launch_bounds__(128, LGAR_MB_FINISH) lgar_wave_finish_kernel(c
           lg_corr_run(L.k, L.f, *L.cls, use_ff != 0);
           L.stage = LG_ST_TAIL;
           break;
-        case LG_ST_GEFF: lg_stage_geff(cfg, L); break;  // a slot the rounds left waiting for its Geff values
         default: L.stage = LG_ST_DONE; break;
       }
     }
@@ -544,7 +522,6 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
       if (w.use_ff) lgar_wave_kernel<LG_ST_CORR, true><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum);
       else lgar_wave_kernel<LG_ST_CORR><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum);
       break;
-    case LG_ST_GEFF: lgar_wave_kernel<LG_ST_GEFF><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
     default: lgar_wave_kernel<LG_ST_TAIL><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
   }
   lgar_wave_reset_kernel<<<1, 32, 0, stream>>>(wv.qcount + (stage * 2 + consume) * LGAR_NBIN, refill ? wv.cursor : nullptr);

@@ -52,10 +52,9 @@ struct LgarWindow {
 // Wavefront scheduler state (mode 3): contexts of in-flight column-steps parked in HBM and one
 // compacted queue pair per stage (see lgar_kernels.cu).
 struct LgLane;
-#define LGAR_NSTAGE 7
-// stages of the resumable column program (lgar_lanes.cuh); GEFF exists for configurations with the numeric Geff only
-enum { LG_ST_FETCH = 0, LG_ST_HEAD = 1, LG_ST_FRONT = 2, LG_ST_SEARCH = 3, LG_ST_TAIL = 4, LG_ST_CORR = 5, LG_ST_GEFF = 6, LG_ST_DONE = 7 };
-#define LGAR_NSTAGE_TIMED 6   // stages lgarb_get_stage_times reports (GEFF is booked under TAIL)
+#define LGAR_NSTAGE 6
+// stages of the resumable column program (lgar_lanes.cuh)
+enum { LG_ST_FETCH = 0, LG_ST_HEAD = 1, LG_ST_FRONT = 2, LG_ST_SEARCH = 3, LG_ST_TAIL = 4, LG_ST_CORR = 5, LG_ST_DONE = 6 };
 // Every queue is kept in LGAR_NBIN bins so that the lanes of a warp work on slots that look alike: HEAD / FRONT / TAIL slots are
 // binned by their front count (LGAR_NBIN_N levels: the per-front loops of those stages then have the same trip count across the
 // warp) and by flags (LGAR_NBIN_FLAG levels: HEAD -- it rains in the hour of the step; TAIL -- the step creates a surficial front,

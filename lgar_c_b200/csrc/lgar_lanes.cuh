@@ -57,9 +57,6 @@ struct LgLane {
   int me_phase, me_correction, fx_cur, fx_nx, fx_l;
   double fx_prior_mass, fx_mass_change;
   bool create, resume, fx_resume;
-  // GEFF stage (numeric Geff only): 0 nothing pending, 1 the step waits for the Geff values of lg_dzdt_calc, 2 they are in geff[]
-  int tail_phase, geff_n;
-  double geff[LGAR_GEFF_MAX];
   unsigned int tr_iters, tr_kcyc;  // work trace of the current column (debug)
   alignas(16) LgCorr k;   // TAIL/CORR stop copying after this
   alignas(32) LgOld old;  // FRONT only
@@ -584,17 +581,13 @@ LG_FN_NOINLINE void lg_cycle_begin(const LgarConfig& cfg, LgLane& L) {
 // From the end of the front loop to the end of the sub-cycle (bmi_lgar.cxx:553-805).  Returns 1 when the
 // forcing step is complete, 0 when another sub-cycle has been started, 2 when a correction search has
 // to iterate first (call again afterwards).
-// stage_geff: with the numeric Geff, leave before lg_dzdt_calc (return 3) so that its calc_Geff calls can be made by the GEFF stage;
-// the call after that stage resumes at lg_dzdt_calc.
-LG_FN_NOINLINE int lg_cycle_end(const LgarConfig& cfg, LgLane& L, bool stage_geff = false) {
+LG_FN_NOINLINE int lg_cycle_end(const LgarConfig& cfg, LgLane& L) {
   LgCtx& c = L.c;
   LgFronts& f = L.f;
   LgScalars& s = L.s;
   const LgarColumnClass& cls = *L.cls;
   const double dt = L.pro.subtimestep_h;
   LgCycle& cy = L.cy;
-  const bool resume_at_dzdt = L.tail_phase == 2;
-  if (!resume_at_dzdt) {
   if ((L.nwf != 0 || L.create) && L.me_phase != 3) {
     if (lg_move_end(L)) return 2;
     L.temp_rch = L.bottom_flux;
@@ -614,17 +607,9 @@ LG_FN_NOINLINE int lg_cycle_end(const LgarConfig& cfg, LgLane& L, bool stage_gef
   }
   if (!(c.status & LGAR_FAIL_MASK)) {
     lg_clean_redundant(c);
-    if (stage_geff && !cfg.use_closed_form_G && f.n > 1) {
-      L.tail_phase = 1;
-      return 3;
-    }
-  }
-  }  // !resume_at_dzdt
-  if (!(c.status & LGAR_FAIL_MASK)) {
     int new_front = (L.pro.switch_caching && L.create) ? 1 : -1;
-    lg_dzdt_calc(c, L.ponded, dt, L.pro.switch_caching, s.cache_count, new_front, resume_at_dzdt ? L.geff : nullptr, resume_at_dzdt ? L.geff_n : 0);
+    lg_dzdt_calc(c, L.ponded, dt, L.pro.switch_caching, s.cache_count, new_front);
   }
-  L.tail_phase = 0;
   if (L.pro.switch_caching) s.cache_count = 1;
   double volrech = L.temp_rch;
   if (!cfg.free_drainage_to_CR) {
@@ -699,7 +684,6 @@ LG_FN_NOINLINE void lg_stage_head(const LgarConfig& cfg, const LgarDeviceState& 
   L.c.paths = w.paths;
   L.c.use_ff = w.use_ff != 0;
   L.c.status = 0;
-  L.tail_phase = 0;
   L.volon_ts = L.s.volon;
   L.volend_sub = L.s.storage;
   L.last_AET = L.last_PET_sub = L.last_volrech = 0.0;
@@ -721,26 +705,14 @@ LG_FN void lg_stage_front(LgLane& L) {
 }
 
 // TAIL: ends in FRONT (next sub-cycle), CORR, or FETCH (step finished: GIUH, cumulative volumes, outputs)
-// GEFF: the calc_Geff calls of the lg_dzdt_calc the step is waiting at; ends in TAIL
-LG_FN void lg_stage_geff(const LgarConfig& cfg, LgLane& L) {
-  L.geff_n = lg_geff_compute(cfg, *L.cls, L.f, L.ffv, L.geff, LGAR_GEFF_MAX);
-  L.tail_phase = 2;
-  L.stage = LG_ST_TAIL;
-}
-
-LG_FN_NOINLINE void lg_stage_tail(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, LgLane& L, unsigned long long* front_sum,
-                                  bool stage_geff = false) {
-  const int r = lg_cycle_end(cfg, L, stage_geff);
+LG_FN_NOINLINE void lg_stage_tail(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWindow& w, LgLane& L, unsigned long long* front_sum) {
+  const int r = lg_cycle_end(cfg, L);
   if (r == 0) {
     L.stage = LG_ST_FRONT;
     return;
   }
   if (r == 2) {
     L.stage = LG_ST_CORR;
-    return;
-  }
-  if (r == 3) {
-    L.stage = LG_ST_GEFF;
     return;
   }
   const int64_t col = L.col;

@@ -994,15 +994,11 @@ LG_FN_NOINLINE void lg_create_surficial_front(LgCtx& c, double* ponded_depth_cm,
 }
 
 // lgar_dzdt_calc, lgar.cxx:2764-2945
-// geff_pre / n_pre: the values of the first n_pre calc_Geff calls of this walk, computed beforehand by the GEFF stage (lg_geff_compute
-// below meets the fronts in the same order); null: every call is made here.
-LG_FN_NOINLINE void lg_dzdt_calc(LgCtx& c, double h_p, double subtimestep_h, bool switch_caching, int cache_count, int new_front,
-                                 const double* geff_pre = nullptr, int n_pre = 0) {
+LG_FN_NOINLINE void lg_dzdt_calc(LgCtx& c, double h_p, double subtimestep_h, bool switch_caching, int cache_count, int new_front) {
   LgFronts& f = *c.f;
   const LgarColumnClass& cls = *c.cls;
   const double* cum = cls.cum;
   int count_correct_for_crossing = 0;
-  int geff_calls = 0;
   for (int i = 0; i < f.n; i++) {
     // Only the fronts that are not to-bottom (about one in four) need the Green-Ampt evaluation below.  The cheap
     // cases are skipped in this inner loop, so that the k-th trip of the outer loop is the k-th MOVING front of
@@ -1034,8 +1030,7 @@ LG_FN_NOINLINE void lg_dzdt_calc(LgCtx& c, double h_p, double subtimestep_h, boo
       return;
     }
     const double Ksat = sp.Ksat * c.ff[layer_num];  // lgar.cxx:2824
-    double Geff = (geff_pre && geff_calls < n_pre) ? geff_pre[geff_calls] : lg_Geff(*c.cfg, theta1, theta2, sp, Ksat);
-    geff_calls++;
+    double Geff = lg_Geff(*c.cfg, theta1, theta2, sp, Ksat);
     double delta_theta = f.theta[i] - f.theta[i + 1];
     if (layer_num == 1) {
       if (delta_theta > 0)
@@ -1069,28 +1064,6 @@ LG_FN_NOINLINE void lg_dzdt_calc(LgCtx& c, double h_p, double subtimestep_h, boo
     }
     f.dzdt[i] = dzdt;
   }
-}
-
-// The calc_Geff calls lg_dzdt_calc is about to make, in its order, made beforehand: the walk below is lg_dzdt_calc's own up to the
-// call (same skips, same two failure exits), without side effects.  Returns how many values were written (at most cap; the walk
-// may need more: lg_dzdt_calc makes the remaining calls itself).  With the numeric Geff (an adaptive trapezoid of ~10^2 trips, five
-// pow each: soil_funcs.cxx:69-114) these calls are most of the TAIL stage; as a stage of their own they run converged and out of
-// registers (lgar_wave_kernel<LG_ST_GEFF>).
-#define LGAR_GEFF_MAX 8
-LG_FN_NOINLINE int lg_geff_compute(const LgarConfig& cfg, const LgarColumnClass& cls, const LgFronts& f, const double* ff, double* geff, int cap) {
-  int n = 0;
-  for (int i = 0; i < f.n; i++) {
-    while (i + 1 < f.n && f.tb[i] && !(f.K[i] < 0)) i++;
-    if (f.K[i] < 0) break;
-    if (i + 1 >= f.n) break;
-    if (f.tb[i]) continue;
-    const double theta1 = f.theta[i + 1], theta2 = f.theta[i];
-    if (theta1 > theta2) break;
-    if (n >= cap) break;
-    const LgarLayer& sp = cls.lay[f.layer[i]];
-    geff[n++] = lg_Geff(cfg, theta1, theta2, sp, sp.Ksat * ff[f.layer[i]]);
-  }
-  return n;
 }
 
 // calc_aet, src/aet.cxx:17-77.  psi_50 (the reference's psi_wp_cm) is a class constant.

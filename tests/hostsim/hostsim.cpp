@@ -108,8 +108,7 @@ extern "C" int hostsim_run_series(const char* cfg_path, const int* types_in, con
             case LG_ST_SEARCH:
               lg_search_run(L.q, *L.cls, hostsim_use_ff != 0);
               L.resume = true; L.stage = LG_ST_FRONT; break;
-            case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, nullptr, /*stage_geff=*/true); break;
-            case LG_ST_GEFF: lg_stage_geff(cfg, L); break;
+            case LG_ST_TAIL: lg_stage_tail(cfg, d, w, L, nullptr); break;
             case LG_ST_CORR:
               lg_corr_run(L.k, L.f, *L.cls, hostsim_use_ff != 0);
               L.stage = LG_ST_TAIL; break;
