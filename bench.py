@@ -425,7 +425,7 @@ def parity_block(cfgobj, ids, T, chunk, dev_index, cores, mode, what):
     sys.path.insert(0, str(ROOT / "tools"))
     import parity_sampling_full as pf
     pos = np.arange(len(ids))
-    hP, hE, scal, nf, status, final, info = pf.run_engine(cfgobj, ids, pos, T, chunk, mode)
+    hP, hE, scal, nf, status, final, info = pf.run_engine(cfgobj, ids, pos, T, chunk, mode, dev_index)
     r = pf.diff_against_oracle(cfgobj, ids, hP, hE, scal, nf, status, final, cores)
     worst = max(v["worst_rel"] for v in r["scalars"].values())
     return {"what": what, "columns": int(len(ids)), "steps_per_column": int(T), "column_steps_diffed": r["column_steps_diffed"],

@@ -131,11 +131,28 @@ struct alignas(32) LgLaneSlot {
 // Parts of the lane record (lgar_lanes.cuh) a stage moves between HBM and its thread-private copy.  The front
 // arrays have capacity LGAR_W = 32 but a column carries 4-5 fronts on average: only the live prefix of each
 // array travels (counts kept in the record's first sector), which removes about a third of the context traffic.
-enum { LG_PART_STATE = 1, LG_PART_STEP = 2, LG_PART_OLD = 4, LG_PART_SEARCH = 8, LG_PART_ALL = 15 };
-constexpr int kOffF = (int)offsetof(LgLane, f), kOffPro = (int)offsetof(LgLane, pro), kOffOld = (int)offsetof(LgLane, old),
-              kOffQ = (int)offsetof(LgLane, q);
+// Every stage moves only what it reads or writes: HEAD leaves the epilogue state (GIUH queue, cumulative volumes) where it is,
+// FRONT moves the fronts, 128 bytes of step context, state_previous (in only) and the search record -- not the scalars, not the
+// rest of the step context.
+enum {
+  LG_PART_CTX = 1,       // LgCtx (status word; the pointers are set by every stage)
+  LG_PART_S = 2,         // scalars, frozen factors
+  LG_PART_EP = 4,        // epilogue state
+  LG_PART_FRONTS = 8,
+  LG_PART_STEPF = 16,    // the front loop's part of the step context
+  LG_PART_STEPR = 32,    // the rest of it, up to and including the correction record
+  LG_PART_OLD = 64,
+  LG_PART_SEARCH = 128,
+  LG_PART_STATE = LG_PART_CTX | LG_PART_S | LG_PART_EP | LG_PART_FRONTS,
+  LG_PART_STEP = LG_PART_STEPF | LG_PART_STEPR,
+  LG_PART_ALL = 255
+};
+constexpr int kOffC = (int)offsetof(LgLane, c), kOffS = (int)offsetof(LgLane, s), kOffEp = (int)offsetof(LgLane, ep), kOffF = (int)offsetof(LgLane, f),
+              kOffPro = (int)offsetof(LgLane, pro), kOffStepR = (int)offsetof(LgLane, P), kOffOld = (int)offsetof(LgLane, old), kOffQ = (int)offsetof(LgLane, q);
 constexpr int kFrontTail = (int)offsetof(LgFronts, layer);  // layer[], tb[], n behind the five double arrays
-static_assert(kOffF % 32 == 0 && kOffPro % 32 == 0 && kOffOld % 32 == 0 && kOffQ % 32 == 0 && sizeof(LgLaneSlot) % 32 == 0, "LgLane layout");
+static_assert(kOffC == 32 && kOffS % 32 == 0 && kOffEp % 32 == 0 && kOffF % 32 == 0 && kOffPro % 32 == 0 && kOffStepR == kOffPro + 128 && kOffOld % 32 == 0 &&
+                  kOffQ % 32 == 0 && sizeof(LgLaneSlot) % 32 == 0,
+              "LgLane layout");
 constexpr int kPitch = 8 * LGAR_W;                           // bytes between the arrays of LgFronts / LgOld
 constexpr int kFrontTailBytes = kOffPro - kOffF - kFrontTail;  // layer[], tb[], n (+ padding up to `pro`)
 static_assert(offsetof(LgFronts, depth) == 0 && offsetof(LgFronts, theta) == kPitch && offsetof(LgFronts, psi) == 2 * kPitch &&
@@ -146,53 +163,62 @@ static_assert(offsetof(LgOld, theta) == kPitch && offsetof(LgOld, psi) == 2 * kP
               "LgOld layout");
 static_assert(offsetof(LgLane, nold_stored) < 32, "front counts must sit in the first sector of the record");
 
+#define LG_CTX_RANGE(fn, from, to) fn<(to) - (from)>(reinterpret_cast<LgLaneSlot*>(l + (from)), reinterpret_cast<const LgLaneSlot*>(g + (from)))
+
 template <int PARTS>
 __device__ __forceinline__ void lane_load(LgLaneSlot* S, const LgLaneSlot* G) {
   char* l = reinterpret_cast<char*>(S);
   const char* g = reinterpret_cast<const char*>(G);
   ctx_load<32>(S, G);  // first sector: stage, hour, column, class, front counts
   const int cf = (S->L.nf_stored + 3) >> 2, co = (S->L.nold_stored + 3) >> 2;
-  if (PARTS & LG_PART_STATE) {
-    ctx_load<kOffF - 32>(reinterpret_cast<LgLaneSlot*>(l + 32), reinterpret_cast<const LgLaneSlot*>(g + 32));
+  if (PARTS & LG_PART_CTX) LG_CTX_RANGE(ctx_load, kOffC, kOffS);
+  if (PARTS & LG_PART_S) LG_CTX_RANGE(ctx_load, kOffS, kOffEp);
+  if (PARTS & LG_PART_EP) LG_CTX_RANGE(ctx_load, kOffEp, kOffF);
+  if (PARTS & LG_PART_FRONTS) {
 #pragma unroll
     for (int a = 0; a < 5; a++) ctx_load_n(l + kOffF + kPitch * a, g + kOffF + kPitch * a, cf);
-    ctx_load<kFrontTailBytes>(reinterpret_cast<LgLaneSlot*>(l + kOffF + kFrontTail), reinterpret_cast<const LgLaneSlot*>(g + kOffF + kFrontTail));
+    LG_CTX_RANGE(ctx_load, kOffF + kFrontTail, kOffPro);
   }
-  if (PARTS & LG_PART_STEP) ctx_load<kOffOld - kOffPro>(reinterpret_cast<LgLaneSlot*>(l + kOffPro), reinterpret_cast<const LgLaneSlot*>(g + kOffPro));
+  if (PARTS & LG_PART_STEPF) LG_CTX_RANGE(ctx_load, kOffPro, kOffStepR);
+  if (PARTS & LG_PART_STEPR) LG_CTX_RANGE(ctx_load, kOffStepR, kOffOld);
   if (PARTS & LG_PART_OLD) {
 #pragma unroll
     for (int a = 0; a < 3; a++) ctx_load_n(l + kOffOld + kPitch * a, g + kOffOld + kPitch * a, co);
-    ctx_load<32>(reinterpret_cast<LgLaneSlot*>(l + kOffOld + 3 * kPitch), reinterpret_cast<const LgLaneSlot*>(g + kOffOld + 3 * kPitch));
+    LG_CTX_RANGE(ctx_load, kOffOld + 3 * kPitch, kOffQ);
   }
-  if (PARTS & LG_PART_SEARCH)
-    ctx_load<(int)sizeof(LgLaneSlot) - kOffQ>(reinterpret_cast<LgLaneSlot*>(l + kOffQ), reinterpret_cast<const LgLaneSlot*>(g + kOffQ));
+  if (PARTS & LG_PART_SEARCH) LG_CTX_RANGE(ctx_load, kOffQ, (int)sizeof(LgLaneSlot));
 #ifdef LGAR_POISON  // validation build: whatever was not moved must never be read
-  if (PARTS & LG_PART_STATE)
+  if (PARTS & LG_PART_FRONTS)
     for (int i = 4 * cf; i < LGAR_W; i++) S->L.f.depth[i] = S->L.f.theta[i] = S->L.f.psi[i] = S->L.f.K[i] = S->L.f.dzdt[i] = LG_NAN;
   if (PARTS & LG_PART_OLD)
     for (int i = 4 * co; i < LGAR_W; i++) S->L.old.depth[i] = S->L.old.theta[i] = S->L.old.psi[i] = LG_NAN;
 #endif
 }
+#undef LG_CTX_RANGE
+#define LG_CTX_RANGE(fn, from, to) fn<(to) - (from)>(reinterpret_cast<LgLaneSlot*>(g + (from)), reinterpret_cast<const LgLaneSlot*>(l + (from)))
 template <int PARTS>
 __device__ __forceinline__ void lane_store(LgLaneSlot* G, LgLaneSlot* S) {
   const char* l = reinterpret_cast<const char*>(S);
   char* g = reinterpret_cast<char*>(G);
-  if (PARTS & LG_PART_STATE) S->L.nf_stored = S->L.f.n;
+  if (PARTS & LG_PART_FRONTS) S->L.nf_stored = S->L.f.n;
   if (PARTS & LG_PART_OLD) S->L.nold_stored = S->L.old.n;
   const int cf = (S->L.nf_stored + 3) >> 2, co = (S->L.nold_stored + 3) >> 2;
   ctx_store<32>(G, S);
-  if (PARTS & LG_PART_STATE) {
-    ctx_store<kOffF - 32>(reinterpret_cast<LgLaneSlot*>(g + 32), reinterpret_cast<const LgLaneSlot*>(l + 32));
+  if (PARTS & LG_PART_CTX) LG_CTX_RANGE(ctx_store, kOffC, kOffS);
+  if (PARTS & LG_PART_S) LG_CTX_RANGE(ctx_store, kOffS, kOffEp);
+  if (PARTS & LG_PART_EP) LG_CTX_RANGE(ctx_store, kOffEp, kOffF);
+  if (PARTS & LG_PART_FRONTS) {
 #pragma unroll
     for (int a = 0; a < 5; a++) ctx_store_n(g + kOffF + kPitch * a, l + kOffF + kPitch * a, cf);
-    ctx_store<kFrontTailBytes>(reinterpret_cast<LgLaneSlot*>(g + kOffF + kFrontTail), reinterpret_cast<const LgLaneSlot*>(l + kOffF + kFrontTail));
+    LG_CTX_RANGE(ctx_store, kOffF + kFrontTail, kOffPro);
   }
-  if (PARTS & LG_PART_STEP) ctx_store<kOffOld - kOffPro>(reinterpret_cast<LgLaneSlot*>(g + kOffPro), reinterpret_cast<const LgLaneSlot*>(l + kOffPro));
+  if (PARTS & LG_PART_STEPF) LG_CTX_RANGE(ctx_store, kOffPro, kOffStepR);
+  if (PARTS & LG_PART_STEPR) LG_CTX_RANGE(ctx_store, kOffStepR, kOffOld);
   if (PARTS & LG_PART_OLD) {
 #pragma unroll
     for (int a = 0; a < 3; a++) ctx_store_n(g + kOffOld + kPitch * a, l + kOffOld + kPitch * a, co);
-    ctx_store<32>(reinterpret_cast<LgLaneSlot*>(g + kOffOld + 3 * kPitch), reinterpret_cast<const LgLaneSlot*>(l + kOffOld + 3 * kPitch));
+    LG_CTX_RANGE(ctx_store, kOffOld + 3 * kPitch, kOffQ);
   }
-  if (PARTS & LG_PART_SEARCH)
-    ctx_store<(int)sizeof(LgLaneSlot) - kOffQ>(reinterpret_cast<LgLaneSlot*>(g + kOffQ), reinterpret_cast<const LgLaneSlot*>(l + kOffQ));
+  if (PARTS & LG_PART_SEARCH) LG_CTX_RANGE(ctx_store, kOffQ, (int)sizeof(LgLaneSlot));
 }
+#undef LG_CTX_RANGE

@@ -224,19 +224,27 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
     } else if (valid) {
       LgLaneSlot S;
       LgLane& L = S.L;
+      // What each stage moves (parts of the record: lgar_ctx.cuh).  HEAD: status word, scalars, fronts in (the epilogue state stays
+      // where it is unless the test mode that can finish a step here is on); everything it has built out.  FRONT: status word,
+      // fronts, the 128 bytes of step context the front loop works on, state_previous (in only), the search record.  TAIL:
+      // the whole state and step context in; the state out when the step is over, state + step context when it goes on.
+      constexpr int kHeadIn = LG_PART_CTX | LG_PART_S | LG_PART_FRONTS;
+      constexpr int kFrontIO = LG_PART_CTX | LG_PART_FRONTS | LG_PART_STEPF;
+      constexpr int kGoOn = LG_PART_CTX | LG_PART_S | LG_PART_FRONTS | LG_PART_STEP;
       if (STAGE == LG_ST_HEAD) {  // HEAD starts the step context behind the resident column state
-        lane_load<LG_PART_STATE>(&S, &slots[slot]);
+        if (w.force_all_active)
+          lane_load<LG_PART_STATE>(&S, &slots[slot]);
+        else
+          lane_load<kHeadIn>(&S, &slots[slot]);
         lg_stage_head(cfg, d, w, L, fsp);
         active_sum += (L.stage == LG_ST_FRONT) ? 1 : 0;
         // every new step goes straight into its front loop: saves one context round trip per step
         if (L.stage == LG_ST_FRONT) lg_stage_front(L);
       } else {
-        // TAIL works on everything up to and including the correction record; FRONT needs state_previous
-        // and the search record as well
         if (STAGE == LG_ST_TAIL)
           lane_load<LG_PART_STATE | LG_PART_STEP>(&S, &slots[slot]);
         else
-          lane_load<LG_PART_ALL>(&S, &slots[slot]);
+          lane_load<kFrontIO | LG_PART_OLD | LG_PART_SEARCH>(&S, &slots[slot]);
         L.c.cfg = &cfg;
         L.c.cls = L.cls;
         L.c.f = &L.f;
@@ -250,14 +258,19 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
       }
       next = L.stage;
       bin = next == LG_ST_SEARCH ? wave_bin_layers(L.q.layer_num) : (next == LG_ST_CORR || next == LG_ST_FETCH) ? 0 : wave_bin_fronts(L.f.n, next == LG_ST_TAIL ? wave_tail_flags(L) : 0);
-      if (next == LG_ST_FETCH) {
+      if (STAGE == LG_ST_FRONT) {
+        if (next == LG_ST_SEARCH)
+          lane_store<kFrontIO | LG_PART_SEARCH>(&slots[slot], &S);
+        else
+          lane_store<kFrontIO>(&slots[slot], &S);  // the front loop is over
+      } else if (next == LG_ST_FETCH) {
         lane_store<LG_PART_STATE>(&slots[slot], &S);  // the step is over: only the column state lives on
-      } else if (STAGE == LG_ST_TAIL && next == LG_ST_CORR) {
-        lane_store<LG_PART_STATE | LG_PART_STEP>(&slots[slot], &S);  // TAIL -> CORR -> TAIL: neither state_previous nor the psi search is live
-      } else if (next == LG_ST_TAIL) {
-        lane_store<LG_PART_STATE | LG_PART_STEP>(&slots[slot], &S);  // the front loop is over
+      } else if (next == LG_ST_TAIL || next == LG_ST_CORR) {
+        lane_store<kGoOn>(&slots[slot], &S);  // HEAD -> TAIL (no search), TAIL -> CORR -> TAIL: neither state_previous nor the psi search is live
+      } else if (next == LG_ST_FRONT) {
+        lane_store<kGoOn | LG_PART_OLD>(&slots[slot], &S);  // TAIL has begun the next sub-cycle
       } else {
-        lane_store<LG_PART_ALL>(&slots[slot], &S);
+        lane_store<kGoOn | LG_PART_OLD | LG_PART_SEARCH>(&slots[slot], &S);  // HEAD -> SEARCH
       }
     }
     wave_push(wv, append_mask, valid ? next : -1, bin, slot);

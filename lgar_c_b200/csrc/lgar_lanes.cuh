@@ -38,25 +38,29 @@ struct LgLane {
   const LgarColumnClass* cls;
   int nf_stored, nold_stored;  // front counts the record was last stored with: only that prefix of the arrays is moved
   LgCtx c;
-  alignas(16) LgScalars s;
+  alignas(32) LgScalars s;
   double ffv[LGAR_MAXL + 2];  // frozen_factor per layer (1-based) of this column for the window: all 1.0 unless the run is SFT-coupled
-  LgEpi ep;
+  alignas(32) LgEpi ep;
   alignas(32) LgFronts f;
   // ---- step context (locals of lg_step_active) ----
+  // first the 128 bytes the front loop works on (FRONT moves these and nothing else of the step context, lgar_ctx.cuh)
   alignas(32) LgPrologue pro;
-  double P, E;
+  int wf, nwf, wf_fd_demand, search_case;   // front-loop context (locals of lg_move_wetting_fronts)
+  int me_phase, me_correction;              // resumable lgar_move_wetting_fronts epilogue (the correction type is found at the end of the front loop)
+  bool create, resume;
+  double precip_mass_to_add, bottom_flux, actual_ET_demand, AET, free_drainage, mass_corr_fd, volend_sub;
+  // then the rest
+  alignas(32) double P;
+  double E;
   LgStepVols v;
   LgCycle cy;
   int cycle, wf_fd;
-  double PET_rate, ponded, volon_ts, volend_sub, AET, free_drainage, mass_corr_fd, temp_rch;
+  double PET_rate, ponded, volon_ts, temp_rch;
   double volin, runoff, volon_sub, last_AET, last_PET_sub, last_volrech;
-  // front-loop context (locals of lg_move_wetting_fronts)
-  int wf, nwf, wf_fd_demand, search_case;
-  double precip_mass_to_add, bottom_flux, actual_ET_demand;
-  // resumable lgar_move_wetting_fronts epilogue: correction loop + lgar_fix_dry_over_wet_wetting_fronts
-  int me_phase, me_correction, fx_cur, fx_nx, fx_l;
+  // lgar_fix_dry_over_wet_wetting_fronts, resumable around its correction search
+  int fx_cur, fx_nx, fx_l;
   double fx_prior_mass, fx_mass_change;
-  bool create, resume, fx_resume;
+  bool fx_resume;
   unsigned int tr_iters, tr_kcyc;  // work trace of the current column (debug)
   alignas(16) LgCorr k;   // TAIL/CORR stop copying after this
   alignas(32) LgOld old;  // FRONT only

@@ -251,28 +251,29 @@ def diff_against_oracle(cfgobj, sample, hP, hE, scal, nf, status, final, cores):
 
 
 # --------------------------------------------------------------------------------------------------
-def run_engine(cfgobj: Config, ids: np.ndarray, pos: np.ndarray, T: int, chunk: int, mode: int):
+def run_engine(cfgobj: Config, ids: np.ndarray, pos: np.ndarray, T: int, chunk: int, mode: int, device: int = 0):
     """The engine on the batch `ids`; returns forcing, 12 scalars and front counts of the sampled positions `pos`
     for every step, status and final fronts of the sample, and device seconds."""
     import torch
     import lgar_c_b200
     nb, ns = len(ids), len(pos)
     b = lgar_c_b200.BmiLGARBatch()
-    b.initialize(cfgobj.cfg, nb, 0, cfgobj.soils(ids), cfgobj.layers(ids))
+    dev = torch.device("cuda", device)
+    b.initialize(cfgobj.cfg, nb, device, cfgobj.soils(ids), cfgobj.layers(ids))
     b.set_window_mode(mode)
-    ext = torch.cuda.ExternalStream(b.get_stream())
-    dpos = torch.from_numpy(pos).cuda()
-    sinks = torch.zeros((12, chunk, nb), dtype=torch.float64, device="cuda")
-    nfs = torch.zeros((chunk, nb), dtype=torch.int32, device="cuda")
+    ext = torch.cuda.ExternalStream(b.get_stream(), device=dev)
+    dpos = torch.from_numpy(pos).to(dev)
+    sinks = torch.zeros((12, chunk, nb), dtype=torch.float64, device=dev)
+    nfs = torch.zeros((chunk, nb), dtype=torch.int32, device=dev)
     hP, hE = np.empty((T, ns)), np.empty((T, ns))
     scal = np.empty((T, 12, ns))
     nf = np.empty((T, ns), dtype=np.int32)
     dev_ms = 0.0
-    dids = torch.from_numpy(ids).cuda()
+    dids = torch.from_numpy(ids).to(dev)
     for t0 in range(0, T, chunk):
         nt = min(chunk, T - t0)
         dP, dE = cfgobj.forcing(dids, t0, nt)
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext)
         b.update_steps_device(nt, dP.data_ptr(), dE.data_ptr(), nb, {n: sinks[k].data_ptr() for k, n in enumerate(lgar_c_b200.OUTPUT_SCALARS)},
