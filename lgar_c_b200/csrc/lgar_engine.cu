@@ -122,7 +122,7 @@ struct lgarb_engine {
   int64_t frontier_waits = 0;  // times the scheduler had to wait for forcing
   int wave_finish_below = 16384;
   // Rounds with at most this many slots in flight run their psi searches through the fast path (lgar_search.cuh).  0: never --
-  // measured (profiles/r2_call5_summary.md): a round lasts as long as its longest search, and the fast path runs every search
+  // measured (profiles/r2_call5_call6_summary.md): a round lasts as long as its longest search, and the fast path runs every search
   // to its end inside one launch where the plain walk parks a 10^4-trip search after `quantum` trips: 4.09e8 with 65 536 against
   // 4.74e8 with 0.
   int wave_ff_below = 0;
@@ -136,7 +136,7 @@ struct lgarb_engine {
   int finish_lane_stride = 4;  // finishing kernel: one slot per this many lanes
   int sm_count = 0;            // multiprocessors of the device: grids are sized in multiples of it
   // lgarb_update: batches of at least this many columns hand their active columns to the stage kernels (measured on 1.25 M columns,
-  // profiles/r2_call11_summary.md: 23.0 ms per hour with the stream/active kernel pair, 9.8 ms this way)
+  // profiles/r2_call10_15_summary.md: 23.0 ms per hour with the stream/active kernel pair, 9.8 ms this way)
   int update_wave_min_cols = 100000;
   int update_wave_slots = 262144;      // ... through this many slots
   int update_wave_finish_below = 40000;  // ... with the finishing kernel taking over below this many slots in flight

@@ -9,7 +9,7 @@
 // goes; a lane whose column has finished the window takes the next slot from the cursor.  No context traffic at stage
 // boundaries, every access of the serial chain at shared-memory latency.
 //
-// Measured (profiles/r2_call6_summary.md, 1.25 M columns): a call of 480 h 4.79e8 -> 4.90e8 column-timesteps/s with 32 records
+// Measured (profiles/r2_call5_call6_summary.md, 1.25 M columns): a call of 480 h 4.79e8 -> 4.90e8 column-timesteps/s with 32 records
 // per warp, 5.00e8 with 16; a call of 1 460 h 5.29e8 -> 5.48e8.  The same kernel fed EARLY with the busiest columns, beside the
 // rounds (an "express lane": slots that advance fewer than two hours per round leave the rounds from round 24 on), was measured
 // too and removed: 3.3e8 -- its shared memory takes the L1 away from the stage kernels, whose bulk rounds went from 13.4 to 22 ms
