@@ -46,7 +46,7 @@ PH_LAYERS = (44.0, 131.0, 25.0)   # data/configs/config_lasam_Phillipsburg.txt
 BU_LAYERS = (18.0, 76.0, 135.0)   # data/configs/config_lasam_Bushland.txt
 N_GIUH = 5
 # Measured DRAM traffic and stage shares come from a committed ncu capture (profiles/r2_window_profile.json), keyed to the sha256
-# of the liblgarb.so it was taken with: a line printed by another build says so instead of repeating stale numbers.
+# of the sources of the liblgarb.so it was taken with: a line printed by other sources says so instead of repeating stale numbers.
 WINDOW_PROFILE = ROOT / "profiles" / "r2_window_profile.json"
 
 
@@ -396,14 +396,28 @@ def lib_sha256() -> str:
     return hashlib.sha256(Path(library_path()).read_bytes()).hexdigest()
 
 
+def kernel_source_sha256() -> str:
+    """sha256 over the sources liblgarb.so is built from (two builds of the same sources differ in their bytes: nvcc's fatbin ids),
+    the key of the committed ncu capture"""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = ROOT / "lgar_c_b200" / "csrc"
+    for f in sorted(list(csrc.glob("*.cu")) + list(csrc.glob("*.cuh")) + list(csrc.glob("*.h")) + list(csrc.glob("*.hpp")) + [csrc / "Makefile"]):
+        if f.name in ("lgar_group.cu", "lasam_b200_standalone.cpp"):
+            continue
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()
+
+
 def committed_window_profile():
     """(traffic bytes per column-timestep, stage time shares, source) of the committed ncu capture if it belongs to this build"""
     try:
         p = json.loads(WINDOW_PROFILE.read_text())
     except Exception:
         return None, None, "no committed capture (profiles/r2_window_profile.json)"
-    if p.get("lib_sha256") != lib_sha256():
-        return None, None, f"the committed capture ({WINDOW_PROFILE.name}) was taken with another build of liblgarb.so"
+    if p.get("source_sha256") != kernel_source_sha256():
+        return None, None, f"the committed capture ({WINDOW_PROFILE.name}) was taken with other sources of liblgarb.so"
     return p.get("dram_bytes_per_column_timestep"), p.get("stage_time_share"), f"{WINDOW_PROFILE.name}: {p.get('source', '')}"
 
 

@@ -11,6 +11,7 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
 src, ncol, hours = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 lib = Path(sys.argv[4]) if len(sys.argv) > 4 else ROOT / "lgar_c_b200" / "liblgarb.so"
 lines = [l for l in open(src) if not l.startswith("==")]
@@ -34,6 +35,7 @@ B = sum(a[2] + a[3] for a in by.values())
 units = ncol * hours
 print(json.dumps({
     "lib_sha256": hashlib.sha256(lib.read_bytes()).hexdigest(),
+    "source_sha256": __import__("bench").kernel_source_sha256(),
     "source": f"ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over every launch of one timed window "
               f"({ncol} columns x {hours} h; tools/prof_window.sh; launch list profiles/r2_window_launches.csv)",
     "columns": ncol, "hours": hours, "launches": sum(a[0] for a in by.values()), "window_ms_under_ncu": T * 1e3,
