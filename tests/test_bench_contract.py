@@ -57,3 +57,17 @@ def test_parity_sampling_tool_selftest(tmp_path):
         assert c["column_steps_diffed"] == 450 and c["front_count_mismatch_columns"] == 0 and c["failure_mismatch_columns"] == 0
         assert c["final_front_flag_mismatch_columns"] == 0 and c["final_front_field_mismatch_columns"] == 0
         assert all(v["columns_outside_bar"] == 0 for v in c["scalars"].values())
+
+
+def test_committed_ncu_capture_belongs_to_the_sources():
+    """bench.py prints the measured DRAM traffic of profiles/r2_window_profile.json only when the capture was taken with the
+    sources liblgarb.so is built from (kernel_source_sha256): a kernel change without a new capture must show as `traffic: null`,
+    never as stale numbers.  Here: the committed capture is the one of the committed sources, and it carries what the line needs."""
+    import bench
+    p = json.loads((ROOT / "profiles" / "r2_window_profile.json").read_text())
+    for key in ("source_sha256", "dram_bytes_per_column_timestep", "stage_time_share", "launches", "columns", "hours"):
+        assert key in p, key
+    assert abs(sum(p["stage_time_share"].values()) - 1.0) < 1e-9
+    traffic, share, source = bench.committed_window_profile()
+    assert p["source_sha256"] == bench.kernel_source_sha256(), "kernel sources changed after the ncu capture: re-capture (tools/prof_window.sh, tools/make_window_profile.py)"
+    assert traffic == p["dram_bytes_per_column_timestep"] and share and "r2_window_profile.json" in source
