@@ -62,6 +62,23 @@ __device__ __forceinline__ int wave_item(const LgarWave& wv, const WaveItems& it
   const int j = i - it.voff[b];
   return j < it.cnt[b] ? wv.queue[stage][buf][(size_t)b * wv.nslots + j] : -1;
 }
+// End of a consumer of queue (stage, consume): the last of its blocks to get here clears the counts of that queue (and the FETCH
+// cursor), so that the queue is empty when its turn to be appended to comes -- round 1 launched a one-thread kernel per stage launch
+// for this (half of all launches).  Every thread of the block must call it.  Nobody reads those counts any more: every block read
+// them when it started, and it is the last block that clears them.
+__device__ __forceinline__ void wave_consumed(const LgarWave& wv, int stage, int consume, bool reset_cursor) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(wv.done_blocks + stage, 1) + 1 == (int)gridDim.x) {
+      for (int b = 0; b < LGAR_NBIN; b++) wv.qcount[(stage * 2 + consume) * LGAR_NBIN + b] = 0;
+      if (reset_cursor) *wv.cursor = 0;
+      wv.done_blocks[stage] = 0;
+      __threadfence();
+    }
+  }
+}
+
 // item j of the concatenation of every bin of every queue (the finishing kernels): slot and the stage it is parked in
 __device__ __forceinline__ int wave_item_any(const LgarWave& wv, int j, int* stage) {
   for (int q = 0; q < 2 * LGAR_NSTAGE * LGAR_NBIN; q++) {

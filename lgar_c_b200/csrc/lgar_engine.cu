@@ -978,6 +978,7 @@ void ensure_wave(lgarb_engine* e) {
     wv.done_columns = e->dalloc<int32_t>(1);
     wv.cursor = e->dalloc<int32_t>(1);
     wv.waiting = e->dalloc<int32_t>(1);
+    wv.done_blocks = e->dalloc<int32_t>(LGAR_NSTAGE);
     if (!e->side_stream) {
       CUDA_TRY(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
       for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->side_ev[i], cudaEventDisableTiming));
@@ -1074,7 +1075,7 @@ void run_wave_window(lgarb_engine* e, LgarWindow w, int use_slots) {
       CUDA_TRY(cudaEventRecord(se.b, launch_stream));
       e->stage_evs.push_back(se);
     }
-    e->launches += 2;
+    e->launches += 1;
   };
   int32_t* h_cnt = (int32_t*)e->pinned(64 * sizeof(int32_t));
   const bool debug = getenv("LGARB_WAVE_DEBUG") != nullptr;

@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(128, wave_min_blocks(STAGE)) lgar_wave_kernel(
     if (front_sum) atomicAdd(w.prof, front_sum);
     if (active_sum) atomicAdd(w.prof + 1, active_sum);
   }
+  wave_consumed(wv, STAGE, consume, false);
 }
 
 // ---- FETCH with per-lane refill -------------------------------------------------------------------------
@@ -377,6 +378,7 @@ __global__ void __launch_bounds__(128) lgar_wave_fetch_kernel(const __grid_const
     wave_push(wv, append_mask, (next == LG_ST_HEAD || next == LG_ST_FETCH) ? next : -1, next == LG_ST_HEAD ? wave_bin_fronts(nf, rain ? 1 : 0) : 0, slot);
   }
   if (w.prof && front_sum) atomicAdd(w.prof, front_sum);
+  wave_consumed(wv, LG_ST_FETCH, consume, true);
 }
 
 // Finishing kernel: when only a few slots are left in flight (the columns that are active in almost every
@@ -500,12 +502,6 @@ __global__ void lgar_wave_init_kernel(const __grid_constant__ LgarConfig cfg, co
   }
 }
 
-// reset the consumed queue's count (and the FETCH cursor) after its kernel ran
-__global__ void lgar_wave_reset_kernel(int32_t* count, int32_t* cursor) {
-  for (int i = threadIdx.x; i < LGAR_NBIN; i += blockDim.x) count[i] = 0;  // every bin of the consumed queue
-  if (cursor && threadIdx.x == 0) *cursor = 0;
-}
-
 cudaError_t lgar_launch_wave_init(const LgarConfig& cfg, const LgarDeviceState& d, const LgarWave& wv, int slot_is_column, cudaStream_t stream) {
   lgar_wave_init_kernel<<<(wv.nslots + 255) / 256, 256, 0, stream>>>(cfg, d, wv, slot_is_column);
   return cudaGetLastError();
@@ -537,8 +533,7 @@ cudaError_t lgar_launch_wave_stage(const LgarConfig& cfg, const LgarDeviceState&
       break;
     default: lgar_wave_kernel<LG_ST_TAIL><<<blocks, 128, sm, stream>>>(cfg, d, w, wv, consume, append_mask, quantum); break;
   }
-  lgar_wave_reset_kernel<<<1, 32, 0, stream>>>(wv.qcount + (stage * 2 + consume) * LGAR_NBIN, refill ? wv.cursor : nullptr);
-  return cudaGetLastError();
+  return cudaGetLastError();  // the consumed queue is cleared by the last block of the kernel itself (wave_consumed)
 }
 
 size_t lgar_lane_context_bytes() { return sizeof(LgLaneSlot); }

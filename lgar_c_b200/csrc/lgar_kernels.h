@@ -77,6 +77,7 @@ struct LgarWave {
   int32_t* done_columns;       // columns that finished their window
   int32_t* cursor;             // FETCH kernel: next queue entry to hand out (zero between launches)
   int32_t* waiting;            // slots FETCH left waiting for forcing since the last poll (the poll reads and clears it)
+  int32_t* done_blocks;        // [LGAR_NSTAGE] blocks of the running consumer of a stage that have finished: the last one clears the consumed queue
 };
 
 #ifndef LGAR_HOSTSIM
